@@ -1,0 +1,441 @@
+"""CPU oracle for the VAE training step (forward + loss + backward).
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``mmvae_b200/`` may import this file.
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
+``--impl reference`` legs use it, and only as the checker / the thing timed on
+the host cores -- never as the product path.
+
+What it restates (reference = /root/reference, praateekmahajan/moving-mnist-vae):
+
+  * ``VAE_Encoder``  model.py:88-150   (stem conv k5 s2 p2 + BN + ReLU, four
+    ``BasicBlock`` model.py:23-55 with a 1x1/BN shortcut, avg-pool, 1x1 heads)
+  * ``rsample``      model.py:148-150  (mu + eps * exp(0.5 * logvar))
+  * ``VAE_Decoder``  model.py:153-209  (convT k2 stem + BN + ReLU, four or five
+    ``DeconvBottleneck`` model.py:57-85, conv 3x3 + bias + BN tail)
+  * ``VAE.forward``  model.py:316-342  (crop by ``adjust`` model.py:307-310)
+  * ``VAE.loss``     model.py:385-406  (Gaussian NLL model.py:403 or weighted
+    cross-entropy model.py:399-401, KL model.py:364-365, /N model.py:405)
+  * BatchNorm2d training semantics relied on by all of the above (SURVEY.md
+    Appendix A): biased batch variance for normalisation, unbiased variance
+    and momentum 0.1 for the running buffers.
+
+The arithmetic itself lives in PyTorch (third-party for the reference, not
+vendored, not pinned by it; torch 2.11.0 is what this image has).  The oracle is
+written functionally over a ``state_dict`` (same key names as the reference) so
+that it has no ``nn.Module`` in common with the reference source: convolutions
+go through ``torch.nn.functional`` on the CPU, BatchNorm / loss / KL are spelled
+out as formulas, gradients come from autograd over those formulas.
+
+Parity pin: the reference stores NO golden vectors, so
+this oracle is pinned against outputs of the reference itself, produced in the
+build container by ``tests/golden/make_golden.py`` (imports
+/root/reference/model.py unmodified) and committed as ``tests/golden/*.npz``;
+``tests/test_oracle_golden.py`` replays them.  The fixtures are self-generated,
+and DESIGN.md says so.
+
+Extensions the reference cannot express: ``width`` multiplies
+the hard-coded channel literals of model.py:92-101 / model.py:157-170 (config
+C4); ``kl_weight`` may be passed per call (the "annealed" configuration).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+BN_EPS = 1e-5        # nn.BatchNorm2d default, constructed at model.py:30 etc.
+BN_MOMENTUM = 0.1
+
+
+@dataclass(frozen=True)
+class VAEConfig:
+    """Constructor arguments of the reference ``VAE`` (model.py:259-262) that the
+    hot path depends on, plus the builder-defined ``width`` multiplier."""
+    in_channels: int = 1
+    decoder_out_channels: int = 1
+    z_dimension: int = 64
+    input_image_size: int = 64
+    nll: float = 1.0
+    kl: float = 1.0
+    sigma_decoder: float = 0.1
+    require_rsample: bool = True
+    width: int = 1
+
+    @property
+    def categorical(self) -> bool:
+        # model.py:399: CE branch when decoder_out_channels > in_channels
+        return self.decoder_out_channels > self.in_channels
+
+    @property
+    def enc_planes(self) -> Tuple[int, ...]:
+        return tuple(c * self.width for c in (32, 64, 128, 256))   # model.py:97-100
+
+    @property
+    def stem_planes(self) -> int:
+        return 32 * self.width                                      # model.py:92-94
+
+    @property
+    def dec_stem_planes(self) -> int:
+        return 128 * self.width                                     # model.py:157
+
+    @property
+    def dec_planes(self) -> Tuple[int, ...]:
+        p = [128, 64, 32, 16]                                       # model.py:164-167
+        if self.input_image_size > 32:
+            p.append(16)                                            # model.py:169-170
+        return tuple(c * self.width for c in p)
+
+    @property
+    def adjust(self) -> int:
+        # model.py:307-310
+        if self.input_image_size > 32:
+            return (64 - self.input_image_size) // 2
+        return (32 - self.input_image_size) // 2
+
+
+# ----------------------------------------------------------------------------
+# parameter / buffer inventory (same names, shapes and order as the reference's
+# named_parameters(); checked against the live reference by the golden script)
+# ----------------------------------------------------------------------------
+
+def param_specs(cfg: VAEConfig) -> List[Tuple[str, Tuple[int, ...]]]:
+    out: List[Tuple[str, Tuple[int, ...]]] = []
+
+    def bn(prefix: str, c: int):
+        out.append((prefix + ".weight", (c,)))
+        out.append((prefix + ".bias", (c,)))
+
+    s = cfg.stem_planes
+    out.append(("encoder.conv1.weight", (s, cfg.in_channels, 5, 5)))
+    bn("encoder.bn1", s)
+    inpl = s
+    for i, pl in enumerate(cfg.enc_planes, start=1):
+        p = f"encoder.layer{i}.0"
+        out.append((p + ".conv1.weight", (pl, inpl, 3, 3)))
+        bn(p + ".bn1", pl)
+        out.append((p + ".conv2.weight", (pl, pl, 3, 3)))
+        bn(p + ".bn2", pl)
+        out.append((p + ".downsample.0.weight", (pl, inpl, 1, 1)))
+        bn(p + ".downsample.1", pl)
+        inpl = pl
+    out.append(("encoder.conv_mu.weight", (cfg.z_dimension, inpl, 1, 1)))
+    if cfg.require_rsample:
+        out.append(("encoder.conv_logvar.weight", (cfg.z_dimension, inpl, 1, 1)))
+    d = cfg.dec_stem_planes
+    out.append(("decoder.conv1.weight", (cfg.z_dimension, d, 2, 2)))
+    bn("decoder.bn1", d)
+    inpl = d
+    for i, pl in enumerate(cfg.dec_planes, start=1):
+        p = f"decoder.uplayer{i}.0"
+        out.append((p + ".conv1.weight", (pl, inpl, 1, 1)))
+        bn(p + ".bn1", pl)
+        out.append((p + ".conv2.weight", (pl, pl, 4, 4)))          # convT [Cin, Cout, 4, 4]
+        bn(p + ".bn2", pl)
+        out.append((p + ".upsample.0.weight", (inpl, pl, 4, 4)))   # convT [Cin, Cout, 4, 4]
+        bn(p + ".upsample.1", pl)
+        inpl = pl
+    out.append(("decoder.conv2.weight", (cfg.decoder_out_channels, inpl, 3, 3)))
+    out.append(("decoder.conv2.bias", (cfg.decoder_out_channels,)))
+    bn("decoder.bn2", cfg.decoder_out_channels)
+    return out
+
+
+def bn_names(cfg: VAEConfig) -> List[Tuple[str, int]]:
+    """(prefix, channels) of every BatchNorm2d in state_dict order."""
+    res = []
+    specs = param_specs(cfg)
+    for i, (name, shape) in enumerate(specs):
+        if name.endswith(".weight") and len(shape) == 1:
+            res.append((name[: -len(".weight")], shape[0]))
+    return res
+
+
+def init_state(cfg: VAEConfig, seed: int = 0, dtype=torch.float32) -> Dict[str, torch.Tensor]:
+    """Parameters drawn from the reference's default-init *distributions*
+    (conv/convT weights U(+-1/sqrt(fan_in)) with
+    fan_in = weight.size(1) * kH * kW; BN gamma=1, beta=0; tail bias
+    U(+-1/sqrt(fan_in))) plus fresh BN buffers.  Not the reference's RNG stream --
+    golden fixtures carry the reference's own draws."""
+    g = torch.Generator().manual_seed(seed)
+    st: Dict[str, torch.Tensor] = {}
+    for name, shape in param_specs(cfg):
+        if len(shape) == 4:
+            bound = 1.0 / math.sqrt(shape[1] * shape[2] * shape[3])
+            st[name] = ((torch.rand(shape, generator=g, dtype=torch.float64) * 2 - 1) * bound).to(dtype)
+        elif name == "decoder.conv2.bias":
+            w = st["decoder.conv2.weight"]
+            bound = 1.0 / math.sqrt(w.shape[1] * w.shape[2] * w.shape[3])
+            st[name] = ((torch.rand(shape, generator=g, dtype=torch.float64) * 2 - 1) * bound).to(dtype)
+        elif name.endswith(".weight"):
+            st[name] = torch.ones(shape, dtype=dtype)
+        else:
+            st[name] = torch.zeros(shape, dtype=dtype)
+    for prefix, c in bn_names(cfg):
+        st[prefix + ".running_mean"] = torch.zeros(c, dtype=dtype)
+        st[prefix + ".running_var"] = torch.ones(c, dtype=dtype)
+        st[prefix + ".num_batches_tracked"] = torch.zeros((), dtype=torch.int64)
+    return st
+
+
+# ----------------------------------------------------------------------------
+# forward
+# ----------------------------------------------------------------------------
+
+class _Ctx:
+    """Carries the state dict, the training flag and the BN side effects."""
+
+    def __init__(self, st, training: bool, keep: bool):
+        self.st = st
+        self.training = training
+        self.keep = keep
+        self.new_buffers: Dict[str, torch.Tensor] = {}
+        self.acts: Dict[str, torch.Tensor] = {}
+
+    def save(self, name: str, t: torch.Tensor):
+        if self.keep:
+            self.acts[name] = t
+
+
+def _batchnorm(ctx: _Ctx, y: torch.Tensor, prefix: str) -> torch.Tensor:
+    """nn.BatchNorm2d with default arguments."""
+    st = ctx.st
+    gamma, beta = st[prefix + ".weight"], st[prefix + ".bias"]
+    if ctx.training:
+        m = y.shape[0] * y.shape[2] * y.shape[3]
+        mean = y.mean(dim=(0, 2, 3))
+        var = ((y - mean[None, :, None, None]) ** 2).mean(dim=(0, 2, 3))       # biased
+        with torch.no_grad():
+            unbiased = var * (m / (m - 1)) if m > 1 else var
+            ctx.new_buffers[prefix + ".running_mean"] = (
+                (1 - BN_MOMENTUM) * st[prefix + ".running_mean"] + BN_MOMENTUM * mean.detach())
+            ctx.new_buffers[prefix + ".running_var"] = (
+                (1 - BN_MOMENTUM) * st[prefix + ".running_var"] + BN_MOMENTUM * unbiased.detach())
+            ctx.new_buffers[prefix + ".num_batches_tracked"] = st[prefix + ".num_batches_tracked"] + 1
+    else:
+        mean, var = st[prefix + ".running_mean"], st[prefix + ".running_var"]
+    xhat = (y - mean[None, :, None, None]) / torch.sqrt(var[None, :, None, None] + BN_EPS)
+    return gamma[None, :, None, None] * xhat + beta[None, :, None, None]
+
+
+def _basic_block(ctx: _Ctx, x: torch.Tensor, p: str) -> torch.Tensor:
+    """model.py:39-55 with the 1x1 stride-2 shortcut of model.py:132-138."""
+    st = ctx.st
+    y1 = F.conv2d(x, st[p + ".conv1.weight"], stride=2, padding=1)
+    ctx.save(p + ".conv1", y1)
+    a1 = torch.relu(_batchnorm(ctx, y1, p + ".bn1"))
+    y2 = F.conv2d(a1, st[p + ".conv2.weight"], stride=1, padding=1)
+    ctx.save(p + ".conv2", y2)
+    yd = F.conv2d(x, st[p + ".downsample.0.weight"], stride=2)
+    ctx.save(p + ".downsample.0", yd)
+    out = torch.relu(_batchnorm(ctx, y2, p + ".bn2") + _batchnorm(ctx, yd, p + ".downsample.1"))
+    ctx.save(p, out)
+    return out
+
+
+def _deconv_block(ctx: _Ctx, x: torch.Tensor, p: str) -> torch.Tensor:
+    """model.py:70-85 with the upsample branch of model.py:197-204."""
+    st = ctx.st
+    y1 = F.conv2d(x, st[p + ".conv1.weight"])
+    ctx.save(p + ".conv1", y1)
+    a1 = torch.relu(_batchnorm(ctx, y1, p + ".bn1"))
+    y2 = F.conv_transpose2d(a1, st[p + ".conv2.weight"], stride=2, padding=1)
+    ctx.save(p + ".conv2", y2)
+    yu = F.conv_transpose2d(x, st[p + ".upsample.0.weight"], stride=2, padding=1)
+    ctx.save(p + ".upsample.0", yu)
+    out = torch.relu(_batchnorm(ctx, y2, p + ".bn2") + _batchnorm(ctx, yu, p + ".upsample.1"))
+    ctx.save(p, out)
+    return out
+
+
+def encode(ctx: _Ctx, cfg: VAEConfig, x: torch.Tensor):
+    st = ctx.st
+    y = F.conv2d(x, st["encoder.conv1.weight"], stride=2, padding=2)           # model.py:115
+    ctx.save("encoder.conv1", y)
+    a = torch.relu(_batchnorm(ctx, y, "encoder.bn1"))                          # model.py:116-117
+    for i in range(1, 5):                                                      # model.py:119-122
+        a = _basic_block(ctx, a, f"encoder.layer{i}.0")
+    pooled = a.mean(dim=(2, 3), keepdim=True)                                  # model.py:123
+    mu = F.conv2d(pooled, st["encoder.conv_mu.weight"])                        # model.py:125
+    logvar = None
+    if cfg.require_rsample:
+        logvar = F.conv2d(pooled, st["encoder.conv_logvar.weight"])            # model.py:128
+    return mu, logvar
+
+
+def decode(ctx: _Ctx, cfg: VAEConfig, z: torch.Tensor) -> torch.Tensor:
+    st = ctx.st
+    y = F.conv_transpose2d(z, st["decoder.conv1.weight"])                      # model.py:182
+    ctx.save("decoder.conv1", y)
+    a = torch.relu(_batchnorm(ctx, y, "decoder.bn1"))                          # model.py:183-184
+    for i in range(1, len(cfg.dec_planes) + 1):                                # model.py:186-192
+        a = _deconv_block(ctx, a, f"decoder.uplayer{i}.0")
+    y = F.conv2d(a, st["decoder.conv2.weight"], st["decoder.conv2.bias"], padding=1)
+    ctx.save("decoder.conv2", y)
+    out = _batchnorm(ctx, y, "decoder.bn2")                                    # model.py:193
+    adj = cfg.adjust
+    if adj != 0:                                                               # model.py:328-329
+        out = out[:, :, adj:-adj, adj:-adj]
+    return out
+
+
+def forward(st, cfg: VAEConfig, x: torch.Tensor, eps: Optional[torch.Tensor],
+            training: bool = True, keep_activations: bool = False):
+    """VAE.forward (model.py:316-342) for the ``pixelcnn is None`` configuration.
+    ``eps`` is the standard-normal draw of ``rsample`` (model.py:149-150),
+    shape [N, z, 1, 1].  Returns (mu, logvar, encoding, reconstruction, ctx)."""
+    ctx = _Ctx(st, training, keep_activations)
+    mu, logvar = encode(ctx, cfg, x)
+    if cfg.require_rsample:
+        encoding = mu + eps * torch.exp(0.5 * logvar)
+    else:
+        encoding = mu
+    recon = decode(ctx, cfg, encoding)
+    return mu, logvar, encoding, recon, ctx
+
+
+# ----------------------------------------------------------------------------
+# loss
+# ----------------------------------------------------------------------------
+
+def kl_sum(mu: torch.Tensor, logvar: torch.Tensor) -> torch.Tensor:
+    """model.py:364-365."""
+    return -0.5 * torch.sum(logvar - torch.exp(logvar) - mu * mu + 1)
+
+
+def gaussian_nll_sum(recon: torch.Tensor, target: torch.Tensor, sigma: float) -> torch.Tensor:
+    """-Normal(recon, sigma).log_prob(target).sum()  (model.py:403)."""
+    return torch.sum((target - recon) ** 2 / (2 * sigma * sigma) + math.log(sigma) + 0.5 * math.log(2 * math.pi))
+
+
+def weighted_ce_sum(recon: torch.Tensor, target: torch.Tensor, weight: Optional[torch.Tensor]) -> torch.Tensor:
+    """F.cross_entropy(recon, target, reduction='none', weight=w).sum() (model.py:400-401)."""
+    logp = recon - torch.logsumexp(recon, dim=1, keepdim=True)
+    picked = torch.gather(logp, 1, target[:, None]).squeeze(1)
+    if weight is not None:
+        picked = picked * weight[target]
+    return -picked.sum()
+
+
+def loss(cfg: VAEConfig, target, mu, logvar, recon, ce_weight=None, kl_weight: Optional[float] = None):
+    """VAE.loss (model.py:385-406) without the MMD diagnostic (coefficient 0 in
+    every in-scope model).
+    Returns (loss, pxz/N, kl/N) with the last two as 0-d tensors."""
+    n = target.shape[0]
+    klw = cfg.kl if kl_weight is None else kl_weight
+    kl = kl_sum(mu, logvar) if (mu is not None and logvar is not None) else torch.zeros((), dtype=recon.dtype)
+    if cfg.categorical:
+        pxz = cfg.nll * weighted_ce_sum(recon, target, ce_weight)
+    else:
+        pxz = cfg.nll * gaussian_nll_sum(recon, target, cfg.sigma_decoder)
+    total = (pxz + klw * kl) / n
+    return total, pxz.detach() / n, kl.detach() / n
+
+
+# ----------------------------------------------------------------------------
+# one training step (main.py:389-390, main.py:398)
+# ----------------------------------------------------------------------------
+
+@dataclass
+class StepResult:
+    loss: float
+    pxz: float
+    kl: float
+    mu: torch.Tensor
+    logvar: Optional[torch.Tensor]
+    encoding: torch.Tensor
+    recon: torch.Tensor
+    grads: Dict[str, torch.Tensor]
+    new_buffers: Dict[str, torch.Tensor]
+    acts: Dict[str, torch.Tensor] = field(default_factory=dict)
+
+
+def train_step(st, cfg: VAEConfig, x, target, eps, ce_weight=None, kl_weight=None,
+               keep_activations: bool = False, dtype=None) -> StepResult:
+    """forward -> loss -> backward on the CPU.  ``dtype=torch.float64`` gives a
+    higher-precision referee for the 1e-5 fp32 comparison."""
+    names = [n for n, _ in param_specs(cfg)]
+    work = {}
+    for k, v in st.items():
+        t = v.detach().clone()
+        if dtype is not None and t.is_floating_point():
+            t = t.to(dtype)
+        work[k] = t
+    for n in names:
+        work[n].requires_grad_(True)
+    if dtype is not None:
+        x = x.to(dtype)
+        eps = eps.to(dtype) if eps is not None else None
+        if target.is_floating_point():
+            target = target.to(dtype)
+        if ce_weight is not None:
+            ce_weight = ce_weight.to(dtype)
+    mu, logvar, enc, recon, ctx = forward(work, cfg, x, eps, training=True, keep_activations=keep_activations)
+    total, pxz, kl = loss(cfg, target, mu, logvar, recon, ce_weight, kl_weight)
+    grads = torch.autograd.grad(total, [work[n] for n in names], allow_unused=True)
+    gd = {n: (g if g is not None else torch.zeros_like(work[n])) for n, g in zip(names, grads)}
+    return StepResult(float(total.detach()), float(pxz), float(kl), mu.detach(),
+                      None if logvar is None else logvar.detach(), enc.detach(), recon.detach(),
+                      gd, ctx.new_buffers, {k: v.detach() for k, v in ctx.acts.items()})
+
+
+def dp_mean_grads(st, cfg: VAEConfig, shards) -> Dict[str, torch.Tensor]:
+    """Data-parallel oracle: the mean over ranks of the
+    per-shard gradients (BatchNorm statistics stay per shard).  ``shards`` is a
+    list of (x, target, eps)."""
+    acc = None
+    for (x, t, e) in shards:
+        r = train_step(st, cfg, x, t, e)
+        if acc is None:
+            acc = {k: v.clone() for k, v in r.grads.items()}
+        else:
+            for k, v in r.grads.items():
+                acc[k] += v
+    return {k: v / len(shards) for k, v in acc.items()}
+
+
+# ----------------------------------------------------------------------------
+# synthetic Moving-MNIST-like input
+# ----------------------------------------------------------------------------
+
+DATA_MEAN = 0.0521   # k=2 label mean  (test-output-models.ipynb:40-43)
+DATA_STD = 0.2222
+
+
+def synthetic_labels(n_frames: int, size: int = 64, seq_len: int = 20, seed: int = 1234) -> torch.Tensor:
+    """k=2 k-means label maps of Moving-MNIST-like sequences: two random binary
+    blobs of (28/64)*size pixels per sequence bouncing with constant velocity;
+    sequences flattened to frames the way movingmnistdataset.py:20-24 does.
+    Returns uint8 [n_frames, size, size] with values in {0, 1}."""
+    g = torch.Generator().manual_seed(seed)
+    d = max(4, (28 * size) // 64)
+    n_seq = (n_frames + seq_len - 1) // seq_len
+    frames = torch.zeros(n_seq * seq_len, size, size, dtype=torch.uint8)
+    for s in range(n_seq):
+        for _ in range(2):
+            yy, xx = torch.meshgrid(torch.arange(d), torch.arange(d), indexing="ij")
+            cy, cx = (d - 1) / 2.0, (d - 1) / 2.0
+            r = d * (0.25 + 0.15 * torch.rand((), generator=g).item())
+            ring = ((yy - cy) ** 2 + (xx - cx) ** 2).sqrt()
+            blob = ((ring < r) & (torch.rand(d, d, generator=g) < 0.45)).to(torch.uint8)
+            pos = torch.rand(2, generator=g) * (size - d)
+            vel = (torch.rand(2, generator=g) - 0.5) * 8.0
+            for t in range(seq_len):
+                py, px = int(pos[0].item()), int(pos[1].item())
+                f = frames[s * seq_len + t]
+                f[py:py + d, px:px + d] |= blob
+                pos = pos + vel
+                for a in range(2):
+                    if pos[a] < 0:
+                        pos[a] = -pos[a]; vel[a] = -vel[a]
+                    if pos[a] > size - d:
+                        pos[a] = 2 * (size - d) - pos[a]; vel[a] = -vel[a]
+    return frames[:n_frames]
+
+
+def normalise(labels: torch.Tensor) -> torch.Tensor:
+    """main.py:383-388: (x - data_mean) / data_std on the label map, as [N,1,H,W] fp32."""
+    n, h, w = labels.shape
+    return (labels.float().view(n, 1, h, w) - DATA_MEAN) / DATA_STD
