@@ -1,0 +1,174 @@
+/* mmvae.h -- C ABI of libmmvae_b200.so: the B200-native VAE training step.
+ *
+ * This is the drop-in boundary for ONE hot path of praateekmahajan/moving-mnist-vae:
+ * forward + loss + backward of the `VAE` module (reference model.py:258-406) as driven
+ * by the train-loop body main.py:389-390,398.  Everything behind these entry points is
+ * hand-written CUDA for sm_100a.  There is no CPU fallback: every compute entry point
+ * returns MMVAE_ERR_NO_DEVICE / MMVAE_ERR_ARCH instead of computing on the host.
+ *
+ * Conventions
+ *   - plain C, no torch / CUDA types in signatures (`stream` is a cudaStream_t passed
+ *     as void*; device pointers are plain pointers);
+ *   - the library never allocates, frees or retains device memory: inputs, parameter /
+ *     gradient / buffer arenas, outputs and the workspace are owned by the caller (the
+ *     Python shim uses torch's caching allocator);
+ *   - all work is enqueued on `stream`; no host synchronisation, no default-stream use,
+ *     so a sequence of calls is CUDA-graph capturable;
+ *   - return 0 on success, a negative MMVAE_ERR_* otherwise; the message is available
+ *     through mmvae_last_error() (thread-local);
+ *   - public tensors use the reference's layout: NCHW fp32.  Internal activations are
+ *     NHWC in the storage type of `precision`.
+ *
+ * Parameter arena: all 93 (base model) parameter tensors of the reference's
+ * `named_parameters()` order, back to back, fp32, no padding (2,112,819 floats for the
+ * base model).  The gradient arena has the same layout.  The BatchNorm buffer arena is
+ * [running_mean(C), running_var(C)] per BatchNorm2d in state_dict order; `bn_counters`
+ * holds the matching `num_batches_tracked` values (int64).  mmvae_param_entry /
+ * mmvae_bn_entry enumerate both so the host never hard-codes offsets.
+ */
+#ifndef MMVAE_H_
+#define MMVAE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMVAE_ABI_VERSION 1
+
+enum {
+  MMVAE_OK = 0,
+  MMVAE_ERR_BAD_DESC = -1,    /* unsupported / inconsistent mmvae_desc                  */
+  MMVAE_ERR_BAD_ARG = -2,     /* NULL / misaligned pointer, workspace too small         */
+  MMVAE_ERR_NO_DEVICE = -3,   /* no CUDA device visible                                 */
+  MMVAE_ERR_ARCH = -4,        /* device is not sm_100 (B200); nothing else is compiled  */
+  MMVAE_ERR_CUDA = -5         /* a CUDA runtime call / launch failed                    */
+};
+
+enum { MMVAE_PREC_FP32 = 0,   /* fp32 storage, fp32 SIMT arithmetic: validation mode    */
+       MMVAE_PREC_BF16 = 1 }; /* bf16 storage, tcgen05 bf16 MMA with fp32 accumulation  */
+
+enum { MMVAE_LOSS_GAUSSIAN = 0,   /* -nll * Normal(recon, sigma).log_prob(target).sum()  model.py:403     */
+       MMVAE_LOSS_CATEGORICAL = 1 /*  nll * cross_entropy(recon, target, w).sum()        model.py:400-401 */ };
+
+/* Mirrors the constructor arguments of the reference VAE (model.py:259-262) that shape the
+ * hot path, plus the local batch size and the arithmetic mode. */
+typedef struct mmvae_desc {
+  int32_t struct_size;      /* = sizeof(mmvae_desc), checked                                   */
+  int32_t batch;            /* N: frames in this call (per GPU)                                */
+  int32_t in_channels;      /* model.py:259 in_channels                                        */
+  int32_t out_channels;     /* model.py:259 decoder_out_channels                               */
+  int32_t z_dim;            /* model.py:260 z_dimension                                        */
+  int32_t image_size;       /* model.py:262 input_image_size (>32: five up-blocks, else four)  */
+  int32_t width;            /* channel multiplier of the literals at model.py:92-101,157-170   */
+  int32_t require_rsample;  /* model.py:262; 0 => encoding = mu, no logvar head                 */
+  int32_t precision;        /* MMVAE_PREC_*                                                    */
+  int32_t training;         /* 1: batch-statistics BatchNorm + running-stat update; 0: eval    */
+  int32_t reserved[6];
+} mmvae_desc;
+
+typedef struct mmvae_layout_info {
+  int64_t n_params;         /* floats in the parameter / gradient arena         */
+  int64_t n_bn_buffers;     /* floats in the BatchNorm buffer arena             */
+  int32_t n_param_tensors;  /* 93 for the base model                            */
+  int32_t n_bn;             /* 30 for the base model (29 at image_size <= 32)   */
+  int64_t workspace_bytes;  /* activations + saved statistics + backward scratch */
+  int32_t decoder_size;     /* spatial size the decoder emits (64 or 32) before the crop */
+  int32_t crop;             /* `adjust` of model.py:307-310 (>= 0 pixels per side)       */
+  int64_t train_flops;      /* 2*MAC over every conv, fwd + dgrad + wgrad, for `batch` frames */
+} mmvae_layout_info;
+
+typedef struct mmvae_loss_args {
+  int32_t struct_size;      /* = sizeof(mmvae_loss_args)                                        */
+  int32_t kind;             /* MMVAE_LOSS_*                                                     */
+  float nll;                /* model.py:285 self.nll                                            */
+  float kl;                 /* model.py:285 self.kl -- a per-call scalar so it can be annealed  */
+  float sigma;              /* model.py:286 sigma_decoder (Gaussian branch)                     */
+  int32_t batch;            /* N = target.shape[0]   (model.py:405)                             */
+  int32_t channels;         /* C of recon                                                       */
+  int32_t height, width;    /* spatial size of recon / target (after the crop)                  */
+  int32_t z_dim;            /* elements of mu / logvar per frame                                */
+} mmvae_loss_args;
+
+/* ---- introspection: callable without a GPU --------------------------------------------- */
+int mmvae_abi_version(void);
+const char* mmvae_last_error(void);
+int mmvae_layout(const mmvae_desc* d, mmvae_layout_info* out);
+/* i-th parameter tensor (reference named_parameters() order): name, arena offset, shape. */
+int mmvae_param_entry(const mmvae_desc* d, int32_t i, char* name, size_t name_cap,
+                      int64_t* offset, int32_t* ndim, int32_t shape[4]);
+/* i-th BatchNorm2d: state_dict prefix, channels, offset of running_mean in the buffer arena
+ * (running_var follows at +channels). */
+int mmvae_bn_entry(const mmvae_desc* d, int32_t i, char* prefix, size_t prefix_cap,
+                   int32_t* channels, int64_t* buffer_offset);
+/* Named tensor inside the workspace (debug / parity tests): "encoder.layer1.0.conv1" is the raw
+ * conv output y (NHWC, storage type), "encoder.layer1.0" the block output.  dims = {N,H,W,C}. */
+int mmvae_workspace_tensor(const mmvae_desc* d, const char* name, int64_t* byte_offset, int32_t dims[4]);
+
+/* ---- the hot path ---------------------------------------------------------------------------
+ * VAE.forward (model.py:316-342, pixelcnn None): encoder -> rsample -> decoder.
+ *   x        [N, in_channels, S, S] fp32 NCHW (device)
+ *   params   parameter arena (fp32, device)
+ *   bn_buffers / bn_counters   updated in place when d->training (momentum 0.1, unbiased var)
+ *   eps      [N, z] fp32 standard-normal draw of rsample (model.py:149-150); NULL => generated on
+ *            device with Philox4x32-10 keyed by (seed, offset) and written to eps_out
+ *   eps_out  [N, z] fp32 or NULL
+ *   mu, logvar, encoding   [N, z] fp32 outputs (logvar may be NULL iff !require_rsample)
+ *   recon    [N, out_channels, D, D] fp32 NCHW, D = decoder_size (crop is a host-side view)
+ * The workspace keeps what mmvae_backward needs. */
+int mmvae_forward(const mmvae_desc* d, const float* x, const float* params, float* bn_buffers,
+                  int64_t* bn_counters, const float* eps, uint64_t seed, uint64_t offset, float* eps_out,
+                  void* workspace, size_t workspace_bytes,
+                  float* mu, float* logvar, float* encoding, float* recon, void* stream);
+
+/* Decoder only (get_z_image / get_reconstruction, model.py:344-362): encoding [N, z] -> recon. */
+int mmvae_decode(const mmvae_desc* d, const float* encoding, const float* params, float* bn_buffers,
+                 int64_t* bn_counters, void* workspace, size_t workspace_bytes, float* recon, void* stream);
+
+/* VAE.loss forward (model.py:385-406, MMD excluded): out[0] = (pxz + kl*KL)/N, out[1] = pxz/N,
+ * out[2] = KL/N, all fp32 on the device.  target: fp32 [N,C,H,W] (Gaussian) or int64 [N,H,W]
+ * (categorical); ce_weight [C] fp32 or NULL.  mu/logvar may be NULL (KL = 0).
+ * scratch: >= mmvae_loss_scratch_bytes() bytes of device memory. */
+size_t mmvae_loss_scratch_bytes(void);
+int mmvae_loss_forward(const mmvae_loss_args* a, const float* recon, const void* target,
+                       const float* ce_weight, const float* mu, const float* logvar,
+                       float* out, void* scratch, void* stream);
+/* Gradient of out[0] scaled by the device scalar *grad_out: d_recon [N,C,H,W], d_mu, d_logvar [N,z]. */
+int mmvae_loss_backward(const mmvae_loss_args* a, const float* recon, const void* target,
+                        const float* ce_weight, const float* mu, const float* logvar,
+                        const float* grad_out, float* d_recon, float* d_mu, float* d_logvar, void* stream);
+
+/* Backward of mmvae_forward: given dL/d(mu, logvar, encoding, recon) (any may be NULL = zero;
+ * d_recon is [N, out_channels, D, D] uncropped) fill the gradient arena `grads` (overwritten, fp32,
+ * same layout as `params`).  Must follow a mmvae_forward with the same desc / workspace / x / params.
+ * `phases` selects which part of the backward sweep to enqueue, so that a data-parallel host can record
+ * an event after each part and start that part's gradient all-reduce while the rest still runs; the
+ * parts must be issued in order DECODER, ENC_DEEP, ENC_SHALLOW.  Each part owns a contiguous range of
+ * the gradient arena (mmvae_backward_range). */
+enum { MMVAE_BWD_DECODER = 1,      /* tail conv .. decoder stem: every decoder.* gradient          */
+       MMVAE_BWD_ENC_DEEP = 2,     /* heads, encoder.layer4, encoder.layer3                        */
+       MMVAE_BWD_ENC_SHALLOW = 4,  /* encoder.layer2, layer1, stem                                 */
+       MMVAE_BWD_ALL = 7 };
+int mmvae_backward(const mmvae_desc* d, const float* x, const float* params,
+                   void* workspace, size_t workspace_bytes,
+                   const float* d_mu, const float* d_logvar, const float* d_encoding, const float* d_recon,
+                   float* grads, int32_t phases, void* stream);
+/* [begin, end) float offsets of the gradient-arena range written by one phase. */
+int mmvae_backward_range(const mmvae_desc* d, int32_t phase, int64_t* begin, int64_t* end);
+
+/* Counter-based standard normals, the generator mmvae_forward uses when eps == NULL:
+ * element i = Box-Muller of Philox4x32-10(key = seed, counter = offset + i/4)[i%4 pair]. */
+int mmvae_philox_normal(uint64_t seed, uint64_t offset, int64_t n, float* out, void* stream);
+
+/* Fused multi-tensor Adam over the flat arenas (optim.Adam defaults of main.py:468):
+ * p -= lr * m_hat / (sqrt(v_hat) + eps), grads pre-scaled by grad_scale (1/world_size for DP). */
+int mmvae_adam_step(int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                    float lr, float beta1, float beta2, float eps, float weight_decay,
+                    int64_t step, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMVAE_H_ */

@@ -1,0 +1,562 @@
+// api.cu -- extern "C" entry points of libmmvae_b200.so (see include/mmvae.h) and the host-side
+// orchestration of one VAE step: which kernel runs on which tensors, in which order.
+//
+// Order of operations follows the reference: VAE.forward model.py:316-342 -> VAE_Encoder.forward
+// model.py:114-130 (BasicBlock.forward model.py:39-55) -> rsample model.py:148-150 ->
+// VAE_Decoder.forward model.py:181-194 (DeconvBottleneck.forward model.py:70-85); the backward is
+// the hand-derived adjoint of the same graph (formulas in SURVEY.md Appendix A / DESIGN.md).
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "kernels.cuh"
+#include "plan.hpp"
+#include "tc.cuh"
+
+namespace mmvae {
+
+thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+// One check per device per process: the library only carries sm_100a code.
+static int check_device() {
+  static std::atomic<int> cached[64];
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(MMVAE_ERR_NO_DEVICE, "no CUDA device: %s (libmmvae_b200 has no CPU fallback)", cudaGetErrorString(e));
+  }
+  if (dev >= 0 && dev < 64 && cached[dev].load() == 1) return 0;
+  int major = 0, minor = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  if (major != 10)
+    return fail(MMVAE_ERR_ARCH, "device %d is sm_%d%d; libmmvae_b200 is built for sm_100a (B200) only", dev, major, minor);
+  if (dev >= 0 && dev < 64) cached[dev].store(1);
+  return 0;
+}
+
+static int check_launches(const char* what) {
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(MMVAE_ERR_CUDA, "%s: CUDA error: %s", what, cudaGetErrorString(e));
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// gather-convolution descriptors
+// ------------------------------------------------------------------------------------------------
+static void add_tap(GVar& v, int dy, int dx, int wofs) {
+  v.dy[v.ntaps] = (signed char)dy; v.dx[v.ntaps] = (signed char)dx; v.wofs[v.ntaps] = wofs; ++v.ntaps;
+}
+
+// Forward geometry of a conv / transposed conv (also used by its weight gradient).
+static void geom_fprop(const ConvT_& c, int N, GConvParams& g) {
+  memset(&g, 0, sizeof(g));
+  g.N = N; g.Hi = c.Hi; g.Wi = c.Wi; g.Ci = c.Ci; g.Ho = c.Ho; g.Wo = c.Wo; g.Co = c.Co;
+  const int k = c.k;
+  if (c.kind == CONV) {
+    g.nvar = 1; g.Hg = c.Ho; g.Wg = c.Wo; g.os = 1; g.is = c.s;
+    g.w_sci = k * k; g.w_sco = c.Ci * k * k;                       // weight [Co][Ci][k][k]
+    for (int kh = 0; kh < k; ++kh)
+      for (int kw = 0; kw < k; ++kw) add_tap(g.var[0], kh - c.p, kw - c.p, kh * k + kw);
+  } else if (c.k == 4) {
+    // ConvTranspose2d k4 s2 p1 (model.py:62-65,198-201): oy = 2*iy - 1 + ky, so output parity py only sees
+    // ky == (py+1) mod 2: four 2x2-tap sub-convolutions, no scatter, no atomics.
+    g.nvar = 4; g.Hg = c.Hi; g.Wg = c.Wi; g.os = 2; g.is = 1;
+    g.w_sci = c.Co * 16; g.w_sco = 16;                             // weight [Ci][Co][4][4]
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px) {
+        GVar& v = g.var[py * 2 + px];
+        v.oy0 = py; v.ox0 = px;
+        for (int ky = 0; ky < 4; ++ky) {
+          if ((py + 1 - ky) % 2 != 0) continue;
+          for (int kx = 0; kx < 4; ++kx) {
+            if ((px + 1 - kx) % 2 != 0) continue;
+            add_tap(v, (py + 1 - ky) / 2, (px + 1 - kx) / 2, ky * 4 + kx);
+          }
+        }
+      }
+  } else {
+    // ConvTranspose2d k2 s1 p0 on a 1x1 input (model.py:159-161): y[ky,kx] = W[:, :, ky, kx]^T z
+    g.nvar = 4; g.Hg = 1; g.Wg = 1; g.os = 2; g.is = 1;
+    g.w_sci = c.Co * 4; g.w_sco = 4;                               // weight [Ci][Co][2][2]
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px) {
+        GVar& v = g.var[py * 2 + px];
+        v.oy0 = py; v.ox0 = px;
+        add_tap(v, 0, 0, py * 2 + px);
+      }
+  }
+  g.M = N * g.Hg * g.Wg;
+}
+
+// Data gradient: input = dY [N,Ho,Wo,Co], output = dX [N,Hi,Wi,Ci]; the op's in-channel is the conv's Co.
+static void geom_dgrad(const ConvT_& c, int N, GConvParams& g) {
+  memset(&g, 0, sizeof(g));
+  g.N = N; g.Hi = c.Ho; g.Wi = c.Wo; g.Ci = c.Co; g.Ho = c.Hi; g.Wo = c.Wi; g.Co = c.Ci;
+  const int k = c.k;
+  if (c.kind == CONV) {
+    g.w_sci = c.Ci * k * k; g.w_sco = k * k;
+    if (c.s == 1) {
+      g.nvar = 1; g.Hg = c.Hi; g.Wg = c.Wi; g.os = 1; g.is = 1;
+      for (int kh = 0; kh < k; ++kh)
+        for (int kw = 0; kw < k; ++kw) add_tap(g.var[0], c.p - kh, c.p - kw, kh * k + kw);
+    } else {
+      // stride 2: dX[2i+py] = sum over kh with (py + p - kh) even of dY[i + (py+p-kh)/2]
+      g.Hg = (c.Hi + 1) / 2; g.Wg = (c.Wi + 1) / 2; g.os = 2; g.is = 1;
+      int nv = 0;
+      for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px) {
+          GVar v; memset(&v, 0, sizeof(v));
+          v.oy0 = py; v.ox0 = px;
+          for (int kh = 0; kh < k; ++kh) {
+            if ((py + c.p - kh) % 2 != 0) continue;
+            for (int kw = 0; kw < k; ++kw) {
+              if ((px + c.p - kw) % 2 != 0) continue;
+              add_tap(v, (py + c.p - kh) / 2, (px + c.p - kw) / 2, kh * k + kw);
+            }
+          }
+          if (v.ntaps > 0) g.var[nv++] = v;
+        }
+      g.nvar = nv;
+    }
+  } else if (c.k == 4) {
+    // dX[iy] = sum_ky dY[2*iy - 1 + ky] W[ci][co][ky][kx]: a stride-2 4x4 convolution over dY
+    g.nvar = 1; g.Hg = c.Hi; g.Wg = c.Wi; g.os = 1; g.is = 2;
+    g.w_sci = 16; g.w_sco = c.Co * 16;
+    for (int ky = 0; ky < 4; ++ky)
+      for (int kx = 0; kx < 4; ++kx) add_tap(g.var[0], ky - 1, kx - 1, ky * 4 + kx);
+  } else {
+    g.nvar = 1; g.Hg = 1; g.Wg = 1; g.os = 1; g.is = 1;
+    g.w_sci = 4; g.w_sco = c.Co * 4;
+    for (int ky = 0; ky < 2; ++ky)
+      for (int kx = 0; kx < 2; ++kx) add_tap(g.var[0], ky, kx, ky * 2 + kx);
+  }
+  g.M = N * g.Hg * g.Wg;
+}
+
+// ------------------------------------------------------------------------------------------------
+// step executor
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct Exec {
+  const Plan& P;
+  char* ws;
+  const float* params;
+  float* grads;
+  float* bnbuf;
+  long long* counters;
+  cudaStream_t st;
+  const float* x;       // fp32 NCHW network input
+
+  template <typename U> U* at(size_t off) const { return reinterpret_cast<U*>(ws + off); }
+  const ActT& act(int i) const { return P.acts[i]; }
+
+  // y = conv(in) with per-CTA partial statistics, then BatchNorm finalize
+  void conv_bn_fwd(const ConvT_& c) {
+    GConvParams g;
+    geom_fprop(c, P.d.batch, g);
+    if (c.in < 0) { g.in = x; g.in_nchw_f32 = 1; }
+    else g.in = at<T>(act(c.in).off);
+    g.out = at<T>(act(c.out).off);
+    g.w = params + c.w;
+    g.bias = c.bias >= 0 ? params + c.bias : nullptr;
+    const BnT& b = P.bns[c.bn];
+    g.partials = P.d.training ? at<float>(b.part_off) : nullptr;
+    int prow = conv_forward<T>(g, c, st);
+    BnFinalizeArgs f;
+    f.partials = g.partials; f.P = prow; f.C = b.C; f.m = b.m;
+    f.gamma = params + b.gamma; f.beta = params + b.beta;
+    f.running_mean = bnbuf ? bnbuf + b.rm : nullptr;
+    f.running_var = bnbuf ? bnbuf + b.rm + b.C : nullptr;
+    f.counter = counters ? counters + b.idx : nullptr;
+    f.stat = at<float>(b.stat_off); f.coef = at<float>(b.coef_off);
+    f.training = P.d.training;
+    launch_bn_finalize(f, st);
+  }
+
+  void apply(const ConvT_& c, const ConvT_* c2, int out_act, int relu) {
+    const ActT& o = act(out_act);
+    long long rows = (long long)P.d.batch * o.H * o.W;
+    launch_bn_apply<T>(at<T>(act(c.out).off), at<float>(P.bns[c.bn].coef_off),
+                       c2 ? at<T>(act(c2->out).off) : nullptr, c2 ? at<float>(P.bns[c2->bn].coef_off) : nullptr,
+                       at<T>(o.off), rows, o.C, relu, st);
+  }
+
+  void block_fwd(const BlockT& b) {
+    const ConvT_& c1 = P.convs[b.c1]; const ConvT_& c2 = P.convs[b.c2]; const ConvT_& cs = P.convs[b.cs];
+    conv_bn_fwd(c1);
+    apply(c1, nullptr, b.a1, 1);
+    conv_bn_fwd(c2);
+    conv_bn_fwd(cs);
+    apply(c2, &cs, b.out, 1);
+  }
+
+  void encode(const float* eps, unsigned long long seed, unsigned long long offset, float* eps_out,
+              float* mu, float* logvar, float* enc) {
+    const ConvT_& s = P.convs[P.stem];
+    conv_bn_fwd(s);
+    apply(s, nullptr, P.a_stem, 1);
+    for (const BlockT& b : P.enc) block_fwd(b);
+    HeadsArgs h;
+    const ActT& f = act(P.enc.back().out);
+    h.feat = at<T>(f.off);
+    h.w_mu = params + P.w_mu; h.w_lv = P.w_lv >= 0 ? params + P.w_lv : nullptr;
+    h.eps = eps; h.seed = seed; h.offset = offset;
+    h.pooled = at<float>(P.pooled_off); h.heads = at<float>(P.heads_off);
+    h.mu_out = mu; h.lv_out = logvar; h.enc_out = enc; h.eps_out = eps_out;
+    h.z_act = at<T>(act(P.a_z).off);
+    h.N = P.d.batch; h.hw = P.feat_hw; h.C = P.feat_c; h.z = P.d.z_dim;
+    launch_heads_fwd<T>(h, st);
+  }
+
+  void decode(float* recon) {
+    const ConvT_& s = P.convs[P.dstem];
+    conv_bn_fwd(s);
+    apply(s, nullptr, P.a_dstem, 1);
+    for (const BlockT& b : P.dec) block_fwd(b);
+    const ConvT_& t = P.convs[P.tail];
+    conv_bn_fwd(t);
+    launch_bn_apply_out<T>(at<T>(act(t.out).off), at<float>(P.bns[t.bn].coef_off), recon, P.d.batch,
+                           t.Ho * t.Wo, t.Co, st);
+  }
+
+  // ---------------- backward ----------------
+  void wgrad(const ConvT_& c) {
+    GConvParams g;
+    geom_fprop(c, P.d.batch, g);
+    WGradParams w;
+    memset(&w, 0, sizeof(w));
+    if (c.in < 0) { w.in = x; w.in_nchw_f32 = 1; }
+    else w.in = at<T>(act(c.in).off);
+    w.dout = at<T>(act(c.out).goff);
+    w.dw = grads + c.w;
+    w.N = g.N; w.Hi = g.Hi; w.Wi = g.Wi; w.Ci = g.Ci; w.Ho = g.Ho; w.Wo = g.Wo; w.Co = g.Co;
+    w.Hg = g.Hg; w.Wg = g.Wg; w.M = g.M; w.os = g.os; w.is = g.is; w.w_sci = g.w_sci; w.w_sco = g.w_sco;
+    w.nvar = g.nvar;
+    for (int i = 0; i < g.nvar; ++i) w.var[i] = g.var[i];
+    conv_wgrad<T>(w, c, st);
+  }
+
+  void dgrad(const ConvT_& c, int accumulate) {
+    GConvParams g;
+    geom_dgrad(c, P.d.batch, g);
+    g.in = at<T>(act(c.out).goff);
+    g.out = at<T>(act(c.in).goff);
+    g.w = params + c.w;
+    g.accumulate = accumulate;
+    conv_dgrad<T>(g, c, st);
+  }
+
+  // BatchNorm (+ReLU mask from `mask_act`) backward of conv c (and of the parallel branch c2)
+  void bn_bwd(const void* dA, int dA_f32, int mask_act, const ConvT_& c, const ConvT_* c2) {
+    const BnT& b = P.bns[c.bn];
+    BnBwdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.dA = dA; a.dA_f32 = dA_f32;
+    a.a = mask_act >= 0 ? at<T>(act(mask_act).off) : nullptr;
+    a.y = at<T>(act(c.out).off); a.stat = at<float>(b.stat_off); a.gamma = params + b.gamma;
+    a.partials = at<float>(b.bpart_off);
+    a.bcoef = at<float>(b.bcoef_off);
+    a.g_gamma = grads + b.gamma; a.g_beta = grads + b.beta;
+    a.dY = at<T>(act(c.out).goff);
+    if (c2) {
+      const BnT& b2 = P.bns[c2->bn];
+      a.y2 = at<T>(act(c2->out).off); a.stat2 = at<float>(b2.stat_off); a.gamma2 = params + b2.gamma;
+      a.bcoef2 = at<float>(b2.bcoef_off);
+      a.g_gamma2 = grads + b2.gamma; a.g_beta2 = grads + b2.beta;
+      a.dY2 = at<T>(act(c2->out).goff);
+    }
+    a.rows = (long long)P.d.batch * c.Ho * c.Wo; a.C = c.Co;
+    launch_bn_bwd<T>(a, st);
+  }
+
+  void block_bwd(const BlockT& b) {
+    const ConvT_& c1 = P.convs[b.c1]; const ConvT_& c2 = P.convs[b.c2]; const ConvT_& cs = P.convs[b.cs];
+    bn_bwd(at<T>(act(b.out).goff), 0, b.out, c2, &cs);
+    wgrad(c2);
+    wgrad(cs);
+    dgrad(c2, 0);                                     // -> d a1
+    bn_bwd(at<T>(act(b.a1).goff), 0, b.a1, c1, nullptr);
+    wgrad(c1);
+    dgrad(c1, 0);                                     // -> d in
+    dgrad(cs, 1);                                     // += shortcut
+  }
+
+  // gradient-arena range [begin, end) owned by a backward phase
+  static void phase_range(const Plan& P, int phase, int64_t& b, int64_t& e) {
+    const int64_t deep = P.convs[P.enc[2].c1].w;             // encoder.layer3.0.conv1.weight
+    const int64_t dec = P.convs[P.dstem].w;                  // decoder.conv1.weight
+    if (phase == MMVAE_BWD_DECODER) { b = dec; e = P.n_params; }
+    else if (phase == MMVAE_BWD_ENC_DEEP) { b = deep; e = dec; }
+    else { b = 0; e = deep; }
+  }
+  void clear(int phase) {
+    int64_t b, e;
+    phase_range(P, phase, b, e);
+    cudaMemsetAsync(grads + b, 0, sizeof(float) * size_t(e - b), st);
+  }
+
+  void backward(const float* d_mu, const float* d_lv, const float* d_enc, const float* d_recon, int phases) {
+    if (phases & MMVAE_BWD_DECODER) {
+      clear(MMVAE_BWD_DECODER);
+      if (d_recon) {
+        const ConvT_& t = P.convs[P.tail];
+        const float* dr = d_recon;
+        if (t.Co > 1) {      // NCHW -> NHWC
+          launch_nchw_to_nhwc(d_recon, at<float>(P.drecon_off), P.d.batch, t.Co, t.Ho * t.Wo, st);
+          dr = at<float>(P.drecon_off);
+        }
+        bn_bwd(dr, 1, -1, t, nullptr);
+        wgrad(t);
+        // decoder.conv2.bias feeds a BatchNorm: its gradient is identically zero;
+        // the arena range was cleared above.
+        dgrad(t, 0);
+        for (int i = (int)P.dec.size() - 1; i >= 0; --i) block_bwd(P.dec[i]);
+        const ConvT_& s = P.convs[P.dstem];
+        bn_bwd(at<T>(act(P.a_dstem).goff), 0, P.a_dstem, s, nullptr);
+        wgrad(s);
+        dgrad(s, 0);
+      }
+    }
+    if (phases & MMVAE_BWD_ENC_DEEP) {
+      clear(MMVAE_BWD_ENC_DEEP);
+      HeadsBwdArgs h;
+      memset(&h, 0, sizeof(h));
+      h.dz_act = d_recon ? at<T>(act(P.a_z).goff) : nullptr;
+      h.d_mu = d_mu; h.d_lv = d_lv; h.d_enc = d_enc;
+      h.heads = at<float>(P.heads_off); h.pooled = at<float>(P.pooled_off);
+      h.w_mu = params + P.w_mu; h.w_lv = P.w_lv >= 0 ? params + P.w_lv : nullptr;
+      h.dheads = at<float>(P.dheads_off); h.dpool = at<float>(P.dpool_off);
+      h.g_wmu = grads + P.w_mu; h.g_wlv = P.w_lv >= 0 ? grads + P.w_lv : nullptr;
+      h.dfeat = at<T>(act(P.enc.back().out).goff);
+      h.N = P.d.batch; h.hw = P.feat_hw; h.C = P.feat_c; h.z = P.d.z_dim;
+      launch_heads_bwd<T>(h, st);
+      block_bwd(P.enc[3]);
+      block_bwd(P.enc[2]);
+    }
+    if (phases & MMVAE_BWD_ENC_SHALLOW) {
+      clear(MMVAE_BWD_ENC_SHALLOW);
+      block_bwd(P.enc[1]);
+      block_bwd(P.enc[0]);
+      const ConvT_& s = P.convs[P.stem];
+      bn_bwd(at<T>(act(P.a_stem).goff), 0, P.a_stem, s, nullptr);
+      wgrad(s);
+    }
+  }
+};
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace mmvae
+
+using namespace mmvae;
+
+extern "C" {
+
+int mmvae_abi_version(void) { return MMVAE_ABI_VERSION; }
+const char* mmvae_last_error(void) { return g_err; }
+
+int mmvae_layout(const mmvae_desc* d, mmvae_layout_info* out) {
+  Plan P;
+  if (!P.build(d)) return fail(MMVAE_ERR_BAD_DESC, "%s", P.err.c_str());
+  if (!out) return fail(MMVAE_ERR_BAD_ARG, "out is NULL");
+  out->n_params = P.n_params; out->n_bn_buffers = P.n_bn_buffers;
+  out->n_param_tensors = (int32_t)P.params.size(); out->n_bn = (int32_t)P.bns.size();
+  out->workspace_bytes = (int64_t)P.ws_bytes; out->decoder_size = P.dec_size; out->crop = P.crop;
+  out->train_flops = P.train_flops;
+  return 0;
+}
+
+int mmvae_param_entry(const mmvae_desc* d, int32_t i, char* name, size_t name_cap, int64_t* offset,
+                      int32_t* ndim, int32_t shape[4]) {
+  Plan P;
+  if (!P.build(d)) return fail(MMVAE_ERR_BAD_DESC, "%s", P.err.c_str());
+  if (i < 0 || i >= (int)P.params.size()) return fail(MMVAE_ERR_BAD_ARG, "parameter index %d out of range", i);
+  const ParamT& p = P.params[i];
+  if (name && name_cap) { strncpy(name, p.name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+  if (offset) *offset = p.off;
+  if (ndim) *ndim = p.ndim;
+  if (shape) for (int k = 0; k < 4; ++k) shape[k] = p.shape[k];
+  return 0;
+}
+
+int mmvae_bn_entry(const mmvae_desc* d, int32_t i, char* prefix, size_t prefix_cap, int32_t* channels,
+                   int64_t* buffer_offset) {
+  Plan P;
+  if (!P.build(d)) return fail(MMVAE_ERR_BAD_DESC, "%s", P.err.c_str());
+  if (i < 0 || i >= (int)P.bns.size()) return fail(MMVAE_ERR_BAD_ARG, "BatchNorm index %d out of range", i);
+  const BnT& b = P.bns[i];
+  if (prefix && prefix_cap) { strncpy(prefix, b.prefix.c_str(), prefix_cap - 1); prefix[prefix_cap - 1] = 0; }
+  if (channels) *channels = b.C;
+  if (buffer_offset) *buffer_offset = b.rm;
+  return 0;
+}
+
+int mmvae_workspace_tensor(const mmvae_desc* d, const char* name, int64_t* byte_offset, int32_t dims[4]) {
+  Plan P;
+  if (!P.build(d)) return fail(MMVAE_ERR_BAD_DESC, "%s", P.err.c_str());
+  if (!name) return fail(MMVAE_ERR_BAD_ARG, "name is NULL");
+  std::string nm(name);
+  bool grad = false;
+  if (nm.size() > 5 && nm.compare(nm.size() - 5, 5, ".grad") == 0) { grad = true; nm.resize(nm.size() - 5); }
+  const ActT* a = P.find_act(nm.c_str());
+  if (!a) return fail(MMVAE_ERR_BAD_ARG, "no workspace tensor named '%s'", name);
+  if (byte_offset) *byte_offset = (int64_t)(grad ? a->goff : a->off);
+  if (dims) { dims[0] = P.d.batch; dims[1] = a->H; dims[2] = a->W; dims[3] = a->C; }
+  return 0;
+}
+
+#define MMVAE_COMMON_CHECKS()                                                                   \
+  Plan P;                                                                                       \
+  if (!P.build(d)) return fail(MMVAE_ERR_BAD_DESC, "%s", P.err.c_str());                        \
+  if (int rc = check_device()) return rc;                                                       \
+  if (!workspace || workspace_bytes < P.ws_bytes)                                               \
+    return fail(MMVAE_ERR_BAD_ARG, "workspace too small: %zu < %zu bytes", workspace_bytes, P.ws_bytes); \
+  if (!aligned16(workspace)) return fail(MMVAE_ERR_BAD_ARG, "workspace must be 16-byte aligned");
+
+int mmvae_forward(const mmvae_desc* d, const float* x, const float* params, float* bn_buffers,
+                  int64_t* bn_counters, const float* eps, uint64_t seed, uint64_t offset, float* eps_out,
+                  void* workspace, size_t workspace_bytes, float* mu, float* logvar, float* encoding,
+                  float* recon, void* stream) {
+  MMVAE_COMMON_CHECKS();
+  if (!x || !params || !mu || !encoding || !recon) return fail(MMVAE_ERR_BAD_ARG, "x/params/mu/encoding/recon must be non-NULL");
+  if (d->require_rsample && !logvar) return fail(MMVAE_ERR_BAD_ARG, "logvar must be non-NULL when require_rsample");
+  if (!bn_buffers) return fail(MMVAE_ERR_BAD_ARG, "bn_buffers must be non-NULL");
+  if (!aligned16(params) || !aligned16(x)) return fail(MMVAE_ERR_BAD_ARG, "x and params must be 16-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (P.d.precision == MMVAE_PREC_FP32) {
+    Exec<float> E{P, (char*)workspace, params, nullptr, bn_buffers, (long long*)bn_counters, st, x};
+    if (!P.d.training) { E.counters = nullptr; }
+    E.encode(eps, seed, offset, eps_out, mu, logvar, encoding);
+    E.decode(recon);
+  } else {
+    Exec<__nv_bfloat16> E{P, (char*)workspace, params, nullptr, bn_buffers, (long long*)bn_counters, st, x};
+    if (!P.d.training) { E.counters = nullptr; }
+    E.encode(eps, seed, offset, eps_out, mu, logvar, encoding);
+    E.decode(recon);
+  }
+  return check_launches("mmvae_forward");
+}
+
+int mmvae_decode(const mmvae_desc* d, const float* encoding, const float* params, float* bn_buffers,
+                 int64_t* bn_counters, void* workspace, size_t workspace_bytes, float* recon, void* stream) {
+  MMVAE_COMMON_CHECKS();
+  if (!encoding || !params || !recon || !bn_buffers) return fail(MMVAE_ERR_BAD_ARG, "encoding/params/bn_buffers/recon must be non-NULL");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const long long nz = (long long)P.d.batch * P.d.z_dim;
+  if (P.d.precision == MMVAE_PREC_FP32) {
+    Exec<float> E{P, (char*)workspace, params, nullptr, bn_buffers, (long long*)bn_counters, st, nullptr};
+    if (!P.d.training) E.counters = nullptr;
+    launch_cast_latent<float>(encoding, E.at<float>(P.acts[P.a_z].off), nz, st);
+    E.decode(recon);
+  } else {
+    Exec<__nv_bfloat16> E{P, (char*)workspace, params, nullptr, bn_buffers, (long long*)bn_counters, st, nullptr};
+    if (!P.d.training) E.counters = nullptr;
+    launch_cast_latent<__nv_bfloat16>(encoding, E.at<__nv_bfloat16>(P.acts[P.a_z].off), nz, st);
+    E.decode(recon);
+  }
+  return check_launches("mmvae_decode");
+}
+
+int mmvae_backward(const mmvae_desc* d, const float* x, const float* params, void* workspace,
+                   size_t workspace_bytes, const float* d_mu, const float* d_logvar, const float* d_encoding,
+                   const float* d_recon, float* grads, int32_t phases, void* stream) {
+  MMVAE_COMMON_CHECKS();
+  if (!x || !params || !grads) return fail(MMVAE_ERR_BAD_ARG, "x/params/grads must be non-NULL");
+  if (phases <= 0 || phases > MMVAE_BWD_ALL) return fail(MMVAE_ERR_BAD_ARG, "phases must be a non-empty MMVAE_BWD_* mask");
+  if (!d->training) return fail(MMVAE_ERR_BAD_DESC, "mmvae_backward needs a training-mode forward (batch statistics)");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (P.d.precision == MMVAE_PREC_FP32) {
+    Exec<float> E{P, (char*)workspace, params, grads, nullptr, nullptr, st, x};
+    E.backward(d_mu, d_logvar, d_encoding, d_recon, phases);
+  } else {
+    Exec<__nv_bfloat16> E{P, (char*)workspace, params, grads, nullptr, nullptr, st, x};
+    E.backward(d_mu, d_logvar, d_encoding, d_recon, phases);
+  }
+  return check_launches("mmvae_backward");
+}
+
+int mmvae_backward_range(const mmvae_desc* d, int32_t phase, int64_t* begin, int64_t* end) {
+  Plan P;
+  if (!P.build(d)) return fail(MMVAE_ERR_BAD_DESC, "%s", P.err.c_str());
+  if (phase != MMVAE_BWD_DECODER && phase != MMVAE_BWD_ENC_DEEP && phase != MMVAE_BWD_ENC_SHALLOW)
+    return fail(MMVAE_ERR_BAD_ARG, "phase must be a single MMVAE_BWD_* value");
+  int64_t b, e;
+  Exec<float>::phase_range(P, phase, b, e);
+  if (begin) *begin = b;
+  if (end) *end = e;
+  return 0;
+}
+
+size_t mmvae_loss_scratch_bytes(void) { return loss_scratch_bytes(); }
+
+static int loss_args_check(const mmvae_loss_args* a, LossArgs& L) {
+  if (!a || a->struct_size != (int32_t)sizeof(mmvae_loss_args)) return fail(MMVAE_ERR_BAD_ARG, "mmvae_loss_args.struct_size mismatch");
+  if (a->kind != MMVAE_LOSS_GAUSSIAN && a->kind != MMVAE_LOSS_CATEGORICAL) return fail(MMVAE_ERR_BAD_ARG, "unknown loss kind");
+  if (a->batch < 1 || a->channels < 1 || a->height < 1 || a->width < 1) return fail(MMVAE_ERR_BAD_ARG, "bad loss shape");
+  if (a->kind == MMVAE_LOSS_GAUSSIAN && !(a->sigma > 0.f)) return fail(MMVAE_ERR_BAD_ARG, "sigma_decoder must be > 0 (main.py:91-93)");
+  L.kind = a->kind; L.nll = a->nll; L.kl = a->kl; L.sigma = a->sigma;
+  L.N = a->batch; L.C = a->channels; L.H = a->height; L.W = a->width; L.z = a->z_dim;
+  return 0;
+}
+
+int mmvae_loss_forward(const mmvae_loss_args* a, const float* recon, const void* target, const float* ce_weight,
+                       const float* mu, const float* logvar, float* out, void* scratch, void* stream) {
+  LossArgs L;
+  if (int rc = loss_args_check(a, L)) return rc;
+  if (int rc = check_device()) return rc;
+  if (!out || !scratch) return fail(MMVAE_ERR_BAD_ARG, "out/scratch must be non-NULL");
+  if ((recon == nullptr) != (target == nullptr)) return fail(MMVAE_ERR_BAD_ARG, "recon and target must both be given or both be NULL (KL only)");
+  if (!aligned16(recon) || !aligned16(target)) return fail(MMVAE_ERR_BAD_ARG, "recon and target must be 16-byte aligned");
+  launch_loss_fwd(L, recon, target, ce_weight, mu, logvar, out, scratch, reinterpret_cast<cudaStream_t>(stream));
+  return check_launches("mmvae_loss_forward");
+}
+
+int mmvae_loss_backward(const mmvae_loss_args* a, const float* recon, const void* target, const float* ce_weight,
+                        const float* mu, const float* logvar, const float* grad_out, float* d_recon, float* d_mu,
+                        float* d_logvar, void* stream) {
+  LossArgs L;
+  if (int rc = loss_args_check(a, L)) return rc;
+  if (int rc = check_device()) return rc;
+  if (!grad_out) return fail(MMVAE_ERR_BAD_ARG, "grad_out must be non-NULL");
+  if (d_recon && (!recon || !target)) return fail(MMVAE_ERR_BAD_ARG, "d_recon needs recon and target");
+  if (!aligned16(recon) || !aligned16(target) || (d_recon && !aligned16(d_recon)))
+    return fail(MMVAE_ERR_BAD_ARG, "recon, target and d_recon must be 16-byte aligned");
+  launch_loss_bwd(L, recon, target, ce_weight, mu, logvar, grad_out, d_recon, d_mu, d_logvar,
+                  reinterpret_cast<cudaStream_t>(stream));
+  return check_launches("mmvae_loss_backward");
+}
+
+int mmvae_philox_normal(uint64_t seed, uint64_t offset, int64_t n, float* out, void* stream) {
+  if (int rc = check_device()) return rc;
+  if (!out || n < 0) return fail(MMVAE_ERR_BAD_ARG, "bad arguments");
+  launch_philox_normal(seed, offset, n, out, reinterpret_cast<cudaStream_t>(stream));
+  return check_launches("mmvae_philox_normal");
+}
+
+int mmvae_adam_step(int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float lr,
+                    float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
+                    void* stream) {
+  if (int rc = check_device()) return rc;
+  if (!params || !grads || !exp_avg || !exp_avg_sq || n < 0 || step < 1) return fail(MMVAE_ERR_BAD_ARG, "bad arguments");
+  launch_adam(n, params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale,
+              reinterpret_cast<cudaStream_t>(stream));
+  return check_launches("mmvae_adam_step");
+}
+
+}  // extern "C"

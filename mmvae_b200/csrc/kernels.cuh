@@ -1,0 +1,173 @@
+// kernels.cuh -- launch descriptors and launcher prototypes shared by the .cu files.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace mmvae {
+
+constexpr int kMaxTaps = 25;   // 5x5 stem conv
+constexpr int kMaxVar = 4;     // output-parity variants of a stride-2 transposed conv / dgrad
+
+// One output-parity variant of a gather-convolution.
+struct GVar {
+  int oy0, ox0;                // out y = oy0 + os * i
+  int ntaps;
+  int wofs[kMaxTaps];          // weight offset of the tap inside the reference-layout weight tensor
+  signed char dy[kMaxTaps];    // in y = is * i + dy
+  signed char dx[kMaxTaps];
+};
+
+// Gather-convolution: every conv / transposed conv / dgrad of the model is an instance.
+//   out[n, oy0+os*i, ox0+os*j, co] (+)= bias[co] + sum_t sum_ci in[n, is*i+dy_t, is*j+dx_t, ci] * W[wofs_t + ci*w_sci + co*w_sco]
+// for i < Hg, j < Wg; out-of-range input coordinates read as zero.
+// GEMM view: M = N*Hg*Wg rows, Co columns, K = ntaps*Ci.
+struct GConvParams {
+  const void* in;              // NHWC [N,Hi,Wi,Ci], storage type -- or fp32 NCHW when in_nchw_f32
+  void* out;                   // NHWC [N,Ho,Wo,Co], storage type
+  const float* w;              // fp32 weight tensor in the reference layout
+  const float* bias;           // fp32 [Co] or nullptr
+  float* partials;             // fp32 [nvar*gridM][Co][2] per-CTA (sum, sum of squares) or nullptr
+  int N, Hi, Wi, Ci, Ho, Wo, Co;
+  int Hg, Wg, M;
+  int os, is;
+  int w_sci, w_sco;
+  int nvar;
+  int accumulate;              // out += result
+  int in_nchw_f32;             // network input x: fp32 NCHW
+  GVar var[kMaxVar];
+};
+
+// Weight gradient of a gather-convolution: dW[wofs_t + ci*w_sci + co*w_sco] += sum_m in(m,t,ci) * dout(m,co)
+struct WGradParams {
+  const void* in;              // layer input activation (or fp32 NCHW x)
+  const void* dout;            // dY, NHWC [N,Ho,Wo,Co], storage type
+  float* dw;                   // gradient arena + weight offset (fp32, atomically accumulated; pre-zeroed)
+  int N, Hi, Wi, Ci, Ho, Wo, Co;
+  int Hg, Wg, M;
+  int os, is;
+  int w_sci, w_sco;
+  int nvar, nsplit, rows_per_split;
+  int in_nchw_f32;
+  GVar var[kMaxVar];
+};
+
+template <typename T> int launch_gconv_simt(const GConvParams& p, cudaStream_t st);
+template <typename T> void launch_wgrad_simt(const WGradParams& p, cudaStream_t st);
+
+// ---- pointwise / reduction kernels (pointwise.cu) ----
+struct BnFinalizeArgs {
+  const float* partials; int P; int C; long long m;
+  const float* gamma; const float* beta;
+  float* running_mean; float* running_var; long long* counter;   // nullptr when not updating
+  float* stat;    // [2][C] mean, rstd
+  float* coef;    // [2][C] scale, shift
+  int training;   // 0: use running stats
+};
+void launch_bn_finalize(const BnFinalizeArgs& a, cudaStream_t st);
+
+// a = act( y*scale+shift [+ y2*scale2+shift2] ), NHWC, rows x C
+template <typename T>
+void launch_bn_apply(const T* y, const float* coef, const T* y2, const float* coef2, T* out,
+                     long long rows, int C, int relu, cudaStream_t st);
+// recon (fp32 NCHW) = y*scale+shift from NHWC storage
+template <typename T>
+void launch_bn_apply_out(const T* y, const float* coef, float* out_nchw, int N, int HW, int C, cudaStream_t st);
+
+struct HeadsArgs {
+  const void* feat;        // encoder output activation NHWC [N,hw,C]
+  const float* w_mu; const float* w_lv;   // [z][C] fp32 (w_lv may be nullptr)
+  const float* eps;        // [N][z] or nullptr -> Philox
+  unsigned long long seed, offset;
+  float* pooled;           // [N][C]
+  float* heads;            // [4][N][z]: mu, logvar, eps, std
+  float* mu_out; float* lv_out; float* enc_out; float* eps_out;   // user-visible fp32 outputs
+  void* z_act;             // decoder input activation [N][z] storage type
+  int N, hw, C, z;
+};
+template <typename T> void launch_heads_fwd(const HeadsArgs& a, cudaStream_t st);
+template <typename T> void launch_cast_latent(const float* enc, T* z_act, long long n, cudaStream_t st);
+
+struct HeadsBwdArgs {
+  const void* dz_act;      // gradient wrt decoder input [N][z] storage type (or nullptr)
+  const float* d_mu; const float* d_lv; const float* d_enc;   // incoming user grads or nullptr
+  const float* heads;      // [4][N][z]
+  const float* pooled;     // [N][C]
+  const float* w_mu; const float* w_lv;
+  float* dheads;           // [3][N][z] scratch: dmu, dlogvar
+  float* dpool;            // [N][C]
+  float* g_wmu; float* g_wlv;   // gradient arena slots
+  void* dfeat;             // gradient wrt encoder output activation NHWC [N,hw,C] storage type
+  int N, hw, C, z;
+};
+template <typename T> void launch_heads_bwd(const HeadsBwdArgs& a, cudaStream_t st);
+
+// BatchNorm backward.  g = dA * [a > 0] (mask from the block output when relu), per channel:
+//   S0 = sum g, S1 = sum g*xhat(y), S2 = sum g*xhat(y2)
+struct BnBwdArgs {
+  const void* dA;          // incoming gradient NHWC storage type (or fp32 when dA_f32)
+  const void* a;           // activation output for the ReLU mask, or nullptr (no ReLU)
+  const void* y;  const float* stat;  const float* gamma;           // main branch
+  const void* y2; const float* stat2; const float* gamma2;          // second branch or nullptr
+  float* partials;         // [blocks][C][3]
+  float* bcoef; float* bcoef2;       // [3][C]: scale, c1, c2
+  float* g_gamma; float* g_beta; float* g_gamma2; float* g_beta2;   // gradient arena slots
+  void* dY; void* dY2;     // outputs, storage type
+  long long rows; int C;
+  int dA_f32;
+};
+template <typename T> void launch_bn_bwd(const BnBwdArgs& a, cudaStream_t st);
+
+// NCHW fp32 -> NHWC fp32 (d_recon with more than one channel)
+void launch_nchw_to_nhwc(const float* in, float* out, int N, int C, int HW, cudaStream_t st);
+
+// ---- loss (loss.cu) ----
+struct LossArgs {
+  int kind; float nll, kl, sigma; int N, C, H, W, z;
+};
+size_t loss_scratch_bytes();
+void launch_loss_fwd(const LossArgs& a, const float* recon, const void* target, const float* w,
+                     const float* mu, const float* lv, float* out, void* scratch, cudaStream_t st);
+void launch_loss_bwd(const LossArgs& a, const float* recon, const void* target, const float* w,
+                     const float* mu, const float* lv, const float* gout,
+                     float* d_recon, float* d_mu, float* d_lv, cudaStream_t st);
+void launch_philox_normal(unsigned long long seed, unsigned long long offset, long long n, float* out, cudaStream_t st);
+void launch_adam(long long n, float* p, const float* g, float* m, float* v, float lr, float b1, float b2,
+                 float eps, float wd, long long step, float gscale, cudaStream_t st);
+
+// ---- device helpers ----
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// Philox4x32-10 (Salmon et al. 2011), counter = (c0,c1,0,0), key = (k0,k1)
+__device__ __forceinline__ void philox4x32_10(unsigned long long ctr, unsigned long long key, unsigned int out[4]) {
+  unsigned int c0 = (unsigned int)ctr, c1 = (unsigned int)(ctr >> 32), c2 = 0u, c3 = 0u;
+  unsigned int k0 = (unsigned int)key, k1 = (unsigned int)(key >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    unsigned int hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    unsigned int hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    unsigned int n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// element i of the stream: Box-Muller on the uniform pair (2*(i%2)... ) of counter i/4... see philox_normal_at
+__device__ __forceinline__ float philox_normal_at(unsigned long long seed, unsigned long long offset, long long i) {
+  unsigned int r[4];
+  philox4x32_10(offset + (unsigned long long)(i >> 2), seed, r);
+  int pair = (int)((i >> 1) & 1);
+  // uniforms in (0,1]: (u + 1) * 2^-32 keeps log() finite
+  float u1 = ((float)r[2 * pair] + 1.0f) * 2.3283064365386963e-10f;
+  float u2 = ((float)r[2 * pair + 1] + 1.0f) * 2.3283064365386963e-10f;
+  u1 = fminf(u1, 1.0f);
+  float rad = sqrtf(-2.0f * logf(u1));
+  float ang = 6.283185307179586f * u2;
+  return (i & 1) ? rad * sinf(ang) : rad * cosf(ang);
+}
+
+}  // namespace mmvae

@@ -1,0 +1,448 @@
+// pointwise.cu -- BatchNorm statistics / apply / backward, encoder heads + rsample, layout helpers.
+//
+// BatchNorm2d training semantics (reference constructs nn.BatchNorm2d with defaults at
+// model.py:30,34,61,66,95,137,162,173,202): biased batch variance for normalisation, running
+// buffers updated with momentum 0.1 and the unbiased variance, num_batches_tracked += 1.
+// The per-channel sums come from the producing conv's epilogue as per-CTA partials and are
+// combined here in a fixed order in fp64, so a step is bit-reproducible.
+#include "kernels.cuh"
+
+namespace mmvae {
+
+namespace {
+
+constexpr float kBnEps = 1e-5f;
+constexpr float kBnMomentum = 0.1f;
+
+template <int NT>
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+  const int tid = threadIdx.x;
+  sh[tid] = v;
+  __syncthreads();
+#pragma unroll
+  for (int s = NT / 2; s > 0; s >>= 1) {
+    if (tid < s) sh[tid] += sh[tid + s];
+    __syncthreads();
+  }
+  double r = sh[0];
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(128) bn_finalize_kernel(const BnFinalizeArgs a) {
+  __shared__ double sh[128];
+  const int c = blockIdx.x;
+  float mean, var;
+  if (a.training) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int i = threadIdx.x; i < a.P; i += 128) {
+      s1 += (double)a.partials[(size_t(i) * a.C + c) * 2 + 0];
+      s2 += (double)a.partials[(size_t(i) * a.C + c) * 2 + 1];
+    }
+    s1 = block_sum<128>(s1, sh);
+    s2 = block_sum<128>(s2, sh);
+    double mu = s1 / (double)a.m;
+    double vv = s2 / (double)a.m - mu * mu;
+    if (vv < 0.0) vv = 0.0;
+    mean = (float)mu; var = (float)vv;
+    if (threadIdx.x == 0 && a.running_mean) {
+      double unb = a.m > 1 ? vv * ((double)a.m / (double)(a.m - 1)) : vv;
+      a.running_mean[c] = (1.f - kBnMomentum) * a.running_mean[c] + kBnMomentum * mean;
+      a.running_var[c] = (1.f - kBnMomentum) * a.running_var[c] + kBnMomentum * (float)unb;
+      if (c == 0 && a.counter) *a.counter += 1;
+    }
+  } else {
+    mean = a.running_mean[c]; var = a.running_var[c];
+  }
+  if (threadIdx.x == 0) {
+    float rstd = 1.0f / sqrtf(var + kBnEps);
+    a.stat[c] = mean; a.stat[a.C + c] = rstd;
+    float scale = a.gamma[c] * rstd;
+    a.coef[c] = scale; a.coef[a.C + c] = a.beta[c] - mean * scale;
+  }
+}
+
+template <typename T, int VEC> struct Vec;
+template <> struct Vec<float, 4> { using type = float4; };
+template <> struct Vec<float, 1> { using type = float; };
+template <> struct Vec<__nv_bfloat16, 8> { using type = uint4; };
+template <> struct Vec<__nv_bfloat16, 1> { using type = __nv_bfloat16; };
+
+template <typename T, int VEC>
+__device__ __forceinline__ void load_vec(const T* p, float (&f)[VEC]) {
+  typename Vec<T, VEC>::type raw = *reinterpret_cast<const typename Vec<T, VEC>::type*>(p);
+  const T* e = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) f[i] = to_f(e[i]);
+}
+template <typename T, int VEC>
+__device__ __forceinline__ void store_vec(T* p, const float (&f)[VEC]) {
+  typename Vec<T, VEC>::type raw;
+  T* e = reinterpret_cast<T*>(&raw);
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) e[i] = from_f<T>(f[i]);
+  *reinterpret_cast<typename Vec<T, VEC>::type*>(p) = raw;
+}
+
+// incoming gradient: storage type, or fp32 (the user-facing d_recon)
+template <typename T, int VEC>
+__device__ __forceinline__ void load_grad(const void* dA, int is_f32, size_t off, float (&g)[VEC]) {
+  if (is_f32) {
+    const float* p = reinterpret_cast<const float*>(dA) + off;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) g[k] = p[k];
+  } else {
+    load_vec<T, VEC>(reinterpret_cast<const T*>(dA) + off, g);
+  }
+}
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ y, const float* __restrict__ coef,
+                                                       const T* __restrict__ y2, const float* __restrict__ coef2,
+                                                       T* __restrict__ out, long long nvec, int C, int relu) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < nvec; i += gridDim.x * 256LL) {
+    int c0 = (int)((i * VEC) % C);
+    float v[VEC], r[VEC];
+    load_vec<T, VEC>(y + i * VEC, v);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) r[k] = fmaf(v[k], __ldg(coef + c0 + k), __ldg(coef + C + c0 + k));
+    if (y2) {
+      load_vec<T, VEC>(y2 + i * VEC, v);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) r[k] += fmaf(v[k], __ldg(coef2 + c0 + k), __ldg(coef2 + C + c0 + k));
+    }
+    if (relu) {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) r[k] = fmaxf(r[k], 0.f);
+    }
+    store_vec<T, VEC>(out + i * VEC, r);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_apply_out_kernel(const T* __restrict__ y, const float* __restrict__ coef,
+                                                           float* __restrict__ out, long long total, int HW, int C) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
+    int hw = (int)(i % HW); long long t = i / HW; int c = (int)(t % C); long long n = t / C;
+    float v = to_f(y[(n * HW + hw) * C + c]);
+    out[i] = fmaf(v, __ldg(coef + c), __ldg(coef + C + c));
+  }
+}
+
+// ---------------- encoder heads: avg-pool + two 1x1 convs + rsample (model.py:123-128,148-150) ----------
+template <typename T>
+__global__ void __launch_bounds__(128) heads_fwd_kernel(const HeadsArgs a) {
+  extern __shared__ float sm[];          // pooled[C] then out[2z]
+  float* pooled = sm;
+  float* outv = sm + a.C;
+  const int n = blockIdx.x, tid = threadIdx.x;
+  const T* feat = reinterpret_cast<const T*>(a.feat) + size_t(n) * a.hw * a.C;
+  const float inv = 1.0f / (float)a.hw;
+  for (int c = tid; c < a.C; c += 128) {
+    float s = 0.f;
+    for (int p = 0; p < a.hw; ++p) s += to_f(feat[size_t(p) * a.C + c]);
+    s *= inv;
+    pooled[c] = s;
+    a.pooled[size_t(n) * a.C + c] = s;
+  }
+  __syncthreads();
+  const int nout = a.w_lv ? 2 * a.z : a.z;
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int o = warp; o < nout; o += 4) {
+    const float* w = (o < a.z) ? a.w_mu + size_t(o) * a.C : a.w_lv + size_t(o - a.z) * a.C;
+    float s = 0.f;
+    for (int c = lane; c < a.C; c += 32) s = fmaf(__ldg(w + c), pooled[c], s);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if (lane == 0) outv[o] = s;
+  }
+  __syncthreads();
+  const size_t NZ = size_t(a.N) * a.z;
+  for (int zc = tid; zc < a.z; zc += 128) {
+    size_t idx = size_t(n) * a.z + zc;
+    float mu = outv[zc];
+    float lv = 0.f, eps = 0.f, sd = 0.f, enc = mu;
+    if (a.w_lv) {
+      lv = outv[a.z + zc];
+      eps = a.eps ? a.eps[idx] : philox_normal_at(a.seed, a.offset, (long long)idx);
+      sd = expf(0.5f * lv);
+      enc = fmaf(eps, sd, mu);
+    }
+    a.heads[idx] = mu; a.heads[NZ + idx] = lv; a.heads[2 * NZ + idx] = eps; a.heads[3 * NZ + idx] = sd;
+    a.mu_out[idx] = mu;
+    if (a.lv_out) a.lv_out[idx] = lv;
+    a.enc_out[idx] = enc;
+    if (a.eps_out) a.eps_out[idx] = eps;
+    reinterpret_cast<T*>(a.z_act)[idx] = from_f<T>(enc);
+  }
+}
+
+template <typename T>
+__global__ void cast_latent_kernel(const float* __restrict__ in, T* __restrict__ out, long long n) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += gridDim.x * 256LL) out[i] = from_f<T>(in[i]);
+}
+
+// dz -> (dmu, dlogvar) -> dpooled -> d(encoder output)
+template <typename T>
+__global__ void __launch_bounds__(128) heads_bwd_kernel(const HeadsBwdArgs a) {
+  extern __shared__ float sm[];          // dmu[z], dlv[z]
+  float* dmu = sm; float* dlv = sm + a.z;
+  const int n = blockIdx.x, tid = threadIdx.x;
+  const size_t NZ = size_t(a.N) * a.z;
+  for (int zc = tid; zc < a.z; zc += 128) {
+    size_t idx = size_t(n) * a.z + zc;
+    float dz = 0.f;
+    if (a.dz_act) dz += to_f(reinterpret_cast<const T*>(a.dz_act)[idx]);
+    if (a.d_enc) dz += a.d_enc[idx];
+    float gm = dz + (a.d_mu ? a.d_mu[idx] : 0.f);
+    float gl = a.d_lv ? a.d_lv[idx] : 0.f;
+    if (a.w_lv) gl += dz * 0.5f * a.heads[2 * NZ + idx] * a.heads[3 * NZ + idx];   // dz * 0.5 * eps * std
+    dmu[zc] = gm; dlv[zc] = gl;
+    a.dheads[idx] = gm; a.dheads[NZ + idx] = gl;
+  }
+  __syncthreads();
+  T* dfeat = reinterpret_cast<T*>(a.dfeat) + size_t(n) * a.hw * a.C;
+  const float inv = 1.0f / (float)a.hw;
+  for (int c = tid; c < a.C; c += 128) {
+    float s = 0.f;
+    for (int zc = 0; zc < a.z; ++zc) {
+      s = fmaf(dmu[zc], __ldg(a.w_mu + size_t(zc) * a.C + c), s);
+      if (a.w_lv) s = fmaf(dlv[zc], __ldg(a.w_lv + size_t(zc) * a.C + c), s);
+    }
+    a.dpool[size_t(n) * a.C + c] = s;
+    T v = from_f<T>(s * inv);
+    for (int p = 0; p < a.hw; ++p) dfeat[size_t(p) * a.C + c] = v;
+  }
+}
+
+// dW_head[zc][c] = sum_n dhead[n][zc] * pooled[n][c]
+__global__ void __launch_bounds__(128) heads_wgrad_kernel(const float* __restrict__ dh, const float* __restrict__ pooled,
+                                                          float* __restrict__ gw, int N, int z, int C) {
+  const int zc = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += 128) {
+    float s = 0.f;
+    for (int n = 0; n < N; ++n) s = fmaf(dh[size_t(n) * z + zc], pooled[size_t(n) * C + c], s);
+    gw[size_t(zc) * C + c] = s;
+  }
+}
+
+// ---------------- BatchNorm backward ----------------
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
+  __shared__ float red[256 * VEC * 3];
+  const int CV = a.C / VEC;
+  const int RPI = 256 / CV;              // rows per iteration (CV <= 256 guaranteed by the launcher)
+  const int tid = threadIdx.x;
+  const int cv = tid % CV, rsub = tid / CV;
+  const bool active = rsub < RPI;
+  float s0[VEC], s1[VEC], s2[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) { s0[k] = s1[k] = s2[k] = 0.f; }
+  const int c0 = cv * VEC;
+  float mean[VEC], rstd[VEC], mean2[VEC], rstd2[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    mean[k] = a.stat[c0 + k]; rstd[k] = a.stat[a.C + c0 + k];
+    mean2[k] = a.y2 ? a.stat2[c0 + k] : 0.f; rstd2[k] = a.y2 ? a.stat2[a.C + c0 + k] : 0.f;
+  }
+  if (active) {
+    for (long long r = (long long)blockIdx.x * RPI + rsub; r < a.rows; r += (long long)gridDim.x * RPI) {
+      size_t off = size_t(r) * a.C + c0;
+      float g[VEC], yv[VEC];
+      load_grad<T, VEC>(a.dA, a.dA_f32, off, g);
+      if (a.a) {
+        float av[VEC];
+        load_vec<T, VEC>(reinterpret_cast<const T*>(a.a) + off, av);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) g[k] = av[k] > 0.f ? g[k] : 0.f;
+      }
+      load_vec<T, VEC>(reinterpret_cast<const T*>(a.y) + off, yv);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) { s0[k] += g[k]; s1[k] = fmaf(g[k], (yv[k] - mean[k]) * rstd[k], s1[k]); }
+      if (a.y2) {
+        load_vec<T, VEC>(reinterpret_cast<const T*>(a.y2) + off, yv);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) s2[k] = fmaf(g[k], (yv[k] - mean2[k]) * rstd2[k], s2[k]);
+      }
+    }
+  }
+  // red[which][rsub][c]
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      red[(0 * RPI + rsub) * a.C + c0 + k] = s0[k];
+      red[(1 * RPI + rsub) * a.C + c0 + k] = s1[k];
+      red[(2 * RPI + rsub) * a.C + c0 + k] = s2[k];
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < 3 * a.C; e += 256) {
+    int which = e / a.C, c = e % a.C;
+    float s = 0.f;
+    for (int q = 0; q < RPI; ++q) s += red[(which * RPI + q) * a.C + c];
+    a.partials[(size_t(blockIdx.x) * a.C + c) * 3 + which] = s;
+  }
+}
+
+__global__ void __launch_bounds__(128) bn_bwd_finalize_kernel(const BnBwdArgs a, int nblocks, long long m) {
+  __shared__ double sh[128];
+  const int c = blockIdx.x;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  for (int i = threadIdx.x; i < nblocks; i += 128) {
+    const float* p = a.partials + (size_t(i) * a.C + c) * 3;
+    s0 += (double)p[0]; s1 += (double)p[1]; s2 += (double)p[2];
+  }
+  s0 = block_sum<128>(s0, sh);
+  s1 = block_sum<128>(s1, sh);
+  s2 = block_sum<128>(s2, sh);
+  if (threadIdx.x == 0) {
+    const double im = 1.0 / (double)m;
+    a.g_beta[c] = (float)s0; a.g_gamma[c] = (float)s1;
+    a.bcoef[c] = a.gamma[c] * a.stat[a.C + c];
+    a.bcoef[a.C + c] = (float)(s0 * im);
+    a.bcoef[2 * a.C + c] = (float)(s1 * im);
+    if (a.y2) {
+      a.g_beta2[c] = (float)s0; a.g_gamma2[c] = (float)s2;
+      a.bcoef2[c] = a.gamma2[c] * a.stat2[a.C + c];
+      a.bcoef2[a.C + c] = (float)(s0 * im);
+      a.bcoef2[2 * a.C + c] = (float)(s2 * im);
+    }
+  }
+}
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a) {
+  const long long nvec = a.rows * a.C / VEC;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < nvec; i += gridDim.x * 256LL) {
+    const int c0 = (int)((i * VEC) % a.C);
+    const size_t off = size_t(i) * VEC;
+    float g[VEC], yv[VEC], o[VEC];
+    load_grad<T, VEC>(a.dA, a.dA_f32, off, g);
+    if (a.a) {
+      float av[VEC];
+      load_vec<T, VEC>(reinterpret_cast<const T*>(a.a) + off, av);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) g[k] = av[k] > 0.f ? g[k] : 0.f;
+    }
+    load_vec<T, VEC>(reinterpret_cast<const T*>(a.y) + off, yv);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      int c = c0 + k;
+      float xh = (yv[k] - __ldg(a.stat + c)) * __ldg(a.stat + a.C + c);
+      o[k] = __ldg(a.bcoef + c) * (g[k] - __ldg(a.bcoef + a.C + c) - xh * __ldg(a.bcoef + 2 * a.C + c));
+    }
+    store_vec<T, VEC>(reinterpret_cast<T*>(a.dY) + off, o);
+    if (a.y2) {
+      load_vec<T, VEC>(reinterpret_cast<const T*>(a.y2) + off, yv);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        int c = c0 + k;
+        float xh = (yv[k] - __ldg(a.stat2 + c)) * __ldg(a.stat2 + a.C + c);
+        o[k] = __ldg(a.bcoef2 + c) * (g[k] - __ldg(a.bcoef2 + a.C + c) - xh * __ldg(a.bcoef2 + 2 * a.C + c));
+      }
+      store_vec<T, VEC>(reinterpret_cast<T*>(a.dY2) + off, o);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                           long long total, int C, int HW) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
+    int c = (int)(i % C); long long t = i / C; int hw = (int)(t % HW); long long n = t / HW;
+    out[i] = in[(n * C + c) * HW + hw];
+  }
+}
+
+inline int grid_for(long long work_items, int per_block = 256, int cap = 148 * 8) {
+  long long b = (work_items + per_block - 1) / per_block;
+  if (b < 1) b = 1;
+  if (b > cap) b = cap;
+  return (int)b;
+}
+
+template <typename T> constexpr int vec_of() { return 16 / (int)sizeof(T); }
+
+}  // namespace
+
+void launch_bn_finalize(const BnFinalizeArgs& a, cudaStream_t st) {
+  bn_finalize_kernel<<<a.C, 128, 0, st>>>(a);
+}
+
+template <typename T>
+void launch_bn_apply(const T* y, const float* coef, const T* y2, const float* coef2, T* out,
+                     long long rows, int C, int relu, cudaStream_t st) {
+  constexpr int V = vec_of<T>();
+  if (C % V == 0) {
+    long long nvec = rows * C / V;
+    bn_apply_kernel<T, V><<<grid_for(nvec), 256, 0, st>>>(y, coef, y2, coef2, out, nvec, C, relu);
+  } else {
+    long long nvec = rows * C;
+    bn_apply_kernel<T, 1><<<grid_for(nvec), 256, 0, st>>>(y, coef, y2, coef2, out, nvec, C, relu);
+  }
+}
+
+template <typename T>
+void launch_bn_apply_out(const T* y, const float* coef, float* out_nchw, int N, int HW, int C, cudaStream_t st) {
+  long long total = (long long)N * HW * C;
+  bn_apply_out_kernel<T><<<grid_for(total), 256, 0, st>>>(y, coef, out_nchw, total, HW, C);
+}
+
+template <typename T>
+void launch_heads_fwd(const HeadsArgs& a, cudaStream_t st) {
+  size_t smem = sizeof(float) * (size_t(a.C) + 2 * size_t(a.z));
+  heads_fwd_kernel<T><<<a.N, 128, smem, st>>>(a);
+}
+
+template <typename T>
+void launch_cast_latent(const float* enc, T* z_act, long long n, cudaStream_t st) {
+  cast_latent_kernel<T><<<grid_for(n), 256, 0, st>>>(enc, z_act, n);
+}
+
+template <typename T>
+void launch_heads_bwd(const HeadsBwdArgs& a, cudaStream_t st) {
+  size_t smem = sizeof(float) * 2 * size_t(a.z);
+  heads_bwd_kernel<T><<<a.N, 128, smem, st>>>(a);
+  const size_t NZ = size_t(a.N) * a.z;
+  heads_wgrad_kernel<<<a.z, 128, 0, st>>>(a.dheads, a.pooled, a.g_wmu, a.N, a.z, a.C);
+  if (a.w_lv) heads_wgrad_kernel<<<a.z, 128, 0, st>>>(a.dheads + NZ, a.pooled, a.g_wlv, a.N, a.z, a.C);
+}
+
+template <typename T>
+void launch_bn_bwd(const BnBwdArgs& a, cudaStream_t st) {
+  constexpr int V = vec_of<T>();
+  const bool vec_ok = (a.C % V == 0) && (a.C / V <= 256);
+  int nblocks;
+  if (vec_ok) {
+    int rpi = 256 / (a.C / V);
+    nblocks = (int)((a.rows + rpi - 1) / rpi);
+  } else {
+    int rpi = a.C <= 256 ? 256 / a.C : 1;
+    nblocks = (int)((a.rows + rpi - 1) / rpi);
+  }
+  if (nblocks > 592) nblocks = 592;
+  if (nblocks < 1) nblocks = 1;
+  if (vec_ok) bn_bwd_reduce_kernel<T, V><<<nblocks, 256, 0, st>>>(a);
+  else bn_bwd_reduce_kernel<T, 1><<<nblocks, 256, 0, st>>>(a);
+  bn_bwd_finalize_kernel<<<a.C, 128, 0, st>>>(a, nblocks, a.rows);
+  long long total = a.rows * a.C;
+  if (a.C % V == 0) bn_bwd_apply_kernel<T, V><<<grid_for(total / V), 256, 0, st>>>(a);
+  else bn_bwd_apply_kernel<T, 1><<<grid_for(total), 256, 0, st>>>(a);
+}
+
+void launch_nchw_to_nhwc(const float* in, float* out, int N, int C, int HW, cudaStream_t st) {
+  long long total = (long long)N * C * HW;
+  nchw_to_nhwc_kernel<<<grid_for(total), 256, 0, st>>>(in, out, total, C, HW);
+}
+
+#define INST(T)                                                                                              \
+  template void launch_bn_apply<T>(const T*, const float*, const T*, const float*, T*, long long, int, int, cudaStream_t); \
+  template void launch_bn_apply_out<T>(const T*, const float*, float*, int, int, int, cudaStream_t);         \
+  template void launch_heads_fwd<T>(const HeadsArgs&, cudaStream_t);                                         \
+  template void launch_cast_latent<T>(const float*, T*, long long, cudaStream_t);                            \
+  template void launch_heads_bwd<T>(const HeadsBwdArgs&, cudaStream_t);                                      \
+  template void launch_bn_bwd<T>(const BnBwdArgs&, cudaStream_t);
+INST(float)
+INST(__nv_bfloat16)
+#undef INST
+
+}  // namespace mmvae

@@ -1,0 +1,145 @@
+"""GPU: parity of the CUDA path (through the drop-in module API -> C ABI) against the golden fixtures made
+from the live reference and against the CPU oracle.
+
+Tolerances (relative L2 per tensor):
+  * fp32 validation mode: north_star asks 1e-5, but the reference's OWN fp32 result sits 2.5e-5 (N=4) to
+    1.8e-4 (N=32) away from an fp64 evaluation of the same formulas (tests/test_oracle_golden.py),
+    so the test is two-sided: (a) against the reference fixture within 5e-4 (its own noise floor), and
+    (b) against the fp64 oracle no worse than 3x the reference-fp32's distance from fp64, floor 1e-5.
+  * bf16 mode: 1e-2 loss; gradients 2e-2 per tensor (bf16 activations through 60 layers), see DESIGN.md.
+"""
+import numpy as np
+import pytest
+import torch
+
+from golden_util import CASES, Golden, sample_idx
+from oracle import vae_oracle as O
+from ours_util import build_model, rel_l2, train_step, workspace_tensor
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_fp32_step_matches_reference_fixture(name):
+    g = Golden(name)
+    m = build_model(g.cfg, g.state(), "fp32")
+    res = train_step(m, g.cfg, g.x, g.target, g.eps, g.ce_weight)
+    g.check_step(res, rtol=5e-4)
+
+
+@pytest.mark.parametrize("name", ["base64_n4", "base64_n32"])
+def test_fp32_step_vs_fp64_oracle(name):
+    g = Golden(name)
+    st = g.state()
+    r64 = O.train_step(st, g.cfg, g.x, g.target, g.eps, ce_weight=g.ce_weight, dtype=torch.float64)
+    r32 = O.train_step(st, g.cfg, g.x, g.target, g.eps, ce_weight=g.ce_weight)
+    m = build_model(g.cfg, st, "fp32")
+    res = train_step(m, g.cfg, g.x, g.target, g.eps, g.ce_weight)
+    assert abs(res.loss - r64.loss) <= 1e-5 * abs(r64.loss)
+    worst_ours = worst_ref = 0.0
+    bad = []
+    for n, _ in O.param_specs(g.cfg):
+        if n == "decoder.conv2.bias":
+            continue
+        e_ours = rel_l2(res.grads[n], r64.grads[n])
+        e_ref = rel_l2(r32.grads[n], r64.grads[n])
+        worst_ours, worst_ref = max(worst_ours, e_ours), max(worst_ref, e_ref)
+        if e_ours > max(1e-5, 3 * e_ref):
+            bad.append((n, e_ours, e_ref))
+    print(f"{name}: worst grad rel-L2 vs fp64: ours {worst_ours:.2e}, torch-fp32 {worst_ref:.2e}")
+    assert not bad, bad[:10]
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_layer_activations_vs_oracle(prec):
+    """Every raw conv output and block output of the forward pass, layer by layer."""
+    g = Golden("base64_n4")
+    st = g.state()
+    mu, lv, enc, recon, ctx = O.forward(st, g.cfg, g.x, g.eps, training=True, keep_activations=True)
+    m = build_model(g.cfg, st, prec)
+    m.train(True)
+    with torch.no_grad():
+        m._run_forward(g.x.cuda(), g.eps.cuda(), training=True)
+    torch.cuda.synchronize()
+    tol = 1e-4 if prec == "fp32" else 3e-2
+    bad = []
+    for name, ref in ctx.acts.items():
+        got = workspace_tensor(m, g.x.shape[0], name)
+        e = rel_l2(got, ref)
+        if not e <= tol:
+            bad.append((name, e))
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("name", ["base64_n4", "base64_n32", "categorical2_n2", "crop28_n2"])
+def test_bf16_step_within_tolerance(name):
+    g = Golden(name)
+    st = g.state()
+    ref = O.train_step(st, g.cfg, g.x, g.target, g.eps, ce_weight=g.ce_weight, dtype=torch.float64)
+    m = build_model(g.cfg, st, "bf16")
+    res = train_step(m, g.cfg, g.x, g.target, g.eps, g.ce_weight)
+    assert abs(res.loss - ref.loss) <= 1e-2 * abs(ref.loss)
+    errs = {n: rel_l2(res.grads[n], ref.grads[n]) for n, _ in O.param_specs(g.cfg) if n != "decoder.conv2.bias"}
+    worst = max(errs.values())
+    print(f"{name}: bf16 worst grad rel-L2 {worst:.3e}; median {np.median(list(errs.values())):.3e}")
+    bad = {k: v for k, v in errs.items() if v > 2e-2}
+    assert not bad, sorted(bad.items(), key=lambda kv: -kv[1])[:10]
+    assert rel_l2(res.recon, ref.recon) <= 1e-2
+    assert rel_l2(res.mu, ref.mu) <= 2e-2
+
+
+def test_eval_mode_and_decoder_only():
+    g = Golden("base64_n4")
+    st = g.state()
+    # make the running statistics non-trivial
+    gen = torch.Generator().manual_seed(5)
+    for k in st:
+        if k.endswith("running_mean"):
+            st[k] = 0.1 * torch.randn(st[k].shape, generator=gen)
+        elif k.endswith("running_var"):
+            st[k] = 0.5 + torch.rand(st[k].shape, generator=gen)
+    mu, lv, enc, recon, _ = O.forward(st, g.cfg, g.x, g.eps, training=False)
+    m = build_model(g.cfg, st, "fp32")
+    m.eval()
+    with torch.no_grad():
+        mu2, lv2, enc2, recon2 = m(g.x.cuda(), eps=g.eps.cuda())
+        rec3 = m.get_reconstruction(enc.cuda())
+    assert rel_l2(mu2.cpu(), mu) < 1e-4 and rel_l2(recon2.cpu(), recon) < 1e-4
+    assert rel_l2(rec3.cpu(), recon) < 1e-4
+    # eval must not touch the buffers
+    sd = m.state_dict()
+    assert torch.equal(sd["encoder.bn1.running_mean"].cpu(), st["encoder.bn1.running_mean"])
+    assert int(sd["encoder.bn1.num_batches_tracked"]) == 0
+
+
+def test_philox_eps_is_reproducible_and_normal():
+    import mmvae_b200 as M
+    from ctypes import c_void_p
+    n = 1 << 16
+    a = torch.empty(n, device="cuda"); b = torch.empty(n, device="cuda")
+    s = c_void_p(torch.cuda.current_stream().cuda_stream)
+    M._lib.check(M._lib.lib.mmvae_philox_normal(1234, 0, n, c_void_p(a.data_ptr()), s))
+    M._lib.check(M._lib.lib.mmvae_philox_normal(1234, 0, n, c_void_p(b.data_ptr()), s))
+    assert torch.equal(a, b)
+    assert abs(a.mean().item()) < 0.02 and abs(a.std().item() - 1.0) < 0.02
+    # the module's own draw is exposed so the same noise can be fed to the reference
+    g = Golden("base64_n4")
+    m = build_model(g.cfg, g.state(), "fp32")
+    m.train(True)
+    mu, lv, enc, rec = m(g.x.cuda())
+    eps = m.last_eps
+    assert eps.shape == (4, 64, 1, 1)
+    assert rel_l2((mu + eps * torch.exp(0.5 * lv)).detach().cpu(), enc.detach().cpu()) < 1e-6
+
+
+def test_kl_weight_and_kl_divergence():
+    g = Golden("base64_n4")
+    m = build_model(g.cfg, g.state(), "fp32")
+    mu = torch.randn(4, 64, 1, 1, device="cuda", requires_grad=True)
+    lv = (0.3 * torch.randn(4, 64, 1, 1, device="cuda")).requires_grad_(True)
+    kl = m.kl_divergence(mu, lv)
+    want = O.kl_sum(mu.detach().cpu().double(), lv.detach().cpu().double())
+    assert abs(kl.item() - want.item()) <= 1e-5 * abs(want.item())
+    kl.backward()
+    assert rel_l2(mu.grad.cpu(), mu.detach().cpu()) < 1e-5                       # dKL/dmu = mu
+    assert rel_l2(lv.grad.cpu(), 0.5 * (torch.exp(lv.detach().cpu()) - 1)) < 1e-5
