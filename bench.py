@@ -1,0 +1,261 @@
+#!/usr/bin/env python
+"""bench.py -- train frames/sec (forward + loss + backward) of the VAE step on N B200s.
+
+    python bench.py --gpus 1 --steps 200 --warmup 20
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference's CPU train step on this box's host cores
+
+Workload (BASELINE.json configs[1]): the reference model.py VAE (z=64, 64x64, Gaussian NLL sigma=0.1),
+bf16, 256 frames per GPU of synthetic Moving-MNIST label maps (20-frame sequences flattened to frames),
+random-init weights.  N > 1 is weak scaling: 256 frames per GPU, gradients averaged over NVLink.
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PER_GPU_BATCH = 256
+TRAIN_MFLOP_PER_FRAME = 227.016704      # 2*MAC over every conv, fwd + dgrad + wgrad (mmvae_layout.train_flops)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1399.0), d.get("bf16_tflops", 1608.4), d.get("hbm_gbs", 6527.8), "measured"
+    return 1400.0, 1590.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake": 0x80}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def cpu_reference_fps(steps, warmup, batch=32):
+    """The reference's train step (forward -> loss -> backward, main.py:389-390,398) on the host cores.
+    /root/reference is not shipped to the GPU box, so this times the oracle port of it (oracle/vae_oracle.py:
+    same torch CPU conv kernels, BatchNorm / loss restated) -- kind 'port'."""
+    import torch
+    from oracle import vae_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = O.VAEConfig(input_image_size=64, z_dimension=64)
+    st = O.init_state(cfg, seed=0)
+    x = O.normalise(O.synthetic_labels(batch, 64))
+    eps = torch.randn(batch, 64, 1, 1, generator=torch.Generator().manual_seed(4321))
+    step = O.make_timed_step(st, cfg)
+    for _ in range(warmup):
+        step(x, x, eps)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step(x, x, eps)
+        times.append(time.perf_counter() - t0)
+    times.sort()
+    med = times[len(times) // 2]
+    return batch / med, med * 1e3, cores, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = min(args.steps, 30)
+    fps, ms, cores, threads = cpu_reference_fps(steps, min(args.warmup, 3))
+    line = {
+        "impl": "reference", "metric": "train frames/sec (fwd+bwd)", "value": fps, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 3), "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "model.py VAE z=64 64x64 Gaussian-NLL sigma=0.1, fwd+loss+bwd", "batch_per_step": 32},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                         "sample": f"{steps} steps of 32 frames on {cores} host cores (median), fp32"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="frames per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import types
+
+    import torch
+    import torch.distributed as dist
+
+    import mmvae_b200 as M
+    from mmvae_b200 import data as D
+    from mmvae_b200 import parallel as PAR
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.batch
+    torch.manual_seed(0)
+    model = M.VAE(1, 32, decoder_out_channels=1, pixelcnn_out_channels=0, z_dimension=64, pixelcnn=False,
+                  only_pixelcnn=False, nll=1, kl=1, mmd=0, sigma_decoder=0.1, input_image_size=64,
+                  precision=args.precision).to(dev).train()
+    model.defer_metrics = True
+    if world > 1:
+        PAR.data_parallel(model)
+    largs = types.SimpleNamespace(data_ratio_of_labels=None)
+
+    # several distinct batches per rank; the step's working set (activation workspace, ~0.5 GB at N=256)
+    # is streamed through once per step and is several times the 126 MB L2
+    n_batches = 4
+    labels_host = [D.synthetic_labels(n, 64, seed=1234 + 97 * rank + b).pin_memory() for b in range(n_batches)]
+    x_dev = [D.prepare_input(l.to(dev)) for l in labels_host]
+    ws_bytes = M._lib.layout(model._desc(n, True)).workspace_bytes
+    params = list(model.parameters())
+
+    def step_resident(i):
+        x = x_dev[i % n_batches]
+        mu, logvar, enc, recon = model(x)
+        loss, pxz, kl, _ = model.loss(x, mu, logvar, enc, recon, dev, largs)
+        for p in params:
+            p.grad = None                      # optimizer.zero_grad(), main.py:397
+        loss.backward()
+        return loss
+
+    def step_e2e(i):
+        lab = labels_host[i % n_batches].to(dev, non_blocking=True)     # H2D from pinned memory
+        x = D.prepare_input(lab)                                        # main.py:383-388 on the device
+        mu, logvar, enc, recon = model(x)
+        loss, pxz, kl, _ = model.loss(x, mu, logvar, enc, recon, dev, largs)
+        for p in params:
+            p.grad = None
+        loss.backward()
+        return float(loss)                                              # D2H read of the step's loss (syncs)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for i in range(steps):
+            fn(i)
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for i in range(args.warmup):
+        step_resident(i)
+    with ClockSampler(local) as clk:
+        l0 = M._lib.lib.mmvae_launch_count()
+        ms = timed(step_resident, args.steps)
+        launches = M._lib.lib.mmvae_launch_count() - l0
+    for i in range(3):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, args.steps)
+
+    fps = world * n * args.steps / (ms * 1e-3)
+    fps_e2e = world * n * args.steps / (ms_e2e * 1e-3)
+    sustained, burst, hbm, which = peaks()
+    tflops_per_gpu = fps / world * TRAIN_MFLOP_PER_FRAME * 1e6 / 1e12
+    line = {
+        "metric": "train frames/sec (fwd+bwd)", "value": fps, "unit": "frames/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
+        "data": "synthetic",
+        "config": {"workload": "model.py VAE z=64 64x64 Gaussian-NLL sigma=0.1, fwd+loss+bwd (BASELINE configs[1])",
+                   "frames_per_gpu": n, "global_batch": n * world, "seq_len": 20,
+                   "parallelism": f"dp{world}", "precision": args.precision,
+                   "l2": f"activation workspace {ws_bytes / 1e6:.0f} MB streamed every step (> 126 MB L2), "
+                         f"{n_batches} rotating input batches"},
+        "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": n * 64 * 64, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clk.summary(),
+        "roofline": {"bound": "tensor", "achieved": tflops_per_gpu, "peak": sustained, "unit": "TFLOP/s",
+                     "frac": tflops_per_gpu / sustained, "traffic": None,
+                     "note": f"whole step, 227.02 MFLOP/frame algorithmic, per GPU, of {which} sustained bf16 peak"},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cfps, cms, cores, threads = cpu_reference_fps(10, 3)
+        line["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": threads, "kind": "port",
+                                "sample": f"10 steps of 32 frames (BASELINE configs[0]) on {cores} host cores, fp32, median"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -158,6 +158,14 @@ int mmvae_backward(const mmvae_desc* d, const float* x, const float* params,
 /* [begin, end) float offsets of the gradient-arena range written by one phase. */
 int mmvae_backward_range(const mmvae_desc* d, int32_t phase, int64_t* begin, int64_t* end);
 
+/* Input side of the step (main.py:381-388): k-means label map (uint8, N*H*W) -> normalised fp32 network
+ * input x = (label - data_mean) / data_std, and optionally the int64 cross-entropy target. */
+int mmvae_prepare_input(const uint8_t* labels, int64_t n, float data_mean, float data_std, float* x, int64_t* target,
+                        void* stream);
+
+/* Kernels this library has launched in this process so far (monotonic). */
+int64_t mmvae_launch_count(void);
+
 /* Counter-based standard normals, the generator mmvae_forward uses when eps == NULL:
  * element i = Box-Muller of Philox4x32-10(key = seed, counter = offset + i/4)[i%4 pair]. */
 int mmvae_philox_normal(uint64_t seed, uint64_t offset, int64_t n, float* out, void* stream);

@@ -20,7 +20,7 @@ EXPORTS = [
     "mmvae_abi_version", "mmvae_last_error", "mmvae_layout", "mmvae_param_entry", "mmvae_bn_entry",
     "mmvae_workspace_tensor", "mmvae_forward", "mmvae_decode", "mmvae_loss_scratch_bytes",
     "mmvae_loss_forward", "mmvae_loss_backward", "mmvae_backward", "mmvae_backward_range",
-    "mmvae_philox_normal", "mmvae_adam_step",
+    "mmvae_philox_normal", "mmvae_adam_step", "mmvae_prepare_input", "mmvae_launch_count",
 ]
 
 
@@ -71,10 +71,12 @@ def _load():
     lib.mmvae_philox_normal.argtypes = [c_uint64, c_uint64, c_int64, P, P]
     lib.mmvae_adam_step.argtypes = [c_int64, P, P, P, P, c_float, c_float, c_float, c_float, c_float, c_int64,
                                     c_float, P]
+    lib.mmvae_prepare_input.argtypes = [P, c_int64, c_float, c_float, P, P, P]
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name not in ("mmvae_last_error", "mmvae_loss_scratch_bytes"):
+        if name not in ("mmvae_last_error", "mmvae_loss_scratch_bytes", "mmvae_launch_count"):
             fn.restype = c_int32
+    lib.mmvae_launch_count.restype = c_int64
     if lib.mmvae_abi_version() != ABI_VERSION:
         raise ImportError(f"libmmvae_b200.so ABI {lib.mmvae_abi_version()} != binding {ABI_VERSION}; rebuild it")
     return lib

@@ -19,6 +19,7 @@
 namespace mmvae {
 
 thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
 
 static int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -177,9 +178,9 @@ struct Exec {
     g.bias = c.bias >= 0 ? params + c.bias : nullptr;
     const BnT& b = P.bns[c.bn];
     g.partials = P.d.training ? at<float>(b.part_off) : nullptr;
-    int prow = conv_forward<T>(g, c, st);
+    StatLayout sl = conv_forward<T>(g, c, st);
     BnFinalizeArgs f;
-    f.partials = g.partials; f.P = prow; f.C = b.C; f.m = b.m;
+    f.partials = g.partials; f.sl = sl; f.C = b.C; f.m = b.m;
     f.gamma = params + b.gamma; f.beta = params + b.beta;
     f.running_mean = bnbuf ? bnbuf + b.rm : nullptr;
     f.running_var = bnbuf ? bnbuf + b.rm + b.C : nullptr;
@@ -540,6 +541,16 @@ int mmvae_loss_backward(const mmvae_loss_args* a, const float* recon, const void
   launch_loss_bwd(L, recon, target, ce_weight, mu, logvar, grad_out, d_recon, d_mu, d_logvar,
                   reinterpret_cast<cudaStream_t>(stream));
   return check_launches("mmvae_loss_backward");
+}
+
+int64_t mmvae_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int mmvae_prepare_input(const uint8_t* labels, int64_t n, float data_mean, float data_std, float* x, int64_t* target,
+                        void* stream) {
+  if (int rc = check_device()) return rc;
+  if (!labels || !x || n < 0 || !(data_std > 0.f)) return fail(MMVAE_ERR_BAD_ARG, "bad arguments");
+  launch_prepare_input(labels, n, data_mean, 1.0f / data_std, x, (long long*)target, reinterpret_cast<cudaStream_t>(stream));
+  return check_launches("mmvae_prepare_input");
 }
 
 int mmvae_philox_normal(uint64_t seed, uint64_t offset, int64_t n, float* out, void* stream) {

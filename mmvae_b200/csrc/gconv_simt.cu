@@ -97,40 +97,67 @@ __global__ void __launch_bounds__(kThreads) gconv_simt_kernel(const __grid_const
     __syncthreads();
   }
 
-  // epilogue: bias, store, per-channel partial statistics
-  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+  // epilogue: bias, store, per-channel partial statistics.  The statistics are taken over the values
+  // as stored (after rounding to the storage type), as a (sum, M2 = sum of squared deviations from the
+  // tile mean) pair per CTA: bn_finalize combines the pairs with Chan's formula, so the batch variance
+  // has no E[y^2] - mean^2 cancellation (a 1e-6 relative variance error is amplified by var/eps in the
+  // BatchNorm backward when only a few values share a channel).
   T* out = reinterpret_cast<T*>(p.out);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     int r = ty * 4 + i;
     int n = row_n[r];
-    if (n < 0) continue;
     int oy = v.oy0 + p.os * row_i[r], ox = v.ox0 + p.os * row_j[r];
-    if (oy >= p.Ho || ox >= p.Wo) continue;        // odd-sized stride-2 dgrad: ragged parity sub-grid
-    size_t base = ((size_t(n) * p.Ho + oy) * p.Wo + ox) * p.Co;
+    bool valid = n >= 0 && oy < p.Ho && ox < p.Wo;   // ragged parity sub-grid of an odd-sized stride-2 dgrad
+    size_t base = valid ? ((size_t(n) * p.Ho + oy) * p.Wo + ox) * p.Co : 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int co = n0 + tx * 4 + j;
-      if (co >= p.Co) continue;
-      float val = acc[i][j];
-      if (p.bias) val += p.bias[co];
-      if (p.accumulate) val += to_f(out[base + co]);
-      out[base + co] = from_f<T>(val);
-      s1[j] += val; s2[j] += val * val;
+      float val = 0.f;
+      if (valid && co < p.Co) {
+        val = acc[i][j];
+        if (p.bias) val += p.bias[co];
+        if (p.accumulate) val += to_f(out[base + co]);
+        T tv = from_f<T>(val);
+        out[base + co] = tv;
+        val = to_f(tv);
+      }
+      acc[i][j] = val;
     }
   }
   if (p.partials) {
+    float* csum = &Bs[0][0];            // BN_ floats each, the B tile is dead by now
+    float* cmean = &Bs[1][0];
+    const int n_valid = min(BM, p.M - m0);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { red[0][ty][tx * 4 + j] = s1[j]; red[1][ty][tx * 4 + j] = s2[j]; }
+    for (int j = 0; j < 4; ++j) red[0][ty][tx * 4 + j] = (acc[0][j] + acc[1][j]) + (acc[2][j] + acc[3][j]);
     __syncthreads();
-    for (int e = tid; e < 2 * BN_; e += kThreads) {
-      int which = e / BN_, c = e % BN_;
+    for (int c = tid; c < BN_; c += kThreads) {
+      float s = 0.f;
+      for (int q = 0; q < BM / 4; ++q) s += red[0][q][c];         // fixed order: deterministic
+      csum[c] = s; cmean[c] = s / (float)n_valid;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float mu = cmean[tx * 4 + j], s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        int r = ty * 4 + i;
+        float dlt = (row_n[r] >= 0) ? acc[i][j] - mu : 0.f;
+        s = fmaf(dlt, dlt, s);
+      }
+      red[1][ty][tx * 4 + j] = s;
+    }
+    __syncthreads();
+    for (int c = tid; c < BN_; c += kThreads) {
       int co = n0 + c;
       if (co >= p.Co) continue;
       float s = 0.f;
-      for (int q = 0; q < BM / 4; ++q) s += red[which][q][c];     // fixed order: deterministic
+      for (int q = 0; q < BM / 4; ++q) s += red[1][q][c];
       size_t prow = size_t(blockIdx.z) * gridDim.x + blockIdx.x;
-      p.partials[(prow * p.Co + co) * 2 + which] = s;
+      p.partials[(prow * p.Co + co) * 2 + 0] = csum[c];
+      p.partials[(prow * p.Co + co) * 2 + 1] = s;
     }
   }
 }
@@ -219,22 +246,28 @@ __global__ void __launch_bounds__(kThreads) wgrad_simt_kernel(const __grid_const
 
 }  // namespace
 
-// returns the number of per-CTA partial-statistics rows written (nvar * gridDim.x)
+// returns the layout of the per-CTA partial statistics it wrote
 template <typename T>
-int launch_gconv_simt(const GConvParams& p, cudaStream_t st) {
-  if (p.M <= 0) return 0;
+StatLayout launch_gconv_simt(const GConvParams& p, cudaStream_t st) {
+  StatLayout sl{0, 0, 0, 0};
+  if (p.M <= 0) return sl;
   dim3 grid;
   if (p.Co <= 16) {
     grid = dim3((p.M + 255) / 256, 1, p.nvar);
+    count_launch();
     gconv_simt_kernel<T, 16><<<grid, kThreads, 0, st>>>(p);
   } else if (p.Co <= 32) {
     grid = dim3((p.M + 127) / 128, 1, p.nvar);
+    count_launch();
     gconv_simt_kernel<T, 32><<<grid, kThreads, 0, st>>>(p);
   } else {
     grid = dim3((p.M + 63) / 64, (p.Co + 63) / 64, p.nvar);
+    count_launch();
     gconv_simt_kernel<T, 64><<<grid, kThreads, 0, st>>>(p);
   }
-  return (int)(grid.x * grid.z);
+  sl.parts = (int)(grid.x * grid.z); sl.parts_per_var = (int)grid.x;
+  sl.tile_rows = p.Co <= 16 ? 256 : (p.Co <= 32 ? 128 : 64); sl.rows_per_var = p.M;
+  return sl;
 }
 
 template <typename T>
@@ -255,13 +288,13 @@ void launch_wgrad_simt(const WGradParams& p0, cudaStream_t st) {
   nsplit = (p.M + rps - 1) / rps;
   p.nsplit = nsplit; p.rows_per_split = rps;
   dim3 grid(gx, gy, p.nvar * nsplit);
-  if (bn == 16) wgrad_simt_kernel<T, 16><<<grid, kThreads, 0, st>>>(p);
-  else if (bn == 32) wgrad_simt_kernel<T, 32><<<grid, kThreads, 0, st>>>(p);
-  else wgrad_simt_kernel<T, 64><<<grid, kThreads, 0, st>>>(p);
+  if (bn == 16) { count_launch(); wgrad_simt_kernel<T, 16><<<grid, kThreads, 0, st>>>(p); }
+  else if (bn == 32) { count_launch(); wgrad_simt_kernel<T, 32><<<grid, kThreads, 0, st>>>(p); }
+  else { count_launch(); wgrad_simt_kernel<T, 64><<<grid, kThreads, 0, st>>>(p); }
 }
 
-template int launch_gconv_simt<float>(const GConvParams&, cudaStream_t);
-template int launch_gconv_simt<__nv_bfloat16>(const GConvParams&, cudaStream_t);
+template StatLayout launch_gconv_simt<float>(const GConvParams&, cudaStream_t);
+template StatLayout launch_gconv_simt<__nv_bfloat16>(const GConvParams&, cudaStream_t);
 template void launch_wgrad_simt<float>(const WGradParams&, cudaStream_t);
 template void launch_wgrad_simt<__nv_bfloat16>(const WGradParams&, cudaStream_t);
 

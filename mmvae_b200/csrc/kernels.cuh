@@ -2,9 +2,14 @@
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdint>
 
 namespace mmvae {
+
+// kernels launched by this library in this process (bench.py reports the delta over its timed region)
+extern std::atomic<long long> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 constexpr int kMaxTaps = 25;   // 5x5 stem conv
 constexpr int kMaxVar = 4;     // output-parity variants of a stride-2 transposed conv / dgrad
@@ -27,7 +32,7 @@ struct GConvParams {
   void* out;                   // NHWC [N,Ho,Wo,Co], storage type
   const float* w;              // fp32 weight tensor in the reference layout
   const float* bias;           // fp32 [Co] or nullptr
-  float* partials;             // fp32 [nvar*gridM][Co][2] per-CTA (sum, sum of squares) or nullptr
+  float* partials;             // fp32 [nvar*gridM][Co][2] per-CTA (sum, M2 about the tile mean) or nullptr
   int N, Hi, Wi, Ci, Ho, Wo, Co;
   int Hg, Wg, M;
   int os, is;
@@ -52,12 +57,16 @@ struct WGradParams {
   GVar var[kMaxVar];
 };
 
-template <typename T> int launch_gconv_simt(const GConvParams& p, cudaStream_t st);
+// Layout of the per-CTA partial statistics a conv kernel wrote: `parts` rows of [Co][2] = (sum, M2);
+// row i covers GEMM rows [(i % parts_per_var) * tile_rows, +tile_rows) of its variant, clipped to rows_per_var.
+struct StatLayout { int parts, parts_per_var, tile_rows, rows_per_var; };
+
+template <typename T> StatLayout launch_gconv_simt(const GConvParams& p, cudaStream_t st);
 template <typename T> void launch_wgrad_simt(const WGradParams& p, cudaStream_t st);
 
 // ---- pointwise / reduction kernels (pointwise.cu) ----
 struct BnFinalizeArgs {
-  const float* partials; int P; int C; long long m;
+  const float* partials; StatLayout sl; int C; long long m;
   const float* gamma; const float* beta;
   float* running_mean; float* running_var; long long* counter;   // nullptr when not updating
   float* stat;    // [2][C] mean, rstd
@@ -131,6 +140,9 @@ void launch_loss_fwd(const LossArgs& a, const float* recon, const void* target, 
 void launch_loss_bwd(const LossArgs& a, const float* recon, const void* target, const float* w,
                      const float* mu, const float* lv, const float* gout,
                      float* d_recon, float* d_mu, float* d_lv, cudaStream_t st);
+// k-means label map (uint8) -> normalised fp32 network input (+ int64 CE target)   main.py:381-388
+void launch_prepare_input(const unsigned char* labels, long long n, float mean, float inv_std, float* x,
+                          long long* target, cudaStream_t st);
 void launch_philox_normal(unsigned long long seed, unsigned long long offset, long long n, float* out, cudaStream_t st);
 void launch_adam(long long n, float* p, const float* g, float* m, float* v, float lr, float b1, float b2,
                  float eps, float wd, long long step, float gscale, cudaStream_t st);

@@ -188,6 +188,15 @@ __global__ void __launch_bounds__(256) adam_kernel(long long n, float* __restric
   }
 }
 
+__global__ void __launch_bounds__(256) prepare_input_kernel(const unsigned char* __restrict__ labels, long long n, float mean,
+                                                            float inv_std, float* __restrict__ x, long long* __restrict__ target) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += gridDim.x * 256LL) {
+    unsigned char l = labels[i];
+    x[i] = ((float)l - mean) * inv_std;
+    if (target) target[i] = (long long)l;
+  }
+}
+
 inline int grid_for(long long items, int per_block = 256, int cap = 148 * 8) {
   long long b = (items + per_block - 1) / per_block;
   if (b < 1) b = 1;
@@ -210,15 +219,18 @@ void launch_loss_fwd(const LossArgs& a, const float* recon, const void* target, 
     blocks = (int)((n / 4 + kLossThreads - 1) / kLossThreads);
     if (blocks < 1) blocks = 1;
     if (blocks > kLossBlocks) blocks = kLossBlocks;
+    count_launch();
     loss_gauss_fwd_kernel<<<blocks, kLossThreads, 0, st>>>(recon, reinterpret_cast<const float*>(target), n, partial);
   } else {
     long long npix = (long long)a.N * a.H * a.W;
     blocks = (int)((npix + kLossThreads - 1) / kLossThreads);
     if (blocks < 1) blocks = 1;
     if (blocks > kLossBlocks) blocks = kLossBlocks;
+    count_launch();
     loss_ce_fwd_kernel<<<blocks, kLossThreads, 0, st>>>(recon, reinterpret_cast<const long long*>(target), w, npix,
                                                         a.C, a.H * a.W, partial);
   }
+  count_launch();
   loss_finalize_kernel<<<1, 256, 0, st>>>(a, partial, blocks, mu, lv, out);
 }
 
@@ -229,22 +241,32 @@ void launch_loss_bwd(const LossArgs& a, const float* recon, const void* target, 
     if (a.kind == 0) {
       long long n = (long long)a.N * a.C * a.H * a.W;
       float coef = a.nll / (a.sigma * a.sigma * (float)a.N);
+      count_launch();
       loss_gauss_bwd_kernel<<<grid_for(n / 4 + 1), 256, 0, st>>>(recon, reinterpret_cast<const float*>(target), n, gout,
                                                                  coef, d_recon);
     } else {
       long long npix = (long long)a.N * a.H * a.W;
       float coef = a.nll / (float)a.N;
+      count_launch();
       loss_ce_bwd_kernel<<<grid_for(npix), 256, 0, st>>>(recon, reinterpret_cast<const long long*>(target), w, npix, a.C,
                                                          a.H * a.W, gout, coef, d_recon);
     }
   }
   if (d_mu && d_lv && mu && lv) {
     long long nz = (long long)a.N * a.z;
+    count_launch();
     kl_bwd_kernel<<<grid_for(nz), 256, 0, st>>>(mu, lv, nz, gout, a.kl / (float)a.N, d_mu, d_lv);
   }
 }
 
+void launch_prepare_input(const unsigned char* labels, long long n, float mean, float inv_std, float* x,
+                          long long* target, cudaStream_t st) {
+  count_launch();
+  prepare_input_kernel<<<grid_for(n), 256, 0, st>>>(labels, n, mean, inv_std, x, target);
+}
+
 void launch_philox_normal(unsigned long long seed, unsigned long long offset, long long n, float* out, cudaStream_t st) {
+  count_launch();
   philox_normal_kernel<<<grid_for(n), 256, 0, st>>>(seed, offset, n, out);
 }
 
@@ -252,6 +274,7 @@ void launch_adam(long long n, float* p, const float* g, float* m, float* v, floa
                  float eps, float wd, long long step, float gscale, cudaStream_t st) {
   double bc1 = 1.0 - pow((double)b1, (double)step);
   double bc2 = 1.0 - pow((double)b2, (double)step);
+  count_launch();
   adam_kernel<<<grid_for(n), 256, 0, st>>>(n, p, g, m, v, lr, b1, b2, eps, wd, (float)bc1, (float)sqrt(bc2), gscale);
 }
 

@@ -34,16 +34,20 @@ __global__ void __launch_bounds__(128) bn_finalize_kernel(const BnFinalizeArgs a
   const int c = blockIdx.x;
   float mean, var;
   if (a.training) {
-    double s1 = 0.0, s2 = 0.0;
-    for (int i = threadIdx.x; i < a.P; i += 128) {
-      s1 += (double)a.partials[(size_t(i) * a.C + c) * 2 + 0];
-      s2 += (double)a.partials[(size_t(i) * a.C + c) * 2 + 1];
-    }
+    // Chan et al. pairwise combination of per-CTA (n_i, sum_i, M2_i), in fp64 and in a fixed order.
+    double s1 = 0.0;
+    for (int i = threadIdx.x; i < a.sl.parts; i += 128) s1 += (double)a.partials[(size_t(i) * a.C + c) * 2 + 0];
     s1 = block_sum<128>(s1, sh);
+    const double mu = s1 / (double)a.m;
+    double s2 = 0.0;
+    for (int i = threadIdx.x; i < a.sl.parts; i += 128) {
+      int row0 = (i % a.sl.parts_per_var) * a.sl.tile_rows;
+      int ni = min(a.sl.tile_rows, a.sl.rows_per_var - row0);
+      double mi = (double)a.partials[(size_t(i) * a.C + c) * 2 + 0] / (double)ni - mu;
+      s2 += (double)a.partials[(size_t(i) * a.C + c) * 2 + 1] + (double)ni * mi * mi;
+    }
     s2 = block_sum<128>(s2, sh);
-    double mu = s1 / (double)a.m;
-    double vv = s2 / (double)a.m - mu * mu;
-    if (vv < 0.0) vv = 0.0;
+    double vv = s2 / (double)a.m;
     mean = (float)mu; var = (float)vv;
     if (threadIdx.x == 0 && a.running_mean) {
       double unb = a.m > 1 ? vv * ((double)a.m / (double)(a.m - 1)) : vv;
@@ -365,6 +369,7 @@ template <typename T> constexpr int vec_of() { return 16 / (int)sizeof(T); }
 }  // namespace
 
 void launch_bn_finalize(const BnFinalizeArgs& a, cudaStream_t st) {
+  count_launch();
   bn_finalize_kernel<<<a.C, 128, 0, st>>>(a);
 }
 
@@ -374,9 +379,11 @@ void launch_bn_apply(const T* y, const float* coef, const T* y2, const float* co
   constexpr int V = vec_of<T>();
   if (C % V == 0) {
     long long nvec = rows * C / V;
+    count_launch();
     bn_apply_kernel<T, V><<<grid_for(nvec), 256, 0, st>>>(y, coef, y2, coef2, out, nvec, C, relu);
   } else {
     long long nvec = rows * C;
+    count_launch();
     bn_apply_kernel<T, 1><<<grid_for(nvec), 256, 0, st>>>(y, coef, y2, coef2, out, nvec, C, relu);
   }
 }
@@ -384,27 +391,32 @@ void launch_bn_apply(const T* y, const float* coef, const T* y2, const float* co
 template <typename T>
 void launch_bn_apply_out(const T* y, const float* coef, float* out_nchw, int N, int HW, int C, cudaStream_t st) {
   long long total = (long long)N * HW * C;
+  count_launch();
   bn_apply_out_kernel<T><<<grid_for(total), 256, 0, st>>>(y, coef, out_nchw, total, HW, C);
 }
 
 template <typename T>
 void launch_heads_fwd(const HeadsArgs& a, cudaStream_t st) {
   size_t smem = sizeof(float) * (size_t(a.C) + 2 * size_t(a.z));
+  count_launch();
   heads_fwd_kernel<T><<<a.N, 128, smem, st>>>(a);
 }
 
 template <typename T>
 void launch_cast_latent(const float* enc, T* z_act, long long n, cudaStream_t st) {
+  count_launch();
   cast_latent_kernel<T><<<grid_for(n), 256, 0, st>>>(enc, z_act, n);
 }
 
 template <typename T>
 void launch_heads_bwd(const HeadsBwdArgs& a, cudaStream_t st) {
   size_t smem = sizeof(float) * 2 * size_t(a.z);
+  count_launch();
   heads_bwd_kernel<T><<<a.N, 128, smem, st>>>(a);
   const size_t NZ = size_t(a.N) * a.z;
+  count_launch();
   heads_wgrad_kernel<<<a.z, 128, 0, st>>>(a.dheads, a.pooled, a.g_wmu, a.N, a.z, a.C);
-  if (a.w_lv) heads_wgrad_kernel<<<a.z, 128, 0, st>>>(a.dheads + NZ, a.pooled, a.g_wlv, a.N, a.z, a.C);
+  if (a.w_lv) { count_launch(); heads_wgrad_kernel<<<a.z, 128, 0, st>>>(a.dheads + NZ, a.pooled, a.g_wlv, a.N, a.z, a.C); }
 }
 
 template <typename T>
@@ -421,16 +433,18 @@ void launch_bn_bwd(const BnBwdArgs& a, cudaStream_t st) {
   }
   if (nblocks > 592) nblocks = 592;
   if (nblocks < 1) nblocks = 1;
-  if (vec_ok) bn_bwd_reduce_kernel<T, V><<<nblocks, 256, 0, st>>>(a);
-  else bn_bwd_reduce_kernel<T, 1><<<nblocks, 256, 0, st>>>(a);
+  if (vec_ok) { count_launch(); bn_bwd_reduce_kernel<T, V><<<nblocks, 256, 0, st>>>(a); }
+  else { count_launch(); bn_bwd_reduce_kernel<T, 1><<<nblocks, 256, 0, st>>>(a); }
+  count_launch();
   bn_bwd_finalize_kernel<<<a.C, 128, 0, st>>>(a, nblocks, a.rows);
   long long total = a.rows * a.C;
-  if (a.C % V == 0) bn_bwd_apply_kernel<T, V><<<grid_for(total / V), 256, 0, st>>>(a);
-  else bn_bwd_apply_kernel<T, 1><<<grid_for(total), 256, 0, st>>>(a);
+  if (a.C % V == 0) { count_launch(); bn_bwd_apply_kernel<T, V><<<grid_for(total / V), 256, 0, st>>>(a); }
+  else { count_launch(); bn_bwd_apply_kernel<T, 1><<<grid_for(total), 256, 0, st>>>(a); }
 }
 
 void launch_nchw_to_nhwc(const float* in, float* out, int N, int C, int HW, cudaStream_t st) {
   long long total = (long long)N * C * HW;
+  count_launch();
   nchw_to_nhwc_kernel<<<grid_for(total), 256, 0, st>>>(in, out, total, C, HW);
 }
 

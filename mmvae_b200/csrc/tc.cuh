@@ -6,9 +6,9 @@
 
 namespace mmvae {
 
-// forward conv: returns the number of per-CTA partial-statistics rows it wrote
+// forward conv: returns the layout of the per-CTA partial statistics it wrote
 template <typename T>
-int conv_forward(const GConvParams& g, const ConvT_& c, cudaStream_t st) {
+StatLayout conv_forward(const GConvParams& g, const ConvT_& c, cudaStream_t st) {
   (void)c;
   return launch_gconv_simt<T>(g, st);
 }

@@ -184,15 +184,34 @@ def init_state(cfg: VAEConfig, seed: int = 0, dtype=torch.float32) -> Dict[str, 
 # forward
 # ----------------------------------------------------------------------------
 
+class _RoundBF16(torch.autograd.Function):
+    """Storage rounding of the bf16 mode: the value is rounded to bf16 on the way forward and the
+    gradient on the way back (both tensors live in bf16 in the CUDA path)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(g.dtype)
+
+
 class _Ctx:
     """Carries the state dict, the training flag and the BN side effects."""
 
-    def __init__(self, st, training: bool, keep: bool):
+    def __init__(self, st, training: bool, keep: bool, emulate_bf16: bool = False):
         self.st = st
         self.training = training
         self.keep = keep
+        self.emulate_bf16 = emulate_bf16
+        self.native_bn = False
         self.new_buffers: Dict[str, torch.Tensor] = {}
         self.acts: Dict[str, torch.Tensor] = {}
+
+    def store(self, t: torch.Tensor) -> torch.Tensor:
+        """A tensor the CUDA path materialises in HBM in its storage type."""
+        return _RoundBF16.apply(t) if self.emulate_bf16 else t
 
     def save(self, name: str, t: torch.Tensor):
         if self.keep:
@@ -203,6 +222,10 @@ def _batchnorm(ctx: _Ctx, y: torch.Tensor, prefix: str) -> torch.Tensor:
     """nn.BatchNorm2d with default arguments."""
     st = ctx.st
     gamma, beta = st[prefix + ".weight"], st[prefix + ".bias"]
+    if ctx.native_bn:
+        # the very kernel the reference's nn.BatchNorm2d calls; used for the timed CPU baseline
+        return F.batch_norm(y, st[prefix + ".running_mean"], st[prefix + ".running_var"], gamma, beta,
+                            ctx.training, BN_MOMENTUM, BN_EPS)
     if ctx.training:
         m = y.shape[0] * y.shape[2] * y.shape[3]
         mean = y.mean(dim=(0, 2, 3))
@@ -223,14 +246,14 @@ def _batchnorm(ctx: _Ctx, y: torch.Tensor, prefix: str) -> torch.Tensor:
 def _basic_block(ctx: _Ctx, x: torch.Tensor, p: str) -> torch.Tensor:
     """model.py:39-55 with the 1x1 stride-2 shortcut of model.py:132-138."""
     st = ctx.st
-    y1 = F.conv2d(x, st[p + ".conv1.weight"], stride=2, padding=1)
+    y1 = ctx.store(F.conv2d(x, st[p + ".conv1.weight"], stride=2, padding=1))
     ctx.save(p + ".conv1", y1)
-    a1 = torch.relu(_batchnorm(ctx, y1, p + ".bn1"))
-    y2 = F.conv2d(a1, st[p + ".conv2.weight"], stride=1, padding=1)
+    a1 = ctx.store(torch.relu(_batchnorm(ctx, y1, p + ".bn1")))
+    y2 = ctx.store(F.conv2d(a1, st[p + ".conv2.weight"], stride=1, padding=1))
     ctx.save(p + ".conv2", y2)
-    yd = F.conv2d(x, st[p + ".downsample.0.weight"], stride=2)
+    yd = ctx.store(F.conv2d(x, st[p + ".downsample.0.weight"], stride=2))
     ctx.save(p + ".downsample.0", yd)
-    out = torch.relu(_batchnorm(ctx, y2, p + ".bn2") + _batchnorm(ctx, yd, p + ".downsample.1"))
+    out = ctx.store(torch.relu(_batchnorm(ctx, y2, p + ".bn2") + _batchnorm(ctx, yd, p + ".downsample.1")))
     ctx.save(p, out)
     return out
 
@@ -238,23 +261,23 @@ def _basic_block(ctx: _Ctx, x: torch.Tensor, p: str) -> torch.Tensor:
 def _deconv_block(ctx: _Ctx, x: torch.Tensor, p: str) -> torch.Tensor:
     """model.py:70-85 with the upsample branch of model.py:197-204."""
     st = ctx.st
-    y1 = F.conv2d(x, st[p + ".conv1.weight"])
+    y1 = ctx.store(F.conv2d(x, st[p + ".conv1.weight"]))
     ctx.save(p + ".conv1", y1)
-    a1 = torch.relu(_batchnorm(ctx, y1, p + ".bn1"))
-    y2 = F.conv_transpose2d(a1, st[p + ".conv2.weight"], stride=2, padding=1)
+    a1 = ctx.store(torch.relu(_batchnorm(ctx, y1, p + ".bn1")))
+    y2 = ctx.store(F.conv_transpose2d(a1, st[p + ".conv2.weight"], stride=2, padding=1))
     ctx.save(p + ".conv2", y2)
-    yu = F.conv_transpose2d(x, st[p + ".upsample.0.weight"], stride=2, padding=1)
+    yu = ctx.store(F.conv_transpose2d(x, st[p + ".upsample.0.weight"], stride=2, padding=1))
     ctx.save(p + ".upsample.0", yu)
-    out = torch.relu(_batchnorm(ctx, y2, p + ".bn2") + _batchnorm(ctx, yu, p + ".upsample.1"))
+    out = ctx.store(torch.relu(_batchnorm(ctx, y2, p + ".bn2") + _batchnorm(ctx, yu, p + ".upsample.1")))
     ctx.save(p, out)
     return out
 
 
 def encode(ctx: _Ctx, cfg: VAEConfig, x: torch.Tensor):
     st = ctx.st
-    y = F.conv2d(x, st["encoder.conv1.weight"], stride=2, padding=2)           # model.py:115
+    y = ctx.store(F.conv2d(x, st["encoder.conv1.weight"], stride=2, padding=2))    # model.py:115
     ctx.save("encoder.conv1", y)
-    a = torch.relu(_batchnorm(ctx, y, "encoder.bn1"))                          # model.py:116-117
+    a = ctx.store(torch.relu(_batchnorm(ctx, y, "encoder.bn1")))                   # model.py:116-117
     for i in range(1, 5):                                                      # model.py:119-122
         a = _basic_block(ctx, a, f"encoder.layer{i}.0")
     pooled = a.mean(dim=(2, 3), keepdim=True)                                  # model.py:123
@@ -267,12 +290,12 @@ def encode(ctx: _Ctx, cfg: VAEConfig, x: torch.Tensor):
 
 def decode(ctx: _Ctx, cfg: VAEConfig, z: torch.Tensor) -> torch.Tensor:
     st = ctx.st
-    y = F.conv_transpose2d(z, st["decoder.conv1.weight"])                      # model.py:182
+    y = ctx.store(F.conv_transpose2d(ctx.store(z), st["decoder.conv1.weight"]))    # model.py:182
     ctx.save("decoder.conv1", y)
-    a = torch.relu(_batchnorm(ctx, y, "decoder.bn1"))                          # model.py:183-184
+    a = ctx.store(torch.relu(_batchnorm(ctx, y, "decoder.bn1")))                   # model.py:183-184
     for i in range(1, len(cfg.dec_planes) + 1):                                # model.py:186-192
         a = _deconv_block(ctx, a, f"decoder.uplayer{i}.0")
-    y = F.conv2d(a, st["decoder.conv2.weight"], st["decoder.conv2.bias"], padding=1)
+    y = ctx.store(F.conv2d(a, st["decoder.conv2.weight"], st["decoder.conv2.bias"], padding=1))
     ctx.save("decoder.conv2", y)
     out = _batchnorm(ctx, y, "decoder.bn2")                                    # model.py:193
     adj = cfg.adjust
@@ -282,11 +305,11 @@ def decode(ctx: _Ctx, cfg: VAEConfig, z: torch.Tensor) -> torch.Tensor:
 
 
 def forward(st, cfg: VAEConfig, x: torch.Tensor, eps: Optional[torch.Tensor],
-            training: bool = True, keep_activations: bool = False):
+            training: bool = True, keep_activations: bool = False, emulate_bf16: bool = False):
     """VAE.forward (model.py:316-342) for the ``pixelcnn is None`` configuration.
     ``eps`` is the standard-normal draw of ``rsample`` (model.py:149-150),
     shape [N, z, 1, 1].  Returns (mu, logvar, encoding, reconstruction, ctx)."""
-    ctx = _Ctx(st, training, keep_activations)
+    ctx = _Ctx(st, training, keep_activations, emulate_bf16)
     mu, logvar = encode(ctx, cfg, x)
     if cfg.require_rsample:
         encoding = mu + eps * torch.exp(0.5 * logvar)
@@ -353,9 +376,13 @@ class StepResult:
 
 
 def train_step(st, cfg: VAEConfig, x, target, eps, ce_weight=None, kl_weight=None,
-               keep_activations: bool = False, dtype=None) -> StepResult:
+               keep_activations: bool = False, dtype=None, emulate_bf16: bool = False) -> StepResult:
     """forward -> loss -> backward on the CPU.  ``dtype=torch.float64`` gives a
-    higher-precision referee for the 1e-5 fp32 comparison."""
+    higher-precision referee for the 1e-5 fp32 comparison.  ``emulate_bf16`` rounds
+    every tensor the CUDA bf16 mode keeps in HBM (conv outputs, activations and their
+    gradients) to bf16 at the point it is stored, leaving the arithmetic in ``dtype``:
+    the referee for the bf16 mode's *implementation*, as opposed to bf16's own distance
+    from fp32."""
     names = [n for n, _ in param_specs(cfg)]
     work = {}
     for k, v in st.items():
@@ -372,13 +399,39 @@ def train_step(st, cfg: VAEConfig, x, target, eps, ce_weight=None, kl_weight=Non
             target = target.to(dtype)
         if ce_weight is not None:
             ce_weight = ce_weight.to(dtype)
-    mu, logvar, enc, recon, ctx = forward(work, cfg, x, eps, training=True, keep_activations=keep_activations)
+    mu, logvar, enc, recon, ctx = forward(work, cfg, x, eps, training=True, keep_activations=keep_activations,
+                                          emulate_bf16=emulate_bf16)
     total, pxz, kl = loss(cfg, target, mu, logvar, recon, ce_weight, kl_weight)
     grads = torch.autograd.grad(total, [work[n] for n in names], allow_unused=True)
     gd = {n: (g if g is not None else torch.zeros_like(work[n])) for n, g in zip(names, grads)}
     return StepResult(float(total.detach()), float(pxz), float(kl), mu.detach(),
                       None if logvar is None else logvar.detach(), enc.detach(), recon.detach(),
                       gd, ctx.new_buffers, {k: v.detach() for k, v in ctx.acts.items()})
+
+
+def make_timed_step(st, cfg: VAEConfig):
+    """CPU baseline for bench.py: the same step as ``train_step`` arranged the way the reference runs it
+    (persistent leaf parameters, ``loss.backward()`` into ``.grad``, torch's native batch_norm kernel as
+    nn.BatchNorm2d calls it) so that the timing is representative of the reference on these cores.
+    Returns step(x, target, eps) -> loss value."""
+    names = [n for n, _ in param_specs(cfg)]
+    work = {k: v.detach().clone() for k, v in st.items()}
+    for n in names:
+        work[n].requires_grad_(True)
+
+    def step(x, target, eps):
+        ctx = _Ctx(work, True, False)
+        ctx.native_bn = True
+        mu, logvar = encode(ctx, cfg, x)
+        enc = mu + eps * torch.exp(0.5 * logvar) if cfg.require_rsample else mu
+        recon = decode(ctx, cfg, enc)
+        total, _, _ = loss(cfg, target, mu, logvar, recon)
+        for n in names:
+            work[n].grad = None
+        total.backward()
+        return float(total.detach())
+
+    return step
 
 
 def dp_mean_grads(st, cfg: VAEConfig, shards) -> Dict[str, torch.Tensor]:
