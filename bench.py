@@ -193,7 +193,7 @@ def main():
         for p in params:
             p.grad = None
         loss.backward()
-        return float(loss)                                              # D2H read of the step's loss (syncs)
+        return float(loss.detach())                                     # D2H read of the step's loss (syncs)
 
     def barrier():
         if world > 1:

