@@ -66,8 +66,14 @@ typedef struct mmvae_desc {
   int32_t require_rsample;  /* model.py:262; 0 => encoding = mu, no logvar head                 */
   int32_t precision;        /* MMVAE_PREC_*                                                    */
   int32_t training;         /* 1: batch-statistics BatchNorm + running-stat update; 0: eval    */
-  int32_t reserved[6];
+  int32_t flags;            /* MMVAE_FLAG_* (0 = default kernel selection)                     */
+  int32_t reserved[5];
 } mmvae_desc;
+
+/* Kernel selection for validation: MMVAE_PREC_BF16 normally runs every layer shape the tcgen05
+ * kernels cover on the tensor cores; this flag forces the fp32-FMA SIMT kernels (same bf16 storage)
+ * so the two can be compared tensor by tensor. */
+enum { MMVAE_FLAG_FORCE_SIMT = 1 };
 
 typedef struct mmvae_layout_info {
   int64_t n_params;         /* floats in the parameter / gradient arena         */
@@ -175,6 +181,19 @@ int mmvae_philox_normal(uint64_t seed, uint64_t offset, int64_t n, float* out, v
 int mmvae_adam_step(int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
                     float lr, float beta1, float beta2, float eps, float weight_decay,
                     int64_t step, float grad_scale, void* stream);
+
+/* i-th Conv2d / ConvTranspose2d in execution order: name ("encoder.layer1.0.conv1") and
+ * shape = {kind (0 conv, 1 transposed), k, stride, padding, Ci, Co, H_in, H_out}. */
+int mmvae_conv_entry(const mmvae_desc* d, int32_t i, char* name, size_t name_cap, int32_t shape[8]);
+
+/* Self-test of the tcgen05 kernels: every conv of the model that the tensor-core path covers is run in
+ * all three directions (forward + BatchNorm statistics, weight gradient, data gradient) through both
+ * the tcgen05 kernel and the fp32-FMA SIMT kernel on identical pseudo-random bf16 inputs.
+ * report[16*i + 4*j + {0,1,2}] = {sum (tc - simt)^2, sum simt^2, max |tc - simt|} for conv i and
+ * j = 0 forward output, 1 BatchNorm (mean, rstd), 2 weight gradient, 3 data gradient (zeros = not run).
+ * grads_a / grads_b: two scratch gradient arenas (n_params floats each).  Overwrites the workspace. */
+int mmvae_selftest_tc(const mmvae_desc* d, const float* params, void* workspace, size_t workspace_bytes,
+                      float* grads_a, float* grads_b, float* report, int32_t report_cap, void* stream);
 
 #ifdef __cplusplus
 }

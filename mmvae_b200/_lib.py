@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(HERE, "libmmvae_b200.so")
 PREC_FP32, PREC_BF16 = 0, 1
 LOSS_GAUSSIAN, LOSS_CATEGORICAL = 0, 1
 BWD_DECODER, BWD_ENC_DEEP, BWD_ENC_SHALLOW, BWD_ALL = 1, 2, 4, 7
+FLAG_FORCE_SIMT = 1
 ABI_VERSION = 1
 
 EXPORTS = [
@@ -21,6 +22,7 @@ EXPORTS = [
     "mmvae_workspace_tensor", "mmvae_forward", "mmvae_decode", "mmvae_loss_scratch_bytes",
     "mmvae_loss_forward", "mmvae_loss_backward", "mmvae_backward", "mmvae_backward_range",
     "mmvae_philox_normal", "mmvae_adam_step", "mmvae_prepare_input", "mmvae_launch_count",
+    "mmvae_conv_entry", "mmvae_selftest_tc",
 ]
 
 
@@ -28,7 +30,7 @@ class Desc(Structure):
     _fields_ = [("struct_size", c_int32), ("batch", c_int32), ("in_channels", c_int32),
                 ("out_channels", c_int32), ("z_dim", c_int32), ("image_size", c_int32), ("width", c_int32),
                 ("require_rsample", c_int32), ("precision", c_int32), ("training", c_int32),
-                ("reserved", c_int32 * 6)]
+                ("flags", c_int32), ("reserved", c_int32 * 5)]
 
 
 class LayoutInfo(Structure):
@@ -72,6 +74,8 @@ def _load():
     lib.mmvae_adam_step.argtypes = [c_int64, P, P, P, P, c_float, c_float, c_float, c_float, c_float, c_int64,
                                     c_float, P]
     lib.mmvae_prepare_input.argtypes = [P, c_int64, c_float, c_float, P, P, P]
+    lib.mmvae_conv_entry.argtypes = [POINTER(Desc), c_int32, c_char_p, c_size_t, POINTER(c_int32 * 8)]
+    lib.mmvae_selftest_tc.argtypes = [POINTER(Desc), P, P, c_size_t, P, P, P, c_int32, P]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ("mmvae_last_error", "mmvae_loss_scratch_bytes", "mmvae_launch_count"):
@@ -92,12 +96,13 @@ def check(rc, what=""):
 
 
 def make_desc(batch, in_channels, out_channels, z_dim, image_size, width=1, require_rsample=True,
-              precision=PREC_BF16, training=True):
+              precision=PREC_BF16, training=True, flags=0):
     d = Desc()
     d.struct_size = ctypes.sizeof(Desc)
     d.batch, d.in_channels, d.out_channels, d.z_dim = int(batch), int(in_channels), int(out_channels), int(z_dim)
     d.image_size, d.width = int(image_size), int(width)
     d.require_rsample, d.precision, d.training = int(bool(require_rsample)), int(precision), int(bool(training))
+    d.flags = int(flags)
     return d
 
 
@@ -141,3 +146,15 @@ def backward_range(desc, phase):
     b, e = c_int64(), c_int64()
     check(lib.mmvae_backward_range(byref(desc), phase, byref(b), byref(e)), "mmvae_backward_range")
     return b.value, e.value
+
+
+def conv_table(desc):
+    """[(name, kind, k, stride, padding, Ci, Co, H_in, H_out)] in execution order."""
+    out = []
+    name = create_string_buffer(256)
+    shape = (c_int32 * 8)()
+    i = 0
+    while lib.mmvae_conv_entry(byref(desc), i, name, 256, byref(shape)) == 0:
+        out.append((name.value.decode(),) + tuple(shape[k] for k in range(8)))
+        i += 1
+    return out

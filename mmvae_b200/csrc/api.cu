@@ -64,91 +64,41 @@ static void add_tap(GVar& v, int dy, int dx, int wofs) {
   v.dy[v.ntaps] = (signed char)dy; v.dx[v.ntaps] = (signed char)dx; v.wofs[v.ntaps] = wofs; ++v.ntaps;
 }
 
-// Forward geometry of a conv / transposed conv (also used by its weight gradient).
-static void geom_fprop(const ConvT_& c, int N, GConvParams& g) {
+// Gather-convolution descriptor of conv `c` in direction `dir` (geom.hpp enumerates variants and taps).
+static void geom_build(const ConvT_& c, int dir, int N, GConvParams& g) {
   memset(&g, 0, sizeof(g));
-  g.N = N; g.Hi = c.Hi; g.Wi = c.Wi; g.Ci = c.Ci; g.Ho = c.Ho; g.Wo = c.Wo; g.Co = c.Co;
-  const int k = c.k;
-  if (c.kind == CONV) {
-    g.nvar = 1; g.Hg = c.Ho; g.Wg = c.Wo; g.os = 1; g.is = c.s;
-    g.w_sci = k * k; g.w_sco = c.Ci * k * k;                       // weight [Co][Ci][k][k]
-    for (int kh = 0; kh < k; ++kh)
-      for (int kw = 0; kw < k; ++kw) add_tap(g.var[0], kh - c.p, kw - c.p, kh * k + kw);
-  } else if (c.k == 4) {
-    // ConvTranspose2d k4 s2 p1 (model.py:62-65,198-201): oy = 2*iy - 1 + ky, so output parity py only sees
-    // ky == (py+1) mod 2: four 2x2-tap sub-convolutions, no scatter, no atomics.
-    g.nvar = 4; g.Hg = c.Hi; g.Wg = c.Wi; g.os = 2; g.is = 1;
-    g.w_sci = c.Co * 16; g.w_sco = 16;                             // weight [Ci][Co][4][4]
-    for (int py = 0; py < 2; ++py)
-      for (int px = 0; px < 2; ++px) {
-        GVar& v = g.var[py * 2 + px];
-        v.oy0 = py; v.ox0 = px;
-        for (int ky = 0; ky < 4; ++ky) {
-          if ((py + 1 - ky) % 2 != 0) continue;
-          for (int kx = 0; kx < 4; ++kx) {
-            if ((px + 1 - kx) % 2 != 0) continue;
-            add_tap(v, (py + 1 - ky) / 2, (px + 1 - kx) / 2, ky * 4 + kx);
-          }
-        }
-      }
+  const ConvGeom cg = c.geom();
+  int op_ci, op_co;
+  geom_strides(cg, dir, op_ci, op_co, g.w_sci, g.w_sco);
+  g.N = N; g.Ci = op_ci; g.Co = op_co;
+  if (dir == DIR_FPROP) {
+    g.Hi = c.Hi; g.Wi = c.Wi; g.Ho = c.Ho; g.Wo = c.Wo;
+    if (c.kind == CONV) { g.Hg = c.Ho; g.Wg = c.Wo; g.os = 1; g.is = c.s; }
+    else if (c.k == 4)  { g.Hg = c.Hi; g.Wg = c.Wi; g.os = 2; g.is = 1; }
+    else                { g.Hg = 1; g.Wg = 1; g.os = 2; g.is = 1; }
   } else {
-    // ConvTranspose2d k2 s1 p0 on a 1x1 input (model.py:159-161): y[ky,kx] = W[:, :, ky, kx]^T z
-    g.nvar = 4; g.Hg = 1; g.Wg = 1; g.os = 2; g.is = 1;
-    g.w_sci = c.Co * 4; g.w_sco = 4;                               // weight [Ci][Co][2][2]
-    for (int py = 0; py < 2; ++py)
-      for (int px = 0; px < 2; ++px) {
-        GVar& v = g.var[py * 2 + px];
-        v.oy0 = py; v.ox0 = px;
-        add_tap(v, 0, 0, py * 2 + px);
-      }
+    // data gradient: input = dY [N,Ho,Wo,Co], output = dX [N,Hi,Wi,Ci]
+    g.Hi = c.Ho; g.Wi = c.Wo; g.Ho = c.Hi; g.Wo = c.Wi;
+    if (c.kind == CONV && c.s == 1)      { g.Hg = c.Hi; g.Wg = c.Wi; g.os = 1; g.is = 1; }
+    else if (c.kind == CONV)             { g.Hg = (c.Hi + 1) / 2; g.Wg = (c.Wi + 1) / 2; g.os = 2; g.is = 1; }
+    else if (c.k == 4)                   { g.Hg = c.Hi; g.Wg = c.Wi; g.os = 1; g.is = 2; }
+    else                                 { g.Hg = 1; g.Wg = 1; g.os = 1; g.is = 1; }
+  }
+  g.nvar = geom_nvar(cg, dir);
+  for (int v = 0; v < g.nvar; ++v) {
+    GVar& gv = g.var[v];
+    geom_origin(cg, dir, v, gv.oy0, gv.ox0);
+    int dy, dx, wofs;
+    while (geom_tap(cg, dir, v, gv.ntaps, dy, dx, wofs)) add_tap(gv, dy, dx, wofs);
   }
   g.M = N * g.Hg * g.Wg;
-}
-
-// Data gradient: input = dY [N,Ho,Wo,Co], output = dX [N,Hi,Wi,Ci]; the op's in-channel is the conv's Co.
-static void geom_dgrad(const ConvT_& c, int N, GConvParams& g) {
-  memset(&g, 0, sizeof(g));
-  g.N = N; g.Hi = c.Ho; g.Wi = c.Wo; g.Ci = c.Co; g.Ho = c.Hi; g.Wo = c.Wi; g.Co = c.Ci;
-  const int k = c.k;
-  if (c.kind == CONV) {
-    g.w_sci = c.Ci * k * k; g.w_sco = k * k;
-    if (c.s == 1) {
-      g.nvar = 1; g.Hg = c.Hi; g.Wg = c.Wi; g.os = 1; g.is = 1;
-      for (int kh = 0; kh < k; ++kh)
-        for (int kw = 0; kw < k; ++kw) add_tap(g.var[0], c.p - kh, c.p - kw, kh * k + kw);
-    } else {
-      // stride 2: dX[2i+py] = sum over kh with (py + p - kh) even of dY[i + (py+p-kh)/2]
-      g.Hg = (c.Hi + 1) / 2; g.Wg = (c.Wi + 1) / 2; g.os = 2; g.is = 1;
-      int nv = 0;
-      for (int py = 0; py < 2; ++py)
-        for (int px = 0; px < 2; ++px) {
-          GVar v; memset(&v, 0, sizeof(v));
-          v.oy0 = py; v.ox0 = px;
-          for (int kh = 0; kh < k; ++kh) {
-            if ((py + c.p - kh) % 2 != 0) continue;
-            for (int kw = 0; kw < k; ++kw) {
-              if ((px + c.p - kw) % 2 != 0) continue;
-              add_tap(v, (py + c.p - kh) / 2, (px + c.p - kw) / 2, kh * k + kw);
-            }
-          }
-          if (v.ntaps > 0) g.var[nv++] = v;
-        }
-      g.nvar = nv;
-    }
-  } else if (c.k == 4) {
-    // dX[iy] = sum_ky dY[2*iy - 1 + ky] W[ci][co][ky][kx]: a stride-2 4x4 convolution over dY
-    g.nvar = 1; g.Hg = c.Hi; g.Wg = c.Wi; g.os = 1; g.is = 2;
-    g.w_sci = 16; g.w_sco = c.Co * 16;
-    for (int ky = 0; ky < 4; ++ky)
-      for (int kx = 0; kx < 4; ++kx) add_tap(g.var[0], ky - 1, kx - 1, ky * 4 + kx);
-  } else {
-    g.nvar = 1; g.Hg = 1; g.Wg = 1; g.os = 1; g.is = 1;
-    g.w_sci = 4; g.w_sco = c.Co * 4;
-    for (int ky = 0; ky < 2; ++ky)
-      for (int kx = 0; kx < 2; ++kx) add_tap(g.var[0], ky, kx, ky * 2 + kx);
+  if (c.wp_chunks[dir] > 0) {
+    g.co_pad = (op_co + 15) & ~15;
+    g.wpack_var_stride = c.wp_chunks[dir] * g.co_pad * 128;
   }
-  g.M = N * g.Hg * g.Wg;
 }
+static void geom_fprop(const ConvT_& c, int N, GConvParams& g) { geom_build(c, DIR_FPROP, N, g); }
+static void geom_dgrad(const ConvT_& c, int N, GConvParams& g) { geom_build(c, DIR_DGRAD, N, g); }
 
 // ------------------------------------------------------------------------------------------------
 // step executor
@@ -167,6 +117,22 @@ struct Exec {
   template <typename U> U* at(size_t off) const { return reinterpret_cast<U*>(ws + off); }
   const ActT& act(int i) const { return P.acts[i]; }
 
+  // fp32 master weights -> bf16 tiles of the tcgen05 kernels (both directions), one launch
+  void pack_weights() {
+    PackTable tab;
+    tab.n = 0;
+    for (const ConvT_& c : P.convs)
+      for (int dir = 0; dir < 2; ++dir) {
+        if (c.wp_chunks[dir] <= 0 || tab.n >= kMaxPackOps) continue;
+        PackOp& o = tab.ops[tab.n++];
+        o.w_off = c.w; o.dst_off16 = (unsigned int)(c.wp_off[dir] / 16);
+        o.Ci = (unsigned short)c.Ci; o.Co = (unsigned short)c.Co; o.maxchunks = (unsigned short)c.wp_chunks[dir];
+        o.kind = (unsigned char)(c.kind == CONV ? GEOM_CONV : GEOM_CONVT);
+        o.k = (unsigned char)c.k; o.s = (unsigned char)c.s; o.p = (unsigned char)c.p; o.dir = (unsigned char)dir;
+      }
+    launch_pack_weights(tab, params, ws, st);
+  }
+
   // y = conv(in) with per-CTA partial statistics, then BatchNorm finalize
   void conv_bn_fwd(const ConvT_& c) {
     GConvParams g;
@@ -175,6 +141,7 @@ struct Exec {
     else g.in = at<T>(act(c.in).off);
     g.out = at<T>(act(c.out).off);
     g.w = params + c.w;
+    g.wpack = c.wp_chunks[DIR_FPROP] > 0 ? ws + c.wp_off[DIR_FPROP] : nullptr;
     g.bias = c.bias >= 0 ? params + c.bias : nullptr;
     const BnT& b = P.bns[c.bn];
     g.partials = P.d.training ? at<float>(b.part_off) : nullptr;
@@ -250,7 +217,7 @@ struct Exec {
     w.Hg = g.Hg; w.Wg = g.Wg; w.M = g.M; w.os = g.os; w.is = g.is; w.w_sci = g.w_sci; w.w_sco = g.w_sco;
     w.nvar = g.nvar;
     for (int i = 0; i < g.nvar; ++i) w.var[i] = g.var[i];
-    conv_wgrad<T>(w, c, st);
+    conv_wgrad<T>(w, c, !(P.d.flags & MMVAE_FLAG_FORCE_SIMT), st);
   }
 
   void dgrad(const ConvT_& c, int accumulate) {
@@ -259,6 +226,7 @@ struct Exec {
     g.in = at<T>(act(c.out).goff);
     g.out = at<T>(act(c.in).goff);
     g.w = params + c.w;
+    g.wpack = c.wp_chunks[DIR_DGRAD] > 0 ? ws + c.wp_off[DIR_DGRAD] : nullptr;
     g.accumulate = accumulate;
     conv_dgrad<T>(g, c, st);
   }
@@ -365,6 +333,28 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 }  // namespace mmvae
 
+namespace mmvae {
+__global__ void selftest_fill_kernel(__nv_bfloat16* out, long long n, unsigned int seed) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += gridDim.x * 256LL) {
+    unsigned int h = (unsigned int)i * 2654435761u ^ seed;
+    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13; h *= 3266489917u; h ^= h >> 16;
+    out[i] = __float2bfloat16_rn(((float)(h & 0xffff) - 32768.0f) * (1.0f / 32768.0f));
+  }
+}
+template <typename T>
+__global__ void selftest_cmp_kernel(const T* a, const T* ref, long long n, float* rep) {
+  float d2 = 0.f, r2 = 0.f, mx = 0.f;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += gridDim.x * 256LL) {
+    float x = to_f(a[i]), y = to_f(ref[i]);
+    float d = x - y;
+    if (!(d == d)) d = 1e30f;                      // NaN counts as a huge error
+    d2 += d * d; r2 += y * y; mx = fmaxf(mx, fabsf(d));
+  }
+  atomicAdd(rep + 0, d2); atomicAdd(rep + 1, r2);
+  atomicMax(reinterpret_cast<int*>(rep + 2), __float_as_int(mx));
+}
+}  // namespace mmvae
+
 using namespace mmvae;
 
 extern "C" {
@@ -448,6 +438,7 @@ int mmvae_forward(const mmvae_desc* d, const float* x, const float* params, floa
   } else {
     Exec<__nv_bfloat16> E{P, (char*)workspace, params, nullptr, bn_buffers, (long long*)bn_counters, st, x};
     if (!P.d.training) { E.counters = nullptr; }
+    E.pack_weights();
     E.encode(eps, seed, offset, eps_out, mu, logvar, encoding);
     E.decode(recon);
   }
@@ -468,6 +459,7 @@ int mmvae_decode(const mmvae_desc* d, const float* encoding, const float* params
   } else {
     Exec<__nv_bfloat16> E{P, (char*)workspace, params, nullptr, bn_buffers, (long long*)bn_counters, st, nullptr};
     if (!P.d.training) E.counters = nullptr;
+    E.pack_weights();
     launch_cast_latent<__nv_bfloat16>(encoding, E.at<__nv_bfloat16>(P.acts[P.a_z].off), nz, st);
     E.decode(recon);
   }
@@ -568,6 +560,96 @@ int mmvae_adam_step(int64_t n, float* params, const float* grads, float* exp_avg
   launch_adam(n, params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale,
               reinterpret_cast<cudaStream_t>(stream));
   return check_launches("mmvae_adam_step");
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// self-test of the tcgen05 kernels against the SIMT kernels on identical inputs
+// ------------------------------------------------------------------------------------------------
+
+int mmvae_selftest_tc(const mmvae_desc* d, const float* params, void* workspace, size_t workspace_bytes,
+                      float* grads_a, float* grads_b, float* report, int32_t report_cap, void* stream) {
+  MMVAE_COMMON_CHECKS();
+  if (P.d.precision != MMVAE_PREC_BF16 || (P.d.flags & MMVAE_FLAG_FORCE_SIMT) || !P.d.training)
+    return fail(MMVAE_ERR_BAD_DESC, "mmvae_selftest_tc needs a training-mode bf16 desc without MMVAE_FLAG_FORCE_SIMT");
+  if (!params || !grads_a || !grads_b || !report) return fail(MMVAE_ERR_BAD_ARG, "NULL argument");
+  const int nconv = (int)P.convs.size();
+  if (report_cap < nconv * 4 * 4) return fail(MMVAE_ERR_BAD_ARG, "report needs %d floats", nconv * 16);
+  typedef __nv_bfloat16 T;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  Exec<T> E{P, (char*)workspace, params, grads_a, nullptr, nullptr, st, nullptr};
+  cudaMemsetAsync(report, 0, sizeof(float) * nconv * 16, st);
+  cudaMemsetAsync(grads_a, 0, sizeof(float) * P.n_params, st);
+  cudaMemsetAsync(grads_b, 0, sizeof(float) * P.n_params, st);
+  E.pack_weights();
+  const int N = P.d.batch;
+  for (int ci = 0; ci < nconv; ++ci) {
+    const ConvT_& c = P.convs[ci];
+    float* rep = report + ci * 16;
+    if (c.in < 0 || c.wp_chunks[DIR_FPROP] <= 0) continue;        // stem / tail: SIMT only
+    const ActT& ai = P.acts[c.in]; const ActT& ao = P.acts[c.out];
+    const long long n_in = (long long)N * ai.H * ai.W * ai.C, n_out = (long long)N * ao.H * ao.W * ao.C;
+    // ---- fprop (+ BatchNorm statistics) ----
+    selftest_fill_kernel<<<296, 256, 0, st>>>(E.at<T>(ai.off), n_in, 0x1234u + ci);
+    GConvParams g;
+    geom_fprop(c, N, g);
+    g.in = E.at<T>(ai.off); g.w = params + c.w;
+    g.wpack = (char*)workspace + c.wp_off[DIR_FPROP];
+    const BnT& b = P.bns[c.bn];
+    g.partials = E.at<float>(b.part_off);
+    BnFinalizeArgs f;
+    memset(&f, 0, sizeof(f));
+    f.partials = g.partials; f.C = b.C; f.m = b.m; f.gamma = params + b.gamma; f.beta = params + b.beta;
+    f.stat = E.at<float>(b.stat_off); f.coef = E.at<float>(b.coef_off); f.training = 1;
+    g.out = E.at<T>(ao.off);
+    f.sl = launch_gconv_simt<T>(g, st);
+    launch_bn_finalize(f, st);
+    cudaMemcpyAsync(E.at<float>(b.bcoef_off), E.at<float>(b.stat_off), sizeof(float) * 2 * b.C, cudaMemcpyDeviceToDevice, st);
+    g.out = E.at<T>(ao.goff);
+    f.sl = launch_gconv_tc(g, st);
+    launch_bn_finalize(f, st);
+    selftest_cmp_kernel<T><<<148, 256, 0, st>>>(E.at<T>(ao.goff), E.at<T>(ao.off), n_out, rep + 0);
+    selftest_cmp_kernel<float><<<1, 256, 0, st>>>(E.at<float>(b.stat_off), E.at<float>(b.bcoef_off), 2 * b.C, rep + 4);
+    // ---- wgrad: in = act(in), dY = random ----
+    selftest_fill_kernel<<<296, 256, 0, st>>>(E.at<T>(ao.goff), n_out, 0x9876u + ci);
+    E.grads = grads_a;
+    {
+      GConvParams gg; geom_fprop(c, N, gg);
+      WGradParams w; memset(&w, 0, sizeof(w));
+      w.in = E.at<T>(ai.off); w.dout = E.at<T>(ao.goff);
+      w.N = gg.N; w.Hi = gg.Hi; w.Wi = gg.Wi; w.Ci = gg.Ci; w.Ho = gg.Ho; w.Wo = gg.Wo; w.Co = gg.Co;
+      w.Hg = gg.Hg; w.Wg = gg.Wg; w.M = gg.M; w.os = gg.os; w.is = gg.is; w.w_sci = gg.w_sci; w.w_sco = gg.w_sco;
+      w.nvar = gg.nvar;
+      for (int i = 0; i < gg.nvar; ++i) w.var[i] = gg.var[i];
+      w.dw = grads_a + c.w; launch_wgrad_simt<T>(w, st);
+      w.dw = grads_b + c.w; launch_wgrad_tc(w, st);
+      long long nw = (long long)c.Ci * c.Co * c.k * c.k;
+      selftest_cmp_kernel<float><<<148, 256, 0, st>>>(grads_b + c.w, grads_a + c.w, nw, rep + 8);
+    }
+    // ---- dgrad: dY = act(out).grad (random) -> dX ----
+    if (c.wp_chunks[DIR_DGRAD] > 0) {
+      GConvParams gd;
+      geom_dgrad(c, N, gd);
+      gd.in = E.at<T>(ao.goff); gd.w = params + c.w;
+      gd.wpack = (char*)workspace + c.wp_off[DIR_DGRAD];
+      cudaMemsetAsync(E.at<T>(ai.off), 0, n_in * sizeof(T), st);
+      cudaMemsetAsync(E.at<T>(ai.goff), 0, n_in * sizeof(T), st);
+      gd.out = E.at<T>(ai.off); launch_gconv_simt<T>(gd, st);
+      gd.out = E.at<T>(ai.goff); launch_gconv_tc(gd, st);
+      selftest_cmp_kernel<T><<<148, 256, 0, st>>>(E.at<T>(ai.goff), E.at<T>(ai.off), n_in, rep + 12);
+    }
+  }
+  return check_launches("mmvae_selftest_tc");
+}
+
+int mmvae_conv_entry(const mmvae_desc* d, int32_t i, char* name, size_t name_cap, int32_t shape[8]) {
+  Plan P;
+  if (!P.build(d)) return fail(MMVAE_ERR_BAD_DESC, "%s", P.err.c_str());
+  if (i < 0 || i >= (int)P.convs.size()) return fail(MMVAE_ERR_BAD_ARG, "conv index %d out of range", i);
+  const ConvT_& c = P.convs[i];
+  if (name && name_cap) { strncpy(name, c.name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+  if (shape) { shape[0] = c.kind; shape[1] = c.k; shape[2] = c.s; shape[3] = c.p; shape[4] = c.Ci; shape[5] = c.Co; shape[6] = c.Hi; shape[7] = c.Ho; }
+  return 0;
 }
 
 }  // extern "C"

@@ -40,6 +40,11 @@ struct GConvParams {
   int nvar;
   int accumulate;              // out += result
   int in_nchw_f32;             // network input x: fp32 NCHW
+  // tcgen05 path: pre-packed bf16 weight tiles [variant][k-chunk of 64][co_pad rows][128 B, swizzled]
+  const void* wpack;           // nullptr: no packed weights (SIMT only)
+  int wpack_var_stride;        // bytes between variants
+  int co_pad;                  // Co rounded up to 16
+  int tc_bn, tc_stages;        // set by the launcher
   GVar var[kMaxVar];
 };
 
@@ -54,6 +59,7 @@ struct WGradParams {
   int w_sci, w_sco;
   int nvar, nsplit, rows_per_split;
   int in_nchw_f32;
+  int tc_bn, tc_stages;        // set by the launcher (tcgen05 path)
   GVar var[kMaxVar];
 };
 
@@ -63,6 +69,24 @@ struct StatLayout { int parts, parts_per_var, tile_rows, rows_per_var; };
 
 template <typename T> StatLayout launch_gconv_simt(const GConvParams& p, cudaStream_t st);
 template <typename T> void launch_wgrad_simt(const WGradParams& p, cudaStream_t st);
+
+// ---- tcgen05 kernels (gconv_tc.cu), bf16 storage only ----
+bool tc_supported_gconv(const GConvParams& p);
+bool tc_supported_wgrad(const WGradParams& p);
+StatLayout launch_gconv_tc(const GConvParams& p, cudaStream_t st);
+void launch_wgrad_tc(const WGradParams& p, cudaStream_t st);
+
+// One entry per (conv, direction) whose weights are packed for the tcgen05 path.
+struct PackOp {
+  long long w_off;             // floats into the parameter arena
+  unsigned int dst_off16;      // 16-byte units into the workspace
+  unsigned short Ci, Co;       // the conv's own channels
+  unsigned short maxchunks;    // k-chunks (of 64) per variant
+  unsigned char kind, k, s, p, dir;
+};
+constexpr int kMaxPackOps = 72;
+struct PackTable { int n; PackOp ops[kMaxPackOps]; };
+void launch_pack_weights(const PackTable& tab, const float* params, void* ws, cudaStream_t st);
 
 // ---- pointwise / reduction kernels (pointwise.cu) ----
 struct BnFinalizeArgs {

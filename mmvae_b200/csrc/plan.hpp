@@ -7,11 +7,13 @@
 #pragma once
 #include <cstdint>
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "../../include/mmvae.h"
+#include "geom.hpp"
 
 namespace mmvae {
 
@@ -57,6 +59,10 @@ struct ConvT_ {            // one Conv2d / ConvTranspose2d
   int64_t bias = -1;       // ... of the bias, or -1
   int in = -1, out = -1;   // activation indices (in == -1: the fp32 NCHW network input / latent)
   int bn = -1;
+  // tcgen05 path: packed bf16 weight tiles in the workspace (bytes), per direction; 0 chunks = not packed
+  size_t wp_off[2] = {0, 0};
+  int wp_chunks[2] = {0, 0};       // k-chunks of 64 per variant
+  ConvGeom geom() const { return ConvGeom{kind == CONV ? GEOM_CONV : GEOM_CONVT, k, s, p, Ci, Co}; }
 };
 
 struct BlockT {            // BasicBlock or DeconvBottleneck: main = c1 -> bn1 -> relu -> c2 -> bn2, shortcut = cs -> bns
@@ -222,6 +228,25 @@ struct Plan {
     if (curH != dec_size) { err = "decoder size mismatch"; return false; }
     tail = add_conv("decoder.conv2", "decoder.bn2", CONV, 3, 1, 1, curC, d.out_channels, curH, cur, true);
     drecon_off = bump(sizeof(float) * size_t(d.batch) * dec_size * dec_size * d.out_channels);
+
+    // ---------------- packed weights of the tcgen05 path ----------------
+    if (d.precision == MMVAE_PREC_BF16 && !(d.flags & MMVAE_FLAG_FORCE_SIMT)) {
+      for (auto& c : convs) {
+        if (c.Ci % 8 != 0 || c.Co % 8 != 0) continue;          // stem (Ci = in_channels) / tail (Co = out_channels): SIMT
+        ConvGeom g = c.geom();
+        for (int dir = 0; dir < 2; ++dir) {
+          if (dir == DIR_DGRAD && (c.in < 0 || !d.training)) continue;
+          int op_ci, op_co, sci, sco;
+          geom_strides(g, dir, op_ci, op_co, sci, sco);
+          const int nv = geom_nvar(g, dir);
+          int mc = 1;
+          for (int v = 0; v < nv; ++v) mc = std::max(mc, (geom_ntaps(g, dir, v) * op_ci + 63) / 64);
+          const int co_pad = (op_co + 15) & ~15;
+          c.wp_chunks[dir] = mc;
+          c.wp_off[dir] = bump(size_t(nv) * mc * co_pad * 128);
+        }
+      }
+    }
     return true;
   }
 

@@ -115,6 +115,7 @@ class VAE(nn.Module):
         self.precision = precision
         self.width = width
         self._prec = _lib.PREC_BF16 if precision == "bf16" else _lib.PREC_FP32
+        self.kernel_flags = 0         # _lib.FLAG_FORCE_SIMT: validation of the tcgen05 kernels against the SIMT ones
 
         d1 = self._desc(1, True)
         info = _lib.layout(d1)               # validates the configuration (raises MMVAEError otherwise)
@@ -155,7 +156,8 @@ class VAE(nn.Module):
     # ------------------------------------------------------------------ structure
     def _desc(self, batch, training):
         return _lib.make_desc(batch, self.in_channels, self.decoder_out_channels, self.z_dimensions,
-                              self.input_image_size, self.width, self.require_rsample, self._prec, training)
+                              self.input_image_size, self.width, self.require_rsample, self._prec, training,
+                              flags=self.kernel_flags)
 
     def _node_for(self, dotted):
         parts = dotted.split(".")
@@ -263,7 +265,7 @@ class VAE(nn.Module):
 
     # ------------------------------------------------------------------ execution
     def _workspace(self, n, training):
-        key = (n, bool(training))
+        key = (n, bool(training), self.kernel_flags)
         hit = self._ws.get(key)
         if hit is None:
             if len(self._ws) >= 4:
