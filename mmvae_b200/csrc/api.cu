@@ -11,6 +11,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <type_traits>
 
 #include "kernels.cuh"
 #include "plan.hpp"
@@ -117,6 +118,15 @@ struct Exec {
   template <typename U> U* at(size_t off) const { return reinterpret_cast<U*>(ws + off); }
   const ActT& act(int i) const { return P.acts[i]; }
 
+  // dedicated kernels of the 1-channel stem / tail convolutions (bf16 mode)
+  bool special_ok() const { return std::is_same<T, __nv_bfloat16>::value && !(P.d.flags & MMVAE_FLAG_FORCE_SIMT); }
+  bool use_stem(const ConvT_& c) const {
+    return special_ok() && c.in < 0 && &c == &P.convs[P.stem] && stem_supported(c.Ci, c.Co, c.Hi, c.k, c.s, c.p);
+  }
+  bool use_tail(const ConvT_& c) const {
+    return special_ok() && &c == &P.convs[P.tail] && c.kind == CONV && tail_supported(c.Ci, c.Co, c.Hi, c.k, c.s, c.p);
+  }
+
   // fp32 master weights -> bf16 tiles of the tcgen05 kernels (both directions), one launch
   void pack_weights() {
     PackTable tab;
@@ -145,7 +155,19 @@ struct Exec {
     g.bias = c.bias >= 0 ? params + c.bias : nullptr;
     const BnT& b = P.bns[c.bn];
     g.partials = P.d.training ? at<float>(b.part_off) : nullptr;
-    StatLayout sl = conv_forward<T>(g, c, st);
+    StatLayout sl;
+    if (use_stem(c)) {
+      StemArgs a{};
+      a.x = x; a.w = g.w; a.y = at<__nv_bfloat16>(act(c.out).off); a.partials = g.partials; a.N = P.d.batch; a.S = c.Hi;
+      sl = launch_stem_fwd(a, c.Co, st);
+    } else if (use_tail(c)) {
+      TailArgs a{};
+      a.in = at<__nv_bfloat16>(act(c.in).off); a.w = g.w; a.bias = g.bias; a.y = at<__nv_bfloat16>(act(c.out).off);
+      a.partials = g.partials; a.N = P.d.batch; a.H = c.Hi; a.W = c.Wi;
+      sl = launch_tail_fwd(a, c.Ci, st);
+    } else {
+      sl = conv_forward<T>(g, c, st);
+    }
     BnFinalizeArgs f;
     f.partials = g.partials; f.sl = sl; f.C = b.C; f.m = b.m;
     f.gamma = params + b.gamma; f.beta = params + b.beta;
@@ -205,6 +227,12 @@ struct Exec {
 
   // ---------------- backward ----------------
   void wgrad(const ConvT_& c) {
+    if (use_stem(c)) {
+      StemArgs a{};
+      a.x = x; a.dy = at<__nv_bfloat16>(act(c.out).goff); a.dw = grads + c.w; a.N = P.d.batch; a.S = c.Hi;
+      launch_stem_wgrad(a, c.Co, st);
+      return;
+    }
     GConvParams g;
     geom_fprop(c, P.d.batch, g);
     WGradParams w;
@@ -291,10 +319,17 @@ struct Exec {
           dr = at<float>(P.drecon_off);
         }
         bn_bwd(dr, 1, -1, t, nullptr);
-        wgrad(t);
         // decoder.conv2.bias feeds a BatchNorm: its gradient is identically zero;
         // the arena range was cleared above.
-        dgrad(t, 0);
+        if (use_tail(t)) {
+          TailArgs a{};
+          a.in = at<__nv_bfloat16>(act(t.in).off); a.w = params + t.w; a.dy = at<__nv_bfloat16>(act(t.out).goff);
+          a.dx = at<__nv_bfloat16>(act(t.in).goff); a.dw = grads + t.w; a.N = P.d.batch; a.H = t.Hi; a.W = t.Wi;
+          launch_tail_bwd(a, t.Ci, st);
+        } else {
+          wgrad(t);
+          dgrad(t, 0);
+        }
         for (int i = (int)P.dec.size() - 1; i >= 0; --i) block_bwd(P.dec[i]);
         const ConvT_& s = P.convs[P.dstem];
         bn_bwd(at<T>(act(P.a_dstem).goff), 0, P.a_dstem, s, nullptr);
@@ -334,6 +369,13 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 }  // namespace mmvae
 
 namespace mmvae {
+__global__ void selftest_fill_f32_kernel(float* out, long long n, unsigned int seed) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += gridDim.x * 256LL) {
+    unsigned int h = (unsigned int)i * 2654435761u ^ seed;
+    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13; h *= 3266489917u; h ^= h >> 16;
+    out[i] = ((float)(h & 0xffff) - 32768.0f) * (1.0f / 32768.0f);
+  }
+}
 __global__ void selftest_fill_kernel(__nv_bfloat16* out, long long n, unsigned int seed) {
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += gridDim.x * 256LL) {
     unsigned int h = (unsigned int)i * 2654435761u ^ seed;
@@ -586,7 +628,89 @@ int mmvae_selftest_tc(const mmvae_desc* d, const float* params, void* workspace,
   for (int ci = 0; ci < nconv; ++ci) {
     const ConvT_& c = P.convs[ci];
     float* rep = report + ci * 16;
-    if (c.in < 0 || c.wp_chunks[DIR_FPROP] <= 0) continue;        // stem / tail: SIMT only
+    if (E.use_stem(c)) {
+      // stem: dedicated kernels vs the generic SIMT gather-convolution, on a random fp32 input
+      const ActT& ao = P.acts[c.out];
+      const long long n_out = (long long)N * ao.H * ao.W * ao.C;
+      float* xr = E.at<float>(P.drecon_off);
+      E.x = xr;
+      selftest_fill_f32_kernel<<<296, 256, 0, st>>>(xr, (long long)N * c.Hi * c.Wi, 0x77u);
+      GConvParams g;
+      geom_fprop(c, N, g);
+      g.in = xr; g.in_nchw_f32 = 1; g.w = params + c.w;
+      const BnT& b = P.bns[c.bn];
+      g.partials = E.at<float>(b.part_off);
+      BnFinalizeArgs f;
+      memset(&f, 0, sizeof(f));
+      f.partials = g.partials; f.C = b.C; f.m = b.m; f.gamma = params + b.gamma; f.beta = params + b.beta;
+      f.stat = E.at<float>(b.stat_off); f.coef = E.at<float>(b.coef_off); f.training = 1;
+      g.out = E.at<T>(ao.off);
+      f.sl = launch_gconv_simt<T>(g, st);
+      launch_bn_finalize(f, st);
+      cudaMemcpyAsync(E.at<float>(b.bcoef_off), E.at<float>(b.stat_off), sizeof(float) * 2 * b.C, cudaMemcpyDeviceToDevice, st);
+      StemArgs sa{};
+      sa.x = xr; sa.w = params + c.w; sa.y = E.at<T>(ao.goff); sa.partials = g.partials; sa.N = N; sa.S = c.Hi;
+      f.sl = launch_stem_fwd(sa, c.Co, st);
+      launch_bn_finalize(f, st);
+      selftest_cmp_kernel<T><<<148, 256, 0, st>>>(E.at<T>(ao.goff), E.at<T>(ao.off), n_out, rep + 0);
+      selftest_cmp_kernel<float><<<1, 256, 0, st>>>(E.at<float>(b.stat_off), E.at<float>(b.bcoef_off), 2 * b.C, rep + 4);
+      selftest_fill_kernel<<<296, 256, 0, st>>>(E.at<T>(ao.goff), n_out, 0x9876u + ci);
+      WGradParams w; memset(&w, 0, sizeof(w));
+      w.in = xr; w.in_nchw_f32 = 1; w.dout = E.at<T>(ao.goff);
+      w.N = g.N; w.Hi = g.Hi; w.Wi = g.Wi; w.Ci = g.Ci; w.Ho = g.Ho; w.Wo = g.Wo; w.Co = g.Co;
+      w.Hg = g.Hg; w.Wg = g.Wg; w.M = g.M; w.os = g.os; w.is = g.is; w.w_sci = g.w_sci; w.w_sco = g.w_sco;
+      w.nvar = g.nvar; w.var[0] = g.var[0];
+      w.dw = grads_a + c.w; launch_wgrad_simt<T>(w, st);
+      sa.dy = E.at<T>(ao.goff); sa.dw = grads_b + c.w;
+      launch_stem_wgrad(sa, c.Co, st);
+      selftest_cmp_kernel<float><<<148, 256, 0, st>>>(grads_b + c.w, grads_a + c.w, (long long)c.Ci * c.Co * c.k * c.k, rep + 8);
+      continue;
+    }
+    if (E.use_tail(c)) {
+      const ActT& ai = P.acts[c.in]; const ActT& ao = P.acts[c.out];
+      const long long n_in = (long long)N * ai.H * ai.W * ai.C, n_out = (long long)N * ao.H * ao.W * ao.C;
+      selftest_fill_kernel<<<296, 256, 0, st>>>(E.at<T>(ai.off), n_in, 0x1234u + ci);
+      GConvParams g;
+      geom_fprop(c, N, g);
+      g.in = E.at<T>(ai.off); g.w = params + c.w; g.bias = c.bias >= 0 ? params + c.bias : nullptr;
+      const BnT& b = P.bns[c.bn];
+      g.partials = E.at<float>(b.part_off);
+      BnFinalizeArgs f;
+      memset(&f, 0, sizeof(f));
+      f.partials = g.partials; f.C = b.C; f.m = b.m; f.gamma = params + b.gamma; f.beta = params + b.beta;
+      f.stat = E.at<float>(b.stat_off); f.coef = E.at<float>(b.coef_off); f.training = 1;
+      g.out = E.at<T>(ao.off);
+      f.sl = launch_gconv_simt<T>(g, st);
+      launch_bn_finalize(f, st);
+      cudaMemcpyAsync(E.at<float>(b.bcoef_off), E.at<float>(b.stat_off), sizeof(float) * 2 * b.C, cudaMemcpyDeviceToDevice, st);
+      TailArgs ta{};
+      ta.in = E.at<T>(ai.off); ta.w = params + c.w; ta.bias = g.bias; ta.y = E.at<T>(ao.goff); ta.partials = g.partials;
+      ta.N = N; ta.H = c.Hi; ta.W = c.Wi;
+      f.sl = launch_tail_fwd(ta, c.Ci, st);
+      launch_bn_finalize(f, st);
+      selftest_cmp_kernel<T><<<148, 256, 0, st>>>(E.at<T>(ao.goff), E.at<T>(ao.off), n_out, rep + 0);
+      selftest_cmp_kernel<float><<<1, 256, 0, st>>>(E.at<float>(b.stat_off), E.at<float>(b.bcoef_off), 2 * b.C, rep + 4);
+      // backward: dY random; SIMT wgrad + dgrad vs the fused tail_bwd
+      selftest_fill_kernel<<<296, 256, 0, st>>>(E.at<T>(ao.goff), n_out, 0x9876u + ci);
+      WGradParams w; memset(&w, 0, sizeof(w));
+      w.in = E.at<T>(ai.off); w.dout = E.at<T>(ao.goff);
+      w.N = g.N; w.Hi = g.Hi; w.Wi = g.Wi; w.Ci = g.Ci; w.Ho = g.Ho; w.Wo = g.Wo; w.Co = g.Co;
+      w.Hg = g.Hg; w.Wg = g.Wg; w.M = g.M; w.os = g.os; w.is = g.is; w.w_sci = g.w_sci; w.w_sco = g.w_sco;
+      w.nvar = g.nvar; w.var[0] = g.var[0];
+      w.dw = grads_a + c.w; launch_wgrad_simt<T>(w, st);
+      GConvParams gd;
+      geom_dgrad(c, N, gd);
+      gd.in = E.at<T>(ao.goff); gd.w = params + c.w; gd.out = E.at<T>(ai.goff);
+      launch_gconv_simt<T>(gd, st);
+      // the fused kernel's dX goes to a scratch tensor of the same shape (the last block's raw conv2 output)
+      T* dx_scratch = E.at<T>(P.acts[P.convs[P.dec.back().c2].out].off);
+      ta.dy = E.at<T>(ao.goff); ta.dw = grads_b + c.w; ta.dx = dx_scratch;
+      launch_tail_bwd(ta, c.Ci, st);
+      selftest_cmp_kernel<float><<<148, 256, 0, st>>>(grads_b + c.w, grads_a + c.w, (long long)c.Ci * c.Co * c.k * c.k, rep + 8);
+      selftest_cmp_kernel<T><<<148, 256, 0, st>>>(dx_scratch, E.at<T>(ai.goff), n_in, rep + 12);
+      continue;
+    }
+    if (c.in < 0 || c.wp_chunks[DIR_FPROP] <= 0) continue;        // covered by neither path
     const ActT& ai = P.acts[c.in]; const ActT& ao = P.acts[c.out];
     const long long n_in = (long long)N * ai.H * ai.W * ai.C, n_out = (long long)N * ao.H * ao.W * ao.C;
     // ---- fprop (+ BatchNorm statistics) ----

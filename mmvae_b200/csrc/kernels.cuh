@@ -88,6 +88,38 @@ constexpr int kMaxPackOps = 72;
 struct PackTable { int n; PackOp ops[kMaxPackOps]; };
 void launch_pack_weights(const PackTable& tab, const float* params, void* ws, cudaStream_t st);
 
+// ---- 1-channel stem / tail convolutions (special.cu), bf16 storage only ----
+struct StemArgs {
+  const float* x;              // [N,1,S,S] fp32 NCHW network input
+  const float* w;              // [Co][1][5][5] fp32
+  __nv_bfloat16* y;            // forward: [N,Ho,Wo,Co]
+  float* partials;             // forward: [tiles][Co][2] or nullptr
+  const __nv_bfloat16* dy;     // wgrad: dY [N,Ho,Wo,Co]
+  float* dw;                   // wgrad: gradient arena slot (atomically accumulated; pre-zeroed)
+  int N, S;
+  int Ho, Wo, R, tiles_per_frame, ntiles;   // filled by the launcher
+};
+struct TailArgs {
+  const __nv_bfloat16* in;     // [N,H,W,Ci] activation feeding the tail conv
+  const float* w;              // [1][Ci][3][3] fp32
+  const float* bias;           // [1] or nullptr
+  __nv_bfloat16* y;            // forward: [N,H,W,1]
+  float* partials;             // forward: [tiles][1][2] or nullptr
+  const __nv_bfloat16* dy;     // backward: dY [N,H,W,1]
+  __nv_bfloat16* dx;           // backward: dX [N,H,W,Ci]
+  float* dw;                   // backward: gradient arena slot (atomically accumulated; pre-zeroed)
+  int N, H, W;
+  int R, tiles_per_frame, ntiles;           // filled by the launcher
+};
+bool stem_supported(int Cin, int Co, int S, int k, int s, int p);
+bool tail_supported(int Ci, int Co, int H, int k, int s, int p);
+StatLayout launch_stem_fwd(StemArgs a, int Co, cudaStream_t st);
+void launch_stem_wgrad(StemArgs a, int Co, cudaStream_t st);
+StatLayout launch_tail_fwd(TailArgs a, int Ci, cudaStream_t st);
+void launch_tail_bwd(TailArgs a, int Ci, cudaStream_t st);
+void launch_heads_wgrad(const float* dheads, const float* pooled, float* g_mu, float* g_lv, int N, int z, int C,
+                        cudaStream_t st);
+
 // ---- pointwise / reduction kernels (pointwise.cu) ----
 struct BnFinalizeArgs {
   const float* partials; StatLayout sl; int C; long long m;

@@ -219,17 +219,6 @@ __global__ void __launch_bounds__(128) heads_bwd_kernel(const HeadsBwdArgs a) {
   }
 }
 
-// dW_head[zc][c] = sum_n dhead[n][zc] * pooled[n][c]
-__global__ void __launch_bounds__(128) heads_wgrad_kernel(const float* __restrict__ dh, const float* __restrict__ pooled,
-                                                          float* __restrict__ gw, int N, int z, int C) {
-  const int zc = blockIdx.x;
-  for (int c = threadIdx.x; c < C; c += 128) {
-    float s = 0.f;
-    for (int n = 0; n < N; ++n) s = fmaf(dh[size_t(n) * z + zc], pooled[size_t(n) * C + c], s);
-    gw[size_t(zc) * C + c] = s;
-  }
-}
-
 // ---------------- BatchNorm backward ----------------
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
@@ -413,10 +402,7 @@ void launch_heads_bwd(const HeadsBwdArgs& a, cudaStream_t st) {
   size_t smem = sizeof(float) * 2 * size_t(a.z);
   count_launch();
   heads_bwd_kernel<T><<<a.N, 128, smem, st>>>(a);
-  const size_t NZ = size_t(a.N) * a.z;
-  count_launch();
-  heads_wgrad_kernel<<<a.z, 128, 0, st>>>(a.dheads, a.pooled, a.g_wmu, a.N, a.z, a.C);
-  if (a.w_lv) { count_launch(); heads_wgrad_kernel<<<a.z, 128, 0, st>>>(a.dheads + NZ, a.pooled, a.g_wlv, a.N, a.z, a.C); }
+  launch_heads_wgrad(a.dheads, a.pooled, a.g_wmu, a.w_lv ? a.g_wlv : nullptr, a.N, a.z, a.C, st);
 }
 
 template <typename T>

@@ -55,7 +55,8 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
 
 // ---------------- cp.async (16-byte, zero-fill when src_bytes == 0) ----------------
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+  // .ca: keep the line in L1 -- neighbouring taps / rows of the same tile re-read it
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>

@@ -197,6 +197,19 @@ class _RoundBF16(torch.autograd.Function):
         return g.to(torch.bfloat16).to(g.dtype)
 
 
+class _RoundBF16Operand(torch.autograd.Function):
+    """A tensor-core operand that is kept in fp32 in HBM (a weight): bf16 on the way into the product,
+    gradient left in fp32 (the CUDA path accumulates dW in fp32)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
 class _Ctx:
     """Carries the state dict, the training flag and the BN side effects."""
 
@@ -212,6 +225,11 @@ class _Ctx:
     def store(self, t: torch.Tensor) -> torch.Tensor:
         """A tensor the CUDA path materialises in HBM in its storage type."""
         return _RoundBF16.apply(t) if self.emulate_bf16 else t
+
+    def w(self, name: str) -> torch.Tensor:
+        """A conv / transposed-conv weight as the tensor cores see it (bf16 operand in the bf16 mode)."""
+        t = self.st[name]
+        return _RoundBF16Operand.apply(t) if self.emulate_bf16 else t
 
     def save(self, name: str, t: torch.Tensor):
         if self.keep:
@@ -246,12 +264,12 @@ def _batchnorm(ctx: _Ctx, y: torch.Tensor, prefix: str) -> torch.Tensor:
 def _basic_block(ctx: _Ctx, x: torch.Tensor, p: str) -> torch.Tensor:
     """model.py:39-55 with the 1x1 stride-2 shortcut of model.py:132-138."""
     st = ctx.st
-    y1 = ctx.store(F.conv2d(x, st[p + ".conv1.weight"], stride=2, padding=1))
+    y1 = ctx.store(F.conv2d(x, ctx.w(p + ".conv1.weight"), stride=2, padding=1))
     ctx.save(p + ".conv1", y1)
     a1 = ctx.store(torch.relu(_batchnorm(ctx, y1, p + ".bn1")))
-    y2 = ctx.store(F.conv2d(a1, st[p + ".conv2.weight"], stride=1, padding=1))
+    y2 = ctx.store(F.conv2d(a1, ctx.w(p + ".conv2.weight"), stride=1, padding=1))
     ctx.save(p + ".conv2", y2)
-    yd = ctx.store(F.conv2d(x, st[p + ".downsample.0.weight"], stride=2))
+    yd = ctx.store(F.conv2d(x, ctx.w(p + ".downsample.0.weight"), stride=2))
     ctx.save(p + ".downsample.0", yd)
     out = ctx.store(torch.relu(_batchnorm(ctx, y2, p + ".bn2") + _batchnorm(ctx, yd, p + ".downsample.1")))
     ctx.save(p, out)
@@ -261,12 +279,12 @@ def _basic_block(ctx: _Ctx, x: torch.Tensor, p: str) -> torch.Tensor:
 def _deconv_block(ctx: _Ctx, x: torch.Tensor, p: str) -> torch.Tensor:
     """model.py:70-85 with the upsample branch of model.py:197-204."""
     st = ctx.st
-    y1 = ctx.store(F.conv2d(x, st[p + ".conv1.weight"]))
+    y1 = ctx.store(F.conv2d(x, ctx.w(p + ".conv1.weight")))
     ctx.save(p + ".conv1", y1)
     a1 = ctx.store(torch.relu(_batchnorm(ctx, y1, p + ".bn1")))
-    y2 = ctx.store(F.conv_transpose2d(a1, st[p + ".conv2.weight"], stride=2, padding=1))
+    y2 = ctx.store(F.conv_transpose2d(a1, ctx.w(p + ".conv2.weight"), stride=2, padding=1))
     ctx.save(p + ".conv2", y2)
-    yu = ctx.store(F.conv_transpose2d(x, st[p + ".upsample.0.weight"], stride=2, padding=1))
+    yu = ctx.store(F.conv_transpose2d(x, ctx.w(p + ".upsample.0.weight"), stride=2, padding=1))
     ctx.save(p + ".upsample.0", yu)
     out = ctx.store(torch.relu(_batchnorm(ctx, y2, p + ".bn2") + _batchnorm(ctx, yu, p + ".upsample.1")))
     ctx.save(p, out)
@@ -275,27 +293,27 @@ def _deconv_block(ctx: _Ctx, x: torch.Tensor, p: str) -> torch.Tensor:
 
 def encode(ctx: _Ctx, cfg: VAEConfig, x: torch.Tensor):
     st = ctx.st
-    y = ctx.store(F.conv2d(x, st["encoder.conv1.weight"], stride=2, padding=2))    # model.py:115
+    y = ctx.store(F.conv2d(x, ctx.w("encoder.conv1.weight"), stride=2, padding=2))    # model.py:115
     ctx.save("encoder.conv1", y)
     a = ctx.store(torch.relu(_batchnorm(ctx, y, "encoder.bn1")))                   # model.py:116-117
     for i in range(1, 5):                                                      # model.py:119-122
         a = _basic_block(ctx, a, f"encoder.layer{i}.0")
     pooled = a.mean(dim=(2, 3), keepdim=True)                                  # model.py:123
-    mu = F.conv2d(pooled, st["encoder.conv_mu.weight"])                        # model.py:125
+    mu = F.conv2d(pooled, st["encoder.conv_mu.weight"])                      # model.py:125
     logvar = None
     if cfg.require_rsample:
-        logvar = F.conv2d(pooled, st["encoder.conv_logvar.weight"])            # model.py:128
+        logvar = F.conv2d(pooled, st["encoder.conv_logvar.weight"])          # model.py:128
     return mu, logvar
 
 
 def decode(ctx: _Ctx, cfg: VAEConfig, z: torch.Tensor) -> torch.Tensor:
     st = ctx.st
-    y = ctx.store(F.conv_transpose2d(ctx.store(z), st["decoder.conv1.weight"]))    # model.py:182
+    y = ctx.store(F.conv_transpose2d(ctx.store(z), ctx.w("decoder.conv1.weight")))    # model.py:182
     ctx.save("decoder.conv1", y)
     a = ctx.store(torch.relu(_batchnorm(ctx, y, "decoder.bn1")))                   # model.py:183-184
     for i in range(1, len(cfg.dec_planes) + 1):                                # model.py:186-192
         a = _deconv_block(ctx, a, f"decoder.uplayer{i}.0")
-    y = ctx.store(F.conv2d(a, st["decoder.conv2.weight"], st["decoder.conv2.bias"], padding=1))
+    y = ctx.store(F.conv2d(a, ctx.w("decoder.conv2.weight"), st["decoder.conv2.bias"], padding=1))
     ctx.save("decoder.conv2", y)
     out = _batchnorm(ctx, y, "decoder.bn2")                                    # model.py:193
     adj = cfg.adjust
