@@ -155,6 +155,7 @@ struct Exec {
     g.bias = c.bias >= 0 ? params + c.bias : nullptr;
     const BnT& b = P.bns[c.bn];
     g.partials = P.d.training ? at<float>(b.part_off) : nullptr;
+    g.part_counts = at<float>(b.pcnt_off);
     StatLayout sl;
     if (use_stem(c)) {
       StemArgs a{};
@@ -721,6 +722,7 @@ int mmvae_selftest_tc(const mmvae_desc* d, const float* params, void* workspace,
     g.wpack = (char*)workspace + c.wp_off[DIR_FPROP];
     const BnT& b = P.bns[c.bn];
     g.partials = E.at<float>(b.part_off);
+    g.part_counts = E.at<float>(b.pcnt_off);
     BnFinalizeArgs f;
     memset(&f, 0, sizeof(f));
     f.partials = g.partials; f.C = b.C; f.m = b.m; f.gamma = params + b.gamma; f.beta = params + b.beta;

@@ -87,19 +87,29 @@ __device__ __forceinline__ int warp_colsum16(float (&v)[16], int lane) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// forward / data-gradient gather-convolution
+// forward / data-gradient gather-convolution: persistent, warp-specialised
+//   warps 0-3  producers: A gather (cp.async) + B tile (bulk copy), operand ring of S stages
+//   warp  4    TMEM allocation; lane 0 issues tcgen05.mma into one of two accumulator buffers
+//   warps 5-8  epilogue of tile i while the producers / MMA already work on tile i+1
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTcThreads) gconv_tc_kernel(const __grid_constant__ GConvParams p) {
+constexpr int kGconvThreads = 288;
+
+__device__ __forceinline__ void decode_tile(const GConvParams& p, int t, int& mt, int& v, int& nt) {
+  nt = t % p.n_tiles;
+  int r = t / p.n_tiles;
+  v = r % p.nvar;
+  mt = r / p.nvar;
+}
+
+__global__ void __launch_bounds__(kGconvThreads) gconv_tc_kernel(const __grid_constant__ GConvParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  __shared__ TcShared sh;
+  __shared__ __align__(8) unsigned long long full[kMaxStages], empty[kMaxStages], tfull[2], tempty[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float part[2][4][256];
+  __shared__ float mean_s[256];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int vi = blockIdx.z;
-  const GVar& var = p.var[vi];
   const int BN = p.tc_bn, S = p.tc_stages;
   const int stageB = BN * 128;
-  const int K = var.ntaps * p.Ci;
-  const int nchunks = (K + 63) >> 6;
-  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * BN;
 
   // 1024-byte aligned operand ring (SWIZZLE_128B atoms are 1024 bytes)
   const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -107,55 +117,66 @@ __global__ void __launch_bounds__(kTcThreads) gconv_tc_kernel(const __grid_const
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(smem_u32(&sh.full[s]), kGatherThreads + 1);
-      mbar_init(smem_u32(&sh.empty[s]), 1);
+      mbar_init(smem_u32(&full[s]), kGatherThreads + 1);
+      mbar_init(smem_u32(&empty[s]), 1);
     }
-    mbar_init(smem_u32(&sh.accum), 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&tfull[b]), 1);
+      mbar_init(smem_u32(&tempty[b]), 128);
+    }
     fence_barrier_init();
   }
-  if (tid < var.ntaps) { sh.tap_dy[tid] = var.dy[tid]; sh.tap_dx[tid] = var.dx[tid]; }
-  const uint32_t ncols = BN <= 32 ? 32u : (BN <= 64 ? 64u : (BN <= 128 ? 128u : 256u));
-  if (warp == 4) tmem_alloc(smem_u32(&sh.tmem_base), ncols);
+  const uint32_t ncols = 2 * BN <= 32 ? 32u : (2 * BN <= 64 ? 64u : (2 * BN <= 128 ? 128u : (2 * BN <= 256 ? 256u : 512u)));
+  if (warp == 4) tmem_alloc(smem_u32(&tmem_base_s), ncols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = sh.tmem_base;
+  const uint32_t tmem = tmem_base_s;
 
   if (warp < 4) {
-    // ---------------- A gather: thread -> 16-byte chunk j of rows rg + 16*i ----------------
+    // ---------------- producers: thread -> 16-byte chunk j of rows rg + 16*i ----------------
     const int j = tid & 7, rg = tid >> 3;
-    int pix_base[8];      // element offset of input pixel (n, 0, 0), or -1 when the row is beyond M
-    int iyx[8];           // (iy0 << 16) | ix0 (already multiplied by the input stride)
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      int m = m0 + rg + 16 * i;
-      if (m < p.M) {
-        int jj = m % p.Wg; int t = m / p.Wg; int ii = t % p.Hg; int n = t / p.Hg;
-        pix_base[i] = n * p.Hi * p.Wi;
-        iyx[i] = ((ii * p.is) << 16) | (jj * p.is);
-      } else {
-        pix_base[i] = -1; iyx[i] = 0;
-      }
-    }
     const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(p.in);
-    const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(p.wpack) + (size_t)vi * p.wpack_var_stride +
-                                (size_t)(n0 >> 3) * 1024;
     const uint32_t row_off = (uint32_t)(rg >> 3) * 1024u + (uint32_t)(rg & 7) * 128u + (uint32_t)((j ^ (rg & 7)) << 4);
     const int D = S - 1;
-    for (int it = 0; it < nchunks + D; ++it) {
-      if (it < nchunks) {
-        const int s = it % S;
-        if (it >= S) mbar_wait(smem_u32(&sh.empty[s]), (uint32_t)((it / S) - 1) & 1u);
-        if (tid == 0) {
-          const uint32_t bar = smem_u32(&sh.full[s]);
-          mbar_arrive_expect_tx(bar, (uint32_t)stageB);
-          bulk_g2s(b_base + (uint32_t)s * stageB, wsrc + (size_t)it * p.co_pad * 128, (uint32_t)stageB, bar);
+    int g = 0, stage = 0, sig_stage = 0;          // chunks issued; ring slot of chunk g; slot of the next chunk to signal
+    uint32_t ephase = 1;                          // parity to wait on empty[stage]: the first lap passes immediately
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      int mt, vi, nt;
+      decode_tile(p, t, mt, vi, nt);
+      const GVar& var = p.var[vi];
+      const int K = var.ntaps * p.Ci;
+      const int nchunks = (K + 63) >> 6;
+      const int m0 = mt * 128;
+      int pix_base[8];      // element offset of input pixel (n, 0, 0), or -1 when the row is beyond M
+      int iyx[8];           // (iy0 << 16) | ix0 (already multiplied by the input stride)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        int m = m0 + rg + 16 * i;
+        if (m < p.M) {
+          int tq, jj, n, ii;
+          p.fd_wg.divmod(m, tq, jj);
+          p.fd_hg.divmod(tq, n, ii);
+          pix_base[i] = n * p.Hi * p.Wi;
+          iyx[i] = ((ii * p.is) << 16) | (jj * p.is);
+        } else {
+          pix_base[i] = -1; iyx[i] = 0;
         }
-        const int k = it * 64 + j * 8;
+      }
+      const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(p.wpack) + (size_t)vi * p.wpack_var_stride +
+                                  (size_t)((nt * BN) >> 3) * 1024;
+      for (int kc = 0; kc < nchunks; ++kc) {
+        mbar_wait(smem_u32(&empty[stage]), ephase);
+        if (tid == 0) {
+          const uint32_t bar = smem_u32(&full[stage]);
+          mbar_arrive_expect_tx(bar, (uint32_t)stageB);
+          bulk_g2s(b_base + (uint32_t)stage * stageB, wsrc + (size_t)kc * p.co_pad * 128, (uint32_t)stageB, bar);
+        }
+        const int k = kc * 64 + j * 8;
         const bool kin = k < K;
-        int tap = 0, ci = 0, dy = 0, dx = 0;
-        if (kin) { tap = k / p.Ci; ci = k - tap * p.Ci; dy = sh.tap_dy[tap]; dx = sh.tap_dx[tap]; }
-        const uint32_t dst = a_base + (uint32_t)s * kStageA + row_off;
+        int ci = 0, dy = 0, dx = 0;
+        if (kin) { int tap; p.fd_ci.divmod(k, tap, ci); dy = var.dy[tap]; dx = var.dx[tap]; }
+        const uint32_t dst = a_base + (uint32_t)stage * kStageA + row_off;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           int iy = (iyx[i] >> 16) + dy, ix = (iyx[i] & 0xffff) + dx;
@@ -163,92 +184,130 @@ __global__ void __launch_bounds__(kTcThreads) gconv_tc_kernel(const __grid_const
           const __nv_bfloat16* src = ok ? in + ((size_t)(pix_base[i] + iy * p.Wi + ix) * p.Ci + ci) : in;
           cp_async16(dst + (uint32_t)i * 2048u, src, ok ? 16u : 0u);
         }
-      }
-      cp_async_commit();
-      if (it >= D) {
-        cp_async_wait_dyn(D);
-        fence_proxy_async_smem();
-        mbar_arrive(smem_u32(&sh.full[(it - D) % S]));
+        cp_async_commit();
+        if (++stage == S) { stage = 0; ephase ^= 1u; }
+        if (g >= D) {
+          cp_async_wait_dyn(D);
+          fence_proxy_async_smem();
+          mbar_arrive(smem_u32(&full[sig_stage]));
+          if (++sig_stage == S) sig_stage = 0;
+        }
+        ++g;
       }
     }
-  } else if (lane == 0) {
-    // ---------------- MMA issue ----------------
-    const uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
-    for (int kc = 0; kc < nchunks; ++kc) {
-      const int s = kc % S;
-      mbar_wait(smem_u32(&sh.full[s]), (uint32_t)(kc / S) & 1u);
-      tc_fence_after();
-      const int kleft = K - kc * 64;
-      const int nk = kleft >= 64 ? 4 : (kleft + 15) >> 4;
-      const uint32_t sa = a_base + (uint32_t)s * kStageA, sb = b_base + (uint32_t)s * stageB;
-      for (int q = 0; q < nk; ++q) {
-        uint64_t da = make_smem_desc(sa + q * 32, 16, 1024, SWZ_128);
-        uint64_t db = make_smem_desc(sb + q * 32, 16, 1024, SWZ_128);
-        mma_bf16(tmem, da, db, idesc, (kc | q) != 0);
-      }
-      mma_commit(smem_u32(&sh.empty[s]));
+    // drain: signal the last min(g, D) chunks
+    cp_async_wait_dyn(0);
+    fence_proxy_async_smem();
+    for (int e = (g < D ? g : D); e > 0; --e) {
+      mbar_arrive(smem_u32(&full[sig_stage]));
+      if (++sig_stage == S) sig_stage = 0;
     }
-    mma_commit(smem_u32(&sh.accum));
-  }
-
-  // ---------------- epilogue: TMEM -> bf16 NHWC (+ BatchNorm partial statistics) ----------------
-  if (warp < 4) {
-    mbar_wait(smem_u32(&sh.accum), 0);
-    tc_fence_after();
-    const int r = tid;                                   // TMEM lane == tile row
-    const int m = m0 + r;
-    bool valid = m < p.M;
-    size_t obase = 0;
-    if (valid) {
-      int jj = m % p.Wg; int t = m / p.Wg; int ii = t % p.Hg; int n = t / p.Hg;
-      int oy = var.oy0 + p.os * ii, ox = var.ox0 + p.os * jj;
-      valid = oy < p.Ho && ox < p.Wo;                    // ragged parity sub-grid of an odd-sized stride-2 dgrad
-      obase = ((size_t)(n * p.Ho + oy) * p.Wo + ox) * p.Co;
-    }
-    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
-    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
-    const int n_valid = min(128, p.M - m0);
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      float v[16];
-      tmem_ld16(tlane + (uint32_t)c0, v);
-      const int co0 = n0 + c0;
-      if (p.bias) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) if (co0 + i < p.Co) v[i] += __ldg(p.bias + co0 + i);
-      }
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int co = co0 + h * 8;
-        if (valid && co < p.Co) {
-          uint4* dst = reinterpret_cast<uint4*>(out + obase + co);
-          if (p.accumulate) {
-            uint4 old = *dst;
-            const __nv_bfloat16* o = reinterpret_cast<const __nv_bfloat16*>(&old);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[h * 8 + i] += __bfloat162float(o[i]);
+  } else if (warp == 4) {
+    if (lane == 0) {
+      // ---------------- MMA issue ----------------
+      const uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+      int stage = 0;
+      uint32_t fphase = 0;
+      int i = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
+        int mt, vi, nt;
+        decode_tile(p, t, mt, vi, nt);
+        const int K = p.var[vi].ntaps * p.Ci;
+        const int nchunks = (K + 63) >> 6;
+        const int buf = i & 1;
+        mbar_wait(smem_u32(&tempty[buf]), (uint32_t)(((i >> 1) & 1) ^ 1));   // epilogue drained this buffer
+        tc_fence_after();
+        const uint32_t dtm = tmem + (uint32_t)(buf * BN);
+        for (int kc = 0; kc < nchunks; ++kc) {
+          mbar_wait(smem_u32(&full[stage]), fphase);
+          tc_fence_after();
+          const int kleft = K - kc * 64;
+          const int nk = kleft >= 64 ? 4 : (kleft + 15) >> 4;
+          const uint32_t sa = a_base + (uint32_t)stage * kStageA, sb = b_base + (uint32_t)stage * stageB;
+          for (int q = 0; q < nk; ++q) {
+            uint64_t da = make_smem_desc(sa + q * 32, 16, 1024, SWZ_128);
+            uint64_t db = make_smem_desc(sb + q * 32, 16, 1024, SWZ_128);
+            mma_bf16(dtm, da, db, idesc, (kc | q) != 0);
           }
-          uint4 pk;
-          pk.x = pack_bf16x2(v[h * 8 + 0], v[h * 8 + 1]); pk.y = pack_bf16x2(v[h * 8 + 2], v[h * 8 + 3]);
-          pk.z = pack_bf16x2(v[h * 8 + 4], v[h * 8 + 5]); pk.w = pack_bf16x2(v[h * 8 + 6], v[h * 8 + 7]);
-          *dst = pk;
+          mma_commit(smem_u32(&empty[stage]));
+          if (++stage == S) { stage = 0; fphase ^= 1u; }
+        }
+        mma_commit(smem_u32(&tfull[buf]));
+      }
+    }
+  } else {
+    // ---------------- epilogue: TMEM -> bf16 NHWC (+ BatchNorm partial statistics) ----------------
+    const int q = warp & 3;                              // TMEM lane quarter this warp may read
+    const int r = q * 32 + lane;                         // tile row == TMEM lane
+    const int et = (warp - 5) * 32 + lane;               // index among the 128 epilogue threads
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+    float run_n = 0.f, run_mean = 0.f, run_m2 = 0.f;     // merged statistics of column `et` over this CTA's tiles
+    int i = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
+      int mt, vi, nt;
+      decode_tile(p, t, mt, vi, nt);
+      const GVar& var = p.var[vi];
+      const int m0 = mt * 128, n0 = nt * BN;
+      const int buf = i & 1;
+      const int m = m0 + r;
+      bool valid = m < p.M;
+      size_t obase = 0;
+      if (valid) {
+        int tq, jj, n, ii;
+        p.fd_wg.divmod(m, tq, jj);
+        p.fd_hg.divmod(tq, n, ii);
+        int oy = var.oy0 + p.os * ii, ox = var.ox0 + p.os * jj;
+        valid = oy < p.Ho && ox < p.Wo;                  // ragged parity sub-grid of an odd-sized stride-2 dgrad
+        obase = ((size_t)(n * p.Ho + oy) * p.Wo + ox) * p.Co;
+      }
+      mbar_wait(smem_u32(&tfull[buf]), (uint32_t)((i >> 1) & 1));
+      tc_fence_after();
+      const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        float v[16];
+        tmem_ld16(tlane + (uint32_t)c0, v);
+        const int co0 = n0 + c0;
+        if (p.bias) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) if (co0 + e < p.Co) v[e] += __ldg(p.bias + co0 + e);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int co = co0 + h * 8;
+          if (valid && co < p.Co) {
+            uint4* dst = reinterpret_cast<uint4*>(out + obase + co);
+            if (p.accumulate) {
+              uint4 old = *dst;
+              const __nv_bfloat16* o = reinterpret_cast<const __nv_bfloat16*>(&old);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[h * 8 + e] += __bfloat162float(o[e]);
+            }
+            uint4 pk;
+            pk.x = pack_bf16x2(v[h * 8 + 0], v[h * 8 + 1]); pk.y = pack_bf16x2(v[h * 8 + 2], v[h * 8 + 3]);
+            pk.z = pack_bf16x2(v[h * 8 + 4], v[h * 8 + 5]); pk.w = pack_bf16x2(v[h * 8 + 6], v[h * 8 + 7]);
+            *dst = pk;
+          }
+        }
+        if (p.partials) {
+          // statistics over the values as stored (after rounding), zero for rows / channels outside the tensor
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            v[e] = (valid && co0 + e < p.Co) ? __bfloat162float(__float2bfloat16_rn(v[e])) : 0.f;
+          int c = warp_colsum16(v, lane);
+          if ((lane & 1) == 0) part[0][q][c0 + c] = v[0];
         }
       }
-      if (p.partials) {
-        // statistics over the values as stored (after rounding), zero for rows / channels outside the tensor
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          v[i] = (valid && co0 + i < p.Co) ? __bfloat162float(__float2bfloat16_rn(v[i])) : 0.f;
-        int c = warp_colsum16(v, lane);
-        if ((lane & 1) == 0) sh.part[warp][c0 + c] = v[0];
+      if (!p.partials) {
+        tc_fence_before();
+        mbar_arrive(smem_u32(&tempty[buf]));
+        continue;
       }
-    }
-    if (p.partials) {
+      const int n_valid = min(128, p.M - m0);
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      const size_t prow = (size_t)blockIdx.z * gridDim.x + blockIdx.x;
-      if (tid < BN) {
-        float s = (sh.part[0][tid] + sh.part[1][tid]) + (sh.part[2][tid] + sh.part[3][tid]);
-        sh.mean[tid] = s / (float)n_valid;
-        if (n0 + tid < p.Co) p.partials[(prow * p.Co + n0 + tid) * 2 + 0] = s;
+      float tile_sum = 0.f;
+      if (et < BN) {
+        tile_sum = (part[0][0][et] + part[0][1][et]) + (part[0][2][et] + part[0][3][et]);
+        mean_s[et] = tile_sum / (float)n_valid;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       // second pass: M2 about the tile mean (no E[y^2] - mean^2 cancellation)
@@ -257,20 +316,40 @@ __global__ void __launch_bounds__(kTcThreads) gconv_tc_kernel(const __grid_const
         tmem_ld16(tlane + (uint32_t)c0, v);
         const int co0 = n0 + c0;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float x = v[i];
-          if (p.bias && co0 + i < p.Co) x += __ldg(p.bias + co0 + i);
-          float d = (valid && co0 + i < p.Co) ? __bfloat162float(__float2bfloat16_rn(x)) - sh.mean[c0 + i] : 0.f;
-          v[i] = d * d;
+        for (int e = 0; e < 16; ++e) {
+          float x = v[e];
+          if (p.bias && co0 + e < p.Co) x += __ldg(p.bias + co0 + e);
+          float d = (valid && co0 + e < p.Co) ? __bfloat162float(__float2bfloat16_rn(x)) - mean_s[c0 + e] : 0.f;
+          v[e] = d * d;
         }
         int c = warp_colsum16(v, lane);
-        if ((lane & 1) == 0) sh.part[warp][c0 + c] = v[0];
+        if ((lane & 1) == 0) part[1][q][c0 + c] = v[0];
       }
+      tc_fence_before();
+      mbar_arrive(smem_u32(&tempty[buf]));               // accumulator buffer is free for tile i+2
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (tid < BN && n0 + tid < p.Co) {
-        float s = (sh.part[0][tid] + sh.part[1][tid]) + (sh.part[2][tid] + sh.part[3][tid]);
-        p.partials[(prow * p.Co + n0 + tid) * 2 + 1] = s;
+      if (et < BN) {
+        const float tile_m2 = (part[1][0][et] + part[1][1][et]) + (part[1][2][et] + part[1][3][et]);
+        if (p.tc_merge) {
+          // Chan et al.: merge (n_valid, tile_sum, tile_m2) into the running (n, mean, M2)
+          const float nb = (float)n_valid, mb = tile_sum / nb;
+          const float nn = run_n + nb, delta = mb - run_mean;
+          run_mean += delta * (nb / nn);
+          run_m2 += tile_m2 + delta * delta * (run_n * nb / nn);
+          run_n = nn;
+        } else if (n0 + et < p.Co) {
+          const size_t prow = (size_t)vi * p.tiles_m + mt;
+          p.partials[(prow * p.Co + n0 + et) * 2 + 0] = tile_sum;
+          p.partials[(prow * p.Co + n0 + et) * 2 + 1] = tile_m2;
+        }
       }
+    }
+    if (p.partials && p.tc_merge) {
+      if (et < BN && et < p.Co) {
+        p.partials[((size_t)blockIdx.x * p.Co + et) * 2 + 0] = run_mean * run_n;
+        p.partials[((size_t)blockIdx.x * p.Co + et) * 2 + 1] = run_m2;
+      }
+      if (et == 0) p.part_counts[blockIdx.x] = run_n;
     }
   }
   tc_fence_before();
@@ -331,10 +410,11 @@ __global__ void __launch_bounds__(kTcThreads) wgrad_tc_kernel(const __grid_const
     const int k = k0 + jk * 8;
     const bool kin = k < K;
     int ci = 0, dy = 0, dx = 0;
-    if (kin) { int tap = k / p.Ci; ci = k - tap * p.Ci; dy = var.dy[tap]; dx = var.dx[tap]; }
+    if (kin) { int tap; p.fd_ci.divmod(k, tap, ci); dy = var.dy[tap]; dx = var.dx[tap]; }
     const uint32_t a_off = (uint32_t)(jk >> 3) * 8192u + (uint32_t)pg * 128u + (uint32_t)(((jk & 7) ^ pg) << 4);
     // dY: 64 pixels x (BN/8) chunks, thread -> transfers e = tid + 128*q
     const int cpr = BN >> 3;                   // chunks per pixel row: 2 / 4 / 8
+    const int cpr_log2 = cpr == 2 ? 1 : (cpr == 4 ? 2 : 3);
     const int nb = cpr >> 1;                   // transfers per thread: 1 / 2 / 4
     const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(p.in);
     const __nv_bfloat16* dout = reinterpret_cast<const __nv_bfloat16*>(p.dout);
@@ -348,10 +428,13 @@ __global__ void __launch_bounds__(kTcThreads) wgrad_tc_kernel(const __grid_const
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int m = mb + pg + 8 * i;
-          bool ok = kin && m < m_hi;
+          if (!kin) continue;                    // rows k >= K of the accumulator are never read: leave the tile as is
+          bool ok = m < m_hi;
           const __nv_bfloat16* src = in;
           if (ok) {
-            int jj = m % p.Wg; int t = m / p.Wg; int ii = t % p.Hg; int n = t / p.Hg;
+            int t, jj, n, ii;
+            p.fd_wg.divmod(m, t, jj);
+            p.fd_hg.divmod(t, n, ii);
             int iy = ii * p.is + dy, ix = jj * p.is + dx;
             ok = (unsigned)iy < (unsigned)p.Hi && (unsigned)ix < (unsigned)p.Wi;
             if (ok) src = in + ((size_t)((n * p.Hi + iy) * p.Wi + ix) * p.Ci + ci);
@@ -361,13 +444,15 @@ __global__ void __launch_bounds__(kTcThreads) wgrad_tc_kernel(const __grid_const
         const uint32_t bdst = b_base + (uint32_t)s * stageB;
         for (int q = 0; q < nb; ++q) {
           const int e = tid + 128 * q;
-          const int px = e / cpr, c = e - px * cpr;
+          const int px = e >> cpr_log2, c = e & (cpr - 1);
           const int m = mb + px;
           const int co = n0 + c * 8;
           bool ok = m < m_hi && co < p.Co;
           const __nv_bfloat16* src = dout;
           if (ok) {
-            int jj = m % p.Wg; int t = m / p.Wg; int ii = t % p.Hg; int n = t / p.Hg;
+            int t, jj, n, ii;
+            p.fd_wg.divmod(m, t, jj);
+            p.fd_hg.divmod(t, n, ii);
             int oy = var.oy0 + p.os * ii, ox = var.ox0 + p.os * jj;
             ok = oy < p.Ho && ox < p.Wo;
             if (ok) src = dout + ((size_t)((n * p.Ho + oy) * p.Wo + ox) * p.Co + co);
@@ -492,25 +577,31 @@ StatLayout launch_gconv_tc(const GConvParams& p0, cudaStream_t st) {
   const int tiles_m = (p.M + 127) / 128;
   const int co_pad = (p.Co + 15) & ~15;
   // widest channel tile that still leaves >= ~1 CTA per SM; never narrower than 32 unless the layer is
-  int bn = co_pad > 256 ? 256 : pow2_floor(co_pad);
+  int bn = co_pad > 128 ? 128 : pow2_floor(co_pad);   // <= 128: one epilogue thread per column for the statistics
   if (co_pad % bn != 0) bn = 16;
   while (bn > 32 && (long long)tiles_m * p.nvar * ((co_pad + bn - 1) / bn) < 128) bn >>= 1;
   int maxchunks = 1;
   for (int v = 0; v < p.nvar; ++v) maxchunks = max(maxchunks, (p.var[v].ntaps * p.Ci + 63) / 64);
   const int stage_bytes = kStageA + bn * 128;
-  int stages = min(min(maxchunks, kMaxStages), max(2, (100 * 1024) / stage_bytes));
-  if (maxchunks == 1) stages = 1;
+  int stages = min(kMaxStages, max(2, (100 * 1024) / stage_bytes));
   p.tc_bn = bn; p.tc_stages = stages; p.co_pad = co_pad;
+  p.tiles_m = tiles_m; p.n_tiles = (co_pad + bn - 1) / bn; p.total_tiles = tiles_m * p.nvar * p.n_tiles;
+  p.tc_merge = (p.partials != nullptr && p.n_tiles == 1 && p.part_counts != nullptr) ? 1 : 0;
+  p.fd_wg = FastDiv(p.Wg); p.fd_hg = FastDiv(p.Hg); p.fd_ci = FastDiv(p.Ci);
   const size_t smem = (size_t)stages * stage_bytes + 1024;
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(gconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_done = true;
   }
-  dim3 grid(tiles_m, (co_pad + bn - 1) / bn, p.nvar);
+  const int grid = min(p.total_tiles, 2 * 148);
   count_launch();
-  gconv_tc_kernel<<<grid, kTcThreads, smem, st>>>(p);
-  sl.parts = tiles_m * p.nvar; sl.parts_per_var = tiles_m; sl.tile_rows = 128; sl.rows_per_var = p.M;
+  gconv_tc_kernel<<<grid, kGconvThreads, smem, st>>>(p);
+  if (p.tc_merge) {
+    sl.parts = grid; sl.parts_per_var = grid; sl.tile_rows = 128; sl.rows_per_var = p.M; sl.counts = p.part_counts;
+  } else {
+    sl.parts = tiles_m * p.nvar; sl.parts_per_var = tiles_m; sl.tile_rows = 128; sl.rows_per_var = p.M;
+  }
   return sl;
 }
 
@@ -529,6 +620,7 @@ void launch_wgrad_tc(const WGradParams& p0, cudaStream_t st) {
   rps = (rps + 63) / 64 * 64;
   nsplit = (p.M + rps - 1) / rps;
   p.nsplit = nsplit; p.rows_per_split = rps; p.tc_bn = bn;
+  p.fd_wg = FastDiv(p.Wg); p.fd_hg = FastDiv(p.Hg); p.fd_ci = FastDiv(p.Ci);
   const int nchunks = rps / 64;
   const int stage_bytes = kStageA + 64 * bn * 2;
   int stages = min(min(nchunks, kMaxStages), max(2, (100 * 1024) / stage_bytes));

@@ -11,6 +11,26 @@ namespace mmvae {
 extern std::atomic<long long> g_launches;
 inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// Division by a runtime constant without the integer-divide sequence (valid for numerators < 2^31).
+struct FastDiv {
+  unsigned int mul = 0, shr = 0, div = 1;
+  FastDiv() = default;
+  explicit FastDiv(int d) {
+    div = (unsigned int)d;
+    if (d > 1) {
+      int lg = 0;
+      while ((1u << lg) < (unsigned int)d) ++lg;           // ceil(log2(d))
+      const unsigned long long pw = 1ull << (31 + lg);
+      mul = (unsigned int)((pw + (unsigned long long)d - 1) / (unsigned long long)d);
+      shr = (unsigned int)(lg - 1);
+    }
+  }
+#ifdef __CUDACC__
+  __device__ __forceinline__ int quo(int x) const { return div == 1 ? x : (int)(__umulhi((unsigned int)x, mul) >> shr); }
+  __device__ __forceinline__ void divmod(int x, int& q, int& r) const { q = quo(x); r = x - q * (int)div; }
+#endif
+};
+
 constexpr int kMaxTaps = 25;   // 5x5 stem conv
 constexpr int kMaxVar = 4;     // output-parity variants of a stride-2 transposed conv / dgrad
 
@@ -44,7 +64,11 @@ struct GConvParams {
   const void* wpack;           // nullptr: no packed weights (SIMT only)
   int wpack_var_stride;        // bytes between variants
   int co_pad;                  // Co rounded up to 16
-  int tc_bn, tc_stages;        // set by the launcher
+  float* part_counts;          // rows behind each `partials` row when the kernel merges its tiles (or nullptr)
+  // set by the launcher
+  int tc_bn, tc_stages, tc_merge;
+  int tiles_m, n_tiles, total_tiles;
+  FastDiv fd_wg, fd_hg, fd_ci;
   GVar var[kMaxVar];
 };
 
@@ -60,12 +84,14 @@ struct WGradParams {
   int nvar, nsplit, rows_per_split;
   int in_nchw_f32;
   int tc_bn, tc_stages;        // set by the launcher (tcgen05 path)
+  FastDiv fd_wg, fd_hg, fd_ci;
   GVar var[kMaxVar];
 };
 
 // Layout of the per-CTA partial statistics a conv kernel wrote: `parts` rows of [Co][2] = (sum, M2);
 // row i covers GEMM rows [(i % parts_per_var) * tile_rows, +tile_rows) of its variant, clipped to rows_per_var.
-struct StatLayout { int parts, parts_per_var, tile_rows, rows_per_var; };
+// counts != nullptr: row i covers counts[i] rows instead (a persistent kernel merged its tiles).
+struct StatLayout { int parts, parts_per_var, tile_rows, rows_per_var; const float* counts = nullptr; };
 
 template <typename T> StatLayout launch_gconv_simt(const GConvParams& p, cudaStream_t st);
 template <typename T> void launch_wgrad_simt(const WGradParams& p, cudaStream_t st);

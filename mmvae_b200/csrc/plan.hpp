@@ -43,6 +43,7 @@ struct BnT {               // one BatchNorm2d
   size_t coef_off = 0;           // fp32 [2][C]: scale = gamma*rstd, shift = beta - mean*scale
   size_t part_off = 0;           // fp32 forward partial sums [P][C][2]
   size_t part_cap = 0;           // P capacity
+  size_t pcnt_off = 0;           // fp32 [max(P, 1024)]: rows behind each partial row (persistent kernels)
   size_t bpart_off = 0;          // fp32 backward partial sums [PB][C][3]
   size_t bcoef_off = 0;          // fp32 [3][C]: backward coefficients (scale, c1, c2)
 };
@@ -127,7 +128,8 @@ struct Plan {
     b.stat_off = bump(sizeof(float) * 2 * C);
     b.coef_off = bump(sizeof(float) * 2 * C);
     b.part_cap = part_rows;
-    b.part_off = bump(sizeof(float) * 2 * C * part_rows);
+    b.part_off = bump(sizeof(float) * 2 * C * std::max<size_t>(part_rows, 1024));
+    b.pcnt_off = bump(sizeof(float) * std::max<size_t>(part_rows, 1024));
     b.bpart_off = bump(sizeof(float) * 3 * C * kBwdBlocks);
     b.bcoef_off = bump(sizeof(float) * 3 * C);
     bns.push_back(b);

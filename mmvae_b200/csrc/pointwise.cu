@@ -42,9 +42,10 @@ __global__ void __launch_bounds__(128) bn_finalize_kernel(const BnFinalizeArgs a
     double s2 = 0.0;
     for (int i = threadIdx.x; i < a.sl.parts; i += 128) {
       int row0 = (i % a.sl.parts_per_var) * a.sl.tile_rows;
-      int ni = min(a.sl.tile_rows, a.sl.rows_per_var - row0);
-      double mi = (double)a.partials[(size_t(i) * a.C + c) * 2 + 0] / (double)ni - mu;
-      s2 += (double)a.partials[(size_t(i) * a.C + c) * 2 + 1] + (double)ni * mi * mi;
+      double ni = a.sl.counts ? (double)a.sl.counts[i] : (double)min(a.sl.tile_rows, a.sl.rows_per_var - row0);
+      if (ni <= 0.0) continue;
+      double mi = (double)a.partials[(size_t(i) * a.C + c) * 2 + 0] / ni - mu;
+      s2 += (double)a.partials[(size_t(i) * a.C + c) * 2 + 1] + ni * mi * mi;
     }
     s2 = block_sum<128>(s2, sh);
     double vv = s2 / (double)a.m;
