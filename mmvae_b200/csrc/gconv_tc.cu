@@ -1,19 +1,24 @@
 // gconv_tc.cu -- tcgen05 (5th-generation tensor core) implicit-GEMM kernels of the bf16 mode.
 //
 //   gconv_tc_kernel   forward conv / transposed conv / data gradient ("gather-convolution", kernels.cuh):
-//                     D[128 pixels][BN channels] = A[128][K] * W[K][BN]; A is gathered from the NHWC bf16
-//                     activation with cp.async (im2col on the fly, zero fill at the borders) into a
-//                     K-major SWIZZLE_128B tile, W arrives as pre-packed, pre-swizzled tiles through the
-//                     TMA engine (cp.async.bulk), the fp32 accumulator lives in TMEM, and the epilogue
-//                     (tcgen05.ld) rounds to bf16, stores NHWC and emits the per-CTA BatchNorm partials.
+//                     D[128 pixels][BN channels] = A[128][K] * W[K][BN].  Persistent and warp-specialised:
+//                     one producer thread stages, per (tap, channel block), a TMA box of the NHWC bf16
+//                     activation (im2col on the fly: the tap is a coordinate offset, the conv padding is the
+//                     TMA out-of-bounds zero fill, a stride-2 conv is a traversal stride) next to the
+//                     pre-packed weight tile (bulk copy); one thread issues tcgen05.mma into one of two
+//                     TMEM accumulators; four epilogue warps drain the other one (tcgen05.ld -> bf16 NHWC +
+//                     per-warp BatchNorm partial sums kept in registers across the CTA's tiles).
+//                     Layer shapes whose 128-pixel tile is not a box (odd sizes of the cropped models) use
+//                     the same kernel with a cp.async gather by four producer warps instead.
 //   wgrad_tc_kernel   weight gradient: D[128 (tap,ci)][BN co] = sum over pixels of A^T * dY; both operands
-//                     are MN-major (the pixel axis is the GEMM K axis), split over pixel ranges, reduced
-//                     into the fp32 gradient arena with red.global.add.
+//                     are MN-major (the pixel axis is the GEMM K axis), TMA-staged the same way, split over
+//                     pixel ranges, reduced into the fp32 gradient arena with red.global.add.
 //   pack_weights_kernel  fp32 reference-layout weights -> bf16 tiles in the exact shared-memory image
 //                     (8-row x 128-byte swizzle atoms) that gconv_tc_kernel bulk-copies.
-//
-// Warp roles (160 threads): warps 0-3 gather operands and run the epilogue (thread t owns TMEM lane t),
-// warp 4 allocates TMEM and its lane 0 issues every tcgen05.mma.
+#include <cuda.h>
+
+#include <cstdlib>
+
 #include "geom.hpp"
 #include "kernels.cuh"
 #include "tc_common.cuh"
@@ -25,19 +30,9 @@ using namespace tc;
 namespace {
 
 constexpr int kGatherThreads = 128;
-constexpr int kTcThreads = 160;
-constexpr int kStageA = 128 * 128;      // bytes: 128 rows x 64 bf16 (fprop) or 2 x (64 pixels x 64 bf16) (wgrad)
+constexpr int kTcThreads = 288;         // 4 producer warps, 1 MMA warp, 4 epilogue warps
+constexpr int kStageA = 128 * 128;      // bytes: 128 rows x 64 bf16 (fprop) or 128 (tap,ci) x 64 pixels (wgrad)
 constexpr int kMaxStages = 8;
-
-struct __align__(8) TcShared {
-  unsigned long long full[kMaxStages];
-  unsigned long long empty[kMaxStages];
-  unsigned long long accum;
-  uint32_t tmem_base;
-  int tap_dy[kMaxTaps], tap_dx[kMaxTaps];
-  float part[4][256];
-  float mean[256];
-};
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -45,10 +40,9 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 }
 
 // Sum over the 32 rows held by the lanes of a warp of 16 per-thread column values: a transposing
-// butterfly (16 shuffles).  On return lanes (2c, 2c+1) ... hold column perm(lane): returns the column
-// index this lane ended up owning; the sum is in v[0].
+// butterfly (16 shuffles).  Returns the column this lane ends up owning; its sum is in v[0]
+// (lanes 2c and 2c+1 hold the same column).
 __device__ __forceinline__ int warp_colsum16(float (&v)[16], int lane) {
-  // step 1: lanes with bit4 = 0 keep columns [0,8), bit4 = 1 keep [8,16)
   {
     const bool hi = lane & 16;
 #pragma unroll
@@ -86,30 +80,27 @@ __device__ __forceinline__ int warp_colsum16(float (&v)[16], int lane) {
   return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
 }
 
-// ------------------------------------------------------------------------------------------------
-// forward / data-gradient gather-convolution: persistent, warp-specialised
-//   warps 0-3  producers: A gather (cp.async) + B tile (bulk copy), operand ring of S stages
-//   warp  4    TMEM allocation; lane 0 issues tcgen05.mma into one of two accumulator buffers
-//   warps 5-8  epilogue of tile i while the producers / MMA already work on tile i+1
-// ------------------------------------------------------------------------------------------------
-constexpr int kGconvThreads = 288;
+__device__ __forceinline__ uint32_t swz_code(int row_bytes) { return row_bytes == 128 ? SWZ_128 : (row_bytes == 64 ? SWZ_64 : SWZ_32); }
 
+// ------------------------------------------------------------------------------------------------
+// forward / data-gradient gather-convolution
+// ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void decode_tile(const GConvParams& p, int t, int& mt, int& v, int& nt) {
-  nt = t % p.n_tiles;
-  int r = t / p.n_tiles;
-  v = r % p.nvar;
-  mt = r / p.nvar;
+  int r;
+  p.fd_ntiles.divmod(t, r, nt);
+  p.fd_nvar.divmod(r, mt, v);
 }
 
-__global__ void __launch_bounds__(kGconvThreads) gconv_tc_kernel(const __grid_constant__ GConvParams p) {
+__global__ void __launch_bounds__(kTcThreads) gconv_tc_kernel(const __grid_constant__ GConvParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long full[kMaxStages], empty[kMaxStages], tfull[2], tempty[2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float part[2][4][256];
-  __shared__ float mean_s[256];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int BN = p.tc_bn, S = p.tc_stages;
   const int stageB = BN * 128;
+  const int kb = p.tc_kb;                       // channels per A sub-tile: 64 (gather) or min(Ci, 64) (TMA)
+  const int kbB = kb * 2;                       // bytes per sub-tile row
+  const int sub_bytes = 128 * kbB;
 
   // 1024-byte aligned operand ring (SWIZZLE_128B atoms are 1024 bytes)
   const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -117,7 +108,7 @@ __global__ void __launch_bounds__(kGconvThreads) gconv_tc_kernel(const __grid_co
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(smem_u32(&full[s]), kGatherThreads + 1);
+      mbar_init(smem_u32(&full[s]), p.use_tma ? 1 : kGatherThreads + 1);
       mbar_init(smem_u32(&empty[s]), 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -134,78 +125,117 @@ __global__ void __launch_bounds__(kGconvThreads) gconv_tc_kernel(const __grid_co
   const uint32_t tmem = tmem_base_s;
 
   if (warp < 4) {
-    // ---------------- producers: thread -> 16-byte chunk j of rows rg + 16*i ----------------
-    const int j = tid & 7, rg = tid >> 3;
-    const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(p.in);
-    const uint32_t row_off = (uint32_t)(rg >> 3) * 1024u + (uint32_t)(rg & 7) * 128u + (uint32_t)((j ^ (rg & 7)) << 4);
-    const int D = S - 1;
-    int g = 0, stage = 0, sig_stage = 0;          // chunks issued; ring slot of chunk g; slot of the next chunk to signal
-    uint32_t ephase = 1;                          // parity to wait on empty[stage]: the first lap passes immediately
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-      int mt, vi, nt;
-      decode_tile(p, t, mt, vi, nt);
-      const GVar& var = p.var[vi];
-      const int K = var.ntaps * p.Ci;
-      const int nchunks = (K + 63) >> 6;
-      const int m0 = mt * 128;
-      int pix_base[8];      // element offset of input pixel (n, 0, 0), or -1 when the row is beyond M
-      int iyx[8];           // (iy0 << 16) | ix0 (already multiplied by the input stride)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        int m = m0 + rg + 16 * i;
-        if (m < p.M) {
-          int tq, jj, n, ii;
-          p.fd_wg.divmod(m, tq, jj);
-          p.fd_hg.divmod(tq, n, ii);
-          pix_base[i] = n * p.Hi * p.Wi;
-          iyx[i] = ((ii * p.is) << 16) | (jj * p.is);
-        } else {
-          pix_base[i] = -1; iyx[i] = 0;
+    if (p.use_tma) {
+      // ---------------- producer: one thread, TMA boxes ----------------
+      if (tid == 0) {
+        const uint64_t tmap = reinterpret_cast<uint64_t>(&p.tmap_a);
+        int stage = 0;
+        uint32_t ephase = 1;                    // the first lap over the ring passes immediately
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+          int mt, vi, nt;
+          decode_tile(p, t, mt, vi, nt);
+          const GVar& var = p.var[vi];
+          const int K = var.ntaps * p.Ci;
+          const int nchunks = (K + 63) >> 6;
+          // origin of the tile's pixel box in the gather grid: m0 -> (n0, i0, 0)
+          int n0, i0, j0, rem;
+          p.fd_hw.divmod(mt * 128, n0, rem);
+          p.fd_wg.divmod(rem, i0, j0);
+          const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(p.wpack) + (size_t)vi * p.wpack_var_stride +
+                                      (size_t)((nt * BN) >> 3) * 1024;
+          for (int kc = 0; kc < nchunks; ++kc) {
+            mbar_wait(smem_u32(&empty[stage]), ephase);
+            const uint32_t bar = smem_u32(&full[stage]);
+            const int kend = min(K, kc * 64 + 64);
+            const int nsub = (kend - kc * 64 + kb - 1) / kb;
+            mbar_arrive_expect_tx(bar, (uint32_t)(stageB + nsub * sub_bytes));
+            bulk_g2s(b_base + (uint32_t)stage * stageB, wsrc + (size_t)kc * p.co_pad * 128, (uint32_t)stageB, bar);
+            for (int g = 0; g < nsub; ++g) {
+              int tap, ci;
+              p.fd_ci.divmod(kc * 64 + g * kb, tap, ci);
+              tma_load_4d(a_base + (uint32_t)stage * kStageA + (uint32_t)g * sub_bytes, tmap, bar, ci,
+                          j0 * p.is + var.dx[tap], i0 * p.is + var.dy[tap], n0);
+            }
+            if (++stage == S) { stage = 0; ephase ^= 1u; }
+          }
         }
       }
-      const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(p.wpack) + (size_t)vi * p.wpack_var_stride +
-                                  (size_t)((nt * BN) >> 3) * 1024;
-      for (int kc = 0; kc < nchunks; ++kc) {
-        mbar_wait(smem_u32(&empty[stage]), ephase);
-        if (tid == 0) {
-          const uint32_t bar = smem_u32(&full[stage]);
-          mbar_arrive_expect_tx(bar, (uint32_t)stageB);
-          bulk_g2s(b_base + (uint32_t)stage * stageB, wsrc + (size_t)kc * p.co_pad * 128, (uint32_t)stageB, bar);
-        }
-        const int k = kc * 64 + j * 8;
-        const bool kin = k < K;
-        int ci = 0, dy = 0, dx = 0;
-        if (kin) { int tap; p.fd_ci.divmod(k, tap, ci); dy = var.dy[tap]; dx = var.dx[tap]; }
-        const uint32_t dst = a_base + (uint32_t)stage * kStageA + row_off;
+    } else {
+      // ---------------- producers: cp.async gather, thread -> 16-byte chunk j of rows rg + 16*i ----------------
+      const int j = tid & 7, rg = tid >> 3;
+      const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(p.in);
+      const uint32_t row_off = (uint32_t)(rg >> 3) * 1024u + (uint32_t)(rg & 7) * 128u + (uint32_t)((j ^ (rg & 7)) << 4);
+      const int D = S - 1;
+      int g = 0, stage = 0, sig_stage = 0;      // chunks issued; ring slot of chunk g; slot of the next chunk to signal
+      uint32_t ephase = 1;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        int mt, vi, nt;
+        decode_tile(p, t, mt, vi, nt);
+        const GVar& var = p.var[vi];
+        const int K = var.ntaps * p.Ci;
+        const int nchunks = (K + 63) >> 6;
+        const int m0 = mt * 128;
+        int pix_base[8];      // element offset of input pixel (n, 0, 0), or -1 when the row is beyond M
+        int iyx[8];           // (iy0 << 16) | ix0 (already multiplied by the input stride)
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          int iy = (iyx[i] >> 16) + dy, ix = (iyx[i] & 0xffff) + dx;
-          bool ok = kin && pix_base[i] >= 0 && (unsigned)iy < (unsigned)p.Hi && (unsigned)ix < (unsigned)p.Wi;
-          const __nv_bfloat16* src = ok ? in + ((size_t)(pix_base[i] + iy * p.Wi + ix) * p.Ci + ci) : in;
-          cp_async16(dst + (uint32_t)i * 2048u, src, ok ? 16u : 0u);
+          int m = m0 + rg + 16 * i;
+          if (m < p.M) {
+            int tq, jj, n, ii;
+            p.fd_wg.divmod(m, tq, jj);
+            p.fd_hg.divmod(tq, n, ii);
+            pix_base[i] = n * p.Hi * p.Wi;
+            iyx[i] = ((ii * p.is) << 16) | (jj * p.is);
+          } else {
+            pix_base[i] = -1; iyx[i] = 0;
+          }
         }
-        cp_async_commit();
-        if (++stage == S) { stage = 0; ephase ^= 1u; }
-        if (g >= D) {
-          cp_async_wait_dyn(D);
-          fence_proxy_async_smem();
-          mbar_arrive(smem_u32(&full[sig_stage]));
-          if (++sig_stage == S) sig_stage = 0;
+        const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(p.wpack) + (size_t)vi * p.wpack_var_stride +
+                                    (size_t)((nt * BN) >> 3) * 1024;
+        for (int kc = 0; kc < nchunks; ++kc) {
+          mbar_wait(smem_u32(&empty[stage]), ephase);
+          if (tid == 0) {
+            const uint32_t bar = smem_u32(&full[stage]);
+            mbar_arrive_expect_tx(bar, (uint32_t)stageB);
+            bulk_g2s(b_base + (uint32_t)stage * stageB, wsrc + (size_t)kc * p.co_pad * 128, (uint32_t)stageB, bar);
+          }
+          const int k = kc * 64 + j * 8;
+          const bool kin = k < K;
+          int ci = 0, dy = 0, dx = 0;
+          if (kin) { int tap; p.fd_ci.divmod(k, tap, ci); dy = var.dy[tap]; dx = var.dx[tap]; }
+          const uint32_t dst = a_base + (uint32_t)stage * kStageA + row_off;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            int iy = (iyx[i] >> 16) + dy, ix = (iyx[i] & 0xffff) + dx;
+            bool ok = kin && pix_base[i] >= 0 && (unsigned)iy < (unsigned)p.Hi && (unsigned)ix < (unsigned)p.Wi;
+            const __nv_bfloat16* src = ok ? in + ((size_t)(pix_base[i] + iy * p.Wi + ix) * p.Ci + ci) : in;
+            cp_async16(dst + (uint32_t)i * 2048u, src, ok ? 16u : 0u);
+          }
+          cp_async_commit();
+          if (++stage == S) { stage = 0; ephase ^= 1u; }
+          if (g >= D) {
+            cp_async_wait_dyn(D);
+            fence_proxy_async_smem();
+            mbar_arrive(smem_u32(&full[sig_stage]));
+            if (++sig_stage == S) sig_stage = 0;
+          }
+          ++g;
         }
-        ++g;
       }
-    }
-    // drain: signal the last min(g, D) chunks
-    cp_async_wait_dyn(0);
-    fence_proxy_async_smem();
-    for (int e = (g < D ? g : D); e > 0; --e) {
-      mbar_arrive(smem_u32(&full[sig_stage]));
-      if (++sig_stage == S) sig_stage = 0;
+      // drain: signal the last min(g, D) chunks
+      cp_async_wait_dyn(0);
+      fence_proxy_async_smem();
+      for (int e = (g < D ? g : D); e > 0; --e) {
+        mbar_arrive(smem_u32(&full[sig_stage]));
+        if (++sig_stage == S) sig_stage = 0;
+      }
     }
   } else if (warp == 4) {
     if (lane == 0) {
       // ---------------- MMA issue ----------------
       const uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+      const uint32_t aswz = swz_code(kbB);
+      const uint32_t asbo = 8u * (uint32_t)kbB;
       int stage = 0;
       uint32_t fphase = 0;
       int i = 0;
@@ -225,7 +255,9 @@ __global__ void __launch_bounds__(kGconvThreads) gconv_tc_kernel(const __grid_co
           const int nk = kleft >= 64 ? 4 : (kleft + 15) >> 4;
           const uint32_t sa = a_base + (uint32_t)stage * kStageA, sb = b_base + (uint32_t)stage * stageB;
           for (int q = 0; q < nk; ++q) {
-            uint64_t da = make_smem_desc(sa + q * 32, 16, 1024, SWZ_128);
+            const int kel = q * 16;
+            const int g = kel / kb, within = kel - g * kb;        // kb is 16 / 32 / 64
+            uint64_t da = make_smem_desc(sa + (uint32_t)g * sub_bytes + (uint32_t)within * 2, 16, asbo, aswz);
             uint64_t db = make_smem_desc(sb + q * 32, 16, 1024, SWZ_128);
             mma_bf16(dtm, da, db, idesc, (kc | q) != 0);
           }
@@ -239,9 +271,12 @@ __global__ void __launch_bounds__(kGconvThreads) gconv_tc_kernel(const __grid_co
     // ---------------- epilogue: TMEM -> bf16 NHWC (+ BatchNorm partial statistics) ----------------
     const int q = warp & 3;                              // TMEM lane quarter this warp may read
     const int r = q * 32 + lane;                         // tile row == TMEM lane
-    const int et = (warp - 5) * 32 + lane;               // index among the 128 epilogue threads
     __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
-    float run_n = 0.f, run_mean = 0.f, run_m2 = 0.f;     // merged statistics of column `et` over this CTA's tiles
+    // merged mode: this lane's running (sum, sum of squares) of one column per 16-column group, over all tiles
+    float run_s[8], run_q[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { run_s[e] = 0.f; run_q[e] = 0.f; }
+    float run_n = 0.f;
     int i = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
       int mt, vi, nt;
@@ -260,96 +295,79 @@ __global__ void __launch_bounds__(kGconvThreads) gconv_tc_kernel(const __grid_co
         valid = oy < p.Ho && ox < p.Wo;                  // ragged parity sub-grid of an odd-sized stride-2 dgrad
         obase = ((size_t)(n * p.Ho + oy) * p.Wo + ox) * p.Co;
       }
+      const float rows_here = (float)__popc(__ballot_sync(0xffffffffu, valid));
       mbar_wait(smem_u32(&tfull[buf]), (uint32_t)((i >> 1) & 1));
       tc_fence_after();
       const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
-      for (int c0 = 0; c0 < BN; c0 += 16) {
-        float v[16];
-        tmem_ld16(tlane + (uint32_t)c0, v);
-        const int co0 = n0 + c0;
-        if (p.bias) {
+      const size_t prow = p.tc_merge ? ((size_t)blockIdx.x * 4 + q) : (((size_t)vi * p.tiles_m + mt) * 4 + q);
 #pragma unroll
-          for (int e = 0; e < 16; ++e) if (co0 + e < p.Co) v[e] += __ldg(p.bias + co0 + e);
-        }
+      for (int gq = 0; gq < 8; ++gq) {
+        const int c0 = gq * 16;
+        if (c0 < BN) {
+          float v[16];
+          tmem_ld16(tlane + (uint32_t)c0, v);
+          const int co0 = n0 + c0;
+          if (p.bias) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int co = co0 + h * 8;
-          if (valid && co < p.Co) {
-            uint4* dst = reinterpret_cast<uint4*>(out + obase + co);
-            if (p.accumulate) {
-              uint4 old = *dst;
-              const __nv_bfloat16* o = reinterpret_cast<const __nv_bfloat16*>(&old);
+            for (int e = 0; e < 16; ++e) if (co0 + e < p.Co) v[e] += __ldg(p.bias + co0 + e);
+          }
 #pragma unroll
-              for (int e = 0; e < 8; ++e) v[h * 8 + e] += __bfloat162float(o[e]);
+          for (int h = 0; h < 2; ++h) {
+            const int co = co0 + h * 8;
+            if (valid && co < p.Co) {
+              uint4* dst = reinterpret_cast<uint4*>(out + obase + co);
+              if (p.accumulate) {
+                uint4 old = *dst;
+                const __nv_bfloat16* o = reinterpret_cast<const __nv_bfloat16*>(&old);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[h * 8 + e] += __bfloat162float(o[e]);
+              }
+              uint4 pk;
+              pk.x = pack_bf16x2(v[h * 8 + 0], v[h * 8 + 1]); pk.y = pack_bf16x2(v[h * 8 + 2], v[h * 8 + 3]);
+              pk.z = pack_bf16x2(v[h * 8 + 4], v[h * 8 + 5]); pk.w = pack_bf16x2(v[h * 8 + 6], v[h * 8 + 7]);
+              *dst = pk;
             }
-            uint4 pk;
-            pk.x = pack_bf16x2(v[h * 8 + 0], v[h * 8 + 1]); pk.y = pack_bf16x2(v[h * 8 + 2], v[h * 8 + 3]);
-            pk.z = pack_bf16x2(v[h * 8 + 4], v[h * 8 + 5]); pk.w = pack_bf16x2(v[h * 8 + 6], v[h * 8 + 7]);
-            *dst = pk;
+          }
+          if (p.partials) {
+            // statistics over the values as stored (after rounding), zero for rows / channels outside the tensor
+            float sq[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              v[e] = (valid && co0 + e < p.Co) ? __bfloat162float(__float2bfloat16_rn(v[e])) : 0.f;
+              sq[e] = v[e] * v[e];
+            }
+            const int c = warp_colsum16(v, lane);
+            warp_colsum16(sq, lane);
+            if (p.tc_merge) {
+              run_s[gq] += v[0]; run_q[gq] += sq[0];
+            } else if ((lane & 1) == 0 && co0 + c < p.Co) {
+              p.partials[(prow * p.Co + co0 + c) * 2 + 0] = v[0];
+              p.partials[(prow * p.Co + co0 + c) * 2 + 1] = sq[0];
+            }
           }
         }
-        if (p.partials) {
-          // statistics over the values as stored (after rounding), zero for rows / channels outside the tensor
-#pragma unroll
-          for (int e = 0; e < 16; ++e)
-            v[e] = (valid && co0 + e < p.Co) ? __bfloat162float(__float2bfloat16_rn(v[e])) : 0.f;
-          int c = warp_colsum16(v, lane);
-          if ((lane & 1) == 0) part[0][q][c0 + c] = v[0];
-        }
-      }
-      if (!p.partials) {
-        tc_fence_before();
-        mbar_arrive(smem_u32(&tempty[buf]));
-        continue;
-      }
-      const int n_valid = min(128, p.M - m0);
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      float tile_sum = 0.f;
-      if (et < BN) {
-        tile_sum = (part[0][0][et] + part[0][1][et]) + (part[0][2][et] + part[0][3][et]);
-        mean_s[et] = tile_sum / (float)n_valid;
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      // second pass: M2 about the tile mean (no E[y^2] - mean^2 cancellation)
-      for (int c0 = 0; c0 < BN; c0 += 16) {
-        float v[16];
-        tmem_ld16(tlane + (uint32_t)c0, v);
-        const int co0 = n0 + c0;
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          float x = v[e];
-          if (p.bias && co0 + e < p.Co) x += __ldg(p.bias + co0 + e);
-          float d = (valid && co0 + e < p.Co) ? __bfloat162float(__float2bfloat16_rn(x)) - mean_s[c0 + e] : 0.f;
-          v[e] = d * d;
-        }
-        int c = warp_colsum16(v, lane);
-        if ((lane & 1) == 0) part[1][q][c0 + c] = v[0];
       }
       tc_fence_before();
       mbar_arrive(smem_u32(&tempty[buf]));               // accumulator buffer is free for tile i+2
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (et < BN) {
-        const float tile_m2 = (part[1][0][et] + part[1][1][et]) + (part[1][2][et] + part[1][3][et]);
-        if (p.tc_merge) {
-          // Chan et al.: merge (n_valid, tile_sum, tile_m2) into the running (n, mean, M2)
-          const float nb = (float)n_valid, mb = tile_sum / nb;
-          const float nn = run_n + nb, delta = mb - run_mean;
-          run_mean += delta * (nb / nn);
-          run_m2 += tile_m2 + delta * delta * (run_n * nb / nn);
-          run_n = nn;
-        } else if (n0 + et < p.Co) {
-          const size_t prow = (size_t)vi * p.tiles_m + mt;
-          p.partials[(prow * p.Co + n0 + et) * 2 + 0] = tile_sum;
-          p.partials[(prow * p.Co + n0 + et) * 2 + 1] = tile_m2;
-        }
+      if (p.partials) {
+        if (p.tc_merge) run_n += rows_here;
+        else if (lane == 0) p.part_counts[prow] = rows_here;
       }
     }
     if (p.partials && p.tc_merge) {
-      if (et < BN && et < p.Co) {
-        p.partials[((size_t)blockIdx.x * p.Co + et) * 2 + 0] = run_mean * run_n;
-        p.partials[((size_t)blockIdx.x * p.Co + et) * 2 + 1] = run_m2;
+      const int c = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+      const size_t prow = (size_t)blockIdx.x * 4 + q;
+      if ((lane & 1) == 0) {
+#pragma unroll
+        for (int gq = 0; gq < 8; ++gq) {
+          const int co = gq * 16 + c;
+          if (gq * 16 < BN && co < p.Co) {
+            p.partials[(prow * p.Co + co) * 2 + 0] = run_s[gq];
+            p.partials[(prow * p.Co + co) * 2 + 1] = run_q[gq];
+          }
+        }
       }
-      if (et == 0) p.part_counts[blockIdx.x] = run_n;
+      if (lane == 0) p.part_counts[prow] = run_n;
     }
   }
   tc_fence_before();
@@ -365,39 +383,44 @@ __global__ void __launch_bounds__(kGconvThreads) gconv_tc_kernel(const __grid_co
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kTcThreads) wgrad_tc_kernel(const __grid_constant__ WGradParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  __shared__ TcShared sh;
+  __shared__ __align__(8) unsigned long long full[kMaxStages], empty[kMaxStages], accum;
+  __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int vi = blockIdx.z / p.nsplit, split = blockIdx.z % p.nsplit;
   const GVar& var = p.var[vi];
   const int BN = p.tc_bn, S = p.tc_stages;
   const int rowB = BN * 2;                     // bytes per pixel row of the dY tile: 32 / 64 / 128
   const int stageB = 64 * rowB;
+  const int kb = p.tc_kb, kbB = kb * 2;        // A^T sub-tile: 64 pixels x kb (tap,ci) values
+  const int sub_bytes = 64 * kbB;
   const int K = var.ntaps * p.Ci;
   const int k0 = blockIdx.x * 128, n0 = blockIdx.y * BN;
   const int m_lo = split * p.rows_per_split;
   const int m_hi = min(p.M, m_lo + p.rows_per_split);
   const int nchunks = (m_hi - m_lo + 63) >> 6;
+  const bool need_gather = !(p.tma_a && p.tma_b);
 
   const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = ring, b_base = ring + (uint32_t)S * kStageA;
 
   if (tid == 0) {
+    const int arrivals = (need_gather ? kGatherThreads : 0) + ((p.tma_a || p.tma_b) ? 1 : 0);
     for (int s = 0; s < S; ++s) {
-      mbar_init(smem_u32(&sh.full[s]), kGatherThreads);
-      mbar_init(smem_u32(&sh.empty[s]), 1);
+      mbar_init(smem_u32(&full[s]), arrivals);
+      mbar_init(smem_u32(&empty[s]), 1);
     }
-    mbar_init(smem_u32(&sh.accum), 1);
+    mbar_init(smem_u32(&accum), 1);
     fence_barrier_init();
   }
   const uint32_t ncols = BN <= 32 ? 32u : 64u;
-  if (warp == 4) tmem_alloc(smem_u32(&sh.tmem_base), ncols);
+  if (warp == 4) tmem_alloc(smem_u32(&tmem_base_s), ncols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = sh.tmem_base;
+  const uint32_t tmem = tmem_base_s;
 
   if (k0 >= K || nchunks <= 0) {
-    // nothing to do for this (variant, k-tile, split): variants of a stride-2 dgrad-style geometry differ in K
+    // nothing to do for this (variant, k-tile, split)
     tc_fence_before();
     __syncthreads();
     if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem, ncols); }
@@ -405,43 +428,74 @@ __global__ void __launch_bounds__(kTcThreads) wgrad_tc_kernel(const __grid_const
   }
 
   if (warp < 4) {
-    // A^T: thread -> 16-byte chunk jk (8 consecutive (tap,ci) indices) of pixels pg + 8*i
-    const int jk = tid & 15, pg = tid >> 4;
-    const int k = k0 + jk * 8;
-    const bool kin = k < K;
-    int ci = 0, dy = 0, dx = 0;
-    if (kin) { int tap; p.fd_ci.divmod(k, tap, ci); dy = var.dy[tap]; dx = var.dx[tap]; }
-    const uint32_t a_off = (uint32_t)(jk >> 3) * 8192u + (uint32_t)pg * 128u + (uint32_t)(((jk & 7) ^ pg) << 4);
-    // dY: 64 pixels x (BN/8) chunks, thread -> transfers e = tid + 128*q
-    const int cpr = BN >> 3;                   // chunks per pixel row: 2 / 4 / 8
-    const int cpr_log2 = cpr == 2 ? 1 : (cpr == 4 ? 2 : 3);
-    const int nb = cpr >> 1;                   // transfers per thread: 1 / 2 / 4
-    const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(p.in);
-    const __nv_bfloat16* dout = reinterpret_cast<const __nv_bfloat16*>(p.dout);
-    const int D = S - 1;
-    for (int it = 0; it < nchunks + D; ++it) {
-      if (it < nchunks) {
-        const int s = it % S;
-        if (it >= S) mbar_wait(smem_u32(&sh.empty[s]), (uint32_t)((it / S) - 1) & 1u);
-        const int mb = m_lo + it * 64;
-        const uint32_t adst = a_base + (uint32_t)s * kStageA + a_off;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int m = mb + pg + 8 * i;
-          if (!kin) continue;                    // rows k >= K of the accumulator are never read: leave the tile as is
-          bool ok = m < m_hi;
-          const __nv_bfloat16* src = in;
-          if (ok) {
-            int t, jj, n, ii;
-            p.fd_wg.divmod(m, t, jj);
-            p.fd_hg.divmod(t, n, ii);
-            int iy = ii * p.is + dy, ix = jj * p.is + dx;
-            ok = (unsigned)iy < (unsigned)p.Hi && (unsigned)ix < (unsigned)p.Wi;
-            if (ok) src = in + ((size_t)((n * p.Hi + iy) * p.Wi + ix) * p.Ci + ci);
+    // ---- TMA part: one thread ----
+    if (tid == 0 && (p.tma_a || p.tma_b)) {
+      const uint64_t tmap_a = reinterpret_cast<uint64_t>(&p.tmap_a);
+      const uint64_t tmap_b = reinterpret_cast<uint64_t>(&p.tmap_b);
+      const int nsub = (min(K, k0 + 128) - k0 + kb - 1) / kb;
+      const uint32_t bytes = (p.tma_a ? (uint32_t)(nsub * sub_bytes) : 0u) + (p.tma_b ? (uint32_t)stageB : 0u);
+      int stage = 0;
+      uint32_t ephase = 1;
+      for (int it = 0; it < nchunks; ++it) {
+        mbar_wait(smem_u32(&empty[stage]), ephase);
+        const uint32_t bar = smem_u32(&full[stage]);
+        mbar_arrive_expect_tx(bar, bytes);
+        int n0p, i0, j0, rem;
+        p.fd_hw.divmod(m_lo + it * 64, n0p, rem);
+        p.fd_wg.divmod(rem, i0, j0);
+        if (p.tma_a) {
+          for (int g = 0; g < nsub; ++g) {
+            int tap, ci;
+            p.fd_ci.divmod(k0 + g * kb, tap, ci);
+            tma_load_4d(a_base + (uint32_t)stage * kStageA + (uint32_t)g * sub_bytes, tmap_a, bar, ci,
+                        j0 * p.is + var.dx[tap], i0 * p.is + var.dy[tap], n0p);
           }
-          cp_async16(adst + (uint32_t)i * 1024u, src, ok ? 16u : 0u);
         }
-        const uint32_t bdst = b_base + (uint32_t)s * stageB;
+        if (p.tma_b)
+          tma_load_4d(b_base + (uint32_t)stage * stageB, tmap_b, bar, n0, var.ox0 + p.os * j0, var.oy0 + p.os * i0, n0p);
+        if (++stage == S) { stage = 0; ephase ^= 1u; }
+      }
+    }
+    if (need_gather) {
+      // ---- cp.async part ----
+      // A^T: thread -> 16-byte chunk jk (8 consecutive (tap,ci) indices) of pixels pg + 8*i
+      const int jk = tid & 15, pg = tid >> 4;
+      const int k = k0 + jk * 8;
+      const bool kin = k < K && !p.tma_a;        // rows k >= K of the accumulator are never read: leave them as they are
+      int ci = 0, dy = 0, dx = 0;
+      if (kin) { int tap; p.fd_ci.divmod(k, tap, ci); dy = var.dy[tap]; dx = var.dx[tap]; }
+      const uint32_t a_off = (uint32_t)(jk >> 3) * 8192u + (uint32_t)pg * 128u + (uint32_t)(((jk & 7) ^ pg) << 4);
+      // dY: 64 pixels x (BN/8) chunks, thread -> transfers e = tid + 128*q
+      const int cpr = BN >> 3;                   // chunks per pixel row: 2 / 4 / 8
+      const int cpr_log2 = cpr == 2 ? 1 : (cpr == 4 ? 2 : 3);
+      const int nb = p.tma_b ? 0 : (cpr >> 1);   // transfers per thread: 1 / 2 / 4
+      const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(p.in);
+      const __nv_bfloat16* dout = reinterpret_cast<const __nv_bfloat16*>(p.dout);
+      const int D = S - 1;
+      int stage = 0, sig_stage = 0;
+      uint32_t ephase = 1;
+      for (int it = 0; it < nchunks; ++it) {
+        mbar_wait(smem_u32(&empty[stage]), ephase);
+        const int mb = m_lo + it * 64;
+        if (kin) {
+          const uint32_t adst = a_base + (uint32_t)stage * kStageA + a_off;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int m = mb + pg + 8 * i;
+            bool ok = m < m_hi;
+            const __nv_bfloat16* src = in;
+            if (ok) {
+              int t, jj, n, ii;
+              p.fd_wg.divmod(m, t, jj);
+              p.fd_hg.divmod(t, n, ii);
+              int iy = ii * p.is + dy, ix = jj * p.is + dx;
+              ok = (unsigned)iy < (unsigned)p.Hi && (unsigned)ix < (unsigned)p.Wi;
+              if (ok) src = in + ((size_t)((n * p.Hi + iy) * p.Wi + ix) * p.Ci + ci);
+            }
+            cp_async16(adst + (uint32_t)i * 1024u, src, ok ? 16u : 0u);
+          }
+        }
+        const uint32_t bdst = b_base + (uint32_t)stage * stageB;
         for (int q = 0; q < nb; ++q) {
           const int e = tid + 128 * q;
           const int px = e >> cpr_log2, c = e & (cpr - 1);
@@ -461,41 +515,52 @@ __global__ void __launch_bounds__(kTcThreads) wgrad_tc_kernel(const __grid_const
           a ^= ((a >> 7) & (uint32_t)(cpr - 1)) << 4;
           cp_async16(bdst + a, src, ok ? 16u : 0u);
         }
+        cp_async_commit();
+        if (++stage == S) { stage = 0; ephase ^= 1u; }
+        if (it >= D) {
+          cp_async_wait_dyn(D);
+          fence_proxy_async_smem();
+          mbar_arrive(smem_u32(&full[sig_stage]));
+          if (++sig_stage == S) sig_stage = 0;
+        }
       }
-      cp_async_commit();
-      if (it >= D) {
-        cp_async_wait_dyn(D);
-        fence_proxy_async_smem();
-        mbar_arrive(smem_u32(&sh.full[(it - D) % S]));
+      cp_async_wait_dyn(0);
+      fence_proxy_async_smem();
+      for (int e = (nchunks < D ? nchunks : D); e > 0; --e) {
+        mbar_arrive(smem_u32(&full[sig_stage]));
+        if (++sig_stage == S) sig_stage = 0;
       }
     }
-  } else if (lane == 0) {
-    const uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
-    const uint32_t bswz = BN == 64 ? SWZ_128 : (BN == 32 ? SWZ_64 : SWZ_32);
-    for (int kc = 0; kc < nchunks; ++kc) {
-      const int s = kc % S;
-      mbar_wait(smem_u32(&sh.full[s]), (uint32_t)(kc / S) & 1u);
-      tc_fence_after();
-      const uint32_t sa = a_base + (uint32_t)s * kStageA, sb = b_base + (uint32_t)s * stageB;
+  } else if (warp == 4) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
+      const uint32_t bswz = swz_code(rowB), aswz = swz_code(kbB);
+      int stage = 0;
+      uint32_t fphase = 0;
+      for (int kc = 0; kc < nchunks; ++kc) {
+        mbar_wait(smem_u32(&full[stage]), fphase);
+        tc_fence_after();
+        const uint32_t sa = a_base + (uint32_t)stage * kStageA, sb = b_base + (uint32_t)stage * stageB;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {            // 16 pixels per MMA
-        uint64_t da = make_smem_desc(sa + q * 2048, 8192, 1024, SWZ_128);
-        uint64_t db = make_smem_desc(sb + q * 16 * rowB, 8 * rowB, 8 * rowB, bswz);
-        mma_bf16(tmem, da, db, idesc, (kc | q) != 0);
+        for (int q = 0; q < 4; ++q) {            // 16 pixels per MMA
+          uint64_t da = make_smem_desc(sa + q * 16 * kbB, (uint32_t)sub_bytes, 8 * kbB, aswz);
+          uint64_t db = make_smem_desc(sb + q * 16 * rowB, 8 * rowB, 8 * rowB, bswz);
+          mma_bf16(tmem, da, db, idesc, (kc | q) != 0);
+        }
+        mma_commit(smem_u32(&empty[stage]));
+        if (++stage == S) { stage = 0; fphase ^= 1u; }
       }
-      mma_commit(smem_u32(&sh.empty[s]));
+      mma_commit(smem_u32(&accum));
     }
-    mma_commit(smem_u32(&sh.accum));
-  }
-
-  if (warp < 4) {
-    mbar_wait(smem_u32(&sh.accum), 0);
+  } else {
+    mbar_wait(smem_u32(&accum), 0);
     tc_fence_after();
-    const int k = k0 + tid;
+    const int q = warp & 3;
+    const int k = k0 + q * 32 + lane;
     const bool kin = k < K;
     size_t wbase = 0;
-    if (kin) { int tap = k / p.Ci; int ci = k - tap * p.Ci; wbase = (size_t)var.wofs[tap] + (size_t)ci * p.w_sci; }
-    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+    if (kin) { int tap, ci; p.fd_ci.divmod(k, tap, ci); wbase = (size_t)var.wofs[tap] + (size_t)ci * p.w_sci; }
+    const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
     for (int c0 = 0; c0 < BN; c0 += 16) {
       float v[16];
       tmem_ld16(tlane + (uint32_t)c0, v);
@@ -561,6 +626,57 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const __grid_constant
 
 inline int pow2_floor(int x) { int r = 1; while (r * 2 <= x) r *= 2; return r; }
 
+// ---------------- host: TMA descriptors ----------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return (EncodeTiledFn)f;
+  }();
+  return fn;
+}
+
+// NHWC bf16 tensor [N][H][W][C]; box = cb channels x (bw x bh x bn) pixels visited with traversal stride `st`
+bool make_tmap(TmaDesc& out, const void* base, int N, int H, int W, int C, int cb, int bw, int bh, int bn, int st) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  static_assert(sizeof(CUtensorMap) == sizeof(TmaDesc), "TmaDesc must mirror CUtensorMap");
+  if (cb * 2 != 32 && cb * 2 != 64 && cb * 2 != 128) return false;
+  if (bw * st > 256 || bh * st > 256 || bn > 256) return false;
+  cuuint64_t dim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t str[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)cb, (cuuint32_t)(bw * st), (cuuint32_t)(bh * st), (cuuint32_t)bn};
+  cuuint32_t est[4] = {1u, (cuuint32_t)st, (cuuint32_t)st, 1u};
+  CUtensorMapSwizzle sw = cb * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (cb * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUresult r = fn(reinterpret_cast<CUtensorMap*>(&out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dim, str,
+                  box, est, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+// Is a run of `rows` consecutive gather-grid positions (n, i, j), starting at a multiple of `rows`, a box?
+bool pixel_box(int rows, int Hg, int Wg, int& bw, int& bh, int& bn) {
+  if (Wg > rows) { if (Wg % rows) return false; bw = rows; bh = 1; bn = 1; return true; }
+  if (rows % Wg) return false;
+  bw = Wg;
+  const int r = rows / Wg;
+  if (r <= Hg) { if (Hg % r) return false; bh = r; bn = 1; return true; }
+  if (r % Hg) return false;
+  bh = Hg; bn = r / Hg;
+  return true;
+}
+
+int tma_mask() {                        // bit 0: gconv A, bit 1: wgrad A, bit 2: wgrad dY   (MMVAE_TMA env, debugging)
+  static int m = [] { const char* e = getenv("MMVAE_TMA"); return e ? atoi(e) : 7; }();
+  return m;
+}
+
 }  // namespace
 
 bool tc_supported_gconv(const GConvParams& p) {
@@ -576,18 +692,25 @@ StatLayout launch_gconv_tc(const GConvParams& p0, cudaStream_t st) {
   GConvParams p = p0;
   const int tiles_m = (p.M + 127) / 128;
   const int co_pad = (p.Co + 15) & ~15;
-  // widest channel tile that still leaves >= ~1 CTA per SM; never narrower than 32 unless the layer is
-  int bn = co_pad > 128 ? 128 : pow2_floor(co_pad);   // <= 128: one epilogue thread per column for the statistics
+  // widest channel tile (<= 128) that still leaves >= ~1 CTA per SM; never narrower than 32 unless the layer is
+  int bn = co_pad > 128 ? 128 : pow2_floor(co_pad);
   if (co_pad % bn != 0) bn = 16;
   while (bn > 32 && (long long)tiles_m * p.nvar * ((co_pad + bn - 1) / bn) < 128) bn >>= 1;
-  int maxchunks = 1;
-  for (int v = 0; v < p.nvar; ++v) maxchunks = max(maxchunks, (p.var[v].ntaps * p.Ci + 63) / 64);
   const int stage_bytes = kStageA + bn * 128;
   int stages = min(kMaxStages, max(2, (100 * 1024) / stage_bytes));
   p.tc_bn = bn; p.tc_stages = stages; p.co_pad = co_pad;
   p.tiles_m = tiles_m; p.n_tiles = (co_pad + bn - 1) / bn; p.total_tiles = tiles_m * p.nvar * p.n_tiles;
-  p.tc_merge = (p.partials != nullptr && p.n_tiles == 1 && p.part_counts != nullptr) ? 1 : 0;
+  p.tc_merge = (p.partials != nullptr && p.n_tiles == 1) ? 1 : 0;
   p.fd_wg = FastDiv(p.Wg); p.fd_hg = FastDiv(p.Hg); p.fd_ci = FastDiv(p.Ci);
+  p.fd_hw = FastDiv(p.Hg * p.Wg); p.fd_ntiles = FastDiv(p.n_tiles); p.fd_nvar = FastDiv(p.nvar);
+  // TMA staging of A: the 128-pixel tile must be a box of the gather grid and the channel block a swizzle width
+  p.use_tma = 0; p.tc_kb = 64;
+  int bw, bh, bnb;
+  const int kb = p.Ci >= 64 ? 64 : p.Ci;
+  if ((tma_mask() & 1) && (kb == 16 || kb == 32 || kb == 64) && p.Ci % kb == 0 && pixel_box(128, p.Hg, p.Wg, bw, bh, bnb) &&
+      make_tmap(p.tmap_a, p.in, p.N, p.Hi, p.Wi, p.Ci, kb, bw, bh, bnb, p.is)) {
+    p.use_tma = 1; p.tc_kb = kb;
+  }
   const size_t smem = (size_t)stages * stage_bytes + 1024;
   static bool attr_done = false;
   if (!attr_done) {
@@ -596,12 +719,10 @@ StatLayout launch_gconv_tc(const GConvParams& p0, cudaStream_t st) {
   }
   const int grid = min(p.total_tiles, 2 * 148);
   count_launch();
-  gconv_tc_kernel<<<grid, kGconvThreads, smem, st>>>(p);
-  if (p.tc_merge) {
-    sl.parts = grid; sl.parts_per_var = grid; sl.tile_rows = 128; sl.rows_per_var = p.M; sl.counts = p.part_counts;
-  } else {
-    sl.parts = tiles_m * p.nvar; sl.parts_per_var = tiles_m; sl.tile_rows = 128; sl.rows_per_var = p.M;
-  }
+  gconv_tc_kernel<<<grid, kTcThreads, smem, st>>>(p);
+  sl.parts = 4 * (p.tc_merge ? grid : tiles_m * p.nvar);
+  sl.parts_per_var = sl.parts; sl.tile_rows = 32; sl.rows_per_var = p.M;
+  sl.counts = p.part_counts; sl.sumsq = 1;
   return sl;
 }
 
@@ -620,12 +741,24 @@ void launch_wgrad_tc(const WGradParams& p0, cudaStream_t st) {
   rps = (rps + 63) / 64 * 64;
   nsplit = (p.M + rps - 1) / rps;
   p.nsplit = nsplit; p.rows_per_split = rps; p.tc_bn = bn;
-  p.fd_wg = FastDiv(p.Wg); p.fd_hg = FastDiv(p.Hg); p.fd_ci = FastDiv(p.Ci);
+  p.fd_wg = FastDiv(p.Wg); p.fd_hg = FastDiv(p.Hg); p.fd_ci = FastDiv(p.Ci); p.fd_hw = FastDiv(p.Hg * p.Wg);
   const int nchunks = rps / 64;
   const int stage_bytes = kStageA + 64 * bn * 2;
   int stages = min(min(nchunks, kMaxStages), max(2, (100 * 1024) / stage_bytes));
   if (nchunks == 1) stages = 1;
   p.tc_stages = stages;
+  // TMA staging: a 64-pixel chunk must be a box of the gather grid
+  p.tma_a = p.tma_b = 0; p.tc_kb = 64;
+  int bw, bh, bnb;
+  const int kb = p.Ci >= 64 ? 64 : p.Ci;
+  if (pixel_box(64, p.Hg, p.Wg, bw, bh, bnb)) {
+    if ((tma_mask() & 2) && (kb == 16 || kb == 32 || kb == 64) && p.Ci % kb == 0 &&
+        make_tmap(p.tmap_a, p.in, p.N, p.Hi, p.Wi, p.Ci, kb, bw, bh, bnb, p.is)) {
+      p.tma_a = 1; p.tc_kb = kb;
+    }
+    if ((tma_mask() & 4) && p.Co % bn == 0 && make_tmap(p.tmap_b, p.dout, p.N, p.Ho, p.Wo, p.Co, bn, bw, bh, bnb, p.os))
+      p.tma_b = 1;
+  }
   const size_t smem = (size_t)stages * stage_bytes + 1024;
   static bool attr_done = false;
   if (!attr_done) {

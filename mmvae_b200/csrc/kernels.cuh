@@ -31,6 +31,9 @@ struct FastDiv {
 #endif
 };
 
+// Opaque copy of a CUtensorMap (TMA descriptor); lives inside the __grid_constant__ kernel parameter.
+struct alignas(64) TmaDesc { unsigned long long v[16]; };
+
 constexpr int kMaxTaps = 25;   // 5x5 stem conv
 constexpr int kMaxVar = 4;     // output-parity variants of a stride-2 transposed conv / dgrad
 
@@ -67,9 +70,11 @@ struct GConvParams {
   float* part_counts;          // rows behind each `partials` row when the kernel merges its tiles (or nullptr)
   // set by the launcher
   int tc_bn, tc_stages, tc_merge;
+  int tc_kb, use_tma;          // channels per A sub-tile; A staged by TMA boxes (else cp.async gather)
   int tiles_m, n_tiles, total_tiles;
-  FastDiv fd_wg, fd_hg, fd_ci;
+  FastDiv fd_wg, fd_hg, fd_ci, fd_hw, fd_ntiles, fd_nvar;
   GVar var[kMaxVar];
+  TmaDesc tmap_a;              // NHWC activation, box = tc_kb channels x 128 pixels
 };
 
 // Weight gradient of a gather-convolution: dW[wofs_t + ci*w_sci + co*w_sco] += sum_m in(m,t,ci) * dout(m,co)
@@ -84,14 +89,17 @@ struct WGradParams {
   int nvar, nsplit, rows_per_split;
   int in_nchw_f32;
   int tc_bn, tc_stages;        // set by the launcher (tcgen05 path)
-  FastDiv fd_wg, fd_hg, fd_ci;
+  int tc_kb, tma_a, tma_b;
+  FastDiv fd_wg, fd_hg, fd_ci, fd_hw;
   GVar var[kMaxVar];
+  TmaDesc tmap_a, tmap_b;      // layer input (box = tc_kb channels x 64 pixels) / dY (box = tc_bn channels x 64 pixels)
 };
 
 // Layout of the per-CTA partial statistics a conv kernel wrote: `parts` rows of [Co][2] = (sum, M2);
 // row i covers GEMM rows [(i % parts_per_var) * tile_rows, +tile_rows) of its variant, clipped to rows_per_var.
 // counts != nullptr: row i covers counts[i] rows instead (a persistent kernel merged its tiles).
-struct StatLayout { int parts, parts_per_var, tile_rows, rows_per_var; const float* counts = nullptr; };
+// sumsq: column 1 of a row is the plain sum of squares instead of M2.
+struct StatLayout { int parts, parts_per_var, tile_rows, rows_per_var; const float* counts = nullptr; int sumsq = 0; };
 
 template <typename T> StatLayout launch_gconv_simt(const GConvParams& p, cudaStream_t st);
 template <typename T> void launch_wgrad_simt(const WGradParams& p, cudaStream_t st);

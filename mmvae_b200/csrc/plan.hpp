@@ -152,7 +152,8 @@ struct Plan {
     int nvar = (kind == CONVT) ? 4 : 1;
     int64_t rows_per_var = (kind == CONVT) ? int64_t(d.batch) * Hi * Hi : m;
     if (kind == CONVT && k == 2) rows_per_var = d.batch;
-    size_t part_rows = size_t(nvar) * size_t((rows_per_var + 63) / 64);
+    // ... the tcgen05 kernels write one row per epilogue warp: 4 per 128-row tile, or 4 per CTA (<= 296 CTAs)
+    size_t part_rows = std::max<size_t>(size_t(nvar) * size_t((rows_per_var + 63) / 64) * 2 + 8, 1280);
     c.bn = add_bn(bn_prefix, Co, m, part_rows);
     // 2*MAC: forward + wgrad always, dgrad unless it is the first layer (input needs no gradient)
     int64_t macs = (kind == CONV) ? m * Co * int64_t(Ci) * k * k

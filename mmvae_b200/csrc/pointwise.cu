@@ -44,8 +44,11 @@ __global__ void __launch_bounds__(128) bn_finalize_kernel(const BnFinalizeArgs a
       int row0 = (i % a.sl.parts_per_var) * a.sl.tile_rows;
       double ni = a.sl.counts ? (double)a.sl.counts[i] : (double)min(a.sl.tile_rows, a.sl.rows_per_var - row0);
       if (ni <= 0.0) continue;
-      double mi = (double)a.partials[(size_t(i) * a.C + c) * 2 + 0] / ni - mu;
-      s2 += (double)a.partials[(size_t(i) * a.C + c) * 2 + 1] + ni * mi * mi;
+      const double si = (double)a.partials[(size_t(i) * a.C + c) * 2 + 0];
+      double m2i = (double)a.partials[(size_t(i) * a.C + c) * 2 + 1];
+      if (a.sl.sumsq) m2i = fmax(m2i - si * si / ni, 0.0);      // row carries sum of squares: M2 = sum x^2 - (sum x)^2 / n
+      double mi = si / ni - mu;
+      s2 += m2i + ni * mi * mi;
     }
     s2 = block_sum<128>(s2, sh);
     double vv = s2 / (double)a.m;

@@ -53,6 +53,14 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
                : "memory");
 }
 
+// TMA tiled load of a 4-D box (coordinates innermost first); out-of-bounds elements arrive as zeros
+__device__ __forceinline__ void tma_load_4d(uint32_t dst_smem, uint64_t tmap, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst_smem),
+      "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
 // ---------------- cp.async (16-byte, zero-fill when src_bytes == 0) ----------------
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
   // .ca: keep the line in L1 -- neighbouring taps / rows of the same tile re-read it
