@@ -8,6 +8,7 @@ fails if that library has not been built (`python -m mmvae_b200.build`).
 """
 from . import _lib
 from ._lib import MMVAEError
+from .graph import GraphedTrainStep
 from .model import VAE
 
-__all__ = ["VAE", "MMVAEError", "_lib"]
+__all__ = ["VAE", "GraphedTrainStep", "MMVAEError", "_lib"]

@@ -15,7 +15,7 @@ PREC_FP32, PREC_BF16 = 0, 1
 LOSS_GAUSSIAN, LOSS_CATEGORICAL = 0, 1
 BWD_DECODER, BWD_ENC_DEEP, BWD_ENC_SHALLOW, BWD_ALL = 1, 2, 4, 7
 FLAG_FORCE_SIMT = 1
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 EXPORTS = [
     "mmvae_abi_version", "mmvae_last_error", "mmvae_layout", "mmvae_param_entry", "mmvae_bn_entry",
@@ -63,7 +63,7 @@ def _load():
                                       POINTER(c_int32), POINTER(c_int32 * 4)]
     lib.mmvae_bn_entry.argtypes = [POINTER(Desc), c_int32, c_char_p, c_size_t, POINTER(c_int32), POINTER(c_int64)]
     lib.mmvae_workspace_tensor.argtypes = [POINTER(Desc), c_char_p, POINTER(c_int64), POINTER(c_int32 * 4)]
-    lib.mmvae_forward.argtypes = [POINTER(Desc), P, P, P, P, P, c_uint64, c_uint64, P, P, c_size_t, P, P, P, P, P]
+    lib.mmvae_forward.argtypes = [POINTER(Desc), P, P, P, P, P, c_uint64, c_uint64, P, P, P, c_size_t, P, P, P, P, P]
     lib.mmvae_decode.argtypes = [POINTER(Desc), P, P, P, P, P, c_size_t, P, P]
     lib.mmvae_loss_scratch_bytes.restype = c_size_t
     lib.mmvae_loss_forward.argtypes = [POINTER(LossArgs), P, P, P, P, P, P, P, P]

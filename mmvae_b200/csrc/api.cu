@@ -143,7 +143,22 @@ struct Exec {
     launch_pack_weights(tab, params, ws, st);
   }
 
-  // y = conv(in) with per-CTA partial statistics, then BatchNorm finalize
+  // fused training-mode statistics of BatchNorm b (bn_fused.cuh): accumulators were zeroed by clear_bn_acc()
+  BnFused bn_fused(const BnT& b) const {
+    BnFused f{};
+    f.acc = at<double>(b.acc_off); f.counter = at<unsigned int>(b.cnt_off);
+    f.gamma = params + b.gamma; f.beta = params + b.beta;
+    f.running_mean = bnbuf ? bnbuf + b.rm : nullptr;
+    f.running_var = bnbuf ? bnbuf + b.rm + b.C : nullptr;
+    f.nbt = counters ? counters + b.idx : nullptr;
+    f.stat = at<float>(b.stat_off); f.coef = at<float>(b.coef_off);
+    f.C = b.C; f.inv_m = 1.0 / (double)b.m; f.unbias = b.m > 1 ? (double)b.m / (double)(b.m - 1) : 1.0;
+    return f;
+  }
+  void clear_bn_acc() { cudaMemsetAsync(ws + P.bnacc_off, 0, P.bnacc_bytes, st); }
+
+  // y = conv(in) + BatchNorm statistics (fused into the producing kernel on the bf16 path; per-CTA partial rows
+  // and a finalize kernel on the SIMT path and in eval mode)
   void conv_bn_fwd(const ConvT_& c) {
     GConvParams g;
     geom_fprop(c, P.d.batch, g);
@@ -154,23 +169,30 @@ struct Exec {
     g.wpack = c.wp_chunks[DIR_FPROP] > 0 ? ws + c.wp_off[DIR_FPROP] : nullptr;
     g.bias = c.bias >= 0 ? params + c.bias : nullptr;
     const BnT& b = P.bns[c.bn];
-    g.partials = P.d.training ? at<float>(b.part_off) : nullptr;
-    g.part_counts = at<float>(b.pcnt_off);
-    StatLayout sl;
+    const bool training = P.d.training != 0;
+    bool fused = false;
+    StatLayout sl{0, 0, 0, 0};
     if (use_stem(c)) {
       StemArgs a{};
-      a.x = x; a.w = g.w; a.y = at<__nv_bfloat16>(act(c.out).off); a.partials = g.partials; a.N = P.d.batch; a.S = c.Hi;
-      sl = launch_stem_fwd(a, c.Co, st);
+      a.x = x; a.w = g.w; a.y = at<__nv_bfloat16>(act(c.out).off); a.N = P.d.batch; a.S = c.Hi;
+      if (training) { a.bn = bn_fused(b); fused = true; }
+      launch_stem_fwd(a, c.Co, st);
     } else if (use_tail(c)) {
       TailArgs a{};
       a.in = at<__nv_bfloat16>(act(c.in).off); a.w = g.w; a.bias = g.bias; a.y = at<__nv_bfloat16>(act(c.out).off);
-      a.partials = g.partials; a.N = P.d.batch; a.H = c.Hi; a.W = c.Wi;
-      sl = launch_tail_fwd(a, c.Ci, st);
+      a.N = P.d.batch; a.H = c.Hi; a.W = c.Wi;
+      if (training) { a.bn = bn_fused(b); fused = true; }
+      launch_tail_fwd(a, c.Ci, st);
+    } else if (std::is_same<T, __nv_bfloat16>::value && tc_supported_gconv(g)) {
+      if (training) { g.bn = bn_fused(b); fused = true; }
+      launch_gconv_tc(g, st);
     } else {
-      sl = conv_forward<T>(g, c, st);
+      g.partials = training ? at<float>(b.part_off) : nullptr;
+      sl = launch_gconv_simt<T>(g, st);
     }
+    if (fused) return;
     BnFinalizeArgs f;
-    f.partials = g.partials; f.sl = sl; f.C = b.C; f.m = b.m;
+    f.partials = training ? at<float>(b.part_off) : nullptr; f.sl = sl; f.C = b.C; f.m = b.m;
     f.gamma = params + b.gamma; f.beta = params + b.beta;
     f.running_mean = bnbuf ? bnbuf + b.rm : nullptr;
     f.running_var = bnbuf ? bnbuf + b.rm + b.C : nullptr;
@@ -197,8 +219,8 @@ struct Exec {
     apply(c2, &cs, b.out, 1);
   }
 
-  void encode(const float* eps, unsigned long long seed, unsigned long long offset, float* eps_out,
-              float* mu, float* logvar, float* enc) {
+  void encode(const float* eps, unsigned long long seed, unsigned long long offset, const uint64_t* rng_state,
+              float* eps_out, float* mu, float* logvar, float* enc) {
     const ConvT_& s = P.convs[P.stem];
     conv_bn_fwd(s);
     apply(s, nullptr, P.a_stem, 1);
@@ -207,7 +229,7 @@ struct Exec {
     const ActT& f = act(P.enc.back().out);
     h.feat = at<T>(f.off);
     h.w_mu = params + P.w_mu; h.w_lv = P.w_lv >= 0 ? params + P.w_lv : nullptr;
-    h.eps = eps; h.seed = seed; h.offset = offset;
+    h.eps = eps; h.seed = seed; h.offset = offset; h.rng_dev = reinterpret_cast<const unsigned long long*>(rng_state);
     h.pooled = at<float>(P.pooled_off); h.heads = at<float>(P.heads_off);
     h.mu_out = mu; h.lv_out = logvar; h.enc_out = enc; h.eps_out = eps_out;
     h.z_act = at<T>(act(P.a_z).off);
@@ -269,6 +291,7 @@ struct Exec {
     a.a = mask_act >= 0 ? at<T>(act(mask_act).off) : nullptr;
     a.y = at<T>(act(c.out).off); a.stat = at<float>(b.stat_off); a.gamma = params + b.gamma;
     a.partials = at<float>(b.bpart_off);
+    if (special_ok()) { a.acc = at<double>(b.acc_off) + kBnAccCopies * 2 * b.C; a.counter = at<unsigned int>(b.cnt_off) + 1; }
     a.bcoef = at<float>(b.bcoef_off);
     a.g_gamma = grads + b.gamma; a.g_beta = grads + b.beta;
     a.dY = at<T>(act(c.out).goff);
@@ -465,8 +488,8 @@ int mmvae_workspace_tensor(const mmvae_desc* d, const char* name, int64_t* byte_
 
 int mmvae_forward(const mmvae_desc* d, const float* x, const float* params, float* bn_buffers,
                   int64_t* bn_counters, const float* eps, uint64_t seed, uint64_t offset, float* eps_out,
-                  void* workspace, size_t workspace_bytes, float* mu, float* logvar, float* encoding,
-                  float* recon, void* stream) {
+                  const uint64_t* rng_state, void* workspace, size_t workspace_bytes, float* mu, float* logvar,
+                  float* encoding, float* recon, void* stream) {
   MMVAE_COMMON_CHECKS();
   if (!x || !params || !mu || !encoding || !recon) return fail(MMVAE_ERR_BAD_ARG, "x/params/mu/encoding/recon must be non-NULL");
   if (d->require_rsample && !logvar) return fail(MMVAE_ERR_BAD_ARG, "logvar must be non-NULL when require_rsample");
@@ -476,13 +499,14 @@ int mmvae_forward(const mmvae_desc* d, const float* x, const float* params, floa
   if (P.d.precision == MMVAE_PREC_FP32) {
     Exec<float> E{P, (char*)workspace, params, nullptr, bn_buffers, (long long*)bn_counters, st, x};
     if (!P.d.training) { E.counters = nullptr; }
-    E.encode(eps, seed, offset, eps_out, mu, logvar, encoding);
+    E.encode(eps, seed, offset, rng_state, eps_out, mu, logvar, encoding);
     E.decode(recon);
   } else {
     Exec<__nv_bfloat16> E{P, (char*)workspace, params, nullptr, bn_buffers, (long long*)bn_counters, st, x};
     if (!P.d.training) { E.counters = nullptr; }
+    E.clear_bn_acc();
     E.pack_weights();
-    E.encode(eps, seed, offset, eps_out, mu, logvar, encoding);
+    E.encode(eps, seed, offset, rng_state, eps_out, mu, logvar, encoding);
     E.decode(recon);
   }
   return check_launches("mmvae_forward");
@@ -502,6 +526,7 @@ int mmvae_decode(const mmvae_desc* d, const float* encoding, const float* params
   } else {
     Exec<__nv_bfloat16> E{P, (char*)workspace, params, nullptr, bn_buffers, (long long*)bn_counters, st, nullptr};
     if (!P.d.training) E.counters = nullptr;
+    E.clear_bn_acc();
     E.pack_weights();
     launch_cast_latent<__nv_bfloat16>(encoding, E.at<__nv_bfloat16>(P.acts[P.a_z].off), nz, st);
     E.decode(recon);
@@ -650,9 +675,10 @@ int mmvae_selftest_tc(const mmvae_desc* d, const float* params, void* workspace,
       launch_bn_finalize(f, st);
       cudaMemcpyAsync(E.at<float>(b.bcoef_off), E.at<float>(b.stat_off), sizeof(float) * 2 * b.C, cudaMemcpyDeviceToDevice, st);
       StemArgs sa{};
-      sa.x = xr; sa.w = params + c.w; sa.y = E.at<T>(ao.goff); sa.partials = g.partials; sa.N = N; sa.S = c.Hi;
-      f.sl = launch_stem_fwd(sa, c.Co, st);
-      launch_bn_finalize(f, st);
+      sa.x = xr; sa.w = params + c.w; sa.y = E.at<T>(ao.goff); sa.N = N; sa.S = c.Hi;
+      E.clear_bn_acc();
+      sa.bn = E.bn_fused(b);
+      launch_stem_fwd(sa, c.Co, st);
       selftest_cmp_kernel<T><<<148, 256, 0, st>>>(E.at<T>(ao.goff), E.at<T>(ao.off), n_out, rep + 0);
       selftest_cmp_kernel<float><<<1, 256, 0, st>>>(E.at<float>(b.stat_off), E.at<float>(b.bcoef_off), 2 * b.C, rep + 4);
       selftest_fill_kernel<<<296, 256, 0, st>>>(E.at<T>(ao.goff), n_out, 0x9876u + ci);
@@ -685,10 +711,11 @@ int mmvae_selftest_tc(const mmvae_desc* d, const float* params, void* workspace,
       launch_bn_finalize(f, st);
       cudaMemcpyAsync(E.at<float>(b.bcoef_off), E.at<float>(b.stat_off), sizeof(float) * 2 * b.C, cudaMemcpyDeviceToDevice, st);
       TailArgs ta{};
-      ta.in = E.at<T>(ai.off); ta.w = params + c.w; ta.bias = g.bias; ta.y = E.at<T>(ao.goff); ta.partials = g.partials;
+      ta.in = E.at<T>(ai.off); ta.w = params + c.w; ta.bias = g.bias; ta.y = E.at<T>(ao.goff);
       ta.N = N; ta.H = c.Hi; ta.W = c.Wi;
-      f.sl = launch_tail_fwd(ta, c.Ci, st);
-      launch_bn_finalize(f, st);
+      E.clear_bn_acc();
+      ta.bn = E.bn_fused(b);
+      launch_tail_fwd(ta, c.Ci, st);
       selftest_cmp_kernel<T><<<148, 256, 0, st>>>(E.at<T>(ao.goff), E.at<T>(ao.off), n_out, rep + 0);
       selftest_cmp_kernel<float><<<1, 256, 0, st>>>(E.at<float>(b.stat_off), E.at<float>(b.bcoef_off), 2 * b.C, rep + 4);
       // backward: dY random; SIMT wgrad + dgrad vs the fused tail_bwd
@@ -732,8 +759,10 @@ int mmvae_selftest_tc(const mmvae_desc* d, const float* params, void* workspace,
     launch_bn_finalize(f, st);
     cudaMemcpyAsync(E.at<float>(b.bcoef_off), E.at<float>(b.stat_off), sizeof(float) * 2 * b.C, cudaMemcpyDeviceToDevice, st);
     g.out = E.at<T>(ao.goff);
-    f.sl = launch_gconv_tc(g, st);
-    launch_bn_finalize(f, st);
+    g.partials = nullptr;
+    E.clear_bn_acc();
+    g.bn = E.bn_fused(b);
+    launch_gconv_tc(g, st);
     selftest_cmp_kernel<T><<<148, 256, 0, st>>>(E.at<T>(ao.goff), E.at<T>(ao.off), n_out, rep + 0);
     selftest_cmp_kernel<float><<<1, 256, 0, st>>>(E.at<float>(b.stat_off), E.at<float>(b.bcoef_off), 2 * b.C, rep + 4);
     // ---- wgrad: in = act(in), dY = random ----

@@ -19,6 +19,7 @@
 
 #include <cstdlib>
 
+#include "bn_fused.cuh"
 #include "geom.hpp"
 #include "kernels.cuh"
 #include "tc_common.cuh"
@@ -91,12 +92,15 @@ __device__ __forceinline__ void decode_tile(const GConvParams& p, int t, int& mt
   p.fd_nvar.divmod(r, mt, v);
 }
 
-__global__ void __launch_bounds__(kTcThreads) gconv_tc_kernel(const __grid_constant__ GConvParams p) {
+template <int kBN>
+__global__ void __launch_bounds__(kTcThreads, 3) gconv_tc_kernel(const __grid_constant__ GConvParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long full[kMaxStages], empty[kMaxStages], tfull[2], tempty[2];
   __shared__ uint32_t tmem_base_s;
+  __shared__ float stat_red[4][2][kBN];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int BN = p.tc_bn, S = p.tc_stages;
+  constexpr int BN = kBN;
+  const int S = p.tc_stages;
   const int stageB = BN * 128;
   const int kb = p.tc_kb;                       // channels per A sub-tile: 64 (gather) or min(Ci, 64) (TMA)
   const int kbB = kb * 2;                       // bytes per sub-tile row
@@ -268,15 +272,19 @@ __global__ void __launch_bounds__(kTcThreads) gconv_tc_kernel(const __grid_const
       }
     }
   } else {
-    // ---------------- epilogue: TMEM -> bf16 NHWC (+ BatchNorm partial statistics) ----------------
+    // ---------------- epilogue: TMEM -> bf16 NHWC (+ fused BatchNorm statistics) ----------------
+    constexpr int NG = kBN / 16;                         // 16-column groups
+    constexpr bool kPerThread = kBN == 16;               // statistics kept per thread (row) across tiles: no shuffles per tile
+    constexpr int NR = kPerThread ? 16 : NG;
     const int q = warp & 3;                              // TMEM lane quarter this warp may read
     const int r = q * 32 + lane;                         // tile row == TMEM lane
     __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
-    // merged mode: this lane's running (sum, sum of squares) of one column per 16-column group, over all tiles
-    float run_s[8], run_q[8];
+    const bool stats = p.bn.acc != nullptr;
+    const bool merge = p.tc_merge != 0;                  // one channel tile: sums can live in registers over all tiles
+    const int lane_col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+    float run_s[NR], run_q[NR];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { run_s[e] = 0.f; run_q[e] = 0.f; }
-    float run_n = 0.f;
+    for (int e = 0; e < NR; ++e) { run_s[e] = 0.f; run_q[e] = 0.f; }
     int i = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
       int mt, vi, nt;
@@ -295,79 +303,84 @@ __global__ void __launch_bounds__(kTcThreads) gconv_tc_kernel(const __grid_const
         valid = oy < p.Ho && ox < p.Wo;                  // ragged parity sub-grid of an odd-sized stride-2 dgrad
         obase = ((size_t)(n * p.Ho + oy) * p.Wo + ox) * p.Co;
       }
-      const float rows_here = (float)__popc(__ballot_sync(0xffffffffu, valid));
       mbar_wait(smem_u32(&tfull[buf]), (uint32_t)((i >> 1) & 1));
       tc_fence_after();
       const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
-      const size_t prow = p.tc_merge ? ((size_t)blockIdx.x * 4 + q) : (((size_t)vi * p.tiles_m + mt) * 4 + q);
 #pragma unroll
-      for (int gq = 0; gq < 8; ++gq) {
+      for (int gq = 0; gq < NG; ++gq) {
         const int c0 = gq * 16;
-        if (c0 < BN) {
-          float v[16];
-          tmem_ld16(tlane + (uint32_t)c0, v);
-          const int co0 = n0 + c0;
-          if (p.bias) {
+        float v[16];
+        tmem_ld16(tlane + (uint32_t)c0, v);
+        const int co0 = n0 + c0;
+        if (p.bias) {
 #pragma unroll
-            for (int e = 0; e < 16; ++e) if (co0 + e < p.Co) v[e] += __ldg(p.bias + co0 + e);
-          }
+          for (int e = 0; e < 16; ++e) if (co0 + e < p.Co) v[e] += __ldg(p.bias + co0 + e);
+        }
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int co = co0 + h * 8;
-            if (valid && co < p.Co) {
-              uint4* dst = reinterpret_cast<uint4*>(out + obase + co);
-              if (p.accumulate) {
-                uint4 old = *dst;
-                const __nv_bfloat16* o = reinterpret_cast<const __nv_bfloat16*>(&old);
+        for (int h = 0; h < 2; ++h) {
+          const int co = co0 + h * 8;
+          if (valid && co < p.Co) {
+            uint4* dst = reinterpret_cast<uint4*>(out + obase + co);
+            if (p.accumulate) {
+              uint4 old = *dst;
+              const __nv_bfloat16* o = reinterpret_cast<const __nv_bfloat16*>(&old);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[h * 8 + e] += __bfloat162float(o[e]);
-              }
-              uint4 pk;
-              pk.x = pack_bf16x2(v[h * 8 + 0], v[h * 8 + 1]); pk.y = pack_bf16x2(v[h * 8 + 2], v[h * 8 + 3]);
-              pk.z = pack_bf16x2(v[h * 8 + 4], v[h * 8 + 5]); pk.w = pack_bf16x2(v[h * 8 + 6], v[h * 8 + 7]);
-              *dst = pk;
+              for (int e = 0; e < 8; ++e) v[h * 8 + e] += __bfloat162float(o[e]);
             }
+            uint4 pk;
+            pk.x = pack_bf16x2(v[h * 8 + 0], v[h * 8 + 1]); pk.y = pack_bf16x2(v[h * 8 + 2], v[h * 8 + 3]);
+            pk.z = pack_bf16x2(v[h * 8 + 4], v[h * 8 + 5]); pk.w = pack_bf16x2(v[h * 8 + 6], v[h * 8 + 7]);
+            *dst = pk;
           }
-          if (p.partials) {
-            // statistics over the values as stored (after rounding), zero for rows / channels outside the tensor
+        }
+        if (stats) {
+          // statistics over the values as stored (after rounding), zero for rows / channels outside the tensor
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            v[e] = (valid && co0 + e < p.Co) ? __bfloat162float(__float2bfloat16_rn(v[e])) : 0.f;
+          if (kPerThread && merge) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) { run_s[e % NR] += v[e]; run_q[e % NR] = fmaf(v[e], v[e], run_q[e % NR]); }
+          } else {
             float sq[16];
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              v[e] = (valid && co0 + e < p.Co) ? __bfloat162float(__float2bfloat16_rn(v[e])) : 0.f;
-              sq[e] = v[e] * v[e];
-            }
-            const int c = warp_colsum16(v, lane);
+            for (int e = 0; e < 16; ++e) sq[e] = v[e] * v[e];
+            warp_colsum16(v, lane);
             warp_colsum16(sq, lane);
-            if (p.tc_merge) {
-              run_s[gq] += v[0]; run_q[gq] += sq[0];
-            } else if ((lane & 1) == 0 && co0 + c < p.Co) {
-              p.partials[(prow * p.Co + co0 + c) * 2 + 0] = v[0];
-              p.partials[(prow * p.Co + co0 + c) * 2 + 1] = sq[0];
+            if (merge) {
+              run_s[gq % NR] += v[0]; run_q[gq % NR] += sq[0];
+            } else if ((lane & 1) == 0 && co0 + lane_col < p.Co) {
+              atomicAdd(bn_acc_copy(p.bn) + co0 + lane_col, (double)v[0]);
+              atomicAdd(bn_acc_copy(p.bn) + p.bn.C + co0 + lane_col, (double)sq[0]);
             }
           }
         }
       }
       tc_fence_before();
       mbar_arrive(smem_u32(&tempty[buf]));               // accumulator buffer is free for tile i+2
-      if (p.partials) {
-        if (p.tc_merge) run_n += rows_here;
-        else if (lane == 0) p.part_counts[prow] = rows_here;
-      }
     }
-    if (p.partials && p.tc_merge) {
-      const int c = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-      const size_t prow = (size_t)blockIdx.x * 4 + q;
-      if ((lane & 1) == 0) {
+    if (stats && merge) {
+      // combine the four epilogue warps in shared memory, then one set of atomics per CTA
+      if constexpr (kPerThread) {
+        warp_colsum16(run_s, lane);                      // NR == 16 here
+        warp_colsum16(run_q, lane);
+        if ((lane & 1) == 0) { stat_red[q][0][lane_col] = run_s[0]; stat_red[q][1][lane_col] = run_q[0]; }
+      } else if ((lane & 1) == 0) {
 #pragma unroll
-        for (int gq = 0; gq < 8; ++gq) {
-          const int co = gq * 16 + c;
-          if (gq * 16 < BN && co < p.Co) {
-            p.partials[(prow * p.Co + co) * 2 + 0] = run_s[gq];
-            p.partials[(prow * p.Co + co) * 2 + 1] = run_q[gq];
-          }
+        for (int gq = 0; gq < NG; ++gq) {
+          stat_red[q][0][gq * 16 + lane_col] = run_s[gq % NR];
+          stat_red[q][1][gq * 16 + lane_col] = run_q[gq % NR];
         }
       }
-      if (lane == 0) p.part_counts[prow] = run_n;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int et = (warp - 5) * 32 + lane;
+      for (int e = et; e < 2 * kBN; e += 128) {
+        const int which = e / kBN, c = e - which * kBN;
+        if (c < p.Co) {
+          const float t = (stat_red[0][which][c] + stat_red[1][which][c]) + (stat_red[2][which][c] + stat_red[3][which][c]);
+          atomicAdd(bn_acc_copy(p.bn) + which * p.bn.C + c, (double)t);
+        }
+      }
     }
   }
   tc_fence_before();
@@ -376,6 +389,7 @@ __global__ void __launch_bounds__(kTcThreads) gconv_tc_kernel(const __grid_const
     tc_fence_after();
     tmem_dealloc(tmem, ncols);
   }
+  if (p.bn.acc) bn_fused_finish(p.bn, gridDim.x);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -697,10 +711,13 @@ StatLayout launch_gconv_tc(const GConvParams& p0, cudaStream_t st) {
   if (co_pad % bn != 0) bn = 16;
   while (bn > 32 && (long long)tiles_m * p.nvar * ((co_pad + bn - 1) / bn) < 128) bn >>= 1;
   const int stage_bytes = kStageA + bn * 128;
-  int stages = min(kMaxStages, max(2, (100 * 1024) / stage_bytes));
+  int maxchunks = 1;
+  for (int v = 0; v < p.nvar; ++v) maxchunks = max(maxchunks, (p.var[v].ntaps * p.Ci + 63) / 64);
+  // shallow-K layers live on many small CTAs per SM (latency hiding by occupancy), deep-K layers on a deep ring
+  int stages = maxchunks <= 2 ? 3 : min(kMaxStages, max(2, (100 * 1024) / stage_bytes));
   p.tc_bn = bn; p.tc_stages = stages; p.co_pad = co_pad;
   p.tiles_m = tiles_m; p.n_tiles = (co_pad + bn - 1) / bn; p.total_tiles = tiles_m * p.nvar * p.n_tiles;
-  p.tc_merge = (p.partials != nullptr && p.n_tiles == 1) ? 1 : 0;
+  p.tc_merge = p.n_tiles == 1 ? 1 : 0;
   p.fd_wg = FastDiv(p.Wg); p.fd_hg = FastDiv(p.Hg); p.fd_ci = FastDiv(p.Ci);
   p.fd_hw = FastDiv(p.Hg * p.Wg); p.fd_ntiles = FastDiv(p.n_tiles); p.fd_nvar = FastDiv(p.nvar);
   // TMA staging of A: the 128-pixel tile must be a box of the gather grid and the channel block a swizzle width
@@ -714,16 +731,22 @@ StatLayout launch_gconv_tc(const GConvParams& p0, cudaStream_t st) {
   const size_t smem = (size_t)stages * stage_bytes + 1024;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(gconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(gconv_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(gconv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(gconv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(gconv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_done = true;
   }
-  const int grid = min(p.total_tiles, 2 * 148);
+  const int per_sm = smem <= 72 * 1024 ? 3 : 2;
+  const int grid = min(p.total_tiles, per_sm * 148);
   count_launch();
-  gconv_tc_kernel<<<grid, kTcThreads, smem, st>>>(p);
-  sl.parts = 4 * (p.tc_merge ? grid : tiles_m * p.nvar);
-  sl.parts_per_var = sl.parts; sl.tile_rows = 32; sl.rows_per_var = p.M;
-  sl.counts = p.part_counts; sl.sumsq = 1;
-  return sl;
+  switch (bn) {
+    case 16: gconv_tc_kernel<16><<<grid, kTcThreads, smem, st>>>(p); break;
+    case 32: gconv_tc_kernel<32><<<grid, kTcThreads, smem, st>>>(p); break;
+    case 64: gconv_tc_kernel<64><<<grid, kTcThreads, smem, st>>>(p); break;
+    default: gconv_tc_kernel<128><<<grid, kTcThreads, smem, st>>>(p); break;
+  }
+  return sl;       // statistics are finalised inside the kernel (p.bn); no partial rows
 }
 
 void launch_wgrad_tc(const WGradParams& p0, cudaStream_t st) {

@@ -31,6 +31,18 @@ struct FastDiv {
 #endif
 };
 
+// Training-mode BatchNorm statistics folded into the producing kernel (bn_fused.cuh).  acc == nullptr: off.
+constexpr int kBnAccCopies = 8;
+struct BnFused {
+  double* acc;                 // [kBnAccCopies][2][C] sum, sum of squares -- zeroed before the kernel
+  unsigned int* counter;       // CTAs finished -- zeroed before the kernel
+  const float* gamma; const float* beta;
+  float* running_mean; float* running_var; long long* nbt;   // nullptr: do not update
+  float* stat; float* coef;    // outputs [2][C] each: (mean, rstd), (scale, shift)
+  int C;
+  double inv_m, unbias;        // 1/m and m/(m-1) for the m = N*H*W values per channel
+};
+
 // Opaque copy of a CUtensorMap (TMA descriptor); lives inside the __grid_constant__ kernel parameter.
 struct alignas(64) TmaDesc { unsigned long long v[16]; };
 
@@ -68,6 +80,7 @@ struct GConvParams {
   int wpack_var_stride;        // bytes between variants
   int co_pad;                  // Co rounded up to 16
   float* part_counts;          // rows behind each `partials` row when the kernel merges its tiles (or nullptr)
+  BnFused bn;                  // tcgen05 / stem / tail kernels: fused statistics (bn.acc != nullptr)
   // set by the launcher
   int tc_bn, tc_stages, tc_merge;
   int tc_kb, use_tma;          // channels per A sub-tile; A staged by TMA boxes (else cp.async gather)
@@ -128,6 +141,7 @@ struct StemArgs {
   const float* w;              // [Co][1][5][5] fp32
   __nv_bfloat16* y;            // forward: [N,Ho,Wo,Co]
   float* partials;             // forward: [tiles][Co][2] or nullptr
+  BnFused bn;                  // forward: fused statistics when bn.acc != nullptr (then `partials` is unused)
   const __nv_bfloat16* dy;     // wgrad: dY [N,Ho,Wo,Co]
   float* dw;                   // wgrad: gradient arena slot (atomically accumulated; pre-zeroed)
   int N, S;
@@ -139,6 +153,7 @@ struct TailArgs {
   const float* bias;           // [1] or nullptr
   __nv_bfloat16* y;            // forward: [N,H,W,1]
   float* partials;             // forward: [tiles][1][2] or nullptr
+  BnFused bn;                  // forward: fused statistics when bn.acc != nullptr (then `partials` is unused)
   const __nv_bfloat16* dy;     // backward: dY [N,H,W,1]
   __nv_bfloat16* dx;           // backward: dX [N,H,W,Ci]
   float* dw;                   // backward: gradient arena slot (atomically accumulated; pre-zeroed)
@@ -178,6 +193,7 @@ struct HeadsArgs {
   const float* w_mu; const float* w_lv;   // [z][C] fp32 (w_lv may be nullptr)
   const float* eps;        // [N][z] or nullptr -> Philox
   unsigned long long seed, offset;
+  const unsigned long long* rng_dev;   // device {seed, offset} overriding the pair above, or nullptr
   float* pooled;           // [N][C]
   float* heads;            // [4][N][z]: mu, logvar, eps, std
   float* mu_out; float* lv_out; float* enc_out; float* eps_out;   // user-visible fp32 outputs
@@ -209,6 +225,8 @@ struct BnBwdArgs {
   const void* y;  const float* stat;  const float* gamma;           // main branch
   const void* y2; const float* stat2; const float* gamma2;          // second branch or nullptr
   float* partials;         // [blocks][C][3]
+  double* acc;             // bf16 mode: [kBnAccCopies][3][C] fp64 accumulators (zeroed) + last-block finalize; nullptr: partials path
+  unsigned int* counter;   // blocks finished (zeroed)
   float* bcoef; float* bcoef2;       // [3][C]: scale, c1, c2
   float* g_gamma; float* g_beta; float* g_gamma2; float* g_beta2;   // gradient arena slots
   void* dY; void* dY2;     // outputs, storage type

@@ -46,6 +46,8 @@ struct BnT {               // one BatchNorm2d
   size_t pcnt_off = 0;           // fp32 [max(P, 1024)]: rows behind each partial row (persistent kernels)
   size_t bpart_off = 0;          // fp32 backward partial sums [PB][C][3]
   size_t bcoef_off = 0;          // fp32 [3][C]: backward coefficients (scale, c1, c2)
+  size_t acc_off = 0;            // fp64 [8 copies][2][C] forward (sum, sumsq) then [8 copies][3][C] backward (s0, s1, s2)
+  size_t cnt_off = 0;            // uint32 [2]: CTA-done counters (fwd, bwd)
 };
 
 enum ConvKind { CONV = 0, CONVT = 1 };
@@ -94,6 +96,7 @@ struct Plan {
   size_t dheads_off = 0;             // fp32 [N][z] x 3: dmu, dlogvar, dz
   size_t dpool_off = 0;              // fp32 [N][feat_c]
   size_t drecon_off = 0;             // fp32 NHWC copy of d_recon when out_channels > 1
+  size_t bnacc_off = 0, bnacc_bytes = 0;   // all BatchNorm accumulators + counters: one memset per forward
   size_t ws_bytes = 0;
   int64_t train_flops = 0;
   std::string err;
@@ -231,6 +234,16 @@ struct Plan {
     if (curH != dec_size) { err = "decoder size mismatch"; return false; }
     tail = add_conv("decoder.conv2", "decoder.bn2", CONV, 3, 1, 1, curC, d.out_channels, curH, cur, true);
     drecon_off = bump(sizeof(float) * size_t(d.batch) * dec_size * dec_size * d.out_channels);
+
+    // ---------------- fused BatchNorm statistics: accumulators, contiguous ----------------
+    {
+      size_t total = 0;
+      for (auto& b : bns) { b.acc_off = total; total += sizeof(double) * 8 * 5 * b.C; }
+      for (auto& b : bns) { b.cnt_off = total; total += 16; }
+      bnacc_bytes = total;
+      bnacc_off = bump(total);
+      for (auto& b : bns) { b.acc_off += bnacc_off; b.cnt_off += bnacc_off; }
+    }
 
     // ---------------- packed weights of the tcgen05 path ----------------
     if (d.precision == MMVAE_PREC_BF16 && !(d.flags & MMVAE_FLAG_FORCE_SIMT)) {

@@ -5,6 +5,7 @@
 // buffers updated with momentum 0.1 and the unbiased variance, num_batches_tracked += 1.
 // The per-channel sums come from the producing conv's epilogue as per-CTA partials and are
 // combined here in a fixed order in fp64, so a step is bit-reproducible.
+#include "bn_fused.cuh"
 #include "kernels.cuh"
 
 namespace mmvae {
@@ -172,7 +173,7 @@ __global__ void __launch_bounds__(128) heads_fwd_kernel(const HeadsArgs a) {
     float lv = 0.f, eps = 0.f, sd = 0.f, enc = mu;
     if (a.w_lv) {
       lv = outv[a.z + zc];
-      eps = a.eps ? a.eps[idx] : philox_normal_at(a.seed, a.offset, (long long)idx);
+      eps = a.eps ? a.eps[idx] : philox_normal_at(a.rng_dev ? a.rng_dev[0] : a.seed, a.rng_dev ? a.rng_dev[1] : a.offset, (long long)idx);
       sd = expf(0.5f * lv);
       enc = fmaf(eps, sd, mu);
     }
@@ -277,7 +278,36 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
     int which = e / a.C, c = e % a.C;
     float s = 0.f;
     for (int q = 0; q < RPI; ++q) s += red[(which * RPI + q) * a.C + c];
-    a.partials[(size_t(blockIdx.x) * a.C + c) * 3 + which] = s;
+    if (a.acc) atomicAdd(a.acc + (size_t)(blockIdx.x % kBnAccCopies) * 3 * a.C + which * a.C + c, (double)s);
+    else a.partials[(size_t(blockIdx.x) * a.C + c) * 3 + which] = s;
+  }
+  if (!a.acc) return;
+  // fused finalize: the block that finishes last turns the fp64 sums into the backward coefficients
+  __shared__ int is_last;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) is_last = (atomicAdd(a.counter, 1u) == gridDim.x - 1u) ? 1 : 0;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const double im = 1.0 / (double)a.rows;
+  for (int c = tid; c < a.C; c += 256) {
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < kBnAccCopies; ++k) {
+      const double* ak = a.acc + (size_t)k * 3 * a.C;
+      s0 += ld_cg_f64(ak + c); s1 += ld_cg_f64(ak + a.C + c); s2 += ld_cg_f64(ak + 2 * a.C + c);
+    }
+    a.g_beta[c] = (float)s0; a.g_gamma[c] = (float)s1;
+    a.bcoef[c] = a.gamma[c] * a.stat[a.C + c];
+    a.bcoef[a.C + c] = (float)(s0 * im);
+    a.bcoef[2 * a.C + c] = (float)(s1 * im);
+    if (a.y2) {
+      a.g_beta2[c] = (float)s0; a.g_gamma2[c] = (float)s2;
+      a.bcoef2[c] = a.gamma2[c] * a.stat2[a.C + c];
+      a.bcoef2[a.C + c] = (float)(s0 * im);
+      a.bcoef2[2 * a.C + c] = (float)(s2 * im);
+    }
   }
 }
 
@@ -425,8 +455,10 @@ void launch_bn_bwd(const BnBwdArgs& a, cudaStream_t st) {
   if (nblocks < 1) nblocks = 1;
   if (vec_ok) { count_launch(); bn_bwd_reduce_kernel<T, V><<<nblocks, 256, 0, st>>>(a); }
   else { count_launch(); bn_bwd_reduce_kernel<T, 1><<<nblocks, 256, 0, st>>>(a); }
-  count_launch();
-  bn_bwd_finalize_kernel<<<a.C, 128, 0, st>>>(a, nblocks, a.rows);
+  if (!a.acc) {
+    count_launch();
+    bn_bwd_finalize_kernel<<<a.C, 128, 0, st>>>(a, nblocks, a.rows);
+  }
   long long total = a.rows * a.C;
   if (a.C % V == 0) { count_launch(); bn_bwd_apply_kernel<T, V><<<grid_for(total / V), 256, 0, st>>>(a); }
   else { count_launch(); bn_bwd_apply_kernel<T, 1><<<grid_for(total), 256, 0, st>>>(a); }

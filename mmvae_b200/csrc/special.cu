@@ -9,6 +9,7 @@
 //
 // All of them walk tiles of whole output rows of one frame; tiles are numbered so that tile i covers
 // GEMM rows [i * tile_rows, (i+1) * tile_rows), which is what bn_finalize's StatLayout expects.
+#include "bn_fused.cuh"
 #include "kernels.cuh"
 
 namespace mmvae {
@@ -45,9 +46,10 @@ __global__ void __launch_bounds__(256) stem_fwd_kernel(const StemArgs a) {
   constexpr int H = CO / 2;                          // channels per thread
   __shared__ float xs[kStemMaxRows * kStemMaxCols];
   __shared__ __align__(16) float ws[25 * CO];
-  __shared__ float wsum[8][CO];
-  __shared__ float mean_s[CO];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
+  float run_s[H], run_q[H];
+#pragma unroll
+  for (int j = 0; j < H; ++j) { run_s[j] = 0.f; run_q[j] = 0.f; }
   for (int e = tid; e < 25 * CO; e += 256) { int co = e / 25, t = e - co * 25; ws[t * CO + co] = __ldg(a.w + e); }
   const int rows = 2 * a.R + 3, cols = 2 * a.Wo + 3;
   const int p = tid >> 1, h = tid & 1;
@@ -55,7 +57,7 @@ __global__ void __launch_bounds__(256) stem_fwd_kernel(const StemArgs a) {
   const bool in_tile = p < a.R * a.Wo;
   for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
     const int n = tile / a.tiles_per_frame, oy0 = (tile - n * a.tiles_per_frame) * a.R;
-    __syncthreads();                                 // previous tile's readers are done with xs / wsum
+    __syncthreads();                                 // previous tile's readers are done with xs
     stem_load_x(a, n, oy0, xs, rows, cols, 256);
     __syncthreads();
     float acc[H];
@@ -86,51 +88,30 @@ __global__ void __launch_bounds__(256) stem_fwd_kernel(const StemArgs a) {
 #pragma unroll
       for (int j = 0; j < H; ++j) acc[j] = bf16_round(acc[j]);      // statistics over the values as stored
     }
-    if (a.partials) {
-      const int n_valid = a.R * a.Wo;
-      // pass 1: per-channel sums over the tile (lanes of equal parity hold the same channel half)
-      float s[H];
+    if (a.bn.acc) {
 #pragma unroll
-      for (int j = 0; j < H; ++j) {
-        float v = acc[j];
-#pragma unroll
-        for (int d = 2; d < 32; d <<= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-        s[j] = v;
-      }
-      if (lane < 2) {
-#pragma unroll
-        for (int j = 0; j < H; ++j) wsum[warp][h * H + j] = s[j];
-      }
-      __syncthreads();
-      if (tid < CO) {
-        float t = 0.f;
-#pragma unroll
-        for (int w8 = 0; w8 < 8; ++w8) t += wsum[w8][tid];
-        mean_s[tid] = t / (float)n_valid;
-        a.partials[((size_t)tile * CO + tid) * 2 + 0] = t;
-      }
-      __syncthreads();
-      // pass 2: M2 about the tile mean
-#pragma unroll
-      for (int j = 0; j < H; ++j) {
-        float d0 = in_tile ? acc[j] - mean_s[h * H + j] : 0.f;
-        float v = d0 * d0;
-#pragma unroll
-        for (int d = 2; d < 32; d <<= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-        s[j] = v;
-      }
-      if (lane < 2) {
-#pragma unroll
-        for (int j = 0; j < H; ++j) wsum[warp][h * H + j] = s[j];
-      }
-      __syncthreads();
-      if (tid < CO) {
-        float t = 0.f;
-#pragma unroll
-        for (int w8 = 0; w8 < 8; ++w8) t += wsum[w8][tid];
-        a.partials[((size_t)tile * CO + tid) * 2 + 1] = t;
-      }
+      for (int j = 0; j < H; ++j) { run_s[j] += acc[j]; run_q[j] = fmaf(acc[j], acc[j], run_q[j]); }
     }
+  }
+  if (a.bn.acc) {
+    // per-channel sums over this CTA's pixels: lanes of equal parity hold the same channel half
+    __shared__ float wred[8][2][CO];
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+      float v = run_s[j], w = run_q[j];
+#pragma unroll
+      for (int d = 2; d < 32; d <<= 1) { v += __shfl_xor_sync(0xffffffffu, v, d); w += __shfl_xor_sync(0xffffffffu, w, d); }
+      if (lane < 2) { wred[tid >> 5][0][h * H + j] = v; wred[tid >> 5][1][h * H + j] = w; }
+    }
+    __syncthreads();
+    if (tid < 2 * CO) {
+      const int which = tid / CO, c = tid - which * CO;
+      float t = 0.f;
+#pragma unroll
+      for (int w8 = 0; w8 < 8; ++w8) t += wred[w8][which][c];
+      atomicAdd(bn_acc_copy(a.bn) + which * CO + c, (double)t);
+    }
+    bn_fused_finish(a.bn, gridDim.x);
   }
 }
 
@@ -226,6 +207,7 @@ __global__ void __launch_bounds__(kTailThreads) tail_fwd_kernel(const TailArgs a
   const int p = tid / G, grp = tid - p * G;
   const int oy_l = p / a.W, ox = p - oy_l * a.W;
   const uint4* in = reinterpret_cast<const uint4*>(a.in);
+  float run_s = 0.f, run_q = 0.f;
   for (int t_i = blockIdx.x; t_i < a.ntiles; t_i += gridDim.x) {
     const int n = t_i / a.tiles_per_frame, oy0 = (t_i - n * a.tiles_per_frame) * a.R;
     __syncthreads();
@@ -255,14 +237,13 @@ __global__ void __launch_bounds__(kTailThreads) tail_fwd_kernel(const TailArgs a
     const size_t m = ((size_t)n * a.H + oy0 + oy_l) * a.W + ox;
     const __nv_bfloat16 o = __float2bfloat16_rn(acc);
     if (grp == 0) a.y[m] = o;
-    if (a.partials) {
-      const float v = grp == 0 ? __bfloat162float(o) : 0.f;
-      const float s = block_sum512(v, sh);
-      const float mean = s / (float)PX;
-      const float d = grp == 0 ? v - mean : 0.f;
-      const float m2 = block_sum512(d * d, sh);
-      if (tid == 0) { a.partials[(size_t)t_i * 2 + 0] = s; a.partials[(size_t)t_i * 2 + 1] = m2; }
-    }
+    if (a.bn.acc && grp == 0) { const float v = __bfloat162float(o); run_s += v; run_q = fmaf(v, v, run_q); }
+  }
+  if (a.bn.acc) {
+    const float s = block_sum512(run_s, sh);
+    const float q = block_sum512(run_q, sh);
+    if (tid == 0) { atomicAdd(bn_acc_copy(a.bn), (double)s); atomicAdd(bn_acc_copy(a.bn) + 1, (double)q); }
+    bn_fused_finish(a.bn, gridDim.x);
   }
 }
 
@@ -364,28 +345,37 @@ __global__ void __launch_bounds__(kTailThreads) tail_bwd_kernel(const TailArgs a
   }
 }
 
-template <int NZ>
-__global__ void __launch_bounds__(128) heads_wgrad2_kernel(const float* __restrict__ dh, const float* __restrict__ pooled,
+// dW_head[zc][c] = sum_n dhead[n][zc] * pooled[n][c].  Block = 8 latent rows x 64 channels, 4 slices of the batch;
+// blockIdx.y selects mu / logvar, blockIdx.z the channel block.
+__global__ void __launch_bounds__(256) heads_wgrad2_kernel(const float* __restrict__ dh, const float* __restrict__ pooled,
                                                            float* __restrict__ g_mu, float* __restrict__ g_lv,
                                                            int N, int z, int C) {
-  // dW_head[zc][c] = sum_n dhead[n][zc] * pooled[n][c]; blockIdx.y selects mu / logvar
+  __shared__ float red[4][8][64];
   const float* d = dh + (size_t)blockIdx.y * N * z;
   float* gw = blockIdx.y == 0 ? g_mu : g_lv;
-  const int zc0 = blockIdx.x * NZ;
-  for (int c = threadIdx.x; c < C; c += 128) {
-    float s[NZ];
+  const int zc0 = blockIdx.x * 8;
+  const int cl = threadIdx.x & 63, sl = threadIdx.x >> 6;
+  const int c = blockIdx.z * 64 + cl;
+  float s[8];
 #pragma unroll
-    for (int j = 0; j < NZ; ++j) s[j] = 0.f;
+  for (int j = 0; j < 8; ++j) s[j] = 0.f;
+  if (c < C) {
 #pragma unroll 4
-    for (int n = 0; n < N; ++n) {
+    for (int n = sl; n < N; n += 4) {
       const float pv = __ldg(pooled + (size_t)n * C + c);
+      const float* dr = d + (size_t)n * z + zc0;
 #pragma unroll
-      for (int j = 0; j < NZ; ++j)
-        if (zc0 + j < z) s[j] = fmaf(__ldg(d + (size_t)n * z + zc0 + j), pv, s[j]);
+      for (int j = 0; j < 8; ++j) s[j] = fmaf(zc0 + j < z ? __ldg(dr + j) : 0.f, pv, s[j]);
     }
+  }
 #pragma unroll
-    for (int j = 0; j < NZ; ++j)
-      if (zc0 + j < z) gw[(size_t)(zc0 + j) * C + c] = s[j];
+  for (int j = 0; j < 8; ++j) red[sl][j][cl] = s[j];
+  __syncthreads();
+  for (int e = threadIdx.x; e < 8 * 64; e += 256) {
+    const int j = e >> 6, cc = e & 63;
+    const int co = blockIdx.z * 64 + cc;
+    if (zc0 + j < z && co < C)
+      gw[(size_t)(zc0 + j) * C + co] = (red[0][j][cc] + red[1][j][cc]) + (red[2][j][cc] + red[3][j][cc]);
   }
 }
 
@@ -415,18 +405,16 @@ static void stem_fill(StemArgs& a) {
 
 StatLayout launch_stem_fwd(StemArgs a, int Co, cudaStream_t st) {
   stem_fill(a);
-  const int grid = min(a.ntiles, 148 * 6);
+  const int grid = min(a.ntiles, 148 * 3);
   count_launch();
   if (Co == 32) stem_fwd_kernel<32><<<grid, 256, 0, st>>>(a);
   else stem_fwd_kernel<64><<<grid, 256, 0, st>>>(a);
-  StatLayout sl;
-  sl.parts = a.ntiles; sl.parts_per_var = a.ntiles; sl.tile_rows = a.R * a.Wo; sl.rows_per_var = a.N * a.Ho * a.Wo;
-  return sl;
+  return StatLayout{0, 0, 0, 0};     // statistics are finalised inside the kernel (a.bn)
 }
 
 void launch_stem_wgrad(StemArgs a, int Co, cudaStream_t st) {
   stem_fill(a);
-  const int grid = min(a.ntiles, 148);
+  const int grid = min(a.ntiles, 2 * 148);
   count_launch();
   if (Co == 32) stem_wgrad_kernel<32><<<grid, 320, 0, st>>>(a);
   else stem_wgrad_kernel<64><<<grid, 320, 0, st>>>(a);
@@ -452,9 +440,7 @@ StatLayout launch_tail_fwd(TailArgs a, int Ci, cudaStream_t st) {
   count_launch();
   if (Ci == 16) tail_fwd_kernel<16><<<grid, kTailThreads, smem, st>>>(a);
   else tail_fwd_kernel<32><<<grid, kTailThreads, smem, st>>>(a);
-  StatLayout sl;
-  sl.parts = a.ntiles; sl.parts_per_var = a.ntiles; sl.tile_rows = a.R * a.W; sl.rows_per_var = a.N * a.H * a.W;
-  return sl;
+  return StatLayout{0, 0, 0, 0};     // statistics are finalised inside the kernel (a.bn)
 }
 
 void launch_tail_bwd(TailArgs a, int Ci, cudaStream_t st) {
@@ -468,10 +454,9 @@ void launch_tail_bwd(TailArgs a, int Ci, cudaStream_t st) {
 
 void launch_heads_wgrad(const float* dheads, const float* pooled, float* g_mu, float* g_lv, int N, int z, int C,
                         cudaStream_t st) {
-  constexpr int NZ = 4;
-  dim3 grid((z + NZ - 1) / NZ, g_lv ? 2 : 1);
+  dim3 grid((z + 7) / 8, g_lv ? 2 : 1, (C + 63) / 64);
   count_launch();
-  heads_wgrad2_kernel<NZ><<<grid, 128, 0, st>>>(dheads, pooled, g_mu, g_lv, N, z, C);
+  heads_wgrad2_kernel<<<grid, 256, 0, st>>>(dheads, pooled, g_mu, g_lv, N, z, C);
 }
 
 }  // namespace mmvae

@@ -42,15 +42,19 @@ def synthetic_labels(n_frames, size=64, seq_len=20, seed=1234, device="cpu"):
     return out.to(device)
 
 
-def prepare_input(labels, data_mean=DATA_MEAN, data_std=DATA_STD, want_target=False):
+def prepare_input(labels, data_mean=DATA_MEAN, data_std=DATA_STD, want_target=False, out=None, out_target=None):
     """Device side of main.py:381-388: uint8 label map [N,H,W] (CUDA) -> x = (label - mean)/std as
     [N,1,H,W] fp32, and the int64 cross-entropy target when `want_target`."""
     if not labels.is_cuda or labels.dtype != torch.uint8:
         raise ValueError("labels must be a CUDA uint8 tensor")
     labels = labels.contiguous()
     n, h, w = labels.shape
-    x = torch.empty(n, 1, h, w, dtype=torch.float32, device=labels.device)
-    tgt = torch.empty(n, h, w, dtype=torch.int64, device=labels.device) if want_target else None
+    x = out if out is not None else torch.empty(n, 1, h, w, dtype=torch.float32, device=labels.device)
+    if x.shape != (n, 1, h, w) or x.dtype != torch.float32 or not x.is_contiguous():
+        raise ValueError("out must be a contiguous fp32 [N,1,H,W] tensor")
+    tgt = None
+    if want_target:
+        tgt = out_target if out_target is not None else torch.empty(n, h, w, dtype=torch.int64, device=labels.device)
     check(lib.mmvae_prepare_input(ctypes.c_void_p(labels.data_ptr()), labels.numel(), data_mean, data_std,
                                   ctypes.c_void_p(x.data_ptr()),
                                   ctypes.c_void_p(tgt.data_ptr() if tgt is not None else 0),

@@ -1,0 +1,88 @@
+"""One training step of the VAE as a single CUDA-graph replay.
+
+The reference's loop body (main.py:389-390,397-398)
+
+    mu, logvar, enc, recon = model(image);  loss, *_ = model.loss(target, mu, logvar, enc, recon, device, args)
+    optimizer.zero_grad();  loss.backward()
+
+issues ~160 short sm_100a kernels; at a few microseconds each the host cannot launch them as fast as a
+B200 retires them.  `GraphedTrainStep` runs exactly that body once under stream capture (through the same
+public `VAE.forward` / `VAE.loss` / autograd path, so it is the same code that the parity tests check) and
+replays the captured graph afterwards: one launch per step.  Shapes are fixed by construction; inputs are
+copied into static buffers, outputs and `.grad` tensors are static tensors that every replay overwrites.
+
+The rsample noise stays fresh across replays: the Philox {seed, offset} pair lives in device memory and is
+advanced inside the graph (include/mmvae.h, `rng_state`).
+"""
+import types
+
+import torch
+
+
+class GraphedTrainStep:
+    def __init__(self, model, batch_size, args=None, kl_weight=None, warmup=3, from_labels=None):
+        """`from_labels=(data_mean, data_std)`: the step starts from the uint8 k-means label map
+        (`self.labels`, [N,S,S]) and normalises it on the device (main.py:381-388) inside the graph."""
+        if not next(model.parameters()).is_cuda:
+            raise ValueError("GraphedTrainStep needs the module on a CUDA device")
+        self.model = model
+        dev = next(model.parameters()).device
+        s = model.input_image_size
+        categorical = model.decoder_out_channels > model.in_channels
+        self.x = torch.zeros(batch_size, model.in_channels, s, s, dtype=torch.float32, device=dev)
+        self.target = (torch.zeros(batch_size, s, s, dtype=torch.int64, device=dev) if categorical else self.x)
+        self.args = args if args is not None else types.SimpleNamespace(data_ratio_of_labels=None)
+        self.kl_weight = kl_weight
+        self._own_target = categorical
+        self.from_labels = from_labels
+        self.labels = torch.zeros(batch_size, s, s, dtype=torch.uint8, device=dev) if from_labels is not None else None
+        model.train(True)
+        self._saved_defer = model.defer_metrics
+        model.defer_metrics = True                      # no host synchronisation inside the step
+        if model.require_rsample and model._rng_dev is None:
+            if model._philox_seed is None:
+                model._philox_seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
+            seed = model._philox_seed
+            seed = seed - (1 << 64) if seed >= (1 << 63) else seed
+            model._rng_dev = torch.tensor([seed, model._philox_offset], dtype=torch.int64, device=dev)
+
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):             # allocates the workspace, loads kernels, sets attributes
+                self._body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        for p in model.parameters():
+            p.grad = None
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._body()
+        self.grads = [p.grad for p in model.parameters()]
+
+    def _body(self):
+        m = self.model
+        for p in m.parameters():
+            p.grad = None                               # optimizer.zero_grad(), main.py:397
+        if self.from_labels is not None:
+            from .data import prepare_input
+            prepare_input(self.labels, self.from_labels[0], self.from_labels[1], want_target=self._own_target,
+                          out=self.x, out_target=self.target if self._own_target else None)
+        mu, logvar, enc, recon = m(self.x)
+        loss, pxz, kl, _ = m.loss(self.target, mu, logvar, enc, recon, self.x.device, self.args, kl_weight=self.kl_weight)
+        loss.backward()
+        self.mu, self.logvar, self.encoding, self.reconstruction = mu, logvar, enc, recon
+        self.loss, self.pxz, self.kl = loss.detach(), pxz, kl
+
+    def __call__(self, x=None, target=None):
+        """Copy the batch into the static input (pass None when `self.x` was filled in place) and replay.
+        Returns (loss, pxz/N, KL/N) as 0-d device tensors; gradients are in `p.grad` of every parameter."""
+        if x is not None and self.labels is not None:
+            if x.data_ptr() != self.labels.data_ptr():
+                self.labels.copy_(x, non_blocking=True)     # H2D straight into the static buffer when x is pinned host memory
+        elif x is not None and x.data_ptr() != self.x.data_ptr():
+            self.x.copy_(x, non_blocking=True)
+        if self._own_target and target is not None:
+            self.target.copy_(target, non_blocking=True)
+        self.graph.replay()
+        return self.loss, self.pxz, self.kl

@@ -148,6 +148,7 @@ class VAE(nn.Module):
         self._gen = 0
         self._philox_seed = None
         self._philox_offset = 0
+        self._rng_dev = None          # int64[2] device tensor {seed, offset} while a GraphedTrainStep owns the noise
         self.last_eps = None
         self._loss_scratch = None
         self._grad_sync = None        # set by mmvae_b200.parallel.DataParallel
@@ -298,12 +299,17 @@ class VAE(nn.Module):
         recon = torch.empty(n, self.decoder_out_channels, d, d, dtype=torch.float32, device=dev)
         eps_out = None
         seed = offset = 0
+        rng = None
         if self.require_rsample:
             if eps is None:
                 if self._philox_seed is None:
                     self._philox_seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
-                seed, offset = self._philox_seed, self._philox_offset
-                self._philox_offset += (n * z + 3) // 4
+                if self._rng_dev is not None:
+                    # device-resident {seed, offset}: a captured graph draws fresh noise on every replay
+                    rng = self._rng_dev
+                else:
+                    seed, offset = self._philox_seed, self._philox_offset
+                    self._philox_offset += (n * z + 3) // 4
                 eps_out = torch.empty(n, z, 1, 1, dtype=torch.float32, device=dev)
             else:
                 eps = eps.to(device=dev, dtype=torch.float32).contiguous()
@@ -311,8 +317,10 @@ class VAE(nn.Module):
                     raise ValueError("eps must have N*z elements")
         self._gen += 1
         check(lib.mmvae_forward(byref(desc), _ptr(x), _ptr(self._arena), _ptr(self._bn_arena), _ptr(self._counters),
-                                _ptr(eps), seed, offset, _ptr(eps_out), _ptr(ws), ws.numel(), _ptr(mu), _ptr(logvar),
-                                _ptr(enc), _ptr(recon), _stream()), "mmvae_forward")
+                                _ptr(eps), seed, offset, _ptr(eps_out), _ptr(rng), _ptr(ws), ws.numel(), _ptr(mu),
+                                _ptr(logvar), _ptr(enc), _ptr(recon), _stream()), "mmvae_forward")
+        if rng is not None:
+            rng[1] += (n * z + 3) // 4
         self.last_eps = eps_out if eps_out is not None else eps
         return mu, logvar, enc, recon, (desc, ws, self._gen)
 

@@ -61,7 +61,8 @@ class GradSync:
         with torch.cuda.stream(self.comm_stream):
             self.comm_stream.wait_event(ev)
             self.reduce_range(grads, begin, end)
-        grads.record_stream(self.comm_stream)
+        if not torch.cuda.is_current_stream_capturing():
+            grads.record_stream(self.comm_stream)
 
     def finish(self):
         if self.comm_stream is not None:
