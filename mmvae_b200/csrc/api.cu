@@ -11,6 +11,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <type_traits>
 
 #include "kernels.cuh"
@@ -102,6 +103,34 @@ static void geom_fprop(const ConvT_& c, int N, GConvParams& g) { geom_build(c, D
 static void geom_dgrad(const ConvT_& c, int N, GConvParams& g) { geom_build(c, DIR_DGRAD, N, g); }
 
 // ------------------------------------------------------------------------------------------------
+// auxiliary stream: work that is off the critical path of the step (weight gradients, the shortcut
+// branch of a block) is enqueued on a second, per-device stream that forks from and joins back into
+// the caller's stream with events -- eagerly this is plain concurrency, under stream capture it becomes
+// a parallel branch of the CUDA graph.  The pair (stream, events) is the only state the library keeps.
+// ------------------------------------------------------------------------------------------------
+struct AuxPool {
+  cudaStream_t s = nullptr;
+  cudaEvent_t ev[32];
+  int next = 0;
+  bool ok = false;
+};
+static AuxPool* aux_pool() {
+  static AuxPool pools[64];
+  static std::mutex mu;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  AuxPool& p = pools[dev];
+  if (!p.ok) {
+    if (cudaStreamCreateWithFlags(&p.s, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    for (auto& e : p.ev)
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    p.ok = true;
+  }
+  return &p;
+}
+
+// ------------------------------------------------------------------------------------------------
 // step executor
 // ------------------------------------------------------------------------------------------------
 template <typename T>
@@ -115,8 +144,34 @@ struct Exec {
   cudaStream_t st;
   const float* x;       // fp32 NCHW network input
 
+  AuxPool* aux = nullptr;       // set by use_aux(): second stream for off-critical-path work
+
   template <typename U> U* at(size_t off) const { return reinterpret_cast<U*>(ws + off); }
   const ActT& act(int i) const { return P.acts[i]; }
+
+  void use_aux() { if (special_ok() && !getenv("MMVAE_NO_AUX")) aux = aux_pool(); }
+  cudaEvent_t next_event() { cudaEvent_t e = aux->ev[aux->next]; aux->next = (aux->next + 1) & 31; return e; }
+  // run f() on the auxiliary stream, ordered after everything enqueued on the main stream so far
+  template <typename F> void side(F f) {
+    if (!aux) { f(); return; }
+    cudaEvent_t e = next_event();
+    cudaEventRecord(e, st);
+    cudaStreamWaitEvent(aux->s, e, 0);
+    cudaStream_t keep = st;
+    st = aux->s;
+    f();
+    st = keep;
+    forked = true;
+  }
+  // the main stream waits for everything enqueued on the auxiliary stream
+  void join() {
+    if (!aux || !forked) return;
+    cudaEvent_t e = next_event();
+    cudaEventRecord(e, aux->s);
+    cudaStreamWaitEvent(st, e, 0);
+    forked = false;
+  }
+  bool forked = false;
 
   // dedicated kernels of the 1-channel stem / tail convolutions (bf16 mode)
   bool special_ok() const { return std::is_same<T, __nv_bfloat16>::value && !(P.d.flags & MMVAE_FLAG_FORCE_SIMT); }
@@ -212,10 +267,11 @@ struct Exec {
 
   void block_fwd(const BlockT& b) {
     const ConvT_& c1 = P.convs[b.c1]; const ConvT_& c2 = P.convs[b.c2]; const ConvT_& cs = P.convs[b.cs];
+    side([&] { conv_bn_fwd(cs); });                   // shortcut branch: only needs the block input
     conv_bn_fwd(c1);
     apply(c1, nullptr, b.a1, 1);
     conv_bn_fwd(c2);
-    conv_bn_fwd(cs);
+    join();
     apply(c2, &cs, b.out, 1);
   }
 
@@ -309,11 +365,10 @@ struct Exec {
   void block_bwd(const BlockT& b) {
     const ConvT_& c1 = P.convs[b.c1]; const ConvT_& c2 = P.convs[b.c2]; const ConvT_& cs = P.convs[b.cs];
     bn_bwd(at<T>(act(b.out).goff), 0, b.out, c2, &cs);
-    wgrad(c2);
-    wgrad(cs);
+    side([&] { wgrad(c2); wgrad(cs); });              // weight gradients are off the critical path
     dgrad(c2, 0);                                     // -> d a1
     bn_bwd(at<T>(act(b.a1).goff), 0, b.a1, c1, nullptr);
-    wgrad(c1);
+    side([&] { wgrad(c1); });
     dgrad(c1, 0);                                     // -> d in
     dgrad(cs, 1);                                     // += shortcut
   }
@@ -357,9 +412,10 @@ struct Exec {
         for (int i = (int)P.dec.size() - 1; i >= 0; --i) block_bwd(P.dec[i]);
         const ConvT_& s = P.convs[P.dstem];
         bn_bwd(at<T>(act(P.a_dstem).goff), 0, P.a_dstem, s, nullptr);
-        wgrad(s);
+        side([&] { wgrad(s); });
         dgrad(s, 0);
       }
+      join();
     }
     if (phases & MMVAE_BWD_ENC_DEEP) {
       clear(MMVAE_BWD_ENC_DEEP);
@@ -376,6 +432,7 @@ struct Exec {
       launch_heads_bwd<T>(h, st);
       block_bwd(P.enc[3]);
       block_bwd(P.enc[2]);
+      join();
     }
     if (phases & MMVAE_BWD_ENC_SHALLOW) {
       clear(MMVAE_BWD_ENC_SHALLOW);
@@ -384,6 +441,7 @@ struct Exec {
       const ConvT_& s = P.convs[P.stem];
       bn_bwd(at<T>(act(P.a_stem).goff), 0, P.a_stem, s, nullptr);
       wgrad(s);
+      join();
     }
   }
 };
@@ -504,6 +562,7 @@ int mmvae_forward(const mmvae_desc* d, const float* x, const float* params, floa
   } else {
     Exec<__nv_bfloat16> E{P, (char*)workspace, params, nullptr, bn_buffers, (long long*)bn_counters, st, x};
     if (!P.d.training) { E.counters = nullptr; }
+    E.use_aux();
     E.clear_bn_acc();
     E.pack_weights();
     E.encode(eps, seed, offset, rng_state, eps_out, mu, logvar, encoding);
@@ -526,6 +585,7 @@ int mmvae_decode(const mmvae_desc* d, const float* encoding, const float* params
   } else {
     Exec<__nv_bfloat16> E{P, (char*)workspace, params, nullptr, bn_buffers, (long long*)bn_counters, st, nullptr};
     if (!P.d.training) E.counters = nullptr;
+    E.use_aux();
     E.clear_bn_acc();
     E.pack_weights();
     launch_cast_latent<__nv_bfloat16>(encoding, E.at<__nv_bfloat16>(P.acts[P.a_z].off), nz, st);
@@ -547,6 +607,7 @@ int mmvae_backward(const mmvae_desc* d, const float* x, const float* params, voi
     E.backward(d_mu, d_logvar, d_encoding, d_recon, phases);
   } else {
     Exec<__nv_bfloat16> E{P, (char*)workspace, params, grads, nullptr, nullptr, st, x};
+    E.use_aux();
     E.backward(d_mu, d_logvar, d_encoding, d_recon, phases);
   }
   return check_launches("mmvae_backward");
