@@ -10,6 +10,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <type_traits>
@@ -21,6 +22,10 @@
 namespace mmvae {
 
 thread_local char g_err[512] = "";
+bool pdl_enabled() {
+  static bool on = [] { const char* e = getenv("MMVAE_NO_PDL"); return !(e && e[0] == '1'); }();
+  return on;
+}
 std::atomic<long long> g_launches{0};
 
 static int fail(int code, const char* fmt, ...) {

@@ -111,6 +111,7 @@ __global__ void __launch_bounds__(kTcThreads, 3) gconv_tc_kernel(const __grid_co
   const uint32_t a_base = ring, b_base = ring + (uint32_t)S * kStageA;
 
   if (tid == 0) {
+    if (p.use_tma) prefetch_tensormap(&p.tmap_a);
     for (int s = 0; s < S; ++s) {
       mbar_init(smem_u32(&full[s]), p.use_tma ? 1 : kGatherThreads + 1);
       mbar_init(smem_u32(&empty[s]), 1);
@@ -127,6 +128,8 @@ __global__ void __launch_bounds__(kTcThreads, 3) gconv_tc_kernel(const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
+  pdl_wait();                                   // everything above overlapped the previous kernel's tail
+  pdl_trigger();
 
   if (warp < 4) {
     if (p.use_tma) {
@@ -418,6 +421,8 @@ __global__ void __launch_bounds__(kTcThreads) wgrad_tc_kernel(const __grid_const
   const uint32_t a_base = ring, b_base = ring + (uint32_t)S * kStageA;
 
   if (tid == 0) {
+    if (p.tma_a) prefetch_tensormap(&p.tmap_a);
+    if (p.tma_b) prefetch_tensormap(&p.tmap_b);
     const int arrivals = (need_gather ? kGatherThreads : 0) + ((p.tma_a || p.tma_b) ? 1 : 0);
     for (int s = 0; s < S; ++s) {
       mbar_init(smem_u32(&full[s]), arrivals);
@@ -432,6 +437,8 @@ __global__ void __launch_bounds__(kTcThreads) wgrad_tc_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
+  pdl_wait();
+  pdl_trigger();
 
   if (k0 >= K || nchunks <= 0) {
     // nothing to do for this (variant, k-tile, split)
@@ -600,6 +607,8 @@ __global__ void __launch_bounds__(kTcThreads) wgrad_tc_kernel(const __grid_const
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pack_weights_kernel(const __grid_constant__ PackTable tab, const float* __restrict__ params,
                                                            unsigned char* __restrict__ ws) {
+  pdl_wait();                                       // PDL: may start while the previous kernel drains
+  pdl_trigger();
   const PackOp& op = tab.ops[blockIdx.y];
   ConvGeom g{op.kind, op.k, op.s, op.p, op.Ci, op.Co};
   int op_ci, op_co, w_sci, w_sco;
@@ -686,6 +695,15 @@ bool pixel_box(int rows, int Hg, int Wg, int& bw, int& bh, int& bn) {
   return true;
 }
 
+int wgrad_ctas() {                      // CTA budget of a weight-gradient launch (MMVAE_WGRAD_CTAS env, tuning)
+  static int m = [] { const char* e = getenv("MMVAE_WGRAD_CTAS"); return e ? atoi(e) : 148; }();
+  return m;
+}
+int gconv_per_sm() {
+  static int m = [] { const char* e = getenv("MMVAE_GCONV_PER_SM"); return e ? atoi(e) : 3; }();
+  return m;
+}
+
 int tma_mask() {                        // bit 0: gconv A, bit 1: wgrad A, bit 2: wgrad dY   (MMVAE_TMA env, debugging)
   static int m = [] { const char* e = getenv("MMVAE_TMA"); return e ? atoi(e) : 7; }();
   return m;
@@ -737,14 +755,14 @@ StatLayout launch_gconv_tc(const GConvParams& p0, cudaStream_t st) {
     cudaFuncSetAttribute(gconv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_done = true;
   }
-  const int per_sm = smem <= 72 * 1024 ? 3 : 2;
+  const int per_sm = min(gconv_per_sm(), smem <= 72 * 1024 ? 3 : 2);
   const int grid = min(p.total_tiles, per_sm * 148);
   count_launch();
   switch (bn) {
-    case 16: gconv_tc_kernel<16><<<grid, kTcThreads, smem, st>>>(p); break;
-    case 32: gconv_tc_kernel<32><<<grid, kTcThreads, smem, st>>>(p); break;
-    case 64: gconv_tc_kernel<64><<<grid, kTcThreads, smem, st>>>(p); break;
-    default: gconv_tc_kernel<128><<<grid, kTcThreads, smem, st>>>(p); break;
+    case 16: launch_pdl(gconv_tc_kernel<16>, grid, kTcThreads, smem, st, p); break;
+    case 32: launch_pdl(gconv_tc_kernel<32>, grid, kTcThreads, smem, st, p); break;
+    case 64: launch_pdl(gconv_tc_kernel<64>, grid, kTcThreads, smem, st, p); break;
+    default: launch_pdl(gconv_tc_kernel<128>, grid, kTcThreads, smem, st, p); break;
   }
   return sl;       // statistics are finalised inside the kernel (p.bn); no partial rows
 }
@@ -758,7 +776,7 @@ void launch_wgrad_tc(const WGradParams& p0, cudaStream_t st) {
   const int bn = co_pad >= 64 ? 64 : (co_pad >= 32 ? 32 : 16);
   const int gx = (maxK + 127) / 128, gy = (co_pad + bn - 1) / bn;
   const int base = gx * gy * p.nvar;
-  int nsplit = max(1, (2 * 148) / base);
+  int nsplit = max(1, wgrad_ctas() / base);
   nsplit = min(nsplit, max(1, (p.M + 255) / 256));      // at least 256 pixels per split
   int rps = (p.M + nsplit - 1) / nsplit;
   rps = (rps + 63) / 64 * 64;
@@ -790,14 +808,14 @@ void launch_wgrad_tc(const WGradParams& p0, cudaStream_t st) {
   }
   dim3 grid(gx, gy, p.nvar * nsplit);
   count_launch();
-  wgrad_tc_kernel<<<grid, kTcThreads, smem, st>>>(p);
+  launch_pdl(wgrad_tc_kernel, grid, kTcThreads, smem, st, p);
 }
 
 void launch_pack_weights(const PackTable& tab, const float* params, void* ws, cudaStream_t st) {
   if (tab.n <= 0) return;
   dim3 grid(48, tab.n);
   count_launch();
-  pack_weights_kernel<<<grid, 256, 0, st>>>(tab, params, reinterpret_cast<unsigned char*>(ws));
+  launch_pdl(pack_weights_kernel, grid, 256, 0, st, tab, params, reinterpret_cast<unsigned char*>(ws));
 }
 
 }  // namespace mmvae

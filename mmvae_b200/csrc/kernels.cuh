@@ -11,6 +11,27 @@ namespace mmvae {
 extern std::atomic<long long> g_launches;
 inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// ---- programmatic dependent launch (PDL) ----
+// A kernel launched through launch_pdl() may be scheduled while its stream predecessor is still running; it must
+// execute pdl_wait() before it touches global memory, and calls pdl_trigger() once its own dependents may start
+// their prologue (barrier init, TMEM allocation, descriptor prefetch).  Under stream capture the edge becomes a
+// programmatic dependency of the CUDA graph.  MMVAE_NO_PDL=1 turns the attribute off (plain stream order).
+bool pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 // Division by a runtime constant without the integer-divide sequence (valid for numerators < 2^31).
 struct FastDiv {
   unsigned int mul = 0, shr = 0, div = 1;

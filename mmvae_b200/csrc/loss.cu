@@ -37,6 +37,8 @@ __device__ __forceinline__ float block_sum_f(float v, float* sh) {
 __global__ void __launch_bounds__(kLossThreads) loss_gauss_fwd_kernel(const float* __restrict__ recon,
                                                                       const float* __restrict__ target,
                                                                       long long n, float* __restrict__ partial) {
+  pdl_wait();                                       // PDL: may start while the previous kernel drains
+  pdl_trigger();
   __shared__ float sh[kLossThreads / 32];
   float s = 0.f;
   const long long n4 = n >> 2;
@@ -80,6 +82,8 @@ __global__ void __launch_bounds__(kLossThreads) loss_ce_fwd_kernel(const float* 
 __global__ void __launch_bounds__(256) loss_finalize_kernel(LossArgs a, const float* __restrict__ partial, int nparts,
                                                             const float* __restrict__ mu, const float* __restrict__ lv,
                                                             float* __restrict__ out) {
+  pdl_wait();                                       // PDL: may start while the previous kernel drains
+  pdl_trigger();
   __shared__ double sh[256];
   double s = 0.0;
   for (int i = threadIdx.x; i < nparts; i += 256) s += (double)partial[i];
@@ -118,6 +122,8 @@ __global__ void __launch_bounds__(256) loss_finalize_kernel(LossArgs a, const fl
 __global__ void __launch_bounds__(256) loss_gauss_bwd_kernel(const float* __restrict__ recon, const float* __restrict__ target,
                                                              long long n, const float* __restrict__ gout, float coef,
                                                              float* __restrict__ d_recon) {
+  pdl_wait();                                       // PDL: may start while the previous kernel drains
+  pdl_trigger();
   const float g = __ldg(gout) * coef;     // nll / (sigma^2 * N) * upstream
   const long long n4 = n >> 2;
   const float4* r4 = reinterpret_cast<const float4*>(recon);
@@ -159,6 +165,8 @@ __global__ void __launch_bounds__(256) loss_ce_bwd_kernel(const float* __restric
 __global__ void __launch_bounds__(256) kl_bwd_kernel(const float* __restrict__ mu, const float* __restrict__ lv, long long nz,
                                                      const float* __restrict__ gout, float coef,
                                                      float* __restrict__ d_mu, float* __restrict__ d_lv) {
+  pdl_wait();                                       // PDL: may start while the previous kernel drains
+  pdl_trigger();
   const float g = __ldg(gout) * coef;     // kl / N * upstream
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < nz; i += gridDim.x * 256LL) {
     d_mu[i] = g * mu[i];
@@ -190,6 +198,8 @@ __global__ void __launch_bounds__(256) adam_kernel(long long n, float* __restric
 
 __global__ void __launch_bounds__(256) prepare_input_kernel(const unsigned char* __restrict__ labels, long long n, float mean,
                                                             float inv_std, float* __restrict__ x, long long* __restrict__ target) {
+  pdl_wait();                                       // PDL: may start while the previous kernel drains
+  pdl_trigger();
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += gridDim.x * 256LL) {
     unsigned char l = labels[i];
     x[i] = ((float)l - mean) * inv_std;
@@ -220,7 +230,7 @@ void launch_loss_fwd(const LossArgs& a, const float* recon, const void* target, 
     if (blocks < 1) blocks = 1;
     if (blocks > kLossBlocks) blocks = kLossBlocks;
     count_launch();
-    loss_gauss_fwd_kernel<<<blocks, kLossThreads, 0, st>>>(recon, reinterpret_cast<const float*>(target), n, partial);
+    launch_pdl(loss_gauss_fwd_kernel, blocks, kLossThreads, 0, st, recon, reinterpret_cast<const float*>(target), n, partial);
   } else {
     long long npix = (long long)a.N * a.H * a.W;
     blocks = (int)((npix + kLossThreads - 1) / kLossThreads);
@@ -231,7 +241,7 @@ void launch_loss_fwd(const LossArgs& a, const float* recon, const void* target, 
                                                         a.C, a.H * a.W, partial);
   }
   count_launch();
-  loss_finalize_kernel<<<1, 256, 0, st>>>(a, partial, blocks, mu, lv, out);
+  launch_pdl(loss_finalize_kernel, 1, 256, 0, st, a, partial, blocks, mu, lv, out);
 }
 
 void launch_loss_bwd(const LossArgs& a, const float* recon, const void* target, const float* w,
@@ -242,7 +252,7 @@ void launch_loss_bwd(const LossArgs& a, const float* recon, const void* target, 
       long long n = (long long)a.N * a.C * a.H * a.W;
       float coef = a.nll / (a.sigma * a.sigma * (float)a.N);
       count_launch();
-      loss_gauss_bwd_kernel<<<grid_for(n / 4 + 1), 256, 0, st>>>(recon, reinterpret_cast<const float*>(target), n, gout,
+      launch_pdl(loss_gauss_bwd_kernel, grid_for(n / 4 + 1), 256, 0, st, recon, reinterpret_cast<const float*>(target), n, gout,
                                                                  coef, d_recon);
     } else {
       long long npix = (long long)a.N * a.H * a.W;
@@ -255,14 +265,14 @@ void launch_loss_bwd(const LossArgs& a, const float* recon, const void* target, 
   if (d_mu && d_lv && mu && lv) {
     long long nz = (long long)a.N * a.z;
     count_launch();
-    kl_bwd_kernel<<<grid_for(nz), 256, 0, st>>>(mu, lv, nz, gout, a.kl / (float)a.N, d_mu, d_lv);
+    launch_pdl(kl_bwd_kernel, grid_for(nz), 256, 0, st, mu, lv, nz, gout, a.kl / (float)a.N, d_mu, d_lv);
   }
 }
 
 void launch_prepare_input(const unsigned char* labels, long long n, float mean, float inv_std, float* x,
                           long long* target, cudaStream_t st) {
   count_launch();
-  prepare_input_kernel<<<grid_for(n), 256, 0, st>>>(labels, n, mean, inv_std, x, target);
+  launch_pdl(prepare_input_kernel, grid_for(n), 256, 0, st, labels, n, mean, inv_std, x, target);
 }
 
 void launch_philox_normal(unsigned long long seed, unsigned long long offset, long long n, float* out, cudaStream_t st) {

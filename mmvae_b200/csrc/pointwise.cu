@@ -109,6 +109,8 @@ template <typename T, int VEC>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ y, const float* __restrict__ coef,
                                                        const T* __restrict__ y2, const float* __restrict__ coef2,
                                                        T* __restrict__ out, long long nvec, int C, int relu) {
+  pdl_wait();                                       // PDL: may start while the previous kernel drains
+  pdl_trigger();
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < nvec; i += gridDim.x * 256LL) {
     int c0 = (int)((i * VEC) % C);
     float v[VEC], r[VEC];
@@ -131,6 +133,8 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ y, 
 template <typename T>
 __global__ void __launch_bounds__(256) bn_apply_out_kernel(const T* __restrict__ y, const float* __restrict__ coef,
                                                            float* __restrict__ out, long long total, int HW, int C) {
+  pdl_wait();                                       // PDL: may start while the previous kernel drains
+  pdl_trigger();
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
     int hw = (int)(i % HW); long long t = i / HW; int c = (int)(t % C); long long n = t / C;
     float v = to_f(y[(n * HW + hw) * C + c]);
@@ -141,6 +145,8 @@ __global__ void __launch_bounds__(256) bn_apply_out_kernel(const T* __restrict__
 // ---------------- encoder heads: avg-pool + two 1x1 convs + rsample (model.py:123-128,148-150) ----------
 template <typename T>
 __global__ void __launch_bounds__(128) heads_fwd_kernel(const HeadsArgs a) {
+  pdl_wait();                                       // PDL: may start while the previous kernel drains
+  pdl_trigger();
   extern __shared__ float sm[];          // pooled[C] then out[2z]
   float* pooled = sm;
   float* outv = sm + a.C;
@@ -194,6 +200,8 @@ __global__ void cast_latent_kernel(const float* __restrict__ in, T* __restrict__
 // dz -> (dmu, dlogvar) -> dpooled -> d(encoder output)
 template <typename T>
 __global__ void __launch_bounds__(128) heads_bwd_kernel(const HeadsBwdArgs a) {
+  pdl_wait();                                       // PDL: may start while the previous kernel drains
+  pdl_trigger();
   extern __shared__ float sm[];          // dmu[z], dlv[z]
   float* dmu = sm; float* dlv = sm + a.z;
   const int n = blockIdx.x, tid = threadIdx.x;
@@ -227,6 +235,8 @@ __global__ void __launch_bounds__(128) heads_bwd_kernel(const HeadsBwdArgs a) {
 // ---------------- BatchNorm backward ----------------
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
+  pdl_wait();                                       // PDL: may start while the previous kernel drains
+  pdl_trigger();
   __shared__ float red[256 * VEC * 3];
   const int CV = a.C / VEC;
   const int RPI = 256 / CV;              // rows per iteration (CV <= 256 guaranteed by the launcher)
@@ -339,6 +349,8 @@ __global__ void __launch_bounds__(128) bn_bwd_finalize_kernel(const BnBwdArgs a,
 
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a) {
+  pdl_wait();                                       // PDL: may start while the previous kernel drains
+  pdl_trigger();
   const long long nvec = a.rows * a.C / VEC;
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < nvec; i += gridDim.x * 256LL) {
     const int c0 = (int)((i * VEC) % a.C);
@@ -403,11 +415,11 @@ void launch_bn_apply(const T* y, const float* coef, const T* y2, const float* co
   if (C % V == 0) {
     long long nvec = rows * C / V;
     count_launch();
-    bn_apply_kernel<T, V><<<grid_for(nvec), 256, 0, st>>>(y, coef, y2, coef2, out, nvec, C, relu);
+    launch_pdl(bn_apply_kernel<T, V>, grid_for(nvec), 256, 0, st, y, coef, y2, coef2, out, nvec, C, relu);
   } else {
     long long nvec = rows * C;
     count_launch();
-    bn_apply_kernel<T, 1><<<grid_for(nvec), 256, 0, st>>>(y, coef, y2, coef2, out, nvec, C, relu);
+    launch_pdl(bn_apply_kernel<T, 1>, grid_for(nvec), 256, 0, st, y, coef, y2, coef2, out, nvec, C, relu);
   }
 }
 
@@ -415,14 +427,14 @@ template <typename T>
 void launch_bn_apply_out(const T* y, const float* coef, float* out_nchw, int N, int HW, int C, cudaStream_t st) {
   long long total = (long long)N * HW * C;
   count_launch();
-  bn_apply_out_kernel<T><<<grid_for(total), 256, 0, st>>>(y, coef, out_nchw, total, HW, C);
+  launch_pdl(bn_apply_out_kernel<T>, grid_for(total), 256, 0, st, y, coef, out_nchw, total, HW, C);
 }
 
 template <typename T>
 void launch_heads_fwd(const HeadsArgs& a, cudaStream_t st) {
   size_t smem = sizeof(float) * (size_t(a.C) + 2 * size_t(a.z));
   count_launch();
-  heads_fwd_kernel<T><<<a.N, 128, smem, st>>>(a);
+  launch_pdl(heads_fwd_kernel<T>, a.N, 128, smem, st, a);
 }
 
 template <typename T>
@@ -435,7 +447,7 @@ template <typename T>
 void launch_heads_bwd(const HeadsBwdArgs& a, cudaStream_t st) {
   size_t smem = sizeof(float) * 2 * size_t(a.z);
   count_launch();
-  heads_bwd_kernel<T><<<a.N, 128, smem, st>>>(a);
+  launch_pdl(heads_bwd_kernel<T>, a.N, 128, smem, st, a);
   launch_heads_wgrad(a.dheads, a.pooled, a.g_wmu, a.w_lv ? a.g_wlv : nullptr, a.N, a.z, a.C, st);
 }
 
@@ -453,15 +465,15 @@ void launch_bn_bwd(const BnBwdArgs& a, cudaStream_t st) {
   }
   if (nblocks > 592) nblocks = 592;
   if (nblocks < 1) nblocks = 1;
-  if (vec_ok) { count_launch(); bn_bwd_reduce_kernel<T, V><<<nblocks, 256, 0, st>>>(a); }
-  else { count_launch(); bn_bwd_reduce_kernel<T, 1><<<nblocks, 256, 0, st>>>(a); }
+  if (vec_ok) { count_launch(); launch_pdl(bn_bwd_reduce_kernel<T, V>, nblocks, 256, 0, st, a); }
+  else { count_launch(); launch_pdl(bn_bwd_reduce_kernel<T, 1>, nblocks, 256, 0, st, a); }
   if (!a.acc) {
     count_launch();
     bn_bwd_finalize_kernel<<<a.C, 128, 0, st>>>(a, nblocks, a.rows);
   }
   long long total = a.rows * a.C;
-  if (a.C % V == 0) { count_launch(); bn_bwd_apply_kernel<T, V><<<grid_for(total / V), 256, 0, st>>>(a); }
-  else { count_launch(); bn_bwd_apply_kernel<T, 1><<<grid_for(total), 256, 0, st>>>(a); }
+  if (a.C % V == 0) { count_launch(); launch_pdl(bn_bwd_apply_kernel<T, V>, grid_for(total / V), 256, 0, st, a); }
+  else { count_launch(); launch_pdl(bn_bwd_apply_kernel<T, 1>, grid_for(total), 256, 0, st, a); }
 }
 
 void launch_nchw_to_nhwc(const float* in, float* out, int N, int C, int HW, cudaStream_t st) {

@@ -43,6 +43,8 @@ __device__ __forceinline__ void stem_load_x(const StemArgs& a, int n, int oy0, f
 
 template <int CO>
 __global__ void __launch_bounds__(256) stem_fwd_kernel(const StemArgs a) {
+  pdl_wait();                                       // PDL: may start while the previous kernel drains
+  pdl_trigger();
   constexpr int H = CO / 2;                          // channels per thread
   __shared__ float xs[kStemMaxRows * kStemMaxCols];
   __shared__ __align__(16) float ws[25 * CO];
@@ -118,6 +120,8 @@ __global__ void __launch_bounds__(256) stem_fwd_kernel(const StemArgs a) {
 // thread = (pixel slice, kernel row kh, 4 output channels): 5 x 4 accumulators kept across all tiles of the CTA
 template <int CO>
 __global__ void __launch_bounds__(320) stem_wgrad_kernel(const StemArgs a) {
+  pdl_wait();                                       // PDL: may start while the previous kernel drains
+  pdl_trigger();
   constexpr int CG = CO / 4;                         // channel groups
   constexpr int PER = 5 * CG;                        // threads per pixel slice
   constexpr int NSL = 320 / PER;                     // pixel slices
@@ -194,6 +198,8 @@ __device__ __forceinline__ float block_sum512(float v, float* sh) {
 // thread = (pixel, group of 8 input channels); the CI/8 lanes of a pixel are adjacent
 template <int CI>
 __global__ void __launch_bounds__(kTailThreads) tail_fwd_kernel(const TailArgs a) {
+  pdl_wait();                                       // PDL: may start while the previous kernel drains
+  pdl_trigger();
   constexpr int G = CI / 8;
   constexpr int PX = kTailThreads / G;               // pixels per tile
   extern __shared__ __align__(16) unsigned char tail_smem[];
@@ -252,6 +258,8 @@ __global__ void __launch_bounds__(kTailThreads) tail_fwd_kernel(const TailArgs a
 //   dW[ci][t]     += a[q][ci] * dY[q + (1-kh, 1-kw)]
 template <int CI>
 __global__ void __launch_bounds__(kTailThreads) tail_bwd_kernel(const TailArgs a) {
+  pdl_wait();                                       // PDL: may start while the previous kernel drains
+  pdl_trigger();
   constexpr int G = CI / 8;
   extern __shared__ __align__(16) unsigned char tail_smem[];
   float* gs = reinterpret_cast<float*>(tail_smem);                   // [(R+2)][(W+2)] dY with zero halo
@@ -350,6 +358,8 @@ __global__ void __launch_bounds__(kTailThreads) tail_bwd_kernel(const TailArgs a
 __global__ void __launch_bounds__(256) heads_wgrad2_kernel(const float* __restrict__ dh, const float* __restrict__ pooled,
                                                            float* __restrict__ g_mu, float* __restrict__ g_lv,
                                                            int N, int z, int C) {
+  pdl_wait();                                       // PDL: may start while the previous kernel drains
+  pdl_trigger();
   __shared__ float red[4][8][64];
   const float* d = dh + (size_t)blockIdx.y * N * z;
   float* gw = blockIdx.y == 0 ? g_mu : g_lv;
@@ -407,8 +417,8 @@ StatLayout launch_stem_fwd(StemArgs a, int Co, cudaStream_t st) {
   stem_fill(a);
   const int grid = min(a.ntiles, 148 * 3);
   count_launch();
-  if (Co == 32) stem_fwd_kernel<32><<<grid, 256, 0, st>>>(a);
-  else stem_fwd_kernel<64><<<grid, 256, 0, st>>>(a);
+  if (Co == 32) launch_pdl(stem_fwd_kernel<32>, grid, 256, 0, st, a);
+  else launch_pdl(stem_fwd_kernel<64>, grid, 256, 0, st, a);
   return StatLayout{0, 0, 0, 0};     // statistics are finalised inside the kernel (a.bn)
 }
 
@@ -416,8 +426,8 @@ void launch_stem_wgrad(StemArgs a, int Co, cudaStream_t st) {
   stem_fill(a);
   const int grid = min(a.ntiles, 2 * 148);
   count_launch();
-  if (Co == 32) stem_wgrad_kernel<32><<<grid, 320, 0, st>>>(a);
-  else stem_wgrad_kernel<64><<<grid, 320, 0, st>>>(a);
+  if (Co == 32) launch_pdl(stem_wgrad_kernel<32>, grid, 320, 0, st, a);
+  else launch_pdl(stem_wgrad_kernel<64>, grid, 320, 0, st, a);
 }
 
 bool tail_supported(int Ci, int Co, int H, int k, int s, int p) {
@@ -438,8 +448,8 @@ StatLayout launch_tail_fwd(TailArgs a, int Ci, cudaStream_t st) {
   const int grid = min(a.ntiles, 148 * 3);
   const size_t smem = (size_t)(a.R + 2) * (a.W + 2) * Ci * 2;
   count_launch();
-  if (Ci == 16) tail_fwd_kernel<16><<<grid, kTailThreads, smem, st>>>(a);
-  else tail_fwd_kernel<32><<<grid, kTailThreads, smem, st>>>(a);
+  if (Ci == 16) launch_pdl(tail_fwd_kernel<16>, grid, kTailThreads, smem, st, a);
+  else launch_pdl(tail_fwd_kernel<32>, grid, kTailThreads, smem, st, a);
   return StatLayout{0, 0, 0, 0};     // statistics are finalised inside the kernel (a.bn)
 }
 
@@ -448,15 +458,15 @@ void launch_tail_bwd(TailArgs a, int Ci, cudaStream_t st) {
   const int grid = min(a.ntiles, 148);
   const size_t smem = sizeof(float) * ((size_t)(a.R + 2) * (a.W + 2) + (size_t)(kTailThreads / 32) * (Ci / 8) * 72);
   count_launch();
-  if (Ci == 16) tail_bwd_kernel<16><<<grid, kTailThreads, smem, st>>>(a);
-  else tail_bwd_kernel<32><<<grid, kTailThreads, smem, st>>>(a);
+  if (Ci == 16) launch_pdl(tail_bwd_kernel<16>, grid, kTailThreads, smem, st, a);
+  else launch_pdl(tail_bwd_kernel<32>, grid, kTailThreads, smem, st, a);
 }
 
 void launch_heads_wgrad(const float* dheads, const float* pooled, float* g_mu, float* g_lv, int N, int z, int C,
                         cudaStream_t st) {
   dim3 grid((z + 7) / 8, g_lv ? 2 : 1, (C + 63) / 64);
   count_launch();
-  heads_wgrad2_kernel<<<grid, 256, 0, st>>>(dheads, pooled, g_mu, g_lv, N, z, C);
+  launch_pdl(heads_wgrad2_kernel, grid, 256, 0, st, dheads, pooled, g_mu, g_lv, N, z, C);
 }
 
 }  // namespace mmvae

@@ -61,6 +61,10 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst_smem, uint64_t tmap, ui
       : "memory");
 }
 
+__device__ __forceinline__ void prefetch_tensormap(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
+
 // ---------------- cp.async (16-byte, zero-fill when src_bytes == 0) ----------------
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
   // .ca: keep the line in L1 -- neighbouring taps / rows of the same tile re-read it
