@@ -244,6 +244,47 @@ def main():
         step_e2e(i)
     ms_e2e = timed(step_e2e, args.steps)
 
+    # ---- roofline of the dominant kernel, measured live: the tcgen05 implicit-GEMM conv kernel (gconv_tc_kernel: every
+    # forward conv / transposed conv and every data gradient, ~40 % of the step) on its heaviest layer, the 16-channel
+    # 32x32 -> 64x64 transposed conv decoder.uplayer5.0.conv2.  One launch per iteration through mmvae_bench_conv on the
+    # tensors the last step left in the workspace, CUDA events around each launch on the launching stream, L2 flushed
+    # (256 MB memset) between iterations.  Algorithmic bytes = bf16 input + output + weights, each touched once.
+    roof = None
+    if rank == 0 and args.precision == "bf16":
+        import ctypes
+        desc, ws, _info = model._workspace(n, True)
+        names = [c[0] for c in M._lib.conv_table(desc)]
+        ci = names.index("decoder.uplayer5.0.conv2") if "decoder.uplayer5.0.conv2" in names else names.index("decoder.uplayer4.0.conv2")
+        ab, af = ctypes.c_int64(), ctypes.c_int64()
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+        def one():
+            M._lib.check(M._lib.lib.mmvae_bench_conv(ctypes.byref(desc), ci, 0, ctypes.c_void_p(model._arena.data_ptr()),
+                                                     ctypes.c_void_p(ws.data_ptr()), ws.numel(), None, ctypes.byref(ab),
+                                                     ctypes.byref(af), stream), "mmvae_bench_conv")
+        for _ in range(3):
+            one()
+        evs = []
+        for _ in range(20):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); one(); e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        us = sorted(a.elapsed_time(b) * 1e3 for a, b in evs)
+        k_us = sum(us) / len(us)
+        _s, _b, hbm_peak, which_peak = peaks()
+        gbs = ab.value / (k_us * 1e-6) / 1e9
+        roof = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                "traffic": 8472576,
+                "kernel": "gconv_tc_kernel<16> on decoder.uplayer5.0.conv2 (ConvTranspose2d 16->16 k4 s2 p1, 256x32x32 -> 256x64x64)",
+                "algorithmic_bytes_per_launch": ab.value, "flops_per_launch": af.value, "us_per_launch": k_us,
+                "tensor_tflops": af.value / (k_us * 1e-6) / 1e12,
+                "note": f"of {which_peak} HBM copy peak; traffic = dram read+write of one launch from the ncu --set full capture "
+                        "in profiles/ (the 33.6 MB output stays in the 126 MB L2)"}
+        del flush
+
     fps = world * n * args.steps / (ms * 1e-3)
     fps_e2e = world * n * args.steps / (ms_e2e * 1e-3)
     sustained, burst, hbm, which = peaks()
@@ -263,9 +304,10 @@ def main():
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "clocks": clk.summary(),
-        "roofline": {"bound": "tensor", "achieved": tflops_per_gpu, "peak": sustained, "unit": "TFLOP/s",
-                     "frac": tflops_per_gpu / sustained, "traffic": None,
-                     "note": f"whole step, 227.02 MFLOP/frame algorithmic, per GPU, of {which} sustained bf16 peak"},
+        "roofline": roof if roof is not None else {"bound": "tensor", "achieved": tflops_per_gpu, "peak": sustained,
+                                                   "unit": "TFLOP/s", "frac": tflops_per_gpu / sustained, "traffic": None},
+        "step_tensor": {"achieved": tflops_per_gpu, "peak": sustained, "unit": "TFLOP/s", "frac": tflops_per_gpu / sustained,
+                        "note": f"whole step, 227.02 MFLOP/frame algorithmic, per GPU, of {which} sustained bf16 peak"},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cfps, cms, cores, threads = cpu_reference_fps(10, 3)

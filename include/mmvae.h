@@ -189,6 +189,14 @@ int mmvae_adam_step(int64_t n, float* params, const float* grads, float* exp_avg
  * shape = {kind (0 conv, 1 transposed), k, stride, padding, Ci, Co, H_in, H_out}. */
 int mmvae_conv_entry(const mmvae_desc* d, int32_t i, char* name, size_t name_cap, int32_t shape[8]);
 
+/* Measurement hook: enqueue ONE launch of the production tcgen05 kernel of conv `conv_index` (mmvae_conv_entry order)
+ * in direction `dir` (0 forward + fused BatchNorm statistics, 1 data gradient, 2 weight gradient) on whatever the
+ * workspace currently holds (run a forward / backward first).  algo_bytes / algo_flops receive the algorithmic
+ * traffic (bf16 input + output + weights, each touched once) and 2*MAC of that launch, so that a caller can bracket
+ * it with events and report achieved GB/s or FLOP/s (bench.py's roofline).  grads_scratch: n_params floats (dir 2). */
+int mmvae_bench_conv(const mmvae_desc* d, int32_t conv_index, int32_t dir, const float* params, void* workspace,
+                     size_t workspace_bytes, float* grads_scratch, int64_t* algo_bytes, int64_t* algo_flops, void* stream);
+
 /* Self-test of the tcgen05 kernels: every conv of the model that the tensor-core path covers is run in
  * all three directions (forward + BatchNorm statistics, weight gradient, data gradient) through both
  * the tcgen05 kernel and the fp32-FMA SIMT kernel on identical pseudo-random bf16 inputs.

@@ -22,7 +22,7 @@ EXPORTS = [
     "mmvae_workspace_tensor", "mmvae_forward", "mmvae_decode", "mmvae_loss_scratch_bytes",
     "mmvae_loss_forward", "mmvae_loss_backward", "mmvae_backward", "mmvae_backward_range",
     "mmvae_philox_normal", "mmvae_adam_step", "mmvae_prepare_input", "mmvae_launch_count",
-    "mmvae_conv_entry", "mmvae_selftest_tc",
+    "mmvae_conv_entry", "mmvae_selftest_tc", "mmvae_bench_conv",
 ]
 
 
@@ -76,6 +76,7 @@ def _load():
     lib.mmvae_prepare_input.argtypes = [P, c_int64, c_float, c_float, P, P, P]
     lib.mmvae_conv_entry.argtypes = [POINTER(Desc), c_int32, c_char_p, c_size_t, POINTER(c_int32 * 8)]
     lib.mmvae_selftest_tc.argtypes = [POINTER(Desc), P, P, c_size_t, P, P, P, c_int32, P]
+    lib.mmvae_bench_conv.argtypes = [POINTER(Desc), c_int32, c_int32, P, P, c_size_t, P, POINTER(c_int64), POINTER(c_int64), P]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ("mmvae_last_error", "mmvae_loss_scratch_bytes", "mmvae_launch_count"):

@@ -863,6 +863,49 @@ int mmvae_selftest_tc(const mmvae_desc* d, const float* params, void* workspace,
   return check_launches("mmvae_selftest_tc");
 }
 
+int mmvae_bench_conv(const mmvae_desc* d, int32_t conv_index, int32_t dir, const float* params, void* workspace,
+                     size_t workspace_bytes, float* grads_scratch, int64_t* algo_bytes, int64_t* algo_flops, void* stream) {
+  MMVAE_COMMON_CHECKS();
+  if (P.d.precision != MMVAE_PREC_BF16 || (P.d.flags & MMVAE_FLAG_FORCE_SIMT) || !P.d.training)
+    return fail(MMVAE_ERR_BAD_DESC, "mmvae_bench_conv needs a training-mode bf16 desc without MMVAE_FLAG_FORCE_SIMT");
+  if (conv_index < 0 || conv_index >= (int)P.convs.size()) return fail(MMVAE_ERR_BAD_ARG, "conv index out of range");
+  if (dir < 0 || dir > 2 || !params) return fail(MMVAE_ERR_BAD_ARG, "bad arguments");
+  typedef __nv_bfloat16 T;
+  const ConvT_& c = P.convs[conv_index];
+  if (c.in < 0 || c.wp_chunks[DIR_FPROP] <= 0) return fail(MMVAE_ERR_BAD_ARG, "conv %s is not on the tcgen05 path", c.name.c_str());
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  Exec<T> E{P, (char*)workspace, params, grads_scratch, nullptr, nullptr, st, nullptr};
+  const ActT& ai = P.acts[c.in]; const ActT& ao = P.acts[c.out];
+  const long long n_in = (long long)P.d.batch * ai.H * ai.W * ai.C, n_out = (long long)P.d.batch * ao.H * ao.W * ao.C;
+  const long long nw = (long long)c.Ci * c.Co * c.k * c.k;
+  // every conv / transposed conv of the model does batch * (input pixels or output pixels) * Ci*Co*k*k / s^2 MACs
+  const long long macs = (c.kind == CONV) ? n_out / ao.C * c.Co * (long long)c.Ci * c.k * c.k
+                                          : n_in / ai.C * c.Ci * (long long)c.Co * c.k * c.k;
+  if (algo_flops) *algo_flops = 2 * macs;
+  if (dir == 0) {
+    GConvParams g;
+    geom_fprop(c, P.d.batch, g);
+    g.in = E.at<T>(ai.off); g.out = E.at<T>(ao.off); g.w = params + c.w;
+    g.wpack = (char*)workspace + c.wp_off[DIR_FPROP];
+    g.bn = E.bn_fused(P.bns[c.bn]);          // statistics accumulate as in the step; running buffers are not touched
+    launch_gconv_tc(g, st);
+    if (algo_bytes) *algo_bytes = 2 * (n_in + n_out + nw);
+  } else if (dir == 1) {
+    if (c.wp_chunks[DIR_DGRAD] <= 0) return fail(MMVAE_ERR_BAD_ARG, "conv %s has no data gradient", c.name.c_str());
+    GConvParams g;
+    geom_dgrad(c, P.d.batch, g);
+    g.in = E.at<T>(ao.goff); g.out = E.at<T>(ai.goff); g.w = params + c.w;
+    g.wpack = (char*)workspace + c.wp_off[DIR_DGRAD];
+    launch_gconv_tc(g, st);
+    if (algo_bytes) *algo_bytes = 2 * (n_in + n_out + nw);
+  } else {
+    if (!grads_scratch) return fail(MMVAE_ERR_BAD_ARG, "wgrad needs grads_scratch");
+    E.wgrad(c);
+    if (algo_bytes) *algo_bytes = 2 * (n_in + n_out) + 4 * nw;
+  }
+  return check_launches("mmvae_bench_conv");
+}
+
 int mmvae_conv_entry(const mmvae_desc* d, int32_t i, char* name, size_t name_cap, int32_t shape[8]) {
   Plan P;
   if (!P.build(d)) return fail(MMVAE_ERR_BAD_DESC, "%s", P.err.c_str());
