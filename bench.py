@@ -316,7 +316,22 @@ def main():
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
+        # The captured graphs hold NCCL work on this communicator: release them before tearing it down (destroying the
+        # process group with live graphs deadlocks), and never let a stuck teardown outlive the measurement.
+        import gc
+        watchdog = threading.Timer(30.0, lambda: os._exit(0))
+        watchdog.daemon = True
+        watchdog.start()
+        torch.cuda.synchronize()
+        dist.barrier()
+        if not args.no_graph:
+            del step_resident, step_e2e
+            gstep.graph = gstep_lab.graph = None
+            del gstep, gstep_lab
+        gc.collect()
+        torch.cuda.synchronize()
         dist.destroy_process_group()
+        watchdog.cancel()
 
 
 if __name__ == "__main__":

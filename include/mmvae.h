@@ -197,6 +197,10 @@ int mmvae_conv_entry(const mmvae_desc* d, int32_t i, char* name, size_t name_cap
 int mmvae_bench_conv(const mmvae_desc* d, int32_t conv_index, int32_t dir, const float* params, void* workspace,
                      size_t workspace_bytes, float* grads_scratch, int64_t* algo_bytes, int64_t* algo_flops, void* stream);
 
+/* Debugging hook: device buffer of [444 CTAs][16] uint64 that the tcgen05 conv kernel fills with %globaltimer stamps
+ * of its pipeline milestones (scripts/trace_conv.py prints the timeline); NULL (the default) turns tracing off. */
+void mmvae_debug_set_trace(void* device_buffer);
+
 /* Self-test of the tcgen05 kernels: every conv of the model that the tensor-core path covers is run in
  * all three directions (forward + BatchNorm statistics, weight gradient, data gradient) through both
  * the tcgen05 kernel and the fp32-FMA SIMT kernel on identical pseudo-random bf16 inputs.

@@ -22,7 +22,7 @@ EXPORTS = [
     "mmvae_workspace_tensor", "mmvae_forward", "mmvae_decode", "mmvae_loss_scratch_bytes",
     "mmvae_loss_forward", "mmvae_loss_backward", "mmvae_backward", "mmvae_backward_range",
     "mmvae_philox_normal", "mmvae_adam_step", "mmvae_prepare_input", "mmvae_launch_count",
-    "mmvae_conv_entry", "mmvae_selftest_tc", "mmvae_bench_conv",
+    "mmvae_conv_entry", "mmvae_selftest_tc", "mmvae_bench_conv", "mmvae_debug_set_trace",
 ]
 
 
@@ -79,9 +79,11 @@ def _load():
     lib.mmvae_bench_conv.argtypes = [POINTER(Desc), c_int32, c_int32, P, P, c_size_t, P, POINTER(c_int64), POINTER(c_int64), P]
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name not in ("mmvae_last_error", "mmvae_loss_scratch_bytes", "mmvae_launch_count"):
+        if name not in ("mmvae_last_error", "mmvae_loss_scratch_bytes", "mmvae_launch_count", "mmvae_debug_set_trace"):
             fn.restype = c_int32
     lib.mmvae_launch_count.restype = c_int64
+    lib.mmvae_debug_set_trace.argtypes = [P]
+    lib.mmvae_debug_set_trace.restype = None
     if lib.mmvae_abi_version() != ABI_VERSION:
         raise ImportError(f"libmmvae_b200.so ABI {lib.mmvae_abi_version()} != binding {ABI_VERSION}; rebuild it")
     return lib

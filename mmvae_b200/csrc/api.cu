@@ -27,6 +27,8 @@ bool pdl_enabled() {
   return on;
 }
 std::atomic<long long> g_launches{0};
+static unsigned long long* g_trace_buf = nullptr;
+unsigned long long* debug_trace_buffer() { return g_trace_buf; }
 
 static int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -332,14 +334,98 @@ struct Exec {
     conv_wgrad<T>(w, c, !(P.d.flags & MMVAE_FLAG_FORCE_SIMT), st);
   }
 
-  void dgrad(const ConvT_& c, int accumulate) {
-    GConvParams g;
+  // ---- BatchNorm-backward reduction fused into the producer of the incoming gradient (BnBwdFused) ----
+  // Which BatchNorm(s) consume d(activation `a`): conv c (+ the shortcut conv c2 at a block output); mask = a itself.
+  bool consumer_of(int a, const ConvT_*& c, const ConvT_*& c2) const {
+    c = c2 = nullptr;
+    if (a == P.a_stem) { c = &P.convs[P.stem]; return true; }
+    if (a == P.a_dstem) { c = &P.convs[P.dstem]; return true; }
+    for (const std::vector<BlockT>* bl : {&P.enc, &P.dec})
+      for (const BlockT& b : *bl) {
+        if (a == b.a1) { c = &P.convs[b.c1]; return true; }
+        if (a == b.out) { c = &P.convs[b.c2]; c2 = &P.convs[b.cs]; return true; }
+      }
+    return false;
+  }
+  // The conv whose data gradient completes d(activation `a`): the shortcut of the block that reads `a` (it accumulates
+  // onto the main branch's gradient), or conv2 for a block's inner activation.  -1: produced by another kernel.
+  int last_dgrad_conv(int a) const {
+    for (const std::vector<BlockT>* bl : {&P.enc, &P.dec})
+      for (const BlockT& b : *bl) {
+        if (a == b.in) return b.cs;
+        if (a == b.a1) return b.c2;
+      }
+    return -1;
+  }
+  void fill_dgrad(const ConvT_& c, GConvParams& g) const {
     geom_dgrad(c, P.d.batch, g);
     g.in = at<T>(act(c.out).goff);
     g.out = at<T>(act(c.in).goff);
     g.w = params + c.w;
     g.wpack = c.wp_chunks[DIR_DGRAD] > 0 ? ws + c.wp_off[DIR_DGRAD] : nullptr;
+  }
+  // Does the data gradient of conv c reach every pixel of its input?  (A strided 1x1 shortcut only reaches the even ones.)
+  static bool dgrad_covers_all(const GConvParams& g) { return g.os == 1 || g.nvar == g.os * g.os; }
+  // The block whose shortcut is conv index ci (or nullptr)
+  const BlockT* block_of_shortcut(int ci) const {
+    for (const std::vector<BlockT>* bl : {&P.enc, &P.dec})
+      for (const BlockT& b : *bl) if (b.cs == ci) return &b;
+    return nullptr;
+  }
+  // A pure function of the plan (backward phases run in separate calls): do the producers of d(a) mask and reduce?
+  bool fused_reduce(int a) const {
+    static const bool off = getenv("MMVAE_NO_BWD_FUSE") != nullptr;
+    if (off || a < 0 || !special_ok()) return false;
+    const int ci = last_dgrad_conv(a);
+    const ConvT_ *c, *c2;
+    if (ci < 0 || !consumer_of(a, c, c2)) return false;
+    GConvParams g;
+    fill_dgrad(P.convs[ci], g);
+    if (!tc_supported_gconv(g)) return false;
+    // measured (profiles/r01_fused_bn_bwd.md): with one epilogue warp per scheduler the extra loads and column sums
+    // only pay off for 16-channel tensors (one 16-column group per tile); wider ones keep the separate reduce kernel
+    static const bool all = getenv("MMVAE_BWD_FUSE_ALL") != nullptr;
+    if (g.Co > 16 && !all) return false;
+    if (dgrad_covers_all(g)) return true;
+    // partial coverage (even pixels only): the main branch's data gradient handles the other parity classes
+    const BlockT* b = block_of_shortcut(ci);
+    if (!b || g.nvar != 1 || g.os != 2 || g.var[0].oy0 != 0 || g.var[0].ox0 != 0) return false;
+    GConvParams g1;
+    fill_dgrad(P.convs[b->c1], g1);
+    return tc_supported_gconv(g1) && g1.os == 2 && g1.nvar == 4;
+  }
+
+  void dgrad(const ConvT_& c, int accumulate) {
+    GConvParams g;
+    fill_dgrad(c, g);
     g.accumulate = accumulate;
+    if (c.in >= 0 && fused_reduce(c.in)) {
+      const int last = last_dgrad_conv(c.in);
+      GConvParams gl;
+      fill_dgrad(P.convs[last], gl);
+      int var_mask = 0, finish = 0;
+      if (&P.convs[last] == &c) { var_mask = (1 << g.nvar) - 1; finish = 1; }
+      else if (!dgrad_covers_all(gl)) {              // c is the main-branch conv1 of an encoder block: all but (even, even)
+        for (int v = 0; v < g.nvar; ++v) if (g.var[v].oy0 != 0 || g.var[v].ox0 != 0) var_mask |= 1 << v;
+      }
+      if (var_mask) {
+        const ConvT_ *bc, *bc2;
+        consumer_of(c.in, bc, bc2);
+        const BnT& b = P.bns[bc->bn];
+        BnBwdFused& f = g.bb;
+        f.a = at<T>(act(c.in).off);
+        f.y = at<T>(act(bc->out).off); f.stat = at<float>(b.stat_off); f.gamma = params + b.gamma;
+        f.acc = at<double>(b.acc_off) + kBnAccCopies * 2 * b.C; f.counter = at<unsigned int>(b.cnt_off) + 1;
+        f.bcoef = at<float>(b.bcoef_off);
+        if (bc2) {
+          const BnT& b2 = P.bns[bc2->bn];
+          f.y2 = at<T>(act(bc2->out).off); f.stat2 = at<float>(b2.stat_off); f.gamma2 = params + b2.gamma;
+          f.bcoef2 = at<float>(b2.bcoef_off);
+        }
+        f.C = b.C; f.var_mask = var_mask; f.finish = finish;
+        f.inv_rows = 1.0 / ((double)P.d.batch * bc->Ho * bc->Wo);
+      }
+    }
     conv_dgrad<T>(g, c, st);
   }
 
@@ -364,6 +450,7 @@ struct Exec {
       a.dY2 = at<T>(act(c2->out).goff);
     }
     a.rows = (long long)P.d.batch * c.Ho * c.Wo; a.C = c.Co;
+    if (mask_act >= 0 && fused_reduce(mask_act)) { a.reduced = 1; a.a = nullptr; }   // dA arrives masked and reduced
     launch_bn_bwd<T>(a, st);
   }
 
@@ -670,6 +757,7 @@ int mmvae_loss_backward(const mmvae_loss_args* a, const float* recon, const void
 }
 
 int64_t mmvae_launch_count(void) { return (int64_t)g_launches.load(); }
+void mmvae_debug_set_trace(void* device_buffer) { g_trace_buf = reinterpret_cast<unsigned long long*>(device_buffer); }
 
 int mmvae_prepare_input(const uint8_t* labels, int64_t n, float data_mean, float data_std, float* x, int64_t* target,
                         void* stream) {

@@ -53,4 +53,41 @@ __device__ __forceinline__ void bn_fused_finish(const BnFused& b, unsigned int n
   }
 }
 
+__device__ __forceinline__ double* bn_bwd_acc_copy(const BnBwdFused& b) {
+  return b.acc + (size_t)(blockIdx.x % kBnAccCopies) * 3 * b.C;
+}
+
+// Backward counterpart of bn_fused_finish: called by ALL threads of the CTA after their atomicAdd contributions
+// to the [copies][3][C] accumulators; the last CTA writes the backward coefficients (and the raw sums, from which
+// the BatchNorm-backward apply kernel publishes d gamma / d beta).
+__device__ __forceinline__ void bn_bwd_fused_finish(const BnBwdFused& b, unsigned int nctas) {
+  __shared__ int bnb_is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) bnb_is_last = (atomicAdd(b.counter, 1u) == nctas - 1u) ? 1 : 0;
+  __syncthreads();
+  if (!bnb_is_last) return;
+  __threadfence();
+  for (int c = threadIdx.x; c < b.C; c += blockDim.x) {
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < kBnAccCopies; ++k) {           // fixed order over the copies
+      const double* ak = b.acc + (size_t)k * 3 * b.C;
+      s0 += ld_cg_f64(ak + c); s1 += ld_cg_f64(ak + b.C + c); s2 += ld_cg_f64(ak + 2 * b.C + c);
+    }
+    b.bcoef[c] = b.gamma[c] * b.stat[b.C + c];
+    b.bcoef[b.C + c] = (float)(s0 * b.inv_rows);
+    b.bcoef[2 * b.C + c] = (float)(s1 * b.inv_rows);
+    b.bcoef[3 * b.C + c] = (float)s0;
+    b.bcoef[4 * b.C + c] = (float)s1;
+    if (b.y2) {
+      b.bcoef2[c] = b.gamma2[c] * b.stat2[b.C + c];
+      b.bcoef2[b.C + c] = (float)(s0 * b.inv_rows);
+      b.bcoef2[2 * b.C + c] = (float)(s2 * b.inv_rows);
+      b.bcoef2[3 * b.C + c] = (float)s0;
+      b.bcoef2[4 * b.C + c] = (float)s2;
+    }
+  }
+}
+
 }  // namespace mmvae

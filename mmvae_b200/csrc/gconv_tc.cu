@@ -33,7 +33,8 @@ namespace {
 constexpr int kGatherThreads = 128;
 constexpr int kTcThreads = 288;         // 4 producer warps, 1 MMA warp, 4 epilogue warps
 constexpr int kStageA = 128 * 128;      // bytes: 128 rows x 64 bf16 (fprop) or 128 (tap,ci) x 64 pixels (wgrad)
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 12;
+constexpr int kTabCap = 320;            // TMA coordinate table entries (variants x k-chunks x sub-tiles)
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -81,6 +82,14 @@ __device__ __forceinline__ int warp_colsum16(float (&v)[16], int lane) {
   return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// debugging timeline: slot s of this CTA's row (p.trace == nullptr in production)
+#define MMVAE_TRACE(p, s) do { if ((p).trace) (p).trace[(size_t)blockIdx.x * 32 + (s)] = globaltimer_ns(); } while (0)
+
 __device__ __forceinline__ uint32_t swz_code(int row_bytes) { return row_bytes == 128 ? SWZ_128 : (row_bytes == 64 ? SWZ_64 : SWZ_32); }
 
 // ------------------------------------------------------------------------------------------------
@@ -92,13 +101,20 @@ __device__ __forceinline__ void decode_tile(const GConvParams& p, int t, int& mt
   p.fd_nvar.divmod(r, mt, v);
 }
 
-template <int kBN>
-__global__ void __launch_bounds__(kTcThreads, 3) gconv_tc_kernel(const __grid_constant__ GConvParams p) {
+// experiment: tc_flags bit 0 = poll with mbarrier.test_wait instead of the (suspending) try_wait
+#define MBAR_WAIT(bar, ph) do { if (p.tc_flags & 1) { while (!mbar_test_wait((bar), (ph))) {} } else mbar_wait((bar), (ph)); } while (0)
+
+// kBwd: data-gradient instantiation whose epilogue also masks the gradient with the consumer's ReLU and reduces the
+// consumer's BatchNorm-backward sums (BnBwdFused) -- more live registers, so two CTAs per SM instead of three
+template <int kBN, bool kBwd>
+__global__ void __launch_bounds__(kTcThreads, kBwd ? 2 : 3) gconv_tc_kernel(const __grid_constant__ GConvParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long full[kMaxStages], empty[kMaxStages], tfull[2], tempty[2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float stat_red[4][2][kBN];
+  __shared__ float stat_red[4][kBwd ? 3 : 2][kBN];
+  __shared__ uint32_t tma_tab[kTabCap];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) MMVAE_TRACE(p, 0);
   constexpr int BN = kBN;
   const int S = p.tc_stages;
   const int stageB = BN * 128;
@@ -110,6 +126,24 @@ __global__ void __launch_bounds__(kTcThreads, 3) gconv_tc_kernel(const __grid_co
   const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = ring, b_base = ring + (uint32_t)S * kStageA;
 
+  // TMA coordinate table: entry (variant, k-chunk, sub-tile) = channel offset | dx << 16 | dy << 24 of the box; built by
+  // all threads here (kernel parameters only: legal before the PDL wait) so that the producer thread's loop is lean
+  const int kb_log2 = p.tc_kb_log2, sub_shift = 6 - kb_log2;
+  if (p.use_tma) {
+    const int total = (p.nvar * p.tc_maxchunks) << sub_shift;
+    for (int e = tid; e < total; e += kTcThreads) {
+      const int g = e & ((1 << sub_shift) - 1), r = e >> sub_shift;
+      const int vi = r / p.tc_maxchunks, kc = r - vi * p.tc_maxchunks;
+      const int k = kc * 64 + (g << kb_log2);
+      uint32_t ent = 0;
+      if (k < p.var[vi].ntaps * p.Ci) {
+        int tap, ci;
+        p.fd_ci.divmod(k, tap, ci);
+        ent = (uint32_t)ci | ((uint32_t)(unsigned char)p.var[vi].dx[tap] << 16) | ((uint32_t)(unsigned char)p.var[vi].dy[tap] << 24);
+      }
+      tma_tab[e] = ent;
+    }
+  }
   if (tid == 0) {
     if (p.use_tma) prefetch_tensormap(&p.tmap_a);
     for (int s = 0; s < S; ++s) {
@@ -128,8 +162,10 @@ __global__ void __launch_bounds__(kTcThreads, 3) gconv_tc_kernel(const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
+  if (tid == 0) MMVAE_TRACE(p, 1);
   pdl_wait();                                   // everything above overlapped the previous kernel's tail
   pdl_trigger();
+  if (tid == 0) MMVAE_TRACE(p, 2);
 
   if (warp < 4) {
     if (p.use_tma) {
@@ -150,22 +186,28 @@ __global__ void __launch_bounds__(kTcThreads, 3) gconv_tc_kernel(const __grid_co
           p.fd_wg.divmod(rem, i0, j0);
           const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(p.wpack) + (size_t)vi * p.wpack_var_stride +
                                       (size_t)((nt * BN) >> 3) * 1024;
+          if (t == (int)blockIdx.x) MMVAE_TRACE(p, 16);
+          const int xb = j0 * p.is, yb = i0 * p.is;
+          const uint32_t* tab = tma_tab + ((vi * p.tc_maxchunks) << sub_shift);
+          const size_t wstep = (size_t)p.co_pad * 128;
           for (int kc = 0; kc < nchunks; ++kc) {
-            mbar_wait(smem_u32(&empty[stage]), ephase);
+            MBAR_WAIT(smem_u32(&empty[stage]), ephase);
             const uint32_t bar = smem_u32(&full[stage]);
-            const int kend = min(K, kc * 64 + 64);
-            const int nsub = (kend - kc * 64 + kb - 1) / kb;
+            const int nsub = kc + 1 < nchunks ? (1 << sub_shift) : ((K - kc * 64 + kb - 1) >> kb_log2);
             mbar_arrive_expect_tx(bar, (uint32_t)(stageB + nsub * sub_bytes));
-            bulk_g2s(b_base + (uint32_t)stage * stageB, wsrc + (size_t)kc * p.co_pad * 128, (uint32_t)stageB, bar);
-            for (int g = 0; g < nsub; ++g) {
-              int tap, ci;
-              p.fd_ci.divmod(kc * 64 + g * kb, tap, ci);
-              tma_load_4d(a_base + (uint32_t)stage * kStageA + (uint32_t)g * sub_bytes, tmap, bar, ci,
-                          j0 * p.is + var.dx[tap], i0 * p.is + var.dy[tap], n0);
+            bulk_g2s(b_base + (uint32_t)stage * stageB, wsrc, (uint32_t)stageB, bar);
+            wsrc += wstep;
+            uint32_t dst = a_base + (uint32_t)stage * kStageA;
+            for (int g = 0; g < nsub; ++g, dst += (uint32_t)sub_bytes) {
+              const uint32_t ent = tab[(kc << sub_shift) + g];
+              tma_load_4d(dst, tmap, bar, (int)(ent & 0xffffu), xb + (int)(signed char)(ent >> 16), yb + (int)(signed char)(ent >> 24), n0);
             }
             if (++stage == S) { stage = 0; ephase ^= 1u; }
+            if (t == (int)blockIdx.x && kc == 0) MMVAE_TRACE(p, 3);
+            if (t == (int)blockIdx.x && kc == 1) MMVAE_TRACE(p, 17);
           }
         }
+        MMVAE_TRACE(p, 4);
       }
     } else {
       // ---------------- producers: cp.async gather, thread -> 16-byte chunk j of rows rg + 16*i ----------------
@@ -243,6 +285,13 @@ __global__ void __launch_bounds__(kTcThreads, 3) gconv_tc_kernel(const __grid_co
       const uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
       const uint32_t aswz = swz_code(kbB);
       const uint32_t asbo = 8u * (uint32_t)kbB;
+      // descriptors of stage 0 / k-step 0; a stage or k-step only moves the (address >> 4) field (no carry: smem < 256 KB)
+      const uint64_t da0 = make_smem_desc(a_base, 16, asbo, aswz);
+      const uint64_t db0 = make_smem_desc(b_base, 16, 1024, SWZ_128);
+      uint32_t aoff[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        aoff[q] = ((uint32_t)((q * 16) >> kb_log2) * (uint32_t)sub_bytes + (uint32_t)((q * 16) & (kb - 1)) * 2u) >> 4;
       int stage = 0;
       uint32_t fphase = 0;
       int i = 0;
@@ -252,27 +301,30 @@ __global__ void __launch_bounds__(kTcThreads, 3) gconv_tc_kernel(const __grid_co
         const int K = p.var[vi].ntaps * p.Ci;
         const int nchunks = (K + 63) >> 6;
         const int buf = i & 1;
-        mbar_wait(smem_u32(&tempty[buf]), (uint32_t)(((i >> 1) & 1) ^ 1));   // epilogue drained this buffer
+        MBAR_WAIT(smem_u32(&tempty[buf]), (uint32_t)(((i >> 1) & 1) ^ 1));   // epilogue drained this buffer
         tc_fence_after();
         const uint32_t dtm = tmem + (uint32_t)(buf * BN);
         for (int kc = 0; kc < nchunks; ++kc) {
-          mbar_wait(smem_u32(&full[stage]), fphase);
+          MBAR_WAIT(smem_u32(&full[stage]), fphase);
           tc_fence_after();
+          if (i == 0 && kc == 0) MMVAE_TRACE(p, 5);
+          if (i == 0 && kc == 1) MMVAE_TRACE(p, 19);
           const int kleft = K - kc * 64;
           const int nk = kleft >= 64 ? 4 : (kleft + 15) >> 4;
-          const uint32_t sa = a_base + (uint32_t)stage * kStageA, sb = b_base + (uint32_t)stage * stageB;
-          for (int q = 0; q < nk; ++q) {
-            const int kel = q * 16;
-            const int g = kel / kb, within = kel - g * kb;        // kb is 16 / 32 / 64
-            uint64_t da = make_smem_desc(sa + (uint32_t)g * sub_bytes + (uint32_t)within * 2, 16, asbo, aswz);
-            uint64_t db = make_smem_desc(sb + q * 32, 16, 1024, SWZ_128);
-            mma_bf16(dtm, da, db, idesc, (kc | q) != 0);
-          }
+          const uint64_t da = da0 + (uint64_t)(((uint32_t)stage * kStageA) >> 4);
+          const uint64_t db = db0 + (uint64_t)(((uint32_t)stage * (uint32_t)stageB) >> 4);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (q < nk) mma_bf16(dtm, da + aoff[q], db + (uint64_t)(q * 2), idesc, (kc | q) != 0);
           mma_commit(smem_u32(&empty[stage]));
+          if (i == 0 && kc == 0) MMVAE_TRACE(p, 18);
+          if (i == 0 && kc == 1) MMVAE_TRACE(p, 20);
           if (++stage == S) { stage = 0; fphase ^= 1u; }
         }
         mma_commit(smem_u32(&tfull[buf]));
+        if (i == 0) MMVAE_TRACE(p, 6);
       }
+      MMVAE_TRACE(p, 7);
     }
   } else {
     // ---------------- epilogue: TMEM -> bf16 NHWC (+ fused BatchNorm statistics) ----------------
@@ -288,6 +340,10 @@ __global__ void __launch_bounds__(kTcThreads, 3) gconv_tc_kernel(const __grid_co
     float run_s[NR], run_q[NR];
 #pragma unroll
     for (int e = 0; e < NR; ++e) { run_s[e] = 0.f; run_q[e] = 0.f; }
+    float run_b[kBwd ? 3 * NG : 1];                      // kBwd: S0, S1, S2 of this lane's column per 16-column group
+#pragma unroll
+    for (int e = 0; e < (kBwd ? 3 * NG : 1); ++e) run_b[e] = 0.f;
+    const bool bwd2 = kBwd && p.bb.y2 != nullptr;
     int i = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
       int mt, vi, nt;
@@ -306,8 +362,10 @@ __global__ void __launch_bounds__(kTcThreads, 3) gconv_tc_kernel(const __grid_co
         valid = oy < p.Ho && ox < p.Wo;                  // ragged parity sub-grid of an odd-sized stride-2 dgrad
         obase = ((size_t)(n * p.Ho + oy) * p.Wo + ox) * p.Co;
       }
-      mbar_wait(smem_u32(&tfull[buf]), (uint32_t)((i >> 1) & 1));
+      const bool fuse_v = kBwd && ((p.bb.var_mask >> vi) & 1);       // this tile's pixels are final here: mask + reduce
+      MBAR_WAIT(smem_u32(&tfull[buf]), (uint32_t)((i >> 1) & 1));
       tc_fence_after();
+      if (i == 0 && tid == 160) MMVAE_TRACE(p, 8);
       const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
 #pragma unroll
       for (int gq = 0; gq < NG; ++gq) {
@@ -319,9 +377,14 @@ __global__ void __launch_bounds__(kTcThreads, 3) gconv_tc_kernel(const __grid_co
 #pragma unroll
           for (int e = 0; e < 16; ++e) if (co0 + e < p.Co) v[e] += __ldg(p.bias + co0 + e);
         }
+        float t1[kBwd ? 16 : 1], t2[kBwd ? 16 : 1];      // kBwd: g * xhat(y), g * xhat(y2)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int co = co0 + h * 8;
+          if constexpr (kBwd) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { t1[h * 8 + e] = 0.f; t2[h * 8 + e] = 0.f; }
+          }
           if (valid && co < p.Co) {
             uint4* dst = reinterpret_cast<uint4*>(out + obase + co);
             if (p.accumulate) {
@@ -329,6 +392,25 @@ __global__ void __launch_bounds__(kTcThreads, 3) gconv_tc_kernel(const __grid_co
               const __nv_bfloat16* o = reinterpret_cast<const __nv_bfloat16*>(&old);
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[h * 8 + e] += __bfloat162float(o[e]);
+            }
+            if (kBwd && fuse_v) {
+              // g = bf16(dA) * [a > 0]; the masked value is what gets stored and what the sums see
+              const uint4 yr = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.bb.y) + obase + co));
+              const __nv_bfloat16* yb = reinterpret_cast<const __nv_bfloat16*>(&yr);
+              uint4 ar = make_uint4(0u, 0u, 0u, 0u), y2r = make_uint4(0u, 0u, 0u, 0u);
+              if (p.bb.a) ar = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.bb.a) + obase + co));
+              if (bwd2) y2r = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.bb.y2) + obase + co));
+              const __nv_bfloat16* ab = reinterpret_cast<const __nv_bfloat16*>(&ar);
+              const __nv_bfloat16* y2b = reinterpret_cast<const __nv_bfloat16*>(&y2r);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                float g = __bfloat162float(__float2bfloat16_rn(v[h * 8 + e]));
+                if (p.bb.a && !(__bfloat162float(ab[e]) > 0.f)) g = 0.f;
+                v[h * 8 + e] = g;
+                const int c = co + e;
+                t1[h * 8 + e] = g * ((__bfloat162float(yb[e]) - __ldg(p.bb.stat + c)) * __ldg(p.bb.stat + p.bb.C + c));
+                if (bwd2) t2[h * 8 + e] = g * ((__bfloat162float(y2b[e]) - __ldg(p.bb.stat2 + c)) * __ldg(p.bb.stat2 + p.bb.C + c));
+              }
             }
             uint4 pk;
             pk.x = pack_bf16x2(v[h * 8 + 0], v[h * 8 + 1]); pk.y = pack_bf16x2(v[h * 8 + 2], v[h * 8 + 3]);
@@ -358,10 +440,30 @@ __global__ void __launch_bounds__(kTcThreads, 3) gconv_tc_kernel(const __grid_co
             }
           }
         }
+        if constexpr (kBwd) {
+          if (fuse_v) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              if (!(valid && co0 + e < p.Co)) v[e] = 0.f;
+            warp_colsum16(v, lane);
+            warp_colsum16(t1, lane);
+            if (bwd2) warp_colsum16(t2, lane);
+            if (merge) {
+              run_b[gq * 3 + 0] += v[0]; run_b[gq * 3 + 1] += t1[0]; run_b[gq * 3 + 2] += t2[0];
+            } else if ((lane & 1) == 0 && co0 + lane_col < p.Co) {
+              double* acc = bn_bwd_acc_copy(p.bb) + co0 + lane_col;
+              atomicAdd(acc, (double)v[0]);
+              atomicAdd(acc + p.bb.C, (double)t1[0]);
+              if (bwd2) atomicAdd(acc + 2 * p.bb.C, (double)t2[0]);
+            }
+          }
+        }
       }
       tc_fence_before();
       mbar_arrive(smem_u32(&tempty[buf]));               // accumulator buffer is free for tile i+2
+      if (i == 0 && tid == 160) MMVAE_TRACE(p, 9);
     }
+    if (tid == 160) MMVAE_TRACE(p, 10);
     if (stats && merge) {
       // combine the four epilogue warps in shared memory, then one set of atomics per CTA
       if constexpr (kPerThread) {
@@ -385,14 +487,39 @@ __global__ void __launch_bounds__(kTcThreads, 3) gconv_tc_kernel(const __grid_co
         }
       }
     }
+    if constexpr (kBwd) {
+      if (p.bb.acc && merge) {
+        if ((lane & 1) == 0) {
+#pragma unroll
+          for (int gq = 0; gq < NG; ++gq)
+#pragma unroll
+            for (int w3 = 0; w3 < 3; ++w3) stat_red[q][w3][gq * 16 + lane_col] = run_b[gq * 3 + w3];
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int et = (warp - 5) * 32 + lane;
+        for (int e = et; e < (bwd2 ? 3 : 2) * kBN; e += 128) {
+          const int which = e / kBN, c = e - which * kBN;
+          if (c < p.Co) {
+            const float t = (stat_red[0][which][c] + stat_red[1][which][c]) + (stat_red[2][which][c] + stat_red[3][which][c]);
+            atomicAdd(bn_bwd_acc_copy(p.bb) + which * p.bb.C + c, (double)t);
+          }
+        }
+      }
+    }
   }
+  if (tid == 160) MMVAE_TRACE(p, 11);
   tc_fence_before();
   __syncthreads();
   if (warp == 4) {
     tc_fence_after();
     tmem_dealloc(tmem, ncols);
   }
+  if (tid == 0) MMVAE_TRACE(p, 12);
   if (p.bn.acc) bn_fused_finish(p.bn, gridDim.x);
+  if constexpr (kBwd) {
+    if (p.bb.acc && p.bb.finish) bn_bwd_fused_finish(p.bb, gridDim.x);
+  }
+  if (tid == 0) MMVAE_TRACE(p, 13);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -420,6 +547,18 @@ __global__ void __launch_bounds__(kTcThreads) wgrad_tc_kernel(const __grid_const
   const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = ring, b_base = ring + (uint32_t)S * kStageA;
 
+  // TMA coordinates of this CTA's (tap, channel block) sub-tiles: channel offset | dx << 16 | dy << 24
+  __shared__ uint32_t tma_tab[8];
+  if (tid < 8) {
+    const int k = k0 + tid * kb;
+    uint32_t ent = 0;
+    if (k < K) {
+      int tap, ci;
+      p.fd_ci.divmod(k, tap, ci);
+      ent = (uint32_t)ci | ((uint32_t)(unsigned char)var.dx[tap] << 16) | ((uint32_t)(unsigned char)var.dy[tap] << 24);
+    }
+    tma_tab[tid] = ent;
+  }
   if (tid == 0) {
     if (p.tma_a) prefetch_tensormap(&p.tmap_a);
     if (p.tma_b) prefetch_tensormap(&p.tmap_b);
@@ -465,11 +604,11 @@ __global__ void __launch_bounds__(kTcThreads) wgrad_tc_kernel(const __grid_const
         p.fd_hw.divmod(m_lo + it * 64, n0p, rem);
         p.fd_wg.divmod(rem, i0, j0);
         if (p.tma_a) {
-          for (int g = 0; g < nsub; ++g) {
-            int tap, ci;
-            p.fd_ci.divmod(k0 + g * kb, tap, ci);
-            tma_load_4d(a_base + (uint32_t)stage * kStageA + (uint32_t)g * sub_bytes, tmap_a, bar, ci,
-                        j0 * p.is + var.dx[tap], i0 * p.is + var.dy[tap], n0p);
+          const int xb = j0 * p.is, yb = i0 * p.is;
+          uint32_t dst = a_base + (uint32_t)stage * kStageA;
+          for (int g = 0; g < nsub; ++g, dst += (uint32_t)sub_bytes) {
+            const uint32_t ent = tma_tab[g];
+            tma_load_4d(dst, tmap_a, bar, (int)(ent & 0xffffu), xb + (int)(signed char)(ent >> 16), yb + (int)(signed char)(ent >> 24), n0p);
           }
         }
         if (p.tma_b)
@@ -556,18 +695,20 @@ __global__ void __launch_bounds__(kTcThreads) wgrad_tc_kernel(const __grid_const
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
       const uint32_t bswz = swz_code(rowB), aswz = swz_code(kbB);
+      // descriptors of stage 0 / pixel step 0; a stage or a 16-pixel step only moves the (address >> 4) field
+      const uint64_t da0 = make_smem_desc(a_base, (uint32_t)sub_bytes, 8 * kbB, aswz);
+      const uint64_t db0 = make_smem_desc(b_base, 8 * rowB, 8 * rowB, bswz);
+      const uint64_t astep = (uint64_t)((16 * kbB) >> 4), bstep = (uint64_t)((16 * rowB) >> 4);
       int stage = 0;
       uint32_t fphase = 0;
       for (int kc = 0; kc < nchunks; ++kc) {
         mbar_wait(smem_u32(&full[stage]), fphase);
         tc_fence_after();
-        const uint32_t sa = a_base + (uint32_t)stage * kStageA, sb = b_base + (uint32_t)stage * stageB;
+        const uint64_t da = da0 + (uint64_t)(((uint32_t)stage * kStageA) >> 4);
+        const uint64_t db = db0 + (uint64_t)(((uint32_t)stage * (uint32_t)stageB) >> 4);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {            // 16 pixels per MMA
-          uint64_t da = make_smem_desc(sa + q * 16 * kbB, (uint32_t)sub_bytes, 8 * kbB, aswz);
-          uint64_t db = make_smem_desc(sb + q * 16 * rowB, 8 * rowB, 8 * rowB, bswz);
-          mma_bf16(tmem, da, db, idesc, (kc | q) != 0);
-        }
+        for (int q = 0; q < 4; ++q)              // 16 pixels per MMA
+          mma_bf16(tmem, da + q * astep, db + q * bstep, idesc, (kc | q) != 0);
         mma_commit(smem_u32(&empty[stage]));
         if (++stage == S) { stage = 0; fphase ^= 1u; }
       }
@@ -732,8 +873,14 @@ StatLayout launch_gconv_tc(const GConvParams& p0, cudaStream_t st) {
   int maxchunks = 1;
   for (int v = 0; v < p.nvar; ++v) maxchunks = max(maxchunks, (p.var[v].ntaps * p.Ci + 63) / 64);
   // shallow-K layers live on many small CTAs per SM (latency hiding by occupancy), deep-K layers on a deep ring
-  int stages = maxchunks <= 2 ? 3 : min(kMaxStages, max(2, (100 * 1024) / stage_bytes));
+  int stages = maxchunks <= 2 ? 3 : min(8, max(2, (100 * 1024) / stage_bytes));
+  // launches with at most one CTA per SM own the whole shared memory: a deep ring hides the L2 latency of deep-K layers
+  {
+    const int tiles = tiles_m * p.nvar * ((co_pad + bn - 1) / bn);
+    if (tiles <= 148 && maxchunks > 2) stages = min(min(kMaxStages, maxchunks * ((tiles + 147) / 148)), max(2, (198 * 1024) / stage_bytes));
+  }
   p.tc_bn = bn; p.tc_stages = stages; p.co_pad = co_pad;
+  p.tc_maxchunks = maxchunks;
   p.tiles_m = tiles_m; p.n_tiles = (co_pad + bn - 1) / bn; p.total_tiles = tiles_m * p.nvar * p.n_tiles;
   p.tc_merge = p.n_tiles == 1 ? 1 : 0;
   p.fd_wg = FastDiv(p.Wg); p.fd_hg = FastDiv(p.Hg); p.fd_ci = FastDiv(p.Ci);
@@ -746,23 +893,41 @@ StatLayout launch_gconv_tc(const GConvParams& p0, cudaStream_t st) {
       make_tmap(p.tmap_a, p.in, p.N, p.Hi, p.Wi, p.Ci, kb, bw, bh, bnb, p.is)) {
     p.use_tma = 1; p.tc_kb = kb;
   }
+  if (p.use_tma && p.nvar * maxchunks * (64 / p.tc_kb) > kTabCap) { p.use_tma = 0; p.tc_kb = 64; }   // coordinate table too small
+  p.tc_kb_log2 = p.tc_kb == 64 ? 6 : (p.tc_kb == 32 ? 5 : 4);
   const size_t smem = (size_t)stages * stage_bytes + 1024;
+  const bool bwd = p.bb.acc != nullptr;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(gconv_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(gconv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(gconv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(gconv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(gconv_tc_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(gconv_tc_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(gconv_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(gconv_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(gconv_tc_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(gconv_tc_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(gconv_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(gconv_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_done = true;
   }
-  const int per_sm = min(gconv_per_sm(), smem <= 72 * 1024 ? 3 : 2);
+  const int per_sm = min(gconv_per_sm(), bwd ? 2 : (smem <= 72 * 1024 ? 3 : 2));
   const int grid = min(p.total_tiles, per_sm * 148);
+  p.trace = debug_trace_buffer();
+  { static int fl = [] { const char* e = getenv("MMVAE_TC_FLAGS"); return e ? atoi(e) : 0; }(); p.tc_flags = fl; }
   count_launch();
-  switch (bn) {
-    case 16: launch_pdl(gconv_tc_kernel<16>, grid, kTcThreads, smem, st, p); break;
-    case 32: launch_pdl(gconv_tc_kernel<32>, grid, kTcThreads, smem, st, p); break;
-    case 64: launch_pdl(gconv_tc_kernel<64>, grid, kTcThreads, smem, st, p); break;
-    default: launch_pdl(gconv_tc_kernel<128>, grid, kTcThreads, smem, st, p); break;
+  if (bwd) {
+    switch (bn) {
+      case 16: launch_pdl(gconv_tc_kernel<16, true>, grid, kTcThreads, smem, st, p); break;
+      case 32: launch_pdl(gconv_tc_kernel<32, true>, grid, kTcThreads, smem, st, p); break;
+      case 64: launch_pdl(gconv_tc_kernel<64, true>, grid, kTcThreads, smem, st, p); break;
+      default: launch_pdl(gconv_tc_kernel<128, true>, grid, kTcThreads, smem, st, p); break;
+    }
+  } else {
+    switch (bn) {
+      case 16: launch_pdl(gconv_tc_kernel<16, false>, grid, kTcThreads, smem, st, p); break;
+      case 32: launch_pdl(gconv_tc_kernel<32, false>, grid, kTcThreads, smem, st, p); break;
+      case 64: launch_pdl(gconv_tc_kernel<64, false>, grid, kTcThreads, smem, st, p); break;
+      default: launch_pdl(gconv_tc_kernel<128, false>, grid, kTcThreads, smem, st, p); break;
+    }
   }
   return sl;       // statistics are finalised inside the kernel (p.bn); no partial rows
 }

@@ -17,6 +17,7 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
 // their prologue (barrier init, TMEM allocation, descriptor prefetch).  Under stream capture the edge becomes a
 // programmatic dependency of the CUDA graph.  MMVAE_NO_PDL=1 turns the attribute off (plain stream order).
 bool pdl_enabled();
+unsigned long long* debug_trace_buffer();   // device buffer set by mmvae_debug_set_trace, or nullptr
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -64,6 +65,24 @@ struct BnFused {
   double inv_m, unbias;        // 1/m and m/(m-1) for the m = N*H*W values per channel
 };
 
+// BatchNorm-backward reduction folded into the kernel that produces the incoming gradient dA (the data-gradient
+// epilogue of the tcgen05 conv kernel): g = bf16(dA) * [a > 0] is what gets stored, and per channel
+//   S0 = sum g, S1 = sum g * xhat(y), S2 = sum g * xhat(y2)
+// go to fp64 accumulators; the CTA that finishes last writes the backward coefficients.  acc == nullptr: off.
+struct BnBwdFused {
+  const void* a;               // activation for the ReLU mask (same shape as dA), bf16
+  const void* y;  const float* stat;  const float* gamma;     // main branch: raw conv output, (mean, rstd)
+  const void* y2; const float* stat2; const float* gamma2;    // second branch or nullptr
+  double* acc;                 // [kBnAccCopies][3][C], zeroed
+  unsigned int* counter;       // CTAs finished, zeroed
+  float* bcoef; float* bcoef2; // [5][C]: scale, S0/m, S1/m, S0, S1 (the last two become d beta, d gamma)
+  int C;
+  int var_mask;                // parity variants of this launch whose pixels get masked + reduced here (the others are
+                               // completed, masked and reduced by a later launch that accumulates onto them)
+  int finish;                  // this launch is the last contributor: its last CTA writes bcoef
+  double inv_rows;
+};
+
 // Opaque copy of a CUtensorMap (TMA descriptor); lives inside the __grid_constant__ kernel parameter.
 struct alignas(64) TmaDesc { unsigned long long v[16]; };
 
@@ -102,9 +121,13 @@ struct GConvParams {
   int co_pad;                  // Co rounded up to 16
   float* part_counts;          // rows behind each `partials` row when the kernel merges its tiles (or nullptr)
   BnFused bn;                  // tcgen05 / stem / tail kernels: fused statistics (bn.acc != nullptr)
+  BnBwdFused bb;               // tcgen05 data gradient: fused BatchNorm-backward reduction of the consumer (bb.acc != nullptr)
   // set by the launcher
   int tc_bn, tc_stages, tc_merge;
   int tc_kb, use_tma;          // channels per A sub-tile; A staged by TMA boxes (else cp.async gather)
+  int tc_kb_log2, tc_maxchunks; // log2(tc_kb); k-chunks (of 64) of the deepest variant
+  int tc_flags;                // experiments (MMVAE_TC_FLAGS env)
+  unsigned long long* trace;   // debugging: [CTA][16] globaltimer stamps (mmvae_debug_set_trace), nullptr = off
   int tiles_m, n_tiles, total_tiles;
   FastDiv fd_wg, fd_hg, fd_ci, fd_hw, fd_ntiles, fd_nvar;
   GVar var[kMaxVar];
@@ -248,7 +271,9 @@ struct BnBwdArgs {
   float* partials;         // [blocks][C][3]
   double* acc;             // bf16 mode: [kBnAccCopies][3][C] fp64 accumulators (zeroed) + last-block finalize; nullptr: partials path
   unsigned int* counter;   // blocks finished (zeroed)
-  float* bcoef; float* bcoef2;       // [3][C]: scale, c1, c2
+  float* bcoef; float* bcoef2;       // [5][C]: scale, c1, c2, S0, S1
+  int reduced;             // the producer of dA already masked it and did the reduction (BnBwdFused): apply only, and
+                           // publish d gamma / d beta from bcoef
   float* g_gamma; float* g_beta; float* g_gamma2; float* g_beta2;   // gradient arena slots
   void* dY; void* dY2;     // outputs, storage type
   long long rows; int C;

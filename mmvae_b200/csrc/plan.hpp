@@ -45,7 +45,7 @@ struct BnT {               // one BatchNorm2d
   size_t part_cap = 0;           // P capacity
   size_t pcnt_off = 0;           // fp32 [max(P, 1024)]: rows behind each partial row (persistent kernels)
   size_t bpart_off = 0;          // fp32 backward partial sums [PB][C][3]
-  size_t bcoef_off = 0;          // fp32 [3][C]: backward coefficients (scale, c1, c2)
+  size_t bcoef_off = 0;          // fp32 [5][C]: backward coefficients (scale, c1, c2) and the sums S0, S1
   size_t acc_off = 0;            // fp64 [8 copies][2][C] forward (sum, sumsq) then [8 copies][3][C] backward (s0, s1, s2)
   size_t cnt_off = 0;            // uint32 [2]: CTA-done counters (fwd, bwd)
 };
@@ -134,7 +134,7 @@ struct Plan {
     b.part_off = bump(sizeof(float) * 2 * C * std::max<size_t>(part_rows, 1024));
     b.pcnt_off = bump(sizeof(float) * std::max<size_t>(part_rows, 1024));
     b.bpart_off = bump(sizeof(float) * 3 * C * kBwdBlocks);
-    b.bcoef_off = bump(sizeof(float) * 3 * C);
+    b.bcoef_off = bump(sizeof(float) * 5 * C);
     bns.push_back(b);
     return b.idx;
   }

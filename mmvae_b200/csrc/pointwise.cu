@@ -352,6 +352,13 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a) {
   pdl_wait();                                       // PDL: may start while the previous kernel drains
   pdl_trigger();
   const long long nvec = a.rows * a.C / VEC;
+  if (a.reduced && blockIdx.x == 0) {
+    // the reduction ran in the producer of dA (BnBwdFused): publish d beta = S0, d gamma = S1 from its sums
+    for (int c = threadIdx.x; c < a.C; c += 256) {
+      a.g_beta[c] = a.bcoef[3 * a.C + c]; a.g_gamma[c] = a.bcoef[4 * a.C + c];
+      if (a.y2) { a.g_beta2[c] = a.bcoef2[3 * a.C + c]; a.g_gamma2[c] = a.bcoef2[4 * a.C + c]; }
+    }
+  }
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < nvec; i += gridDim.x * 256LL) {
     const int c0 = (int)((i * VEC) % a.C);
     const size_t off = size_t(i) * VEC;
@@ -465,9 +472,10 @@ void launch_bn_bwd(const BnBwdArgs& a, cudaStream_t st) {
   }
   if (nblocks > 592) nblocks = 592;
   if (nblocks < 1) nblocks = 1;
-  if (vec_ok) { count_launch(); launch_pdl(bn_bwd_reduce_kernel<T, V>, nblocks, 256, 0, st, a); }
+  if (a.reduced) { /* masked and reduced by the producer of dA */ }
+  else if (vec_ok) { count_launch(); launch_pdl(bn_bwd_reduce_kernel<T, V>, nblocks, 256, 0, st, a); }
   else { count_launch(); launch_pdl(bn_bwd_reduce_kernel<T, 1>, nblocks, 256, 0, st, a); }
-  if (!a.acc) {
+  if (!a.acc && !a.reduced) {
     count_launch();
     bn_bwd_finalize_kernel<<<a.C, 128, 0, st>>>(a, nblocks, a.rows);
   }

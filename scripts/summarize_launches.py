@@ -1,6 +1,6 @@
 """Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: per-kernel totals and, with
 --seq, every launch of the LAST step in order (kernel, grid, us).  Usage:
-    python scripts/summarize_launches.py gpurun_out/launches.csv [--last N] [--seq]"""
+    python scripts/summarize_launches.py gpurun_out/launches.csv [--last N | --step K] [--seq]"""
 import csv, io, re, sys
 from collections import OrderedDict
 
@@ -18,6 +18,19 @@ for r in csv.DictReader(io.StringIO("".join(lines))):
     name = re.sub(r"\(.*$", "", r["Kernel Name"])
     name = re.sub(r"mmvae::\(anonymous namespace\)::|mmvae::", "", name)
     rows.append((name, r.get("Grid Size", ""), r.get("Block Size", ""), us))
+if "--step" in sys.argv:
+    # one training step = the launches from a pack_weights_kernel up to the next one (bench.py's roofline block, which
+    # follows the last step, starts with an L2-flush fill and is cut off); --step K picks the K-th step from the end
+    k = int(sys.argv[sys.argv.index("--step") + 1])
+    starts = [i for i, r in enumerate(rows) if "pack_weights_kernel" in r[0]]
+    b = starts[-k]
+    e = starts[-k + 1] if k > 1 else len(rows)
+    seg = rows[b:e]
+    for j, r in enumerate(seg):
+        if "FillFunctor<unsigned char>" in r[0]:
+            seg = seg[:j]
+            break
+    rows = seg
 if last:
     rows = rows[-last:]
 tot = sum(r[3] for r in rows)
