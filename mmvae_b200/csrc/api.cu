@@ -287,6 +287,7 @@ struct Exec {
     const ConvT_& s = P.convs[P.stem];
     conv_bn_fwd(s);
     apply(s, nullptr, P.a_stem, 1);
+    join();                                           // weight packing (forked by mmvae_forward) ran beside the stem
     for (const BlockT& b : P.enc) block_fwd(b);
     HeadsArgs h;
     const ActT& f = act(P.enc.back().out);
@@ -376,6 +377,8 @@ struct Exec {
   bool fused_reduce(int a) const {
     static const bool off = getenv("MMVAE_NO_BWD_FUSE") != nullptr;
     if (off || a < 0 || !special_ok()) return false;
+    // the last decoder block's output gradient comes out of the fused tail backward kernel (special.cu)
+    if (!P.dec.empty() && a == P.dec.back().out && a == P.convs[P.tail].in && use_tail(P.convs[P.tail])) return true;
     const int ci = last_dgrad_conv(a);
     const ConvT_ *c, *c2;
     if (ci < 0 || !consumer_of(a, c, c2)) return false;
@@ -395,6 +398,24 @@ struct Exec {
     return tc_supported_gconv(g1) && g1.os == 2 && g1.nvar == 4;
   }
 
+  // descriptor of the BatchNorm-backward reduction that consumes d(activation `a`) (every pixel, last contributor)
+  void fill_bwd_fused(int a, BnBwdFused& f) const {
+    const ConvT_ *bc, *bc2;
+    consumer_of(a, bc, bc2);
+    const BnT& b = P.bns[bc->bn];
+    f.a = at<T>(act(a).off);
+    f.y = at<T>(act(bc->out).off); f.stat = at<float>(b.stat_off); f.gamma = params + b.gamma;
+    f.acc = at<double>(b.acc_off) + kBnAccCopies * 2 * b.C; f.counter = at<unsigned int>(b.cnt_off) + 1;
+    f.bcoef = at<float>(b.bcoef_off);
+    if (bc2) {
+      const BnT& b2 = P.bns[bc2->bn];
+      f.y2 = at<T>(act(bc2->out).off); f.stat2 = at<float>(b2.stat_off); f.gamma2 = params + b2.gamma;
+      f.bcoef2 = at<float>(b2.bcoef_off);
+    }
+    f.C = b.C; f.var_mask = 0xF; f.finish = 1;
+    f.inv_rows = 1.0 / ((double)P.d.batch * bc->Ho * bc->Wo);
+  }
+
   void dgrad(const ConvT_& c, int accumulate) {
     GConvParams g;
     fill_dgrad(c, g);
@@ -409,21 +430,8 @@ struct Exec {
         for (int v = 0; v < g.nvar; ++v) if (g.var[v].oy0 != 0 || g.var[v].ox0 != 0) var_mask |= 1 << v;
       }
       if (var_mask) {
-        const ConvT_ *bc, *bc2;
-        consumer_of(c.in, bc, bc2);
-        const BnT& b = P.bns[bc->bn];
-        BnBwdFused& f = g.bb;
-        f.a = at<T>(act(c.in).off);
-        f.y = at<T>(act(bc->out).off); f.stat = at<float>(b.stat_off); f.gamma = params + b.gamma;
-        f.acc = at<double>(b.acc_off) + kBnAccCopies * 2 * b.C; f.counter = at<unsigned int>(b.cnt_off) + 1;
-        f.bcoef = at<float>(b.bcoef_off);
-        if (bc2) {
-          const BnT& b2 = P.bns[bc2->bn];
-          f.y2 = at<T>(act(bc2->out).off); f.stat2 = at<float>(b2.stat_off); f.gamma2 = params + b2.gamma;
-          f.bcoef2 = at<float>(b2.bcoef_off);
-        }
-        f.C = b.C; f.var_mask = var_mask; f.finish = finish;
-        f.inv_rows = 1.0 / ((double)P.d.batch * bc->Ho * bc->Wo);
+        fill_bwd_fused(c.in, g.bb);
+        g.bb.var_mask = var_mask; g.bb.finish = finish;
       }
     }
     conv_dgrad<T>(g, c, st);
@@ -496,6 +504,7 @@ struct Exec {
           TailArgs a{};
           a.in = at<__nv_bfloat16>(act(t.in).off); a.w = params + t.w; a.dy = at<__nv_bfloat16>(act(t.out).goff);
           a.dx = at<__nv_bfloat16>(act(t.in).goff); a.dw = grads + t.w; a.N = P.d.batch; a.H = t.Hi; a.W = t.Wi;
+          if (fused_reduce(t.in)) fill_bwd_fused(t.in, a.bb);
           launch_tail_bwd(a, t.Ci, st);
         } else {
           wgrad(t);
@@ -522,6 +531,7 @@ struct Exec {
       h.dfeat = at<T>(act(P.enc.back().out).goff);
       h.N = P.d.batch; h.hw = P.feat_hw; h.C = P.feat_c; h.z = P.d.z_dim;
       launch_heads_bwd<T>(h, st);
+      side([&] { launch_heads_wgrad(h.dheads, h.pooled, h.g_wmu, h.w_lv ? h.g_wlv : nullptr, h.N, h.z, h.C, st); });
       block_bwd(P.enc[3]);
       block_bwd(P.enc[2]);
       join();
@@ -656,7 +666,8 @@ int mmvae_forward(const mmvae_desc* d, const float* x, const float* params, floa
     if (!P.d.training) { E.counters = nullptr; }
     E.use_aux();
     E.clear_bn_acc();
-    E.pack_weights();
+    if (E.use_stem(P.convs[P.stem])) E.side([&] { E.pack_weights(); });   // the stem kernel does not read packed weights
+    else E.pack_weights();
     E.encode(eps, seed, offset, rng_state, eps_out, mu, logvar, encoding);
     E.decode(recon);
   }

@@ -190,6 +190,7 @@ struct StemArgs {
   float* dw;                   // wgrad: gradient arena slot (atomically accumulated; pre-zeroed)
   int N, S;
   int Ho, Wo, R, tiles_per_frame, ntiles;   // filled by the launcher
+  int qpr, pitch;                           // quads (4 output pixels) per output row; floats per row of the x tile
 };
 struct TailArgs {
   const __nv_bfloat16* in;     // [N,H,W,Ci] activation feeding the tail conv
@@ -201,6 +202,7 @@ struct TailArgs {
   const __nv_bfloat16* dy;     // backward: dY [N,H,W,1]
   __nv_bfloat16* dx;           // backward: dX [N,H,W,Ci]
   float* dw;                   // backward: gradient arena slot (atomically accumulated; pre-zeroed)
+  BnBwdFused bb;               // backward: fused BatchNorm-backward reduction of the block that produced `in`
   int N, H, W;
   int R, tiles_per_frame, ntiles;           // filled by the launcher
 };

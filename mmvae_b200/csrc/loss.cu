@@ -79,43 +79,55 @@ __global__ void __launch_bounds__(kLossThreads) loss_ce_fwd_kernel(const float* 
   if (threadIdx.x == 0) partial[blockIdx.x] = s;
 }
 
-__global__ void __launch_bounds__(256) loss_finalize_kernel(LossArgs a, const float* __restrict__ partial, int nparts,
-                                                            const float* __restrict__ mu, const float* __restrict__ lv,
-                                                            float* __restrict__ out) {
+// One CTA of 1024 threads: fp32 per-thread partials (<= 16 KL terms / <= 1 loss partial each), combined in fp64
+// by warp shuffles in a fixed order.
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+__global__ void __launch_bounds__(1024) loss_finalize_kernel(LossArgs a, const float* __restrict__ partial, int nparts,
+                                                             const float* __restrict__ mu, const float* __restrict__ lv,
+                                                             float* __restrict__ out) {
   pdl_wait();                                       // PDL: may start while the previous kernel drains
   pdl_trigger();
-  __shared__ double sh[256];
+  __shared__ double sh[2][32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double s = 0.0;
-  for (int i = threadIdx.x; i < nparts; i += 256) s += (double)partial[i];
+  for (int i = tid; i < nparts; i += 1024) s += (double)partial[i];
   double k = 0.0;
   if (mu && lv) {
     const long long nz = (long long)a.N * a.z;
-    for (long long i = threadIdx.x; i < nz; i += 256) {
-      float l = lv[i], m = mu[i];
-      k += (double)(l - expf(l) - m * m + 1.0f);
+    float kf = 0.f;
+    int cnt = 0;
+    for (long long i = tid; i < nz; i += 1024) {
+      const float l = __ldg(lv + i), m = __ldg(mu + i);
+      kf += l - expf(l) - m * m + 1.0f;
+      if (++cnt == 16) { k += (double)kf; kf = 0.f; cnt = 0; }      // bounded fp32 run length
     }
+    k += (double)kf;
   }
-  sh[threadIdx.x] = s; __syncthreads();
-  for (int d = 128; d > 0; d >>= 1) { if (threadIdx.x < d) sh[threadIdx.x] += sh[threadIdx.x + d]; __syncthreads(); }
-  s = sh[0]; __syncthreads();
-  sh[threadIdx.x] = k; __syncthreads();
-  for (int d = 128; d > 0; d >>= 1) { if (threadIdx.x < d) sh[threadIdx.x] += sh[threadIdx.x + d]; __syncthreads(); }
-  k = -0.5 * sh[0];
-  if (threadIdx.x == 0) {
-    double pxz;
-    if (nparts == 0) {
-      pxz = 0.0;
-    } else if (a.kind == 0) {
-      const double cnt = (double)a.N * a.C * a.H * a.W;
-      pxz = (double)a.nll * (s / (2.0 * (double)a.sigma * (double)a.sigma) +
-                             cnt * (log((double)a.sigma) + 0.91893853320467274178));
-    } else {
-      pxz = (double)a.nll * s;
+  s = warp_sum_d(s); k = warp_sum_d(k);
+  if (lane == 0) { sh[0][warp] = s; sh[1][warp] = k; }
+  __syncthreads();
+  if (warp == 0) {
+    s = warp_sum_d(sh[0][lane]); k = -0.5 * warp_sum_d(sh[1][lane]);
+    if (lane == 0) {
+      double pxz;
+      if (nparts == 0) {
+        pxz = 0.0;
+      } else if (a.kind == 0) {
+        const double cnt = (double)a.N * a.C * a.H * a.W;
+        pxz = (double)a.nll * (s / (2.0 * (double)a.sigma * (double)a.sigma) +
+                               cnt * (log((double)a.sigma) + 0.91893853320467274178));
+      } else {
+        pxz = (double)a.nll * s;
+      }
+      const double invn = 1.0 / (double)a.N;
+      out[0] = (float)((pxz + (double)a.kl * k) * invn);
+      out[1] = (float)(pxz * invn);
+      out[2] = (float)(k * invn);
     }
-    const double invn = 1.0 / (double)a.N;
-    out[0] = (float)((pxz + (double)a.kl * k) * invn);
-    out[1] = (float)(pxz * invn);
-    out[2] = (float)(k * invn);
   }
 }
 
@@ -241,7 +253,7 @@ void launch_loss_fwd(const LossArgs& a, const float* recon, const void* target, 
                                                         a.C, a.H * a.W, partial);
   }
   count_launch();
-  launch_pdl(loss_finalize_kernel, 1, 256, 0, st, a, partial, blocks, mu, lv, out);
+  launch_pdl(loss_finalize_kernel, 1, 1024, 0, st, a, partial, blocks, mu, lv, out);
 }
 
 void launch_loss_bwd(const LossArgs& a, const float* recon, const void* target, const float* w,

@@ -143,11 +143,15 @@ __global__ void __launch_bounds__(256) bn_apply_out_kernel(const T* __restrict__
 }
 
 // ---------------- encoder heads: avg-pool + two 1x1 convs + rsample (model.py:123-128,148-150) ----------
+// grid (N, kHeadsSplit): CTA (n, q) pools frame n and produces latent channels [q * zq, (q+1) * zq) of mu and logvar
+constexpr int kHeadsSplit = 4;
 template <typename T>
 __global__ void __launch_bounds__(128) heads_fwd_kernel(const HeadsArgs a) {
   pdl_wait();                                       // PDL: may start while the previous kernel drains
   pdl_trigger();
-  extern __shared__ float sm[];          // pooled[C] then out[2z]
+  extern __shared__ float sm[];          // pooled[C] then out[2 * zq]
+  const int zq = (a.z + kHeadsSplit - 1) / kHeadsSplit;
+  const int z0 = blockIdx.y * zq, z1 = min(a.z, z0 + zq);
   float* pooled = sm;
   float* outv = sm + a.C;
   const int n = blockIdx.x, tid = threadIdx.x;
@@ -158,13 +162,16 @@ __global__ void __launch_bounds__(128) heads_fwd_kernel(const HeadsArgs a) {
     for (int p = 0; p < a.hw; ++p) s += to_f(feat[size_t(p) * a.C + c]);
     s *= inv;
     pooled[c] = s;
-    a.pooled[size_t(n) * a.C + c] = s;
+    if (blockIdx.y == 0) a.pooled[size_t(n) * a.C + c] = s;
   }
   __syncthreads();
-  const int nout = a.w_lv ? 2 * a.z : a.z;
+  const int nz = z1 - z0;
+  const int nout = a.w_lv ? 2 * nz : nz;
   const int warp = tid >> 5, lane = tid & 31;
   for (int o = warp; o < nout; o += 4) {
-    const float* w = (o < a.z) ? a.w_mu + size_t(o) * a.C : a.w_lv + size_t(o - a.z) * a.C;
+    const bool is_lv = o >= nz;
+    const int zc = z0 + (is_lv ? o - nz : o);
+    const float* w = (is_lv ? a.w_lv : a.w_mu) + size_t(zc) * a.C;
     float s = 0.f;
     for (int c = lane; c < a.C; c += 32) s = fmaf(__ldg(w + c), pooled[c], s);
 #pragma unroll
@@ -173,12 +180,13 @@ __global__ void __launch_bounds__(128) heads_fwd_kernel(const HeadsArgs a) {
   }
   __syncthreads();
   const size_t NZ = size_t(a.N) * a.z;
-  for (int zc = tid; zc < a.z; zc += 128) {
+  for (int t = tid; t < nz; t += 128) {
+    const int zc = z0 + t;
     size_t idx = size_t(n) * a.z + zc;
-    float mu = outv[zc];
+    float mu = outv[t];
     float lv = 0.f, eps = 0.f, sd = 0.f, enc = mu;
     if (a.w_lv) {
-      lv = outv[a.z + zc];
+      lv = outv[nz + t];
       eps = a.eps ? a.eps[idx] : philox_normal_at(a.rng_dev ? a.rng_dev[0] : a.seed, a.rng_dev ? a.rng_dev[1] : a.offset, (long long)idx);
       sd = expf(0.5f * lv);
       enc = fmaf(eps, sd, mu);
@@ -439,9 +447,9 @@ void launch_bn_apply_out(const T* y, const float* coef, float* out_nchw, int N, 
 
 template <typename T>
 void launch_heads_fwd(const HeadsArgs& a, cudaStream_t st) {
-  size_t smem = sizeof(float) * (size_t(a.C) + 2 * size_t(a.z));
+  size_t smem = sizeof(float) * (size_t(a.C) + 2 * size_t((a.z + kHeadsSplit - 1) / kHeadsSplit));
   count_launch();
-  launch_pdl(heads_fwd_kernel<T>, a.N, 128, smem, st, a);
+  launch_pdl(heads_fwd_kernel<T>, dim3(a.N, kHeadsSplit), 128, smem, st, a);
 }
 
 template <typename T>
@@ -455,7 +463,7 @@ void launch_heads_bwd(const HeadsBwdArgs& a, cudaStream_t st) {
   size_t smem = sizeof(float) * 2 * size_t(a.z);
   count_launch();
   launch_pdl(heads_bwd_kernel<T>, a.N, 128, smem, st, a);
-  launch_heads_wgrad(a.dheads, a.pooled, a.g_wmu, a.w_lv ? a.g_wlv : nullptr, a.N, a.z, a.C, st);
+  // the weight gradients of the two heads are a separate launch (launch_heads_wgrad): the caller decides the stream
 }
 
 template <typename T>

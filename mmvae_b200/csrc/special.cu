@@ -1,109 +1,135 @@
 // special.cu -- the two layers that are not tensor-core work: the 1-channel stem
 // Conv2d(1 -> 32w, k5 s2 p2) (model.py:94) and the 1-channel tail Conv2d(16w -> 1, k3 s1 p1, bias)
-// (model.py:172), forward and backward, as HBM-bound SIMT kernels with shared-memory tiles.
+// (model.py:172), forward and backward, as register-blocked fp32 SIMT kernels over shared-memory tiles.
 //
-//   stem_fwd    x fp32 NCHW -> y bf16 NHWC + per-tile BatchNorm partials        (GEMM K = 25)
-//   stem_wgrad  dW[co][5][5] = sum_p x(p + tap) * dY[p][co]                     (no dgrad: x needs none)
-//   tail_fwd    a bf16 NHWC -> y bf16 [N,H,W,1] + per-tile BatchNorm partials   (GEMM N = 1: a GEMV)
-//   tail_bwd    ONE pass over (a, dY): dX[q][ci] and dW[ci][3][3] share the dY neighbourhood of q
+//   stem_fwd    x fp32 NCHW -> y bf16 NHWC + fused BatchNorm statistics          (GEMM K = 25)
+//               thread = 4 consecutive output pixels x 8 channels: a weight vector is reused by 4 pixels
+//   stem_wgrad  dW[co][5][5] = sum_p x(p + tap) * dY[p][co]                      (no dgrad: x needs none)
+//               warp = (kernel row, 8 channels), lane = pixel slice; cp.async double-buffered tiles
+//   tail_fwd    a bf16 NHWC -> y bf16 [N,H,W,1] + fused BatchNorm statistics     (GEMM N = 1: a GEMV)
+//               thread = a vertical strip of 8 pixels x 8 channels, weights in registers, sliding 3-row window
+//   tail_bwd    ONE pass over (a, dY): dX[q][ci], dW[ci][3][3], and -- the tensor dX is the gradient of the last decoder
+//               block's output -- that block's ReLU mask and BatchNorm-backward sums (BnBwdFused)
 //
-// All of them walk tiles of whole output rows of one frame; tiles are numbered so that tile i covers
-// GEMM rows [i * tile_rows, (i+1) * tile_rows), which is what bn_finalize's StatLayout expects.
+// Arithmetic stays fp32 on fp32 x / fp32 weights (the tensor cores would round x and w to bf16).
 #include "bn_fused.cuh"
 #include "kernels.cuh"
+#include "tc_common.cuh"
 
 namespace mmvae {
 
 namespace {
+
+using tc::cp_async16;
+using tc::cp_async_commit;
+using tc::cp_async_wait;
+using tc::smem_u32;
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
 __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+__device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) { float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+  f[0] = bf_lo(u.x); f[1] = bf_hi(u.x); f[2] = bf_lo(u.y); f[3] = bf_hi(u.y);
+  f[4] = bf_lo(u.z); f[5] = bf_hi(u.z); f[6] = bf_lo(u.w); f[7] = bf_hi(u.w);
+}
+__device__ __forceinline__ void cp_async8(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------
 // stem
 // ------------------------------------------------------------------------------------------------
-constexpr int kStemMaxRows = 21, kStemMaxCols = 67;     // (2R+3) x (2Wo+3) input halo tile, R*Wo <= 128, Wo <= 32
-
-__device__ __forceinline__ void stem_load_x(const StemArgs& a, int n, int oy0, float* xs, int rows, int cols, int nthreads) {
-  const float* xn = a.x + (size_t)n * a.S * a.S;
-  for (int e = threadIdx.x; e < rows * cols; e += nthreads) {
-    int r = e / cols, c = e - r * cols;
-    int iy = 2 * oy0 - 2 + r, ix = c - 2;
-    xs[e] = ((unsigned)iy < (unsigned)a.S && (unsigned)ix < (unsigned)a.S) ? __ldg(xn + (size_t)iy * a.S + ix) : 0.f;
-  }
-}
+constexpr int kStemXs = 1408;          // floats: (2R+3) rows x pitch of the x halo tile (19 x 68 or 35 x 36)
 
 template <int CO>
-__global__ void __launch_bounds__(256) stem_fwd_kernel(const StemArgs a) {
+__global__ void __launch_bounds__(256, 3) stem_fwd_kernel(const StemArgs a) {
   pdl_wait();                                       // PDL: may start while the previous kernel drains
   pdl_trigger();
-  constexpr int H = CO / 2;                          // channels per thread
-  __shared__ float xs[kStemMaxRows * kStemMaxCols];
+  constexpr int CG = CO / 8;                         // channel groups of 8
+  __shared__ __align__(16) float xs[kStemXs];
   __shared__ __align__(16) float ws[25 * CO];
+  __shared__ float wred[8][2][CO];
   const int tid = threadIdx.x, lane = tid & 31;
-  float run_s[H], run_q[H];
+  const int cg = tid % CG, quad = tid / CG;
+  const int r = quad / a.qpr, xq = quad - r * a.qpr;
+  const bool active = r < a.R;
+  float run_s[8], run_q[8];
 #pragma unroll
-  for (int j = 0; j < H; ++j) { run_s[j] = 0.f; run_q[j] = 0.f; }
+  for (int j = 0; j < 8; ++j) { run_s[j] = 0.f; run_q[j] = 0.f; }
   for (int e = tid; e < 25 * CO; e += 256) { int co = e / 25, t = e - co * 25; ws[t * CO + co] = __ldg(a.w + e); }
-  const int rows = 2 * a.R + 3, cols = 2 * a.Wo + 3;
-  const int p = tid >> 1, h = tid & 1;
-  const int oy_l = p / a.Wo, ox = p - oy_l * a.Wo;
-  const bool in_tile = p < a.R * a.Wo;
+  const int rows = 2 * a.R + 3, pitch = a.pitch;
   for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
     const int n = tile / a.tiles_per_frame, oy0 = (tile - n * a.tiles_per_frame) * a.R;
     __syncthreads();                                 // previous tile's readers are done with xs
-    stem_load_x(a, n, oy0, xs, rows, cols, 256);
+    {
+      const float* xn = a.x + (size_t)n * a.S * a.S;
+      for (int e = tid; e < rows * pitch; e += 256) {
+        const int rr = e / pitch, cc = e - rr * pitch;
+        const int iy = 2 * oy0 - 2 + rr, ix = cc - 2;
+        xs[e] = ((unsigned)iy < (unsigned)a.S && (unsigned)ix < (unsigned)a.S) ? __ldg(xn + (size_t)iy * a.S + ix) : 0.f;
+      }
+    }
     __syncthreads();
-    float acc[H];
+    if (!active) continue;
+    float acc[4][8];
 #pragma unroll
-    for (int j = 0; j < H; ++j) acc[j] = 0.f;
-    if (in_tile) {
+    for (int px = 0; px < 4; ++px)
 #pragma unroll
-      for (int kh = 0; kh < 5; ++kh) {
-        const float* xr = xs + (2 * oy_l + kh) * cols + 2 * ox;
+      for (int c = 0; c < 8; ++c) acc[px][c] = 0.f;
 #pragma unroll
-        for (int kw = 0; kw < 5; ++kw) {
-          const float xv = xr[kw];
-          const float4* wr = reinterpret_cast<const float4*>(ws + (kh * 5 + kw) * CO + h * H);
+    for (int kh = 0; kh < 5; ++kh) {
+      const float* xr = xs + (2 * r + kh) * pitch + 8 * xq;           // input column 2*ox - 2 lives at tile column 2*ox
+      float xv[12];
+      *reinterpret_cast<float4*>(xv) = *reinterpret_cast<const float4*>(xr);
+      *reinterpret_cast<float4*>(xv + 4) = *reinterpret_cast<const float4*>(xr + 4);
+      *reinterpret_cast<float4*>(xv + 8) = *reinterpret_cast<const float4*>(xr + 8);
 #pragma unroll
-          for (int j4 = 0; j4 < H / 4; ++j4) {
-            float4 w4 = wr[j4];
-            acc[4 * j4 + 0] = fmaf(xv, w4.x, acc[4 * j4 + 0]); acc[4 * j4 + 1] = fmaf(xv, w4.y, acc[4 * j4 + 1]);
-            acc[4 * j4 + 2] = fmaf(xv, w4.z, acc[4 * j4 + 2]); acc[4 * j4 + 3] = fmaf(xv, w4.w, acc[4 * j4 + 3]);
+      for (int kw = 0; kw < 5; ++kw) {
+        const float4 w0 = *reinterpret_cast<const float4*>(ws + (kh * 5 + kw) * CO + cg * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(ws + (kh * 5 + kw) * CO + cg * 8 + 4);
+#pragma unroll
+        for (int px = 0; px < 4; ++px) {
+          const float v = xv[2 * px + kw];
+          acc[px][0] = fmaf(v, w0.x, acc[px][0]); acc[px][1] = fmaf(v, w0.y, acc[px][1]);
+          acc[px][2] = fmaf(v, w0.z, acc[px][2]); acc[px][3] = fmaf(v, w0.w, acc[px][3]);
+          acc[px][4] = fmaf(v, w1.x, acc[px][4]); acc[px][5] = fmaf(v, w1.y, acc[px][5]);
+          acc[px][6] = fmaf(v, w1.z, acc[px][6]); acc[px][7] = fmaf(v, w1.w, acc[px][7]);
+        }
+      }
+    }
+    const int oy = oy0 + r;
+    if (oy < a.Ho) {
+#pragma unroll
+      for (int px = 0; px < 4; ++px) {
+        const int ox = 4 * xq + px;
+        if (ox < a.Wo) {
+          const size_t m = ((size_t)n * a.Ho + oy) * a.Wo + ox;
+          *reinterpret_cast<uint4*>(a.y + m * CO + cg * 8) =
+              make_uint4(pack2(acc[px][0], acc[px][1]), pack2(acc[px][2], acc[px][3]), pack2(acc[px][4], acc[px][5]),
+                         pack2(acc[px][6], acc[px][7]));
+          if (a.bn.acc) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {            // statistics over the values as stored
+              const float v = bf16_round(acc[px][c]);
+              run_s[c] += v; run_q[c] = fmaf(v, v, run_q[c]);
+            }
           }
         }
       }
-      const size_t m = ((size_t)n * a.Ho + oy0 + oy_l) * a.Wo + ox;
-      uint4* dst = reinterpret_cast<uint4*>(a.y + m * CO + h * H);
-#pragma unroll
-      for (int q = 0; q < H / 8; ++q)
-        dst[q] = make_uint4(pack2(acc[8 * q], acc[8 * q + 1]), pack2(acc[8 * q + 2], acc[8 * q + 3]),
-                            pack2(acc[8 * q + 4], acc[8 * q + 5]), pack2(acc[8 * q + 6], acc[8 * q + 7]));
-#pragma unroll
-      for (int j = 0; j < H; ++j) acc[j] = bf16_round(acc[j]);      // statistics over the values as stored
-    }
-    if (a.bn.acc) {
-#pragma unroll
-      for (int j = 0; j < H; ++j) { run_s[j] += acc[j]; run_q[j] = fmaf(acc[j], acc[j], run_q[j]); }
     }
   }
   if (a.bn.acc) {
-    // per-channel sums over this CTA's pixels: lanes of equal parity hold the same channel half
-    __shared__ float wred[8][2][CO];
+    // per-channel sums over this CTA's pixels: lanes with equal (lane % CG) hold the same channel group
 #pragma unroll
-    for (int j = 0; j < H; ++j) {
-      float v = run_s[j], w = run_q[j];
+    for (int c = 0; c < 8; ++c) {
+      float v = run_s[c], w = run_q[c];
 #pragma unroll
-      for (int d = 2; d < 32; d <<= 1) { v += __shfl_xor_sync(0xffffffffu, v, d); w += __shfl_xor_sync(0xffffffffu, w, d); }
-      if (lane < 2) { wred[tid >> 5][0][h * H + j] = v; wred[tid >> 5][1][h * H + j] = w; }
+      for (int d = CG; d < 32; d <<= 1) { v += __shfl_xor_sync(0xffffffffu, v, d); w += __shfl_xor_sync(0xffffffffu, w, d); }
+      if (lane < CG) { wred[tid >> 5][0][lane * 8 + c] = v; wred[tid >> 5][1][lane * 8 + c] = w; }
     }
     __syncthreads();
     if (tid < 2 * CO) {
@@ -117,239 +143,316 @@ __global__ void __launch_bounds__(256) stem_fwd_kernel(const StemArgs a) {
   }
 }
 
-// thread = (pixel slice, kernel row kh, 4 output channels): 5 x 4 accumulators kept across all tiles of the CTA
-template <int CO>
-__global__ void __launch_bounds__(320) stem_wgrad_kernel(const StemArgs a) {
+// Weight gradient of the stem: 20 warps = (kernel row kh, 8 channels), the 32 lanes of a warp are 32 pixel slices of
+// the tile; each thread keeps 5 (kw) x 8 (channels) accumulators over all tiles of the CTA.  blockIdx.y selects a block
+// of 32 output channels.  Tiles (x halo rows + the bf16 dY rows) are double-buffered with cp.async.
+constexpr int kStemWgThreads = 640;
+constexpr int kStemDyBytes = 256 * 64;               // 256 pixels x 32 channels x 2 bytes
+
+__device__ __forceinline__ void stem_wgrad_prefetch(const StemArgs& a, int tile, int co_base, int CO, float* xs, unsigned char* dys) {
+  const int n = tile / a.tiles_per_frame, oy0 = (tile - n * a.tiles_per_frame) * a.R;
+  const int rows = 2 * a.R + 3, pitch = a.pitch, tid = threadIdx.x;
+  const float* xn = a.x + (size_t)n * a.S * a.S;
+  const int halfp = a.S >> 1;                        // 8-byte pairs per input row
+  for (int e = tid; e < rows * halfp; e += kStemWgThreads) {
+    const int rr = e / halfp, j = e - rr * halfp;
+    const int iy = 2 * oy0 - 2 + rr;
+    const bool ok = (unsigned)iy < (unsigned)a.S;
+    cp_async8(smem_u32(xs + rr * pitch + 2 + 2 * j), ok ? (const void*)(xn + (size_t)iy * a.S + 2 * j) : (const void*)xn, ok ? 8u : 0u);
+  }
+  const int rv = min(a.R, a.Ho - oy0);               // valid output rows of this tile
+  const int npx = rv * a.Wo;
+  const unsigned char* src = reinterpret_cast<const unsigned char*>(a.dy + (((size_t)n * a.Ho + oy0) * a.Wo) * CO + co_base);
+  for (int e = tid; e < npx * 4; e += kStemWgThreads) {
+    const int p = e >> 2, c = e & 3;
+    cp_async16(smem_u32(dys + p * 64 + ((c ^ ((p >> 1) & 3)) << 4)), src + (size_t)p * CO * 2 + c * 16, 16u);
+  }
+}
+
+__global__ void __launch_bounds__(kStemWgThreads, 1) stem_wgrad_kernel(const StemArgs a, int CO) {
   pdl_wait();                                       // PDL: may start while the previous kernel drains
   pdl_trigger();
-  constexpr int CG = CO / 4;                         // channel groups
-  constexpr int PER = 5 * CG;                        // threads per pixel slice
-  constexpr int NSL = 320 / PER;                     // pixel slices
-  __shared__ float xs[kStemMaxRows * kStemMaxCols];
-  __shared__ __align__(16) __nv_bfloat16 dys[128 * CO];
-  __shared__ float red[NSL][25 * CO];
-  const int tid = threadIdx.x;
-  const int sl = tid / PER, rem = tid - sl * PER, kh = rem / CG, cg = rem - kh * CG;
-  const bool active = sl < NSL;
-  const int rows = 2 * a.R + 3, cols = 2 * a.Wo + 3, npx = a.R * a.Wo;
-  float acc[5][4];
+  __shared__ __align__(16) float xs[2][kStemXs];
+  __shared__ __align__(16) unsigned char dys[2][kStemDyBytes];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int kh = warp >> 2, cg = warp & 3;
+  const int co_base = blockIdx.y * 32;
+  const int pitch = a.pitch;
+  for (int e = tid; e < 2 * kStemXs; e += kStemWgThreads) (&xs[0][0])[e] = 0.f;      // halo columns stay zero
+  __syncthreads();
+  float acc[5][8];
 #pragma unroll
   for (int i = 0; i < 5; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+    for (int c = 0; c < 8; ++c) acc[i][c] = 0.f;
+  int buf = 0;
+  if ((int)blockIdx.x < a.ntiles) stem_wgrad_prefetch(a, blockIdx.x, co_base, CO, xs[0], dys[0]);
+  cp_async_commit();
+  for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, buf ^= 1) {
+    const int next = tile + gridDim.x;
+    if (next < a.ntiles) stem_wgrad_prefetch(a, next, co_base, CO, xs[buf ^ 1], dys[buf ^ 1]);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
     const int n = tile / a.tiles_per_frame, oy0 = (tile - n * a.tiles_per_frame) * a.R;
-    __syncthreads();
-    stem_load_x(a, n, oy0, xs, rows, cols, 320);
-    const uint4* src = reinterpret_cast<const uint4*>(a.dy + ((size_t)n * a.Ho + oy0) * a.Wo * CO);
-    for (int e = tid; e < npx * CO / 8; e += 320) reinterpret_cast<uint4*>(dys)[e] = __ldg(src + e);
-    __syncthreads();
-    if (active) {
-      for (int p = sl; p < npx; p += NSL) {
-        const int oy_l = p / a.Wo, ox = p - oy_l * a.Wo;
-        const uint2 g2 = *reinterpret_cast<const uint2*>(dys + p * CO + cg * 4);
-        const float2 g01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&g2.x));
-        const float2 g23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&g2.y));
-        const float* xr = xs + (2 * oy_l + kh) * cols + 2 * ox;
+    const int npx = min(a.R, a.Ho - oy0) * a.Wo;
+    const float* xb = xs[buf];
+    const unsigned char* db = dys[buf];
+#pragma unroll 2
+    for (int p = lane; p < npx; p += 32) {
+      const int oy_l = p / a.Wo, ox = p - oy_l * a.Wo;
+      float g[8];
+      unpack8(*reinterpret_cast<const uint4*>(db + p * 64 + ((cg ^ ((p >> 1) & 3)) << 4)), g);
+      const float* xr = xb + (2 * oy_l + kh) * pitch + 2 * ox;
+      const float2 x01 = *reinterpret_cast<const float2*>(xr), x23 = *reinterpret_cast<const float2*>(xr + 2);
+      const float xv[5] = {x01.x, x01.y, x23.x, x23.y, xr[4]};
 #pragma unroll
-        for (int kw = 0; kw < 5; ++kw) {
-          const float xv = xr[kw];
-          acc[kw][0] = fmaf(xv, g01.x, acc[kw][0]); acc[kw][1] = fmaf(xv, g01.y, acc[kw][1]);
-          acc[kw][2] = fmaf(xv, g23.x, acc[kw][2]); acc[kw][3] = fmaf(xv, g23.y, acc[kw][3]);
-        }
-      }
+      for (int kw = 0; kw < 5; ++kw)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[kw][c] = fmaf(xv[kw], g[c], acc[kw][c]);
     }
+    __syncthreads();                                 // everyone is done with this buffer before it is refilled
   }
-  __syncthreads();
-  if (active) {
+  cp_async_wait<0>();
 #pragma unroll
-    for (int kw = 0; kw < 5; ++kw)
+  for (int kw = 0; kw < 5; ++kw)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) red[sl][(kh * 5 + kw) * CO + cg * 4 + j] = acc[kw][j];
-  }
-  __syncthreads();
-  for (int e = tid; e < 25 * CO; e += 320) {
-    float s = 0.f;
+    for (int c = 0; c < 8; ++c) {
+      float v = acc[kw][c];
 #pragma unroll
-    for (int q = 0; q < NSL; ++q) s += red[q][e];
-    const int tap = e / CO, co = e - tap * CO;
-    atomicAdd(a.dw + co * 25 + tap, s);
-  }
+      for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+      if (lane == 0) atomicAdd(a.dw + (size_t)(co_base + cg * 8 + c) * 25 + kh * 5 + kw, v);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
 // tail
 // ------------------------------------------------------------------------------------------------
-constexpr int kTailThreads = 512;
-
-__device__ __forceinline__ float block_sum512(float v, float* sh) {
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  __syncthreads();
-  if (lane == 0) sh[warp] = v;
-  __syncthreads();
-  float r = 0.f;
-#pragma unroll
-  for (int w = 0; w < kTailThreads / 32; ++w) r += sh[w];
-  return r;
+// Forward.  Thread = (image column x, group g of 8 input channels) of one band of 8 output rows; the G = CI/8 lanes of
+// a pixel are adjacent, so a quarter warp reads 128 contiguous bytes of the tile.  The thread walks the band's 10 input
+// rows once (3 x 16-byte loads per row, converted once) and keeps its 9 x 8 weights in registers.
+template <int CI>
+__device__ __forceinline__ void tail_prefetch(const TailArgs& a, int tile, unsigned char* dst, int nthreads) {
+  constexpr int G = CI / 8;
+  const int n = tile / a.tiles_per_frame, oy0 = (tile - n * a.tiles_per_frame) * a.R;
+  const int W2 = a.W + 2;
+  const uint4* in = reinterpret_cast<const uint4*>(a.in);
+  for (int e = threadIdx.x; e < (a.R + 2) * W2 * G; e += nthreads) {
+    const int pix = e / G, c = e - pix * G;
+    const int rr = pix / W2, cc = pix - rr * W2;
+    const int iy = oy0 - 1 + rr, ix = cc - 1;
+    const bool ok = (unsigned)iy < (unsigned)a.H && (unsigned)ix < (unsigned)a.W;
+    cp_async16(smem_u32(dst + (size_t)e * 16), ok ? (const void*)(in + (((size_t)n * a.H + iy) * a.W + ix) * G + c) : (const void*)in,
+               ok ? 16u : 0u);
+  }
 }
 
-// thread = (pixel, group of 8 input channels); the CI/8 lanes of a pixel are adjacent
 template <int CI>
-__global__ void __launch_bounds__(kTailThreads) tail_fwd_kernel(const TailArgs a) {
+__global__ void __launch_bounds__(256, 2) tail_fwd_kernel(const TailArgs a) {
   pdl_wait();                                       // PDL: may start while the previous kernel drains
   pdl_trigger();
   constexpr int G = CI / 8;
-  constexpr int PX = kTailThreads / G;               // pixels per tile
-  extern __shared__ __align__(16) unsigned char tail_smem[];
-  uint4* tile = reinterpret_cast<uint4*>(tail_smem);                 // [(R+2)][(W+2)][G] 16-byte chunks
-  __shared__ float ws[9 * CI];
-  __shared__ float sh[kTailThreads / 32];
-  const int tid = threadIdx.x;
-  for (int e = tid; e < 9 * CI; e += kTailThreads) { int ci = e / 9, t = e - ci * 9; ws[t * CI + ci] = __ldg(a.w + e); }
-  const float bias = a.bias ? __ldg(a.bias) : 0.f;
+  extern __shared__ __align__(16) unsigned char tail_smem[];         // 2 x [(R+2)][(W+2)][G] 16-byte chunks
+  __shared__ float sh[2][8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int W2 = a.W + 2;
-  const int p = tid / G, grp = tid - p * G;
-  const int oy_l = p / a.W, ox = p - oy_l * a.W;
-  const uint4* in = reinterpret_cast<const uint4*>(a.in);
+  const size_t tile_bytes = (size_t)(a.R + 2) * W2 * G * 16;
+  const int g = tid % G, x = (tid / G) % a.W, band = tid / (G * a.W);
+  float wreg[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) wreg[t][c] = __ldg(a.w + (size_t)(g * 8 + c) * 9 + t);
+  const float bias = a.bias ? __ldg(a.bias) : 0.f;
   float run_s = 0.f, run_q = 0.f;
-  for (int t_i = blockIdx.x; t_i < a.ntiles; t_i += gridDim.x) {
+  int buf = 0;
+  if ((int)blockIdx.x < a.ntiles) tail_prefetch<CI>(a, blockIdx.x, tail_smem, 256);
+  cp_async_commit();
+  for (int t_i = blockIdx.x; t_i < a.ntiles; t_i += gridDim.x, buf ^= 1) {
+    const int next = t_i + gridDim.x;
+    if (next < a.ntiles) tail_prefetch<CI>(a, next, tail_smem + (buf ^ 1) * tile_bytes, 256);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
     const int n = t_i / a.tiles_per_frame, oy0 = (t_i - n * a.tiles_per_frame) * a.R;
-    __syncthreads();
-    for (int e = tid; e < (a.R + 2) * W2 * G; e += kTailThreads) {
-      int pix = e / G, c = e - pix * G;
-      int r = pix / W2, cc = pix - r * W2;
-      int iy = oy0 - 1 + r, ix = cc - 1;
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if ((unsigned)iy < (unsigned)a.H && (unsigned)ix < (unsigned)a.W) v = __ldg(in + (((size_t)n * a.H + iy) * a.W + ix) * G + c);
-      tile[e] = v;
-    }
-    __syncthreads();
-    float acc = 0.f;
+    const uint4* tile = reinterpret_cast<const uint4*>(tail_smem + buf * tile_bytes);
+    float acc[8];
 #pragma unroll
-    for (int kh = 0; kh < 3; ++kh)
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
 #pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        float f[8];
-        unpack8(tile[((oy_l + kh) * W2 + ox + kw) * G + grp], f);
-        const float* wr = ws + (kh * 3 + kw) * CI + grp * 8;
+    for (int rr = 0; rr < 10; ++rr) {                // input row y0 - 1 + rr feeds output rows rr - kh
+      const uint4* row = tile + ((size_t)(band * 8 + rr) * W2 + x) * G + g;
+      float v[3][8];
+      unpack8(row[0], v[0]); unpack8(row[G], v[1]); unpack8(row[2 * G], v[2]);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc = fmaf(f[i], wr[i], acc);
+      for (int kh = 0; kh < 3; ++kh) {
+        const int o = rr - kh;
+        if (o >= 0 && o < 8) {
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[o] = fmaf(v[kw][c], wreg[kh * 3 + kw][c], acc[o]);
+        }
       }
+    }
 #pragma unroll
-    for (int d = 1; d < G; d <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
-    acc += bias;
-    const size_t m = ((size_t)n * a.H + oy0 + oy_l) * a.W + ox;
-    const __nv_bfloat16 o = __float2bfloat16_rn(acc);
-    if (grp == 0) a.y[m] = o;
-    if (a.bn.acc && grp == 0) { const float v = __bfloat162float(o); run_s += v; run_q = fmaf(v, v, run_q); }
+    for (int o = 0; o < 8; ++o) {
+#pragma unroll
+      for (int d = 1; d < G; d <<= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], d);
+      const int oy = oy0 + band * 8 + o;
+      if (g == 0 && oy < a.H) {
+        const __nv_bfloat16 ob = __float2bfloat16_rn(acc[o] + bias);
+        a.y[((size_t)n * a.H + oy) * a.W + x] = ob;
+        const float v = __bfloat162float(ob);
+        run_s += v; run_q = fmaf(v, v, run_q);
+      }
+    }
+    __syncthreads();                                 // everyone is done with this buffer before it is refilled
   }
+  cp_async_wait<0>();
   if (a.bn.acc) {
-    const float s = block_sum512(run_s, sh);
-    const float q = block_sum512(run_q, sh);
-    if (tid == 0) { atomicAdd(bn_acc_copy(a.bn), (double)s); atomicAdd(bn_acc_copy(a.bn) + 1, (double)q); }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { run_s += __shfl_xor_sync(0xffffffffu, run_s, d); run_q += __shfl_xor_sync(0xffffffffu, run_q, d); }
+    if (lane == 0) { sh[0][warp] = run_s; sh[1][warp] = run_q; }
+    __syncthreads();
+    if (tid < 2) {
+      float t = 0.f;
+#pragma unroll
+      for (int w8 = 0; w8 < 8; ++w8) t += sh[tid][w8];
+      atomicAdd(bn_acc_copy(a.bn) + tid, (double)t);
+    }
     bn_fused_finish(a.bn, gridDim.x);
   }
 }
 
-// One pass over the tail conv's input activation a and its output gradient dY:
+// Backward: one pass over the tail conv's input activation a and its output gradient dY.
 //   dX[q][ci]      = sum_t dY[q + (1-kh, 1-kw)] * w[ci][t]
 //   dW[ci][t]     += a[q][ci] * dY[q + (1-kh, 1-kw)]
+// and, when bb.acc is set (dX is the gradient of the last decoder block's output a = relu(bn2(y) + bn_s(y2))):
+//   g = bf16(dX) * [a > 0] is what gets stored;  S0 = sum g, S1 = sum g * xhat(y), S2 = sum g * xhat(y2) per channel.
+// Thread = (image column x, chunk of 4 channels) of a band of 8 rows; the CI/4 lanes of a pixel are adjacent, so a warp
+// reads / writes 256 contiguous bytes of every NHWC tensor.  Weights (4 x 9) and dW accumulators (4 x 9) in registers.
 template <int CI>
-__global__ void __launch_bounds__(kTailThreads) tail_bwd_kernel(const TailArgs a) {
+__global__ void __launch_bounds__(256, 2) tail_bwd_kernel(const TailArgs a) {
   pdl_wait();                                       // PDL: may start while the previous kernel drains
   pdl_trigger();
-  constexpr int G = CI / 8;
+  constexpr int CH = CI / 4;                         // 4-channel chunks per pixel
+  constexpr int NACC = 36 + 12;                      // dW accumulators + (S0, S1', S2') x 4 channels
   extern __shared__ __align__(16) unsigned char tail_smem[];
   float* gs = reinterpret_cast<float*>(tail_smem);                   // [(R+2)][(W+2)] dY with zero halo
-  float* red = gs + (a.R + 2) * (a.W + 2);                           // [16 warps][G][72]
-  __shared__ float ws[9 * CI];
+  float* red = gs + (a.R + 2) * (a.W + 2);                           // [8 warps][CH][NACC]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int e = tid; e < 9 * CI; e += kTailThreads) ws[e] = __ldg(a.w + e);        // [ci][t]
   const int W2 = a.W + 2;
-  const int p = tid / G, grp = tid - p * G;
-  const int oy_l = p / a.W, ox = p - oy_l * a.W;
-  const uint4* in = reinterpret_cast<const uint4*>(a.in);
-  uint4* dx = reinterpret_cast<uint4*>(a.dx);
-  float accw[72];                                    // [8 channels][9 taps]
+  const int ch = tid % CH, x = (tid / CH) % a.W, band = tid / (CH * a.W);
+  const bool fuse = a.bb.acc != nullptr;
+  const bool two = fuse && a.bb.y2 != nullptr;
+  float wreg[4][9], accw[4][9], sb[12];
 #pragma unroll
-  for (int i = 0; i < 72; ++i) accw[i] = 0.f;
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) { wreg[c][t] = __ldg(a.w + (size_t)(ch * 4 + c) * 9 + t); accw[c][t] = 0.f; }
+#pragma unroll
+  for (int i = 0; i < 12; ++i) sb[i] = 0.f;
+  const uint2* in = reinterpret_cast<const uint2*>(a.in);
+  const uint2* y1 = reinterpret_cast<const uint2*>(a.bb.y);
+  const uint2* y2 = reinterpret_cast<const uint2*>(a.bb.y2);
+  uint2* dx = reinterpret_cast<uint2*>(a.dx);
   for (int t_i = blockIdx.x; t_i < a.ntiles; t_i += gridDim.x) {
     const int n = t_i / a.tiles_per_frame, oy0 = (t_i - n * a.tiles_per_frame) * a.R;
     __syncthreads();
-    for (int e = tid; e < (a.R + 2) * W2; e += kTailThreads) {
-      int r = e / W2, cc = e - r * W2;
-      int iy = oy0 - 1 + r, ix = cc - 1;
+    for (int e = tid; e < (a.R + 2) * W2; e += 256) {
+      const int rr = e / W2, cc = e - rr * W2;
+      const int iy = oy0 - 1 + rr, ix = cc - 1;
       gs[e] = ((unsigned)iy < (unsigned)a.H && (unsigned)ix < (unsigned)a.W)
                   ? __bfloat162float(a.dy[((size_t)n * a.H + iy) * a.W + ix]) : 0.f;
     }
     __syncthreads();
-    const size_t q = (((size_t)n * a.H + oy0 + oy_l) * a.W + ox) * G + grp;
-    float f[8];
-    unpack8(__ldg(in + q), f);
-    float g[9];
+    const int r0 = band * 8;
+    float gw[3][3];                                  // dY window rows o-1, o, o+1 (tile rows r0+o .. r0+o+2), columns x-1 .. x+1
 #pragma unroll
-    for (int kh = 0; kh < 3; ++kh)
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
-      for (int kw = 0; kw < 3; ++kw) g[kh * 3 + kw] = gs[(oy_l + 2 - kh) * W2 + ox + 2 - kw];
-    float o[8];
+      for (int j = 0; j < 3; ++j) gw[i + 1][j] = gs[(r0 + i) * W2 + x + j];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const float* wr = ws + (grp * 8 + c) * 9;
-      float s = 0.f;
+    for (int half = 0; half < 2; ++half) {
+      // the global loads of four rows first (independent: 4 x 3 requests in flight per thread)
+      uint2 av[4], y1v[4], y2v[4];
 #pragma unroll
-      for (int t = 0; t < 9; ++t) { s = fmaf(g[t], wr[t], s); accw[c * 9 + t] = fmaf(f[c], g[t], accw[c * 9 + t]); }
-      o[c] = s;
+      for (int o = 0; o < 4; ++o) {
+        const int oy = oy0 + r0 + half * 4 + o;
+        const size_t q = (((size_t)n * a.H + min(oy, a.H - 1)) * a.W + x) * CH + ch;
+        av[o] = __ldg(in + q);
+        y1v[o] = fuse ? __ldg(y1 + q) : make_uint2(0u, 0u);
+        y2v[o] = two ? __ldg(y2 + q) : make_uint2(0u, 0u);
+      }
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        const int ro = half * 4 + o;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { gw[0][j] = gw[1][j]; gw[1][j] = gw[2][j]; gw[2][j] = gs[(r0 + ro + 2) * W2 + x + j]; }
+        const int oy = oy0 + r0 + ro;
+        if (oy >= a.H) continue;
+        const float af[4] = {bf_lo(av[o].x), bf_hi(av[o].x), bf_lo(av[o].y), bf_hi(av[o].y)};
+        float o4[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float sacc = 0.f;
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+              const float gv = gw[2 - kh][2 - kw];     // dY[q + (1-kh, 1-kw)]
+              sacc = fmaf(gv, wreg[c][kh * 3 + kw], sacc);
+              accw[c][kh * 3 + kw] = fmaf(af[c], gv, accw[c][kh * 3 + kw]);
+            }
+          o4[c] = sacc;
+        }
+        if (fuse) {
+          const float yf[4] = {bf_lo(y1v[o].x), bf_hi(y1v[o].x), bf_lo(y1v[o].y), bf_hi(y1v[o].y)};
+          const float zf[4] = {bf_lo(y2v[o].x), bf_hi(y2v[o].x), bf_lo(y2v[o].y), bf_hi(y2v[o].y)};
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float gm = af[c] > 0.f ? bf16_round(o4[c]) : 0.f;
+            o4[c] = gm;
+            sb[c] += gm; sb[4 + c] = fmaf(gm, yf[c], sb[4 + c]); sb[8 + c] = fmaf(gm, zf[c], sb[8 + c]);
+          }
+        }
+        const size_t q = (((size_t)n * a.H + oy) * a.W + x) * CH + ch;
+        dx[q] = make_uint2(pack2(o4[0], o4[1]), pack2(o4[2], o4[3]));
+      }
     }
-    dx[q] = make_uint4(pack2(o[0], o[1]), pack2(o[2], o[3]), pack2(o[4], o[5]), pack2(o[6], o[7]));
   }
-  // reduce the 72 accumulators over the pixels of the warp (lanes of equal grp), halving the live set per step
-  constexpr int LB = G == 1 ? 0 : (G == 2 ? 1 : 2);  // lane bits that index grp
-  int base = 0;
-  {
-    const bool hi = lane & 16;
+  // reduce the per-thread accumulators over the lanes with the same channel chunk, then over the warps
+  __syncthreads();
 #pragma unroll
-    for (int i = 0; i < 36; ++i) {
-      float send = hi ? accw[i] : accw[i + 36], keep = hi ? accw[i + 36] : accw[i];
-      accw[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-    base += hi ? 36 : 0;
-  }
-  {
-    const bool hi = lane & 8;
+  for (int i = 0; i < NACC; ++i) {
+    float v = i < 36 ? accw[i / 9][i % 9] : sb[i - 36];
 #pragma unroll
-    for (int i = 0; i < 18; ++i) {
-      float send = hi ? accw[i] : accw[i + 18], keep = hi ? accw[i + 18] : accw[i];
-      accw[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
-    base += hi ? 18 : 0;
-  }
-  {
-    const bool hi = lane & 4;
-#pragma unroll
-    for (int i = 0; i < 9; ++i) {
-      float send = hi ? accw[i] : accw[i + 9], keep = hi ? accw[i + 9] : accw[i];
-      accw[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    }
-    base += hi ? 9 : 0;
-  }
-#pragma unroll
-  for (int d = 2; d >= (1 << LB); d >>= 1) {
-#pragma unroll
-    for (int i = 0; i < 9; ++i) accw[i] += __shfl_xor_sync(0xffffffffu, accw[i], d);
+    for (int d = CH; d < 32; d <<= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if (lane < CH) red[(warp * CH + lane) * NACC + i] = v;
   }
   __syncthreads();
-  if ((lane & 3 & ~((1 << LB) - 1)) == 0) {          // one lane per (grp, base) inside the warp
-#pragma unroll
-    for (int i = 0; i < 9; ++i) red[(warp * G + grp) * 72 + base + i] = accw[i];
-  }
-  __syncthreads();
-  for (int e = tid; e < G * 72; e += kTailThreads) {
+  for (int e = tid; e < CH * NACC; e += 256) {
+    const int c4 = e / NACC, i = e - c4 * NACC;
     float s = 0.f;
 #pragma unroll
-    for (int w = 0; w < kTailThreads / 32; ++w) s += red[w * G * 72 + e];
-    atomicAdd(a.dw + e, s);                          // e = (grp*8 + c)*9 + t == weight index [0][ci][kh][kw]
+    for (int w8 = 0; w8 < 8; ++w8) s += red[(w8 * CH + c4) * NACC + i];
+    red[e] = s;                                      // warp 0's slot now holds the CTA total (read and written by this thread only)
+    if (i < 36) atomicAdd(a.dw + (size_t)(c4 * 4 + i / 9) * 9 + i % 9, s);      // weight index [0][ci][kh][kw]
+  }
+  if (fuse) {
+    __syncthreads();
+    if (tid < CI) {
+      // S1 = rstd * (sum g*y - mean * S0): the subtraction in fp64 on the CTA totals
+      const int c4 = tid >> 2, c = tid & 3;
+      const double s0 = (double)red[c4 * NACC + 36 + c];
+      const double s1 = (double)red[c4 * NACC + 40 + c], s2 = (double)red[c4 * NACC + 44 + c];
+      double* acc = bn_bwd_acc_copy(a.bb) + tid;
+      atomicAdd(acc, s0);
+      atomicAdd(acc + a.bb.C, (double)a.bb.stat[a.bb.C + tid] * (s1 - (double)a.bb.stat[tid] * s0));
+      if (two) atomicAdd(acc + 2 * a.bb.C, (double)a.bb.stat2[a.bb.C + tid] * (s2 - (double)a.bb.stat2[tid] * s0));
+    }
+    bn_bwd_fused_finish(a.bb, gridDim.x);
   }
 }
 
@@ -391,30 +494,26 @@ __global__ void __launch_bounds__(256) heads_wgrad2_kernel(const float* __restri
 
 }  // namespace
 
-// R = the largest divisor of Ho with R * Wo <= cap pixels
-static int rows_per_tile(int Ho, int Wo, int cap) {
-  int best = 0;
-  for (int r = 1; r <= Ho; ++r)
-    if (Ho % r == 0 && r * Wo <= cap) best = r;
-  return best;
-}
-
+// ---------------- host: tile geometry ----------------
 bool stem_supported(int Cin, int Co, int S, int k, int s, int p) {
   if (Cin != 1 || k != 5 || s != 2 || p != 2 || (Co != 32 && Co != 64) || (S & 1)) return false;
-  const int Ho = S / 2;
-  if (Ho > 32) return false;
-  return rows_per_tile(Ho, Ho, 128) > 0;
+  const int Wo = S / 2;
+  return Wo >= 4 && Wo <= 32;
 }
 
-static void stem_fill(StemArgs& a) {
+static void stem_fill(StemArgs& a, int quads_per_tile) {
   a.Ho = a.S / 2; a.Wo = a.S / 2;
-  a.R = rows_per_tile(a.Ho, a.Wo, 128);
-  a.tiles_per_frame = a.Ho / a.R;
+  a.qpr = (a.Wo + 3) / 4;
+  a.R = quads_per_tile / a.qpr;
+  if (a.R > a.Ho) a.R = a.Ho;
+  if (a.R * a.Wo > 256) a.R = 256 / a.Wo;            // the weight-gradient kernel stages at most 256 pixels of dY
+  a.tiles_per_frame = (a.Ho + a.R - 1) / a.R;
   a.ntiles = a.N * a.tiles_per_frame;
+  a.pitch = (8 * a.qpr + 4 + 3) & ~3;               // columns -2 .. 2*4*qpr + 1 of the input, rounded to 16 bytes
 }
 
 StatLayout launch_stem_fwd(StemArgs a, int Co, cudaStream_t st) {
-  stem_fill(a);
+  stem_fill(a, 256 / (Co / 8));
   const int grid = min(a.ntiles, 148 * 3);
   count_launch();
   if (Co == 32) launch_pdl(stem_fwd_kernel<32>, grid, 256, 0, st, a);
@@ -423,43 +522,50 @@ StatLayout launch_stem_fwd(StemArgs a, int Co, cudaStream_t st) {
 }
 
 void launch_stem_wgrad(StemArgs a, int Co, cudaStream_t st) {
-  stem_fill(a);
-  const int grid = min(a.ntiles, 2 * 148);
+  stem_fill(a, 64);
+  const int ny = Co / 32;
+  dim3 grid(min(a.ntiles, 148 / ny), ny);
   count_launch();
-  if (Co == 32) launch_pdl(stem_wgrad_kernel<32>, grid, 320, 0, st, a);
-  else launch_pdl(stem_wgrad_kernel<64>, grid, 320, 0, st, a);
+  launch_pdl(stem_wgrad_kernel, grid, kStemWgThreads, 0, st, a, Co);
 }
 
 bool tail_supported(int Ci, int Co, int H, int k, int s, int p) {
   if (Co != 1 || k != 3 || s != 1 || p != 1 || (Ci != 16 && Ci != 32)) return false;
-  const int px = kTailThreads / (Ci / 8);
-  const int R = rows_per_tile(H, H, px);
-  return R > 0 && R * H == px;                       // every thread owns exactly one (pixel, channel group)
+  // one band = 8 rows x W columns x (Ci/8 forward, Ci/4 backward) threads must fit 256 threads
+  return H % 8 == 0 && H * (Ci / 4) <= 256 && (256 % (H * (Ci / 4))) == 0;
 }
 
-static void tail_fill(TailArgs& a, int Ci) {
-  a.R = rows_per_tile(a.H, a.W, kTailThreads / (Ci / 8));
-  a.tiles_per_frame = a.H / a.R;
+static void tail_fill(TailArgs& a, int threads_per_pixel) {
+  const int bands = 256 / (a.W * threads_per_pixel);
+  a.R = 8 * bands;
+  if (a.R > a.H) a.R = a.H;
+  a.tiles_per_frame = (a.H + a.R - 1) / a.R;
   a.ntiles = a.N * a.tiles_per_frame;
 }
 
 StatLayout launch_tail_fwd(TailArgs a, int Ci, cudaStream_t st) {
-  tail_fill(a, Ci);
-  const int grid = min(a.ntiles, 148 * 3);
-  const size_t smem = (size_t)(a.R + 2) * (a.W + 2) * Ci * 2;
+  tail_fill(a, Ci / 8);
+  const int grid = min(a.ntiles, 148 * 2);
+  const size_t smem = 2 * (size_t)(a.R + 2) * (a.W + 2) * Ci * 2;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(tail_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(tail_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    attr_done = true;
+  }
   count_launch();
-  if (Ci == 16) launch_pdl(tail_fwd_kernel<16>, grid, kTailThreads, smem, st, a);
-  else launch_pdl(tail_fwd_kernel<32>, grid, kTailThreads, smem, st, a);
+  if (Ci == 16) launch_pdl(tail_fwd_kernel<16>, grid, 256, smem, st, a);
+  else launch_pdl(tail_fwd_kernel<32>, grid, 256, smem, st, a);
   return StatLayout{0, 0, 0, 0};     // statistics are finalised inside the kernel (a.bn)
 }
 
 void launch_tail_bwd(TailArgs a, int Ci, cudaStream_t st) {
-  tail_fill(a, Ci);
-  const int grid = min(a.ntiles, 148);
-  const size_t smem = sizeof(float) * ((size_t)(a.R + 2) * (a.W + 2) + (size_t)(kTailThreads / 32) * (Ci / 8) * 72);
+  tail_fill(a, Ci / 4);
+  const int grid = min(a.ntiles, 148 * 2);
+  const size_t smem = sizeof(float) * ((size_t)(a.R + 2) * (a.W + 2) + (size_t)8 * (Ci / 4) * 48);
   count_launch();
-  if (Ci == 16) launch_pdl(tail_bwd_kernel<16>, grid, kTailThreads, smem, st, a);
-  else launch_pdl(tail_bwd_kernel<32>, grid, kTailThreads, smem, st, a);
+  if (Ci == 16) launch_pdl(tail_bwd_kernel<16>, grid, 256, smem, st, a);
+  else launch_pdl(tail_bwd_kernel<32>, grid, 256, smem, st, a);
 }
 
 void launch_heads_wgrad(const float* dheads, const float* pooled, float* g_mu, float* g_lv, int N, int z, int C,
