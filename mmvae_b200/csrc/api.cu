@@ -101,6 +101,7 @@ static void geom_build(const ConvT_& c, int dir, int N, GConvParams& g) {
     while (geom_tap(cg, dir, v, gv.ntaps, dy, dx, wofs)) add_tap(gv, dy, dx, wofs);
   }
   g.M = N * g.Hg * g.Wg;
+  if (c.kind == CONVT && c.k == 4 && c.s == 2 && c.p == 1) g.conv_class = dir == DIR_FPROP ? 1 : 2;
   if (c.wp_chunks[dir] > 0) {
     g.co_pad = (op_co + 15) & ~15;
     g.wpack_var_stride = c.wp_chunks[dir] * g.co_pad * 128;
@@ -330,7 +331,7 @@ struct Exec {
     w.dw = grads + c.w;
     w.N = g.N; w.Hi = g.Hi; w.Wi = g.Wi; w.Ci = g.Ci; w.Ho = g.Ho; w.Wo = g.Wo; w.Co = g.Co;
     w.Hg = g.Hg; w.Wg = g.Wg; w.M = g.M; w.os = g.os; w.is = g.is; w.w_sci = g.w_sci; w.w_sco = g.w_sco;
-    w.nvar = g.nvar;
+    w.nvar = g.nvar; w.conv_class = g.conv_class;
     for (int i = 0; i < g.nvar; ++i) w.var[i] = g.var[i];
     conv_wgrad<T>(w, c, !(P.d.flags & MMVAE_FLAG_FORCE_SIMT), st);
   }
@@ -939,7 +940,7 @@ int mmvae_selftest_tc(const mmvae_desc* d, const float* params, void* workspace,
       w.in = E.at<T>(ai.off); w.dout = E.at<T>(ao.goff);
       w.N = gg.N; w.Hi = gg.Hi; w.Wi = gg.Wi; w.Ci = gg.Ci; w.Ho = gg.Ho; w.Wo = gg.Wo; w.Co = gg.Co;
       w.Hg = gg.Hg; w.Wg = gg.Wg; w.M = gg.M; w.os = gg.os; w.is = gg.is; w.w_sci = gg.w_sci; w.w_sco = gg.w_sco;
-      w.nvar = gg.nvar;
+      w.nvar = gg.nvar; w.conv_class = gg.conv_class;
       for (int i = 0; i < gg.nvar; ++i) w.var[i] = gg.var[i];
       w.dw = grads_a + c.w; launch_wgrad_simt<T>(w, st);
       w.dw = grads_b + c.w; launch_wgrad_tc(w, st);

@@ -36,52 +36,6 @@ constexpr int kStageA = 128 * 128;      // bytes: 128 rows x 64 bf16 (fprop) or 
 constexpr int kMaxStages = 12;
 constexpr int kTabCap = 320;            // TMA coordinate table entries (variants x k-chunks x sub-tiles)
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
-
-// Sum over the 32 rows held by the lanes of a warp of 16 per-thread column values: a transposing
-// butterfly (16 shuffles).  Returns the column this lane ends up owning; its sum is in v[0]
-// (lanes 2c and 2c+1 hold the same column).
-__device__ __forceinline__ int warp_colsum16(float (&v)[16], int lane) {
-  {
-    const bool hi = lane & 16;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float send = hi ? v[i] : v[i + 8];
-      float keep = hi ? v[i + 8] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-  }
-  {
-    const bool hi = lane & 8;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float send = hi ? v[i] : v[i + 4];
-      float keep = hi ? v[i + 4] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
-  }
-  {
-    const bool hi = lane & 4;
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      float send = hi ? v[i] : v[i + 2];
-      float keep = hi ? v[i + 2] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    }
-  }
-  {
-    const bool hi = lane & 2;
-    float send = hi ? v[0] : v[1];
-    float keep = hi ? v[1] : v[0];
-    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-  }
-  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
-  return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-}
-
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -862,6 +816,7 @@ bool tc_supported_wgrad(const WGradParams& p) {
 StatLayout launch_gconv_tc(const GConvParams& p0, cudaStream_t st) {
   StatLayout sl{0, 0, 0, 0};
   if (p0.M <= 0) return sl;
+  if (slab_supported_gconv(p0)) { launch_slab_gconv(p0, st); return sl; }
   GConvParams p = p0;
   const int tiles_m = (p.M + 127) / 128;
   const int co_pad = (p.Co + 15) & ~15;
@@ -934,6 +889,7 @@ StatLayout launch_gconv_tc(const GConvParams& p0, cudaStream_t st) {
 
 void launch_wgrad_tc(const WGradParams& p0, cudaStream_t st) {
   if (p0.M <= 0) return;
+  if (slab_supported_wgrad(p0)) { launch_slab_wgrad(p0, st); return; }
   WGradParams p = p0;
   int maxK = 0;
   for (int i = 0; i < p.nvar; ++i) maxK = max(maxK, p.var[i].ntaps * p.Ci);

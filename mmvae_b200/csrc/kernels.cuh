@@ -115,6 +115,7 @@ struct GConvParams {
   int nvar;
   int accumulate;              // out += result
   int in_nchw_f32;             // network input x: fp32 NCHW
+  int conv_class;              // 1: ConvTranspose2d k4 s2 p1 forward, 2: its data gradient (slab_tc.cu candidates), else 0
   // tcgen05 path: pre-packed bf16 weight tiles [variant][k-chunk of 64][co_pad rows][128 B, swizzled]
   const void* wpack;           // nullptr: no packed weights (SIMT only)
   int wpack_var_stride;        // bytes between variants
@@ -145,6 +146,7 @@ struct WGradParams {
   int w_sci, w_sco;
   int nvar, nsplit, rows_per_split;
   int in_nchw_f32;
+  int conv_class;              // 1: ConvTranspose2d k4 s2 p1 (slab_tc.cu candidate), else 0
   int tc_bn, tc_stages;        // set by the launcher (tcgen05 path)
   int tc_kb, tma_a, tma_b;
   FastDiv fd_wg, fd_hg, fd_ci, fd_hw;
@@ -165,6 +167,11 @@ template <typename T> void launch_wgrad_simt(const WGradParams& p, cudaStream_t 
 bool tc_supported_gconv(const GConvParams& p);
 bool tc_supported_wgrad(const WGradParams& p);
 StatLayout launch_gconv_tc(const GConvParams& p, cudaStream_t st);
+// shared-memory-resident band kernels for the narrow, large-image transposed convolutions (slab_tc.cu)
+bool slab_supported_gconv(const GConvParams& p);
+bool slab_supported_wgrad(const WGradParams& p);
+void launch_slab_wgrad(const WGradParams& p, cudaStream_t st);
+void launch_slab_gconv(const GConvParams& p, cudaStream_t st);
 void launch_wgrad_tc(const WGradParams& p, cudaStream_t st);
 
 // One entry per (conv, direction) whose weights are packed for the tcgen05 path.

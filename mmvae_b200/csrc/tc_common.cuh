@@ -3,6 +3,7 @@
 // descriptors.  Bit layouts follow the PTX ISA "tcgen05" chapter (matrix descriptor, instruction
 // descriptor for .kind::f16).
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <cstdint>
 
@@ -165,6 +166,53 @@ template <int ROWB>
 __device__ __forceinline__ uint32_t swz_off(uint32_t row, uint32_t chunk) {
   uint32_t a = row * ROWB + chunk * 16;
   return a ^ (((a >> 7) & (ROWB / 16 - 1)) << 4);
+}
+
+// ---------------- epilogue helpers ----------------
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// Sum over the 32 rows held by the lanes of a warp of 16 per-thread column values: a transposing
+// butterfly (16 shuffles).  Returns the column this lane ends up owning; its sum is in v[0]
+// (lanes 2c and 2c+1 hold the same column).
+__device__ __forceinline__ int warp_colsum16(float (&v)[16], int lane) {
+  {
+    const bool hi = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float send = hi ? v[i] : v[i + 8];
+      float keep = hi ? v[i + 8] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  {
+    const bool hi = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float send = hi ? v[i] : v[i + 4];
+      float keep = hi ? v[i + 4] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  {
+    const bool hi = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      float send = hi ? v[i] : v[i + 2];
+      float keep = hi ? v[i + 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+  }
+  {
+    const bool hi = lane & 2;
+    float send = hi ? v[0] : v[1];
+    float keep = hi ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+  return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
 }
 
 }  // namespace tc

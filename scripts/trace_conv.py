@@ -9,6 +9,7 @@ import mmvae_b200 as M
 from mmvae_b200 import data as D
 import types
 
+SLAB_SLOTS = ["entry", "prologue", "pdl_wait", "fill0_issued", "fill0_done", "fill1_done", "m_full0", "m_tile0", "m_slab0", "m_all", "e_tfull0", "e_tile0", "e_all", "dealloc", "bn_fin"]
 SLOTS = ["entry", "prologue", "pdl_wait", "tma0", "tma_all", "full0", "mma_tile0", "mma_all", "tfull0", "epi0", "epi_all",
          "stats", "dealloc", "bn_fin", "-", "-", "p_decoded", "p_chunk1", "m_commit0", "m_full1", "m_commit1"]
 n = int(os.environ.get("N", "256"))
@@ -53,4 +54,5 @@ for name in want:
               f"kernel span {(int(t[used].max()) - t0) / 1e3:.2f} us")
         for label, sel in (("first CTA", int(used[0])), ("last-ending CTA", int(used[t[used].max(dim=1).values.argmax()]))):
             row = t[sel]
-            print(f"   {label:16s} (cta {sel}): " + "  ".join(f"{SLOTS[s]}={(int(row[s]) - t0) / 1e3:.2f}" for s in range(len(SLOTS)) if row[s] > 0))
+            names = SLAB_SLOTS if (os.environ.get("SLAB") == "1") else SLOTS
+            print(f"   {label:16s} (cta {sel}): " + "  ".join(f"{names[s]}={(int(row[s]) - t0) / 1e3:.2f}" for s in range(len(names)) if row[s] > 0))
