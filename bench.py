@@ -244,46 +244,68 @@ def main():
         step_e2e(i)
     ms_e2e = timed(step_e2e, args.steps)
 
-    # ---- roofline of the dominant kernel, measured live: the tcgen05 implicit-GEMM conv kernel (gconv_tc_kernel: every
-    # forward conv / transposed conv and every data gradient, ~40 % of the step) on its heaviest layer, the 16-channel
-    # 32x32 -> 64x64 transposed conv decoder.uplayer5.0.conv2.  One launch per iteration through mmvae_bench_conv on the
-    # tensors the last step left in the workspace, CUDA events around each launch on the launching stream, L2 flushed
-    # (256 MB memset) between iterations.  Algorithmic bytes = bf16 input + output + weights, each touched once.
-    roof = None
+    # ---- rooflines, measured live: one launch per iteration of the production kernel of a (conv, direction) pair through
+    # mmvae_bench_conv on the tensors the last step left in the workspace, CUDA events around each launch on the launching
+    # stream, L2 flushed (256 MB memset) between iterations.  Algorithmic bytes = bf16 input + output + weights, each
+    # touched once; `traffic` = dram read + write of the same launch from the ncu --set full capture in profiles/.
+    #   roofline         the kernel with the largest share of the step (gconv_tc_kernel, the tcgen05 implicit-GEMM conv:
+    #                    ~30 % of the serialized kernel time over 48 launches) on its most expensive launch,
+    #                    encoder.layer4.0.conv2 (256->256, 3x3 on 2x2 maps: M = 1024, N = 256, K = 2304); its arithmetic
+    #                    intensity (542 FLOP/B) is above the ridge, so the bound is the tensor pipe
+    #   roofline_others  the shared-memory-resident band kernels (slab_tc.cu) on the heaviest-traffic layer of the model,
+    #                    decoder.uplayer5.0.conv2 (16->16 transposed conv, 256x32x32 -> 256x64x64): forward, data
+    #                    gradient, weight gradient -- HBM-bound
+    roof, roof_others = None, []
     if rank == 0 and args.precision == "bf16":
         import ctypes
         desc, ws, _info = model._workspace(n, True)
         names = [c[0] for c in M._lib.conv_table(desc)]
-        ci = names.index("decoder.uplayer5.0.conv2") if "decoder.uplayer5.0.conv2" in names else names.index("decoder.uplayer4.0.conv2")
         ab, af = ctypes.c_int64(), ctypes.c_int64()
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        scratch = torch.zeros(model._n_params, dtype=torch.float32, device=dev)
         stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        sustained_tf, burst_tf, hbm_peak, which_peak = peaks()
 
-        def one():
-            M._lib.check(M._lib.lib.mmvae_bench_conv(ctypes.byref(desc), ci, 0, ctypes.c_void_p(model._arena.data_ptr()),
-                                                     ctypes.c_void_p(ws.data_ptr()), ws.numel(), None, ctypes.byref(ab),
-                                                     ctypes.byref(af), stream), "mmvae_bench_conv")
-        for _ in range(3):
-            one()
-        evs = []
-        for _ in range(20):
-            flush.zero_()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); one(); e1.record()
-            evs.append((e0, e1))
-        torch.cuda.synchronize()
-        us = sorted(a.elapsed_time(b) * 1e3 for a, b in evs)
-        k_us = sum(us) / len(us)
-        _s, _b, hbm_peak, which_peak = peaks()
-        gbs = ab.value / (k_us * 1e-6) / 1e9
-        roof = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                "traffic": 8472576,
-                "kernel": "gconv_tc_kernel<16> on decoder.uplayer5.0.conv2 (ConvTranspose2d 16->16 k4 s2 p1, 256x32x32 -> 256x64x64)",
-                "algorithmic_bytes_per_launch": ab.value, "flops_per_launch": af.value, "us_per_launch": k_us,
-                "tensor_tflops": af.value / (k_us * 1e-6) / 1e12,
-                "note": f"of {which_peak} HBM copy peak; traffic = dram read+write of one launch from the ncu --set full capture "
-                        "in profiles/ (the 33.6 MB output stays in the 126 MB L2)"}
-        del flush
+        def measure(conv, direction):
+            ci = names.index(conv)
+
+            def one():
+                M._lib.check(M._lib.lib.mmvae_bench_conv(ctypes.byref(desc), ci, direction, ctypes.c_void_p(model._arena.data_ptr()),
+                                                         ctypes.c_void_p(ws.data_ptr()), ws.numel(),
+                                                         ctypes.c_void_p(scratch.data_ptr()), ctypes.byref(ab), ctypes.byref(af),
+                                                         stream), "mmvae_bench_conv")
+            for _ in range(3):
+                one()
+            evs = []
+            for _ in range(20):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); one(); e1.record()
+                evs.append((e0, e1))
+            torch.cuda.synchronize()
+            us = [a.elapsed_time(b) * 1e3 for a, b in evs]
+            return sum(us) / len(us), ab.value, af.value
+
+        def entry(kernel, conv, direction, bound, traffic):
+            k_us, nbytes, nflops = measure(conv, direction)
+            gbs, tfs = nbytes / (k_us * 1e-6) / 1e9, nflops / (k_us * 1e-6) / 1e12
+            e = {"bound": bound, "unit": "GB/s" if bound == "hbm" else "TFLOP/s",
+                 "achieved": gbs if bound == "hbm" else tfs, "peak": hbm_peak if bound == "hbm" else burst_tf,
+                 "traffic": traffic, "kernel": kernel, "algorithmic_bytes_per_launch": nbytes, "flops_per_launch": nflops,
+                 "us_per_launch": k_us, "gbs": gbs, "tensor_tflops": tfs,
+                 "note": f"of the {which_peak} " + ("HBM copy peak" if bound == "hbm" else "burst bf16 peak (kernel timed alone)") +
+                         "; traffic = dram read+write of one launch, ncu --set full, profiles/r01_conv_kernels_full.md"}
+            e["frac"] = e["achieved"] / e["peak"]
+            return e
+
+        if "encoder.layer4.0.conv2" in names and "decoder.uplayer5.0.conv2" in names:
+            roof = entry("gconv_tc_kernel<32> forward on encoder.layer4.0.conv2 (Conv2d 256->256 k3 s1 p1, 256x2x2): M=1024 N=256 K=2304",
+                         "encoder.layer4.0.conv2", 0, "tensor", 1770000)
+            u5 = "decoder.uplayer5.0.conv2 (ConvTranspose2d 16->16 k4 s2 p1, 256x32x32 -> 256x64x64)"
+            roof_others = [entry("slab_fwd_kernel<16> forward on " + u5, "decoder.uplayer5.0.conv2", 0, "hbm", 8450000),
+                           entry("slab_dgrad_kernel<16> data gradient on " + u5, "decoder.uplayer5.0.conv2", 1, "hbm", 33600000),
+                           entry("slab_wgrad_kernel<16> weight gradient on " + u5, "decoder.uplayer5.0.conv2", 2, "hbm", 41990000)]
+        del flush, scratch
 
     fps = world * n * args.steps / (ms * 1e-3)
     fps_e2e = world * n * args.steps / (ms_e2e * 1e-3)
@@ -306,6 +328,7 @@ def main():
         "clocks": clk.summary(),
         "roofline": roof if roof is not None else {"bound": "tensor", "achieved": tflops_per_gpu, "peak": sustained,
                                                    "unit": "TFLOP/s", "frac": tflops_per_gpu / sustained, "traffic": None},
+        "roofline_others": roof_others,
         "step_tensor": {"achieved": tflops_per_gpu, "peak": sustained, "unit": "TFLOP/s", "frac": tflops_per_gpu / sustained,
                         "note": f"whole step, 227.02 MFLOP/frame algorithmic, per GPU, of {which} sustained bf16 peak"},
     }
