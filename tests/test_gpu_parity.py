@@ -106,6 +106,29 @@ def test_bf16_step_within_bf16_floor(name):
     assert rel_l2(res.mu, ref.mu) <= 2 * rel_l2(emu.mu, ref.mu) + 1e-3
 
 
+def test_bench_batch_bf16_against_fp32_mode():
+    """The bench configuration (N=256, 64x64): the bf16 product path against the fp32 validation path of the same
+    library (itself pinned to the reference fixtures above) on the same weights, frames and noise.  Loss within 1e-2;
+    gradients within the bf16-storage floor seen on the small fixtures (cosine > 0.85, relative L2 < 0.6)."""
+    cfg = O.VAEConfig(input_image_size=64, z_dimension=64)
+    st = O.init_state(cfg, seed=3)
+    n = 256
+    x = O.normalise(O.synthetic_labels(n, 64))
+    eps = torch.randn(n, 64, 1, 1, generator=torch.Generator().manual_seed(11))
+    r32 = train_step(build_model(cfg, st, "fp32"), cfg, x, x, eps)
+    r16 = train_step(build_model(cfg, st, "bf16"), cfg, x, x, eps)
+    assert abs(r16.loss - r32.loss) <= 1e-2 * abs(r32.loss)
+    names = [k for k, _ in O.param_specs(cfg) if k != "decoder.conv2.bias"]
+    cos = {k: torch.nn.functional.cosine_similarity(r16.grads[k].double().reshape(1, -1),
+                                                    r32.grads[k].double().reshape(1, -1)).item() for k in names}
+    rel = {k: rel_l2(r16.grads[k], r32.grads[k]) for k in names}
+    print(f"N=256: bf16 vs fp32 mode: min cosine {min(cos.values()):.3f}, max rel-L2 {max(rel.values()):.3f}, "
+          f"median rel-L2 {float(np.median(list(rel.values()))):.3f}")
+    assert min(cos.values()) > 0.85, sorted(cos.items(), key=lambda kv: kv[1])[:5]
+    assert max(rel.values()) < 0.6, sorted(rel.items(), key=lambda kv: -kv[1])[:5]
+    assert rel_l2(r16.recon, r32.recon) < 3e-2 and rel_l2(r16.mu, r32.mu) < 3e-2
+
+
 def test_eval_mode_and_decoder_only():
     g = Golden("base64_n4")
     st = g.state()

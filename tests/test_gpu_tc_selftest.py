@@ -36,7 +36,8 @@ def run_selftest(n, image_size=64, z=64, width=1, out_channels=1):
     return rows
 
 
-@pytest.mark.parametrize("n,size", [(8, 64), (64, 64), (6, 28), (3, 32)])
+# (256, 64) is the bench batch: persistent CTAs walk several tiles / bands each (ring wrap-around, both TMEM buffers)
+@pytest.mark.parametrize("n,size", [(8, 64), (64, 64), (256, 64), (6, 28), (3, 32), (160, 32)])
 def test_tc_kernels_match_simt(n, size):
     rows = run_selftest(n, image_size=size, z=64 if size == 64 else 32)
     bad = []
