@@ -5,6 +5,10 @@
 // buffers updated with momentum 0.1 and the unbiased variance, num_batches_tracked += 1.
 // The per-channel sums come from the producing conv's epilogue as per-CTA partials and are
 // combined here in a fixed order in fp64, so a step is bit-reproducible.
+#include <algorithm>
+#include <cstdlib>
+#include <type_traits>
+
 #include "bn_fused.cuh"
 #include "kernels.cuh"
 
@@ -91,6 +95,21 @@ __device__ __forceinline__ void store_vec(T* p, const float (&f)[VEC]) {
 #pragma unroll
   for (int i = 0; i < VEC; ++i) e[i] = from_f<T>(f[i]);
   *reinterpret_cast<typename Vec<T, VEC>::type*>(p) = raw;
+}
+
+// raw 16-byte vector of the storage type (kept packed in registers until it is used)
+template <typename T, int VEC> struct RawVec { typename Vec<T, VEC>::type r; };
+template <typename T, int VEC>
+__device__ __forceinline__ void unpack_vec(const RawVec<T, VEC>& raw, float (&f)[VEC]) {
+  const T* e = reinterpret_cast<const T*>(&raw.r);
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) f[i] = to_f(e[i]);
+}
+template <typename T, int VEC>
+__device__ __forceinline__ RawVec<T, VEC> load_raw(const T* p) {
+  RawVec<T, VEC> v;
+  v.r = *reinterpret_cast<const typename Vec<T, VEC>::type*>(p);
+  return v;
 }
 
 // incoming gradient: storage type, or fp32 (the user-facing d_recon)
@@ -399,6 +418,149 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a) {
   }
 }
 
+// BatchNorm backward of a small / medium tensor in ONE launch: every thread keeps its (at most kCoopE) 16-byte vectors
+// of g = dA * [a > 0], y (and y2) packed in registers across a grid-wide barrier -- phase 1 reduces the three per-channel
+// sums into the fp64 accumulators, the barrier is an atomic counter every CTA spins on (the grid is at most one CTA per
+// SM and needs little of it, so all CTAs are co-resident eventually whatever else runs), phase 2 turns the sums into the
+// coefficients and writes dY (dY2) from the registers.  Replaces bn_bwd_reduce + bn_bwd_apply: one launch boundary and
+// one pass over the inputs less.
+constexpr int kCoopE = 4;
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__global__ void __launch_bounds__(256, 2) bn_bwd_coop_kernel(const BnBwdArgs a, int E) {
+  pdl_wait();                                       // PDL: may start while the previous kernel drains
+  pdl_trigger();
+  typedef __nv_bfloat16 T;
+  constexpr int VEC = 8;
+  __shared__ float red[256 * VEC * 3];
+  __shared__ float coef[2][5][256];                  // per branch: mean, rstd, scale, c1, c2
+  const int CV = a.C / VEC, RPI = 256 / CV;
+  const int tid = threadIdx.x;
+  const int cv = tid % CV, rsub = tid / CV, c0 = cv * VEC;
+  const T* dA = reinterpret_cast<const T*>(a.dA);
+  const T* am = reinterpret_cast<const T*>(a.a);
+  const T* y1 = reinterpret_cast<const T*>(a.y);
+  const T* y2 = reinterpret_cast<const T*>(a.y2);
+  float mean[VEC], rstd[VEC], mean2[VEC], rstd2[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    mean[k] = a.stat[c0 + k]; rstd[k] = a.stat[a.C + c0 + k];
+    mean2[k] = y2 ? a.stat2[c0 + k] : 0.f; rstd2[k] = y2 ? a.stat2[a.C + c0 + k] : 0.f;
+  }
+  RawVec<T, VEC> rg[kCoopE], ry[kCoopE], rz[kCoopE];
+  float s0[VEC], s1[VEC], s2[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) { s0[k] = s1[k] = s2[k] = 0.f; }
+  const long long rstride = (long long)gridDim.x * RPI;
+  const long long r00 = (long long)blockIdx.x * RPI + rsub;
+  // ---- phase 1: loads (all issued up front), mask, sums ----
+#pragma unroll
+  for (int e = 0; e < kCoopE; ++e) {
+    const long long r = r00 + e * rstride;
+    if (e < E && r < a.rows) {
+      const size_t off = size_t(r) * a.C + c0;
+      rg[e] = load_raw<T, VEC>(dA + off);
+      ry[e] = load_raw<T, VEC>(y1 + off);
+      if (y2) rz[e] = load_raw<T, VEC>(y2 + off);
+      if (am) {
+        const RawVec<T, VEC> ra = load_raw<T, VEC>(am + off);
+        const T* ae = reinterpret_cast<const T*>(&ra.r);
+        T* ge = reinterpret_cast<T*>(&rg[e].r);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) if (!(to_f(ae[k]) > 0.f)) ge[k] = from_f<T>(0.f);
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < kCoopE; ++e) {
+    const long long r = r00 + e * rstride;
+    if (e < E && r < a.rows) {
+      float g[VEC], yv[VEC];
+      unpack_vec<T, VEC>(rg[e], g);
+      unpack_vec<T, VEC>(ry[e], yv);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) { s0[k] += g[k]; s1[k] = fmaf(g[k], (yv[k] - mean[k]) * rstd[k], s1[k]); }
+      if (y2) {
+        unpack_vec<T, VEC>(rz[e], yv);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) s2[k] = fmaf(g[k], (yv[k] - mean2[k]) * rstd2[k], s2[k]);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    red[(0 * RPI + rsub) * a.C + c0 + k] = s0[k];
+    red[(1 * RPI + rsub) * a.C + c0 + k] = s1[k];
+    red[(2 * RPI + rsub) * a.C + c0 + k] = s2[k];
+  }
+  __syncthreads();
+  for (int e = tid; e < 3 * a.C; e += 256) {
+    const int which = e / a.C, c = e % a.C;
+    float sum = 0.f;
+    for (int q = 0; q < RPI; ++q) sum += red[(which * RPI + q) * a.C + c];
+    atomicAdd(a.acc + (size_t)(blockIdx.x % kBnAccCopies) * 3 * a.C + which * a.C + c, (double)sum);
+  }
+  // ---- grid-wide barrier ----
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    atomicAdd(a.counter, 1u);
+    while (ld_acquire_u32(a.counter) < gridDim.x) { __nanosleep(32); }
+  }
+  __syncthreads();
+  // ---- phase 2: coefficients (one channel per thread), then dY from the registers ----
+  const double im = 1.0 / (double)a.rows;
+  for (int c = tid; c < a.C; c += 256) {
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < kBnAccCopies; ++k) {
+      const double* ak = a.acc + (size_t)k * 3 * a.C;
+      t0 += ld_cg_f64(ak + c); t1 += ld_cg_f64(ak + a.C + c); t2 += ld_cg_f64(ak + 2 * a.C + c);
+    }
+    coef[0][0][c] = a.stat[c]; coef[0][1][c] = a.stat[a.C + c];
+    coef[0][2][c] = a.gamma[c] * a.stat[a.C + c]; coef[0][3][c] = (float)(t0 * im); coef[0][4][c] = (float)(t1 * im);
+    if (y2) {
+      coef[1][0][c] = a.stat2[c]; coef[1][1][c] = a.stat2[a.C + c];
+      coef[1][2][c] = a.gamma2[c] * a.stat2[a.C + c]; coef[1][3][c] = (float)(t0 * im); coef[1][4][c] = (float)(t2 * im);
+    }
+    if (blockIdx.x == 0) {
+      a.g_beta[c] = (float)t0; a.g_gamma[c] = (float)t1;
+      if (y2) { a.g_beta2[c] = (float)t0; a.g_gamma2[c] = (float)t2; }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < kCoopE; ++e) {
+    const long long r = r00 + e * rstride;
+    if (e < E && r < a.rows) {
+      const size_t off = size_t(r) * a.C + c0;
+      float g[VEC], yv[VEC], o[VEC];
+      unpack_vec<T, VEC>(rg[e], g);
+      unpack_vec<T, VEC>(ry[e], yv);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        const int c = c0 + k;
+        const float xh = (yv[k] - coef[0][0][c]) * coef[0][1][c];
+        o[k] = coef[0][2][c] * (g[k] - coef[0][3][c] - xh * coef[0][4][c]);
+      }
+      store_vec<T, VEC>(reinterpret_cast<T*>(a.dY) + off, o);
+      if (y2) {
+        unpack_vec<T, VEC>(rz[e], yv);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          const int c = c0 + k;
+          const float xh = (yv[k] - coef[1][0][c]) * coef[1][1][c];
+          o[k] = coef[1][2][c] * (g[k] - coef[1][3][c] - xh * coef[1][4][c]);
+        }
+        store_vec<T, VEC>(reinterpret_cast<T*>(a.dY2) + off, o);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                            long long total, int C, int HW) {
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
@@ -469,6 +631,23 @@ void launch_heads_bwd(const HeadsBwdArgs& a, cudaStream_t st) {
 template <typename T>
 void launch_bn_bwd(const BnBwdArgs& a, cudaStream_t st) {
   constexpr int V = vec_of<T>();
+  if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+    // one cooperative launch when every thread's share fits its registers (tensors up to 2.4 MB): half a register
+    // file per SM, so it stays co-resident with the weight-gradient kernels of the auxiliary stream
+    static const bool coop_off = getenv("MMVAE_NO_COOP_BN") != nullptr;
+    const int CV = a.C / 8;
+    if (!coop_off && a.acc && !a.reduced && !a.dA_f32 && a.C % 8 == 0 && CV >= 1 && CV <= 32 && 256 % CV == 0) {
+      const int RPI = 256 / CV;
+      const long long row_groups = (a.rows + RPI - 1) / RPI;
+      const int grid = (int)std::min<long long>(148, row_groups);
+      const int E = (int)((row_groups + grid - 1) / grid);
+      if (E <= kCoopE) {
+        count_launch();
+        launch_pdl(bn_bwd_coop_kernel, grid, 256, 0, st, a, E);
+        return;
+      }
+    }
+  }
   const bool vec_ok = (a.C % V == 0) && (a.C / V <= 256);
   int nblocks;
   if (vec_ok) {
