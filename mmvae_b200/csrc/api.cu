@@ -130,7 +130,11 @@ static AuxPool* aux_pool() {
   std::lock_guard<std::mutex> lock(mu);
   AuxPool& p = pools[dev];
   if (!p.ok) {
-    if (cudaStreamCreateWithFlags(&p.s, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    // lowest priority: when both streams have CTAs waiting for an SM, the critical path (the caller's stream) goes first
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    static const bool flat = getenv("MMVAE_AUX_FLAT_PRIORITY") != nullptr;       // A/B: default priority (measured +0.4 % step time)
+    if (cudaStreamCreateWithPriority(&p.s, cudaStreamNonBlocking, flat ? 0 : prio_lo) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     for (auto& e : p.ev)
       if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     p.ok = true;

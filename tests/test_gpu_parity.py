@@ -129,6 +129,32 @@ def test_bench_batch_bf16_against_fp32_mode():
     assert rel_l2(r16.recon, r32.recon) < 3e-2 and rel_l2(r16.mu, r32.mu) < 3e-2
 
 
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_widened_vae_against_oracle(prec):
+    """BASELINE configs[3]: the widened VAE (2x channels, latent dim 256), here at N=4.  fp32 mode against the fp64
+    oracle within 3x the distance of a torch-fp32 evaluation from it; bf16 mode: loss within 1e-2 and gradients along the oracle's."""
+    cfg = O.VAEConfig(input_image_size=64, z_dimension=256, width=2)
+    st = O.init_state(cfg, seed=5)
+    n = 4
+    x = O.normalise(O.synthetic_labels(n, 64))
+    eps = torch.randn(n, 256, 1, 1, generator=torch.Generator().manual_seed(12))
+    ref = O.train_step(st, cfg, x, x, eps, dtype=torch.float64)
+    res = train_step(build_model(cfg, st, prec), cfg, x, x, eps)
+    names = [k for k, _ in O.param_specs(cfg) if k != "decoder.conv2.bias"]
+    if prec == "fp32":
+        # same two-sided bar as test_fp32_step_vs_fp64_oracle: no worse than 3x torch-fp32's own distance from fp64
+        r32 = O.train_step(st, cfg, x, x, eps)
+        assert abs(res.loss - ref.loss) <= 1e-5 * abs(ref.loss)
+        bad = [(k, rel_l2(res.grads[k], ref.grads[k]), rel_l2(r32.grads[k], ref.grads[k])) for k in names
+               if rel_l2(res.grads[k], ref.grads[k]) > max(1e-5, 3 * rel_l2(r32.grads[k], ref.grads[k]))]
+        assert not bad, bad[:10]
+    else:
+        assert abs(res.loss - ref.loss) <= 1e-2 * abs(ref.loss)
+        cos = {k: torch.nn.functional.cosine_similarity(res.grads[k].double().reshape(1, -1),
+                                                        ref.grads[k].double().reshape(1, -1)).item() for k in names}
+        assert min(cos.values()) > 0.8, sorted(cos.items(), key=lambda kv: kv[1])[:5]
+
+
 def test_eval_mode_and_decoder_only():
     g = Golden("base64_n4")
     st = g.state()

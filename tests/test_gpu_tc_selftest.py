@@ -53,3 +53,11 @@ def test_tc_kernels_match_simt(n, size):
                 bad.append((name, ("fwd", "bn", "wgrad", "dgrad")[j], r))
     assert tested >= 80
     assert not bad, bad
+
+
+def test_tc_kernels_match_simt_widened():
+    """BASELINE configs[3]: 2x channels, latent dim 256 (64-channel stem, 512-channel bottleneck, 128-column tiles)."""
+    rows = run_selftest(8, image_size=64, z=256, width=2)
+    tol = (4e-3, 1e-3, 1e-3, 4e-3)
+    bad = [(name, j, r) for name, rel in rows for j, r in enumerate(rel) if r is not None and not r <= tol[j]]
+    assert not bad, bad
