@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define MMVAE_ABI_VERSION 2
+#define MMVAE_ABI_VERSION 3
 
 enum {
   MMVAE_OK = 0,
@@ -67,8 +67,18 @@ typedef struct mmvae_desc {
   int32_t precision;        /* MMVAE_PREC_*                                                    */
   int32_t training;         /* 1: batch-statistics BatchNorm + running-stat update; 0: eval    */
   int32_t flags;            /* MMVAE_FLAG_* (0 = default kernel selection)                     */
-  int32_t reserved[5];
+  int32_t arch;             /* MMVAE_ARCH_* (0 = model.py VAE)                                 */
+  int32_t reserved[4];
 } mmvae_desc;
+
+/* Network family.  MMVAE_ARCH_NOTEBOOK is the BatchNorm-free variant of vae-kl.ipynb:119-166 (BASELINE configs[4]):
+ * encoder conv(1->C,k5,s2,p2) ReLU, conv(C->C,k5,s2,p1) ReLU, conv(k3,s2,p1) ReLU x2, heads conv(C->z,k3,s2,p1) x2;
+ * decoder up2 conv3x3(z->C) ELU, up4 conv ELU, up2 conv ELU, up2 conv3x3(C->out_channels) = logits; every conv has a
+ * bias.  C = 32*width, out_channels = classes (256 in the notebook, a multiple of 8, <= 256), image_size 64 or 128,
+ * in_channels 1; require_rsample / training are ignored (no BatchNorm, always samples).  mu / logvar / encoding are
+ * [N, z, h, h] (h = image_size/32).  Parameter arena order: encoder.conv1.weight, .bias, ... decoder.conv4.bias
+ * (list(encoder.parameters()) + list(decoder.parameters()), vae-kl.ipynb cell 7). */
+enum { MMVAE_ARCH_RESNET = 0, MMVAE_ARCH_NOTEBOOK = 1 };
 
 /* Kernel selection for validation: MMVAE_PREC_BF16 normally runs every layer shape the tcgen05
  * kernels cover on the tensor cores; this flag forces the fp32-FMA SIMT kernels (same bf16 storage)
@@ -131,6 +141,19 @@ int mmvae_forward(const mmvae_desc* d, const float* x, const float* params, floa
                   int64_t* bn_counters, const float* eps, uint64_t seed, uint64_t offset, float* eps_out,
                   const uint64_t* rng_state, void* workspace, size_t workspace_bytes,
                   float* mu, float* logvar, float* encoding, float* recon, void* stream);
+
+/* MMVAE_ARCH_NOTEBOOK: mmvae_forward takes the same arguments (bn_buffers / bn_counters unused, may be NULL); `recon`
+ * (the logits, [N, classes, S, S] fp32 NCHW) may be NULL: at training batch sizes the logits stay in the workspace in the
+ * storage type (4.3 GB at N=512, 128x128) and only mmvae_nb_loss_backward reads them.
+ *
+ * mmvae_nb_loss_backward = the rest of the notebook's loop body (vae-kl.ipynb:225-231) in one call:
+ *   pxz = sum CE(logits, target) / N,  kl = sum KL(N(mu, exp(logvar/2)) || N(0,1)) / N,  loss = pxz + kl_weight * kl
+ * and the gradient of `loss` with respect to every parameter (arena `grads`, overwritten).  target: int64 [N, S, S]
+ * class indices; out: 3 floats on the device {loss, pxz, kl}.  Must follow a mmvae_forward with the same desc /
+ * workspace / x / params.  kl_weight = 1 is the notebook; any other value is the annealed configuration. */
+int mmvae_nb_loss_backward(const mmvae_desc* d, const float* x, const int64_t* target, const float* params,
+                           void* workspace, size_t workspace_bytes, float kl_weight, float* out, float* grads,
+                           void* stream);
 
 /* Decoder only (get_z_image / get_reconstruction, model.py:344-362): encoding [N, z] -> recon. */
 int mmvae_decode(const mmvae_desc* d, const float* encoding, const float* params, float* bn_buffers,

@@ -15,7 +15,8 @@ PREC_FP32, PREC_BF16 = 0, 1
 LOSS_GAUSSIAN, LOSS_CATEGORICAL = 0, 1
 BWD_DECODER, BWD_ENC_DEEP, BWD_ENC_SHALLOW, BWD_ALL = 1, 2, 4, 7
 FLAG_FORCE_SIMT = 1
-ABI_VERSION = 2
+ARCH_RESNET, ARCH_NOTEBOOK = 0, 1
+ABI_VERSION = 3
 
 EXPORTS = [
     "mmvae_abi_version", "mmvae_last_error", "mmvae_layout", "mmvae_param_entry", "mmvae_bn_entry",
@@ -23,6 +24,7 @@ EXPORTS = [
     "mmvae_loss_forward", "mmvae_loss_backward", "mmvae_backward", "mmvae_backward_range",
     "mmvae_philox_normal", "mmvae_adam_step", "mmvae_prepare_input", "mmvae_launch_count",
     "mmvae_conv_entry", "mmvae_selftest_tc", "mmvae_bench_conv", "mmvae_debug_set_trace",
+    "mmvae_nb_loss_backward",
 ]
 
 
@@ -30,7 +32,7 @@ class Desc(Structure):
     _fields_ = [("struct_size", c_int32), ("batch", c_int32), ("in_channels", c_int32),
                 ("out_channels", c_int32), ("z_dim", c_int32), ("image_size", c_int32), ("width", c_int32),
                 ("require_rsample", c_int32), ("precision", c_int32), ("training", c_int32),
-                ("flags", c_int32), ("reserved", c_int32 * 5)]
+                ("flags", c_int32), ("arch", c_int32), ("reserved", c_int32 * 4)]
 
 
 class LayoutInfo(Structure):
@@ -69,6 +71,7 @@ def _load():
     lib.mmvae_loss_forward.argtypes = [POINTER(LossArgs), P, P, P, P, P, P, P, P]
     lib.mmvae_loss_backward.argtypes = [POINTER(LossArgs), P, P, P, P, P, P, P, P, P, P]
     lib.mmvae_backward.argtypes = [POINTER(Desc), P, P, P, c_size_t, P, P, P, P, P, c_int32, P]
+    lib.mmvae_nb_loss_backward.argtypes = [POINTER(Desc), P, P, P, P, c_size_t, c_float, P, P, P]
     lib.mmvae_backward_range.argtypes = [POINTER(Desc), c_int32, POINTER(c_int64), POINTER(c_int64)]
     lib.mmvae_philox_normal.argtypes = [c_uint64, c_uint64, c_int64, P, P]
     lib.mmvae_adam_step.argtypes = [c_int64, P, P, P, P, c_float, c_float, c_float, c_float, c_float, c_int64,
@@ -99,13 +102,14 @@ def check(rc, what=""):
 
 
 def make_desc(batch, in_channels, out_channels, z_dim, image_size, width=1, require_rsample=True,
-              precision=PREC_BF16, training=True, flags=0):
+              precision=PREC_BF16, training=True, flags=0, arch=ARCH_RESNET):
     d = Desc()
     d.struct_size = ctypes.sizeof(Desc)
     d.batch, d.in_channels, d.out_channels, d.z_dim = int(batch), int(in_channels), int(out_channels), int(z_dim)
     d.image_size, d.width = int(image_size), int(width)
     d.require_rsample, d.precision, d.training = int(bool(require_rsample)), int(precision), int(bool(training))
     d.flags = int(flags)
+    d.arch = int(arch)
     return d
 
 

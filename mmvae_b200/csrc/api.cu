@@ -188,10 +188,10 @@ struct Exec {
   // dedicated kernels of the 1-channel stem / tail convolutions (bf16 mode)
   bool special_ok() const { return std::is_same<T, __nv_bfloat16>::value && !(P.d.flags & MMVAE_FLAG_FORCE_SIMT); }
   bool use_stem(const ConvT_& c) const {
-    return special_ok() && c.in < 0 && &c == &P.convs[P.stem] && stem_supported(c.Ci, c.Co, c.Hi, c.k, c.s, c.p);
+    return special_ok() && P.stem >= 0 && c.in < 0 && &c == &P.convs[P.stem] && stem_supported(c.Ci, c.Co, c.Hi, c.k, c.s, c.p);
   }
   bool use_tail(const ConvT_& c) const {
-    return special_ok() && &c == &P.convs[P.tail] && c.kind == CONV && tail_supported(c.Ci, c.Co, c.Hi, c.k, c.s, c.p);
+    return special_ok() && P.tail >= 0 && &c == &P.convs[P.tail] && c.kind == CONV && tail_supported(c.Ci, c.Co, c.Hi, c.k, c.s, c.p);
   }
 
   // fp32 master weights -> bf16 tiles of the tcgen05 kernels (both directions), one launch
@@ -478,6 +478,106 @@ struct Exec {
     dgrad(cs, 1);                                     // += shortcut
   }
 
+  // ---------------- notebook variant (MMVAE_ARCH_NOTEBOOK; vae-kl.ipynb:119-166, loop body :210-233) ----------------
+  // No BatchNorm: bias + activation live in the conv epilogue, the activation derivative in the data-gradient epilogue
+  // of the consumer (or in the upsample adjoint when an upsample sits between producer and consumer).
+  void nb_conv_fwd(const ConvT_& c, int act_kind) {
+    GConvParams g;
+    geom_fprop(c, P.d.batch, g);
+    if (c.in < 0) { g.in = x; g.in_nchw_f32 = 1; }
+    else g.in = at<T>(act(c.in).off);
+    g.out = at<T>(act(c.out).off);
+    g.w = params + c.w; g.bias = params + c.bias; g.act = act_kind;
+    g.wpack = c.wp_chunks[DIR_FPROP] > 0 ? ws + c.wp_off[DIR_FPROP] : nullptr;
+    conv_forward<T>(g, c, st);
+  }
+  int nb_dec_src(int k) const { return k > 0 ? P.convs[P.nb.dc[k - 1]].out : P.nb.a_z; }   // tensor upsampled into decoder.conv{k+1}
+
+  void nb_forward(const float* eps, unsigned long long seed, unsigned long long offset, const uint64_t* rng_state,
+                  float* eps_out, float* mu, float* logvar, float* enc, float* recon) {
+    const NbT& nb = P.nb;
+    const int N = P.d.batch;
+    for (int i = 0; i < 4; ++i) nb_conv_fwd(P.convs[nb.e[i]], ACT_RELU);          // vae-kl.ipynb:134-137
+    const ConvT_& cmu = P.convs[nb.cmu]; const ConvT_& clv = P.convs[nb.clv];
+    nb_conv_fwd(cmu, ACT_NONE);                                                   // vae-kl.ipynb:139-140
+    nb_conv_fwd(clv, ACT_NONE);
+    NbSampleArgs a{};
+    a.mu_y = at<T>(act(cmu.out).off); a.lv_y = at<T>(act(clv.out).off);
+    a.eps = eps; a.seed = seed; a.offset = offset; a.rng_dev = reinterpret_cast<const unsigned long long*>(rng_state);
+    a.eps_keep = at<float>(nb.eps_off);
+    a.mu_out = mu; a.lv_out = logvar; a.enc_out = enc; a.eps_out = eps_out;
+    a.z_act = at<T>(act(nb.a_z).off);
+    a.N = N; a.hw = nb.latent_hw * nb.latent_hw; a.z = P.d.z_dim;
+    launch_nb_rsample<T>(a, st);                                                  // vae-kl.ipynb:144-146
+    nb_decode(recon);
+  }
+  void nb_decode(float* recon) {
+    const NbT& nb = P.nb;
+    const int N = P.d.batch;
+    for (int k = 0; k < 4; ++k) {                                                 // vae-kl.ipynb:162-166
+      const ActT& src = act(nb_dec_src(k));
+      launch_nb_upsample<T>(at<T>(src.off), at<T>(act(nb.a_up[k]).off), N, src.H, src.W, src.C, nb.up[k], st);
+      nb_conv_fwd(P.convs[nb.dc[k]], k < 3 ? ACT_ELU : ACT_NONE);
+    }
+    if (recon) {
+      const ConvT_& c = P.convs[nb.dc[3]];
+      launch_nb_export_nchw<T>(at<T>(act(c.out).off), recon, N, c.Ho * c.Wo, c.Co, st);
+    }
+  }
+  void nb_dgrad(const ConvT_& c, int accumulate, int dact_kind, int dact_act) {
+    GConvParams g;
+    fill_dgrad(c, g);
+    g.accumulate = accumulate;
+    if (dact_act >= 0) { g.dact = at<T>(act(dact_act).off); g.dact_kind = dact_kind; }
+    conv_dgrad<T>(g, c, st);
+  }
+  void nb_param_grads(const ConvT_& c, bool with_bias = true) {
+    wgrad(c);
+    if (with_bias)
+      launch_nb_colsum<T>(at<T>(act(c.out).goff), (long long)P.d.batch * c.Ho * c.Wo, c.Co, grads + c.bias, st);
+  }
+  // loss = sum CE / N + klw * sum KL / N (vae-kl.ipynb:225-228) and its gradient wrt every parameter
+  void nb_loss_backward(const long long* target, float klw, float* out) {
+    const NbT& nb = P.nb;
+    const int N = P.d.batch;
+    const float inv_n = 1.0f / (float)N;
+    cudaMemsetAsync(grads, 0, sizeof(float) * size_t(P.n_params), st);
+    cudaMemsetAsync(ws + nb.acc_off, 0, sizeof(double) * 2, st);
+    double* acc = at<double>(nb.acc_off);
+    const ConvT_& c4 = P.convs[nb.dc[3]];
+    launch_nb_ce<T>(at<T>(act(c4.out).off), target, at<T>(act(c4.out).goff), (long long)N * c4.Ho * c4.Wo, c4.Co, inv_n, acc,
+                    grads + c4.bias, st);
+    for (int k = 3; k >= 0; --k) {
+      const ConvT_& c = P.convs[nb.dc[k]];
+      side([&] { nb_param_grads(c, k < 3); });          // decoder.conv4's bias gradient came out of the CE kernel
+      nb_dgrad(c, 0, ACT_NONE, -1);                     // -> d(upsampled input)
+      const int srci = nb_dec_src(k);
+      const ActT& src = act(srci);
+      launch_nb_upsample_bwd<T>(at<T>(act(nb.a_up[k]).goff), k > 0 ? at<T>(src.off) : nullptr, ACT_ELU, at<T>(src.goff), N,
+                                src.H, src.W, src.C, nb.up[k], st);
+    }
+    const ConvT_& cmu = P.convs[nb.cmu]; const ConvT_& clv = P.convs[nb.clv];
+    NbSampleBwdArgs b{};
+    b.dz = at<T>(act(nb.a_z).goff);
+    b.mu_y = at<T>(act(cmu.out).off); b.lv_y = at<T>(act(clv.out).off); b.eps_keep = at<float>(nb.eps_off);
+    b.d_mu_y = at<T>(act(cmu.out).goff); b.d_lv_y = at<T>(act(clv.out).goff);
+    b.kl_acc = acc + 1; b.klw_over_n = klw * inv_n;
+    b.N = N; b.hw = nb.latent_hw * nb.latent_hw; b.z = P.d.z_dim;
+    launch_nb_rsample_bwd<T>(b, st);
+    launch_nb_loss_finalize(acc, inv_n, klw, out, st);
+    side([&] { nb_param_grads(cmu); nb_param_grads(clv); });
+    const int a4 = P.convs[nb.e[3]].out;
+    nb_dgrad(cmu, 0, ACT_RELU, a4);
+    nb_dgrad(clv, 1, ACT_RELU, a4);
+    for (int i = 3; i >= 1; --i) {
+      const ConvT_& c = P.convs[nb.e[i]];
+      side([&] { nb_param_grads(c); });
+      nb_dgrad(c, 0, ACT_RELU, P.convs[nb.e[i - 1]].out);
+    }
+    nb_param_grads(P.convs[nb.e[0]]);
+    join();
+  }
+
   // gradient-arena range [begin, end) owned by a backward phase
   static void phase_range(const Plan& P, int phase, int64_t& b, int64_t& e) {
     const int64_t deep = P.convs[P.enc[2].c1].w;             // encoder.layer3.0.conv1.weight
@@ -656,6 +756,20 @@ int mmvae_forward(const mmvae_desc* d, const float* x, const float* params, floa
                   const uint64_t* rng_state, void* workspace, size_t workspace_bytes, float* mu, float* logvar,
                   float* encoding, float* recon, void* stream) {
   MMVAE_COMMON_CHECKS();
+  if (P.d.arch == MMVAE_ARCH_NOTEBOOK) {
+    if (!x || !params) return fail(MMVAE_ERR_BAD_ARG, "x/params must be non-NULL");
+    if (!aligned16(params) || !aligned16(x)) return fail(MMVAE_ERR_BAD_ARG, "x and params must be 16-byte aligned");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (P.d.precision == MMVAE_PREC_FP32) {
+      Exec<float> E{P, (char*)workspace, params, nullptr, nullptr, nullptr, st, x};
+      E.nb_forward(eps, seed, offset, rng_state, eps_out, mu, logvar, encoding, recon);
+    } else {
+      Exec<__nv_bfloat16> E{P, (char*)workspace, params, nullptr, nullptr, nullptr, st, x};
+      E.pack_weights();
+      E.nb_forward(eps, seed, offset, rng_state, eps_out, mu, logvar, encoding, recon);
+    }
+    return check_launches("mmvae_forward");
+  }
   if (!x || !params || !mu || !encoding || !recon) return fail(MMVAE_ERR_BAD_ARG, "x/params/mu/encoding/recon must be non-NULL");
   if (d->require_rsample && !logvar) return fail(MMVAE_ERR_BAD_ARG, "logvar must be non-NULL when require_rsample");
   if (!bn_buffers) return fail(MMVAE_ERR_BAD_ARG, "bn_buffers must be non-NULL");
@@ -682,6 +796,24 @@ int mmvae_forward(const mmvae_desc* d, const float* x, const float* params, floa
 int mmvae_decode(const mmvae_desc* d, const float* encoding, const float* params, float* bn_buffers,
                  int64_t* bn_counters, void* workspace, size_t workspace_bytes, float* recon, void* stream) {
   MMVAE_COMMON_CHECKS();
+  if (P.d.arch == MMVAE_ARCH_NOTEBOOK) {
+    if (!encoding || !params || !recon) return fail(MMVAE_ERR_BAD_ARG, "encoding/params/recon must be non-NULL");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    // encoding arrives as fp32 NCHW [N,z,h,h]; the decoder reads NHWC storage: reuse rsample with eps = 0 semantics is
+    // not possible without mu, so transpose through the export kernel's inverse -- a 1-pixel-per-thread copy
+    const int hw = P.nb.latent_hw * P.nb.latent_hw;
+    if (P.d.precision == MMVAE_PREC_FP32) {
+      Exec<float> E{P, (char*)workspace, params, nullptr, nullptr, nullptr, st, nullptr};
+      launch_nb_import_nchw<float>(encoding, E.at<float>(P.acts[P.nb.a_z].off), P.d.batch, hw, P.d.z_dim, st);
+      E.nb_decode(recon);
+    } else {
+      Exec<__nv_bfloat16> E{P, (char*)workspace, params, nullptr, nullptr, nullptr, st, nullptr};
+      E.pack_weights();
+      launch_nb_import_nchw<__nv_bfloat16>(encoding, E.at<__nv_bfloat16>(P.acts[P.nb.a_z].off), P.d.batch, hw, P.d.z_dim, st);
+      E.nb_decode(recon);
+    }
+    return check_launches("mmvae_decode");
+  }
   if (!encoding || !params || !recon || !bn_buffers) return fail(MMVAE_ERR_BAD_ARG, "encoding/params/bn_buffers/recon must be non-NULL");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const long long nz = (long long)P.d.batch * P.d.z_dim;
@@ -706,6 +838,7 @@ int mmvae_backward(const mmvae_desc* d, const float* x, const float* params, voi
                    size_t workspace_bytes, const float* d_mu, const float* d_logvar, const float* d_encoding,
                    const float* d_recon, float* grads, int32_t phases, void* stream) {
   MMVAE_COMMON_CHECKS();
+  if (P.d.arch != MMVAE_ARCH_RESNET) return fail(MMVAE_ERR_BAD_DESC, "mmvae_backward: use mmvae_nb_loss_backward for the notebook variant");
   if (!x || !params || !grads) return fail(MMVAE_ERR_BAD_ARG, "x/params/grads must be non-NULL");
   if (phases <= 0 || phases > MMVAE_BWD_ALL) return fail(MMVAE_ERR_BAD_ARG, "phases must be a non-empty MMVAE_BWD_* mask");
   if (!d->training) return fail(MMVAE_ERR_BAD_DESC, "mmvae_backward needs a training-mode forward (batch statistics)");
@@ -721,11 +854,29 @@ int mmvae_backward(const mmvae_desc* d, const float* x, const float* params, voi
   return check_launches("mmvae_backward");
 }
 
+int mmvae_nb_loss_backward(const mmvae_desc* d, const float* x, const int64_t* target, const float* params, void* workspace,
+                           size_t workspace_bytes, float kl_weight, float* out, float* grads, void* stream) {
+  MMVAE_COMMON_CHECKS();
+  if (P.d.arch != MMVAE_ARCH_NOTEBOOK) return fail(MMVAE_ERR_BAD_DESC, "mmvae_nb_loss_backward needs arch = MMVAE_ARCH_NOTEBOOK");
+  if (!x || !target || !params || !out || !grads) return fail(MMVAE_ERR_BAD_ARG, "x/target/params/out/grads must be non-NULL");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (P.d.precision == MMVAE_PREC_FP32) {
+    Exec<float> E{P, (char*)workspace, params, grads, nullptr, nullptr, st, x};
+    E.nb_loss_backward(reinterpret_cast<const long long*>(target), kl_weight, out);
+  } else {
+    Exec<__nv_bfloat16> E{P, (char*)workspace, params, grads, nullptr, nullptr, st, x};
+    if (!(P.d.flags & MMVAE_FLAG_FORCE_SIMT) && !getenv("MMVAE_NO_AUX")) E.aux = aux_pool();
+    E.nb_loss_backward(reinterpret_cast<const long long*>(target), kl_weight, out);
+  }
+  return check_launches("mmvae_nb_loss_backward");
+}
+
 int mmvae_backward_range(const mmvae_desc* d, int32_t phase, int64_t* begin, int64_t* end) {
   Plan P;
   if (!P.build(d)) return fail(MMVAE_ERR_BAD_DESC, "%s", P.err.c_str());
   if (phase != MMVAE_BWD_DECODER && phase != MMVAE_BWD_ENC_DEEP && phase != MMVAE_BWD_ENC_SHALLOW)
     return fail(MMVAE_ERR_BAD_ARG, "phase must be a single MMVAE_BWD_* value");
+  if (P.d.arch != MMVAE_ARCH_RESNET) return fail(MMVAE_ERR_BAD_DESC, "mmvae_backward_range: model.py VAE only");
   int64_t b, e;
   Exec<float>::phase_range(P, phase, b, e);
   if (begin) *begin = b;

@@ -117,6 +117,8 @@ __global__ void __launch_bounds__(kThreads) gconv_simt_kernel(const __grid_const
       if (valid && co < p.Co) {
         val = acc[i][j];
         if (p.bias) val += p.bias[co];
+        if (p.act) val = act_apply(p.act, val);
+        if (p.dact) val *= act_deriv(p.dact_kind, to_f(reinterpret_cast<const T*>(p.dact)[base + co]));
         if (p.accumulate) val += to_f(out[base + co]);
         T tv = from_f<T>(val);
         out[base + co] = tv;

@@ -60,7 +60,8 @@ __device__ __forceinline__ void decode_tile(const GConvParams& p, int t, int& mt
 
 // kBwd: data-gradient instantiation whose epilogue also masks the gradient with the consumer's ReLU and reduces the
 // consumer's BatchNorm-backward sums (BnBwdFused) -- more live registers, so two CTAs per SM instead of three
-template <int kBN, bool kBwd>
+// kAct: BatchNorm-free networks (notebook variant): out = act(acc + bias) / out = acc * act'(dact) in the epilogue
+template <int kBN, bool kBwd, bool kAct = false>
 __global__ void __launch_bounds__(kTcThreads, kBwd ? 2 : 3) gconv_tc_kernel(const __grid_constant__ GConvParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long full[kMaxStages], empty[kMaxStages], tfull[2], tempty[2];
@@ -331,6 +332,15 @@ __global__ void __launch_bounds__(kTcThreads, kBwd ? 2 : 3) gconv_tc_kernel(cons
 #pragma unroll
           for (int e = 0; e < 16; ++e) if (co0 + e < p.Co) v[e] += __ldg(p.bias + co0 + e);
         }
+        if constexpr (kAct) {
+          if (p.act == ACT_RELU) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.f);
+          } else if (p.act == ACT_ELU) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = v[e] > 0.f ? v[e] : expm1f(v[e]);
+          }
+        }
         float t1[kBwd ? 16 : 1], t2[kBwd ? 16 : 1];      // kBwd: g * xhat(y), g * xhat(y2)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -341,6 +351,14 @@ __global__ void __launch_bounds__(kTcThreads, kBwd ? 2 : 3) gconv_tc_kernel(cons
           }
           if (valid && co < p.Co) {
             uint4* dst = reinterpret_cast<uint4*>(out + obase + co);
+            if constexpr (kAct) {
+              if (p.dact) {
+                const uint4 ar = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.dact) + obase + co));
+                const __nv_bfloat16* ab = reinterpret_cast<const __nv_bfloat16*>(&ar);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[h * 8 + e] *= act_deriv(p.dact_kind, __bfloat162float(ab[e]));
+              }
+            }
             if (p.accumulate) {
               uint4 old = *dst;
               const __nv_bfloat16* o = reinterpret_cast<const __nv_bfloat16*>(&old);
@@ -862,6 +880,10 @@ StatLayout launch_gconv_tc(const GConvParams& p0, cudaStream_t st) {
     cudaFuncSetAttribute(gconv_tc_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(gconv_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(gconv_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(gconv_tc_kernel<16, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(gconv_tc_kernel<32, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(gconv_tc_kernel<64, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(gconv_tc_kernel<128, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_done = true;
   }
   const int per_sm = min(gconv_per_sm(), bwd ? 2 : (smem <= 72 * 1024 ? 3 : 2));
@@ -869,7 +891,14 @@ StatLayout launch_gconv_tc(const GConvParams& p0, cudaStream_t st) {
   p.trace = debug_trace_buffer();
   { static int fl = [] { const char* e = getenv("MMVAE_TC_FLAGS"); return e ? atoi(e) : 0; }(); p.tc_flags = fl; }
   count_launch();
-  if (bwd) {
+  if (p.act || p.dact) {
+    switch (bn) {
+      case 16: launch_pdl(gconv_tc_kernel<16, false, true>, grid, kTcThreads, smem, st, p); break;
+      case 32: launch_pdl(gconv_tc_kernel<32, false, true>, grid, kTcThreads, smem, st, p); break;
+      case 64: launch_pdl(gconv_tc_kernel<64, false, true>, grid, kTcThreads, smem, st, p); break;
+      default: launch_pdl(gconv_tc_kernel<128, false, true>, grid, kTcThreads, smem, st, p); break;
+    }
+  } else if (bwd) {
     switch (bn) {
       case 16: launch_pdl(gconv_tc_kernel<16, true>, grid, kTcThreads, smem, st, p); break;
       case 32: launch_pdl(gconv_tc_kernel<32, true>, grid, kTcThreads, smem, st, p); break;

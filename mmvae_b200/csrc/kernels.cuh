@@ -83,6 +83,21 @@ struct BnBwdFused {
   double inv_rows;
 };
 
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_ELU = 2 };
+#ifdef __CUDACC__
+__device__ __forceinline__ float act_apply(int kind, float v) {
+  if (kind == ACT_RELU) return fmaxf(v, 0.f);
+  if (kind == ACT_ELU) return v > 0.f ? v : expm1f(v);
+  return v;
+}
+// derivative of the activation expressed through its OUTPUT a: relu' = [a > 0]; elu' = a > 0 ? 1 : a + 1 (= e^x)
+__device__ __forceinline__ float act_deriv(int kind, float a) {
+  if (kind == ACT_RELU) return a > 0.f ? 1.f : 0.f;
+  if (kind == ACT_ELU) return a > 0.f ? 1.f : a + 1.f;
+  return 1.f;
+}
+#endif
+
 // Opaque copy of a CUtensorMap (TMA descriptor); lives inside the __grid_constant__ kernel parameter.
 struct alignas(64) TmaDesc { unsigned long long v[16]; };
 
@@ -116,6 +131,11 @@ struct GConvParams {
   int accumulate;              // out += result
   int in_nchw_f32;             // network input x: fp32 NCHW
   int conv_class;              // 1: ConvTranspose2d k4 s2 p1 forward, 2: its data gradient (slab_tc.cu candidates), else 0
+  // BatchNorm-free networks (the notebook variant, nb.cu): activation fused into the epilogue, out = act(acc + bias),
+  // and, for a data gradient, the derivative of the PRODUCER's activation: out = acc * act'(dact[same index])
+  int act;                     // ACT_NONE / ACT_RELU / ACT_ELU
+  int dact_kind;               // activation whose output `dact` is
+  const void* dact;            // stored activation output (same shape / type as out) or nullptr
   // tcgen05 path: pre-packed bf16 weight tiles [variant][k-chunk of 64][co_pad rows][128 B, swizzled]
   const void* wpack;           // nullptr: no packed weights (SIMT only)
   int wpack_var_stride;        // bytes between variants
@@ -309,6 +329,44 @@ void launch_prepare_input(const unsigned char* labels, long long n, float mean, 
 void launch_philox_normal(unsigned long long seed, unsigned long long offset, long long n, float* out, cudaStream_t st);
 void launch_adam(long long n, float* p, const float* g, float* m, float* v, float lr, float b1, float b2,
                  float eps, float wd, long long step, float gscale, cudaStream_t st);
+
+// ---- notebook-variant VAE: BatchNorm-free pointwise / loss kernels (nb.cu) ----
+// nearest-neighbour upsample by f: out[n, f*h+a, f*w+b, c] = in[n,h,w,c]            (vae-kl.ipynb:152-155)
+template <typename T> void launch_nb_upsample(const T* in, T* out, int N, int H, int W, int C, int f, cudaStream_t st);
+// its adjoint fused with the activation derivative of the tensor that was upsampled:
+// dy[n,h,w,c] = act'(a[n,h,w,c]) * sum_{a,b<f} dup[n, f*h+a, f*w+b, c]                 (a == nullptr: no activation)
+template <typename T> void launch_nb_upsample_bwd(const T* dup, const T* a, int act_kind, T* dy, int N, int H, int W, int C, int f,
+                                                  cudaStream_t st);
+struct NbSampleArgs {
+  const void* mu_y; const void* lv_y;   // head conv outputs NHWC [N,h,w,z], storage type
+  const float* eps;                     // [N,z,h,w] fp32 or nullptr -> Philox
+  unsigned long long seed, offset; const unsigned long long* rng_dev;
+  float* eps_keep;                      // [N,z,h,w] fp32 workspace copy for the backward
+  float* mu_out; float* lv_out; float* enc_out; float* eps_out;   // fp32 NCHW [N,z,h,w] user outputs (any may be nullptr)
+  void* z_act;                          // NHWC [N,h,w,z] storage type: decoder input
+  int N, hw, z;
+};
+template <typename T> void launch_nb_rsample(const NbSampleArgs& a, cudaStream_t st);
+struct NbSampleBwdArgs {
+  const void* dz;                       // NHWC [N,h,w,z] storage type: gradient wrt the decoder input
+  const void* mu_y; const void* lv_y; const float* eps_keep;
+  void* d_mu_y; void* d_lv_y;           // NHWC storage type
+  double* kl_acc;                       // += sum KL terms (unscaled)
+  float klw_over_n;                     // kl_weight / N
+  int N, hw, z;
+};
+template <typename T> void launch_nb_rsample_bwd(const NbSampleBwdArgs& a, cudaStream_t st);
+// softmax cross-entropy over NHWC logits [rows][C] with int64 targets: dlogits = (softmax - onehot) * scale,
+// ce_acc += sum_rows (logsumexp - logit[target]), dbias[c] += sum_rows dlogits[row][c]
+template <typename T> void launch_nb_ce(const T* logits, const long long* target, T* dlogits, long long rows, int C, float scale,
+                                        double* ce_acc, float* dbias, cudaStream_t st);
+// dbias[c] += sum_rows dy[row][c]
+template <typename T> void launch_nb_colsum(const T* dy, long long rows, int C, float* dbias, cudaStream_t st);
+// NHWC storage -> fp32 NCHW
+template <typename T> void launch_nb_export_nchw(const T* in, float* out, int N, int HW, int C, cudaStream_t st);
+template <typename T> void launch_nb_import_nchw(const float* in, T* out, int N, int HW, int C, cudaStream_t st);
+// out[0] = ce/N + klw*kl/N, out[1] = ce/N, out[2] = kl/N from the fp64 accumulators acc[0] (ce), acc[1] (kl)
+void launch_nb_loss_finalize(const double* acc, float inv_n, float klw, float* out, cudaStream_t st);
 
 // ---- device helpers ----
 __device__ __forceinline__ float to_f(float v) { return v; }

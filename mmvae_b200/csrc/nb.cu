@@ -1,0 +1,392 @@
+// nb.cu -- pointwise / loss kernels of the notebook variant of the VAE (vae-kl.ipynb:119-166, loop body :210-233;
+// SURVEY.md 8(a) row 12, BASELINE configs[4]).  That network has no BatchNorm: bias + ReLU / ELU live in the
+// convolution epilogues (GConvParams::act / dact), what remains here is HBM-bound streaming work:
+//   nearest upsample (vae-kl.ipynb:152-155) and its adjoint fused with the activation derivative,
+//   rsample (vae-kl.ipynb:144-146) and its adjoint fused with the closed-form KL gradient,
+//   softmax cross-entropy over the 256 grey levels (vae-kl.ipynb:226) fused with d logits and the last bias gradient.
+#include "kernels.cuh"
+
+namespace mmvae {
+
+namespace {
+
+template <typename T> struct Vec;                       // 16-byte vector of storage elements
+template <> struct Vec<float> { static constexpr int n = 4; };
+template <> struct Vec<__nv_bfloat16> { static constexpr int n = 8; };
+
+template <typename T>
+__device__ __forceinline__ void load_vec(const T* p, float* v) {
+  const uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
+  if constexpr (sizeof(T) == 4) {
+    v[0] = __uint_as_float(r.x); v[1] = __uint_as_float(r.y); v[2] = __uint_as_float(r.z); v[3] = __uint_as_float(r.w);
+  } else {
+    const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(&r);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = __bfloat162float(b[e]);
+  }
+}
+template <typename T>
+__device__ __forceinline__ void store_vec(T* p, const float* v) {
+  uint4 r;
+  if constexpr (sizeof(T) == 4) {
+    r.x = __float_as_uint(v[0]); r.y = __float_as_uint(v[1]); r.z = __float_as_uint(v[2]); r.w = __float_as_uint(v[3]);
+  } else {
+    __nv_bfloat16* b = reinterpret_cast<__nv_bfloat16*>(&r);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) b[e] = __float2bfloat16_rn(v[e]);
+  }
+  *reinterpret_cast<uint4*>(p) = r;
+}
+
+// one thread = one 16-byte channel vector of one OUTPUT pixel
+template <typename T>
+__global__ void __launch_bounds__(256) nb_upsample_kernel(const T* __restrict__ in, T* __restrict__ out, int H, int W, int C,
+                                                         int f, long long total) {
+  constexpr int V = Vec<T>::n;
+  pdl_wait();
+  pdl_trigger();
+  const int cv = C / V;
+  const int Wo = W * f, Ho = H * f;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
+    const int c = (int)(i % cv);
+    long long pix = i / cv;
+    const int ox = (int)(pix % Wo); pix /= Wo;
+    const int oy = (int)(pix % Ho);
+    const long long n = pix / Ho;
+    const uint4 r = __ldg(reinterpret_cast<const uint4*>(in + ((n * H + oy / f) * W + ox / f) * C + c * V));
+    *reinterpret_cast<uint4*>(out + i * V) = r;
+  }
+}
+
+// one thread = one 16-byte channel vector of one INPUT-resolution pixel: sums its f x f block
+template <typename T>
+__global__ void __launch_bounds__(256) nb_upsample_bwd_kernel(const T* __restrict__ dup, const T* __restrict__ a, int act_kind,
+                                                             T* __restrict__ dy, int H, int W, int C, int f, long long total) {
+  constexpr int V = Vec<T>::n;
+  pdl_wait();
+  pdl_trigger();
+  const int cv = C / V;
+  const int Wo = W * f, Ho = H * f;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
+    const int c = (int)(i % cv);
+    long long pix = i / cv;
+    const int x = (int)(pix % W); pix /= W;
+    const int y = (int)(pix % H);
+    const long long n = pix / H;
+    float s[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) s[e] = 0.f;
+    for (int dy_ = 0; dy_ < f; ++dy_)
+      for (int dx_ = 0; dx_ < f; ++dx_) {
+        float v[V];
+        load_vec<T>(dup + ((n * Ho + y * f + dy_) * Wo + x * f + dx_) * C + c * V, v);
+#pragma unroll
+        for (int e = 0; e < V; ++e) s[e] += v[e];
+      }
+    if (a) {
+      float av[V];
+      load_vec<T>(a + i * V, av);
+#pragma unroll
+      for (int e = 0; e < V; ++e) s[e] *= act_deriv(act_kind, av[e]);
+    }
+    store_vec<T>(dy + i * V, s);
+  }
+}
+
+// thread = one latent element in NCHW order (the order of the user-visible tensors and of the Philox stream)
+template <typename T>
+__global__ void __launch_bounds__(256) nb_rsample_kernel(const NbSampleArgs a) {
+  pdl_wait();
+  pdl_trigger();
+  const long long total = (long long)a.N * a.z * a.hw;
+  unsigned long long seed = a.seed, offset = a.offset;
+  if (a.rng_dev) { seed = a.rng_dev[0]; offset = a.rng_dev[1]; }
+  const T* mu_y = reinterpret_cast<const T*>(a.mu_y);
+  const T* lv_y = reinterpret_cast<const T*>(a.lv_y);
+  T* z_act = reinterpret_cast<T*>(a.z_act);
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
+    const int p = (int)(i % a.hw);
+    const long long t = i / a.hw;
+    const int c = (int)(t % a.z);
+    const long long n = t / a.z;
+    const long long j = (n * a.hw + p) * a.z + c;            // NHWC index
+    const float mu = to_f(mu_y[j]), lv = to_f(lv_y[j]);
+    const float eps = a.eps ? a.eps[i] : philox_normal_at(seed, offset, i);
+    const float enc = fmaf(eps, expf(0.5f * lv), mu);
+    a.eps_keep[i] = eps;
+    z_act[j] = from_f<T>(enc);
+    if (a.mu_out) a.mu_out[i] = mu;
+    if (a.lv_out) a.lv_out[i] = lv;
+    if (a.enc_out) a.enc_out[i] = enc;
+    if (a.eps_out) a.eps_out[i] = eps;
+  }
+}
+
+// d mu = dz + klw/N * mu;  d logvar = dz * 0.5 * eps * exp(0.5 logvar) + klw/N * 0.5 * (exp(logvar) - 1)
+// KL = -0.5 * sum(logvar - exp(logvar) - mu^2 + 1)                                     (vae-kl.ipynb:119-120, 227)
+template <typename T>
+__global__ void __launch_bounds__(256) nb_rsample_bwd_kernel(const NbSampleBwdArgs a) {
+  pdl_wait();
+  pdl_trigger();
+  const long long total = (long long)a.N * a.z * a.hw;
+  const T* dz = reinterpret_cast<const T*>(a.dz);
+  const T* mu_y = reinterpret_cast<const T*>(a.mu_y);
+  const T* lv_y = reinterpret_cast<const T*>(a.lv_y);
+  T* dmu = reinterpret_cast<T*>(a.d_mu_y);
+  T* dlv = reinterpret_cast<T*>(a.d_lv_y);
+  float kl = 0.f;
+  for (long long j = blockIdx.x * 256LL + threadIdx.x; j < total; j += gridDim.x * 256LL) {
+    // j = NHWC index; the eps copy is NCHW
+    const int c = (int)(j % a.z);
+    const long long t = j / a.z;
+    const int p = (int)(t % a.hw);
+    const long long n = t / a.hw;
+    const float eps = a.eps_keep[(n * a.z + c) * a.hw + p];
+    const float mu = to_f(mu_y[j]), lv = to_f(lv_y[j]);
+    const float g = dz ? to_f(dz[j]) : 0.f;
+    const float ev = expf(lv);
+    dmu[j] = from_f<T>(g + a.klw_over_n * mu);
+    dlv[j] = from_f<T>(g * 0.5f * eps * expf(0.5f * lv) + a.klw_over_n * 0.5f * (ev - 1.f));
+    kl += -0.5f * (lv - ev - mu * mu + 1.f);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) kl += __shfl_xor_sync(0xffffffffu, kl, o);
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = kl;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    atomicAdd(a.kl_acc, (double)s);
+  }
+}
+
+// Softmax cross-entropy, one warp per pixel row of C <= 256 classes: lane l owns classes [8l, 8l+8).
+// Reads the logits once, writes d logits once; the per-class column sums (the bias gradient of the last conv) stay in
+// registers over all rows of the warp and leave through shared memory + one atomic per class and CTA.
+template <typename T>
+__global__ void __launch_bounds__(256) nb_ce_kernel(const T* __restrict__ logits, const long long* __restrict__ target,
+                                                   T* __restrict__ dlogits, long long rows, int C, float scale,
+                                                   double* ce_acc, float* dbias) {
+  __shared__ float bsum[8][256];
+  __shared__ float lred[8];
+  pdl_wait();
+  pdl_trigger();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = lane * 8;
+  const bool on = c0 < C;
+  float db[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) db[e] = 0.f;
+  float loss = 0.f;
+  const long long wstride = (long long)gridDim.x * 8;
+  for (long long r = (long long)blockIdx.x * 8 + warp; r < rows; r += wstride) {
+    float v[8];
+    if (on) {
+      if constexpr (sizeof(T) == 2) {
+        load_vec<T>(logits + r * C + c0, v);
+      } else {
+        load_vec<T>(logits + r * C + c0, v);
+        load_vec<T>(logits + r * C + c0 + 4, v + 4);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = -INFINITY;
+    }
+    float mx = v[0];
+#pragma unroll
+    for (int e = 1; e < 8; ++e) mx = fmaxf(mx, v[e]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float ex[8], s = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { ex[e] = on ? expf(v[e] - mx) : 0.f; s += ex[e]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const int tg = (int)__ldg(target + r);
+    const float inv = 1.f / s;
+    // the target's logit lives in lane tg / 8
+    float tv = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) if (c0 + e == tg) tv = v[e];
+    tv = __shfl_sync(0xffffffffu, tv, tg >> 3);
+    if (lane == 0) loss += (mx + logf(s)) - tv;
+    if (on) {
+      float g[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        g[e] = (ex[e] * inv - (c0 + e == tg ? 1.f : 0.f)) * scale;
+        if constexpr (sizeof(T) == 2) g[e] = __bfloat162float(__float2bfloat16_rn(g[e]));
+        db[e] += g[e];
+      }
+      if constexpr (sizeof(T) == 2) {
+        store_vec<T>(dlogits + r * C + c0, g);
+      } else {
+        store_vec<T>(dlogits + r * C + c0, g);
+        store_vec<T>(dlogits + r * C + c0 + 4, g + 4);
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) bsum[warp][c0 + e] = db[e];
+  if (lane == 0) lred[warp] = loss;
+  __syncthreads();
+  if (dbias) {
+    const int c = threadIdx.x;
+    if (c < C) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += bsum[w][c];
+      atomicAdd(dbias + c, s);
+    }
+  }
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += lred[w];
+    atomicAdd(ce_acc, (double)s);
+  }
+}
+
+// column sums of a [rows][C] tensor, C <= 256 and C % 8 == 0: thread (c/8 slot, row lane) accumulates in registers
+template <typename T>
+__global__ void __launch_bounds__(256) nb_colsum_kernel(const T* __restrict__ dy, long long rows, int C, float* dbias) {
+  __shared__ float part[256][9];
+  pdl_wait();
+  pdl_trigger();
+  const int cv = C / 8;                       // 16-byte (bf16) / 32-byte (fp32) channel groups per row
+  const int slot = threadIdx.x % cv, rl = threadIdx.x / cv, rpb = 256 / cv;
+  float s[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s[e] = 0.f;
+  if (rl < rpb) {
+    for (long long r = (long long)blockIdx.x * rpb + rl; r < rows; r += (long long)gridDim.x * rpb) {
+      float v[8];
+      if constexpr (sizeof(T) == 2) {
+        load_vec<T>(dy + r * C + slot * 8, v);
+      } else {
+        load_vec<T>(dy + r * C + slot * 8, v);
+        load_vec<T>(dy + r * C + slot * 8 + 4, v + 4);
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s[e] += v[e];
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) part[threadIdx.x][e] = s[e];
+  __syncthreads();
+  if (threadIdx.x < C) {
+    const int c = threadIdx.x, sl = c / 8, e = c % 8;
+    float t = 0.f;
+    for (int q = 0; q < rpb; ++q) t += part[q * cv + sl][e];
+    atomicAdd(dbias + c, t);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) nb_export_nchw_kernel(const T* __restrict__ in, float* __restrict__ out, int HW, int C,
+                                                            long long total) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
+    const int p = (int)(i % HW);
+    const long long t = i / HW;
+    const int c = (int)(t % C);
+    const long long n = t / C;
+    out[i] = to_f(in[(n * HW + p) * C + c]);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) nb_import_nchw_kernel(const float* __restrict__ in, T* __restrict__ out, int HW, int C,
+                                                            long long total) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
+    const int p = (int)(i % HW);
+    const long long t = i / HW;
+    const int c = (int)(t % C);
+    const long long n = t / C;
+    out[(n * HW + p) * C + c] = from_f<T>(in[i]);
+  }
+}
+
+__global__ void nb_loss_finalize_kernel(const double* acc, float inv_n, float klw, float* out) {
+  pdl_wait();
+  pdl_trigger();
+  const double ce = acc[0] * (double)inv_n, kl = acc[1] * (double)inv_n;
+  out[0] = (float)(ce + (double)klw * kl);
+  out[1] = (float)ce;
+  out[2] = (float)kl;
+}
+
+inline int grid_for(long long work_items, int cap = 148 * 16) {
+  long long b = (work_items + 255) / 256;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace
+
+template <typename T>
+void launch_nb_upsample(const T* in, T* out, int N, int H, int W, int C, int f, cudaStream_t st) {
+  const long long total = (long long)N * H * f * W * f * (C / Vec<T>::n);
+  count_launch();
+  launch_pdl(nb_upsample_kernel<T>, dim3(grid_for(total)), dim3(256), 0, st, in, out, H, W, C, f, total);
+}
+template <typename T>
+void launch_nb_upsample_bwd(const T* dup, const T* a, int act_kind, T* dy, int N, int H, int W, int C, int f, cudaStream_t st) {
+  const long long total = (long long)N * H * W * (C / Vec<T>::n);
+  count_launch();
+  launch_pdl(nb_upsample_bwd_kernel<T>, dim3(grid_for(total)), dim3(256), 0, st, dup, a, act_kind, dy, H, W, C, f, total);
+}
+template <typename T>
+void launch_nb_rsample(const NbSampleArgs& a, cudaStream_t st) {
+  count_launch();
+  launch_pdl(nb_rsample_kernel<T>, dim3(grid_for((long long)a.N * a.z * a.hw)), dim3(256), 0, st, a);
+}
+template <typename T>
+void launch_nb_rsample_bwd(const NbSampleBwdArgs& a, cudaStream_t st) {
+  count_launch();
+  launch_pdl(nb_rsample_bwd_kernel<T>, dim3(grid_for((long long)a.N * a.z * a.hw, 296)), dim3(256), 0, st, a);
+}
+template <typename T>
+void launch_nb_ce(const T* logits, const long long* target, T* dlogits, long long rows, int C, float scale, double* ce_acc,
+                  float* dbias, cudaStream_t st) {
+  long long b = (rows + 7) / 8;
+  const int grid = (int)(b < 1 ? 1 : (b > 148 * 8 ? 148 * 8 : b));
+  count_launch();
+  launch_pdl(nb_ce_kernel<T>, dim3(grid), dim3(256), 0, st, logits, target, dlogits, rows, C, scale, ce_acc, dbias);
+}
+template <typename T>
+void launch_nb_colsum(const T* dy, long long rows, int C, float* dbias, cudaStream_t st) {
+  const int rpb = 256 / (C / 8);
+  long long b = (rows + rpb - 1) / rpb;
+  const int grid = (int)(b < 1 ? 1 : (b > 148 * 2 ? 148 * 2 : b));
+  count_launch();
+  launch_pdl(nb_colsum_kernel<T>, dim3(grid), dim3(256), 0, st, dy, rows, C, dbias);
+}
+template <typename T>
+void launch_nb_export_nchw(const T* in, float* out, int N, int HW, int C, cudaStream_t st) {
+  const long long total = (long long)N * HW * C;
+  count_launch();
+  nb_export_nchw_kernel<T><<<grid_for(total, 148 * 32), 256, 0, st>>>(in, out, HW, C, total);
+}
+template <typename T>
+void launch_nb_import_nchw(const float* in, T* out, int N, int HW, int C, cudaStream_t st) {
+  const long long total = (long long)N * HW * C;
+  count_launch();
+  nb_import_nchw_kernel<T><<<grid_for(total, 148 * 32), 256, 0, st>>>(in, out, HW, C, total);
+}
+void launch_nb_loss_finalize(const double* acc, float inv_n, float klw, float* out, cudaStream_t st) {
+  count_launch();
+  launch_pdl(nb_loss_finalize_kernel, dim3(1), dim3(1), 0, st, acc, inv_n, klw, out);
+}
+
+#define NB_INST(T)                                                                                                          \
+  template void launch_nb_upsample<T>(const T*, T*, int, int, int, int, int, cudaStream_t);                                 \
+  template void launch_nb_upsample_bwd<T>(const T*, const T*, int, T*, int, int, int, int, int, cudaStream_t);              \
+  template void launch_nb_rsample<T>(const NbSampleArgs&, cudaStream_t);                                                    \
+  template void launch_nb_rsample_bwd<T>(const NbSampleBwdArgs&, cudaStream_t);                                             \
+  template void launch_nb_ce<T>(const T*, const long long*, T*, long long, int, float, double*, float*, cudaStream_t);      \
+  template void launch_nb_colsum<T>(const T*, long long, int, float*, cudaStream_t);                                        \
+  template void launch_nb_export_nchw<T>(const T*, float*, int, int, int, cudaStream_t);                                    \
+  template void launch_nb_import_nchw<T>(const float*, T*, int, int, int, cudaStream_t);
+NB_INST(float)
+NB_INST(__nv_bfloat16)
+
+}  // namespace mmvae

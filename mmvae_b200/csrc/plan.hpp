@@ -75,6 +75,19 @@ struct BlockT {            // BasicBlock or DeconvBottleneck: main = c1 -> bn1 -
   int in;                  // activation index of the block input
 };
 
+// The notebook variant (MMVAE_ARCH_NOTEBOOK, vae-kl.ipynb:119-166): indices into Plan::convs / Plan::acts
+struct NbT {
+  int e[4] = {-1, -1, -1, -1};       // encoder.conv1..conv4 (ReLU)
+  int cmu = -1, clv = -1;            // encoder.conv_mu / conv_logvar
+  int dc[4] = {-1, -1, -1, -1};      // decoder.conv1..conv4 (ELU, ELU, ELU, none)
+  int a_z = -1;                      // sampled latent, NHWC [N,h,h,z]
+  int a_up[4] = {-1, -1, -1, -1};    // nearest-upsampled input of decoder.conv{k+1}
+  int up[4] = {2, 4, 2, 2};          // vae-kl.ipynb:152-155
+  size_t eps_off = 0;                // fp32 [N,z,h,h]: the rsample draw, kept for the backward
+  size_t acc_off = 0;                // fp64 [2]: sum CE, sum KL
+  int latent_hw = 0;                 // h
+};
+
 constexpr int kBwdBlocks = 592;   // grid of the BatchNorm-backward reduction (4 x 148 SMs)
 
 struct Plan {
@@ -99,6 +112,7 @@ struct Plan {
   size_t bnacc_off = 0, bnacc_bytes = 0;   // all BatchNorm accumulators + counters: one memset per forward
   size_t ws_bytes = 0;
   int64_t train_flops = 0;
+  NbT nb;
   std::string err;
 
   // ---- helpers ----
@@ -166,11 +180,88 @@ struct Plan {
     return int(convs.size()) - 1;
   }
 
+  // conv + bias without BatchNorm (notebook variant); parameters in the order (weight, bias)
+  int add_conv_nb(const std::string& name, int k, int s, int p, int Ci, int Co, int Hi, int in_act) {
+    ConvT_ c; c.name = name; c.kind = CONV; c.k = k; c.s = s; c.p = p; c.Ci = Ci; c.Co = Co;
+    c.Hi = c.Wi = Hi;
+    c.Ho = c.Wo = (Hi + 2 * p - k) / s + 1;
+    c.in = in_act;
+    c.w = add_param(name + ".weight", 4, Co, Ci, k, k);
+    c.bias = add_param(name + ".bias", 1, Co);
+    c.out = add_act(name, c.Ho, c.Wo, Co);
+    const int64_t macs = int64_t(d.batch) * c.Ho * c.Wo * Co * int64_t(Ci) * k * k;
+    train_flops += 2 * macs * (in_act == -1 ? 2 : 3);
+    convs.push_back(c);
+    return int(convs.size()) - 1;
+  }
+
+  // packed bf16 weight tiles of the tcgen05 path, both directions
+  void plan_packing() {
+    if (d.precision != MMVAE_PREC_BF16 || (d.flags & MMVAE_FLAG_FORCE_SIMT)) return;
+    for (auto& c : convs) {
+      if (c.Ci % 8 != 0 || c.Co % 8 != 0) continue;          // stem (Ci = in_channels) / tail (Co = out_channels): SIMT
+      ConvGeom g = c.geom();
+      for (int dir = 0; dir < 2; ++dir) {
+        if (dir == DIR_DGRAD && (c.in < 0 || !d.training)) continue;
+        int op_ci, op_co, sci, sco;
+        geom_strides(g, dir, op_ci, op_co, sci, sco);
+        const int nv = geom_nvar(g, dir);
+        int mc = 1;
+        for (int v = 0; v < nv; ++v) mc = std::max(mc, (geom_ntaps(g, dir, v) * op_ci + 63) / 64);
+        const int co_pad = (op_co + 15) & ~15;
+        c.wp_chunks[dir] = mc;
+        c.wp_off[dir] = bump(size_t(nv) * mc * co_pad * 128);
+      }
+    }
+  }
+
+  // vae-kl.ipynb:122-166
+  bool build_nb() {
+    if (d.in_channels != 1) { err = "notebook variant: in_channels must be 1"; return false; }
+    if (d.image_size != 64 && d.image_size != 128) { err = "notebook variant: image_size must be 64 or 128"; return false; }
+    if (d.out_channels % 8 != 0 || d.out_channels > 256) { err = "notebook variant: classes must be a multiple of 8, <= 256"; return false; }
+    if (d.z_dim % 8 != 0) { err = "notebook variant: z_dim must be a multiple of 8"; return false; }
+    d.training = 1;                                              // no BatchNorm: one mode
+    const int C = 32 * d.width, S = d.image_size, z = d.z_dim;
+    nb.e[0] = add_conv_nb("encoder.conv1", 5, 2, 2, 1, C, S, -1);
+    nb.e[1] = add_conv_nb("encoder.conv2", 5, 2, 1, C, C, convs[nb.e[0]].Ho, convs[nb.e[0]].out);
+    nb.e[2] = add_conv_nb("encoder.conv3", 3, 2, 1, C, C, convs[nb.e[1]].Ho, convs[nb.e[1]].out);
+    nb.e[3] = add_conv_nb("encoder.conv4", 3, 2, 1, C, C, convs[nb.e[2]].Ho, convs[nb.e[2]].out);
+    nb.cmu = add_conv_nb("encoder.conv_mu", 3, 2, 1, C, z, convs[nb.e[3]].Ho, convs[nb.e[3]].out);
+    nb.clv = add_conv_nb("encoder.conv_logvar", 3, 2, 1, C, z, convs[nb.e[3]].Ho, convs[nb.e[3]].out);
+    const int h = convs[nb.cmu].Ho;
+    nb.latent_hw = h;
+    nb.a_z = add_act("decoder.input", h, h, z);
+    int curC = z, curH = h;
+    const int couts[4] = {C, C, C, d.out_channels};
+    for (int i = 0; i < 4; ++i) {
+      const std::string nm = "decoder.conv" + std::to_string(i + 1);
+      curH *= nb.up[i];
+      nb.a_up[i] = add_act(nm + ".input", curH, curH, curC);
+      nb.dc[i] = add_conv_nb(nm, 3, 1, 1, curC, couts[i], curH, nb.a_up[i]);
+      curC = couts[i];
+    }
+    if (curH != S) { err = "notebook variant: decoder size mismatch"; return false; }
+    dec_size = S; crop = 0;
+    nb.eps_off = bump(sizeof(float) * size_t(d.batch) * z * h * h);
+    nb.acc_off = bump(sizeof(double) * 2);
+    plan_packing();
+    return true;
+  }
+
   bool build(const mmvae_desc* dd) {
     if (!dd) { err = "desc is NULL"; return false; }
     if (dd->struct_size != (int32_t)sizeof(mmvae_desc)) { err = "mmvae_desc.struct_size mismatch"; return false; }
     d = *dd;
     if (d.batch < 1) { err = "batch must be >= 1"; return false; }
+    if (d.arch != MMVAE_ARCH_RESNET && d.arch != MMVAE_ARCH_NOTEBOOK) { err = "unknown arch"; return false; }
+    if (d.arch == MMVAE_ARCH_NOTEBOOK) {
+      if (d.width < 1 || d.width > 8) { err = "width must be in [1,8]"; return false; }
+      if (d.z_dim < 1 || d.z_dim > 1024) { err = "z_dim must be in [1,1024]"; return false; }
+      if (d.precision != MMVAE_PREC_FP32 && d.precision != MMVAE_PREC_BF16) { err = "unknown precision"; return false; }
+      esz = (d.precision == MMVAE_PREC_BF16) ? 2 : 4;
+      return build_nb();
+    }
     if (d.in_channels < 1 || d.in_channels > 16) { err = "in_channels must be in [1,16]"; return false; }
     if (d.out_channels < 1 || d.out_channels > 256) { err = "out_channels must be in [1,256]"; return false; }
     if (d.z_dim < 1 || d.z_dim > 1024) { err = "z_dim must be in [1,1024]"; return false; }
@@ -245,24 +336,7 @@ struct Plan {
       for (auto& b : bns) { b.acc_off += bnacc_off; b.cnt_off += bnacc_off; }
     }
 
-    // ---------------- packed weights of the tcgen05 path ----------------
-    if (d.precision == MMVAE_PREC_BF16 && !(d.flags & MMVAE_FLAG_FORCE_SIMT)) {
-      for (auto& c : convs) {
-        if (c.Ci % 8 != 0 || c.Co % 8 != 0) continue;          // stem (Ci = in_channels) / tail (Co = out_channels): SIMT
-        ConvGeom g = c.geom();
-        for (int dir = 0; dir < 2; ++dir) {
-          if (dir == DIR_DGRAD && (c.in < 0 || !d.training)) continue;
-          int op_ci, op_co, sci, sco;
-          geom_strides(g, dir, op_ci, op_co, sci, sco);
-          const int nv = geom_nvar(g, dir);
-          int mc = 1;
-          for (int v = 0; v < nv; ++v) mc = std::max(mc, (geom_ntaps(g, dir, v) * op_ci + 63) / 64);
-          const int co_pad = (op_co + 15) & ~15;
-          c.wp_chunks[dir] = mc;
-          c.wp_off[dir] = bump(size_t(nv) * mc * co_pad * 128);
-        }
-      }
-    }
+    plan_packing();
     return true;
   }
 

@@ -26,7 +26,7 @@ def test_exports_match_header(M):
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/mmvae.h but not exported"
     assert declared == set(M._lib.EXPORTS)
-    assert lib.mmvae_abi_version() == M._lib.ABI_VERSION == 2
+    assert lib.mmvae_abi_version() == M._lib.ABI_VERSION == 3
 
 
 def test_struct_sizes(M):

@@ -1,0 +1,114 @@
+"""GPU parity of the notebook variant (BASELINE configs[4]) through the C ABI:
+the CUDA path against fixtures generated from the live reference notebook and against the CPU oracle."""
+import pytest
+import torch
+
+import mmvae_b200 as M
+from oracle import nb_oracle as NB
+from nb_util import NB_CASES, NbGolden
+
+pytestmark = pytest.mark.gpu
+
+
+def build(cfg, st, precision, flags=0):
+    m = M.NotebookVAE(1, cfg.channels, cfg.z_dimensions, image_size=cfg.image_size, n_classes=cfg.n_classes,
+                      precision=precision)
+    m.kernel_flags = flags
+    r = m.load_state_dict(st, strict=True)
+    assert not r.missing_keys and not r.unexpected_keys
+    return m.cuda()
+
+
+def run(m, x, y, eps, klw, materialize=True):
+    mu, logvar, enc, recon = m(x.cuda(), eps=eps.cuda(), materialize=materialize)
+    out = m.loss_backward(y.cuda(), kl_weight=klw)
+    torch.cuda.synchronize()
+    grads = {n: p.grad.detach().cpu() for n, p in m.named_parameters()}
+    loss, pxz, kl = (float(v) for v in out.cpu())
+    return loss, pxz, kl, mu.cpu(), logvar.cpu(), enc.cpu(), None if recon is None else recon.cpu(), grads
+
+
+@pytest.mark.parametrize("case", NB_CASES)
+def test_fp32_mode_matches_notebook_fixture(case):
+    """fp32 validation mode: 1e-5 on the loss (north_star), 1e-4 on tensors and gradients (relative L2)."""
+    g = NbGolden(case)
+    m = build(g.cfg, g.state(), "fp32")
+    loss, pxz, kl, mu, logvar, enc, recon, grads = run(m, g.x, g.y, g.eps, g.kl_weight)
+    worst = g.check(loss, pxz, kl, mu, logvar, enc, recon, grads, tol_loss=1e-5, tol_t=1e-4, tol_g=1e-4)
+    print(case, "fp32 worst gradient rel-L2", worst)
+
+
+@pytest.mark.parametrize("case", NB_CASES)
+@pytest.mark.parametrize("flags", [0, M._lib.FLAG_FORCE_SIMT])
+def test_bf16_mode_within_tolerance(case, flags):
+    """bf16 product mode: 1e-2 on the loss; gradients against the fp64 oracle are bounded by the bf16-storage floor the
+    oracle reproduces (emulate_bf16): no tensor worse than 2x the emulated distance + 0.01, decoder tensors (where the
+    floor is ~3e-3) within the north_star 1e-2."""
+    g = NbGolden(case)
+    st = g.state()
+    m = build(g.cfg, st, "bf16", flags)
+    loss, pxz, kl, mu, logvar, enc, recon, grads = run(m, g.x, g.y, g.eps, g.kl_weight)
+    ref = NB.train_step(st, g.cfg, g.x, g.y, g.eps, kl_weight=g.kl_weight, dtype=torch.float64)
+    emu = NB.train_step(st, g.cfg, g.x, g.y, g.eps, kl_weight=g.kl_weight, dtype=torch.float64, emulate_bf16=True)
+    assert abs(loss - ref.loss) <= 1e-2 * abs(ref.loss)
+    assert abs(pxz - ref.pxz) <= 1e-2 * abs(ref.pxz)
+    assert abs(kl - ref.kl) <= 2e-2 * abs(ref.kl) + 1e-3
+    assert float((recon.double() - ref.logits).norm() / ref.logits.norm()) <= 1e-2
+    assert float((mu.double() - ref.mu).norm() / ref.mu.norm()) <= 1e-2
+    errs = []
+    for k, r in ref.grads.items():
+        d = float((grads[k].double() - r).norm() / r.norm())
+        floor = float((emu.grads[k] - r).norm() / r.norm())
+        bound = 1e-2 if k.startswith("decoder.") else 2 * floor + 0.01
+        if not d <= bound:
+            errs.append(f"{k}: {d:.3e} > {bound:.3e} (emulated floor {floor:.3e})")
+    assert not errs, "\n".join(errs)
+
+
+def test_tc_matches_simt_at_training_batch():
+    """tcgen05 kernels against the fp32-FMA SIMT kernels on identical bf16 storage at a batch that fills the GPU
+    (persistent multi-tile CTAs, TMA boxes): gradients agree to 5e-3 relative L2."""
+    cfg = NB.NbConfig(image_size=64)
+    st = NB.init_state(cfg, seed=1)
+    x, y = NB.synthetic_batch(cfg, 48, seed=7)
+    eps = torch.randn(48, cfg.z_dimensions, cfg.latent_hw, cfg.latent_hw, generator=torch.Generator().manual_seed(3))
+    a = run(build(cfg, st, "bf16", 0), x, y, eps, 1.0, materialize=False)
+    b = run(build(cfg, st, "bf16", M._lib.FLAG_FORCE_SIMT), x, y, eps, 1.0, materialize=False)
+    assert abs(a[0] - b[0]) <= 2e-3 * abs(b[0])
+    for k in a[7]:
+        d = float((a[7][k].double() - b[7][k].double()).norm() / b[7][k].double().norm())
+        assert d <= 5e-3 or k.startswith("encoder.conv1") and d <= 2e-2, (k, d)
+
+
+def test_philox_noise_and_decode():
+    cfg = NB.NbConfig(image_size=64)
+    st = NB.init_state(cfg, seed=2)
+    m = build(cfg, st, "fp32")
+    x, y = NB.synthetic_batch(cfg, 2, seed=5)
+    mu, logvar, enc, recon = m(x.cuda())
+    eps = m.last_eps
+    assert eps.shape == mu.shape and abs(float(eps.mean())) < 0.3 and 0.7 < float(eps.std()) < 1.3
+    assert torch.allclose(enc, mu + eps * torch.exp(0.5 * logvar), atol=1e-5)
+    # decoder-only path reproduces the logits of the full forward
+    rec2 = m.decode(enc)
+    assert float((rec2 - recon).abs().max()) <= 1e-4 * float(recon.abs().max())
+    ref = NB.decode({k: v.double() for k, v in st.items()}, cfg, enc.cpu().double())
+    assert float((rec2.cpu().double() - ref).norm() / ref.norm()) < 1e-5
+
+
+def test_linearity_in_kl_weight():
+    """size-independent property: gradients are affine in kl_weight, g(w) = g(0) + w * (g(1) - g(0))."""
+    cfg = NB.NbConfig(image_size=64)
+    st = NB.init_state(cfg, seed=4)
+    m = build(cfg, st, "fp32")
+    x, y = NB.synthetic_batch(cfg, 4, seed=9)
+    eps = torch.randn(4, cfg.z_dimensions, cfg.latent_hw, cfg.latent_hw, generator=torch.Generator().manual_seed(1))
+    g0 = run(m, x, y, eps, 0.0, False)[7]
+    g1 = run(m, x, y, eps, 1.0, False)[7]
+    g3 = run(m, x, y, eps, 3.0, False)[7]
+    for k in g0:
+        if k.startswith("decoder."):
+            assert torch.equal(g0[k], g1[k])           # KL does not reach the decoder
+            continue
+        pred = g0[k] + 3.0 * (g1[k] - g0[k])
+        assert float((g3[k] - pred).norm() / g3[k].norm()) < 1e-4, k
