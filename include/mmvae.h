@@ -83,7 +83,11 @@ enum { MMVAE_ARCH_RESNET = 0, MMVAE_ARCH_NOTEBOOK = 1 };
 /* Kernel selection for validation: MMVAE_PREC_BF16 normally runs every layer shape the tcgen05
  * kernels cover on the tensor cores; this flag forces the fp32-FMA SIMT kernels (same bf16 storage)
  * so the two can be compared tensor by tensor. */
-enum { MMVAE_FLAG_FORCE_SIMT = 1 };
+enum { MMVAE_FLAG_FORCE_SIMT = 1,
+       /* MMVAE_ARCH_NOTEBOOK, bf16: mmvae_forward (called with recon == NULL) stops before decoder.conv4 and
+        * mmvae_nb_loss_backward runs that conv fused with the softmax cross-entropy, writing d logits directly: the
+        * 256-channel logits never reach HBM.  Both calls must carry the flag. */
+       MMVAE_FLAG_DEFER_LOGITS = 2 };
 
 typedef struct mmvae_layout_info {
   int64_t n_params;         /* floats in the parameter / gradient arena         */

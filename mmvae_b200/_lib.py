@@ -15,6 +15,7 @@ PREC_FP32, PREC_BF16 = 0, 1
 LOSS_GAUSSIAN, LOSS_CATEGORICAL = 0, 1
 BWD_DECODER, BWD_ENC_DEEP, BWD_ENC_SHALLOW, BWD_ALL = 1, 2, 4, 7
 FLAG_FORCE_SIMT = 1
+FLAG_DEFER_LOGITS = 2
 ARCH_RESNET, ARCH_NOTEBOOK = 0, 1
 ABI_VERSION = 3
 

@@ -517,12 +517,29 @@ struct Exec {
     for (int k = 0; k < 4; ++k) {                                                 // vae-kl.ipynb:162-166
       const ActT& src = act(nb_dec_src(k));
       launch_nb_upsample<T>(at<T>(src.off), at<T>(act(nb.a_up[k]).off), N, src.H, src.W, src.C, nb.up[k], st);
+      if (k == 3 && nb_tail_ok()) {
+        if (nb_deferred() && !recon) break;           // fused with the cross-entropy in nb_loss_backward
+        if (nb_tail_fwd(nullptr, nullptr, 0.f, at<T>(act(P.convs[nb.dc[3]].out).off))) continue;
+      }
       nb_conv_fwd(P.convs[nb.dc[k]], k < 3 ? ACT_ELU : ACT_NONE);
     }
     if (recon) {
       const ConvT_& c = P.convs[nb.dc[3]];
       launch_nb_export_nchw<T>(at<T>(act(c.out).off), recon, N, c.Ho * c.Wo, c.Co, st);
     }
+  }
+  // dedicated tcgen05 kernels of decoder.conv4 (nb_tail.cu)
+  bool nb_tail_ok() const {
+    const ConvT_& c = P.convs[P.nb.dc[3]];
+    return special_ok() && nb_tail_supported(c.Ci, c.Co, c.Hi, c.Wi, c.k, c.s, c.p);
+  }
+  bool nb_deferred() const { return (P.d.flags & MMVAE_FLAG_DEFER_LOGITS) && nb_tail_ok(); }
+  bool nb_tail_fwd(const long long* target, double* ce_acc, float scale, void* out) {
+    const ConvT_& c = P.convs[P.nb.dc[3]];
+    NbTailArgs a{};
+    a.x = at<T>(act(c.in).off); a.w = params + c.w; a.bias = params + c.bias; a.out = out;
+    a.target = target; a.ce_acc = ce_acc; a.scale = scale; a.N = P.d.batch; a.H = c.Hi;
+    return launch_nb_tail_fwd(a, st);
   }
   void nb_dgrad(const ConvT_& c, int accumulate, int dact_kind, int dact_act) {
     GConvParams g;
@@ -545,8 +562,13 @@ struct Exec {
     cudaMemsetAsync(ws + nb.acc_off, 0, sizeof(double) * 2, st);
     double* acc = at<double>(nb.acc_off);
     const ConvT_& c4 = P.convs[nb.dc[3]];
-    launch_nb_ce<T>(at<T>(act(c4.out).off), target, at<T>(act(c4.out).goff), (long long)N * c4.Ho * c4.Wo, c4.Co, inv_n, acc,
-                    grads + c4.bias, st);
+    const long long rows4 = (long long)N * c4.Ho * c4.Wo;
+    if (nb_deferred() && nb_tail_fwd(target, acc, inv_n, at<T>(act(c4.out).goff))) {
+      // decoder.conv4 forward + softmax cross-entropy in one kernel: d logits written directly
+      side([&] { launch_nb_colsum<T>(at<T>(act(c4.out).goff), rows4, c4.Co, grads + c4.bias, st); });
+    } else {
+      launch_nb_ce<T>(at<T>(act(c4.out).off), target, at<T>(act(c4.out).goff), rows4, c4.Co, inv_n, acc, grads + c4.bias, st);
+    }
     for (int k = 3; k >= 0; --k) {
       const ConvT_& c = P.convs[nb.dc[k]];
       side([&] { nb_param_grads(c, k < 3); });          // decoder.conv4's bias gradient came out of the CE kernel

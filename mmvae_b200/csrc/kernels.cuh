@@ -368,6 +368,20 @@ template <typename T> void launch_nb_import_nchw(const float* in, T* out, int N,
 // out[0] = ce/N + klw*kl/N, out[1] = ce/N, out[2] = kl/N from the fp64 accumulators acc[0] (ce), acc[1] (kl)
 void launch_nb_loss_finalize(const double* acc, float inv_n, float klw, float* out, cudaStream_t st);
 
+// ---- notebook variant: dedicated tcgen05 kernels of decoder.conv4 (32 -> 256 classes, 3x3, 128-pixel rows; nb_tail.cu) ----
+struct NbTailArgs {
+  const void* x;               // upsampled input activation [N][H][128][32] bf16
+  const float* w;              // [256][32][3][3] fp32
+  const float* bias;           // [256]
+  void* out;                   // forward: logits (target == nullptr) or d logits (cross-entropy mode), [N][H][128][256] bf16
+  const long long* target;     // [N][H][128] or nullptr
+  double* ce_acc;              // cross-entropy mode: += sum (logsumexp - logit[target])
+  float scale;                 // cross-entropy mode: d logits scale (1 / N)
+  int N, H;
+};
+bool nb_tail_supported(int Ci, int Co, int H, int W, int k, int s, int pad);
+bool launch_nb_tail_fwd(const NbTailArgs& a, cudaStream_t st);     // false: TMA descriptor could not be encoded
+
 // ---- device helpers ----
 __device__ __forceinline__ float to_f(float v) { return v; }
 __device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }

@@ -1,0 +1,324 @@
+// nb_tail.cu -- the tensor-core-bound end of the notebook variant (vae-kl.ipynb:160,166,226): decoder.conv4, a 3x3 conv
+// from 32 channels to the 256 grey-level logits on 128x128 frames (94 % of the network's FLOPs),
+// as dedicated tcgen05 kernels instead of the generic gather-convolution of gconv_tc.cu, which refetches the packed
+// weights (80 KB) and an im2col copy of the input (72 KB) from L2 for every 128-pixel tile.
+//
+//   nb_tail_fwd_kernel   out[128 pixels of one image row][256 classes] = sum over the 9 taps of A_tap[128][32] W_tap[32][256]
+//     * the whole weight tensor lives in shared memory for the life of the CTA (144 KB bf16, converted from the fp32
+//       masters by the CTA itself: no pack launch) as nine K-major SWIZZLE_64B tiles [256 co][32 ci];
+//     * an input image row is staged once per band as three dx-shifted copies [128 pixels][32 ci] (TMA boxes starting at
+//       x = -1, 0, +1; the halo pixels and rows arrive as TMA out-of-bounds zeros) and serves the three output rows that
+//       see it as dy = +1, 0, -1 (un-swizzled planes with the dx as a descriptor shift were tried first: the tensor core
+//       fetches un-swizzled operands 16 bytes per row, 2.6 ms; profiles/r01_nb_tail.md).  Three row slots: the oldest
+//       row is released after the first six MMAs of a tile, so its successor loads under the other twelve;
+//     * a CTA walks bands of 32 consecutive rows of one image; 18 MMAs (M=128, N=256, K=16) per row into one of two
+//       256-column TMEM accumulators;
+//     * epilogue, logits mode: + bias -> bf16 NHWC.  Cross-entropy mode (training): the 256 logits of a pixel sit in one
+//       TMEM lane = one thread, so max / sum-exp / log-likelihood need no shuffles; the thread writes
+//       d logits = (softmax - onehot) / N directly: the logits themselves never reach HBM.
+#include <cuda.h>
+
+#include <cstdlib>
+#include <cstring>
+
+#include "kernels.cuh"
+#include "tc_common.cuh"
+
+namespace mmvae {
+
+using namespace tc;
+
+namespace {
+
+constexpr int kW = 128;                     // pixels per image row = GEMM M
+constexpr int kCi = 32, kCo = 256;
+constexpr int kCopyA = kW * 64;             // bytes of one dx-shifted copy of an input row: 128 pixels x 32 channels, SWIZZLE_64B
+constexpr int kSlotA = 3 * kCopyA;          // one input image row: the copies for dx = -1, 0, +1
+constexpr int kSlots = 3;
+constexpr int kTapW = kCo * 64;             // bytes per tap of the weights: 256 rows (co) x 32 ci, SWIZZLE_64B, K-major
+constexpr int kWBytes = 9 * kTapW;          // 147,456
+constexpr int kFwdThreads = 320;            // warp 0: TMA producer, warp 1: MMA issue + TMEM owner, warps 2-9: two epilogue groups
+constexpr size_t kFwdSmem = (size_t)kWBytes + (size_t)kSlots * kSlotA + 1024;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+struct NbTailFwd {
+  TmaDesc tmap_x;              // upsampled decoder.conv3 activation [N][H][128][32] bf16; box = 32 channels x 128 pixels
+  const float* w;              // decoder.conv4.weight [256][32][3][3] fp32
+  const float* bias;           // [256]
+  __nv_bfloat16* out;          // logits, or d logits in cross-entropy mode: [N][H][128][256]
+  const long long* target;     // [N][H][128] class indices: cross-entropy mode; nullptr: logits mode
+  double* ce_acc;              // += sum over pixels of (logsumexp - logit[target])
+  float scale, inv_scale;      // d logits scale 1 / N, and N
+  int H, rows_per_band, bands_per_image, total_bands;
+};
+
+__global__ void __launch_bounds__(kFwdThreads, 1) nb_tail_fwd_kernel(const __grid_constant__ NbTailFwd p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long full[kSlots], empty[kSlots], tfull[2], tempty[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float bias_s[kCo], ebias_s[kCo];   // bias; exp(bias - max bias)
+  __shared__ float loss_red[8], bmax_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t w_base = base, a_base = base + kWBytes;
+  unsigned char* w_gen = smem_raw + (base - smem_u32(smem_raw));
+
+  // ---- prologue (kernel parameters and weights only: legal before the PDL wait) ----
+  if (tid == 0) {
+    prefetch_tensormap(&p.tmap_x);
+    for (int s = 0; s < kSlots; ++s) { mbar_init(smem_u32(&full[s]), 1); mbar_init(smem_u32(&empty[s]), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&tfull[b]), 1); mbar_init(smem_u32(&tempty[b]), 128); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), 512);
+  for (int e = tid; e < kCo * kCi * 9; e += kFwdThreads) {
+    const int co = e / (kCi * 9), r = e - co * (kCi * 9);
+    const int ci = r / 9, t = r - ci * 9;
+    *reinterpret_cast<__nv_bfloat16*>(w_gen + (size_t)t * kTapW + swz_off<64>((uint32_t)co, (uint32_t)(ci >> 3)) + (ci & 7) * 2) =
+        __float2bfloat16_rn(__ldg(p.w + e));
+  }
+  if (warp == 2) {
+    float bm = -INFINITY;
+    for (int c = lane; c < kCo; c += 32) bm = fmaxf(bm, __ldg(p.bias + c));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, o));
+    for (int c = lane; c < kCo; c += 32) { const float b = __ldg(p.bias + c); bias_s[c] = b; ebias_s[c] = __expf(b - bm); }
+    if (lane == 0) bmax_s = bm;
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  pdl_wait();
+  pdl_trigger();
+
+  const int R = p.rows_per_band;
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- producer: one input row = 4 TMA boxes ----------------
+      const uint64_t tmap = reinterpret_cast<uint64_t>(&p.tmap_x);
+      int g = 0;                                       // running input-row index of this CTA
+      for (int band = blockIdx.x; band < p.total_bands; band += gridDim.x) {
+        const int n = band / p.bands_per_image, y0 = (band - n * p.bands_per_image) * R;
+        for (int i = 0; i < R + 2; ++i, ++g) {
+          const int slot = g % kSlots;
+          mbar_wait(smem_u32(&empty[slot]), (uint32_t)(((g / kSlots) & 1) ^ 1));
+          const uint32_t bar = smem_u32(&full[slot]);
+          mbar_arrive_expect_tx(bar, (uint32_t)kSlotA);
+          const uint32_t dst = a_base + (uint32_t)slot * kSlotA;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) tma_load_4d(dst + (uint32_t)c * kCopyA, tmap, bar, 0, c - 1, y0 - 1 + i, n);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issue ----------------
+      const uint32_t idesc = make_idesc_bf16(128, kCo, 0, 0);
+      const uint64_t da0 = make_smem_desc(a_base, 16, 512, SWZ_64);
+      const uint64_t db0 = make_smem_desc(w_base, 16, 512, SWZ_64);
+      int g0 = 0, q = 0;                               // running index of the band's first input row; running output row
+      for (int band = blockIdx.x; band < p.total_bands; band += gridDim.x, g0 += R + 2) {
+        for (int o = 0; o < R; ++o, ++q) {
+          const int buf = q & 1;
+          mbar_wait(smem_u32(&tempty[buf]), (uint32_t)(((q >> 1) & 1) ^ 1));
+          tc_fence_after();
+          const uint32_t dtm = tmem + (uint32_t)(buf * kCo);
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+            const int g = g0 + o + ky;
+            const uint32_t slot = (uint32_t)(g % kSlots);
+            if (o == 0 || ky == 2) {                   // rows o, o+1 were waited for by the previous output row
+              mbar_wait(smem_u32(&full[slot]), (uint32_t)((g / kSlots) & 1));
+              tc_fence_after();
+            }
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks) {
+                const uint64_t da = da0 + (uint64_t)((slot * kSlotA + (uint32_t)kx * kCopyA + (uint32_t)ks * 32u) >> 4);
+                const uint64_t db = db0 + (uint64_t)(((uint32_t)(ky * 3 + kx) * kTapW + (uint32_t)ks * 32u) >> 4);
+                mma_bf16(dtm, da, db, idesc, (ky | kx | ks) != 0);
+              }
+            // input row o is dead after its dy = -1 use by output row o: release it now so that row o + 3 loads under the
+            // remaining twelve MMAs of this tile and the first twelve of the next
+            if (ky == 0 && o < R - 1) mma_commit(smem_u32(&empty[slot]));
+          }
+          mma_commit(smem_u32(&tfull[buf]));
+          if (o == R - 1) {                            // end of the band: its last three input rows
+            mma_commit(smem_u32(&empty[(g0 + R - 1) % kSlots]));
+            mma_commit(smem_u32(&empty[(g0 + R) % kSlots]));
+            mma_commit(smem_u32(&empty[(g0 + R + 1) % kSlots]));
+          }
+        }
+      }
+    }
+  } else {
+    // ---------------- epilogue: thread = pixel = TMEM lane; two warp groups take alternate output rows ----------------
+    // (one group = one warp per scheduler: TMEM / MUFU latency would be exposed; two groups overlap each other)
+    const int lq = warp & 3;                           // TMEM lane quarter this warp may read
+    const int grp = (warp - 2) >> 2;                   // handles output rows with q % 2 == grp, i.e. TMEM buffer grp
+    const int x = lq * 32 + lane;
+    const bool ce = p.target != nullptr;
+    constexpr float kLog2e = 1.4426950408889634f;
+    float loss = 0.f;
+    int q = 0;
+    for (int band = blockIdx.x; band < p.total_bands; band += gridDim.x) {
+      const int n = band / p.bands_per_image, y0 = (band - n * p.bands_per_image) * R;
+      for (int o = 0; o < R; ++o, ++q) {
+        if ((q & 1) != grp) continue;
+        const int buf = grp;
+        const size_t pix = ((size_t)n * p.H + (y0 + o)) * kW + x;
+        __nv_bfloat16* orow = p.out + pix * kCo;
+        int tg = 0;
+        if (ce) tg = (int)__ldg(p.target + pix);
+        mbar_wait(smem_u32(&tfull[buf]), (uint32_t)((q >> 1) & 1));
+        tc_fence_after();
+        const uint32_t tl = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * kCo);
+        if (!ce) {
+#pragma unroll 2
+          for (int g = 0; g < 8; ++g) {
+            float v[32];
+            tmem_ld32(tl + (uint32_t)(g * 32), v);
+            uint4 pk[4];
+            uint32_t* pw = reinterpret_cast<uint32_t*>(pk);
+#pragma unroll
+            for (int e = 0; e < 32; e += 2) pw[e >> 1] = pack_bf16x2(v[e] + bias_s[g * 32 + e], v[e + 1] + bias_s[g * 32 + e + 1]);
+#pragma unroll
+            for (int h = 0; h < 4; ++h) reinterpret_cast<uint4*>(orow + g * 32)[h] = pk[h];
+          }
+          tc_fence_before();
+          mbar_arrive(smem_u32(&tempty[buf]));
+          continue;
+        }
+        // pass 1: maximum of the raw accumulators; + max bias is an upper bound of the row maximum, which is all the
+        // stabilisation needs (the biases span a fraction of a unit)
+        float mx = -INFINITY;
+#pragma unroll 2
+        for (int g = 0; g < 8; ++g) {
+          float v[32];
+          tmem_ld32(tl + (uint32_t)(g * 32), v);
+#pragma unroll
+          for (int e = 0; e < 32; ++e) mx = fmaxf(mx, v[e]);
+        }
+        // pass 2: e_c = exp(v_c - mx) * exp(b_c - bmax) written back over the accumulator (a register copy of the 256
+        // values would not fit beside the other epilogue group), and their sum
+        float sum0 = 0.f, sum1 = 0.f;
+        const float mxl = mx * kLog2e;
+#pragma unroll 2
+        for (int g = 0; g < 16; ++g) {
+          float v[16];
+          tmem_ld16(tl + (uint32_t)(g * 16), v);
+#pragma unroll
+          for (int e = 0; e < 16; e += 2) {
+            v[e] = ex2_approx(fmaf(v[e], kLog2e, -mxl)) * ebias_s[g * 16 + e];
+            v[e + 1] = ex2_approx(fmaf(v[e + 1], kLog2e, -mxl)) * ebias_s[g * 16 + e + 1];
+            sum0 += v[e]; sum1 += v[e + 1];
+          }
+          tmem_st16(tl + (uint32_t)(g * 16), v);
+        }
+        tmem_st_wait();
+        // pass 3: d logits (without the one-hot) = softmax * scale
+        const float inv = p.scale / (sum0 + sum1);
+#pragma unroll 2
+        for (int g = 0; g < 16; ++g) {
+          float v[16];
+          tmem_ld16(tl + (uint32_t)(g * 16), v);
+          uint4 pk[2];
+          uint32_t* pw = reinterpret_cast<uint32_t*>(pk);
+#pragma unroll
+          for (int e = 0; e < 16; e += 2) pw[e >> 1] = pack_bf16x2(v[e] * inv, v[e + 1] * inv);
+          reinterpret_cast<uint4*>(orow + g * 16)[0] = pk[0];
+          reinterpret_cast<uint4*>(orow + g * 16)[1] = pk[1];
+        }
+        tc_fence_before();
+        mbar_arrive(smem_u32(&tempty[buf]));           // the accumulator is free for output row q + 2
+        // the target class: read back this thread's own softmax[target] * scale (the per-class select over 256 register
+        // values would cost more than the whole pass), take the log-likelihood from it and subtract the one-hot
+        const float pt = __bfloat162float(*reinterpret_cast<volatile __nv_bfloat16*>(orow + tg));
+        loss -= __logf(fmaxf(pt, 1e-30f) * p.inv_scale);
+        orow[tg] = __float2bfloat16_rn(pt - p.scale);
+      }
+    }
+    if (ce) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
+      if (lane == 0) loss_red[warp - 2] = loss;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (warp == 2 && lane == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += loss_red[w];
+        atomicAdd(p.ce_acc, (double)t);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// ---------------- host: TMA descriptor without swizzle ----------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return (EncodeTiledFn)f;
+  }();
+  return fn;
+}
+// NHWC bf16 [N][H][W][C]; box = cb channels x bw pixels of one row
+bool make_tmap_rows(TmaDesc& out, const void* base, int N, int H, int W, int C, int cb, int bw, CUtensorMapSwizzle sw) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  static_assert(sizeof(CUtensorMap) == sizeof(TmaDesc), "TmaDesc must mirror CUtensorMap");
+  cuuint64_t dim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t str[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)cb, (cuuint32_t)bw, 1u, 1u};
+  cuuint32_t est[4] = {1u, 1u, 1u, 1u};
+  CUresult r = fn(reinterpret_cast<CUtensorMap*>(&out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dim, str,
+                  box, est, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+bool nb_tail_supported(int Ci, int Co, int H, int W, int k, int s, int pad) {
+  static const bool off = getenv("MMVAE_NO_NB_TAIL") != nullptr;
+  return !off && Ci == kCi && Co == kCo && W == kW && H % 32 == 0 && k == 3 && s == 1 && pad == 1;
+}
+
+bool launch_nb_tail_fwd(const NbTailArgs& a, cudaStream_t st) {
+  NbTailFwd p;
+  memset(&p, 0, sizeof(p));
+  if (!make_tmap_rows(p.tmap_x, a.x, a.N, a.H, kW, kCi, kCi, kW, CU_TENSOR_MAP_SWIZZLE_64B)) return false;
+  p.w = a.w; p.bias = a.bias; p.out = reinterpret_cast<__nv_bfloat16*>(a.out);
+  p.target = a.target; p.ce_acc = a.ce_acc; p.scale = a.scale; p.inv_scale = a.scale > 0.f ? 1.0f / a.scale : 0.f;
+  p.H = a.H; p.rows_per_band = 32; p.bands_per_image = a.H / 32; p.total_bands = a.N * p.bands_per_image;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(nb_tail_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem);
+    attr_done = true;
+  }
+  const int grid = p.total_bands < 148 ? p.total_bands : 148;
+  count_launch();
+  launch_pdl(nb_tail_fwd_kernel, dim3(grid), dim3(kFwdThreads), kFwdSmem, st, p);
+  return true;
+}
+
+}  // namespace mmvae

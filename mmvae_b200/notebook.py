@@ -66,9 +66,10 @@ class NotebookVAE(nn.Module):
         self.last_eps = None
         self._reset_parameters()
 
-    def _desc(self, batch):
+    def _desc(self, batch, defer_logits=False):
+        flags = self.kernel_flags | (_lib.FLAG_DEFER_LOGITS if defer_logits else 0)
         return _lib.make_desc(batch, 1, self.n_classes, self.z_dimensions, self.image_size,
-                              self.intermediate_channels // 32, True, self._prec, True, flags=self.kernel_flags,
+                              self.intermediate_channels // 32, True, self._prec, True, flags=flags,
                               arch=_lib.ARCH_NOTEBOOK)
 
     def _node_for(self, dotted):
@@ -140,12 +141,12 @@ class NotebookVAE(nn.Module):
         st.update({"decoder." + k: v for k, v in decoder_state.items()})
         return self.load_state_dict(st)
 
-    def _workspace(self, n):
-        key = (n, self.kernel_flags)
+    def _workspace(self, n, defer_logits=False):
+        key = (n, self.kernel_flags, defer_logits)
         hit = self._ws.get(key)
         if hit is None:
             self._ws.clear()
-            desc = self._desc(n)
+            desc = self._desc(n, defer_logits)
             info = _lib.layout(desc)
             ws = torch.empty(info.workspace_bytes, dtype=torch.uint8, device=self._arena.device)
             hit = (desc, ws, info)
@@ -170,7 +171,8 @@ class NotebookVAE(nn.Module):
         n, z, h = x.shape[0], self.z_dimensions, self.latent_hw
         if tuple(x.shape[1:]) != (1, self.image_size, self.image_size):
             raise ValueError(f"x must be [N,1,{self.image_size},{self.image_size}]")
-        desc, ws, info = self._workspace(n)
+        # without materialised logits the last conv runs fused with the cross-entropy inside loss_backward()
+        desc, ws, info = self._workspace(n, defer_logits=not materialize and self.precision == "bf16")
         dev = x.device
         mu = torch.empty(n, z, h, h, dtype=torch.float32, device=dev)
         logvar = torch.empty_like(mu)

@@ -65,6 +65,25 @@ def test_bf16_mode_within_tolerance(case, flags):
     assert not errs, "\n".join(errs)
 
 
+def test_fused_tail_matches_materialised_path():
+    """decoder.conv4 fused with the softmax cross-entropy (nb_tail.cu, logits never stored) against the same step with
+    materialised logits + the stand-alone cross-entropy kernel, and against the fp64 oracle, on 128x128 frames."""
+    g = NbGolden("nb128_n2")
+    st = g.state()
+    m = build(g.cfg, st, "bf16")
+    a = run(m, g.x, g.y, g.eps, g.kl_weight, materialize=False)         # fused
+    b = run(m, g.x, g.y, g.eps, g.kl_weight, materialize=True)          # logits kernel + nb_ce
+    ref = NB.train_step(st, g.cfg, g.x, g.y, g.eps, kl_weight=g.kl_weight, dtype=torch.float64)
+    assert float((b[6].double() - ref.logits).norm() / ref.logits.norm()) <= 1e-2
+    assert abs(a[0] - ref.loss) <= 1e-2 * abs(ref.loss) and abs(a[0] - b[0]) <= 1e-3 * abs(b[0])
+    for k, r in ref.grads.items():
+        d_ab = float((a[7][k].double() - b[7][k].double()).norm() / b[7][k].double().norm())
+        d_ref = float((a[7][k].double() - r).norm() / r.norm())
+        assert d_ab <= 1e-2, (k, d_ab)
+        if k.startswith("decoder."):
+            assert d_ref <= 1e-2, (k, d_ref)
+
+
 def test_tc_matches_simt_at_training_batch():
     """tcgen05 kernels against the fp32-FMA SIMT kernels on identical bf16 storage at a batch that fills the GPU
     (persistent multi-tile CTAs, TMA boxes): decoder gradients agree to 5e-3 relative L2, encoder ones to 3e-2."""
