@@ -563,15 +563,22 @@ struct Exec {
     double* acc = at<double>(nb.acc_off);
     const ConvT_& c4 = P.convs[nb.dc[3]];
     const long long rows4 = (long long)N * c4.Ho * c4.Wo;
-    if (nb_deferred() && nb_tail_fwd(target, acc, inv_n, at<T>(act(c4.out).goff))) {
-      // decoder.conv4 forward + softmax cross-entropy in one kernel: d logits written directly
-      side([&] { launch_nb_colsum<T>(at<T>(act(c4.out).goff), rows4, c4.Co, grads + c4.bias, st); });
-    } else {
+    bool ce_bias = false;                               // decoder.conv4's bias gradient already produced
+    if (!(nb_deferred() && nb_tail_fwd(target, acc, inv_n, at<T>(act(c4.out).goff)))) {   // fused: d logits written directly
       launch_nb_ce<T>(at<T>(act(c4.out).off), target, at<T>(act(c4.out).goff), rows4, c4.Co, inv_n, acc, grads + c4.bias, st);
+      ce_bias = true;
     }
     for (int k = 3; k >= 0; --k) {
       const ConvT_& c = P.convs[nb.dc[k]];
-      side([&] { nb_param_grads(c, k < 3); });          // decoder.conv4's bias gradient came out of the CE kernel
+      if (k == 3 && nb_tail_ok()) {
+        side([&] {
+          NbTailArgs a{};
+          a.x = at<T>(act(c.in).off); a.out = at<T>(act(c.out).goff); a.N = N; a.H = c.Hi;
+          if (!launch_nb_tail_wgrad(a, grads + c.w, ce_bias ? nullptr : grads + c.bias, st)) nb_param_grads(c, !ce_bias);
+        });
+      } else {
+        side([&] { nb_param_grads(c, !(k == 3 && ce_bias)); });
+      }
       nb_dgrad(c, 0, ACT_NONE, -1);                     // -> d(upsampled input)
       const int srci = nb_dec_src(k);
       const ActT& src = act(srci);

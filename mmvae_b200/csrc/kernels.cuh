@@ -381,6 +381,8 @@ struct NbTailArgs {
 };
 bool nb_tail_supported(int Ci, int Co, int H, int W, int k, int s, int pad);
 bool launch_nb_tail_fwd(const NbTailArgs& a, cudaStream_t st);     // false: TMA descriptor could not be encoded
+// weight + bias gradient: a.x = upsampled input, a.out = d logits; dw / dbias pre-zeroed, accumulated atomically
+bool launch_nb_tail_wgrad(const NbTailArgs& a, float* dw, float* dbias, cudaStream_t st);
 
 // ---- device helpers ----
 __device__ __forceinline__ float to_f(float v) { return v; }

@@ -266,6 +266,169 @@ __global__ void __launch_bounds__(kFwdThreads, 1) nb_tail_fwd_kernel(const __gri
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// weight gradient of decoder.conv4 (+ its bias gradient):
+//   dW[co][ci][ky][kx] = sum over pixels of Xu[y + ky - 1][x + kx - 1][ci] * G[y][x][co],   G = d logits
+// GEMM with the pixel axis as K, both operands MN-major exactly as TMA delivers the NHWC rows: per image row y and
+// per ky one chain of 8 MMAs (M = 128 = the three dx copies of input row y + ky - 1 stacked along M + 32 don't-care rows,
+// N = 128 classes, K = 16 pixels) into the ky-th of three TMEM accumulators that live for the CTA's whole life.  A CTA owns
+// one half of the classes and every 74th band of rows: G is read from HBM exactly once, the input rows once per class
+// half.  The four otherwise idle warps add up the columns of the G tiles in shared memory (bias gradient) while the
+// tensor core works, then drain the accumulators with red.global.add at the end.
+// ------------------------------------------------------------------------------------------------
+constexpr int kWgSlotsA = 4, kWgSlotsB = 3;
+constexpr int kWgSlotB = 2 * kW * 128;      // one row of G for 128 classes: two [128 pixels][64 classes] SWIZZLE_128B tiles
+constexpr int kWgThreads = 192;
+constexpr size_t kWgSmem = (size_t)kWgSlotsA * kSlotA + (size_t)kWgSlotsB * kWgSlotB + 1024;
+
+struct NbTailWgrad {
+  TmaDesc tmap_x;              // upsampled input [N][H][128][32] bf16, box = 32 channels x 128 pixels, SWIZZLE_64B
+  TmaDesc tmap_g;              // d logits [N][H][128][256] bf16, box = 64 classes x 128 pixels, SWIZZLE_128B
+  float* dw;                   // [256][32][3][3] fp32, accumulated with red.global.add (pre-zeroed)
+  float* dbias;                // [256] or nullptr
+  int H, rows_per_band, bands_per_image, total_bands;
+};
+
+__global__ void __launch_bounds__(kWgThreads, 1) nb_tail_wgrad_kernel(const __grid_constant__ NbTailWgrad p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long full_a[kWgSlotsA], empty_a[kWgSlotsA], full_b[kWgSlotsB], empty_b[kWgSlotsB], accum;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_base = base, b_base = base + kWgSlotsA * kSlotA;
+  const unsigned char* b_gen = smem_raw + (b_base - smem_u32(smem_raw));
+  const int half = blockIdx.x & 1, worker = blockIdx.x >> 1, nworkers = gridDim.x >> 1;
+
+  if (tid == 0) {
+    prefetch_tensormap(&p.tmap_x);
+    prefetch_tensormap(&p.tmap_g);
+    for (int s = 0; s < kWgSlotsA; ++s) { mbar_init(smem_u32(&full_a[s]), 1); mbar_init(smem_u32(&empty_a[s]), 1); }
+    for (int s = 0; s < kWgSlotsB; ++s) { mbar_init(smem_u32(&full_b[s]), 1); mbar_init(smem_u32(&empty_b[s]), 5); }
+    mbar_init(smem_u32(&accum), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  pdl_wait();
+  pdl_trigger();
+
+  const int R = p.rows_per_band;
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- producer: input rows (three dx copies) and G rows, in the order the MMA thread consumes them ----------------
+      const uint64_t tmx = reinterpret_cast<uint64_t>(&p.tmap_x), tmg = reinterpret_cast<uint64_t>(&p.tmap_g);
+      int ga = 0, gb = 0;
+      for (int band = worker; band < p.total_bands; band += nworkers) {
+        const int n = band / p.bands_per_image, y0 = (band - n * p.bands_per_image) * R;
+        for (int o = 0; o < R; ++o) {
+          for (int i = (o == 0 ? 0 : o + 2); i <= o + 2; ++i, ++ga) {
+            const int slot = ga % kWgSlotsA;
+            mbar_wait(smem_u32(&empty_a[slot]), (uint32_t)(((ga / kWgSlotsA) & 1) ^ 1));
+            const uint32_t bar = smem_u32(&full_a[slot]);
+            mbar_arrive_expect_tx(bar, (uint32_t)kSlotA);
+            const uint32_t dst = a_base + (uint32_t)slot * kSlotA;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) tma_load_4d(dst + (uint32_t)c * kCopyA, tmx, bar, 0, c - 1, y0 - 1 + i, n);
+          }
+          const int slot = gb % kWgSlotsB;
+          mbar_wait(smem_u32(&empty_b[slot]), (uint32_t)(((gb / kWgSlotsB) & 1) ^ 1));
+          const uint32_t bar = smem_u32(&full_b[slot]);
+          mbar_arrive_expect_tx(bar, (uint32_t)kWgSlotB);
+          const uint32_t dst = b_base + (uint32_t)slot * kWgSlotB;
+          tma_load_4d(dst, tmg, bar, half * 128, 0, y0 + o, n);
+          tma_load_4d(dst + 16384u, tmg, bar, half * 128 + 64, 0, y0 + o, n);
+          ++gb;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issue ----------------
+      const uint32_t idesc = make_idesc_bf16(128, 128, 1, 1);
+      const uint64_t da0 = make_smem_desc(a_base, kCopyA, 512, SWZ_64);        // M: 4 x 32 channels, one dx copy apart
+      const uint64_t db0 = make_smem_desc(b_base, 16384, 1024, SWZ_128);       // N: 2 x 64 classes
+      int g0 = 0, gb = 0;
+      bool first = true;
+      for (int band = worker; band < p.total_bands; band += nworkers, g0 += R + 2) {
+        for (int o = 0; o < R; ++o, ++gb) {
+          const uint32_t bslot = (uint32_t)(gb % kWgSlotsB);
+          mbar_wait(smem_u32(&full_b[bslot]), (uint32_t)((gb / kWgSlotsB) & 1));
+          const uint64_t db = db0 + (uint64_t)((bslot * kWgSlotB) >> 4);
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+            const int g = g0 + o + ky;
+            const uint32_t slot = (uint32_t)(g % kWgSlotsA);
+            if (o == 0 || ky == 2) mbar_wait(smem_u32(&full_a[slot]), (uint32_t)((g / kWgSlotsA) & 1));
+            tc_fence_after();
+            const uint64_t da = da0 + (uint64_t)((slot * kSlotA) >> 4);
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)       // 16 pixels per MMA
+              mma_bf16(tmem + (uint32_t)(ky * 128), da + (uint64_t)(ks * 64), db + (uint64_t)(ks * 128), idesc, !(first && ks == 0));
+            if (ky == 0 && o < R - 1) mma_commit(smem_u32(&empty_a[slot]));
+          }
+          first = false;
+          mma_commit(smem_u32(&empty_b[bslot]));
+          if (o == R - 1) {
+            mma_commit(smem_u32(&empty_a[(g0 + R - 1) % kWgSlotsA]));
+            mma_commit(smem_u32(&empty_a[(g0 + R) % kWgSlotsA]));
+            mma_commit(smem_u32(&empty_a[(g0 + R + 1) % kWgSlotsA]));
+          }
+        }
+      }
+      mma_commit(smem_u32(&accum));
+    }
+  } else {
+    // ---------------- bias gradient while the tensor core works: thread = class, sums the pixel column of every G tile ----------------
+    const int c = (warp - 2) * 32 + lane;              // class within this CTA's half
+    const uint32_t coff = (uint32_t)(c >> 6) * 16384u + (uint32_t)(c & 7) * 2u;
+    const uint32_t cch = (uint32_t)((c & 63) >> 3);
+    float s0 = 0.f, s1 = 0.f;
+    int gb = 0;
+    for (int band = worker; band < p.total_bands; band += nworkers) {
+      for (int o = 0; o < R; ++o, ++gb) {
+        const int bslot = gb % kWgSlotsB;
+        mbar_wait(smem_u32(&full_b[bslot]), (uint32_t)((gb / kWgSlotsB) & 1));
+        const unsigned char* tile = b_gen + (size_t)bslot * kWgSlotB + coff;
+#pragma unroll 8
+        for (int px = 0; px < kW; px += 2) {
+          s0 += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(tile + px * 128 + ((cch ^ (uint32_t)(px & 7)) << 4)));
+          s1 += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(tile + (px + 1) * 128 + ((cch ^ (uint32_t)((px + 1) & 7)) << 4)));
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&empty_b[bslot]));
+      }
+    }
+    if (gb > 0 && p.dbias) atomicAdd(p.dbias + half * 128 + c, s0 + s1);
+    // ---------------- drain the three accumulators: lane m = (kx, ci), column = class ----------------
+    if (gb > 0) {
+      mbar_wait(smem_u32(&accum), 0);
+      tc_fence_after();
+      const int lq = warp & 3, m = lq * 32 + lane;
+      const int kx = m >> 5, ci = m & 31;
+      for (int ky = 0; ky < 3; ++ky) {
+        for (int c0 = 0; c0 < 128; c0 += 16) {
+          float v[16];
+          tmem_ld16(tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(ky * 128 + c0), v);
+          if (m < 96) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              atomicAdd(p.dw + ((size_t)(half * 128 + c0 + e) * kCi + ci) * 9 + ky * 3 + kx, v[e]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
 // ---------------- host: TMA descriptor without swizzle ----------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -318,6 +481,24 @@ bool launch_nb_tail_fwd(const NbTailArgs& a, cudaStream_t st) {
   const int grid = p.total_bands < 148 ? p.total_bands : 148;
   count_launch();
   launch_pdl(nb_tail_fwd_kernel, dim3(grid), dim3(kFwdThreads), kFwdSmem, st, p);
+  return true;
+}
+
+bool launch_nb_tail_wgrad(const NbTailArgs& a, float* dw, float* dbias, cudaStream_t st) {
+  NbTailWgrad p;
+  memset(&p, 0, sizeof(p));
+  if (!make_tmap_rows(p.tmap_x, a.x, a.N, a.H, kW, kCi, kCi, kW, CU_TENSOR_MAP_SWIZZLE_64B)) return false;
+  if (!make_tmap_rows(p.tmap_g, a.out, a.N, a.H, kW, kCo, 64, kW, CU_TENSOR_MAP_SWIZZLE_128B)) return false;
+  p.dw = dw; p.dbias = dbias;
+  p.H = a.H; p.rows_per_band = 32; p.bands_per_image = a.H / 32; p.total_bands = a.N * p.bands_per_image;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(nb_tail_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgSmem);
+    attr_done = true;
+  }
+  const int workers = p.total_bands < 74 ? p.total_bands : 74;
+  count_launch();
+  launch_pdl(nb_tail_wgrad_kernel, dim3(2 * workers), dim3(kWgThreads), kWgSmem, st, p);
   return true;
 }
 
