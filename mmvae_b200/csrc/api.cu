@@ -579,7 +579,13 @@ struct Exec {
       } else {
         side([&] { nb_param_grads(c, !(k == 3 && ce_bias)); });
       }
-      nb_dgrad(c, 0, ACT_NONE, -1);                     // -> d(upsampled input)
+      bool dg_done = false;
+      if (k == 3 && nb_tail_ok()) {
+        NbTailArgs a{};
+        a.out = at<T>(act(c.out).goff); a.w = params + c.w; a.N = N; a.H = c.Hi;
+        dg_done = launch_nb_tail_dgrad(a, at<T>(act(c.in).goff), st);
+      }
+      if (!dg_done) nb_dgrad(c, 0, ACT_NONE, -1);       // -> d(upsampled input)
       const int srci = nb_dec_src(k);
       const ActT& src = act(srci);
       launch_nb_upsample_bwd<T>(at<T>(act(nb.a_up[k]).goff), k > 0 ? at<T>(src.off) : nullptr, ACT_ELU, at<T>(src.goff), N,

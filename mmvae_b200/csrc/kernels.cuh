@@ -381,6 +381,8 @@ struct NbTailArgs {
 };
 bool nb_tail_supported(int Ci, int Co, int H, int W, int k, int s, int pad);
 bool launch_nb_tail_fwd(const NbTailArgs& a, cudaStream_t st);     // false: TMA descriptor could not be encoded
+// data gradient: a.out = d logits, a.w = weights -> dx [N][H][128][32] bf16
+bool launch_nb_tail_dgrad(const NbTailArgs& a, void* dx, cudaStream_t st);
 // weight + bias gradient: a.x = upsampled input, a.out = d logits; dw / dbias pre-zeroed, accumulated atomically
 bool launch_nb_tail_wgrad(const NbTailArgs& a, float* dw, float* dbias, cudaStream_t st);
 

@@ -429,6 +429,182 @@ __global__ void __launch_bounds__(kWgThreads, 1) nb_tail_wgrad_kernel(const __gr
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// data gradient of decoder.conv4:  dXu[y'][x'][ci] = sum_{ky,kx,co} G[y' - ky + 1][x' - kx + 1][co] * W[co][ci][ky][kx]
+// Computed in the transposed ("col2im") form so that the 512-byte G pixel rows are fetched once and never shifted:
+//   T_r[x][(ky, kx, ci)] = sum_co G[r][x][co] * W[co][ci][ky][kx]            one GEMM row block per image row r of G:
+//   M = 128 pixels, K = 256 classes (four 64-wide SWIZZLE_128B chunks through a 4-stage TMA ring), N = 3 x 96;
+// the ky part of the col2im happens inside the tensor core: the ky-th 96-column block of row r accumulates into the TMEM
+// accumulator of OUTPUT row r + ky - 1 (four rotating 96-column accumulators), so an output row is complete once G rows
+// y'-1, y', y'+1 have passed.  The kx part is a neighbour exchange in the epilogue (thread = pixel: warp shuffles, plus a
+// 64-float shared-memory hand-over at the three warp boundaries).  All 288 x 256 transposed weights stay in shared memory
+// (144 KB) for the life of the CTA.
+// ------------------------------------------------------------------------------------------------
+constexpr int kDgChunkW = 96 * 128;         // bytes of one (ky, 64-class chunk) weight tile: 96 rows (kx, ci) x 64 classes
+constexpr int kDgWBytes = 3 * 4 * kDgChunkW;   // 147,456
+constexpr int kDgStage = kW * 128;          // one 64-class chunk of a G row: 128 pixels x 128 B
+constexpr int kDgStages = 4;
+constexpr int kDgThreads = 192;
+constexpr size_t kDgSmem = (size_t)kDgWBytes + (size_t)kDgStages * kDgStage + 1024;
+
+struct NbTailDgrad {
+  TmaDesc tmap_g;              // d logits [N][H][128][256] bf16, box = 64 classes x 128 pixels, SWIZZLE_128B
+  const float* w;              // [256][32][3][3] fp32
+  __nv_bfloat16* dx;           // gradient wrt the upsampled input [N][H][128][32]
+  int H, rows_per_band, bands_per_image, total_bands;
+};
+
+__global__ void __launch_bounds__(kDgThreads, 1) nb_tail_dgrad_kernel(const __grid_constant__ NbTailDgrad p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long full[kDgStages], empty[kDgStages], tfull[4], tempty[4];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float edge[2][4][2][kCi];                 // [tile parity][pixel quarter][kx = 0 of lane 0 | kx = 2 of lane 31][ci]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t w_base = base, a_base = base + kDgWBytes;
+  unsigned char* w_gen = smem_raw + (base - smem_u32(smem_raw));
+
+  if (tid == 0) {
+    prefetch_tensormap(&p.tmap_g);
+    for (int s = 0; s < kDgStages; ++s) { mbar_init(smem_u32(&full[s]), 1); mbar_init(smem_u32(&empty[s]), 1); }
+    for (int b = 0; b < 4; ++b) { mbar_init(smem_u32(&tfull[b]), 1); mbar_init(smem_u32(&tempty[b]), 128); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), 512);
+  for (int e = tid; e < kCo * kCi * 9; e += kDgThreads) {
+    const int co = e / (kCi * 9), r = e - co * (kCi * 9);
+    const int ci = r / 9, t = r - ci * 9;
+    const int ky = t / 3, kx = t - ky * 3;
+    *reinterpret_cast<__nv_bfloat16*>(w_gen + (size_t)(ky * 4 + (co >> 6)) * kDgChunkW +
+                                      swz_off<128>((uint32_t)(kx * 32 + ci), (uint32_t)((co & 63) >> 3)) + (co & 7) * 2) =
+        __float2bfloat16_rn(__ldg(p.w + e));
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  pdl_wait();
+  pdl_trigger();
+
+  const int R = p.rows_per_band;
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- producer: G rows y0-1 .. y0+R, four 64-class chunks each ----------------
+      const uint64_t tmg = reinterpret_cast<uint64_t>(&p.tmap_g);
+      int g = 0;
+      for (int band = blockIdx.x; band < p.total_bands; band += gridDim.x) {
+        const int n = band / p.bands_per_image, y0 = (band - n * p.bands_per_image) * R;
+        for (int rr = -1; rr <= R; ++rr)
+          for (int kc = 0; kc < 4; ++kc, ++g) {
+            const int stage = g % kDgStages;
+            mbar_wait(smem_u32(&empty[stage]), (uint32_t)(((g / kDgStages) & 1) ^ 1));
+            const uint32_t bar = smem_u32(&full[stage]);
+            mbar_arrive_expect_tx(bar, (uint32_t)kDgStage);
+            tma_load_4d(a_base + (uint32_t)stage * kDgStage, tmg, bar, kc * 64, 0, y0 + rr, n);
+          }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issue ----------------
+      const uint32_t idesc = make_idesc_bf16(128, 96, 0, 0);
+      const uint64_t da0 = make_smem_desc(a_base, 16, 1024, SWZ_128);
+      const uint64_t db0 = make_smem_desc(w_base, 16, 1024, SWZ_128);
+      int g = 0, qb = 0;                               // running chunk index; running index of the band's first output row
+      for (int band = blockIdx.x; band < p.total_bands; band += gridDim.x, qb += R) {
+        for (int rr = -1; rr <= R; ++rr) {
+          // a fresh accumulator (output row rr + 1, first touched by ky = 2) must have been drained by the epilogue
+          if (rr + 1 < R) {
+            const int q = qb + rr + 1;
+            mbar_wait(smem_u32(&tempty[q & 3]), (uint32_t)(((q >> 2) & 1) ^ 1));
+          }
+          for (int kc = 0; kc < 4; ++kc, ++g) {
+            const int stage = g % kDgStages;
+            mbar_wait(smem_u32(&full[stage]), (uint32_t)((g / kDgStages) & 1));
+            tc_fence_after();
+            const uint64_t da = da0 + (uint64_t)(((uint32_t)stage * kDgStage) >> 4);
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+              const int oo = rr + ky - 1;              // band-local output row fed by the ky-th block
+              if (oo < 0 || oo >= R) continue;
+              const uint32_t dtm = tmem + (uint32_t)(((qb + oo) & 3) * 128);
+              const uint64_t db = db0 + (uint64_t)(((uint32_t)(ky * 4 + kc) * kDgChunkW) >> 4);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                mma_bf16(dtm, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc, !(ky == 2 && kc == 0 && ks == 0));
+            }
+            mma_commit(smem_u32(&empty[stage]));
+          }
+          if (rr >= 1) mma_commit(smem_u32(&tfull[(qb + rr - 1) & 3]));      // output row rr - 1 is complete
+        }
+      }
+    }
+  } else {
+    // ---------------- epilogue: thread = pixel; kx neighbour exchange, bf16 NHWC store ----------------
+    const int lq = warp & 3;
+    const int x = lq * 32 + lane;
+    int q = 0;
+    for (int band = blockIdx.x; band < p.total_bands; band += gridDim.x) {
+      const int n = band / p.bands_per_image, y0 = (band - n * p.bands_per_image) * R;
+      for (int oo = 0; oo < R; ++oo, ++q) {
+        const int slot = q & 3;
+        mbar_wait(smem_u32(&tfull[slot]), (uint32_t)((q >> 2) & 1));
+        tc_fence_after();
+        const uint32_t tl = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(slot * 128);
+        float t0[32], t1[32], t2[32];                  // kx = 0, 1, 2 blocks of this pixel
+        {
+          float v[32];
+          tmem_ld32(tl, v);
+#pragma unroll
+          for (int e = 0; e < 32; ++e) t0[e] = v[e];
+          tmem_ld32(tl + 32u, v);
+#pragma unroll
+          for (int e = 0; e < 32; ++e) t1[e] = v[e];
+          tmem_ld32(tl + 64u, v);
+#pragma unroll
+          for (int e = 0; e < 32; ++e) t2[e] = v[e];
+        }
+        tc_fence_before();
+        mbar_arrive(smem_u32(&tempty[slot]));
+        float (*eb)[2][kCi] = edge[q & 1];
+        if (lane == 0) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) eb[lq][0][e] = t0[e];
+        }
+        if (lane == 31) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) eb[lq][1][e] = t2[e];
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        // out[x] = T[x+1][kx=0] + T[x][kx=1] + T[x-1][kx=2]
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          float up = __shfl_down_sync(0xffffffffu, t0[e], 1);      // from pixel x + 1
+          float dn = __shfl_up_sync(0xffffffffu, t2[e], 1);        // from pixel x - 1
+          if (lane == 31) up = lq < 3 ? eb[lq + 1][0][e] : 0.f;
+          if (lane == 0) dn = lq > 0 ? eb[lq - 1][1][e] : 0.f;
+          t1[e] += up + dn;
+        }
+        __nv_bfloat16* orow = p.dx + (((size_t)n * p.H + (y0 + oo)) * kW + x) * kCi;
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          uint4 pk;
+          pk.x = pack_bf16x2(t1[h * 8 + 0], t1[h * 8 + 1]); pk.y = pack_bf16x2(t1[h * 8 + 2], t1[h * 8 + 3]);
+          pk.z = pack_bf16x2(t1[h * 8 + 4], t1[h * 8 + 5]); pk.w = pack_bf16x2(t1[h * 8 + 6], t1[h * 8 + 7]);
+          reinterpret_cast<uint4*>(orow)[h] = pk;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
 // ---------------- host: TMA descriptor without swizzle ----------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -481,6 +657,23 @@ bool launch_nb_tail_fwd(const NbTailArgs& a, cudaStream_t st) {
   const int grid = p.total_bands < 148 ? p.total_bands : 148;
   count_launch();
   launch_pdl(nb_tail_fwd_kernel, dim3(grid), dim3(kFwdThreads), kFwdSmem, st, p);
+  return true;
+}
+
+bool launch_nb_tail_dgrad(const NbTailArgs& a, void* dx, cudaStream_t st) {
+  NbTailDgrad p;
+  memset(&p, 0, sizeof(p));
+  if (!make_tmap_rows(p.tmap_g, a.out, a.N, a.H, kW, kCo, 64, kW, CU_TENSOR_MAP_SWIZZLE_128B)) return false;
+  p.w = a.w; p.dx = reinterpret_cast<__nv_bfloat16*>(dx);
+  p.H = a.H; p.rows_per_band = 32; p.bands_per_image = a.H / 32; p.total_bands = a.N * p.bands_per_image;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(nb_tail_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDgSmem);
+    attr_done = true;
+  }
+  const int grid = p.total_bands < 148 ? p.total_bands : 148;
+  count_launch();
+  launch_pdl(nb_tail_dgrad_kernel, dim3(grid), dim3(kDgThreads), kDgSmem, st, p);
   return true;
 }
 
