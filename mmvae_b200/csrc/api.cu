@@ -497,7 +497,11 @@ struct Exec {
                   float* eps_out, float* mu, float* logvar, float* enc, float* recon) {
     const NbT& nb = P.nb;
     const int N = P.d.batch;
-    for (int i = 0; i < 4; ++i) nb_conv_fwd(P.convs[nb.e[i]], ACT_RELU);          // vae-kl.ipynb:134-137
+    for (int i = 0; i < 4; ++i) {                                                 // vae-kl.ipynb:134-137
+      const ConvT_& c = P.convs[nb.e[i]];
+      if (i == 0 && nb_stem_ok()) launch_nb_stem_fwd(x, params + c.w, params + c.bias, at<T>(act(c.out).off), N, c.Hi, st);
+      else nb_conv_fwd(c, ACT_RELU);
+    }
     const ConvT_& cmu = P.convs[nb.cmu]; const ConvT_& clv = P.convs[nb.clv];
     nb_conv_fwd(cmu, ACT_NONE);                                                   // vae-kl.ipynb:139-140
     nb_conv_fwd(clv, ACT_NONE);
@@ -527,6 +531,10 @@ struct Exec {
       const ConvT_& c = P.convs[nb.dc[3]];
       launch_nb_export_nchw<T>(at<T>(act(c.out).off), recon, N, c.Ho * c.Wo, c.Co, st);
     }
+  }
+  bool nb_stem_ok() const {
+    const ConvT_& c = P.convs[P.nb.e[0]];
+    return special_ok() && nb_stem_supported(c.Ci, c.Co, c.Hi, c.k, c.s, c.p);
   }
   // dedicated tcgen05 kernels of decoder.conv4 (nb_tail.cu)
   bool nb_tail_ok() const {
@@ -609,7 +617,11 @@ struct Exec {
       side([&] { nb_param_grads(c); });
       nb_dgrad(c, 0, ACT_RELU, P.convs[nb.e[i - 1]].out);
     }
-    nb_param_grads(P.convs[nb.e[0]]);
+    {
+      const ConvT_& c = P.convs[nb.e[0]];
+      if (nb_stem_ok()) launch_nb_stem_wgrad(x, at<T>(act(c.out).goff), grads + c.w, grads + c.bias, N, c.Hi, st);
+      else nb_param_grads(c);
+    }
     join();
   }
 

@@ -365,6 +365,10 @@ template <typename T> void launch_nb_colsum(const T* dy, long long rows, int C, 
 // NHWC storage -> fp32 NCHW
 template <typename T> void launch_nb_export_nchw(const T* in, float* out, int N, int HW, int C, cudaStream_t st);
 template <typename T> void launch_nb_import_nchw(const float* in, T* out, int N, int HW, int C, cudaStream_t st);
+// encoder.conv1 (1 -> 32, k5 s2 p2) + bias + ReLU and its weight / bias gradient, bf16 storage (dedicated SIMT kernels)
+bool nb_stem_supported(int Ci, int Co, int S, int k, int s, int pad);
+void launch_nb_stem_fwd(const float* x, const float* w, const float* bias, void* out, int N, int S, cudaStream_t st);
+void launch_nb_stem_wgrad(const float* x, const void* dy, float* dw, float* dbias, int N, int S, cudaStream_t st);
 // out[0] = ce/N + klw*kl/N, out[1] = ce/N, out[2] = kl/N from the fp64 accumulators acc[0] (ce), acc[1] (kl)
 void launch_nb_loss_finalize(const double* acc, float inv_n, float klw, float* out, cudaStream_t st);
 

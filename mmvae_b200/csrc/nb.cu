@@ -4,6 +4,8 @@
 //   nearest upsample (vae-kl.ipynb:152-155) and its adjoint fused with the activation derivative,
 //   rsample (vae-kl.ipynb:144-146) and its adjoint fused with the closed-form KL gradient,
 //   softmax cross-entropy over the 256 grey levels (vae-kl.ipynb:226) fused with d logits and the last bias gradient.
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace mmvae {
@@ -315,6 +317,118 @@ __global__ void nb_loss_finalize_kernel(const double* acc, float inv_n, float kl
   out[2] = (float)kl;
 }
 
+// ---------------- encoder.conv1 of the notebook variant: Conv2d(1 -> 32, k5, s2, p2) + bias + ReLU (vae-kl.ipynb:124,134) ----------------
+// K = 25 on a single input channel is not tensor-core work: register-blocked SIMT over tiles of 8 output rows x Wo columns
+// of one frame; the fp32 input window (19 x (2 Wo + 3), zero halo) is staged in shared memory.
+constexpr int kStemRows = 8;
+constexpr int kStemMaxWo = 64;
+constexpr int kStemPitch = 2 * kStemMaxWo + 4;       // floats per staged input row
+
+template <int CO>
+__device__ __forceinline__ void nb_stem_load_x(const float* __restrict__ x, float* xs, int n, int oy0, int S, int Wo) {
+  const int rows = 2 * kStemRows + 3, cols = 2 * Wo + 3;
+  const float* img = x + (size_t)n * S * S;
+  for (int e = threadIdx.x; e < rows * cols; e += 256) {
+    const int r = e / cols, c = e - r * cols;
+    const int iy = 2 * oy0 - 2 + r, ix = c - 2;
+    xs[r * kStemPitch + c] = ((unsigned)iy < (unsigned)S && (unsigned)ix < (unsigned)S) ? __ldg(img + (size_t)iy * S + ix) : 0.f;
+  }
+}
+
+// forward: warp = 8 output channels, lanes = 32 consecutive pixels of the tile; weights broadcast from shared memory
+__global__ void __launch_bounds__(256) nb_stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int N,
+                                                         int S) {
+  __shared__ float xs[(2 * kStemRows + 3) * kStemPitch];
+  __shared__ __align__(16) float ws[25][32];
+  __shared__ float bs[32];
+  const int Wo = S / 2, Ho = S / 2, tiles_per_frame = Ho / kStemRows;
+  for (int e = threadIdx.x; e < 800; e += 256) ws[e % 25][e / 25] = __ldg(w + e);      // [co][tap] -> [tap][co]
+  if (threadIdx.x < 32) bs[threadIdx.x] = __ldg(bias + threadIdx.x);
+  pdl_wait();
+  pdl_trigger();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cg = warp & 3, half = warp >> 2;           // channel group of 8; which half of the tile's pixel chunks
+  const int npix = kStemRows * Wo;
+  for (int tile = blockIdx.x; tile < N * tiles_per_frame; tile += gridDim.x) {
+    const int n = tile / tiles_per_frame, oy0 = (tile - n * tiles_per_frame) * kStemRows;
+    __syncthreads();
+    nb_stem_load_x<32>(x, xs, n, oy0, S, Wo);
+    __syncthreads();
+    for (int p0 = half * 32; p0 < npix; p0 += 64) {
+      const int px = p0 + lane, py = px / Wo, pxx = px - py * Wo;
+      float acc[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[c] = bs[cg * 8 + c];
+      const float* xp = xs + (2 * py) * kStemPitch + 2 * pxx;
+#pragma unroll
+      for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 5; ++kx) {
+          const float xv = xp[ky * kStemPitch + kx];
+          const float4 w0 = *reinterpret_cast<const float4*>(&ws[ky * 5 + kx][cg * 8]);
+          const float4 w1 = *reinterpret_cast<const float4*>(&ws[ky * 5 + kx][cg * 8 + 4]);
+          acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]); acc[2] = fmaf(xv, w0.z, acc[2]); acc[3] = fmaf(xv, w0.w, acc[3]);
+          acc[4] = fmaf(xv, w1.x, acc[4]); acc[5] = fmaf(xv, w1.y, acc[5]); acc[6] = fmaf(xv, w1.z, acc[6]); acc[7] = fmaf(xv, w1.w, acc[7]);
+        }
+      uint4 pk;
+      __nv_bfloat162* pw = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) pw[c] = __floats2bfloat162_rn(fmaxf(acc[2 * c], 0.f), fmaxf(acc[2 * c + 1], 0.f));
+      *reinterpret_cast<uint4*>(out + (((size_t)n * Ho + oy0 + py) * Wo + pxx) * 32 + cg * 8) = pk;
+    }
+  }
+}
+
+// weight + bias gradient: lane = output channel, warp w owns taps {w, w+8, w+16, w+24}; dY tile (bf16) and input window in
+// shared memory; sums stay in registers over all tiles of the CTA, one atomicAdd per (tap, channel) and CTA at the end
+__global__ void __launch_bounds__(256) nb_stem_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                                                           float* __restrict__ dw, float* __restrict__ dbias, int N, int S) {
+  __shared__ float xs[(2 * kStemRows + 3) * kStemPitch];
+  __shared__ __align__(16) __nv_bfloat16 dys[kStemRows * kStemMaxWo * 32];
+  pdl_wait();
+  pdl_trigger();
+  const int Wo = S / 2, Ho = S / 2, tiles_per_frame = Ho / kStemRows;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int npix = kStemRows * Wo;
+  int toff[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int t = warp + 8 * j;
+    toff[j] = t < 25 ? (t / 5) * kStemPitch + (t % 5) : 0;
+  }
+  const bool four = warp == 0;                         // only warp 0 has a fourth tap (24)
+  float acc[4] = {0.f, 0.f, 0.f, 0.f}, bsum = 0.f;
+  for (int tile = blockIdx.x; tile < N * tiles_per_frame; tile += gridDim.x) {
+    const int n = tile / tiles_per_frame, oy0 = (tile - n * tiles_per_frame) * kStemRows;
+    __syncthreads();
+    nb_stem_load_x<32>(x, xs, n, oy0, S, Wo);
+    const uint4* src = reinterpret_cast<const uint4*>(dy + ((size_t)n * Ho + oy0) * Wo * 32);
+    for (int e = threadIdx.x; e < npix * 4; e += 256) reinterpret_cast<uint4*>(dys)[e] = __ldg(src + e);
+    __syncthreads();
+    for (int py = 0; py < kStemRows; ++py) {
+      const float* xr = xs + (2 * py) * kStemPitch;
+      const __nv_bfloat16* dr = dys + (size_t)py * Wo * 32 + lane;
+#pragma unroll 4
+      for (int pxx = 0; pxx < Wo; ++pxx) {
+        const float g = __bfloat162float(dr[pxx * 32]);
+        const float* xp = xr + 2 * pxx;
+        acc[0] = fmaf(xp[toff[0]], g, acc[0]);
+        acc[1] = fmaf(xp[toff[1]], g, acc[1]);
+        acc[2] = fmaf(xp[toff[2]], g, acc[2]);
+        if (four) acc[3] = fmaf(xp[toff[3]], g, acc[3]);
+        if (warp == 7) bsum += g;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int t = warp + 8 * j;
+    if (t < 25) atomicAdd(dw + lane * 25 + t, acc[j]);
+  }
+  if (warp == 7 && dbias) atomicAdd(dbias + lane, bsum);
+}
+
 inline int grid_for(long long work_items, int cap = 148 * 16) {
   long long b = (work_items + 255) / 256;
   return (int)(b < 1 ? 1 : (b > cap ? cap : b));
@@ -371,6 +485,22 @@ void launch_nb_import_nchw(const float* in, T* out, int N, int HW, int C, cudaSt
   const long long total = (long long)N * HW * C;
   count_launch();
   nb_import_nchw_kernel<T><<<grid_for(total, 148 * 32), 256, 0, st>>>(in, out, HW, C, total);
+}
+bool nb_stem_supported(int Ci, int Co, int S, int k, int s, int pad) {
+  static const bool off = getenv("MMVAE_NO_NB_STEM") != nullptr;
+  return !off && Ci == 1 && Co == 32 && k == 5 && s == 2 && pad == 2 && S % (2 * kStemRows) == 0 && S / 2 <= kStemMaxWo;
+}
+void launch_nb_stem_fwd(const float* x, const float* w, const float* bias, void* out, int N, int S, cudaStream_t st) {
+  const int tiles = N * (S / 2 / kStemRows);
+  count_launch();
+  launch_pdl(nb_stem_fwd_kernel, dim3(tiles < 148 * 4 ? tiles : 148 * 4), dim3(256), 0, st, x, w, bias,
+             reinterpret_cast<__nv_bfloat16*>(out), N, S);
+}
+void launch_nb_stem_wgrad(const float* x, const void* dy, float* dw, float* dbias, int N, int S, cudaStream_t st) {
+  const int tiles = N * (S / 2 / kStemRows);
+  count_launch();
+  launch_pdl(nb_stem_wgrad_kernel, dim3(tiles < 148 * 4 ? tiles : 148 * 4), dim3(256), 0, st, x,
+             reinterpret_cast<const __nv_bfloat16*>(dy), dw, dbias, N, S);
 }
 void launch_nb_loss_finalize(const double* acc, float inv_n, float klw, float* out, cudaStream_t st) {
   count_launch();

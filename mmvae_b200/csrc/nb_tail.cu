@@ -40,6 +40,13 @@ constexpr int kWBytes = 9 * kTapW;          // 147,456
 constexpr int kFwdThreads = 320;            // warp 0: TMA producer, warp 1: MMA issue + TMEM owner, warps 2-9: two epilogue groups
 constexpr size_t kFwdSmem = (size_t)kWBytes + (size_t)kSlots * kSlotA + 1024;
 
+// MMVAE_NB_TAIL_DBG (tuning experiments, results in profiles/r01_nb_tail.md): 1 = epilogues only follow the barrier protocol,
+// 2 = no TMA loads (the MMAs run on whatever is in shared memory)
+int nb_tail_dbg() {
+  static int v = [] { const char* e = getenv("MMVAE_NB_TAIL_DBG"); return e ? atoi(e) : 0; }();
+  return v;
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -55,6 +62,7 @@ struct NbTailFwd {
   double* ce_acc;              // += sum over pixels of (logsumexp - logit[target])
   float scale, inv_scale;      // d logits scale 1 / N, and N
   int H, rows_per_band, bands_per_image, total_bands;
+  int dbg;
 };
 
 __global__ void __launch_bounds__(kFwdThreads, 1) nb_tail_fwd_kernel(const __grid_constant__ NbTailFwd p) {
@@ -110,6 +118,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) nb_tail_fwd_kernel(const __gri
           const int slot = g % kSlots;
           mbar_wait(smem_u32(&empty[slot]), (uint32_t)(((g / kSlots) & 1) ^ 1));
           const uint32_t bar = smem_u32(&full[slot]);
+          if (p.dbg & 2) { mbar_arrive(bar); continue; }
           mbar_arrive_expect_tx(bar, (uint32_t)kSlotA);
           const uint32_t dst = a_base + (uint32_t)slot * kSlotA;
 #pragma unroll
@@ -181,6 +190,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) nb_tail_fwd_kernel(const __gri
         mbar_wait(smem_u32(&tfull[buf]), (uint32_t)((q >> 1) & 1));
         tc_fence_after();
         const uint32_t tl = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * kCo);
+        if (p.dbg & 1) { tc_fence_before(); mbar_arrive(smem_u32(&tempty[buf])); continue; }
         if (!ce) {
 #pragma unroll 2
           for (int g = 0; g < 8; ++g) {
@@ -287,6 +297,7 @@ struct NbTailWgrad {
   float* dw;                   // [256][32][3][3] fp32, accumulated with red.global.add (pre-zeroed)
   float* dbias;                // [256] or nullptr
   int H, rows_per_band, bands_per_image, total_bands;
+  int dbg;
 };
 
 __global__ void __launch_bounds__(kWgThreads, 1) nb_tail_wgrad_kernel(const __grid_constant__ NbTailWgrad p) {
@@ -328,6 +339,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) nb_tail_wgrad_kernel(const __gr
             const int slot = ga % kWgSlotsA;
             mbar_wait(smem_u32(&empty_a[slot]), (uint32_t)(((ga / kWgSlotsA) & 1) ^ 1));
             const uint32_t bar = smem_u32(&full_a[slot]);
+            if (p.dbg & 2) { mbar_arrive(bar); continue; }
             mbar_arrive_expect_tx(bar, (uint32_t)kSlotA);
             const uint32_t dst = a_base + (uint32_t)slot * kSlotA;
 #pragma unroll
@@ -336,6 +348,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) nb_tail_wgrad_kernel(const __gr
           const int slot = gb % kWgSlotsB;
           mbar_wait(smem_u32(&empty_b[slot]), (uint32_t)(((gb / kWgSlotsB) & 1) ^ 1));
           const uint32_t bar = smem_u32(&full_b[slot]);
+          if (p.dbg & 2) { mbar_arrive(bar); ++gb; continue; }
           mbar_arrive_expect_tx(bar, (uint32_t)kWgSlotB);
           const uint32_t dst = b_base + (uint32_t)slot * kWgSlotB;
           tma_load_4d(dst, tmg, bar, half * 128, 0, y0 + o, n);
@@ -393,7 +406,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) nb_tail_wgrad_kernel(const __gr
         mbar_wait(smem_u32(&full_b[bslot]), (uint32_t)((gb / kWgSlotsB) & 1));
         const unsigned char* tile = b_gen + (size_t)bslot * kWgSlotB + coff;
 #pragma unroll 8
-        for (int px = 0; px < kW; px += 2) {
+        for (int px = 0; px < ((p.dbg & 1) ? 0 : kW); px += 2) {
           s0 += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(tile + px * 128 + ((cch ^ (uint32_t)(px & 7)) << 4)));
           s1 += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(tile + (px + 1) * 128 + ((cch ^ (uint32_t)((px + 1) & 7)) << 4)));
         }
@@ -452,6 +465,7 @@ struct NbTailDgrad {
   const float* w;              // [256][32][3][3] fp32
   __nv_bfloat16* dx;           // gradient wrt the upsampled input [N][H][128][32]
   int H, rows_per_band, bands_per_image, total_bands;
+  int dbg;
 };
 
 __global__ void __launch_bounds__(kDgThreads, 1) nb_tail_dgrad_kernel(const __grid_constant__ NbTailDgrad p) {
@@ -500,6 +514,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) nb_tail_dgrad_kernel(const __gr
             const int stage = g % kDgStages;
             mbar_wait(smem_u32(&empty[stage]), (uint32_t)(((g / kDgStages) & 1) ^ 1));
             const uint32_t bar = smem_u32(&full[stage]);
+            if (p.dbg & 2) { mbar_arrive(bar); continue; }
             mbar_arrive_expect_tx(bar, (uint32_t)kDgStage);
             tma_load_4d(a_base + (uint32_t)stage * kDgStage, tmg, bar, kc * 64, 0, y0 + rr, n);
           }
@@ -552,18 +567,16 @@ __global__ void __launch_bounds__(kDgThreads, 1) nb_tail_dgrad_kernel(const __gr
         mbar_wait(smem_u32(&tfull[slot]), (uint32_t)((q >> 2) & 1));
         tc_fence_after();
         const uint32_t tl = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(slot * 128);
+        if (p.dbg & 1) { tc_fence_before(); mbar_arrive(smem_u32(&tempty[slot])); continue; }
         float t0[32], t1[32], t2[32];                  // kx = 0, 1, 2 blocks of this pixel
         {
-          float v[32];
-          tmem_ld32(tl, v);
+          uint32_t r0[32], r1[32], r2[32];
+          tmem_ld32_issue(tl, r0);
+          tmem_ld32_issue(tl + 32u, r1);
+          tmem_ld32_issue(tl + 64u, r2);
+          tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < 32; ++e) t0[e] = v[e];
-          tmem_ld32(tl + 32u, v);
-#pragma unroll
-          for (int e = 0; e < 32; ++e) t1[e] = v[e];
-          tmem_ld32(tl + 64u, v);
-#pragma unroll
-          for (int e = 0; e < 32; ++e) t2[e] = v[e];
+          for (int e = 0; e < 32; ++e) { t0[e] = __uint_as_float(r0[e]); t1[e] = __uint_as_float(r1[e]); t2[e] = __uint_as_float(r2[e]); }
         }
         tc_fence_before();
         mbar_arrive(smem_u32(&tempty[slot]));
@@ -649,6 +662,7 @@ bool launch_nb_tail_fwd(const NbTailArgs& a, cudaStream_t st) {
   p.w = a.w; p.bias = a.bias; p.out = reinterpret_cast<__nv_bfloat16*>(a.out);
   p.target = a.target; p.ce_acc = a.ce_acc; p.scale = a.scale; p.inv_scale = a.scale > 0.f ? 1.0f / a.scale : 0.f;
   p.H = a.H; p.rows_per_band = 32; p.bands_per_image = a.H / 32; p.total_bands = a.N * p.bands_per_image;
+  p.dbg = nb_tail_dbg();
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(nb_tail_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem);
@@ -666,6 +680,7 @@ bool launch_nb_tail_dgrad(const NbTailArgs& a, void* dx, cudaStream_t st) {
   if (!make_tmap_rows(p.tmap_g, a.out, a.N, a.H, kW, kCo, 64, kW, CU_TENSOR_MAP_SWIZZLE_128B)) return false;
   p.w = a.w; p.dx = reinterpret_cast<__nv_bfloat16*>(dx);
   p.H = a.H; p.rows_per_band = 32; p.bands_per_image = a.H / 32; p.total_bands = a.N * p.bands_per_image;
+  p.dbg = nb_tail_dbg();
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(nb_tail_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDgSmem);
@@ -684,6 +699,7 @@ bool launch_nb_tail_wgrad(const NbTailArgs& a, float* dw, float* dbias, cudaStre
   if (!make_tmap_rows(p.tmap_g, a.out, a.N, a.H, kW, kCo, 64, kW, CU_TENSOR_MAP_SWIZZLE_128B)) return false;
   p.dw = dw; p.dbias = dbias;
   p.H = a.H; p.rows_per_band = 32; p.bands_per_image = a.H / 32; p.total_bands = a.N * p.bands_per_image;
+  p.dbg = nb_tail_dbg();
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(nb_tail_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgSmem);
