@@ -127,6 +127,204 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+NB_TRAIN_MFLOP_PER_FRAME = 7714.586624     # notebook variant at 128x128 (mmvae_layout.train_flops)
+
+
+def nb_cpu_fps(steps, warmup, batch=4, size=128):
+    """The notebook's loop body (vae-kl.ipynb:210-233, forward + CE/KL + backward) on the host cores through the oracle port."""
+    import torch
+    from oracle import nb_oracle as NB
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = NB.NbConfig(image_size=size)
+    st = NB.init_state(cfg, seed=0)
+    x, y = NB.synthetic_batch(cfg, batch, seed=1234)
+    eps = torch.randn(batch, cfg.z_dimensions, cfg.latent_hw, cfg.latent_hw, generator=torch.Generator().manual_seed(4321))
+    step = NB.make_timed_step(st, cfg)
+    for _ in range(warmup):
+        step(x, y, eps)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step(x, y, eps)
+        times.append(time.perf_counter() - t0)
+    times.sort()
+    med = times[len(times) // 2]
+    return batch / med, med * 1e3, cores, torch.get_num_threads()
+
+
+def run_reference_notebook(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    steps, warm = min(args.steps, 5), min(args.warmup, 1)
+    fps, ms, cores, threads = nb_cpu_fps(steps, warm)
+    print(json.dumps({
+        "impl": "reference", "metric": "train frames/sec (fwd+bwd)", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "vae-kl.ipynb VAE 128x128, CE over 256 grey levels + KL, fwd+loss+bwd (BASELINE configs[4])",
+                   "batch_per_step": 4},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                         "sample": f"{steps} steps of 4 frames of 128x128 on {cores} host cores (median), fp32"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
+
+
+def main_notebook(args):
+    """BASELINE configs[4]: the notebook variant (vae-kl.ipynb) on 128x128 frames, 512 frames per GPU, bf16, weak scaling."""
+    import ctypes
+
+    import torch
+    import torch.distributed as dist
+
+    import mmvae_b200 as M
+    from mmvae_b200 import parallel as PAR
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n, size = args.batch, 128
+    torch.manual_seed(0)
+    model = M.NotebookVAE(1, 32, 32, image_size=size, precision=args.precision).to(dev)
+    if world > 1:
+        PAR.data_parallel(model)
+
+    def frames(seed):
+        """20-frame sequences of two bouncing grey blobs (56x56 on 128x128), flattened to frames, uint8 grey levels"""
+        g = torch.Generator().manual_seed(seed)
+        d, nseq = 56, (n + 19) // 20
+        out = torch.zeros(nseq * 20, size, size, dtype=torch.uint8)
+        for s in range(nseq):
+            for _ in range(2):
+                blob = (torch.rand(d, d, generator=g) * 255).to(torch.uint8)
+                pos = torch.rand(2, generator=g) * (size - d)
+                vel = (torch.rand(2, generator=g) - 0.5) * 12
+                for t in range(20):
+                    oy, ox = int(pos[0]), int(pos[1])
+                    out[s * 20 + t, oy:oy + d, ox:ox + d] = torch.maximum(out[s * 20 + t, oy:oy + d, ox:ox + d], blob)
+                    pos = pos + vel
+                    for k in range(2):
+                        if pos[k] < 0 or pos[k] > size - d:
+                            vel[k] = -vel[k]
+                            pos[k] = pos[k].clamp(0, size - d)
+        return out[:n].contiguous()
+
+    n_batches = 2
+    host = [frames(1234 + 97 * rank + b).pin_memory() for b in range(n_batches)]
+    resident = [model.prepare_input(h.to(dev)) for h in host]
+    info = M._lib.layout(model._desc(n, True))
+
+    def step_resident(i):
+        x, y = resident[i % n_batches]
+        return model.train_step(x, y)
+
+    def step_e2e(i):
+        f = host[i % n_batches].to(dev, non_blocking=True)        # H2D from pinned memory
+        x, y = model.prepare_input(f)                             # normalisation + int64 targets on the device
+        return float(model.train_step(x, y)[0])                   # D2H read of the loss (syncs)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for i in range(steps):
+            fn(i)
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for i in range(args.warmup):
+        step_resident(i)
+    with ClockSampler(local) as clk:
+        l0 = M._lib.lib.mmvae_launch_count()
+        ms = timed(step_resident, args.steps)
+        launches = M._lib.lib.mmvae_launch_count() - l0
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, args.steps)
+
+    sustained, burst, hbm, which = peaks()
+    roofs = []
+    if rank == 0 and args.precision == "bf16":
+        # the three dedicated tcgen05 kernels of decoder.conv4 (94 % of the step's FLOPs), each timed alone on the tensors the
+        # last step left in the workspace; inputs (4.8 GB) are far larger than L2
+        desc, ws, x_last = model._state
+        y_last = resident[(args.steps - 1) % n_batches][1]
+        scratch = torch.zeros(model._n_params, dtype=torch.float32, device=dev)
+        ab, af = ctypes.c_int64(), ctypes.c_int64()
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        names = ["nb_tail_fwd_kernel: decoder.conv4 forward (32->256, 3x3, 128x128) fused with softmax cross-entropy, writes d logits",
+                 "nb_tail_dgrad_kernel: decoder.conv4 data gradient (transposed form, col2im in TMEM + epilogue)",
+                 "nb_tail_wgrad_kernel: decoder.conv4 weight + bias gradient (pixel axis as K)"]
+        traffic = [4881000000, 5027000000, 4861000000]            # dram read+write per launch, ncu --set full, profiles/r01_nb_tail.md
+        for which_k in (0, 2, 1):                                 # d logits must exist before the gradients read them
+            def one():
+                M._lib.check(M._lib.lib.mmvae_nb_bench_tail(ctypes.byref(desc), which_k, ctypes.c_void_p(model._arena.data_ptr()),
+                                                            ctypes.c_void_p(y_last.data_ptr()), ctypes.c_void_p(ws.data_ptr()), ws.numel(),
+                                                            ctypes.c_void_p(scratch.data_ptr()), ctypes.byref(ab), ctypes.byref(af), stream),
+                             "mmvae_nb_bench_tail")
+            for _ in range(2):
+                one()
+            evs = []
+            for _ in range(10):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); one(); e1.record()
+                evs.append((e0, e1))
+            torch.cuda.synchronize()
+            us = sum(a.elapsed_time(b) for a, b in evs) / len(evs) * 1e3
+            tfs, gbs = af.value / (us * 1e-6) / 1e12, ab.value / (us * 1e-6) / 1e9
+            roofs.append({"bound": "tensor", "unit": "TFLOP/s", "achieved": tfs, "peak": burst, "frac": tfs / burst,
+                          "traffic": traffic[which_k], "kernel": names[which_k], "algorithmic_bytes_per_launch": ab.value,
+                          "flops_per_launch": af.value, "us_per_launch": us, "gbs": gbs, "hbm_frac": gbs / hbm,
+                          "note": f"of the {which} burst bf16 peak (kernel timed alone); hbm_frac = algorithmic GB/s over the {which} HBM copy peak"})
+        roofs.sort(key=lambda r: -r["us_per_launch"])
+
+    fps = world * n * args.steps / (ms * 1e-3)
+    fps_e2e = world * n * args.steps / (ms_e2e * 1e-3)
+    tf = fps / world * NB_TRAIN_MFLOP_PER_FRAME * 1e6 / 1e12
+    line = {
+        "metric": "train frames/sec (fwd+bwd)", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": "vae-kl.ipynb VAE 128x128, CE over 256 grey levels + KL, fwd+loss+bwd (BASELINE configs[4])",
+                   "frames_per_gpu": n, "global_batch": n * world, "seq_len": 20, "parallelism": f"dp{world}",
+                   "precision": args.precision, "launch": "host (51 launches per step)",
+                   "l2": f"activation workspace {info.workspace_bytes / 1e9:.1f} GB streamed every step (>> 126 MB L2), "
+                         f"{n_batches} rotating input batches"},
+        "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": n * size * size, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches), "clocks": clk.summary(),
+        "roofline": roofs[0] if roofs else {"bound": "tensor", "achieved": tf, "peak": sustained, "unit": "TFLOP/s",
+                                            "frac": tf / sustained, "traffic": None},
+        "roofline_others": roofs[1:],
+        "step_tensor": {"achieved": tf, "peak": sustained, "unit": "TFLOP/s", "frac": tf / sustained,
+                        "note": f"whole step, 7714.59 MFLOP/frame algorithmic, per GPU, of {which} sustained bf16 peak"},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cfps, cms, cores, threads = nb_cpu_fps(3, 1)
+        line["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": threads, "kind": "port",
+                                "sample": f"3 steps of 4 frames of 128x128 on {cores} host cores, fp32, median"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -134,14 +332,21 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="frames per GPU")
+    ap.add_argument("--batch", type=int, default=None, help="frames per GPU (default 256; 512 for --workload notebook)")
+    ap.add_argument("--workload", default="resnet", choices=["resnet", "notebook"],
+                    help="resnet: model.py VAE, BASELINE configs[1] (the headline); notebook: vae-kl.ipynb VAE on 128x128, configs[4]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying a CUDA graph")
     args = ap.parse_args()
+    if args.batch is None:
+        args.batch = 512 if args.workload == "notebook" else PER_GPU_BATCH
     if args.impl == "reference":
-        run_reference(args)
+        (run_reference_notebook if args.workload == "notebook" else run_reference)(args)
         return
     args.warmup = max(args.warmup, 3)
+    if args.workload == "notebook":
+        main_notebook(args)
+        return
 
     import types
 

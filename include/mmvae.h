@@ -224,6 +224,13 @@ int mmvae_conv_entry(const mmvae_desc* d, int32_t i, char* name, size_t name_cap
 int mmvae_bench_conv(const mmvae_desc* d, int32_t conv_index, int32_t dir, const float* params, void* workspace,
                      size_t workspace_bytes, float* grads_scratch, int64_t* algo_bytes, int64_t* algo_flops, void* stream);
 
+/* Measurement hook of the notebook variant's dominant kernels (nb_tail.cu, decoder.conv4 on 128-pixel rows): enqueue ONE
+ * launch of `which` = 0 forward fused with the softmax cross-entropy (needs target), 1 data gradient, 2 weight + bias
+ * gradient, on whatever the workspace holds after a mmvae_forward / mmvae_nb_loss_backward pair.  algo_bytes = bf16
+ * tensors the launch must touch once (input rows, d logits, targets, weights), algo_flops = 2*MAC. */
+int mmvae_nb_bench_tail(const mmvae_desc* d, int32_t which, const float* params, const int64_t* target, void* workspace,
+                        size_t workspace_bytes, float* grads_scratch, int64_t* algo_bytes, int64_t* algo_flops, void* stream);
+
 /* Debugging hook: device buffer of [444 CTAs][16] uint64 that the tcgen05 conv kernel fills with %globaltimer stamps
  * of its pipeline milestones (scripts/trace_conv.py prints the timeline); NULL (the default) turns tracing off. */
 void mmvae_debug_set_trace(void* device_buffer);

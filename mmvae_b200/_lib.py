@@ -25,7 +25,7 @@ EXPORTS = [
     "mmvae_loss_forward", "mmvae_loss_backward", "mmvae_backward", "mmvae_backward_range",
     "mmvae_philox_normal", "mmvae_adam_step", "mmvae_prepare_input", "mmvae_launch_count",
     "mmvae_conv_entry", "mmvae_selftest_tc", "mmvae_bench_conv", "mmvae_debug_set_trace",
-    "mmvae_nb_loss_backward",
+    "mmvae_nb_loss_backward", "mmvae_nb_bench_tail",
 ]
 
 
@@ -73,6 +73,7 @@ def _load():
     lib.mmvae_loss_backward.argtypes = [POINTER(LossArgs), P, P, P, P, P, P, P, P, P, P]
     lib.mmvae_backward.argtypes = [POINTER(Desc), P, P, P, c_size_t, P, P, P, P, P, c_int32, P]
     lib.mmvae_nb_loss_backward.argtypes = [POINTER(Desc), P, P, P, P, c_size_t, c_float, P, P, P]
+    lib.mmvae_nb_bench_tail.argtypes = [POINTER(Desc), c_int32, P, P, P, c_size_t, P, POINTER(c_int64), POINTER(c_int64), P]
     lib.mmvae_backward_range.argtypes = [POINTER(Desc), c_int32, POINTER(c_int64), POINTER(c_int64)]
     lib.mmvae_philox_normal.argtypes = [c_uint64, c_uint64, c_int64, P, P]
     lib.mmvae_adam_step.argtypes = [c_int64, P, P, P, P, c_float, c_float, c_float, c_float, c_float, c_int64,

@@ -918,6 +918,37 @@ int mmvae_nb_loss_backward(const mmvae_desc* d, const float* x, const int64_t* t
   return check_launches("mmvae_nb_loss_backward");
 }
 
+int mmvae_nb_bench_tail(const mmvae_desc* d, int32_t which, const float* params, const int64_t* target, void* workspace,
+                        size_t workspace_bytes, float* grads_scratch, int64_t* algo_bytes, int64_t* algo_flops, void* stream) {
+  MMVAE_COMMON_CHECKS();
+  if (P.d.arch != MMVAE_ARCH_NOTEBOOK || P.d.precision != MMVAE_PREC_BF16) return fail(MMVAE_ERR_BAD_DESC, "notebook variant, bf16 only");
+  if (!params || !grads_scratch || which < 0 || which > 2 || (which == 0 && !target)) return fail(MMVAE_ERR_BAD_ARG, "bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  Exec<__nv_bfloat16> E{P, (char*)workspace, params, grads_scratch, nullptr, nullptr, st, nullptr};
+  if (!E.nb_tail_ok()) return fail(MMVAE_ERR_BAD_DESC, "decoder.conv4 is not covered by the dedicated kernels at this shape");
+  const ConvT_& c = P.convs[P.nb.dc[3]];
+  const int64_t px = (int64_t)P.d.batch * c.Ho * c.Wo;
+  if (algo_flops) *algo_flops = 2 * px * c.Co * c.Ci * 9;
+  const int64_t b_in = px * c.Ci * 2, b_g = px * c.Co * 2, b_w = (int64_t)c.Co * c.Ci * 9 * 4;
+  NbTailArgs a{};
+  a.x = E.at<__nv_bfloat16>(P.acts[c.in].off); a.w = params + c.w; a.bias = params + c.bias;
+  a.out = E.at<__nv_bfloat16>(P.acts[c.out].goff); a.N = P.d.batch; a.H = c.Hi;
+  bool ok = false;
+  if (which == 0) {
+    a.target = reinterpret_cast<const long long*>(target); a.ce_acc = E.at<double>(P.nb.acc_off); a.scale = 1.0f / (float)P.d.batch;
+    ok = launch_nb_tail_fwd(a, st);
+    if (algo_bytes) *algo_bytes = b_in + b_g + px * 8 + b_w;
+  } else if (which == 1) {
+    ok = launch_nb_tail_dgrad(a, E.at<__nv_bfloat16>(P.acts[c.in].goff), st);
+    if (algo_bytes) *algo_bytes = b_g + b_in + b_w;
+  } else {
+    ok = launch_nb_tail_wgrad(a, grads_scratch + c.w, grads_scratch + c.bias, st);
+    if (algo_bytes) *algo_bytes = b_g + b_in + b_w;
+  }
+  if (!ok) return fail(MMVAE_ERR_CUDA, "TMA descriptor could not be encoded");
+  return check_launches("mmvae_nb_bench_tail");
+}
+
 int mmvae_backward_range(const mmvae_desc* d, int32_t phase, int64_t* begin, int64_t* end) {
   Plan P;
   if (!P.build(d)) return fail(MMVAE_ERR_BAD_DESC, "%s", P.err.c_str());

@@ -64,6 +64,7 @@ class NotebookVAE(nn.Module):
         self._philox_seed = None
         self._philox_offset = 0
         self.last_eps = None
+        self._grad_sync = None        # set by mmvae_b200.parallel.data_parallel
         self._reset_parameters()
 
     def _desc(self, batch, defer_logits=False):
@@ -215,7 +216,24 @@ class NotebookVAE(nn.Module):
         check(lib.mmvae_nb_loss_backward(byref(desc), _ptr(x), _ptr(y), _ptr(self._arena), _ptr(ws), ws.numel(),
                                          float(kl_weight), _ptr(out), _ptr(self._grads), _stream()),
               "mmvae_nb_loss_backward")
+        if self._grad_sync is not None:                 # data parallel: mean over ranks of the per-shard gradients
+            self._grad_sync.reduce_range(self._grads, 0, self._n_params)
         return out
+
+    DATA_MEAN, DATA_STD = 0.1307, 0.3081               # transforms.Normalize of vae-kl.ipynb cell 2
+
+    @torch.no_grad()
+    def prepare_input(self, frames_u8):
+        """Input side of the loop body on the device (vae-kl.ipynb cell 2 + :211-212): uint8 grey levels [N,S,S] ->
+        x = (frame/255 - 0.1307)/0.3081 as fp32 [N,1,S,S] and the int64 class targets y [N,S,S], one kernel."""
+        self._require_cuda(frames_u8)
+        f = frames_u8.contiguous()
+        n = f.numel()
+        x = torch.empty(f.shape[0], 1, *f.shape[1:], dtype=torch.float32, device=f.device)
+        y = torch.empty(f.shape, dtype=torch.int64, device=f.device)
+        check(lib.mmvae_prepare_input(_ptr(f), n, 255.0 * self.DATA_MEAN, 255.0 * self.DATA_STD, _ptr(x), _ptr(y), _stream()),
+              "mmvae_prepare_input")
+        return x, y
 
     def train_step(self, x, y, kl_weight=1.0, eps=None):
         """forward + loss + backward; returns the device tensor [loss, px_given_z, kl]"""

@@ -70,11 +70,14 @@ class GradSync:
 
 
 def data_parallel(model, group=None, broadcast=True):
-    """Attach gradient averaging to a mmvae_b200.VAE and make the replicas start from rank 0's weights."""
+    """Attach gradient averaging to a mmvae_b200.VAE (three overlapped buckets) or a mmvae_b200.NotebookVAE (its
+    165 k parameters are one 0.66 MB bucket, all-reduced once after the backward call) and make the replicas start
+    from rank 0's weights."""
     sync = GradSync(group)
     if broadcast and sync.world > 1:
         dist.broadcast(model.flat_parameters, src=0, group=group)
-        dist.broadcast(model._bn_arena, src=0, group=group)
+        if getattr(model, "_bn_arena", None) is not None and model._bn_arena.numel():
+            dist.broadcast(model._bn_arena, src=0, group=group)
     model._grad_sync = sync if sync.world > 1 else None
     # decorrelate the rsample noise across ranks: same seed, disjoint Philox counter ranges
     if dist.is_initialized():

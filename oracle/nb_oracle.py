@@ -173,7 +173,7 @@ def make_timed_step(st, cfg: NbConfig):
         n = x.shape[0]
         loss = (F.cross_entropy(logits, y, reduction="none") / n).sum() + kl_sum(mu, logvar) / n
         loss.backward()
-        return float(loss)
+        return float(loss.detach())
 
     return step
 

@@ -72,3 +72,46 @@ def test_shard_bounds_partition():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [e - b for b, e in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _nb_worker(rank, world, port, out):
+    """Notebook variant: NotebookVAE's host-side DP hook (one bucket after the backward call) on CPU-resident
+    gradients from the oracle; oracle = mean over ranks of the per-shard gradients."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import mmvae_b200 as M
+        from mmvae_b200 import parallel as PAR
+        from oracle import nb_oracle as NB
+        cfg = NB.NbConfig(image_size=64)
+        st = NB.init_state(cfg, seed=rank)               # different weights per rank: the broadcast must fix that
+        m = M.NotebookVAE(1, 32, 32, image_size=64, precision="fp32")
+        m.load_state_dict(st)
+        PAR.data_parallel(m)
+        st0 = NB.init_state(cfg, seed=0)
+        assert all(torch.equal(p.detach(), st0[n]) for n, p in m.named_parameters()), "weights must come from rank 0"
+        assert (m._grad_sync is not None) == (world > 1)
+        n_global = 4
+        x, y = NB.synthetic_batch(cfg, n_global, seed=5)
+        eps = torch.randn(n_global, 32, 2, 2, generator=torch.Generator().manual_seed(2))
+        b, e = PAR.shard_bounds(n_global, rank, world)
+        res = NB.train_step(st0, cfg, x[b:e], y[b:e], eps[b:e])
+        flat = torch.zeros(m._n_params)
+        for name, off, shape in m._ptable:
+            flat[off:off + res.grads[name].numel()] = res.grads[name].reshape(-1)
+        mine = flat.clone()
+        m._grad_sync.reduce_range(flat, 0, m._n_params)   # what loss_backward() does after the library call
+        gathered = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        assert torch.allclose(flat, torch.stack(gathered).mean(0), rtol=1e-6, atol=1e-7)
+        out[rank] = True
+    finally:
+        dist.destroy_process_group()
+
+
+def test_notebook_gradient_averaging_world2():
+    world = 2
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_nb_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+        assert all(out.get(r) for r in range(world))
