@@ -124,7 +124,7 @@ def run_reference(args):
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 NB_TRAIN_MFLOP_PER_FRAME = 7714.586624     # notebook variant at 128x128 (mmvae_layout.train_flops)
@@ -158,7 +158,7 @@ def run_reference_notebook(args):
         return
     steps, warm = min(args.steps, 5), min(args.warmup, 1)
     fps, ms, cores, threads = nb_cpu_fps(steps, warm)
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "train frames/sec (fwd+bwd)", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
@@ -166,7 +166,7 @@ def run_reference_notebook(args):
                    "batch_per_step": 4},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
                          "sample": f"{steps} steps of 4 frames of 128x128 on {cores} host cores (median), fp32"},
-        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
 
 
 def main_notebook(args):
@@ -318,14 +318,34 @@ def main_notebook(args):
         line["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": threads, "kind": "port",
                                 "sample": f"3 steps of 4 frames of 128x128 on {cores} host cores, fp32, median"}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         torch.cuda.synchronize()
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def guard_stdout():
+    """Libraries (NCCL's version banner, for one) write to file descriptor 1; the contract is ONE JSON line on stdout.
+    Keep the real stdout aside for that line and send everything else written to fd 1 to stderr."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    guard_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -542,7 +562,7 @@ def main():
         line["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": threads, "kind": "port",
                                 "sample": f"10 steps of 32 frames (BASELINE configs[0]) on {cores} host cores, fp32, median"}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         # The captured graphs hold NCCL work on this communicator: release them before tearing it down (destroying the
         # process group with live graphs deadlocks), and never let a stuck teardown outlive the measurement.
