@@ -47,6 +47,13 @@ int nb_tail_dbg() {
   return v;
 }
 
+// 32-byte store: one full sector per thread and instruction (STG.256)
+__device__ __forceinline__ void st_global_v8(void* ptr, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x),
+               "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -177,6 +184,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) nb_tail_fwd_kernel(const __gri
     const bool ce = p.target != nullptr;
     constexpr float kLog2e = 1.4426950408889634f;
     float loss = 0.f;
+    __nv_bfloat16* pend = nullptr;                     // target element of this thread's previous row, still to be fixed up
     int q = 0;
     for (int band = blockIdx.x; band < p.total_bands; band += gridDim.x) {
       const int n = band / p.bands_per_image, y0 = (band - n * p.bands_per_image) * R;
@@ -244,17 +252,25 @@ __global__ void __launch_bounds__(kFwdThreads, 1) nb_tail_fwd_kernel(const __gri
           uint32_t* pw = reinterpret_cast<uint32_t*>(pk);
 #pragma unroll
           for (int e = 0; e < 16; e += 2) pw[e >> 1] = pack_bf16x2(v[e] * inv, v[e + 1] * inv);
-          reinterpret_cast<uint4*>(orow + g * 16)[0] = pk[0];
-          reinterpret_cast<uint4*>(orow + g * 16)[1] = pk[1];
+          st_global_v8(orow + g * 16, pk[0], pk[1]);
         }
         tc_fence_before();
         mbar_arrive(smem_u32(&tempty[buf]));           // the accumulator is free for output row q + 2
         // the target class: read back this thread's own softmax[target] * scale (the per-class select over 256 register
         // values would cost more than the whole pass), take the log-likelihood from it and subtract the one-hot
-        const float pt = __bfloat162float(*reinterpret_cast<volatile __nv_bfloat16*>(orow + tg));
-        loss -= __logf(fmaxf(pt, 1e-30f) * p.inv_scale);
-        orow[tg] = __float2bfloat16_rn(pt - p.scale);
+        // (deferred by one row: by then the row's stores have drained and the load does not wait for them)
+        if (pend) {
+          const float pt = __bfloat162float(*reinterpret_cast<volatile __nv_bfloat16*>(pend));
+          loss -= __logf(fmaxf(pt, 1e-30f) * p.inv_scale);
+          *pend = __float2bfloat16_rn(pt - p.scale);
+        }
+        pend = orow + tg;
       }
+    }
+    if (pend) {
+      const float pt = __bfloat162float(*reinterpret_cast<volatile __nv_bfloat16*>(pend));
+      loss -= __logf(fmaxf(pt, 1e-30f) * p.inv_scale);
+      *pend = __float2bfloat16_rn(pt - p.scale);
     }
     if (ce) {
 #pragma unroll
@@ -601,11 +617,14 @@ __global__ void __launch_bounds__(kDgThreads, 1) nb_tail_dgrad_kernel(const __gr
         }
         __nv_bfloat16* orow = p.dx + (((size_t)n * p.H + (y0 + oo)) * kW + x) * kCi;
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          uint4 pk;
-          pk.x = pack_bf16x2(t1[h * 8 + 0], t1[h * 8 + 1]); pk.y = pack_bf16x2(t1[h * 8 + 2], t1[h * 8 + 3]);
-          pk.z = pack_bf16x2(t1[h * 8 + 4], t1[h * 8 + 5]); pk.w = pack_bf16x2(t1[h * 8 + 6], t1[h * 8 + 7]);
-          reinterpret_cast<uint4*>(orow)[h] = pk;
+        for (int h = 0; h < 4; h += 2) {
+          uint4 pk[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            pk[u].x = pack_bf16x2(t1[(h + u) * 8 + 0], t1[(h + u) * 8 + 1]); pk[u].y = pack_bf16x2(t1[(h + u) * 8 + 2], t1[(h + u) * 8 + 3]);
+            pk[u].z = pack_bf16x2(t1[(h + u) * 8 + 4], t1[(h + u) * 8 + 5]); pk[u].w = pack_bf16x2(t1[(h + u) * 8 + 6], t1[(h + u) * 8 + 7]);
+          }
+          st_global_v8(orow + h * 8, pk[0], pk[1]);
         }
       }
     }
