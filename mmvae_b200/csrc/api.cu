@@ -327,6 +327,7 @@ struct Exec {
     }
     GConvParams g;
     geom_fprop(c, P.d.batch, g);
+    if (P.d.arch == MMVAE_ARCH_NOTEBOOK) nb_pad_grid(c, g);
     WGradParams w;
     memset(&w, 0, sizeof(w));
     if (c.in < 0) { w.in = x; w.in_nchw_f32 = 1; }
@@ -481,9 +482,17 @@ struct Exec {
   // ---------------- notebook variant (MMVAE_ARCH_NOTEBOOK; vae-kl.ipynb:119-166, loop body :210-233) ----------------
   // No BatchNorm: bias + activation live in the conv epilogue, the activation derivative in the data-gradient epilogue
   // of the consumer (or in the upsample adjoint when an upsample sits between producer and consumer).
+  // A conv whose output is odd-sized (encoder.conv2: 64 -> 31) runs on a gather grid rounded up to the next even size: the
+  // extra row / column of outputs is masked in the epilogues (oy < Ho, ox < Wo) and reads as zero through TMA's
+  // out-of-bounds fill on the dY side, and a 128- / 64-pixel tile of a 32 x 32 grid is a TMA box where one of a 31 x 31 grid
+  // is not (cp.async gather path: 0.2 ms forward, 1.1 ms weight gradient at 512 frames).
+  template <typename G> void nb_pad_grid(const ConvT_& c, G& g) const {
+    if (c.kind == CONV && (c.Ho & 1) && c.Ho > 1) { g.Hg = c.Ho + 1; g.Wg = c.Wo + 1; g.M = P.d.batch * g.Hg * g.Wg; }
+  }
   void nb_conv_fwd(const ConvT_& c, int act_kind) {
     GConvParams g;
     geom_fprop(c, P.d.batch, g);
+    nb_pad_grid(c, g);
     if (c.in < 0) { g.in = x; g.in_nchw_f32 = 1; }
     else g.in = at<T>(act(c.in).off);
     g.out = at<T>(act(c.out).off);

@@ -215,7 +215,8 @@ __global__ void __launch_bounds__(kThreads) wgrad_simt_kernel(const __grid_const
       if (m < m_hi && co < p.Co) {
         int j = m % p.Wg; int tt = m / p.Wg; int i = tt % p.Hg; int n = tt / p.Hg;
         int oy = v.oy0 + p.os * i, ox = v.ox0 + p.os * j;
-        val = to_f(dout[((size_t(n) * p.Ho + oy) * p.Wo + ox) * p.Co + co]);
+        if (oy < p.Ho && ox < p.Wo)                 // gather grids rounded up past an odd-sized output (nb_pad_grid)
+          val = to_f(dout[((size_t(n) * p.Ho + oy) * p.Wo + ox) * p.Co + co]);
       }
       Bs[mm][c] = val;
     }

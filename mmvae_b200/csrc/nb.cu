@@ -40,23 +40,25 @@ __device__ __forceinline__ void store_vec(T* p, const float* v) {
   *reinterpret_cast<uint4*>(p) = r;
 }
 
-// one thread = one 16-byte channel vector of one OUTPUT pixel
+// one thread = one 16-byte channel vector of one INPUT pixel: read once, written f x f times (32-bit index arithmetic)
 template <typename T>
 __global__ void __launch_bounds__(256) nb_upsample_kernel(const T* __restrict__ in, T* __restrict__ out, int H, int W, int C,
                                                          int f, long long total) {
   constexpr int V = Vec<T>::n;
   pdl_wait();
   pdl_trigger();
-  const int cv = C / V;
-  const int Wo = W * f, Ho = H * f;
-  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
-    const int c = (int)(i % cv);
-    long long pix = i / cv;
-    const int ox = (int)(pix % Wo); pix /= Wo;
-    const int oy = (int)(pix % Ho);
-    const long long n = pix / Ho;
-    const uint4 r = __ldg(reinterpret_cast<const uint4*>(in + ((n * H + oy / f) * W + ox / f) * C + c * V));
-    *reinterpret_cast<uint4*>(out + i * V) = r;
+  const unsigned cv = (unsigned)(C / V), uW = (unsigned)W, uH = (unsigned)H;
+  const unsigned Wo = uW * (unsigned)f, Ho = uH * (unsigned)f;
+  for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < (unsigned)total; i += gridDim.x * 256u) {
+    const unsigned c = i % cv;
+    unsigned pix = i / cv;
+    const unsigned x = pix % uW; pix /= uW;
+    const unsigned y = pix % uH;
+    const unsigned n = pix / uH;
+    const uint4 r = __ldg(reinterpret_cast<const uint4*>(in) + i);
+    uint4* o = reinterpret_cast<uint4*>(out) + ((size_t)(n * Ho + y * f) * Wo + x * f) * cv + c;
+    for (int a = 0; a < f; ++a)
+      for (int b = 0; b < f; ++b) o[((size_t)a * Wo + b) * cv] = r;
   }
 }
 
@@ -67,31 +69,32 @@ __global__ void __launch_bounds__(256) nb_upsample_bwd_kernel(const T* __restric
   constexpr int V = Vec<T>::n;
   pdl_wait();
   pdl_trigger();
-  const int cv = C / V;
-  const int Wo = W * f, Ho = H * f;
-  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
-    const int c = (int)(i % cv);
-    long long pix = i / cv;
-    const int x = (int)(pix % W); pix /= W;
-    const int y = (int)(pix % H);
-    const long long n = pix / H;
+  const unsigned cv = (unsigned)(C / V), uW = (unsigned)W, uH = (unsigned)H;
+  const unsigned Wo = uW * (unsigned)f, Ho = uH * (unsigned)f;
+  for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < (unsigned)total; i += gridDim.x * 256u) {
+    const unsigned c = i % cv;
+    unsigned pix = i / cv;
+    const unsigned x = pix % uW; pix /= uW;
+    const unsigned y = pix % uH;
+    const unsigned n = pix / uH;
     float s[V];
 #pragma unroll
     for (int e = 0; e < V; ++e) s[e] = 0.f;
+    const T* src = dup + (((size_t)(n * Ho + y * f) * Wo + x * f) * cv + c) * V;
     for (int dy_ = 0; dy_ < f; ++dy_)
       for (int dx_ = 0; dx_ < f; ++dx_) {
         float v[V];
-        load_vec<T>(dup + ((n * Ho + y * f + dy_) * Wo + x * f + dx_) * C + c * V, v);
+        load_vec<T>(src + ((size_t)dy_ * Wo + dx_) * cv * V, v);
 #pragma unroll
         for (int e = 0; e < V; ++e) s[e] += v[e];
       }
     if (a) {
       float av[V];
-      load_vec<T>(a + i * V, av);
+      load_vec<T>(a + (size_t)i * V, av);
 #pragma unroll
       for (int e = 0; e < V; ++e) s[e] *= act_deriv(act_kind, av[e]);
     }
-    store_vec<T>(dy + i * V, s);
+    store_vec<T>(dy + (size_t)i * V, s);
   }
 }
 
@@ -438,15 +441,15 @@ inline int grid_for(long long work_items, int cap = 148 * 16) {
 
 template <typename T>
 void launch_nb_upsample(const T* in, T* out, int N, int H, int W, int C, int f, cudaStream_t st) {
-  const long long total = (long long)N * H * f * W * f * (C / Vec<T>::n);
+  const long long total = (long long)N * H * W * (C / Vec<T>::n);          // input vectors (< 2^32: 4 GB of bf16 input)
   count_launch();
-  launch_pdl(nb_upsample_kernel<T>, dim3(grid_for(total)), dim3(256), 0, st, in, out, H, W, C, f, total);
+  launch_pdl(nb_upsample_kernel<T>, dim3(grid_for(total, 148 * 8)), dim3(256), 0, st, in, out, H, W, C, f, total);
 }
 template <typename T>
 void launch_nb_upsample_bwd(const T* dup, const T* a, int act_kind, T* dy, int N, int H, int W, int C, int f, cudaStream_t st) {
   const long long total = (long long)N * H * W * (C / Vec<T>::n);
   count_launch();
-  launch_pdl(nb_upsample_bwd_kernel<T>, dim3(grid_for(total)), dim3(256), 0, st, dup, a, act_kind, dy, H, W, C, f, total);
+  launch_pdl(nb_upsample_bwd_kernel<T>, dim3(grid_for(total, 148 * 8)), dim3(256), 0, st, dup, a, act_kind, dy, H, W, C, f, total);
 }
 template <typename T>
 void launch_nb_rsample(const NbSampleArgs& a, cudaStream_t st) {
