@@ -353,13 +353,15 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=None, help="frames per GPU (default 256; 512 for --workload notebook)")
-    ap.add_argument("--workload", default="resnet", choices=["resnet", "notebook"],
-                    help="resnet: model.py VAE, BASELINE configs[1] (the headline); notebook: vae-kl.ipynb VAE on 128x128, configs[4]")
+    ap.add_argument("--workload", default="resnet", choices=["resnet", "widened", "notebook"],
+                    help="resnet: model.py VAE, BASELINE configs[1] (the headline); widened: 2x channels, z=256, 128 frames per GPU, "
+                         "configs[3]; notebook: vae-kl.ipynb VAE on 128x128, configs[4]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.batch is None:
-        args.batch = 512 if args.workload == "notebook" else PER_GPU_BATCH
+        args.batch = {"notebook": 512, "widened": 128}.get(args.workload, PER_GPU_BATCH)
+    width, zdim = (2, 256) if args.workload == "widened" else (1, 64)
     if args.impl == "reference":
         (run_reference_notebook if args.workload == "notebook" else run_reference)(args)
         return
@@ -386,9 +388,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     n = args.batch
     torch.manual_seed(0)
-    model = M.VAE(1, 32, decoder_out_channels=1, pixelcnn_out_channels=0, z_dimension=64, pixelcnn=False,
+    model = M.VAE(1, 32, decoder_out_channels=1, pixelcnn_out_channels=0, z_dimension=zdim, pixelcnn=False,
                   only_pixelcnn=False, nll=1, kl=1, mmd=0, sigma_decoder=0.1, input_image_size=64,
-                  precision=args.precision).to(dev).train()
+                  precision=args.precision, width=width).to(dev).train()
     model.defer_metrics = True
     if world > 1:
         PAR.data_parallel(model)
@@ -481,7 +483,7 @@ def main():
     #                    decoder.uplayer5.0.conv2 (16->16 transposed conv, 256x32x32 -> 256x64x64): forward, data
     #                    gradient, weight gradient -- HBM-bound
     roof, roof_others = None, []
-    if rank == 0 and args.precision == "bf16":
+    if rank == 0 and args.precision == "bf16" and width == 1:          # per-kernel rooflines: the headline configuration only
         import ctypes
         desc, ws, _info = model._workspace(n, True)
         names = [c[0] for c in M._lib.conv_table(desc)]
@@ -535,13 +537,15 @@ def main():
     fps = world * n * args.steps / (ms * 1e-3)
     fps_e2e = world * n * args.steps / (ms_e2e * 1e-3)
     sustained, burst, hbm, which = peaks()
-    tflops_per_gpu = fps / world * TRAIN_MFLOP_PER_FRAME * 1e6 / 1e12
+    mflop_per_frame = M._lib.layout(model._desc(n, True)).train_flops / n / 1e6      # 227.02 base, 896.01 widened
+    tflops_per_gpu = fps / world * mflop_per_frame * 1e6 / 1e12
     line = {
         "metric": "train frames/sec (fwd+bwd)", "value": fps, "unit": "frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
         "data": "synthetic",
-        "config": {"workload": "model.py VAE z=64 64x64 Gaussian-NLL sigma=0.1, fwd+loss+bwd (BASELINE configs[1])",
+        "config": {"workload": ("model.py VAE z=64 64x64 Gaussian-NLL sigma=0.1, fwd+loss+bwd (BASELINE configs[1])" if width == 1 else
+                                "model.py VAE widened 2x channels z=256 64x64 Gaussian-NLL sigma=0.1, fwd+loss+bwd (BASELINE configs[3])"),
                    "frames_per_gpu": n, "global_batch": n * world, "seq_len": 20,
                    "parallelism": f"dp{world}", "precision": args.precision,
                    "launch": "host" if args.no_graph else "cuda-graph replay of the captured step",
@@ -555,7 +559,7 @@ def main():
                                                    "unit": "TFLOP/s", "frac": tflops_per_gpu / sustained, "traffic": None},
         "roofline_others": roof_others,
         "step_tensor": {"achieved": tflops_per_gpu, "peak": sustained, "unit": "TFLOP/s", "frac": tflops_per_gpu / sustained,
-                        "note": f"whole step, 227.02 MFLOP/frame algorithmic, per GPU, of {which} sustained bf16 peak"},
+                        "note": f"whole step, {mflop_per_frame:.2f} MFLOP/frame algorithmic, per GPU, of {which} sustained bf16 peak"},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cfps, cms, cores, threads = cpu_reference_fps(10, 3)

@@ -133,3 +133,49 @@ def test_linearity_in_kl_weight():
             continue
         pred = g0[k] + 3.0 * (g1[k] - g0[k])
         assert float((g3[k] - pred).norm() / g3[k].norm()) < 1e-4, k
+
+
+def test_tail_bench_hook_and_batch_not_multiple_of_grid():
+    """mmvae_nb_bench_tail (bench.py's roofline hook) launches each dedicated decoder.conv4 kernel on the workspace of a
+    finished step and reports its algorithmic work; N = 5 frames (20 bands over 148 CTAs: most CTAs idle, some with
+    one band) against the fp64 oracle exercises the band scheduling at a ragged size."""
+    import ctypes
+    cfg = NB.NbConfig(image_size=128)
+    st = NB.init_state(cfg, seed=6)
+    n = 5
+    x, y = NB.synthetic_batch(cfg, n, seed=11)
+    eps = torch.randn(n, cfg.z_dimensions, cfg.latent_hw, cfg.latent_hw, generator=torch.Generator().manual_seed(8))
+    m = build(cfg, st, "bf16")
+    res = run(m, x, y, eps, 1.0, materialize=False)
+    ref = NB.train_step(st, cfg, x, y, eps, dtype=torch.float64, keep_logits=False)
+    assert abs(res[0] - ref.loss) <= 1e-2 * abs(ref.loss)
+    for k, r in ref.grads.items():
+        if k.startswith("decoder."):
+            assert float((res[7][k].double() - r).norm() / r.norm()) <= 1e-2, k
+    desc, ws, xin = m._state
+    scratch = torch.zeros(m._n_params, dtype=torch.float32, device="cuda")
+    ab, af = ctypes.c_int64(), ctypes.c_int64()
+    yd = y.cuda()
+    for which in (0, 1, 2):
+        M._lib.check(M._lib.lib.mmvae_nb_bench_tail(ctypes.byref(desc), which, ctypes.c_void_p(m.flat_parameters.data_ptr()),
+                                                    ctypes.c_void_p(yd.data_ptr()), ctypes.c_void_p(ws.data_ptr()), ws.numel(),
+                                                    ctypes.c_void_p(scratch.data_ptr()), ctypes.byref(ab), ctypes.byref(af),
+                                                    ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "mmvae_nb_bench_tail")
+        assert af.value == 2 * n * 128 * 128 * 256 * 32 * 9
+        assert ab.value > n * 128 * 128 * 256 * 2
+    torch.cuda.synchronize()
+    # the weight-gradient launch accumulated decoder.conv4's gradient into the scratch arena: same values as the step's
+    off = {nm: (o, s) for nm, o, s in m._ptable}["decoder.conv4.weight"]
+    got = scratch[off[0]:off[0] + 256 * 32 * 9].view(256, 32, 3, 3).cpu()
+    assert float((got - res[7]["decoder.conv4.weight"]).norm() / res[7]["decoder.conv4.weight"].norm()) < 2e-3
+
+
+def test_refuses_cpu_and_bad_shapes():
+    m = M.NotebookVAE(1, 32, 32, image_size=64, precision="bf16").cuda()
+    with pytest.raises(ValueError):
+        m(torch.zeros(2, 1, 32, 32, device="cuda"))
+    with pytest.raises(RuntimeError):
+        m.loss_backward(torch.zeros(2, 64, 64, dtype=torch.int64, device="cuda"))      # no forward yet
+    m(torch.zeros(2, 1, 64, 64, device="cuda"), materialize=False)
+    with pytest.raises(ValueError):
+        m.loss_backward(torch.zeros(2, 32, 32, dtype=torch.int64, device="cuda"))
