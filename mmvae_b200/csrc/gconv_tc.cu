@@ -124,9 +124,15 @@ __global__ void __launch_bounds__(kTcThreads, kBwd ? 2 : 3) gconv_tc_kernel(cons
 
   if (warp < 4) {
     if (p.use_tma) {
-      // ---------------- producer: one thread, TMA boxes ----------------
-      if (tid == 0) {
+      // ---------------- producers: lane 0 of the four warps, TMA boxes ----------------
+      // Issuing one TMA instruction keeps its thread busy for ~0.25 us, so one producer thread caps a deep-K layer at one
+      // k-chunk per ~0.3 us.  Every ring slot has ONE owner thread (slot & 3): all four walk the same chunk sequence and
+      // each issues the chunks that land in its slots (an owner per slot keeps a waiter at most one phase ahead of its
+      // barrier; dealing chunks round-robin regardless of the slot does not).  tc_flags bit 1: single producer (A/B).
+      const int nprod = (p.tc_flags & 2) ? 1 : 4;
+      if (lane == 0 && warp < nprod) {
         const uint64_t tmap = reinterpret_cast<uint64_t>(&p.tmap_a);
+        const int pmask = nprod - 1, pw = warp;
         int stage = 0;
         uint32_t ephase = 1;                    // the first lap over the ring passes immediately
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
@@ -141,28 +147,28 @@ __global__ void __launch_bounds__(kTcThreads, kBwd ? 2 : 3) gconv_tc_kernel(cons
           p.fd_wg.divmod(rem, i0, j0);
           const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(p.wpack) + (size_t)vi * p.wpack_var_stride +
                                       (size_t)((nt * BN) >> 3) * 1024;
-          if (t == (int)blockIdx.x) MMVAE_TRACE(p, 16);
+          if (pw == 0 && t == (int)blockIdx.x) MMVAE_TRACE(p, 16);
           const int xb = j0 * p.is, yb = i0 * p.is;
           const uint32_t* tab = tma_tab + ((vi * p.tc_maxchunks) << sub_shift);
           const size_t wstep = (size_t)p.co_pad * 128;
-          for (int kc = 0; kc < nchunks; ++kc) {
-            MBAR_WAIT(smem_u32(&empty[stage]), ephase);
-            const uint32_t bar = smem_u32(&full[stage]);
-            const int nsub = kc + 1 < nchunks ? (1 << sub_shift) : ((K - kc * 64 + kb - 1) >> kb_log2);
-            mbar_arrive_expect_tx(bar, (uint32_t)(stageB + nsub * sub_bytes));
-            bulk_g2s(b_base + (uint32_t)stage * stageB, wsrc, (uint32_t)stageB, bar);
-            wsrc += wstep;
-            uint32_t dst = a_base + (uint32_t)stage * kStageA;
-            for (int g = 0; g < nsub; ++g, dst += (uint32_t)sub_bytes) {
-              const uint32_t ent = tab[(kc << sub_shift) + g];
-              tma_load_4d(dst, tmap, bar, (int)(ent & 0xffffu), xb + (int)(signed char)(ent >> 16), yb + (int)(signed char)(ent >> 24), n0);
+          for (int kc = 0; kc < nchunks; ++kc, wsrc += wstep) {
+            if ((stage & pmask) == pw) {
+              MBAR_WAIT(smem_u32(&empty[stage]), ephase);
+              const uint32_t bar = smem_u32(&full[stage]);
+              const int nsub = kc + 1 < nchunks ? (1 << sub_shift) : ((K - kc * 64 + kb - 1) >> kb_log2);
+              mbar_arrive_expect_tx(bar, (uint32_t)(stageB + nsub * sub_bytes));
+              bulk_g2s(b_base + (uint32_t)stage * stageB, wsrc, (uint32_t)stageB, bar);
+              uint32_t dst = a_base + (uint32_t)stage * kStageA;
+              for (int g = 0; g < nsub; ++g, dst += (uint32_t)sub_bytes) {
+                const uint32_t ent = tab[(kc << sub_shift) + g];
+                tma_load_4d(dst, tmap, bar, (int)(ent & 0xffffu), xb + (int)(signed char)(ent >> 16), yb + (int)(signed char)(ent >> 24), n0);
+              }
+              if (pw == 0 && t == (int)blockIdx.x && kc == 0) MMVAE_TRACE(p, 3);
             }
             if (++stage == S) { stage = 0; ephase ^= 1u; }
-            if (t == (int)blockIdx.x && kc == 0) MMVAE_TRACE(p, 3);
-            if (t == (int)blockIdx.x && kc == 1) MMVAE_TRACE(p, 17);
           }
         }
-        MMVAE_TRACE(p, 4);
+        if (pw == 0) MMVAE_TRACE(p, 4);
       }
     } else {
       // ---------------- producers: cp.async gather, thread -> 16-byte chunk j of rows rg + 16*i ----------------
