@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(256, 2) tail_fwd_kernel(const TailArgs a) {
 //   g = bf16(dX) * [a > 0] is what gets stored;  S0 = sum g, S1 = sum g * xhat(y), S2 = sum g * xhat(y2) per channel.
 // Thread = (image column x, chunk of 4 channels) of a band of 8 rows; the CI/4 lanes of a pixel are adjacent, so a warp
 // reads / writes 256 contiguous bytes of every NHWC tensor.  Weights (4 x 9) and dW accumulators (4 x 9) in registers.
-template <int CI>
+template <int CI, bool kColBlocks>
 __global__ void __launch_bounds__(256, 2) tail_bwd_kernel(const TailArgs a) {
   pdl_wait();                                       // PDL: may start while the previous kernel drains
   pdl_trigger();
@@ -343,7 +343,10 @@ __global__ void __launch_bounds__(256, 2) tail_bwd_kernel(const TailArgs a) {
   float* red = gs + (a.R + 2) * (a.W + 2);                           // [8 warps][CH][NACC]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int W2 = a.W + 2;
-  const int ch = tid % CH, x = (tid / CH) % a.W, band = tid / (CH * a.W);
+  // a row of W pixels x CH chunks that does not fit the 256 threads (W = 64 with 32 channels: the widened model) is walked in
+  // column blocks of 256 / CH pixels, one band of 8 rows per CTA tile
+  const int cols = kColBlocks ? 256 / CH : a.W;
+  const int ch = tid % CH, xl = (tid / CH) % cols, band = tid / (CH * cols);
   const bool fuse = a.bb.acc != nullptr;
   const bool two = fuse && a.bb.y2 != nullptr;
   float wreg[4][9], accw[4][9], sb[12];
@@ -368,6 +371,8 @@ __global__ void __launch_bounds__(256, 2) tail_bwd_kernel(const TailArgs a) {
     }
     __syncthreads();
     const int r0 = band * 8;
+    for (int xb = 0; xb < (kColBlocks ? a.W : 1); xb += cols) {
+    const int x = xb + xl;
     float gw[3][3];                                  // dY window rows o-1, o, o+1 (tile rows r0+o .. r0+o+2), columns x-1 .. x+1
 #pragma unroll
     for (int i = 0; i < 2; ++i)
@@ -420,6 +425,7 @@ __global__ void __launch_bounds__(256, 2) tail_bwd_kernel(const TailArgs a) {
         const size_t q = (((size_t)n * a.H + oy) * a.W + x) * CH + ch;
         dx[q] = make_uint2(pack2(o4[0], o4[1]), pack2(o4[2], o4[3]));
       }
+    }
     }
   }
   // reduce the per-thread accumulators over the lanes with the same channel chunk, then over the warps
@@ -531,12 +537,14 @@ void launch_stem_wgrad(StemArgs a, int Co, cudaStream_t st) {
 
 bool tail_supported(int Ci, int Co, int H, int k, int s, int p) {
   if (Co != 1 || k != 3 || s != 1 || p != 1 || (Ci != 16 && Ci != 32)) return false;
-  // one band = 8 rows x W columns x (Ci/8 forward, Ci/4 backward) threads must fit 256 threads
-  return H % 8 == 0 && H * (Ci / 4) <= 256 && (256 % (H * (Ci / 4))) == 0;
+  // forward: one band = 8 rows x W columns x Ci/8 threads must fit the 256 threads; backward: W x Ci/4 threads either fit
+  // (whole bands per CTA) or are a multiple of 256 (column blocks, tail_bwd_kernel)
+  const int wf = H * (Ci / 8), wb = H * (Ci / 4);
+  return H % 8 == 0 && wf <= 256 && 256 % wf == 0 && (wb <= 256 ? 256 % wb == 0 : wb % 256 == 0);
 }
 
 static void tail_fill(TailArgs& a, int threads_per_pixel) {
-  const int bands = 256 / (a.W * threads_per_pixel);
+  const int bands = max(1, 256 / (a.W * threads_per_pixel));
   a.R = 8 * bands;
   if (a.R > a.H) a.R = a.H;
   a.tiles_per_frame = (a.H + a.R - 1) / a.R;
@@ -564,8 +572,9 @@ void launch_tail_bwd(TailArgs a, int Ci, cudaStream_t st) {
   const int grid = min(a.ntiles, 148 * 2);
   const size_t smem = sizeof(float) * ((size_t)(a.R + 2) * (a.W + 2) + (size_t)8 * (Ci / 4) * 48);
   count_launch();
-  if (Ci == 16) launch_pdl(tail_bwd_kernel<16>, grid, 256, smem, st, a);
-  else launch_pdl(tail_bwd_kernel<32>, grid, 256, smem, st, a);
+  if (Ci == 16) launch_pdl(tail_bwd_kernel<16, false>, grid, 256, smem, st, a);
+  else if (a.W * (Ci / 4) <= 256) launch_pdl(tail_bwd_kernel<32, false>, grid, 256, smem, st, a);
+  else launch_pdl(tail_bwd_kernel<32, true>, grid, 256, smem, st, a);
 }
 
 void launch_heads_wgrad(const float* dheads, const float* pooled, float* g_mu, float* g_lv, int N, int z, int C,

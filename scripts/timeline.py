@@ -10,10 +10,11 @@ import mmvae_b200 as M
 from mmvae_b200 import data as D
 
 n = int(os.environ.get("N", "256"))
+width = int(os.environ.get("WIDTH", "1"))          # WIDTH=2: the widened model (BASELINE configs[3], z = 256)
 out = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "timeline.csv")
 torch.manual_seed(0)
-model = M.VAE(1, 32, decoder_out_channels=1, pixelcnn_out_channels=0, z_dimension=64, pixelcnn=False, only_pixelcnn=False,
-              sigma_decoder=0.1, input_image_size=64, precision="bf16").cuda().train()
+model = M.VAE(1, 32, decoder_out_channels=1, pixelcnn_out_channels=0, z_dimension=64 if width == 1 else 256, pixelcnn=False,
+              only_pixelcnn=False, sigma_decoder=0.1, input_image_size=64, precision="bf16", width=width).cuda().train()
 model.defer_metrics = True
 largs = types.SimpleNamespace(data_ratio_of_labels=None)
 g = M.GraphedTrainStep(model, n, args=largs, warmup=2)
