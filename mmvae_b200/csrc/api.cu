@@ -534,12 +534,23 @@ struct Exec {
         if (nb_deferred() && !recon) break;           // fused with the cross-entropy in nb_loss_backward
         if (nb_tail_fwd(nullptr, nullptr, 0.f, at<T>(act(P.convs[nb.dc[3]].out).off))) continue;
       }
+      if (nb_mid(P.convs[nb.dc[k]], false, k < 3 ? ACT_ELU : ACT_NONE)) continue;
       nb_conv_fwd(P.convs[nb.dc[k]], k < 3 ? ACT_ELU : ACT_NONE);
     }
     if (recon) {
       const ConvT_& c = P.convs[nb.dc[3]];
       launch_nb_export_nchw<T>(at<T>(act(c.out).off), recon, N, c.Ho * c.Wo, c.Co, st);
     }
+  }
+  // dedicated row-band kernel of the 32 -> 32 3x3 decoder convs (nb_mid_kernel, nb_tail.cu): forward or data gradient
+  bool nb_mid(const ConvT_& c, bool dgrad, int act_kind) {
+    if (!special_ok() || !nb_mid_supported(c.Ci, c.Co, c.Hi, c.Wi, P.d.batch, c.k, c.s, c.p)) return false;
+    NbMidArgs a{};
+    a.in = dgrad ? at<T>(act(c.out).goff) : at<T>(act(c.in).off);
+    a.out = dgrad ? at<T>(act(c.in).goff) : at<T>(act(c.out).off);
+    a.w = params + c.w; a.bias = dgrad ? nullptr : params + c.bias; a.act = act_kind; a.dgrad = dgrad ? 1 : 0;
+    a.N = P.d.batch; a.H = c.Hi; a.W = c.Wi;
+    return launch_nb_mid(a, st);
   }
   bool nb_stem_ok() const {
     const ConvT_& c = P.convs[P.nb.e[0]];
@@ -602,6 +613,7 @@ struct Exec {
         a.out = at<T>(act(c.out).goff); a.w = params + c.w; a.N = N; a.H = c.Hi;
         dg_done = launch_nb_tail_dgrad(a, at<T>(act(c.in).goff), st);
       }
+      if (!dg_done && k < 3) dg_done = nb_mid(c, true, ACT_NONE);
       if (!dg_done) nb_dgrad(c, 0, ACT_NONE, -1);       // -> d(upsampled input)
       const int srci = nb_dec_src(k);
       const ActT& src = act(srci);

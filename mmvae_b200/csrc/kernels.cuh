@@ -385,6 +385,10 @@ struct NbTailArgs {
 };
 bool nb_tail_supported(int Ci, int Co, int H, int W, int k, int s, int pad);
 bool launch_nb_tail_fwd(const NbTailArgs& a, cudaStream_t st);     // false: TMA descriptor could not be encoded
+// the 3x3 / stride 1 / 32 -> 32 decoder convolutions on 64- or 32-pixel rows, forward (bias + act) or data gradient
+struct NbMidArgs { const void* in; const float* w; const float* bias; void* out; int act, dgrad, N, H, W; };
+bool nb_mid_supported(int Ci, int Co, int H, int W, int N, int k, int s, int pad);
+bool launch_nb_mid(const NbMidArgs& a, cudaStream_t st);
 // data gradient: a.out = d logits, a.w = weights -> dx [N][H][128][32] bf16
 bool launch_nb_tail_dgrad(const NbTailArgs& a, void* dx, cudaStream_t st);
 // weight + bias gradient: a.x = upsampled input, a.out = d logits; dw / dbias pre-zeroed, accumulated atomically

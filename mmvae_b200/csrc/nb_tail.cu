@@ -637,6 +637,187 @@ __global__ void __launch_bounds__(kDgThreads, 1) nb_tail_dgrad_kernel(const __gr
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The 3x3 / stride 1 / 32 -> 32 channel convolutions of the decoder (decoder.conv2 on 32x32, decoder.conv3 on 64x64 maps)
+// and their data gradients: same row-band scheme as nb_tail_fwd_kernel (resident weights, every input row staged once per
+// band as three dx-shifted copies, 18 MMAs per 128-pixel tile), N = 32.  Through the generic im2col kernel these layers
+// refetch 72 KB of input + 20 KB of weights per tile from L2 and run at the L2 rate (0.3 ms each at 512 frames of 64x64:
+// 8x their HBM bound).  Image rows are 64 or 32 pixels wide, so one 128-pixel M tile is the SAME row of 2 or 4 consecutive
+// images: one TMA box {32 ch, W px, 1 row, 128/W images} lands contiguously, no pairing of different rows needed.
+//   forward:        out = act(conv(in) + bias)                 Wk[(ky,kx)][ci][co]       = w[co][ci][ky][kx]
+//   data gradient:  out = conv with the flipped, transposed w   Wk[(2-ky,2-kx)][co][ci]  = w[co][ci][ky][kx]   (no bias, no act)
+// ------------------------------------------------------------------------------------------------
+constexpr int kMidSlots = 6;
+constexpr int kMidWBytes = 9 * 32 * 64;     // 18,432
+constexpr int kMidThreads = 288;            // warps 0-3: cp.async producers, warp 4: MMA issue + TMEM owner, warps 5-8: epilogue
+constexpr size_t kMidSmem = (size_t)kMidWBytes + (size_t)kMidSlots * kSlotA + 1024 + 1024;
+
+struct NbMid {
+  const __nv_bfloat16* in;     // input [N][H][W][32] bf16
+  const float* w;              // [32][32][3][3] fp32 (the conv's own weight tensor)
+  const float* bias;           // [32] or nullptr
+  __nv_bfloat16* out;          // [N][H][W][32]
+  int act;                     // ACT_*
+  int dgrad;                   // weights flipped + transposed
+  int H, W, imgs, rows_per_band, bands_per_group, total_bands;
+};
+
+__global__ void __launch_bounds__(kMidThreads, 1) nb_mid_kernel(const __grid_constant__ NbMid p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long full[kMidSlots], empty[kMidSlots], tfull[2], tempty[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float bias_s[32];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t w_base = base, a_base = base + kMidWBytes + 1024 - (kMidWBytes & 1023);
+  unsigned char* w_gen = smem_raw + (base - smem_u32(smem_raw));
+
+  if (tid == 0) {
+    for (int s = 0; s < kMidSlots; ++s) { mbar_init(smem_u32(&full[s]), 128); mbar_init(smem_u32(&empty[s]), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&tfull[b]), 1); mbar_init(smem_u32(&tempty[b]), 128); }
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(smem_u32(&tmem_base_s), 64);
+  for (int e = tid; e < 32 * 32 * 9; e += kMidThreads) {
+    const int co = e / 288, r = e - co * 288;
+    const int ci = r / 9, t = r - ci * 9;
+    // B tile of tap t': rows = output channel o, 32 K values = input channel k
+    const int tp = p.dgrad ? 8 - t : t, o = p.dgrad ? ci : co, k = p.dgrad ? co : ci;
+    *reinterpret_cast<__nv_bfloat16*>(w_gen + (size_t)tp * 2048 + swz_off<64>((uint32_t)o, (uint32_t)(k >> 3)) + (k & 7) * 2) =
+        __float2bfloat16_rn(__ldg(p.w + e));
+  }
+  if (tid < 32) bias_s[tid] = p.bias ? __ldg(p.bias + tid) : 0.f;
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  pdl_wait();
+  pdl_trigger();
+
+  const int R = p.rows_per_band;
+  if (warp < 4) {
+    // ---------------- producers: 128 threads stage one input row as three dx-shifted SWIZZLE_64B copies with cp.async ----------------
+    // (three TMA boxes of 128 x 64-byte rows per tile keep the TMA unit busy ~1.5 us: the row rate, not the bytes, limits
+    // it, and with N = 32 the tensor core needs 0.3 us per tile; the 1536 16-byte cp.async of a row are 12 per thread, the
+    // second and third copy hit L1)
+    const int chunk = tid & 3, rbase = tid >> 2;       // 16-byte chunk of a pixel; tile rows rbase + 32 r
+    constexpr int D = 2;                               // rows in flight before the oldest is published
+    int g = 0, gs = 0;                                 // rows issued / rows signalled
+    for (int band = blockIdx.x; band < p.total_bands; band += gridDim.x) {
+      const int grp = band / p.bands_per_group, y0 = (band - grp * p.bands_per_group) * R;
+      for (int i = 0; i < R + 2; ++i, ++g) {
+        const int slot = g % kMidSlots;
+        mbar_wait(smem_u32(&empty[slot]), (uint32_t)(((g / kMidSlots) & 1) ^ 1));
+        const int y = y0 - 1 + i;
+        const bool yok = (unsigned)y < (unsigned)p.H;
+        const uint32_t dst = a_base + (uint32_t)slot * kSlotA;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int row = rbase + 32 * r;
+          const int img = row / p.W, px = row - img * p.W;
+          const __nv_bfloat16* src = p.in + ((((size_t)grp * p.imgs + img) * p.H + (yok ? y : 0)) * p.W) * 32 + chunk * 8;
+          const uint32_t d = dst + swz_off<64>((uint32_t)row, (uint32_t)chunk);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const int xs = px + c - 1;
+            const bool ok = yok && (unsigned)xs < (unsigned)p.W;
+            cp_async16(d + (uint32_t)c * kCopyA, ok ? (const void*)(src + (size_t)xs * 32) : (const void*)p.in, ok ? 16u : 0u);
+          }
+        }
+        cp_async_commit();
+        if (g - gs >= D) {
+          cp_async_wait<D>();
+          fence_proxy_async_smem();
+          mbar_arrive(smem_u32(&full[gs % kMidSlots]));
+          ++gs;
+        }
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async_smem();
+    for (; gs < g; ++gs) mbar_arrive(smem_u32(&full[gs % kMidSlots]));
+  } else if (warp == 4) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, 32, 0, 0);
+      const uint64_t da0 = make_smem_desc(a_base, 16, 512, SWZ_64);
+      const uint64_t db0 = make_smem_desc(w_base, 16, 512, SWZ_64);
+      int g0 = 0, q = 0;
+      for (int band = blockIdx.x; band < p.total_bands; band += gridDim.x, g0 += R + 2) {
+        for (int o = 0; o < R; ++o, ++q) {
+          const int buf = q & 1;
+          mbar_wait(smem_u32(&tempty[buf]), (uint32_t)(((q >> 1) & 1) ^ 1));
+          tc_fence_after();
+          const uint32_t dtm = tmem + (uint32_t)(buf * 32);
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+            const int g = g0 + o + ky;
+            const uint32_t slot = (uint32_t)(g % kMidSlots);
+            if (o == 0 || ky == 2) {
+              mbar_wait(smem_u32(&full[slot]), (uint32_t)((g / kMidSlots) & 1));
+              tc_fence_after();
+            }
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks) {
+                const uint64_t da = da0 + (uint64_t)((slot * kSlotA + (uint32_t)kx * kCopyA + (uint32_t)ks * 32u) >> 4);
+                const uint64_t db = db0 + (uint64_t)(((uint32_t)(ky * 3 + kx) * 2048u + (uint32_t)ks * 32u) >> 4);
+                mma_bf16(dtm, da, db, idesc, (ky | kx | ks) != 0);
+              }
+            if (ky == 0 && o < R - 1) mma_commit(smem_u32(&empty[slot]));
+          }
+          mma_commit(smem_u32(&tfull[buf]));
+          if (o == R - 1) {
+            mma_commit(smem_u32(&empty[(g0 + R - 1) % kMidSlots]));
+            mma_commit(smem_u32(&empty[(g0 + R) % kMidSlots]));
+            mma_commit(smem_u32(&empty[(g0 + R + 1) % kMidSlots]));
+          }
+        }
+      }
+    }
+  } else {
+    // epilogue: thread = pixel of the tile = (image i, column px) of one row
+    const int lq = warp & 3;
+    const int x = lq * 32 + lane;
+    const int img = x / p.W, px = x - img * p.W;
+    const bool elu = p.act == ACT_ELU, relu = p.act == ACT_RELU;
+    int q = 0;
+    for (int band = blockIdx.x; band < p.total_bands; band += gridDim.x) {
+      const int grp = band / p.bands_per_group, y0 = (band - grp * p.bands_per_group) * R;
+      for (int o = 0; o < R; ++o, ++q) {
+        const int buf = q & 1;
+        mbar_wait(smem_u32(&tfull[buf]), (uint32_t)((q >> 1) & 1));
+        tc_fence_after();
+        float v[32];
+        tmem_ld32(tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * 32), v);
+        tc_fence_before();
+        mbar_arrive(smem_u32(&tempty[buf]));
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          float t = v[e] + bias_s[e];
+          if (elu) t = t > 0.f ? t : ex2_approx(t * 1.4426950408889634f) - 1.0f;   // bf16 output: the approximate exp2 is exact enough
+          else if (relu) t = fmaxf(t, 0.f);
+          v[e] = t;
+        }
+        uint4 pk[4];
+        uint32_t* pw = reinterpret_cast<uint32_t*>(pk);
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) pw[e >> 1] = pack_bf16x2(v[e], v[e + 1]);
+        __nv_bfloat16* orow = p.out + ((((size_t)grp * p.imgs + img) * p.H + (y0 + o)) * p.W + px) * 32;
+        st_global_v8(orow, pk[0], pk[1]);
+        st_global_v8(orow + 16, pk[2], pk[3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 64);
+  }
+}
+
 // ---------------- host: TMA descriptor without swizzle ----------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -690,6 +871,32 @@ bool launch_nb_tail_fwd(const NbTailArgs& a, cudaStream_t st) {
   const int grid = p.total_bands < 148 ? p.total_bands : 148;
   count_launch();
   launch_pdl(nb_tail_fwd_kernel, dim3(grid), dim3(kFwdThreads), kFwdSmem, st, p);
+  return true;
+}
+
+bool nb_mid_supported(int Ci, int Co, int H, int W, int N, int k, int s, int pad) {
+  static const bool off = getenv("MMVAE_NO_NB_MID") != nullptr;
+  if (off || Ci != 32 || Co != 32 || k != 3 || s != 1 || pad != 1 || H != W) return false;
+  if (W != 64 && W != 32) return false;
+  return N % (128 / W) == 0 && H % 32 == 0;
+}
+
+bool launch_nb_mid(const NbMidArgs& a, cudaStream_t st) {
+  NbMid p;
+  memset(&p, 0, sizeof(p));
+  const int imgs = 128 / a.W;
+  p.in = reinterpret_cast<const __nv_bfloat16*>(a.in);
+  p.w = a.w; p.bias = a.bias; p.out = reinterpret_cast<__nv_bfloat16*>(a.out); p.act = a.act; p.dgrad = a.dgrad;
+  p.H = a.H; p.W = a.W; p.imgs = imgs; p.rows_per_band = 32; p.bands_per_group = a.H / 32;
+  p.total_bands = (a.N / imgs) * p.bands_per_group;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(nb_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMidSmem);
+    attr_done = true;
+  }
+  const int grid = p.total_bands < 148 ? p.total_bands : 148;
+  count_launch();
+  launch_pdl(nb_mid_kernel, dim3(grid), dim3(kMidThreads), kMidSmem, st, p);
   return true;
 }
 
