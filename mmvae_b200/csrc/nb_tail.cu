@@ -473,7 +473,7 @@ constexpr int kDgChunkW = 96 * 128;         // bytes of one (ky, 64-class chunk)
 constexpr int kDgWBytes = 3 * 4 * kDgChunkW;   // 147,456
 constexpr int kDgStage = kW * 128;          // one 64-class chunk of a G row: 128 pixels x 128 B
 constexpr int kDgStages = 4;
-constexpr int kDgThreads = 192;
+constexpr int kDgThreads = 320;            // warp 0: TMA producer, warp 1: MMA issue, warps 2-9: two epilogue groups
 constexpr size_t kDgSmem = (size_t)kDgWBytes + (size_t)kDgStages * kDgStage + 1024;
 
 struct NbTailDgrad {
@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) nb_tail_dgrad_kernel(const __gr
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long full[kDgStages], empty[kDgStages], tfull[4], tempty[4];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float edge[2][4][2][kCi];                 // [tile parity][pixel quarter][kx = 0 of lane 0 | kx = 2 of lane 31][ci]
+  __shared__ float edge[4][4][2][kCi];                 // [row & 3][pixel quarter][kx = 0 of lane 0 | kx = 2 of lane 31][ci]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t w_base = base, a_base = base + kDgWBytes;
@@ -572,13 +572,14 @@ __global__ void __launch_bounds__(kDgThreads, 1) nb_tail_dgrad_kernel(const __gr
       }
     }
   } else {
-    // ---------------- epilogue: thread = pixel; kx neighbour exchange, bf16 NHWC store ----------------
-    const int lq = warp & 3;
+    // ---------------- epilogue: thread = pixel; kx neighbour exchange, bf16 NHWC store.  Two warp groups take alternate output rows ----------------
+    const int lq = warp & 3, egrp = (warp - 2) >> 2;
     const int x = lq * 32 + lane;
     int q = 0;
     for (int band = blockIdx.x; band < p.total_bands; band += gridDim.x) {
       const int n = band / p.bands_per_image, y0 = (band - n * p.bands_per_image) * R;
       for (int oo = 0; oo < R; ++oo, ++q) {
+        if ((q & 1) != egrp) continue;
         const int slot = q & 3;
         mbar_wait(smem_u32(&tfull[slot]), (uint32_t)((q >> 2) & 1));
         tc_fence_after();
@@ -596,7 +597,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) nb_tail_dgrad_kernel(const __gr
         }
         tc_fence_before();
         mbar_arrive(smem_u32(&tempty[slot]));
-        float (*eb)[2][kCi] = edge[q & 1];
+        float (*eb)[2][kCi] = edge[q & 3];         // a group's consecutive rows (q, q + 2) use different buffers: one barrier per row
         if (lane == 0) {
 #pragma unroll
           for (int e = 0; e < 32; ++e) eb[lq][0][e] = t0[e];
@@ -605,7 +606,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) nb_tail_dgrad_kernel(const __gr
 #pragma unroll
           for (int e = 0; e < 32; ++e) eb[lq][1][e] = t2[e];
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (egrp == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
         // out[x] = T[x+1][kx=0] + T[x][kx=1] + T[x-1][kx=2]
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
