@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) nb_tail_fwd_kernel(const __gri
   __shared__ __align__(8) unsigned long long full[kSlots], empty[kSlots], tfull[2], tempty[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float bias_s[kCo], ebias_s[kCo];   // bias; exp(bias - max bias)
-  __shared__ float loss_red[8], bmax_s;
+  __shared__ float loss_red[8];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t w_base = base, a_base = base + kWBytes;
@@ -103,7 +103,6 @@ __global__ void __launch_bounds__(kFwdThreads, 1) nb_tail_fwd_kernel(const __gri
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, o));
     for (int c = lane; c < kCo; c += 32) { const float b = __ldg(p.bias + c); bias_s[c] = b; ebias_s[c] = __expf(b - bm); }
-    if (lane == 0) bmax_s = bm;
   }
   fence_proxy_async_smem();
   tc_fence_before();
@@ -299,13 +298,15 @@ __global__ void __launch_bounds__(kFwdThreads, 1) nb_tail_fwd_kernel(const __gri
 // per ky one chain of 8 MMAs (M = 128 = the three dx copies of input row y + ky - 1 stacked along M + 32 don't-care rows,
 // N = 128 classes, K = 16 pixels) into the ky-th of three TMEM accumulators that live for the CTA's whole life.  A CTA owns
 // one half of the classes and every 74th band of rows: G is read from HBM exactly once, the input rows once per class
-// half.  The four otherwise idle warps add up the columns of the G tiles in shared memory (bias gradient) while the
-// tensor core works, then drain the accumulators with red.global.add at the end.
+// half.  The 32 don't-care rows of M read a constant all-ones slice, so rows 96..127 of an accumulator are the sum over
+// pixels of G = the bias gradient, at no extra tensor-core work.  Four warps drain the accumulators with red.global.add at
+// the end.  (A first version column-summed the G tiles from shared memory in the idle warps: +0.25 ms of bank conflicts.)
 // ------------------------------------------------------------------------------------------------
 constexpr int kWgSlotsA = 4, kWgSlotsB = 3;
+constexpr int kWgSlotA = 4 * kCopyA;        // three dx copies of an input row + a constant all-ones slice: the fourth 32-row block of M
 constexpr int kWgSlotB = 2 * kW * 128;      // one row of G for 128 classes: two [128 pixels][64 classes] SWIZZLE_128B tiles
 constexpr int kWgThreads = 192;
-constexpr size_t kWgSmem = (size_t)kWgSlotsA * kSlotA + (size_t)kWgSlotsB * kWgSlotB + 1024;
+constexpr size_t kWgSmem = (size_t)kWgSlotsA * kWgSlotA + (size_t)kWgSlotsB * kWgSlotB + 1024;
 
 struct NbTailWgrad {
   TmaDesc tmap_x;              // upsampled input [N][H][128][32] bf16, box = 32 channels x 128 pixels, SWIZZLE_64B
@@ -322,19 +323,26 @@ __global__ void __launch_bounds__(kWgThreads, 1) nb_tail_wgrad_kernel(const __gr
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t a_base = base, b_base = base + kWgSlotsA * kSlotA;
-  const unsigned char* b_gen = smem_raw + (b_base - smem_u32(smem_raw));
+  const uint32_t a_base = base, b_base = base + kWgSlotsA * kWgSlotA;
+  unsigned char* a_gen = smem_raw + (base - smem_u32(smem_raw));
   const int half = blockIdx.x & 1, worker = blockIdx.x >> 1, nworkers = gridDim.x >> 1;
 
   if (tid == 0) {
     prefetch_tensormap(&p.tmap_x);
     prefetch_tensormap(&p.tmap_g);
     for (int s = 0; s < kWgSlotsA; ++s) { mbar_init(smem_u32(&full_a[s]), 1); mbar_init(smem_u32(&empty_a[s]), 1); }
-    for (int s = 0; s < kWgSlotsB; ++s) { mbar_init(smem_u32(&full_b[s]), 1); mbar_init(smem_u32(&empty_b[s]), 5); }
+    for (int s = 0; s < kWgSlotsB; ++s) { mbar_init(smem_u32(&full_b[s]), 1); mbar_init(smem_u32(&empty_b[s]), 1); }
     mbar_init(smem_u32(&accum), 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), 512);
+  // the fourth slice of every input-row slot is constant 1.0: rows 96..127 of an accumulator become sum over pixels of G, the
+  // bias gradient, at no extra tensor-core work (M = 128 either way); TMA only ever writes slices 0..2
+  for (int e = tid; e < kWgSlotsA * (kCopyA / 4); e += kWgThreads) {
+    const int slot = e / (kCopyA / 4), wd = e - slot * (kCopyA / 4);
+    reinterpret_cast<uint32_t*>(a_gen + (size_t)slot * kWgSlotA + 3 * kCopyA)[wd] = 0x3F803F80u;
+  }
+  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -356,8 +364,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) nb_tail_wgrad_kernel(const __gr
             mbar_wait(smem_u32(&empty_a[slot]), (uint32_t)(((ga / kWgSlotsA) & 1) ^ 1));
             const uint32_t bar = smem_u32(&full_a[slot]);
             if (p.dbg & 2) { mbar_arrive(bar); continue; }
-            mbar_arrive_expect_tx(bar, (uint32_t)kSlotA);
-            const uint32_t dst = a_base + (uint32_t)slot * kSlotA;
+            mbar_arrive_expect_tx(bar, (uint32_t)(3 * kCopyA));
+            const uint32_t dst = a_base + (uint32_t)slot * kWgSlotA;
 #pragma unroll
             for (int c = 0; c < 3; ++c) tma_load_4d(dst + (uint32_t)c * kCopyA, tmx, bar, 0, c - 1, y0 - 1 + i, n);
           }
@@ -392,7 +400,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) nb_tail_wgrad_kernel(const __gr
             const uint32_t slot = (uint32_t)(g % kWgSlotsA);
             if (o == 0 || ky == 2) mbar_wait(smem_u32(&full_a[slot]), (uint32_t)((g / kWgSlotsA) & 1));
             tc_fence_after();
-            const uint64_t da = da0 + (uint64_t)((slot * kSlotA) >> 4);
+            const uint64_t da = da0 + (uint64_t)((slot * kWgSlotA) >> 4);
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks)       // 16 pixels per MMA
               mma_bf16(tmem + (uint32_t)(ky * 128), da + (uint64_t)(ks * 64), db + (uint64_t)(ks * 128), idesc, !(first && ks == 0));
@@ -410,27 +418,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) nb_tail_wgrad_kernel(const __gr
       mma_commit(smem_u32(&accum));
     }
   } else {
-    // ---------------- bias gradient while the tensor core works: thread = class, sums the pixel column of every G tile ----------------
-    const int c = (warp - 2) * 32 + lane;              // class within this CTA's half
-    const uint32_t coff = (uint32_t)(c >> 6) * 16384u + (uint32_t)(c & 7) * 2u;
-    const uint32_t cch = (uint32_t)((c & 63) >> 3);
-    float s0 = 0.f, s1 = 0.f;
-    int gb = 0;
-    for (int band = worker; band < p.total_bands; band += nworkers) {
-      for (int o = 0; o < R; ++o, ++gb) {
-        const int bslot = gb % kWgSlotsB;
-        mbar_wait(smem_u32(&full_b[bslot]), (uint32_t)((gb / kWgSlotsB) & 1));
-        const unsigned char* tile = b_gen + (size_t)bslot * kWgSlotB + coff;
-#pragma unroll 8
-        for (int px = 0; px < ((p.dbg & 1) ? 0 : kW); px += 2) {
-          s0 += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(tile + px * 128 + ((cch ^ (uint32_t)(px & 7)) << 4)));
-          s1 += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(tile + (px + 1) * 128 + ((cch ^ (uint32_t)((px + 1) & 7)) << 4)));
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&empty_b[bslot]));
-      }
-    }
-    if (gb > 0 && p.dbias) atomicAdd(p.dbias + half * 128 + c, s0 + s1);
+    const int gb = (worker < p.total_bands) ? 1 : 0;
     // ---------------- drain the three accumulators: lane m = (kx, ci), column = class ----------------
     if (gb > 0) {
       mbar_wait(smem_u32(&accum), 0);
@@ -445,6 +433,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) nb_tail_wgrad_kernel(const __gr
 #pragma unroll
             for (int e = 0; e < 16; ++e)
               atomicAdd(p.dw + ((size_t)(half * 128 + c0 + e) * kCi + ci) * 9 + ky * 3 + kx, v[e]);
+          } else if (m == 96 && ky == 0 && p.dbias) {          // the all-ones rows: sum over pixels of G = bias gradient
+#pragma unroll
+            for (int e = 0; e < 16; ++e) atomicAdd(p.dbias + half * 128 + c0 + e, v[e]);
           }
         }
       }
