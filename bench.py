@@ -269,7 +269,7 @@ def main_notebook(args):
         names = ["nb_tail_fwd_kernel: decoder.conv4 forward (32->256, 3x3, 128x128) fused with softmax cross-entropy, writes d logits",
                  "nb_tail_dgrad_kernel: decoder.conv4 data gradient (transposed form, col2im in TMEM + epilogue)",
                  "nb_tail_wgrad_kernel: decoder.conv4 weight + bias gradient (pixel axis as K)"]
-        traffic = [4881000000, 5027000000, 4861000000]            # dram read+write per launch, ncu --set full, profiles/r01_nb_tail.md
+        traffic = [4888000000, 5025000000, 4861000000]            # dram read+write per launch, ncu --set full, profiles/r01_nb_tail.md
         for which_k in (0, 2, 1):                                 # d logits must exist before the gradients read them
             def one():
                 M._lib.check(M._lib.lib.mmvae_nb_bench_tail(ctypes.byref(desc), which_k, ctypes.c_void_p(model._arena.data_ptr()),
@@ -289,7 +289,9 @@ def main_notebook(args):
             roofs.append({"bound": "tensor", "unit": "TFLOP/s", "achieved": tfs, "peak": burst, "frac": tfs / burst,
                           "traffic": traffic[which_k], "kernel": names[which_k], "algorithmic_bytes_per_launch": ab.value,
                           "flops_per_launch": af.value, "us_per_launch": us, "gbs": gbs, "hbm_frac": gbs / hbm,
-                          "note": f"of the {which} burst bf16 peak (kernel timed alone); hbm_frac = algorithmic GB/s over the {which} HBM copy peak"})
+                          "note": f"of the {which} burst bf16 peak (kernel timed alone); hbm_frac = algorithmic GB/s over the {which} HBM copy peak"
+                                  + ("; the forward kernel is bound by its 4.26 GB write stream: a pure fill of that size runs at 3.9 TB/s "
+                                     "(scripts/hbm_write_probe.py)" if which_k == 0 else "")})
         roofs.sort(key=lambda r: -r["us_per_launch"])
 
     fps = world * n * args.steps / (ms * 1e-3)
