@@ -604,6 +604,12 @@ struct Exec {
           a.x = at<T>(act(c.in).off); a.out = at<T>(act(c.out).goff); a.N = N; a.H = c.Hi;
           if (!launch_nb_tail_wgrad(a, grads + c.w, ce_bias ? nullptr : grads + c.bias, st)) nb_param_grads(c, !ce_bias);
         });
+      } else if (special_ok() && nb_mid_supported(c.Ci, c.Co, c.Hi, c.Wi, N, c.k, c.s, c.p)) {
+        side([&] {
+          NbMidArgs a{};
+          a.in = at<T>(act(c.in).off); a.N = N; a.H = c.Hi; a.W = c.Wi;
+          if (!launch_nb_mid_wgrad(a, at<T>(act(c.out).goff), grads + c.w, grads + c.bias, st)) nb_param_grads(c);
+        });
       } else {
         side([&] { nb_param_grads(c, !(k == 3 && ce_bias)); });
       }

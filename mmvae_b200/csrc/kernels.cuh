@@ -389,6 +389,8 @@ bool launch_nb_tail_fwd(const NbTailArgs& a, cudaStream_t st);     // false: TMA
 struct NbMidArgs { const void* in; const float* w; const float* bias; void* out; int act, dgrad, N, H, W; };
 bool nb_mid_supported(int Ci, int Co, int H, int W, int N, int k, int s, int pad);
 bool launch_nb_mid(const NbMidArgs& a, cudaStream_t st);
+// their weight + bias gradient: a.in = layer input, dy = gradient of the conv output; dw / dbias pre-zeroed
+bool launch_nb_mid_wgrad(const NbMidArgs& a, const void* dy, float* dw, float* dbias, cudaStream_t st);
 // data gradient: a.out = d logits, a.w = weights -> dx [N][H][128][32] bf16
 bool launch_nb_tail_dgrad(const NbTailArgs& a, void* dx, cudaStream_t st);
 // weight + bias gradient: a.x = upsampled input, a.out = d logits; dw / dbias pre-zeroed, accumulated atomically

@@ -54,6 +54,14 @@ __device__ __forceinline__ void st_global_v8(void* ptr, const uint4& a, const ui
                : "memory");
 }
 
+// CTA budget of the persistent kernels of this file (148 = one per SM); MMVAE_NB_MAX_CTAS lowers it so that a test with a
+// handful of frames still makes every CTA walk several bands.  Read on every launch (tests set and clear it).
+int nb_max_ctas() {
+  const char* e = getenv("MMVAE_NB_MAX_CTAS");
+  const int v = e ? atoi(e) : 148;
+  return v >= 1 && v <= 148 ? v : 148;
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -810,6 +818,187 @@ __global__ void __launch_bounds__(kMidThreads, 1) nb_mid_kernel(const __grid_con
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Weight + bias gradient of the same 32 -> 32 3x3 convs (decoder.conv2 / conv3): nb_tail_wgrad_kernel's scheme with N = 32.
+// Pixel axis = K; per tile (one row of 2 / 4 images = 128 pixels) and ky one chain of 8 MMAs (M = 128 = three dx copies of
+// input row y + ky - 1 + the all-ones slice, N = 32, K = 16 pixels) into three 32-column TMEM accumulators that live for the
+// CTA's whole life; input copies and the dY row are staged with cp.async by 128 threads.  Through the generic
+// wgrad_tc_kernel + column-sum kernel these two layers took 0.73 ms of the auxiliary stream at 512 frames.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMwSlotsA = 4, kMwSlotsB = 4;
+constexpr int kMwSlotB = kW * 64;           // one dY row: 128 pixels x 32 channels, SWIZZLE_64B
+constexpr int kMwThreads = 288;             // warps 0-3: cp.async producers, warp 4: MMA issue + TMEM owner, warps 5-8: final drain
+constexpr size_t kMwSmem = (size_t)kMwSlotsA * kWgSlotA + (size_t)kMwSlotsB * kMwSlotB + 1024;
+
+struct NbMidWgrad {
+  const __nv_bfloat16* in;     // layer input [N][H][W][32]
+  const __nv_bfloat16* dy;     // dY [N][H][W][32]
+  float* dw;                   // [32][32][3][3], accumulated with red.global.add (pre-zeroed)
+  float* dbias;                // [32] or nullptr
+  int H, W, imgs, rows_per_band, bands_per_group, total_bands;
+};
+
+__global__ void __launch_bounds__(kMwThreads, 1) nb_mid_wgrad_kernel(const __grid_constant__ NbMidWgrad p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long full_a[kMwSlotsA], empty_a[kMwSlotsA], full_b[kMwSlotsB], empty_b[kMwSlotsB], accum;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_base = base, b_base = base + kMwSlotsA * kWgSlotA;
+  unsigned char* a_gen = smem_raw + (base - smem_u32(smem_raw));
+
+  if (tid == 0) {
+    for (int s = 0; s < kMwSlotsA; ++s) { mbar_init(smem_u32(&full_a[s]), 128); mbar_init(smem_u32(&empty_a[s]), 1); }
+    for (int s = 0; s < kMwSlotsB; ++s) { mbar_init(smem_u32(&full_b[s]), 128); mbar_init(smem_u32(&empty_b[s]), 1); }
+    mbar_init(smem_u32(&accum), 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(smem_u32(&tmem_base_s), 128);
+  for (int e = tid; e < kMwSlotsA * (kCopyA / 4); e += kMwThreads) {          // the constant all-ones fourth slice of every slot
+    const int slot = e / (kCopyA / 4), wd = e - slot * (kCopyA / 4);
+    reinterpret_cast<uint32_t*>(a_gen + (size_t)slot * kWgSlotA + 3 * kCopyA)[wd] = 0x3F803F80u;
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  pdl_wait();
+  pdl_trigger();
+
+  const int R = p.rows_per_band;
+  if (warp < 4) {
+    // ---------------- producers: per output row o the input row o + 2 (rows 0, 1, 2 at o = 0) and dY row o; one cp.async
+    // group per staged row, published two groups later ----------------
+    const int chunk = tid & 3, rbase = tid >> 2;
+    constexpr int D = 2;
+    int ga = 0, gb = 0;                                // input rows / dY rows issued
+    uint32_t pend[D + 1];                              // barriers of the groups in flight, oldest first
+    int npend = 0;
+    auto publish_oldest = [&]() {
+      fence_proxy_async_smem();
+      mbar_arrive(pend[0]);
+#pragma unroll
+      for (int i = 0; i < D; ++i) pend[i] = pend[i + 1];
+      --npend;
+    };
+    auto commit = [&](uint32_t bar) {
+      cp_async_commit();
+      pend[npend++] = bar;
+      if (npend > D) { cp_async_wait<D>(); publish_oldest(); }
+    };
+    // Before blocking on a slot that is still in use, publish everything staged so far: at a band boundary the MMA thread
+    // needs the last dY row of the old band (still among the unpublished groups) to release the slots the new band waits for.
+    auto wait_free = [&](uint32_t bar, uint32_t parity) {
+      if (!mbar_try_wait(bar, parity)) {
+        cp_async_wait<0>();
+        while (npend > 0) publish_oldest();
+        mbar_wait(bar, parity);
+      }
+    };
+    for (int band = blockIdx.x; band < p.total_bands; band += gridDim.x) {
+      const int grp = band / p.bands_per_group, y0 = (band - grp * p.bands_per_group) * R;
+      for (int o = 0; o < R; ++o) {
+        for (int i = (o == 0 ? 0 : o + 2); i <= o + 2; ++i, ++ga) {
+          const int slot = ga % kMwSlotsA;
+          wait_free(smem_u32(&empty_a[slot]), (uint32_t)(((ga / kMwSlotsA) & 1) ^ 1));
+          const int y = y0 - 1 + i;
+          const bool yok = (unsigned)y < (unsigned)p.H;
+          const uint32_t dst = a_base + (uint32_t)slot * kWgSlotA;
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const int row = rbase + 32 * r;
+            const int img = row / p.W, px = row - img * p.W;
+            const __nv_bfloat16* src = p.in + ((((size_t)grp * p.imgs + img) * p.H + (yok ? y : 0)) * p.W) * 32 + chunk * 8;
+            const uint32_t d = dst + swz_off<64>((uint32_t)row, (uint32_t)chunk);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const int xs = px + c - 1;
+              const bool ok = yok && (unsigned)xs < (unsigned)p.W;
+              cp_async16(d + (uint32_t)c * kCopyA, ok ? (const void*)(src + (size_t)xs * 32) : (const void*)p.in, ok ? 16u : 0u);
+            }
+          }
+          commit(smem_u32(&full_a[slot]));
+        }
+        const int slot = gb % kMwSlotsB;
+        wait_free(smem_u32(&empty_b[slot]), (uint32_t)(((gb / kMwSlotsB) & 1) ^ 1));
+        const uint32_t dst = b_base + (uint32_t)slot * kMwSlotB;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int row = rbase + 32 * r;
+          const int img = row / p.W, px = row - img * p.W;
+          const __nv_bfloat16* src = p.dy + ((((size_t)grp * p.imgs + img) * p.H + (y0 + o)) * p.W + px) * 32 + chunk * 8;
+          cp_async16(dst + swz_off<64>((uint32_t)row, (uint32_t)chunk), src, 16u);
+        }
+        commit(smem_u32(&full_b[slot]));
+        ++gb;
+      }
+    }
+    cp_async_wait<0>();
+    while (npend > 0) publish_oldest();
+  } else if (warp == 4) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, 32, 1, 1);
+      const uint64_t da0 = make_smem_desc(a_base, kCopyA, 512, SWZ_64);        // M: 4 x 32 channels, one slice apart
+      const uint64_t db0 = make_smem_desc(b_base, 512, 512, SWZ_64);           // N: 32 channels = one atom
+      int g0 = 0, gb = 0;
+      bool first = true;
+      for (int band = blockIdx.x; band < p.total_bands; band += gridDim.x, g0 += R + 2) {
+        for (int o = 0; o < R; ++o, ++gb) {
+          const uint32_t bslot = (uint32_t)(gb % kMwSlotsB);
+          const uint64_t db = db0 + (uint64_t)((bslot * kMwSlotB) >> 4);
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+            const int g = g0 + o + ky;
+            const uint32_t slot = (uint32_t)(g % kMwSlotsA);
+            if (o == 0 || ky == 2) mbar_wait(smem_u32(&full_a[slot]), (uint32_t)((g / kMwSlotsA) & 1));
+            // the dY row is staged after input row o + 2: wait for it before the first chain that can run (ky = 0 needs rows
+            // that arrived earlier, but the chain also reads dY)
+            if (ky == 0) mbar_wait(smem_u32(&full_b[bslot]), (uint32_t)((gb / kMwSlotsB) & 1));
+            tc_fence_after();
+            const uint64_t da = da0 + (uint64_t)((slot * kWgSlotA) >> 4);
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+              mma_bf16(tmem + (uint32_t)(ky * 32), da + (uint64_t)(ks * 64), db + (uint64_t)(ks * 64), idesc, !(first && ks == 0));
+            if (ky == 0 && o < R - 1) mma_commit(smem_u32(&empty_a[slot]));
+          }
+          first = false;
+          mma_commit(smem_u32(&empty_b[bslot]));
+          if (o == R - 1) {
+            mma_commit(smem_u32(&empty_a[(g0 + R - 1) % kMwSlotsA]));
+            mma_commit(smem_u32(&empty_a[(g0 + R) % kMwSlotsA]));
+            mma_commit(smem_u32(&empty_a[(g0 + R + 1) % kMwSlotsA]));
+          }
+        }
+      }
+      mma_commit(smem_u32(&accum));
+    }
+  } else if ((int)blockIdx.x < p.total_bands) {
+    // ---------------- drain: lane m = (kx, ci) or the all-ones rows, column = co ----------------
+    mbar_wait(smem_u32(&accum), 0);
+    tc_fence_after();
+    const int lq = warp & 3, m = lq * 32 + lane;
+    const int kx = m >> 5, ci = m & 31;
+    for (int ky = 0; ky < 3; ++ky) {
+      float v[32];
+      tmem_ld32(tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(ky * 32), v);
+      if (m < 96) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) atomicAdd(p.dw + ((size_t)e * 32 + ci) * 9 + ky * 3 + kx, v[e]);
+      } else if (m == 96 && ky == 0 && p.dbias) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) atomicAdd(p.dbias + e, v[e]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 128);
+  }
+}
+
 // ---------------- host: TMA descriptor without swizzle ----------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -860,7 +1049,7 @@ bool launch_nb_tail_fwd(const NbTailArgs& a, cudaStream_t st) {
     cudaFuncSetAttribute(nb_tail_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem);
     attr_done = true;
   }
-  const int grid = p.total_bands < 148 ? p.total_bands : 148;
+  const int grid = p.total_bands < nb_max_ctas() ? p.total_bands : nb_max_ctas();
   count_launch();
   launch_pdl(nb_tail_fwd_kernel, dim3(grid), dim3(kFwdThreads), kFwdSmem, st, p);
   return true;
@@ -886,9 +1075,28 @@ bool launch_nb_mid(const NbMidArgs& a, cudaStream_t st) {
     cudaFuncSetAttribute(nb_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMidSmem);
     attr_done = true;
   }
-  const int grid = p.total_bands < 148 ? p.total_bands : 148;
+  const int grid = p.total_bands < nb_max_ctas() ? p.total_bands : nb_max_ctas();
   count_launch();
   launch_pdl(nb_mid_kernel, dim3(grid), dim3(kMidThreads), kMidSmem, st, p);
+  return true;
+}
+
+bool launch_nb_mid_wgrad(const NbMidArgs& a, const void* dy, float* dw, float* dbias, cudaStream_t st) {
+  NbMidWgrad p;
+  memset(&p, 0, sizeof(p));
+  const int imgs = 128 / a.W;
+  p.in = reinterpret_cast<const __nv_bfloat16*>(a.in); p.dy = reinterpret_cast<const __nv_bfloat16*>(dy);
+  p.dw = dw; p.dbias = dbias;
+  p.H = a.H; p.W = a.W; p.imgs = imgs; p.rows_per_band = 32; p.bands_per_group = a.H / 32;
+  p.total_bands = (a.N / imgs) * p.bands_per_group;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(nb_mid_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMwSmem);
+    attr_done = true;
+  }
+  const int grid = p.total_bands < nb_max_ctas() ? p.total_bands : nb_max_ctas();
+  count_launch();
+  launch_pdl(nb_mid_wgrad_kernel, dim3(grid), dim3(kMwThreads), kMwSmem, st, p);
   return true;
 }
 
@@ -904,7 +1112,7 @@ bool launch_nb_tail_dgrad(const NbTailArgs& a, void* dx, cudaStream_t st) {
     cudaFuncSetAttribute(nb_tail_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDgSmem);
     attr_done = true;
   }
-  const int grid = p.total_bands < 148 ? p.total_bands : 148;
+  const int grid = p.total_bands < nb_max_ctas() ? p.total_bands : nb_max_ctas();
   count_launch();
   launch_pdl(nb_tail_dgrad_kernel, dim3(grid), dim3(kDgThreads), kDgSmem, st, p);
   return true;
@@ -923,7 +1131,8 @@ bool launch_nb_tail_wgrad(const NbTailArgs& a, float* dw, float* dbias, cudaStre
     cudaFuncSetAttribute(nb_tail_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgSmem);
     attr_done = true;
   }
-  const int workers = p.total_bands < 74 ? p.total_bands : 74;
+  const int wcap = nb_max_ctas() >= 2 ? nb_max_ctas() / 2 : 1;
+  const int workers = p.total_bands < wcap ? p.total_bands : wcap;
   count_launch();
   launch_pdl(nb_tail_wgrad_kernel, dim3(2 * workers), dim3(kWgThreads), kWgSmem, st, p);
   return true;

@@ -179,3 +179,25 @@ def test_refuses_cpu_and_bad_shapes():
     m(torch.zeros(2, 1, 64, 64, device="cuda"), materialize=False)
     with pytest.raises(ValueError):
         m.loss_backward(torch.zeros(2, 32, 32, dtype=torch.int64, device="cuda"))
+
+
+def test_mid_kernels_with_several_bands_per_cta():
+    """nb_mid_kernel / nb_mid_wgrad_kernel with 4-image row groups (32-pixel rows need N % 4 == 0) and more bands than CTAs
+    per launch would need N > 296 at 128x128; instead run N = 8 with the grid capped through MMVAE_NB_MAX_CTAS so that every
+    CTA walks several bands (ring slots and accumulators carry over band boundaries), against the fp64 oracle."""
+    import os
+    cfg = NB.NbConfig(image_size=128)
+    st = NB.init_state(cfg, seed=9)
+    n = 8
+    x, y = NB.synthetic_batch(cfg, n, seed=21)
+    eps = torch.randn(n, cfg.z_dimensions, cfg.latent_hw, cfg.latent_hw, generator=torch.Generator().manual_seed(5))
+    ref = NB.train_step(st, cfg, x, y, eps, dtype=torch.float64, keep_logits=False)
+    os.environ["MMVAE_NB_MAX_CTAS"] = "3"
+    try:
+        res = run(build(cfg, st, "bf16"), x, y, eps, 1.0, materialize=False)
+    finally:
+        del os.environ["MMVAE_NB_MAX_CTAS"]
+    assert abs(res[0] - ref.loss) <= 1e-2 * abs(ref.loss)
+    for k, r in ref.grads.items():
+        if k.startswith("decoder."):
+            assert float((res[7][k].double() - r).norm() / r.norm()) <= 1e-2, k
