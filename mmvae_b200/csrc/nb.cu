@@ -383,8 +383,11 @@ __global__ void __launch_bounds__(256) nb_stem_fwd_kernel(const float* __restric
   }
 }
 
-// weight + bias gradient: lane = output channel, warp w owns taps {w, w+8, w+16, w+24}; dY tile (bf16) and input window in
-// shared memory; sums stay in registers over all tiles of the CTA, one atomicAdd per (tap, channel) and CTA at the end
+// weight + bias gradient: lane = output channel, warp = one of the tile's 8 output rows.  The warp slides a 5 x 5 input window
+// along its row in registers (stride 2: ten new values per pixel, broadcast shared-memory loads) and keeps all 25 tap sums
+// of its channel in registers over every tile of the CTA: 11 shared-memory loads per 25 FMAs (a first version with warp =
+// tap group and one load per FMA was bound by the shared-memory pipe: 0.375 ms).  One cross-warp reduction through shared
+// memory and one atomicAdd per (tap, channel) per CTA at the end.
 __global__ void __launch_bounds__(256) nb_stem_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
                                                            float* __restrict__ dw, float* __restrict__ dbias, int N, int S) {
   __shared__ float xs[(2 * kStemRows + 3) * kStemPitch];
@@ -394,14 +397,9 @@ __global__ void __launch_bounds__(256) nb_stem_wgrad_kernel(const float* __restr
   const int Wo = S / 2, Ho = S / 2, tiles_per_frame = Ho / kStemRows;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int npix = kStemRows * Wo;
-  int toff[4];
+  float acc[25], bsum = 0.f;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int t = warp + 8 * j;
-    toff[j] = t < 25 ? (t / 5) * kStemPitch + (t % 5) : 0;
-  }
-  const bool four = warp == 0;                         // only warp 0 has a fourth tap (24)
-  float acc[4] = {0.f, 0.f, 0.f, 0.f}, bsum = 0.f;
+  for (int t = 0; t < 25; ++t) acc[t] = 0.f;
   for (int tile = blockIdx.x; tile < N * tiles_per_frame; tile += gridDim.x) {
     const int n = tile / tiles_per_frame, oy0 = (tile - n * tiles_per_frame) * kStemRows;
     __syncthreads();
@@ -409,27 +407,44 @@ __global__ void __launch_bounds__(256) nb_stem_wgrad_kernel(const float* __restr
     const uint4* src = reinterpret_cast<const uint4*>(dy + ((size_t)n * Ho + oy0) * Wo * 32);
     for (int e = threadIdx.x; e < npix * 4; e += 256) reinterpret_cast<uint4*>(dys)[e] = __ldg(src + e);
     __syncthreads();
-    for (int py = 0; py < kStemRows; ++py) {
-      const float* xr = xs + (2 * py) * kStemPitch;
-      const __nv_bfloat16* dr = dys + (size_t)py * Wo * 32 + lane;
-#pragma unroll 4
-      for (int pxx = 0; pxx < Wo; ++pxx) {
-        const float g = __bfloat162float(dr[pxx * 32]);
-        const float* xp = xr + 2 * pxx;
-        acc[0] = fmaf(xp[toff[0]], g, acc[0]);
-        acc[1] = fmaf(xp[toff[1]], g, acc[1]);
-        acc[2] = fmaf(xp[toff[2]], g, acc[2]);
-        if (four) acc[3] = fmaf(xp[toff[3]], g, acc[3]);
-        if (warp == 7) bsum += g;
+    const float* xr = xs + (2 * warp) * kStemPitch;      // input rows 2 py .. 2 py + 4 of output row py = warp
+    const __nv_bfloat16* dr = dys + (size_t)warp * Wo * 32 + lane;
+    float win[5][5];
+#pragma unroll
+    for (int r = 0; r < 5; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) win[r][c + 2] = xr[r * kStemPitch + c];      // columns 0..2 sit where the first shift puts them
+#pragma unroll 2
+    for (int pxx = 0; pxx < Wo; ++pxx) {
+#pragma unroll
+      for (int r = 0; r < 5; ++r) {
+        win[r][0] = win[r][2]; win[r][1] = win[r][3]; win[r][2] = win[r][4];
+        win[r][3] = xr[r * kStemPitch + 2 * pxx + 3];
+        win[r][4] = xr[r * kStemPitch + 2 * pxx + 4];
       }
+      const float g = __bfloat162float(dr[pxx * 32]);
+      bsum += g;
+#pragma unroll
+      for (int r = 0; r < 5; ++r)
+#pragma unroll
+        for (int c = 0; c < 5; ++c) acc[r * 5 + c] = fmaf(win[r][c], g, acc[r * 5 + c]);
     }
   }
+  // cross-warp reduction: the dY buffer is free now
+  __syncthreads();
+  float* red = reinterpret_cast<float*>(dys);            // [8 warps][26][32]
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int t = warp + 8 * j;
-    if (t < 25) atomicAdd(dw + lane * 25 + t, acc[j]);
+  for (int t = 0; t < 25; ++t) red[(warp * 26 + t) * 32 + lane] = acc[t];
+  red[(warp * 26 + 25) * 32 + lane] = bsum;
+  __syncthreads();
+  for (int e = threadIdx.x; e < 26 * 32; e += 256) {
+    const int t = e >> 5, co = e & 31;
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += red[(w * 26 + t) * 32 + co];
+    if (t < 25) atomicAdd(dw + co * 25 + t, v);
+    else if (dbias) atomicAdd(dbias + co, v);
   }
-  if (warp == 7 && dbias) atomicAdd(dbias + lane, bsum);
 }
 
 inline int grid_for(long long work_items, int cap = 148 * 16) {
