@@ -338,11 +338,29 @@ __device__ __forceinline__ void nb_stem_load_x(const float* __restrict__ x, floa
   }
 }
 
+// the same window through 4-byte cp.async (zero fill outside the image): the next tile loads while the current one computes
+template <int CO>
+__device__ __forceinline__ void nb_stem_prefetch_x(const float* __restrict__ x, float* xs, int n, int oy0, int S, int Wo) {
+  const int rows = 2 * kStemRows + 3, cols = 2 * Wo + 3;
+  const float* img = x + (size_t)n * S * S;
+  const unsigned base = (unsigned)__cvta_generic_to_shared(xs);
+  for (int e = threadIdx.x; e < rows * cols; e += 256) {
+    const int r = e / cols, c = e - r * cols;
+    const int iy = 2 * oy0 - 2 + r, ix = c - 2;
+    const bool ok = (unsigned)iy < (unsigned)S && (unsigned)ix < (unsigned)S;
+    const float* src = ok ? img + (size_t)iy * S + ix : x;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(base + (unsigned)(r * kStemPitch + c) * 4u), "l"(src),
+                 "r"(ok ? 4u : 0u)
+                 : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
 // forward: warp = 8 output channels, lanes = 32 consecutive pixels of the tile; weights broadcast from shared memory
 __global__ void __launch_bounds__(256) nb_stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                          const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int N,
                                                          int S) {
-  __shared__ float xs[(2 * kStemRows + 3) * kStemPitch];
+  __shared__ float xs2[2][(2 * kStemRows + 3) * kStemPitch];
   __shared__ __align__(16) float ws[25][32];
   __shared__ float bs[32];
   const int Wo = S / 2, Ho = S / 2, tiles_per_frame = Ho / kStemRows;
@@ -352,12 +370,21 @@ __global__ void __launch_bounds__(256) nb_stem_fwd_kernel(const float* __restric
   pdl_trigger();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cg = warp & 3, half = warp >> 2;           // channel group of 8; which half of the tile's pixel chunks
-  const int npix = kStemRows * Wo;
-  for (int tile = blockIdx.x; tile < N * tiles_per_frame; tile += gridDim.x) {
+  const int npix = kStemRows * Wo, ntiles = N * tiles_per_frame;
+  int buf = 0;
+  if ((int)blockIdx.x < ntiles)
+    nb_stem_prefetch_x<32>(x, xs2[0], blockIdx.x / tiles_per_frame, (blockIdx.x % tiles_per_frame) * kStemRows, S, Wo);
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
     const int n = tile / tiles_per_frame, oy0 = (tile - n * tiles_per_frame) * kStemRows;
+    const int next = tile + gridDim.x;
+    if (next < ntiles) {                               // the other buffer was released by the barrier that ended the previous tile
+      nb_stem_prefetch_x<32>(x, xs2[buf ^ 1], next / tiles_per_frame, (next % tiles_per_frame) * kStemRows, S, Wo);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
     __syncthreads();
-    nb_stem_load_x<32>(x, xs, n, oy0, S, Wo);
-    __syncthreads();
+    const float* xs = xs2[buf];
     for (int p0 = half * 32; p0 < npix; p0 += 64) {
       const int px = p0 + lane, py = px / Wo, pxx = px - py * Wo;
       float acc[8];
@@ -380,6 +407,7 @@ __global__ void __launch_bounds__(256) nb_stem_fwd_kernel(const float* __restric
       for (int c = 0; c < 4; ++c) pw[c] = __floats2bfloat162_rn(fmaxf(acc[2 * c], 0.f), fmaxf(acc[2 * c + 1], 0.f));
       *reinterpret_cast<uint4*>(out + (((size_t)n * Ho + oy0 + py) * Wo + pxx) * 32 + cg * 8) = pk;
     }
+    __syncthreads();                                   // everyone is done with this buffer before it is refilled
   }
 }
 
