@@ -124,6 +124,21 @@ __device__ __forceinline__ void load_grad(const void* dA, int is_f32, size_t off
   }
 }
 
+// VEC consecutive per-channel coefficients (c0 % VEC == 0, arrays 16-byte aligned): 128-bit loads instead of VEC scalar ones
+template <int VEC>
+__device__ __forceinline__ void load_coef(const float* __restrict__ p, float (&v)[VEC]) {
+  if constexpr (VEC % 4 == 0) {
+#pragma unroll
+    for (int k = 0; k < VEC; k += 4) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(p + k));
+      v[k] = t.x; v[k + 1] = t.y; v[k + 2] = t.z; v[k + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) v[k] = __ldg(p + k);
+  }
+}
+
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ y, const float* __restrict__ coef,
                                                        const T* __restrict__ y2, const float* __restrict__ coef2,
@@ -133,13 +148,16 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ y, 
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < nvec; i += gridDim.x * 256LL) {
     int c0 = (int)((i * VEC) % C);
     float v[VEC], r[VEC];
+    float sc[VEC], sh[VEC];
     load_vec<T, VEC>(y + i * VEC, v);
+    load_coef<VEC>(coef + c0, sc); load_coef<VEC>(coef + C + c0, sh);
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) r[k] = fmaf(v[k], __ldg(coef + c0 + k), __ldg(coef + C + c0 + k));
+    for (int k = 0; k < VEC; ++k) r[k] = fmaf(v[k], sc[k], sh[k]);
     if (y2) {
       load_vec<T, VEC>(y2 + i * VEC, v);
+      load_coef<VEC>(coef2 + c0, sc); load_coef<VEC>(coef2 + C + c0, sh);
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) r[k] += fmaf(v[k], __ldg(coef2 + c0 + k), __ldg(coef2 + C + c0 + k));
+      for (int k = 0; k < VEC; ++k) r[k] += fmaf(v[k], sc[k], sh[k]);
     }
     if (relu) {
 #pragma unroll
@@ -398,20 +416,26 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a) {
       for (int k = 0; k < VEC; ++k) g[k] = av[k] > 0.f ? g[k] : 0.f;
     }
     load_vec<T, VEC>(reinterpret_cast<const T*>(a.y) + off, yv);
+    {
+      float mean[VEC], rstd[VEC], b0[VEC], b1[VEC], b2[VEC];
+      load_coef<VEC>(a.stat + c0, mean); load_coef<VEC>(a.stat + a.C + c0, rstd);
+      load_coef<VEC>(a.bcoef + c0, b0); load_coef<VEC>(a.bcoef + a.C + c0, b1); load_coef<VEC>(a.bcoef + 2 * a.C + c0, b2);
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) {
-      int c = c0 + k;
-      float xh = (yv[k] - __ldg(a.stat + c)) * __ldg(a.stat + a.C + c);
-      o[k] = __ldg(a.bcoef + c) * (g[k] - __ldg(a.bcoef + a.C + c) - xh * __ldg(a.bcoef + 2 * a.C + c));
+      for (int k = 0; k < VEC; ++k) {
+        float xh = (yv[k] - mean[k]) * rstd[k];
+        o[k] = b0[k] * (g[k] - b1[k] - xh * b2[k]);
+      }
     }
     store_vec<T, VEC>(reinterpret_cast<T*>(a.dY) + off, o);
     if (a.y2) {
       load_vec<T, VEC>(reinterpret_cast<const T*>(a.y2) + off, yv);
+      float mean[VEC], rstd[VEC], b0[VEC], b1[VEC], b2[VEC];
+      load_coef<VEC>(a.stat2 + c0, mean); load_coef<VEC>(a.stat2 + a.C + c0, rstd);
+      load_coef<VEC>(a.bcoef2 + c0, b0); load_coef<VEC>(a.bcoef2 + a.C + c0, b1); load_coef<VEC>(a.bcoef2 + 2 * a.C + c0, b2);
 #pragma unroll
       for (int k = 0; k < VEC; ++k) {
-        int c = c0 + k;
-        float xh = (yv[k] - __ldg(a.stat2 + c)) * __ldg(a.stat2 + a.C + c);
-        o[k] = __ldg(a.bcoef2 + c) * (g[k] - __ldg(a.bcoef2 + a.C + c) - xh * __ldg(a.bcoef2 + 2 * a.C + c));
+        float xh = (yv[k] - mean[k]) * rstd[k];
+        o[k] = b0[k] * (g[k] - b1[k] - xh * b2[k]);
       }
       store_vec<T, VEC>(reinterpret_cast<T*>(a.dY2) + off, o);
     }
