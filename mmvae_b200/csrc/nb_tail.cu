@@ -251,16 +251,44 @@ __global__ void __launch_bounds__(kFwdThreads, 1) nb_tail_fwd_kernel(const __gri
         tmem_st_wait();
         // pass 3: d logits (without the one-hot) = softmax * scale
         const float inv = p.scale / (sum0 + sum1);
-#pragma unroll 2
-        for (int g = 0; g < 16; ++g) {
-          float v[16];
-          tmem_ld16(tl + (uint32_t)(g * 16), v);
-          uint4 pk[2];
-          uint32_t* pw = reinterpret_cast<uint32_t*>(pk);
+        // A thread owns a pixel (= 512-byte row of the output), so a plain store instruction of the warp touches 32 rows,
+        // one 32-byte sector each: the store path, not HBM, then bounds the kernel.  Each 64-class block is therefore
+        // transposed inside the lane quad first (4 x 4 units of 16 classes = 32 bytes, two shuffle stages): afterwards lane
+        // j of the quad holds unit j of all four pixels, and store instruction m writes pixel m of every quad with four
+        // adjacent 32-byte pieces: 8 full 128-byte lines per instruction instead of 32 quarter lines.
+        const int qj = lane & 3;
+        __nv_bfloat16* qrow = orow - (size_t)qj * kCo + qj * 16;          // pixel 0 of my quad, my unit's column offset
+#pragma unroll 1
+        for (int b = 0; b < 4; ++b) {
+          uint32_t u[4][8];
 #pragma unroll
-          for (int e = 0; e < 16; e += 2) pw[e >> 1] = pack_bf16x2(v[e] * inv, v[e + 1] * inv);
-          st_global_v8(orow + g * 16, pk[0], pk[1]);
+          for (int j = 0; j < 4; ++j) {
+            float v[16];
+            tmem_ld16(tl + (uint32_t)(b * 64 + j * 16), v);
+#pragma unroll
+            for (int e = 0; e < 16; e += 2) u[j][e >> 1] = pack_bf16x2(v[e] * inv, v[e + 1] * inv);
+          }
+#pragma unroll
+          for (int bit = 0; bit < 2; ++bit) {
+            const bool hi = (lane >> bit) & 1;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              if ((r >> bit) & 1) continue;
+              const int r2 = r | (1 << bit);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const uint32_t send = hi ? u[r][e] : u[r2][e];
+                const uint32_t got = __shfl_xor_sync(0xffffffffu, send, 1 << bit);
+                if (hi) u[r][e] = got; else u[r2][e] = got;
+              }
+            }
+          }
+#pragma unroll
+          for (int m = 0; m < 4; ++m)
+            st_global_v8(qrow + (size_t)m * kCo + b * 64, make_uint4(u[m][0], u[m][1], u[m][2], u[m][3]),
+                         make_uint4(u[m][4], u[m][5], u[m][6], u[m][7]));
         }
+        __syncwarp();                                  // my row was written by the four lanes of my quad: order it before my read-back
         tc_fence_before();
         mbar_arrive(smem_u32(&tempty[buf]));           // the accumulator is free for output row q + 2
         // the target class: read back this thread's own softmax[target] * scale (the per-class select over 256 register
