@@ -221,22 +221,26 @@ def main_notebook(args):
         x, y = resident[i % n_batches]
         return model.train_step(x, y)
 
+    reader = LossReader(torch)
+
     def step_e2e(i):
         f = host[i % n_batches].to(dev, non_blocking=True)        # H2D from pinned memory
         x, y = model.prepare_input(f)                             # normalisation + int64 targets on the device
-        return float(model.train_step(x, y)[0])                   # D2H read of the loss (syncs)
+        reader.push(i, model.train_step(x, y)[0])                 # D2H of the loss into pinned memory, read one step late
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, finish=None):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         ev0.record()
         for i in range(steps):
             fn(i)
+        if finish is not None:
+            finish()
         ev1.record()
         barrier()
         ms = ev0.elapsed_time(ev1)
@@ -254,7 +258,9 @@ def main_notebook(args):
         launches = M._lib.lib.mmvae_launch_count() - l0
     for i in range(2):
         step_e2e(i)
-    ms_e2e = timed(step_e2e, args.steps)
+    reader.finish()
+    ms_e2e = timed(step_e2e, args.steps, finish=reader.finish)
+    assert reader.reads == args.steps + 2 and reader.total == reader.total, "every step's loss must have been read (and be finite)"
 
     sustained, burst, hbm, which = peaks()
     roofs = []
@@ -307,7 +313,9 @@ def main_notebook(args):
                    "l2": f"activation workspace {info.workspace_bytes / 1e9:.1f} GB streamed every step (>> 126 MB L2), "
                          f"{n_batches} rotating input batches"},
         "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": n * size * size, "d2h_bytes_per_step": 4,
-                "ms_per_step": ms_e2e / args.steps},
+                "ms_per_step": ms_e2e / args.steps,
+                "mode": "per step: H2D of the uint8 frames from pinned memory, device normalisation, train step, D2H of the loss into "
+                        "pinned memory; the host reads each loss one step late (asynchronous logging), all inside the timed region"},
         "gpu_launches": int(launches), "clocks": clk.summary(),
         "roofline": roofs[0] if roofs else {"bound": "tensor", "achieved": tf, "peak": sustained, "unit": "TFLOP/s",
                                             "frac": tf / sustained, "traffic": None},
@@ -325,6 +333,41 @@ def main_notebook(args):
         torch.cuda.synchronize()
         dist.barrier()
         dist.destroy_process_group()
+
+
+class LossReader:
+    """Device -> host read of every step's loss without stalling the stream: the scalar is copied into one of two pinned
+    host slots right behind the step (D2H inside the timed region) and the host reads it one step later, after the slot's
+    event -- what a training loop that logs asynchronously does.  finish() reads the last one."""
+
+    def __init__(self, torch):
+        self.torch = torch
+        self.slots = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.events = [torch.cuda.Event(), torch.cuda.Event()]
+        self.pending = None
+        self.total = 0.0
+        self.reads = 0
+
+    def push(self, i, loss_dev):
+        k = i & 1
+        if self.pending is not None and self.pending == k:      # never overwrite a slot that was not read yet
+            self._read(self.pending)
+        self.slots[k].copy_(loss_dev.detach().reshape(1), non_blocking=True)
+        self.events[k].record()
+        prev = self.pending
+        self.pending = k
+        if prev is not None and prev != k:
+            self._read(prev)
+
+    def _read(self, k):
+        self.events[k].synchronize()
+        self.total += float(self.slots[k][0])
+        self.reads += 1
+
+    def finish(self):
+        if self.pending is not None:
+            self._read(self.pending)
+            self.pending = None
 
 
 _REAL_STDOUT = None
@@ -415,6 +458,8 @@ def main():
         loss.backward()
         return loss
 
+    reader = LossReader(torch)
+
     def step_e2e(i):
         lab = labels_host[i % n_batches].to(dev, non_blocking=True)     # H2D from pinned memory
         x = D.prepare_input(lab)                                        # main.py:383-388 on the device
@@ -423,19 +468,21 @@ def main():
         for p in params:
             p.grad = None
         loss.backward()
-        return float(loss.detach())                                     # D2H read of the step's loss (syncs)
+        reader.push(i, loss)                                            # D2H of the loss into pinned memory, read one step late
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, finish=None):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         ev0.record()
         for i in range(steps):
             fn(i)
+        if finish is not None:
+            finish()
         ev1.record()
         barrier()
         ms = ev0.elapsed_time(ev1)
@@ -459,7 +506,7 @@ def main():
 
         def step_e2e(i):                                                      # noqa: F811
             loss = gstep_lab(labels_host[i % n_batches])[0]                   # H2D from pinned memory, then the graph
-            return float(loss)                                                # D2H read of the step's loss (syncs)
+            reader.push(i, loss)                                              # D2H of the loss into pinned memory, read one step late
 
     for i in range(args.warmup):
         step_resident(i)
@@ -471,7 +518,9 @@ def main():
         launches = launches_per_step * args.steps                             # replayed kernels of the captured step
     for i in range(3):
         step_e2e(i)
-    ms_e2e = timed(step_e2e, args.steps)
+    reader.finish()
+    ms_e2e = timed(step_e2e, args.steps, finish=reader.finish)
+    assert reader.reads == args.steps + 3 and reader.total == reader.total, "every step's loss must have been read (and be finite)"
 
     # ---- rooflines, measured live: one launch per iteration of the production kernel of a (conv, direction) pair through
     # mmvae_bench_conv on the tensors the last step left in the workspace, CUDA events around each launch on the launching
@@ -554,7 +603,10 @@ def main():
                    "l2": f"activation workspace {ws_bytes / 1e6:.0f} MB streamed every step (> 126 MB L2), "
                          f"{n_batches} rotating input batches"},
         "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": n * 64 * 64, "d2h_bytes_per_step": 4,
-                "ms_per_step": ms_e2e / args.steps},
+                "ms_per_step": ms_e2e / args.steps,
+                "mode": "per step: H2D of the uint8 label maps from pinned memory, graph replay (normalisation + train step), D2H of "
+                        "the loss into pinned memory; the host reads each loss one step late (asynchronous logging), all inside the "
+                        "timed region"},
         "gpu_launches": int(launches),
         "clocks": clk.summary(),
         "roofline": roof if roof is not None else {"bound": "tensor", "achieved": tflops_per_gpu, "peak": sustained,
