@@ -55,8 +55,6 @@ __device__ __forceinline__ void decode_tile(const GConvParams& p, int t, int& mt
   p.fd_nvar.divmod(r, mt, v);
 }
 
-// experiment: tc_flags bit 0 = poll with mbarrier.test_wait instead of the (suspending) try_wait
-#define MBAR_WAIT(bar, ph) do { if (p.tc_flags & 1) { while (!mbar_test_wait((bar), (ph))) {} } else mbar_wait((bar), (ph)); } while (0)
 
 // kBwd: data-gradient instantiation whose epilogue also masks the gradient with the consumer's ReLU and reduces the
 // consumer's BatchNorm-backward sums (BnBwdFused) -- more live registers, so two CTAs per SM instead of three
@@ -68,7 +66,8 @@ __global__ void __launch_bounds__(kTcThreads, kBwd ? 2 : 3) gconv_tc_kernel(cons
   __shared__ uint32_t tmem_base_s;
   __shared__ float stat_red[4][kBwd ? 3 : 2][kBN];
   __shared__ uint32_t tma_tab[kTabCap];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // the warp index through a shuffle: ptxas then knows the role dispatch below is warp-uniform control flow
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = tid & 31;
   if (tid == 0) MMVAE_TRACE(p, 0);
   constexpr int BN = kBN;
   const int S = p.tc_stages;
@@ -99,11 +98,14 @@ __global__ void __launch_bounds__(kTcThreads, kBwd ? 2 : 3) gconv_tc_kernel(cons
       tma_tab[e] = ent;
     }
   }
+  // csz > 1: the CTAs of a cluster share one pixel tile (one channel tile each) and multicast their slice of every A box
+  // to all of them, so a ring slot is free only when the MMA threads of ALL csz CTAs have released it
+  const int csz = p.tc_csz > 1 ? p.tc_csz : 1;
   if (tid == 0) {
     if (p.use_tma) prefetch_tensormap(&p.tmap_a);
     for (int s = 0; s < S; ++s) {
       mbar_init(smem_u32(&full[s]), p.use_tma ? 1 : kGatherThreads + 1);
-      mbar_init(smem_u32(&empty[s]), 1);
+      mbar_init(smem_u32(&empty[s]), (uint32_t)csz);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&tfull[b]), 1);
@@ -111,12 +113,19 @@ __global__ void __launch_bounds__(kTcThreads, kBwd ? 2 : 3) gconv_tc_kernel(cons
     }
     fence_barrier_init();
   }
-  const uint32_t ncols = 2 * BN <= 32 ? 32u : (2 * BN <= 64 ? 64u : (2 * BN <= 128 ? 128u : (2 * BN <= 256 ? 256u : 512u)));
+  // nacc > 1: the k-steps of a tile rotate over nacc accumulators that the epilogue adds up.  Back-to-back MMAs into ONE
+  // accumulator serialise on the tensor pipe's latency (~220 cycles each, whatever N is): with a narrow tile (N = 32 is 16
+  // cycles of math) a deep-K layer is a chain of K/16 dependent MMAs; independent accumulators overlap in the pipe.
+  const int nacc = (kBN >= 32 && p.tc_nacc > 1) ? p.tc_nacc : 1;     // 16-column tiles: K <= 256, never worth it
+  const int accw = 2 * BN * nacc;
+  const uint32_t ncols = accw <= 32 ? 32u : (accw <= 64 ? 64u : (accw <= 128 ? 128u : (accw <= 256 ? 256u : 512u)));
   if (warp == 4) tmem_alloc(smem_u32(&tmem_base_s), ncols);
   tc_fence_before();
-  __syncthreads();
+  if (csz > 1) cluster_sync_all();              // peers' barriers are initialised before anything is multicast at them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
+  const uint16_t cmask = (uint16_t)((1u << csz) - 1u);
   if (tid == 0) MMVAE_TRACE(p, 1);
   pdl_wait();                                   // everything above overlapped the previous kernel's tail
   pdl_trigger();
@@ -124,15 +133,18 @@ __global__ void __launch_bounds__(kTcThreads, kBwd ? 2 : 3) gconv_tc_kernel(cons
 
   if (warp < 4) {
     if (p.use_tma) {
-      // ---------------- producers: lane 0 of the four warps, TMA boxes ----------------
-      // Issuing one TMA instruction keeps its thread busy for ~0.25 us, so one producer thread caps a deep-K layer at one
-      // k-chunk per ~0.3 us.  Every ring slot has ONE owner thread (slot & 3): all four walk the same chunk sequence and
-      // each issues the chunks that land in its slots (an owner per slot keeps a waiter at most one phase ahead of its
-      // barrier; dealing chunks round-robin regardless of the slot does not).  tc_flags bit 1: single producer (A/B).
+      // ---------------- producers: the four warps, TMA boxes ----------------
+      // Every ring slot has ONE owner warp (slot & 3): all four walk the same chunk sequence and each issues the chunks
+      // that land in its slots (an owner per slot keeps a waiter at most one phase ahead of its barrier; dealing chunks
+      // round-robin regardless of the slot does not).  Whole warps walk the loop (uniform control flow, see elect_one),
+      // one elected lane issues.  tc_flags bit 1: single producer (A/B).
       const int nprod = (p.tc_flags & 2) ? 1 : 4;
-      if (lane == 0 && warp < nprod) {
+      if (warp < nprod) {                       // whole warps walk the loop, one elected lane issues (see elect_one)
         const uint64_t tmap = reinterpret_cast<uint64_t>(&p.tmap_a);
         const int pmask = nprod - 1, pw = warp;
+        const uint32_t crank = csz > 1 ? cluster_ctarank() : 0u;
+        const uint32_t mc_off = crank * (uint32_t)p.tc_mc_bytes;      // this CTA's slice of every A sub-tile
+        const int mc_n = (int)crank * p.tc_mc_imgs;
         int stage = 0;
         uint32_t ephase = 1;                    // the first lap over the ring passes immediately
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
@@ -147,28 +159,43 @@ __global__ void __launch_bounds__(kTcThreads, kBwd ? 2 : 3) gconv_tc_kernel(cons
           p.fd_wg.divmod(rem, i0, j0);
           const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(p.wpack) + (size_t)vi * p.wpack_var_stride +
                                       (size_t)((nt * BN) >> 3) * 1024;
-          if (pw == 0 && t == (int)blockIdx.x) MMVAE_TRACE(p, 16);
+          if (pw == 0 && lane == 0 && t == (int)blockIdx.x) MMVAE_TRACE(p, 16);
           const int xb = j0 * p.is, yb = i0 * p.is;
           const uint32_t* tab = tma_tab + ((vi * p.tc_maxchunks) << sub_shift);
           const size_t wstep = (size_t)p.co_pad * 128;
+          const int nsub_full = 1 << sub_shift, nsub_last = (K - (nchunks - 1) * 64 + kb - 1) >> kb_log2;
           for (int kc = 0; kc < nchunks; ++kc, wsrc += wstep) {
             if ((stage & pmask) == pw) {
-              MBAR_WAIT(smem_u32(&empty[stage]), ephase);
+              mbar_wait(smem_u32(&empty[stage]), ephase);
               const uint32_t bar = smem_u32(&full[stage]);
-              const int nsub = kc + 1 < nchunks ? (1 << sub_shift) : ((K - kc * 64 + kb - 1) >> kb_log2);
-              mbar_arrive_expect_tx(bar, (uint32_t)(stageB + nsub * sub_bytes));
-              bulk_g2s(b_base + (uint32_t)stage * stageB, wsrc, (uint32_t)stageB, bar);
-              uint32_t dst = a_base + (uint32_t)stage * kStageA;
-              for (int g = 0; g < nsub; ++g, dst += (uint32_t)sub_bytes) {
-                const uint32_t ent = tab[(kc << sub_shift) + g];
-                tma_load_4d(dst, tmap, bar, (int)(ent & 0xffffu), xb + (int)(signed char)(ent >> 16), yb + (int)(signed char)(ent >> 24), n0);
+              const int nsub = kc + 1 < nchunks ? nsub_full : nsub_last;
+              if (elect_one()) {
+                mbar_arrive_expect_tx(bar, (uint32_t)(stageB + nsub * sub_bytes));
+                bulk_g2s(b_base + (uint32_t)stage * stageB, wsrc, (uint32_t)stageB, bar);
+                uint32_t dst = a_base + (uint32_t)stage * kStageA;
+                for (int g = 0; g < nsub; ++g, dst += (uint32_t)sub_bytes) {
+                  const uint32_t ent = tab[(kc << sub_shift) + g];
+                  if (csz > 1)
+                    tma_load_4d_mc(dst + mc_off, tmap, bar, (int)(ent & 0xffffu), xb + (int)(signed char)(ent >> 16),
+                                   yb + (int)(signed char)(ent >> 24), n0 + mc_n, cmask);
+                  else
+                    tma_load_4d(dst, tmap, bar, (int)(ent & 0xffffu), xb + (int)(signed char)(ent >> 16), yb + (int)(signed char)(ent >> 24), n0);
+                }
               }
-              if (pw == 0 && t == (int)blockIdx.x && kc == 0) MMVAE_TRACE(p, 3);
+              __syncwarp();
             }
             if (++stage == S) { stage = 0; ephase ^= 1u; }
           }
         }
-        if (pw == 0) MMVAE_TRACE(p, 4);
+        if (csz > 1) {
+          // a peer's MMA thread still arrives on this CTA's `empty` barriers for the last lap: wait for those arrivals
+          // (one more lap of waits, nothing issued) so that no CTA of the cluster exits under a remote arrive
+          for (int e = 0; e < S; ++e) {
+            if ((stage & pmask) == pw) mbar_wait(smem_u32(&empty[stage]), ephase);
+            if (++stage == S) { stage = 0; ephase ^= 1u; }
+          }
+        }
+        if (pw == 0 && lane == 0) MMVAE_TRACE(p, 4);
       }
     } else {
       // ---------------- producers: cp.async gather, thread -> 16-byte chunk j of rows rg + 16*i ----------------
@@ -241,8 +268,8 @@ __global__ void __launch_bounds__(kTcThreads, kBwd ? 2 : 3) gconv_tc_kernel(cons
       }
     }
   } else if (warp == 4) {
-    if (lane == 0) {
-      // ---------------- MMA issue ----------------
+    {
+      // ---------------- MMA issue: the whole warp walks the loop, one elected lane issues ----------------
       const uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
       const uint32_t aswz = swz_code(kbB);
       const uint32_t asbo = 8u * (uint32_t)kbB;
@@ -253,39 +280,54 @@ __global__ void __launch_bounds__(kTcThreads, kBwd ? 2 : 3) gconv_tc_kernel(cons
 #pragma unroll
       for (int q = 0; q < 4; ++q)
         aoff[q] = ((uint32_t)((q * 16) >> kb_log2) * (uint32_t)sub_bytes + (uint32_t)((q * 16) & (kb - 1)) * 2u) >> 4;
+      // The loop below is ONE warp's serial instruction stream: at ~6 cycles per dependent instruction every instruction
+      // in it is ~3 ns per k-chunk, and 100 of them (per-chunk trace stamps, experiment flags, descriptor arithmetic from
+      // the stage index) were 0.3 us per chunk -- more than the TMA loads and the MMAs of the chunk together (measured with
+      // loads and MMAs switched off).  So: running descriptors / barrier addresses that advance by a constant per stage,
+      // nothing per chunk that is not needed to issue it.
+      const uint32_t a_step = (uint32_t)kStageA >> 4, b_step = (uint32_t)stageB >> 4;
+      const uint32_t full0 = smem_u32(&full[0]), empty0 = smem_u32(&empty[0]);
+      uint32_t fbar = full0, ebar = empty0;
+      uint64_t da = da0, db = db0;
       int stage = 0;
       uint32_t fphase = 0;
       int i = 0;
+      const int amask = nacc - 1;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
         int mt, vi, nt;
         decode_tile(p, t, mt, vi, nt);
         const int K = p.var[vi].ntaps * p.Ci;
         const int nchunks = (K + 63) >> 6;
+        const int nk_last = (K - (nchunks - 1) * 64 + 15) >> 4;           // MMAs of the last k-chunk (1..4)
         const int buf = i & 1;
-        MBAR_WAIT(smem_u32(&tempty[buf]), (uint32_t)(((i >> 1) & 1) ^ 1));   // epilogue drained this buffer
+        mbar_wait(smem_u32(&tempty[buf]), (uint32_t)(((i >> 1) & 1) ^ 1));   // epilogue drained this buffer
         tc_fence_after();
-        const uint32_t dtm = tmem + (uint32_t)(buf * BN);
+        const uint32_t dtm = tmem + (uint32_t)(buf * nacc * BN);
         for (int kc = 0; kc < nchunks; ++kc) {
-          MBAR_WAIT(smem_u32(&full[stage]), fphase);
+          mbar_wait(fbar, fphase);
           tc_fence_after();
-          if (i == 0 && kc == 0) MMVAE_TRACE(p, 5);
-          if (i == 0 && kc == 1) MMVAE_TRACE(p, 19);
-          const int kleft = K - kc * 64;
-          const int nk = kleft >= 64 ? 4 : (kleft + 15) >> 4;
-          const uint64_t da = da0 + (uint64_t)(((uint32_t)stage * kStageA) >> 4);
-          const uint64_t db = db0 + (uint64_t)(((uint32_t)stage * (uint32_t)stageB) >> 4);
+          if (elect_one()) {
+            if (kc + 1 < nchunks) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (q < nk) mma_bf16(dtm, da + aoff[q], db + (uint64_t)(q * 2), idesc, (kc | q) != 0);
-          mma_commit(smem_u32(&empty[stage]));
-          if (i == 0 && kc == 0) MMVAE_TRACE(p, 18);
-          if (i == 0 && kc == 1) MMVAE_TRACE(p, 20);
-          if (++stage == S) { stage = 0; fphase ^= 1u; }
+              for (int q = 0; q < 4; ++q)
+                mma_bf16(dtm + (uint32_t)((q & amask) * BN), da + aoff[q], db + (uint64_t)(q * 2), idesc, (kc != 0) | (q >= nacc));
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                if (q < nk_last) mma_bf16(dtm + (uint32_t)((q & amask) * BN), da + aoff[q], db + (uint64_t)(q * 2), idesc, (kc != 0) | (q >= nacc));
+            }
+            if (csz > 1) mma_commit_mc(ebar, cmask);
+            else mma_commit(ebar);
+          }
+          __syncwarp();
+          da += a_step; db += b_step; fbar += 8; ebar += 8;
+          if (++stage == S) { stage = 0; fphase ^= 1u; da = da0; db = db0; fbar = full0; ebar = empty0; }
         }
-        mma_commit(smem_u32(&tfull[buf]));
-        if (i == 0) MMVAE_TRACE(p, 6);
+        if (elect_one()) mma_commit(smem_u32(&tfull[buf]));
+        __syncwarp();
+        if (i == 0 && lane == 0) { MMVAE_TRACE(p, 5); MMVAE_TRACE(p, 6); }
       }
-      MMVAE_TRACE(p, 7);
+      if (lane == 0) MMVAE_TRACE(p, 7);
     }
   } else {
     // ---------------- epilogue: TMEM -> bf16 NHWC (+ fused BatchNorm statistics) ----------------
@@ -324,15 +366,24 @@ __global__ void __launch_bounds__(kTcThreads, kBwd ? 2 : 3) gconv_tc_kernel(cons
         obase = ((size_t)(n * p.Ho + oy) * p.Wo + ox) * p.Co;
       }
       const bool fuse_v = kBwd && ((p.bb.var_mask >> vi) & 1);       // this tile's pixels are final here: mask + reduce
-      MBAR_WAIT(smem_u32(&tfull[buf]), (uint32_t)((i >> 1) & 1));
+      mbar_wait(smem_u32(&tfull[buf]), (uint32_t)((i >> 1) & 1));
       tc_fence_after();
       if (i == 0 && tid == 160) MMVAE_TRACE(p, 8);
-      const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
+      const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * nacc * BN);
 #pragma unroll
       for (int gq = 0; gq < NG; ++gq) {
         const int c0 = gq * 16;
         float v[16];
         tmem_ld16(tlane + (uint32_t)c0, v);
+        for (int a = 1; a < nacc; ++a) {
+          float w8[8];
+          tmem_ld8(tlane + (uint32_t)(a * BN + c0), w8);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] += w8[e];
+          tmem_ld8(tlane + (uint32_t)(a * BN + c0 + 8), w8);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[8 + e] += w8[e];
+        }
         const int co0 = n0 + c0;
         if (p.bias) {
 #pragma unroll
@@ -823,6 +874,18 @@ int gconv_per_sm() {
   return m;
 }
 
+// Both options below measured neutral to slightly negative on every deep-K layer once the issue loops were lean
+// (profiles/r01_issue_loops.md): OFF by default, kept for experiments.
+int mc_min_chunks() {                   // TMA multicast over clusters for layers at least this deep (MMVAE_MC_MIN_CHUNKS env; 0 = off)
+  static int m = [] { const char* e = getenv("MMVAE_MC_MIN_CHUNKS"); return e ? atoi(e) : 0; }();
+  return m;
+}
+
+int nacc_min_chunks() {                 // several TMEM accumulators per tile for layers at least this deep (MMVAE_NACC_MIN_CHUNKS env; 0 = off)
+  static int m = [] { const char* e = getenv("MMVAE_NACC_MIN_CHUNKS"); return e ? atoi(e) : 0; }();
+  return m;
+}
+
 int tma_mask() {                        // bit 0: gconv A, bit 1: wgrad A, bit 2: wgrad dY   (MMVAE_TMA env, debugging)
   static int m = [] { const char* e = getenv("MMVAE_TMA"); return e ? atoi(e) : 7; }();
   return m;
@@ -848,6 +911,7 @@ StatLayout launch_gconv_tc(const GConvParams& p0, cudaStream_t st) {
   int bn = co_pad > 128 ? 128 : pow2_floor(co_pad);
   if (co_pad % bn != 0) bn = 16;
   while (bn > 32 && (long long)tiles_m * p.nvar * ((co_pad + bn - 1) / bn) < 128) bn >>= 1;
+  { static int fb = [] { const char* e = getenv("MMVAE_FORCE_BN"); return e ? atoi(e) : 0; }(); if (fb && co_pad % fb == 0) bn = fb; }
   const int stage_bytes = kStageA + bn * 128;
   int maxchunks = 1;
   for (int v = 0; v < p.nvar; ++v) maxchunks = max(maxchunks, (p.var[v].ntaps * p.Ci + 63) / 64);
@@ -874,7 +938,30 @@ StatLayout launch_gconv_tc(const GConvParams& p0, cudaStream_t st) {
   }
   if (p.use_tma && p.nvar * maxchunks * (64 / p.tc_kb) > kTabCap) { p.use_tma = 0; p.tc_kb = 64; }   // coordinate table too small
   p.tc_kb_log2 = p.tc_kb == 64 ? 6 : (p.tc_kb == 32 ? 5 : 4);
+  // Deep-K layers on few pixel tiles (the 2x2 .. 4x4 maps in the middle of the network) are bound by the rate at which
+  // one SM's TMA unit turns box rows into requests (a 128-row A box per k-chunk, the same box in every channel tile).
+  // Their channel tiles form a thread-block cluster: each CTA fetches 1/csz of the box (a run of images) and multicasts
+  // it to all of them, so an SM generates 128/csz rows per k-chunk instead of 128.
+  p.tc_csz = 1; p.tc_mc_imgs = 0; p.tc_mc_bytes = 0;
+  if (p.use_tma && mc_min_chunks() > 0 && maxchunks >= mc_min_chunks() && (p.n_tiles == 2 || p.n_tiles == 4 || p.n_tiles == 8) &&
+      bnb % p.n_tiles == 0) {
+    const int csz = p.n_tiles;
+    if (make_tmap(p.tmap_a, p.in, p.N, p.Hi, p.Wi, p.Ci, p.tc_kb, bw, bh, bnb / csz, p.is)) {
+      p.tc_csz = csz; p.tc_mc_imgs = bnb / csz; p.tc_mc_bytes = (128 / csz) * p.tc_kb * 2;
+    } else {
+      make_tmap(p.tmap_a, p.in, p.N, p.Hi, p.Wi, p.Ci, p.tc_kb, bw, bh, bnb, p.is);
+    }
+  }
   const size_t smem = (size_t)stages * stage_bytes + 1024;
+  // several accumulators per tile for deep-K layers (see the kernel); every variant must have a full first k-chunk so
+  // that the first nacc MMAs initialise them all; at most 256 TMEM columns so that a second CTA still fits beside it
+  p.tc_nacc = 1;
+  {
+    int minK = 1 << 30;
+    for (int v = 0; v < p.nvar; ++v) minK = min(minK, p.var[v].ntaps * p.Ci);
+    if (nacc_min_chunks() > 0 && maxchunks >= nacc_min_chunks() && minK >= 64 && smem > 76 * 1024)
+      p.tc_nacc = bn < 32 ? 1 : (bn == 32 ? 4 : (bn == 64 ? 2 : 1));
+  }
   const bool bwd = p.bb.acc != nullptr;
   static bool attr_done = false;
   if (!attr_done) {
@@ -893,32 +980,36 @@ StatLayout launch_gconv_tc(const GConvParams& p0, cudaStream_t st) {
     attr_done = true;
   }
   const int per_sm = min(gconv_per_sm(), bwd ? 2 : (smem <= 72 * 1024 ? 3 : 2));
-  const int grid = min(p.total_tiles, per_sm * 148);
+  int grid = min(p.total_tiles, per_sm * 148);
+  if (p.tc_csz > 1) grid -= grid % p.tc_csz;     // whole clusters; total_tiles is a multiple of n_tiles == csz
   p.trace = debug_trace_buffer();
   { static int fl = [] { const char* e = getenv("MMVAE_TC_FLAGS"); return e ? atoi(e) : 0; }(); p.tc_flags = fl; }
   count_launch();
+#define LAUNCH_GCONV(...) \
+  (p.tc_csz > 1 ? launch_pdl_cluster(__VA_ARGS__, grid, kTcThreads, smem, st, p.tc_csz, p) : launch_pdl(__VA_ARGS__, grid, kTcThreads, smem, st, p))
   if (p.act || p.dact) {
     switch (bn) {
-      case 16: launch_pdl(gconv_tc_kernel<16, false, true>, grid, kTcThreads, smem, st, p); break;
-      case 32: launch_pdl(gconv_tc_kernel<32, false, true>, grid, kTcThreads, smem, st, p); break;
-      case 64: launch_pdl(gconv_tc_kernel<64, false, true>, grid, kTcThreads, smem, st, p); break;
-      default: launch_pdl(gconv_tc_kernel<128, false, true>, grid, kTcThreads, smem, st, p); break;
+      case 16: LAUNCH_GCONV(gconv_tc_kernel<16, false, true>); break;
+      case 32: LAUNCH_GCONV(gconv_tc_kernel<32, false, true>); break;
+      case 64: LAUNCH_GCONV(gconv_tc_kernel<64, false, true>); break;
+      default: LAUNCH_GCONV(gconv_tc_kernel<128, false, true>); break;
     }
   } else if (bwd) {
     switch (bn) {
-      case 16: launch_pdl(gconv_tc_kernel<16, true>, grid, kTcThreads, smem, st, p); break;
-      case 32: launch_pdl(gconv_tc_kernel<32, true>, grid, kTcThreads, smem, st, p); break;
-      case 64: launch_pdl(gconv_tc_kernel<64, true>, grid, kTcThreads, smem, st, p); break;
-      default: launch_pdl(gconv_tc_kernel<128, true>, grid, kTcThreads, smem, st, p); break;
+      case 16: LAUNCH_GCONV(gconv_tc_kernel<16, true>); break;
+      case 32: LAUNCH_GCONV(gconv_tc_kernel<32, true>); break;
+      case 64: LAUNCH_GCONV(gconv_tc_kernel<64, true>); break;
+      default: LAUNCH_GCONV(gconv_tc_kernel<128, true>); break;
     }
   } else {
     switch (bn) {
-      case 16: launch_pdl(gconv_tc_kernel<16, false>, grid, kTcThreads, smem, st, p); break;
-      case 32: launch_pdl(gconv_tc_kernel<32, false>, grid, kTcThreads, smem, st, p); break;
-      case 64: launch_pdl(gconv_tc_kernel<64, false>, grid, kTcThreads, smem, st, p); break;
-      default: launch_pdl(gconv_tc_kernel<128, false>, grid, kTcThreads, smem, st, p); break;
+      case 16: LAUNCH_GCONV(gconv_tc_kernel<16, false>); break;
+      case 32: LAUNCH_GCONV(gconv_tc_kernel<32, false>); break;
+      case 64: LAUNCH_GCONV(gconv_tc_kernel<64, false>); break;
+      default: LAUNCH_GCONV(gconv_tc_kernel<128, false>); break;
     }
   }
+#undef LAUNCH_GCONV
   return sl;       // statistics are finalised inside the kernel (p.bn); no partial rows
 }
 

@@ -31,6 +31,20 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
+// launch_pdl over thread-block clusters of `csz` consecutive CTAs (grid.x % csz == 0)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int csz,
+                                      Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)csz; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 #endif
 
 // Division by a runtime constant without the integer-divide sequence (valid for numerators < 2^31).
@@ -148,6 +162,10 @@ struct GConvParams {
   int tc_kb, use_tma;          // channels per A sub-tile; A staged by TMA boxes (else cp.async gather)
   int tc_kb_log2, tc_maxchunks; // log2(tc_kb); k-chunks (of 64) of the deepest variant
   int tc_flags;                // experiments (MMVAE_TC_FLAGS env)
+  // TMA multicast over a thread-block cluster: the tc_csz CTAs of a cluster hold the tc_csz channel tiles of ONE pixel
+  // tile; each fetches 1/tc_csz of the A box (tc_mc_imgs images = tc_mc_bytes bytes of every sub-tile) for all of them
+  int tc_csz, tc_mc_imgs, tc_mc_bytes;
+  int tc_nacc;                 // TMEM accumulators a tile's k-steps rotate over (1, 2 or 4)
   unsigned long long* trace;   // debugging: [CTA][16] globaltimer stamps (mmvae_debug_set_trace), nullptr = off
   int tiles_m, n_tiles, total_tiles;
   FastDiv fd_wg, fd_hg, fd_ci, fd_hw, fd_ntiles, fd_nvar;

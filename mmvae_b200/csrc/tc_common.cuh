@@ -73,6 +73,29 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst_smem, uint64_t tmap, ui
       : "memory");
 }
 
+// The same box delivered to the same CTA-relative shared-memory offset of every CTA of the cluster named in `cta_mask`;
+// each destination CTA's barrier (same offset) receives the transaction bytes
+__device__ __forceinline__ void tma_load_4d_mc(uint32_t dst_smem, uint64_t tmap, uint32_t bar, int c0, int c1, int c2, int c3,
+                                               uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, %6}], "
+      "[%2], %7;" ::"r"(dst_smem),
+      "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(cta_mask)
+      : "memory");
+}
+
+// ---------------- thread-block cluster ----------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// all threads of all CTAs of the cluster (also a CTA-wide barrier)
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 __device__ __forceinline__ void prefetch_tensormap(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
 }
@@ -112,6 +135,20 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// One lane of a fully converged warp.  The single-thread tcgen05 roles run their loops on the WHOLE warp (uniform control
+// flow: ptxas keeps the descriptors / addresses in uniform registers) and only the instructions themselves sit under
+// this predicate; a loop inside `if (lane == 0)` is divergent code, where every operand of a UTCHMMA / UTMALDG goes
+// through R2UR and an ELECT ... BRA.U.ANY wrapper (~200 cycles per MMA issued, measured).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xFFFFFFFF;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // D[tmem] (+)= A[smem desc] * B[smem desc], bf16 x bf16 -> fp32, one CTA
 __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -124,6 +161,13 @@ __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t desc_a, uint6
 // arrive on `bar` once every tcgen05.mma issued so far by this thread has completed
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// the same arrival on the barrier at this CTA-relative offset in every CTA of the cluster named in `cta_mask`
+__device__ __forceinline__ void mma_commit_mc(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(cta_mask)
+               : "memory");
 }
 
 // 32 lanes x 16 consecutive fp32 columns: thread i of the warp reads TMEM lane (lane_base + i)

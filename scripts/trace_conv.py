@@ -11,7 +11,8 @@ import types
 
 SLAB_SLOTS = ["entry", "prologue", "pdl_wait", "fill0_issued", "fill0_done", "fill1_done", "m_full0", "m_tile0", "m_slab0", "m_all", "e_tfull0", "e_tile0", "e_all", "dealloc", "bn_fin"]
 SLOTS = ["entry", "prologue", "pdl_wait", "tma0", "tma_all", "full0", "mma_tile0", "mma_all", "tfull0", "epi0", "epi_all",
-         "stats", "dealloc", "bn_fin", "-", "-", "p_decoded", "p_chunk1", "m_commit0", "m_full1", "m_commit1"]
+         "stats", "dealloc", "bn_fin", "-", "-", "p_decoded", "p_chunk1", "m_commit0", "m_full1", "m_commit1",
+         "k20_full", "k20_mma0", "k20_mma1", "k20_mma2", "k20_mma3", "k20_commit", "k21_full", "k21_commit"]
 n = int(os.environ.get("N", "256"))
 model = M.VAE(1, 32, decoder_out_channels=1, pixelcnn_out_channels=0, z_dimension=64, pixelcnn=False, only_pixelcnn=False,
               sigma_decoder=0.1, input_image_size=64, precision="bf16").cuda().train()
@@ -54,5 +55,5 @@ for name in want:
               f"kernel span {(int(t[used].max()) - t0) / 1e3:.2f} us")
         for label, sel in (("first CTA", int(used[0])), ("last-ending CTA", int(used[t[used].max(dim=1).values.argmax()]))):
             row = t[sel]
-            names = SLAB_SLOTS if (os.environ.get("SLAB") == "1") else SLOTS
-            print(f"   {label:16s} (cta {sel}): " + "  ".join(f"{names[s]}={(int(row[s]) - t0) / 1e3:.2f}" for s in range(len(names)) if row[s] > 0))
+            slots = SLAB_SLOTS if (os.environ.get("SLAB") == "1") else SLOTS
+            print(f"   {label:16s} (cta {sel}): " + "  ".join(f"{slots[s]}={(int(row[s]) - t0) / 1e3:.2f}" for s in range(len(slots)) if row[s] > 0))
