@@ -18,6 +18,7 @@
 #include <cuda.h>
 
 #include <cstdlib>
+#include <type_traits>
 
 #include "bn_fused.cuh"
 #include "geom.hpp"
@@ -558,7 +559,7 @@ __global__ void __launch_bounds__(kTcThreads) wgrad_tc_kernel(const __grid_const
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long full[kMaxStages], empty[kMaxStages], accum;
   __shared__ uint32_t tmem_base_s;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = tid & 31;   // warp-uniform role dispatch for ptxas
   const int vi = blockIdx.z / p.nsplit, split = blockIdx.z % p.nsplit;
   const GVar& var = p.var[vi];
   const int BN = p.tc_bn, S = p.tc_stages;
@@ -617,8 +618,10 @@ __global__ void __launch_bounds__(kTcThreads) wgrad_tc_kernel(const __grid_const
   }
 
   if (warp < 4) {
-    // ---- TMA part: one thread ----
-    if (tid == 0 && (p.tma_a || p.tma_b)) {
+    // ---- TMA part: warp 0 walks the loop and one elected lane issues (uniform control flow, see elect_one); when a
+    // cp.async gather shares the stage (mixed mode) the lanes of warp 0 are needed there, and thread 0 issues alone ----
+    auto tma_loop = [&](auto whole_tag) {
+      constexpr bool kWhole = decltype(whole_tag)::value;
       const uint64_t tmap_a = reinterpret_cast<uint64_t>(&p.tmap_a);
       const uint64_t tmap_b = reinterpret_cast<uint64_t>(&p.tmap_b);
       const int nsub = (min(K, k0 + 128) - k0 + kb - 1) / kb;
@@ -628,22 +631,29 @@ __global__ void __launch_bounds__(kTcThreads) wgrad_tc_kernel(const __grid_const
       for (int it = 0; it < nchunks; ++it) {
         mbar_wait(smem_u32(&empty[stage]), ephase);
         const uint32_t bar = smem_u32(&full[stage]);
-        mbar_arrive_expect_tx(bar, bytes);
         int n0p, i0, j0, rem;
         p.fd_hw.divmod(m_lo + it * 64, n0p, rem);
         p.fd_wg.divmod(rem, i0, j0);
-        if (p.tma_a) {
-          const int xb = j0 * p.is, yb = i0 * p.is;
-          uint32_t dst = a_base + (uint32_t)stage * kStageA;
-          for (int g = 0; g < nsub; ++g, dst += (uint32_t)sub_bytes) {
-            const uint32_t ent = tma_tab[g];
-            tma_load_4d(dst, tmap_a, bar, (int)(ent & 0xffffu), xb + (int)(signed char)(ent >> 16), yb + (int)(signed char)(ent >> 24), n0p);
+        if (!kWhole || elect_one()) {
+          mbar_arrive_expect_tx(bar, bytes);
+          if (p.tma_a) {
+            const int xb = j0 * p.is, yb = i0 * p.is;
+            uint32_t dst = a_base + (uint32_t)stage * kStageA;
+            for (int g = 0; g < nsub; ++g, dst += (uint32_t)sub_bytes) {
+              const uint32_t ent = tma_tab[g];
+              tma_load_4d(dst, tmap_a, bar, (int)(ent & 0xffffu), xb + (int)(signed char)(ent >> 16), yb + (int)(signed char)(ent >> 24), n0p);
+            }
           }
+          if (p.tma_b)
+            tma_load_4d(b_base + (uint32_t)stage * stageB, tmap_b, bar, n0, var.ox0 + p.os * j0, var.oy0 + p.os * i0, n0p);
         }
-        if (p.tma_b)
-          tma_load_4d(b_base + (uint32_t)stage * stageB, tmap_b, bar, n0, var.ox0 + p.os * j0, var.oy0 + p.os * i0, n0p);
+        if (kWhole) __syncwarp();
         if (++stage == S) { stage = 0; ephase ^= 1u; }
       }
+    };
+    if (p.tma_a || p.tma_b) {
+      if (!need_gather) { if (warp == 0) tma_loop(std::true_type{}); }
+      else if (tid == 0) tma_loop(std::false_type{});
     }
     if (need_gather) {
       // ---- cp.async part ----
@@ -721,7 +731,7 @@ __global__ void __launch_bounds__(kTcThreads) wgrad_tc_kernel(const __grid_const
       }
     }
   } else if (warp == 4) {
-    if (lane == 0) {
+    {                                             // whole warp, one elected lane issues (elect_one)
       const uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
       const uint32_t bswz = swz_code(rowB), aswz = swz_code(kbB);
       // descriptors of stage 0 / pixel step 0; a stage or a 16-pixel step only moves the (address >> 4) field
@@ -735,13 +745,17 @@ __global__ void __launch_bounds__(kTcThreads) wgrad_tc_kernel(const __grid_const
         tc_fence_after();
         const uint64_t da = da0 + (uint64_t)(((uint32_t)stage * kStageA) >> 4);
         const uint64_t db = db0 + (uint64_t)(((uint32_t)stage * (uint32_t)stageB) >> 4);
+        if (elect_one()) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q)              // 16 pixels per MMA
-          mma_bf16(tmem, da + q * astep, db + q * bstep, idesc, (kc | q) != 0);
-        mma_commit(smem_u32(&empty[stage]));
+          for (int q = 0; q < 4; ++q)            // 16 pixels per MMA
+            mma_bf16(tmem, da + q * astep, db + q * bstep, idesc, (kc | q) != 0);
+          mma_commit(smem_u32(&empty[stage]));
+        }
+        __syncwarp();
         if (++stage == S) { stage = 0; fphase ^= 1u; }
       }
-      mma_commit(smem_u32(&accum));
+      if (elect_one()) mma_commit(smem_u32(&accum));
+      __syncwarp();
     }
   } else {
     mbar_wait(smem_u32(&accum), 0);

@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) nb_tail_fwd_kernel(const __gri
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float bias_s[kCo], ebias_s[kCo];   // bias; exp(bias - max bias)
   __shared__ float loss_red[8];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = tid & 31;   // warp-uniform role dispatch for ptxas
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t w_base = base, a_base = base + kWBytes;
   unsigned char* w_gen = smem_raw + (base - smem_u32(smem_raw));
@@ -121,8 +121,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) nb_tail_fwd_kernel(const __gri
   pdl_trigger();
 
   const int R = p.rows_per_band;
+  // The single-thread roles below run their loops on the WHOLE warp and only the issuing instructions sit under
+  // elect_one() (tc_common.cuh): uniform control flow keeps descriptors and addresses in uniform registers; inside an
+  // `if (lane == 0)` every UTCHMMA / UTMALDG operand went through R2UR and an ELECT .. BRA.U.ANY wrapper.
   if (warp == 0) {
-    if (lane == 0) {
+    {
       // ---------------- producer: one input row = 4 TMA boxes ----------------
       const uint64_t tmap = reinterpret_cast<uint64_t>(&p.tmap_x);
       int g = 0;                                       // running input-row index of this CTA
@@ -132,16 +135,22 @@ __global__ void __launch_bounds__(kFwdThreads, 1) nb_tail_fwd_kernel(const __gri
           const int slot = g % kSlots;
           mbar_wait(smem_u32(&empty[slot]), (uint32_t)(((g / kSlots) & 1) ^ 1));
           const uint32_t bar = smem_u32(&full[slot]);
-          if (p.dbg & 2) { mbar_arrive(bar); continue; }
-          mbar_arrive_expect_tx(bar, (uint32_t)kSlotA);
-          const uint32_t dst = a_base + (uint32_t)slot * kSlotA;
+          if (elect_one()) {
+            if (p.dbg & 2) {
+              mbar_arrive(bar);
+            } else {
+              mbar_arrive_expect_tx(bar, (uint32_t)kSlotA);
+              const uint32_t dst = a_base + (uint32_t)slot * kSlotA;
 #pragma unroll
-          for (int c = 0; c < 3; ++c) tma_load_4d(dst + (uint32_t)c * kCopyA, tmap, bar, 0, c - 1, y0 - 1 + i, n);
+              for (int c = 0; c < 3; ++c) tma_load_4d(dst + (uint32_t)c * kCopyA, tmap, bar, 0, c - 1, y0 - 1 + i, n);
+            }
+          }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       // ---------------- MMA issue ----------------
       const uint32_t idesc = make_idesc_bf16(128, kCo, 0, 0);
       const uint64_t da0 = make_smem_desc(a_base, 16, 512, SWZ_64);
@@ -161,24 +170,30 @@ __global__ void __launch_bounds__(kFwdThreads, 1) nb_tail_fwd_kernel(const __gri
               mbar_wait(smem_u32(&full[slot]), (uint32_t)((g / kSlots) & 1));
               tc_fence_after();
             }
+            if (elect_one()) {
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx)
+              for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
-              for (int ks = 0; ks < 2; ++ks) {
-                const uint64_t da = da0 + (uint64_t)((slot * kSlotA + (uint32_t)kx * kCopyA + (uint32_t)ks * 32u) >> 4);
-                const uint64_t db = db0 + (uint64_t)(((uint32_t)(ky * 3 + kx) * kTapW + (uint32_t)ks * 32u) >> 4);
-                mma_bf16(dtm, da, db, idesc, (ky | kx | ks) != 0);
-              }
-            // input row o is dead after its dy = -1 use by output row o: release it now so that row o + 3 loads under the
-            // remaining twelve MMAs of this tile and the first twelve of the next
-            if (ky == 0 && o < R - 1) mma_commit(smem_u32(&empty[slot]));
+                for (int ks = 0; ks < 2; ++ks) {
+                  const uint64_t da = da0 + (uint64_t)((slot * kSlotA + (uint32_t)kx * kCopyA + (uint32_t)ks * 32u) >> 4);
+                  const uint64_t db = db0 + (uint64_t)(((uint32_t)(ky * 3 + kx) * kTapW + (uint32_t)ks * 32u) >> 4);
+                  mma_bf16(dtm, da, db, idesc, (ky | kx | ks) != 0);
+                }
+              // input row o is dead after its dy = -1 use by output row o: release it now so that row o + 3 loads under
+              // the remaining twelve MMAs of this tile and the first twelve of the next
+              if (ky == 0 && o < R - 1) mma_commit(smem_u32(&empty[slot]));
+            }
+            __syncwarp();
           }
-          mma_commit(smem_u32(&tfull[buf]));
-          if (o == R - 1) {                            // end of the band: its last three input rows
-            mma_commit(smem_u32(&empty[(g0 + R - 1) % kSlots]));
-            mma_commit(smem_u32(&empty[(g0 + R) % kSlots]));
-            mma_commit(smem_u32(&empty[(g0 + R + 1) % kSlots]));
+          if (elect_one()) {
+            mma_commit(smem_u32(&tfull[buf]));
+            if (o == R - 1) {                          // end of the band: its last three input rows
+              mma_commit(smem_u32(&empty[(g0 + R - 1) % kSlots]));
+              mma_commit(smem_u32(&empty[(g0 + R) % kSlots]));
+              mma_commit(smem_u32(&empty[(g0 + R + 1) % kSlots]));
+            }
           }
+          __syncwarp();
         }
       }
     }
@@ -357,7 +372,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) nb_tail_wgrad_kernel(const __gr
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long full_a[kWgSlotsA], empty_a[kWgSlotsA], full_b[kWgSlotsB], empty_b[kWgSlotsB], accum;
   __shared__ uint32_t tmem_base_s;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = tid & 31;   // warp-uniform role dispatch for ptxas
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = base, b_base = base + kWgSlotsA * kWgSlotA;
   unsigned char* a_gen = smem_raw + (base - smem_u32(smem_raw));
@@ -388,7 +403,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) nb_tail_wgrad_kernel(const __gr
 
   const int R = p.rows_per_band;
   if (warp == 0) {
-    if (lane == 0) {
+    {                                                  // whole warp, one elected lane issues (elect_one)
       // ---------------- producer: input rows (three dx copies) and G rows, in the order the MMA thread consumes them ----------------
       const uint64_t tmx = reinterpret_cast<uint64_t>(&p.tmap_x), tmg = reinterpret_cast<uint64_t>(&p.tmap_g);
       int ga = 0, gb = 0;
@@ -399,26 +414,38 @@ __global__ void __launch_bounds__(kWgThreads, 1) nb_tail_wgrad_kernel(const __gr
             const int slot = ga % kWgSlotsA;
             mbar_wait(smem_u32(&empty_a[slot]), (uint32_t)(((ga / kWgSlotsA) & 1) ^ 1));
             const uint32_t bar = smem_u32(&full_a[slot]);
-            if (p.dbg & 2) { mbar_arrive(bar); continue; }
-            mbar_arrive_expect_tx(bar, (uint32_t)(3 * kCopyA));
-            const uint32_t dst = a_base + (uint32_t)slot * kWgSlotA;
+            if (elect_one()) {
+              if (p.dbg & 2) {
+                mbar_arrive(bar);
+              } else {
+                mbar_arrive_expect_tx(bar, (uint32_t)(3 * kCopyA));
+                const uint32_t dst = a_base + (uint32_t)slot * kWgSlotA;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) tma_load_4d(dst + (uint32_t)c * kCopyA, tmx, bar, 0, c - 1, y0 - 1 + i, n);
+                for (int c = 0; c < 3; ++c) tma_load_4d(dst + (uint32_t)c * kCopyA, tmx, bar, 0, c - 1, y0 - 1 + i, n);
+              }
+            }
+            __syncwarp();
           }
           const int slot = gb % kWgSlotsB;
           mbar_wait(smem_u32(&empty_b[slot]), (uint32_t)(((gb / kWgSlotsB) & 1) ^ 1));
           const uint32_t bar = smem_u32(&full_b[slot]);
-          if (p.dbg & 2) { mbar_arrive(bar); ++gb; continue; }
-          mbar_arrive_expect_tx(bar, (uint32_t)kWgSlotB);
-          const uint32_t dst = b_base + (uint32_t)slot * kWgSlotB;
-          tma_load_4d(dst, tmg, bar, half * 128, 0, y0 + o, n);
-          tma_load_4d(dst + 16384u, tmg, bar, half * 128 + 64, 0, y0 + o, n);
+          if (elect_one()) {
+            if (p.dbg & 2) {
+              mbar_arrive(bar);
+            } else {
+              mbar_arrive_expect_tx(bar, (uint32_t)kWgSlotB);
+              const uint32_t dst = b_base + (uint32_t)slot * kWgSlotB;
+              tma_load_4d(dst, tmg, bar, half * 128, 0, y0 + o, n);
+              tma_load_4d(dst + 16384u, tmg, bar, half * 128 + 64, 0, y0 + o, n);
+            }
+          }
+          __syncwarp();
           ++gb;
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {                                                  // whole warp, one elected lane issues (elect_one)
       // ---------------- MMA issue ----------------
       const uint32_t idesc = make_idesc_bf16(128, 128, 1, 1);
       const uint64_t da0 = make_smem_desc(a_base, kCopyA, 512, SWZ_64);        // M: 4 x 32 channels, one dx copy apart
@@ -437,21 +464,28 @@ __global__ void __launch_bounds__(kWgThreads, 1) nb_tail_wgrad_kernel(const __gr
             if (o == 0 || ky == 2) mbar_wait(smem_u32(&full_a[slot]), (uint32_t)((g / kWgSlotsA) & 1));
             tc_fence_after();
             const uint64_t da = da0 + (uint64_t)((slot * kWgSlotA) >> 4);
+            if (elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks)       // 16 pixels per MMA
-              mma_bf16(tmem + (uint32_t)(ky * 128), da + (uint64_t)(ks * 64), db + (uint64_t)(ks * 128), idesc, !(first && ks == 0));
-            if (ky == 0 && o < R - 1) mma_commit(smem_u32(&empty_a[slot]));
+              for (int ks = 0; ks < 8; ++ks)     // 16 pixels per MMA
+                mma_bf16(tmem + (uint32_t)(ky * 128), da + (uint64_t)(ks * 64), db + (uint64_t)(ks * 128), idesc, !(first && ks == 0));
+              if (ky == 0 && o < R - 1) mma_commit(smem_u32(&empty_a[slot]));
+            }
+            __syncwarp();
           }
           first = false;
-          mma_commit(smem_u32(&empty_b[bslot]));
-          if (o == R - 1) {
-            mma_commit(smem_u32(&empty_a[(g0 + R - 1) % kWgSlotsA]));
-            mma_commit(smem_u32(&empty_a[(g0 + R) % kWgSlotsA]));
-            mma_commit(smem_u32(&empty_a[(g0 + R + 1) % kWgSlotsA]));
+          if (elect_one()) {
+            mma_commit(smem_u32(&empty_b[bslot]));
+            if (o == R - 1) {
+              mma_commit(smem_u32(&empty_a[(g0 + R - 1) % kWgSlotsA]));
+              mma_commit(smem_u32(&empty_a[(g0 + R) % kWgSlotsA]));
+              mma_commit(smem_u32(&empty_a[(g0 + R + 1) % kWgSlotsA]));
+            }
           }
+          __syncwarp();
         }
       }
-      mma_commit(smem_u32(&accum));
+      if (elect_one()) mma_commit(smem_u32(&accum));
+      __syncwarp();
     }
   } else {
     const int gb = (worker < p.total_bands) ? 1 : 0;
@@ -516,7 +550,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) nb_tail_dgrad_kernel(const __gr
   __shared__ __align__(8) unsigned long long full[kDgStages], empty[kDgStages], tfull[4], tempty[4];
   __shared__ uint32_t tmem_base_s;
   __shared__ float edge[4][4][2][kCi];                 // [row & 3][pixel quarter][kx = 0 of lane 0 | kx = 2 of lane 31][ci]
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = tid & 31;   // warp-uniform role dispatch for ptxas
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t w_base = base, a_base = base + kDgWBytes;
   unsigned char* w_gen = smem_raw + (base - smem_u32(smem_raw));
@@ -546,7 +580,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) nb_tail_dgrad_kernel(const __gr
 
   const int R = p.rows_per_band;
   if (warp == 0) {
-    if (lane == 0) {
+    {                                                  // whole warp, one elected lane issues (elect_one)
       // ---------------- producer: G rows y0-1 .. y0+R, four 64-class chunks each ----------------
       const uint64_t tmg = reinterpret_cast<uint64_t>(&p.tmap_g);
       int g = 0;
@@ -557,14 +591,20 @@ __global__ void __launch_bounds__(kDgThreads, 1) nb_tail_dgrad_kernel(const __gr
             const int stage = g % kDgStages;
             mbar_wait(smem_u32(&empty[stage]), (uint32_t)(((g / kDgStages) & 1) ^ 1));
             const uint32_t bar = smem_u32(&full[stage]);
-            if (p.dbg & 2) { mbar_arrive(bar); continue; }
-            mbar_arrive_expect_tx(bar, (uint32_t)kDgStage);
-            tma_load_4d(a_base + (uint32_t)stage * kDgStage, tmg, bar, kc * 64, 0, y0 + rr, n);
+            if (elect_one()) {
+              if (p.dbg & 2) {
+                mbar_arrive(bar);
+              } else {
+                mbar_arrive_expect_tx(bar, (uint32_t)kDgStage);
+                tma_load_4d(a_base + (uint32_t)stage * kDgStage, tmg, bar, kc * 64, 0, y0 + rr, n);
+              }
+            }
+            __syncwarp();
           }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {                                                  // whole warp, one elected lane issues (elect_one)
       // ---------------- MMA issue ----------------
       const uint32_t idesc = make_idesc_bf16(128, 96, 0, 0);
       const uint64_t da0 = make_smem_desc(a_base, 16, 1024, SWZ_128);
@@ -582,19 +622,25 @@ __global__ void __launch_bounds__(kDgThreads, 1) nb_tail_dgrad_kernel(const __gr
             mbar_wait(smem_u32(&full[stage]), (uint32_t)((g / kDgStages) & 1));
             tc_fence_after();
             const uint64_t da = da0 + (uint64_t)(((uint32_t)stage * kDgStage) >> 4);
+            if (elect_one()) {
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-              const int oo = rr + ky - 1;              // band-local output row fed by the ky-th block
-              if (oo < 0 || oo >= R) continue;
-              const uint32_t dtm = tmem + (uint32_t)(((qb + oo) & 3) * 128);
-              const uint64_t db = db0 + (uint64_t)(((uint32_t)(ky * 4 + kc) * kDgChunkW) >> 4);
+              for (int ky = 0; ky < 3; ++ky) {
+                const int oo = rr + ky - 1;            // band-local output row fed by the ky-th block
+                if (oo < 0 || oo >= R) continue;
+                const uint32_t dtm = tmem + (uint32_t)(((qb + oo) & 3) * 128);
+                const uint64_t db = db0 + (uint64_t)(((uint32_t)(ky * 4 + kc) * kDgChunkW) >> 4);
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks)
-                mma_bf16(dtm, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc, !(ky == 2 && kc == 0 && ks == 0));
+                for (int ks = 0; ks < 4; ++ks)
+                  mma_bf16(dtm, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc, !(ky == 2 && kc == 0 && ks == 0));
+              }
+              mma_commit(smem_u32(&empty[stage]));
             }
-            mma_commit(smem_u32(&empty[stage]));
+            __syncwarp();
           }
-          if (rr >= 1) mma_commit(smem_u32(&tfull[(qb + rr - 1) & 3]));      // output row rr - 1 is complete
+          if (rr >= 1) {
+            if (elect_one()) mma_commit(smem_u32(&tfull[(qb + rr - 1) & 3]));      // output row rr - 1 is complete
+            __syncwarp();
+          }
         }
       }
     }
@@ -695,7 +741,7 @@ __global__ void __launch_bounds__(kMidThreads, 1) nb_mid_kernel(const __grid_con
   __shared__ __align__(8) unsigned long long full[kMidSlots], empty[kMidSlots], tfull[2], tempty[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ float bias_s[32];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = tid & 31;   // warp-uniform role dispatch for ptxas
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t w_base = base, a_base = base + kMidWBytes + 1024 - (kMidWBytes & 1023);
   unsigned char* w_gen = smem_raw + (base - smem_u32(smem_raw));
@@ -766,7 +812,7 @@ __global__ void __launch_bounds__(kMidThreads, 1) nb_mid_kernel(const __grid_con
     fence_proxy_async_smem();
     for (; gs < g; ++gs) mbar_arrive(smem_u32(&full[gs % kMidSlots]));
   } else if (warp == 4) {
-    if (lane == 0) {
+    {                                                  // whole warp, one elected lane issues (elect_one)
       const uint32_t idesc = make_idesc_bf16(128, 32, 0, 0);
       const uint64_t da0 = make_smem_desc(a_base, 16, 512, SWZ_64);
       const uint64_t db0 = make_smem_desc(w_base, 16, 512, SWZ_64);
@@ -785,22 +831,28 @@ __global__ void __launch_bounds__(kMidThreads, 1) nb_mid_kernel(const __grid_con
               mbar_wait(smem_u32(&full[slot]), (uint32_t)((g / kMidSlots) & 1));
               tc_fence_after();
             }
+            if (elect_one()) {
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx)
+              for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
-              for (int ks = 0; ks < 2; ++ks) {
-                const uint64_t da = da0 + (uint64_t)((slot * kSlotA + (uint32_t)kx * kCopyA + (uint32_t)ks * 32u) >> 4);
-                const uint64_t db = db0 + (uint64_t)(((uint32_t)(ky * 3 + kx) * 2048u + (uint32_t)ks * 32u) >> 4);
-                mma_bf16(dtm, da, db, idesc, (ky | kx | ks) != 0);
-              }
-            if (ky == 0 && o < R - 1) mma_commit(smem_u32(&empty[slot]));
+                for (int ks = 0; ks < 2; ++ks) {
+                  const uint64_t da = da0 + (uint64_t)((slot * kSlotA + (uint32_t)kx * kCopyA + (uint32_t)ks * 32u) >> 4);
+                  const uint64_t db = db0 + (uint64_t)(((uint32_t)(ky * 3 + kx) * 2048u + (uint32_t)ks * 32u) >> 4);
+                  mma_bf16(dtm, da, db, idesc, (ky | kx | ks) != 0);
+                }
+              if (ky == 0 && o < R - 1) mma_commit(smem_u32(&empty[slot]));
+            }
+            __syncwarp();
           }
-          mma_commit(smem_u32(&tfull[buf]));
-          if (o == R - 1) {
-            mma_commit(smem_u32(&empty[(g0 + R - 1) % kMidSlots]));
-            mma_commit(smem_u32(&empty[(g0 + R) % kMidSlots]));
-            mma_commit(smem_u32(&empty[(g0 + R + 1) % kMidSlots]));
+          if (elect_one()) {
+            mma_commit(smem_u32(&tfull[buf]));
+            if (o == R - 1) {
+              mma_commit(smem_u32(&empty[(g0 + R - 1) % kMidSlots]));
+              mma_commit(smem_u32(&empty[(g0 + R) % kMidSlots]));
+              mma_commit(smem_u32(&empty[(g0 + R + 1) % kMidSlots]));
+            }
           }
+          __syncwarp();
         }
       }
     }
@@ -870,7 +922,7 @@ __global__ void __launch_bounds__(kMwThreads, 1) nb_mid_wgrad_kernel(const __gri
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long full_a[kMwSlotsA], empty_a[kMwSlotsA], full_b[kMwSlotsB], empty_b[kMwSlotsB], accum;
   __shared__ uint32_t tmem_base_s;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = tid & 31;   // warp-uniform role dispatch for ptxas
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = base, b_base = base + kMwSlotsA * kWgSlotA;
   unsigned char* a_gen = smem_raw + (base - smem_u32(smem_raw));
@@ -965,7 +1017,7 @@ __global__ void __launch_bounds__(kMwThreads, 1) nb_mid_wgrad_kernel(const __gri
     cp_async_wait<0>();
     while (npend > 0) publish_oldest();
   } else if (warp == 4) {
-    if (lane == 0) {
+    {                                                  // whole warp, one elected lane issues (elect_one)
       const uint32_t idesc = make_idesc_bf16(128, 32, 1, 1);
       const uint64_t da0 = make_smem_desc(a_base, kCopyA, 512, SWZ_64);        // M: 4 x 32 channels, one slice apart
       const uint64_t db0 = make_smem_desc(b_base, 512, 512, SWZ_64);           // N: 32 channels = one atom
@@ -985,21 +1037,28 @@ __global__ void __launch_bounds__(kMwThreads, 1) nb_mid_wgrad_kernel(const __gri
             if (ky == 0) mbar_wait(smem_u32(&full_b[bslot]), (uint32_t)((gb / kMwSlotsB) & 1));
             tc_fence_after();
             const uint64_t da = da0 + (uint64_t)((slot * kWgSlotA) >> 4);
+            if (elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks)
-              mma_bf16(tmem + (uint32_t)(ky * 32), da + (uint64_t)(ks * 64), db + (uint64_t)(ks * 64), idesc, !(first && ks == 0));
-            if (ky == 0 && o < R - 1) mma_commit(smem_u32(&empty_a[slot]));
+              for (int ks = 0; ks < 8; ++ks)
+                mma_bf16(tmem + (uint32_t)(ky * 32), da + (uint64_t)(ks * 64), db + (uint64_t)(ks * 64), idesc, !(first && ks == 0));
+              if (ky == 0 && o < R - 1) mma_commit(smem_u32(&empty_a[slot]));
+            }
+            __syncwarp();
           }
           first = false;
-          mma_commit(smem_u32(&empty_b[bslot]));
-          if (o == R - 1) {
-            mma_commit(smem_u32(&empty_a[(g0 + R - 1) % kMwSlotsA]));
-            mma_commit(smem_u32(&empty_a[(g0 + R) % kMwSlotsA]));
-            mma_commit(smem_u32(&empty_a[(g0 + R + 1) % kMwSlotsA]));
+          if (elect_one()) {
+            mma_commit(smem_u32(&empty_b[bslot]));
+            if (o == R - 1) {
+              mma_commit(smem_u32(&empty_a[(g0 + R - 1) % kMwSlotsA]));
+              mma_commit(smem_u32(&empty_a[(g0 + R) % kMwSlotsA]));
+              mma_commit(smem_u32(&empty_a[(g0 + R + 1) % kMwSlotsA]));
+            }
           }
+          __syncwarp();
         }
       }
-      mma_commit(smem_u32(&accum));
+      if (elect_one()) mma_commit(smem_u32(&accum));
+      __syncwarp();
     }
   } else if ((int)blockIdx.x < p.total_bands) {
     // ---------------- drain: lane m = (kx, ci) or the all-ones rows, column = co ----------------

@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) slab_fwd_kernel(const __grid_c
   __shared__ uint32_t tmem_base_s;
   __shared__ float stat_red[4 * kFwdSets][2][16];
   const SlabGeom& G = p.g;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = tid & 31;   // warp-uniform role dispatch for ptxas
   constexpr int planes = kCx >> 3, plog2 = kCx == 16 ? 1 : 2;
   if (tid == 0) SLAB_TRACE(p, 0);
   const uint32_t xbytes = (uint32_t)planes * (uint32_t)G.plane_bytes;      // one buffer of the band
@@ -164,8 +164,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) slab_fwd_kernel(const __grid_c
       if (tid == 0 && it == 1) SLAB_TRACE(p, 5);
     }
   } else if (warp == 4) {
-    if (lane == 0) {
+    {
       // ---------------- MMA issue: 9 taps x (Cx / 16) k-steps per tile ----------------
+      // the whole warp walks the loops (uniform control flow: descriptors stay in uniform registers), one elected lane
+      // issues -- see elect_one(), tc_common.cuh
       const uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
       const uint64_t da0 = make_smem_desc(x_base, (uint32_t)G.plane_bytes, 128, SWZ_NONE);
       const uint64_t db0 = make_smem_desc(w_base, 1024, 128, SWZ_NONE);
@@ -184,7 +186,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) slab_fwd_kernel(const __grid_c
         const int buf = it & 1;
         mbar_wait(smem_u32(&full[buf]), (uint32_t)((it >> 1) & 1));
         tc_fence_after();
-        if (it == 0) SLAB_TRACE(p, 6);
+        if (it == 0 && lane == 0) SLAB_TRACE(p, 6);
         for (int t = 0; t < G.T; ++t, ++gt) {
           const int ab = gt % kFwdBufs;
           mbar_wait(smem_u32(&tempty[ab]), (uint32_t)(((gt / kFwdBufs) & 1) ^ 1));
@@ -192,16 +194,20 @@ __global__ void __launch_bounds__(kFwdThreads, 1) slab_fwd_kernel(const __grid_c
           const uint32_t dtm = tmem + (uint32_t)(ab * 64);
           // taps shift the start address down as well as up: 32-bit arithmetic on the descriptor's low word
           const uint32_t dat = (uint32_t)da0 + (((uint32_t)buf * xbytes) >> 4) + (uint32_t)(G.guard + G.P + 128 * t);
+          if (elect_one()) {
 #pragma unroll
-          for (int m = 0; m < 9 * ksteps; ++m)
-            mma_bf16(dtm, (da0 & 0xFFFFFFFF00000000ull) | (uint64_t)(dat + aoff[m]), db0 + (uint64_t)boff[m], idesc, m != 0);
-          mma_commit(smem_u32(&tfull[ab]));
-          if (gt == 0) SLAB_TRACE(p, 7);
+            for (int m = 0; m < 9 * ksteps; ++m)
+              mma_bf16(dtm, (da0 & 0xFFFFFFFF00000000ull) | (uint64_t)(dat + aoff[m]), db0 + (uint64_t)boff[m], idesc, m != 0);
+            mma_commit(smem_u32(&tfull[ab]));
+          }
+          __syncwarp();
+          if (gt == 0 && lane == 0) SLAB_TRACE(p, 7);
         }
-        mma_commit(smem_u32(&empty[buf]));             // the band's shared-memory copy is free once these MMAs are done
-        if (it == 0) SLAB_TRACE(p, 8);
+        if (elect_one()) mma_commit(smem_u32(&empty[buf]));   // the band's shared-memory copy is free once these MMAs are done
+        __syncwarp();
+        if (it == 0 && lane == 0) SLAB_TRACE(p, 8);
       }
-      SLAB_TRACE(p, 9);
+      if (lane == 0) SLAB_TRACE(p, 9);
     }
   } else {
     // ---------------- epilogue: set `es` drains accumulator `es` (tiles es, es + kFwdSets, ...) ----------------
@@ -297,7 +303,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) slab_dgrad_kernel(const __grid_
   __shared__ uint32_t tmem_base_s;
   __shared__ float stat_red[4 * kDgSets][3][16];
   const SlabGeom& G = p.g;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = tid & 31;   // warp-uniform role dispatch for ptxas
   constexpr int kPlanes = 8;                          // 4 parity sub-images x 2 planes (16 channels)
   constexpr uint32_t kTapB = 2u * kCn * 16u;          // weights of one tap: [2][Cn rows][16 B]
   constexpr uint32_t kCols = kDgBufs * kCn <= 128 ? 128u : 256u;
@@ -359,8 +365,9 @@ __global__ void __launch_bounds__(kDgThreads, 1) slab_dgrad_kernel(const __grid_
       mbar_arrive(smem_u32(&full[buf]));
     }
   } else if (warp == 4) {
-    if (lane == 0) {
+    {
       // ---------------- MMA issue: 16 taps per tile; tap ky reads sub-image row parity qy at row shift da ----------------
+      // (whole warp, one elected lane issues: elect_one(), tc_common.cuh)
       const uint32_t idesc = make_idesc_bf16(128, kCn, 0, 0);
       const uint64_t da0 = make_smem_desc(y_base, (uint32_t)G.plane_bytes, 128, SWZ_NONE);
       const uint64_t db0 = make_smem_desc(w_base, kCn * 16, 128, SWZ_NONE);
@@ -385,13 +392,17 @@ __global__ void __launch_bounds__(kDgThreads, 1) slab_dgrad_kernel(const __grid_
           const uint32_t dtm = tmem + (uint32_t)(ab * kCn);
           // taps shift the start address down as well as up: 32-bit arithmetic on the descriptor's low word
           const uint32_t dat = (uint32_t)da0 + (((uint32_t)buf * ybytes) >> 4) + (uint32_t)(G.guard + G.P + 128 * t);
+          if (elect_one()) {
 #pragma unroll
-          for (int tap = 0; tap < 16; ++tap)
-            mma_bf16(dtm, (da0 & 0xFFFFFFFF00000000ull) | (uint64_t)(dat + aoff[tap]), db0 + (uint64_t)((uint32_t)tap * (kTapB >> 4)), idesc,
-                     tap != 0);
-          mma_commit(smem_u32(&tfull[ab]));
+            for (int tap = 0; tap < 16; ++tap)
+              mma_bf16(dtm, (da0 & 0xFFFFFFFF00000000ull) | (uint64_t)(dat + aoff[tap]), db0 + (uint64_t)((uint32_t)tap * (kTapB >> 4)), idesc,
+                       tap != 0);
+            mma_commit(smem_u32(&tfull[ab]));
+          }
+          __syncwarp();
         }
-        mma_commit(smem_u32(&empty[buf]));
+        if (elect_one()) mma_commit(smem_u32(&empty[buf]));
+        __syncwarp();
       }
     }
   } else {
@@ -507,7 +518,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) slab_wgrad_kernel(const __grid_
   __shared__ __align__(8) unsigned long long full[2], empty[2], accum;
   __shared__ uint32_t tmem_base_s;
   const SlabGeom& G = p.g;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = tid & 31;   // warp-uniform role dispatch for ptxas
   constexpr int xplanes = kCx >> 3, xlog2 = kCx == 16 ? 1 : 2;
   constexpr int kN = 3 * kCx;                         // (column shift, ci)
   constexpr int kPlanesBuf = 8 + 3 * xplanes;         // dY: 4 sub-images x 2 planes, then 3 shifted copies of x
@@ -573,8 +584,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) slab_wgrad_kernel(const __grid_
       mbar_arrive(smem_u32(&full[buf]));
     }
   } else if (warp == 4) {
-    if (lane == 0) {
+    {
       // ---------------- MMA issue: per 16 positions, one MMA per row shift da ----------------
+      // (whole warp, one elected lane issues: elect_one(), tc_common.cuh)
       // MN-major operands without swizzle: 8 channels contiguous (16 B), positions at a 16-byte pitch; the stride between
       // channel atoms (planes) goes to the SBO field, the stride between groups of 8 positions (128 B) to the LBO field.
       const uint32_t idesc = make_idesc_bf16(128, kN, 1, 1);
@@ -590,17 +602,22 @@ __global__ void __launch_bounds__(kWgThreads, 1) slab_wgrad_kernel(const __grid_
         tc_fence_after();
         const uint32_t p0 = (((uint32_t)buf * bbytes) >> 4) + (uint32_t)(G.guard + G.P);
         const uint32_t alo = (uint32_t)da0 + p0, blo = (uint32_t)db0 + p0;
-        for (int k = 0; k < ksteps; ++k) {
+        if (elect_one()) {
+          const uint32_t acc0 = first ? 0u : 1u;
+          for (int k = 0; k < ksteps; ++k) {
 #pragma unroll
-          for (int d3 = 0; d3 < 3; ++d3)                // da = d3 - 1: dYq[p] pairs with x[p - da*P - db]
-            mma_bf16(tmem + (uint32_t)(d3 * kN), (da0 & 0xFFFFFFFF00000000ull) | (uint64_t)(alo + (uint32_t)(16 * k)),
-                     (db0 & 0xFFFFFFFF00000000ull) | (uint64_t)(blo + (uint32_t)(16 * k) - (uint32_t)((d3 - 1) * G.P)), idesc,
-                     first ? 0u : 1u);
-          first = false;
+            for (int d3 = 0; d3 < 3; ++d3)              // da = d3 - 1: dYq[p] pairs with x[p - da*P - db]
+              mma_bf16(tmem + (uint32_t)(d3 * kN), (da0 & 0xFFFFFFFF00000000ull) | (uint64_t)(alo + (uint32_t)(16 * k)),
+                       (db0 & 0xFFFFFFFF00000000ull) | (uint64_t)(blo + (uint32_t)(16 * k) - (uint32_t)((d3 - 1) * G.P)), idesc,
+                       k == 0 ? acc0 : 1u);
+          }
+          mma_commit(smem_u32(&empty[buf]));
         }
-        mma_commit(smem_u32(&empty[buf]));
+        __syncwarp();
+        first = false;
       }
-      mma_commit(smem_u32(&accum));
+      if (elect_one()) mma_commit(smem_u32(&accum));
+      __syncwarp();
     }
   } else {
     // ---------------- epilogue (once): rows (qy, qx, co) of the three accumulators -> dW[ci][co][ky][kx] ----------------
