@@ -656,14 +656,18 @@ template <typename T>
 void launch_bn_bwd(const BnBwdArgs& a, cudaStream_t st) {
   constexpr int V = vec_of<T>();
   if constexpr (std::is_same<T, __nv_bfloat16>::value) {
-    // one cooperative launch when every thread's share fits its registers (tensors up to 2.4 MB): half a register
-    // file per SM, so it stays co-resident with the weight-gradient kernels of the auxiliary stream
+    // one cooperative launch when every thread's share fits its registers: half a register file per SM for two CTAs,
+    // so it stays co-resident with the weight-gradient kernels of the auxiliary stream
     static const bool coop_off = getenv("MMVAE_NO_COOP_BN") != nullptr;
     const int CV = a.C / 8;
     if (!coop_off && a.acc && !a.reduced && !a.dA_f32 && a.C % 8 == 0 && CV >= 1 && CV <= 32 && 256 % CV == 0) {
       const int RPI = 256 / CV;
       const long long row_groups = (a.rows + RPI - 1) / RPI;
-      const int grid = (int)std::min<long long>(148, row_groups);
+      // up to two CTAs per SM (__launch_bounds__(256, 2), 34 KB of shared memory each): tensors up to 4.8 MB.  Whatever
+      // else occupies the SMs finishes without waiting for this stream, and a programmatic dependent of this launch is
+      // not scheduled before every CTA here has started, so all CTAs reach the grid barrier.  MMVAE_COOP_CTAS: A/B.
+      static const int coop_ctas = [] { const char* e = getenv("MMVAE_COOP_CTAS"); return e ? atoi(e) : 296; }();
+      const int grid = (int)std::min<long long>(coop_ctas, row_groups);
       const int E = (int)((row_groups + grid - 1) / grid);
       if (E <= kCoopE) {
         count_launch();
