@@ -114,11 +114,8 @@ __global__ void __launch_bounds__(kTcThreads, kBwd ? 2 : 3) gconv_tc_kernel(cons
     }
     fence_barrier_init();
   }
-  // nacc > 1: the k-steps of a tile rotate over nacc accumulators that the epilogue adds up.  Back-to-back MMAs into ONE
-  // accumulator serialise on the tensor pipe's latency (~220 cycles each, whatever N is): with a narrow tile (N = 32 is 16
-  // cycles of math) a deep-K layer is a chain of K/16 dependent MMAs; independent accumulators overlap in the pipe.
-  const int nacc = (kBN >= 32 && p.tc_nacc > 1) ? p.tc_nacc : 1;     // 16-column tiles: K <= 256, never worth it
-  const int accw = 2 * BN * nacc;
+  // (k-steps rotating over 2 / 4 accumulators per tile were tried for the deep-K layers: neutral, profiles/r01_issue_loops.md)
+  const int accw = 2 * BN;
   const uint32_t ncols = accw <= 32 ? 32u : (accw <= 64 ? 64u : (accw <= 128 ? 128u : (accw <= 256 ? 256u : 512u)));
   if (warp == 4) tmem_alloc(smem_u32(&tmem_base_s), ncols);
   tc_fence_before();
@@ -293,7 +290,6 @@ __global__ void __launch_bounds__(kTcThreads, kBwd ? 2 : 3) gconv_tc_kernel(cons
       int stage = 0;
       uint32_t fphase = 0;
       int i = 0;
-      const int amask = nacc - 1;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
         int mt, vi, nt;
         decode_tile(p, t, mt, vi, nt);
@@ -303,7 +299,7 @@ __global__ void __launch_bounds__(kTcThreads, kBwd ? 2 : 3) gconv_tc_kernel(cons
         const int buf = i & 1;
         mbar_wait(smem_u32(&tempty[buf]), (uint32_t)(((i >> 1) & 1) ^ 1));   // epilogue drained this buffer
         tc_fence_after();
-        const uint32_t dtm = tmem + (uint32_t)(buf * nacc * BN);
+        const uint32_t dtm = tmem + (uint32_t)(buf * BN);
         for (int kc = 0; kc < nchunks; ++kc) {
           mbar_wait(fbar, fphase);
           tc_fence_after();
@@ -311,11 +307,11 @@ __global__ void __launch_bounds__(kTcThreads, kBwd ? 2 : 3) gconv_tc_kernel(cons
             if (kc + 1 < nchunks) {
 #pragma unroll
               for (int q = 0; q < 4; ++q)
-                mma_bf16(dtm + (uint32_t)((q & amask) * BN), da + aoff[q], db + (uint64_t)(q * 2), idesc, (kc != 0) | (q >= nacc));
+                mma_bf16(dtm, da + aoff[q], db + (uint64_t)(q * 2), idesc, (kc | q) != 0);
             } else {
 #pragma unroll
               for (int q = 0; q < 4; ++q)
-                if (q < nk_last) mma_bf16(dtm + (uint32_t)((q & amask) * BN), da + aoff[q], db + (uint64_t)(q * 2), idesc, (kc != 0) | (q >= nacc));
+                if (q < nk_last) mma_bf16(dtm, da + aoff[q], db + (uint64_t)(q * 2), idesc, (kc | q) != 0);
             }
             if (csz > 1) mma_commit_mc(ebar, cmask);
             else mma_commit(ebar);
@@ -370,21 +366,17 @@ __global__ void __launch_bounds__(kTcThreads, kBwd ? 2 : 3) gconv_tc_kernel(cons
       mbar_wait(smem_u32(&tfull[buf]), (uint32_t)((i >> 1) & 1));
       tc_fence_after();
       if (i == 0 && tid == 160) MMVAE_TRACE(p, 8);
-      const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * nacc * BN);
+      const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
+      uint32_t rnext[16];                                // the next 16-column group is in flight while this one is worked on
+      tmem_ld16_issue(tlane, rnext);
 #pragma unroll
       for (int gq = 0; gq < NG; ++gq) {
         const int c0 = gq * 16;
         float v[16];
-        tmem_ld16(tlane + (uint32_t)c0, v);
-        for (int a = 1; a < nacc; ++a) {
-          float w8[8];
-          tmem_ld8(tlane + (uint32_t)(a * BN + c0), w8);
+        tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] += w8[e];
-          tmem_ld8(tlane + (uint32_t)(a * BN + c0 + 8), w8);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[8 + e] += w8[e];
-        }
+        for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(rnext[e]);
+        if (gq + 1 < NG) tmem_ld16_issue(tlane + (uint32_t)(c0 + 16), rnext);
         const int co0 = n0 + c0;
         if (p.bias) {
 #pragma unroll
@@ -888,15 +880,10 @@ int gconv_per_sm() {
   return m;
 }
 
-// Both options below measured neutral to slightly negative on every deep-K layer once the issue loops were lean
+// Measured neutral to slightly negative on every deep-K layer once the issue loops were lean
 // (profiles/r01_issue_loops.md): OFF by default, kept for experiments.
 int mc_min_chunks() {                   // TMA multicast over clusters for layers at least this deep (MMVAE_MC_MIN_CHUNKS env; 0 = off)
   static int m = [] { const char* e = getenv("MMVAE_MC_MIN_CHUNKS"); return e ? atoi(e) : 0; }();
-  return m;
-}
-
-int nacc_min_chunks() {                 // several TMEM accumulators per tile for layers at least this deep (MMVAE_NACC_MIN_CHUNKS env; 0 = off)
-  static int m = [] { const char* e = getenv("MMVAE_NACC_MIN_CHUNKS"); return e ? atoi(e) : 0; }();
   return m;
 }
 
@@ -967,15 +954,6 @@ StatLayout launch_gconv_tc(const GConvParams& p0, cudaStream_t st) {
     }
   }
   const size_t smem = (size_t)stages * stage_bytes + 1024;
-  // several accumulators per tile for deep-K layers (see the kernel); every variant must have a full first k-chunk so
-  // that the first nacc MMAs initialise them all; at most 256 TMEM columns so that a second CTA still fits beside it
-  p.tc_nacc = 1;
-  {
-    int minK = 1 << 30;
-    for (int v = 0; v < p.nvar; ++v) minK = min(minK, p.var[v].ntaps * p.Ci);
-    if (nacc_min_chunks() > 0 && maxchunks >= nacc_min_chunks() && minK >= 64 && smem > 76 * 1024)
-      p.tc_nacc = bn < 32 ? 1 : (bn == 32 ? 4 : (bn == 64 ? 2 : 1));
-  }
   const bool bwd = p.bb.acc != nullptr;
   static bool attr_done = false;
   if (!attr_done) {

@@ -235,8 +235,14 @@ __global__ void __launch_bounds__(kFwdThreads, 1) slab_fwd_kernel(const __grid_c
 #pragma unroll
       for (int py = 0; py < 2; ++py) {
         float v0[16], v1[16];
-        tmem_ld16(tl + (uint32_t)(py * 32), v0);
-        tmem_ld16(tl + (uint32_t)(py * 32 + 16), v1);
+        {                                            // both loads in flight, one wait
+          uint32_t r0[16], r1[16];
+          tmem_ld16_issue(tl + (uint32_t)(py * 32), r0);
+          tmem_ld16_issue(tl + (uint32_t)(py * 32 + 16), r1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 16; ++e) { v0[e] = __uint_as_float(r0[e]); v1[e] = __uint_as_float(r1[e]); }
+        }
         if (valid) {
           uint4* dst = reinterpret_cast<uint4*>(p.y + (((size_t)n * 2 * G.H + 2 * i + py) * 2 * G.W + 2 * j) * 16);
           uint32_t pk[16];
