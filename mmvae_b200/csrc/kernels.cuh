@@ -235,6 +235,7 @@ struct StemArgs {
   int N, S;
   int Ho, Wo, R, tiles_per_frame, ntiles;   // filled by the launcher
   int qpr, pitch;                           // quads (4 output pixels) per output row; floats per row of the x tile
+  FastDiv fd_wo;                            // division by Wo (filled by the launcher)
 };
 struct TailArgs {
   const __nv_bfloat16* in;     // [N,H,W,Ci] activation feeding the tail conv

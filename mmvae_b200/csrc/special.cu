@@ -198,9 +198,10 @@ __global__ void __launch_bounds__(kStemWgThreads, 1) stem_wgrad_kernel(const Ste
     const int npx = min(a.R, a.Ho - oy0) * a.Wo;
     const float* xb = xs[buf];
     const unsigned char* db = dys[buf];
-#pragma unroll 2
+#pragma unroll 4
     for (int p = lane; p < npx; p += 32) {
-      const int oy_l = p / a.Wo, ox = p - oy_l * a.Wo;
+      int oy_l, ox;
+      a.fd_wo.divmod(p, oy_l, ox);
       float g[8];
       unpack8(*reinterpret_cast<const uint4*>(db + p * 64 + ((cg ^ ((p >> 1) & 3)) << 4)), g);
       const float* xr = xb + (2 * oy_l + kh) * pitch + 2 * ox;
@@ -509,6 +510,7 @@ bool stem_supported(int Cin, int Co, int S, int k, int s, int p) {
 
 static void stem_fill(StemArgs& a, int quads_per_tile) {
   a.Ho = a.S / 2; a.Wo = a.S / 2;
+  a.fd_wo = FastDiv(a.Wo);
   a.qpr = (a.Wo + 3) / 4;
   a.R = quads_per_tile / a.qpr;
   if (a.R > a.Ho) a.R = a.Ho;
