@@ -61,3 +61,19 @@ def test_tc_kernels_match_simt_widened():
     tol = (4e-3, 1e-3, 1e-3, 4e-3)
     bad = [(name, j, r) for name, rel in rows for j, r in enumerate(rel) if r is not None and not r <= tol[j]]
     assert not bad, bad
+
+
+def test_tc_kernels_match_simt_cluster_multicast():
+    """The optional deep-K path of gconv_tc_kernel (off by default, MMVAE_MC_MIN_CHUNKS): the channel tiles of a pixel tile
+    form a thread-block cluster and multicast their slice of every A box (UTMALDG.MULTICAST, multicast commit, drain lap).
+    The switch is read once per process, so the check runs in a child process."""
+    import os, subprocess, sys
+    code = ("import sys; sys.path.insert(0, 'tests'); import test_gpu_tc_selftest as t; "
+            "rows = t.run_selftest(64, image_size=64, z=64); tol = (4e-3, 1e-3, 1e-3, 4e-3); "
+            "bad = [(n, j, r) for n, rel in rows for j, r in enumerate(rel) if r is not None and not r <= tol[j]]; "
+            "assert not bad, bad; print('ok', len(rows))")
+    env = dict(os.environ, MMVAE_MC_MIN_CHUNKS="4")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "ok" in r.stdout
