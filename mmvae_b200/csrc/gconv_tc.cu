@@ -871,8 +871,11 @@ bool pixel_box(int rows, int Hg, int Wg, int& bw, int& bh, int& bn) {
   return true;
 }
 
-int wgrad_ctas() {                      // CTA budget of a weight-gradient launch (MMVAE_WGRAD_CTAS env, tuning)
-  static int m = [] { const char* e = getenv("MMVAE_WGRAD_CTAS"); return e ? atoi(e) : 148; }();
+// CTA budget of a weight-gradient launch (MMVAE_WGRAD_CTAS env, tuning).  Weight gradients run on the auxiliary stream
+// beside the critical path: leaving ~1/5 of the SMs free for the main stream's kernels beats one CTA per SM
+// (base step 1.2435 ms at 148, 1.232 +- 0.003 ms at 88 .. 132; the widened and notebook steps do not care).
+int wgrad_ctas() {
+  static int m = [] { const char* e = getenv("MMVAE_WGRAD_CTAS"); return e ? atoi(e) : 120; }();
   return m;
 }
 int gconv_per_sm() {
