@@ -514,17 +514,31 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_coop_kernel(const BnBwdArgs a, 
       }
     }
   }
+  // lanes of a warp with the same channel vector (lane % CV; CV is a power of two <= 32) first add up by shuffles, so that
+  // the shared-memory stage sums 8 warps instead of RPI = 256 / CV row groups serially (64 dependent loads at C = 32)
+  for (int d = CV; d < 32; d <<= 1) {
 #pragma unroll
-  for (int k = 0; k < VEC; ++k) {
-    red[(0 * RPI + rsub) * a.C + c0 + k] = s0[k];
-    red[(1 * RPI + rsub) * a.C + c0 + k] = s1[k];
-    red[(2 * RPI + rsub) * a.C + c0 + k] = s2[k];
+    for (int k = 0; k < VEC; ++k) {
+      s0[k] += __shfl_xor_sync(0xffffffffu, s0[k], d);
+      s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], d);
+      s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], d);
+    }
+  }
+  const int wrp = tid >> 5;
+  if ((tid & 31) < CV) {
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      red[(0 * 8 + wrp) * a.C + c0 + k] = s0[k];
+      red[(1 * 8 + wrp) * a.C + c0 + k] = s1[k];
+      red[(2 * 8 + wrp) * a.C + c0 + k] = s2[k];
+    }
   }
   __syncthreads();
   for (int e = tid; e < 3 * a.C; e += 256) {
     const int which = e / a.C, c = e % a.C;
     float sum = 0.f;
-    for (int q = 0; q < RPI; ++q) sum += red[(which * RPI + q) * a.C + c];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) sum += red[(which * 8 + q) * a.C + c];
     atomicAdd(a.acc + (size_t)(blockIdx.x % kBnAccCopies) * 3 * a.C + which * a.C + c, (double)sum);
   }
   // ---- grid-wide barrier ----

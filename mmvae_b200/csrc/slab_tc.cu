@@ -709,16 +709,6 @@ bool slab_supported_gconv(const GConvParams& p) {
   return false;
 }
 
-// Persistent grid of a band kernel: the CTAs walk the slabs round-robin, so the launch lasts ceil(nslabs / grid) rounds.
-// The smallest grid with the same number of rounds as one CTA per SM (256 slabs: 128 CTAs x 2 instead of 148 x 2 | 1) takes
-// no longer and leaves SMs to the other stream and to the early-launched successor (MMVAE_SLAB_FULL_GRID=1: A/B).
-static int slab_grid(int nslabs) {
-  static const bool full = getenv("MMVAE_SLAB_FULL_GRID") != nullptr;
-  if (nslabs <= 148 || full) return min(nslabs, 148);
-  const int rounds = (nslabs + 147) / 148;
-  return (nslabs + rounds - 1) / rounds;
-}
-
 void launch_slab_gconv(const GConvParams& p, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
@@ -737,8 +727,8 @@ void launch_slab_gconv(const GConvParams& p, cudaStream_t st) {
     const int wbytes = 9 * (p.Ci / 8) * 1024;
     slab_geom(q.g, p.N, p.Hi, p.Wi, 2 * (p.Ci / 8), wbytes, 32);
     const size_t smem = 2 * (size_t)(p.Ci / 8) * q.g.plane_bytes + wbytes;
-    if (p.Ci == 16) launch_pdl(slab_fwd_kernel<16>, slab_grid(q.g.nslabs), kFwdThreads, smem, st, q);
-    else launch_pdl(slab_fwd_kernel<32>, slab_grid(q.g.nslabs), kFwdThreads, smem, st, q);
+    if (p.Ci == 16) launch_pdl(slab_fwd_kernel<16>, min(q.g.nslabs, 148), kFwdThreads, smem, st, q);
+    else launch_pdl(slab_fwd_kernel<32>, min(q.g.nslabs, 148), kFwdThreads, smem, st, q);
   } else {
     SlabDgradParams q{};
     q.dy = reinterpret_cast<const __nv_bfloat16*>(p.in); q.dx = reinterpret_cast<__nv_bfloat16*>(p.out); q.w = p.w;
@@ -746,7 +736,7 @@ void launch_slab_gconv(const GConvParams& p, cudaStream_t st) {
     const int wbytes = 16 * 2 * p.Co * 16;
     slab_geom(q.g, p.N, p.Ho, p.Wo, 16, wbytes, 16);
     const size_t smem = 2 * (size_t)8 * q.g.plane_bytes + wbytes;
-    const int grid = slab_grid(q.g.nslabs);
+    const int grid = min(q.g.nslabs, 148);
     if (p.Co == 32) launch_pdl(slab_dgrad_kernel<32, false>, grid, kDgThreads, smem, st, q);
     else if (p.bb.acc) launch_pdl(slab_dgrad_kernel<16, true>, grid, kDgThreads, smem, st, q);
     else launch_pdl(slab_dgrad_kernel<16, false>, grid, kDgThreads, smem, st, q);
@@ -778,8 +768,8 @@ void launch_slab_wgrad(const WGradParams& p, cudaStream_t st) {
   slab_geom(q.g, p.N, p.Hi, p.Wi, total, 0, 8, false);
   const size_t smem = (size_t)total * q.g.plane_bytes;
   count_launch();
-  if (p.Ci == 16) launch_pdl(slab_wgrad_kernel<16>, slab_grid(q.g.nslabs), kWgThreads, smem, st, q);
-  else launch_pdl(slab_wgrad_kernel<32>, slab_grid(q.g.nslabs), kWgThreads, smem, st, q);
+  if (p.Ci == 16) launch_pdl(slab_wgrad_kernel<16>, min(q.g.nslabs, 148), kWgThreads, smem, st, q);
+  else launch_pdl(slab_wgrad_kernel<32>, min(q.g.nslabs, 148), kWgThreads, smem, st, q);
 }
 
 }  // namespace mmvae
