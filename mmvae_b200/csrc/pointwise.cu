@@ -299,6 +299,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
     mean2[k] = a.y2 ? a.stat2[c0 + k] : 0.f; rstd2[k] = a.y2 ? a.stat2[a.C + c0 + k] : 0.f;
   }
   if (active) {
+#pragma unroll 4
     for (long long r = (long long)blockIdx.x * RPI + rsub; r < a.rows; r += (long long)gridDim.x * RPI) {
       size_t off = size_t(r) * a.C + c0;
       float g[VEC], yv[VEC];
@@ -404,6 +405,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a) {
       if (a.y2) { a.g_beta2[c] = a.bcoef2[3 * a.C + c]; a.g_gamma2[c] = a.bcoef2[4 * a.C + c]; }
     }
   }
+#pragma unroll 2
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < nvec; i += gridDim.x * 256LL) {
     const int c0 = (int)((i * VEC) % a.C);
     const size_t off = size_t(i) * VEC;
