@@ -48,6 +48,7 @@ class _VAEForwardFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, module, x, eps, *params):
         mu, logvar, enc, recon, state = module._run_forward(x, eps, training=True)
+        ctx.set_materialize_grads(False)               # unused outputs (encoding) arrive as None, not as a zero-filled tensor
         ctx.module = module
         ctx.state = state
         ctx.save_for_backward(x)
@@ -56,6 +57,8 @@ class _VAEForwardFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_mu, d_logvar, d_enc, d_recon):
         (x,) = ctx.saved_tensors
+        if d_recon is None:                            # a loss without a reconstruction term
+            d_recon = torch.zeros_like(ctx.module._last_recon_like(x))
         grads = ctx.module._run_backward(ctx.state, x, d_mu, d_logvar, d_enc, d_recon)
         return (None, None, None) + grads
 
@@ -69,11 +72,14 @@ class _LossFn(torch.autograd.Function):
         ctx.largs, ctx.ce_weight = largs, ce_weight
         ctx.save_for_backward(recon, target, mu, logvar)
         ctx.mark_non_differentiable(out)
+        ctx.set_materialize_grads(False)               # no zero-filled gradient tensor for the diagnostics output
         return out[0], out
 
     @staticmethod
     def backward(ctx, g_loss, _g_out):
         recon, target, mu, logvar = ctx.saved_tensors
+        if g_loss is None:                             # only the diagnostics output was used
+            return None, None, None, None, None, None, None
         g = g_loss.to(torch.float32).contiguous()
         d_recon = torch.empty_like(recon) if (recon is not None and ctx.needs_input_grad[0]) else None
         need_kl = mu is not None and logvar is not None and (ctx.needs_input_grad[2] or ctx.needs_input_grad[3])
@@ -323,6 +329,11 @@ class VAE(nn.Module):
             rng[1] += (n * z + 3) // 4
         self.last_eps = eps_out if eps_out is not None else eps
         return mu, logvar, enc, recon, (desc, ws, self._gen)
+
+    def _last_recon_like(self, x):
+        """Shape / dtype of the (uncropped) reconstruction the forward Function returned for input x."""
+        return torch.empty(x.shape[0], self.decoder_out_channels, self.input_image_size, self.input_image_size,
+                           dtype=torch.float32, device=x.device)
 
     def _run_backward(self, state, x, d_mu, d_logvar, d_enc, d_recon):
         desc, ws, gen = state
