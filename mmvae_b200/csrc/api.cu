@@ -695,7 +695,8 @@ struct Exec {
         side([&] { wgrad(s); });
         dgrad(s, 0);
       }
-      join();
+      if (phases != MMVAE_BWD_ALL) join();     // a phase on its own hands complete gradients to the caller (all-reduce); the
+                                               // whole sweep in one call joins the auxiliary stream once, at the end
     }
     if (phases & MMVAE_BWD_ENC_DEEP) {
       clear(MMVAE_BWD_ENC_DEEP);
@@ -713,7 +714,7 @@ struct Exec {
       side([&] { launch_heads_wgrad(h.dheads, h.pooled, h.g_wmu, h.w_lv ? h.g_wlv : nullptr, h.N, h.z, h.C, st); });
       block_bwd(P.enc[3]);
       block_bwd(P.enc[2]);
-      join();
+      if (phases != MMVAE_BWD_ALL) join();
     }
     if (phases & MMVAE_BWD_ENC_SHALLOW) {
       clear(MMVAE_BWD_ENC_SHALLOW);
