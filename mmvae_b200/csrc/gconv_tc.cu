@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(kTcThreads, kBwd ? 2 : 3) gconv_tc_kernel(cons
         }
         if (elect_one()) mma_commit(smem_u32(&tfull[buf]));
         __syncwarp();
-        if (i == 0 && lane == 0) { MMVAE_TRACE(p, 5); MMVAE_TRACE(p, 6); }
+        if (i == 0 && lane == 0) MMVAE_TRACE(p, 6);
       }
       if (lane == 0) MMVAE_TRACE(p, 7);
     }

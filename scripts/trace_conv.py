@@ -10,9 +10,8 @@ from mmvae_b200 import data as D
 import types
 
 SLAB_SLOTS = ["entry", "prologue", "pdl_wait", "fill0_issued", "fill0_done", "fill1_done", "m_full0", "m_tile0", "m_slab0", "m_all", "e_tfull0", "e_tile0", "e_all", "dealloc", "bn_fin"]
-SLOTS = ["entry", "prologue", "pdl_wait", "tma0", "tma_all", "full0", "mma_tile0", "mma_all", "tfull0", "epi0", "epi_all",
-         "stats", "dealloc", "bn_fin", "-", "-", "p_decoded", "p_chunk1", "m_commit0", "m_full1", "m_commit1",
-         "k20_full", "k20_mma0", "k20_mma1", "k20_mma2", "k20_mma3", "k20_commit", "k21_full", "k21_commit"]
+SLOTS = ["entry", "prologue", "pdl_wait", "-", "tma_all", "-", "mma_tile0", "mma_all", "tfull0", "epi0", "epi_all",
+         "stats", "dealloc", "bn_fin", "-", "-", "p_decoded"]
 n = int(os.environ.get("N", "256"))
 model = M.VAE(1, 32, decoder_out_channels=1, pixelcnn_out_channels=0, z_dimension=64, pixelcnn=False, only_pixelcnn=False,
               sigma_decoder=0.1, input_image_size=64, precision="bf16").cuda().train()
