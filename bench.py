@@ -504,8 +504,12 @@ def main():
             gstep.x.copy_(x_dev[i % n_batches])                               # device-resident batch -> static input
             return gstep(None)[0]
 
+        gstep_lab.prefetch(labels_host[0])                                    # H2D of the first batch
+
         def step_e2e(i):                                                      # noqa: F811
-            loss = gstep_lab(labels_host[i % n_batches])[0]                   # H2D from pinned memory, then the graph
+            loss = gstep_lab()[0]                                             # staged batch -> static input, then the graph
+            gstep_lab.prefetch(labels_host[(i + 1) % n_batches])              # H2D of the NEXT batch from pinned memory, on a
+                                                                              # copy stream, beside the replay just launched
             reader.push(i, loss)                                              # D2H of the loss into pinned memory, read one step late
 
     for i in range(args.warmup):
@@ -604,7 +608,7 @@ def main():
                          f"{n_batches} rotating input batches"},
         "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": n * 64 * 64, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps,
-                "mode": "per step: H2D of the uint8 label maps from pinned memory, graph replay (normalisation + train step), D2H of "
+                "mode": "per step: H2D of the uint8 label maps from pinned memory (double-buffered on a copy stream: the copy of batch i+1 runs beside step i, GraphedTrainStep.prefetch), graph replay (normalisation + train step), D2H of "
                         "the loss into pinned memory; the host reads each loss one step late (asynchronous logging), all inside the "
                         "timed region"},
         "gpu_launches": int(launches),

@@ -59,6 +59,8 @@ class GraphedTrainStep:
         with torch.cuda.graph(self.graph):
             self._body()
         self.grads = [p.grad for p in model.parameters()]
+        self._copy_stream = None                        # prefetch(): double-buffered H2D beside the running step
+        self._staged = None
 
     def _body(self):
         m = self.model
@@ -74,9 +76,40 @@ class GraphedTrainStep:
         self.mu, self.logvar, self.encoding, self.reconstruction = mu, logvar, enc, recon
         self.loss, self.pxz, self.kl = loss.detach(), pxz, kl
 
+    def prefetch(self, x):
+        """Start the host-to-device copy of the NEXT batch (uint8 label map with `from_labels`, else the fp32 input;
+        pinned host memory) on a copy stream into one of two staging buffers, so that it overlaps the step that is
+        running; the next `step()` call without arguments consumes it (a 1 MB device-to-device copy in front of the replay).
+        The input side of the loop (main.py:374-388) as a double-buffered pipeline."""
+        buf = self.labels if self.labels is not None else self.x
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=buf.device)
+            self._stage = [torch.empty_like(buf) for _ in range(2)]
+            self._ready = [torch.cuda.Event() for _ in range(2)]
+            self._consumed = [None, None]
+            self._slot = 0
+        s = self._slot
+        self._slot ^= 1
+        cs = self._copy_stream
+        if self._consumed[s] is not None:
+            cs.wait_event(self._consumed[s])            # the step that read this staging buffer has copied it out
+        with torch.cuda.stream(cs):
+            self._stage[s].copy_(x, non_blocking=True)
+            self._ready[s].record(cs)
+        self._staged = s
+
     def __call__(self, x=None, target=None):
-        """Copy the batch into the static input (pass None when `self.x` was filled in place) and replay.
+        """Copy the batch into the static input (pass None when `self.x` was filled in place or a batch was staged by
+        `prefetch`) and replay.
         Returns (loss, pxz/N, KL/N) as 0-d device tensors; gradients are in `p.grad` of every parameter."""
+        if x is None and self._staged is not None:
+            s, self._staged = self._staged, None
+            cur = torch.cuda.current_stream()
+            cur.wait_event(self._ready[s])
+            (self.labels if self.labels is not None else self.x).copy_(self._stage[s], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            self._consumed[s] = ev
         if x is not None and self.labels is not None:
             if x.data_ptr() != self.labels.data_ptr():
                 self.labels.copy_(x, non_blocking=True)     # H2D straight into the static buffer when x is pinned host memory

@@ -57,3 +57,28 @@ def test_graphed_step_from_labels():
     assert torch.equal(step.x, want)
     assert torch.isfinite(loss).item()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
+
+
+def test_graphed_step_prefetch_pipeline():
+    """prefetch(): the next batch is copied host-to-device on a copy stream while a step runs; a step() without
+    arguments consumes the staged batch.  Same inputs and inputs order as the direct calls."""
+    from mmvae_b200 import data as D
+    torch.manual_seed(0)
+    m = M.VAE(1, 32, decoder_out_channels=1, pixelcnn_out_channels=0, z_dimension=64, pixelcnn=False, only_pixelcnn=False,
+              sigma_decoder=0.1, input_image_size=64, require_rsample=False).cuda()
+    batches = [D.synthetic_labels(16, 64, seed=100 + b).pin_memory() for b in range(4)]
+    step = M.GraphedTrainStep(m, 16, warmup=1, from_labels=(D.DATA_MEAN, D.DATA_STD))
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    direct = []
+    for b in batches:
+        direct.append(float(step(b)[0]))
+    m.load_state_dict(sd)                               # same BatchNorm running buffers; the losses do not depend on them
+    piped = []
+    step.prefetch(batches[0])
+    for i in range(4):
+        loss = step()[0]
+        if i + 1 < 4:
+            step.prefetch(batches[i + 1])
+        piped.append(float(loss))
+        assert torch.equal(step.labels.cpu(), batches[i])
+    assert piped == direct, (piped, direct)
