@@ -60,3 +60,45 @@ def prepare_input(labels, data_mean=DATA_MEAN, data_std=DATA_STD, want_target=Fa
                                   ctypes.c_void_p(tgt.data_ptr() if tgt is not None else 0),
                                   ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "mmvae_prepare_input")
     return (x, tgt) if want_target else x
+
+
+class Prefetcher:
+    """Double-buffered host-to-device copies on a copy stream (the input side of the loop, main.py:374-380, as a
+    pipeline): `push(host)` starts the copy of the NEXT batch from pinned host memory while the current step runs;
+    `pop()` makes the current stream wait for the staged copy and returns the device tensor.  Two staging buffers:
+    a buffer is refilled only after the step that read it has been enqueued past its last use (`pop` records that
+    point for the buffer handed out by the PREVIOUS pop, i.e. a popped tensor is valid until the next pop)."""
+
+    def __init__(self, device):
+        self.stream = torch.cuda.Stream(device=device)
+        self.slots = [None, None]
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.free = [None, None]
+        self._next = 0
+        self._staged = None
+        self._out = None
+
+    def push(self, host):
+        s = self._next
+        self._next ^= 1
+        if self.slots[s] is None or self.slots[s].shape != host.shape or self.slots[s].dtype != host.dtype:
+            self.slots[s] = torch.empty(host.shape, dtype=host.dtype, device=self.stream.device)
+        if self.free[s] is not None:
+            self.stream.wait_event(self.free[s])
+        with torch.cuda.stream(self.stream):
+            self.slots[s].copy_(host, non_blocking=True)
+            self.ready[s].record(self.stream)
+        self._staged = s
+
+    def pop(self):
+        if self._staged is None:
+            raise RuntimeError("Prefetcher.pop() without a staged batch: call push(host_tensor) first")
+        cur = torch.cuda.current_stream(self.stream.device)
+        if self._out is not None:                        # everything enqueued so far has finished with the previous buffer
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            self.free[self._out] = ev
+        s, self._staged = self._staged, None
+        cur.wait_event(self.ready[s])
+        self._out = s
+        return self.slots[s]

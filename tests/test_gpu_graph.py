@@ -82,3 +82,21 @@ def test_graphed_step_prefetch_pipeline():
         piped.append(float(loss))
         assert torch.equal(step.labels.cpu(), batches[i])
     assert piped == direct, (piped, direct)
+
+
+def test_prefetcher_double_buffer():
+    """mmvae_b200.data.Prefetcher: staged copies arrive in order and a popped tensor stays valid until the next pop."""
+    from mmvae_b200.data import Prefetcher
+    host = [torch.full((1 << 20,), b, dtype=torch.uint8).pin_memory() for b in range(6)]
+    pre = Prefetcher(torch.device("cuda", 0))
+    pre.push(host[0])
+    seen = []
+    for i in range(6):
+        t = pre.pop()
+        s = t.to(torch.float32).sum()                   # work on the current stream that reads the popped buffer
+        if i + 1 < 6:
+            pre.push(host[i + 1])
+        seen.append(float(s) / (1 << 20))
+    assert seen == [float(b) for b in range(6)], seen
+    with pytest.raises(RuntimeError):
+        pre.pop()
