@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define MMVAE_ABI_VERSION 3
+#define MMVAE_ABI_VERSION 4
 
 enum {
   MMVAE_OK = 0,
@@ -110,6 +110,9 @@ typedef struct mmvae_loss_args {
   int32_t channels;         /* C of recon                                                       */
   int32_t height, width;    /* spatial size of recon / target (after the crop)                  */
   int32_t z_dim;            /* elements of mu / logvar per frame                                */
+  int32_t reserved;
+  const float* kl_dev;      /* NULL, or a DEVICE scalar that overrides `kl`: the KL weight can then be
+                             * annealed between replays of a captured CUDA graph                 */
 } mmvae_loss_args;
 
 /* ---- introspection: callable without a GPU --------------------------------------------- */
@@ -163,15 +166,20 @@ int mmvae_nb_loss_backward(const mmvae_desc* d, const float* x, const int64_t* t
 int mmvae_decode(const mmvae_desc* d, const float* encoding, const float* params, float* bn_buffers,
                  int64_t* bn_counters, void* workspace, size_t workspace_bytes, float* recon, void* stream);
 
-/* VAE.loss forward (model.py:385-406, MMD excluded): out[0] = (pxz + kl*KL)/N, out[1] = pxz/N,
- * out[2] = KL/N, all fp32 on the device.  target: fp32 [N,C,H,W] (Gaussian) or int64 [N,H,W]
- * (categorical); ce_weight [C] fp32 or NULL.  mu/logvar may be NULL (KL = 0).
- * scratch: >= mmvae_loss_scratch_bytes() bytes of device memory. */
+/* VAE.loss forward (model.py:385-406; the MMD diagnostic is mmvae_mmd): out[0] = (pxz + kl*KL)/N,
+ * out[1] = pxz/N, out[2] = KL/N, all fp32 on the device.  ONE launch: the reconstruction term and the
+ * KL terms are reduced by the same grid and the CTA that finishes last combines the per-CTA partials in
+ * fp64 in a fixed order.  target: fp32 [N,C,H,W] (Gaussian) or int64 [N,H,W] (categorical; a class
+ * outside [0,C) yields a NaN loss, never an out-of-bounds read); ce_weight [C] fp32 or NULL.
+ * mu/logvar may be NULL (KL = 0).
+ * scratch: >= mmvae_loss_scratch_bytes() bytes of device memory, ZERO before its first use (every call
+ * leaves it zero again). */
 size_t mmvae_loss_scratch_bytes(void);
 int mmvae_loss_forward(const mmvae_loss_args* a, const float* recon, const void* target,
                        const float* ce_weight, const float* mu, const float* logvar,
                        float* out, void* scratch, void* stream);
-/* Gradient of out[0] scaled by the device scalar *grad_out: d_recon [N,C,H,W], d_mu, d_logvar [N,z]. */
+/* Gradient of out[0] scaled by the device scalar *grad_out: d_recon [N,C,H,W], d_mu, d_logvar [N,z]
+ * (ONE launch for all three). */
 int mmvae_loss_backward(const mmvae_loss_args* a, const float* recon, const void* target,
                         const float* ce_weight, const float* mu, const float* logvar,
                         const float* grad_out, float* d_recon, float* d_mu, float* d_logvar, void* stream);
@@ -203,14 +211,29 @@ int mmvae_prepare_input(const uint8_t* labels, int64_t n, float data_mean, float
 int64_t mmvae_launch_count(void);
 
 /* Counter-based standard normals, the generator mmvae_forward uses when eps == NULL:
- * element i = Box-Muller of Philox4x32-10(key = seed, counter = offset + i/4)[i%4 pair]. */
-int mmvae_philox_normal(uint64_t seed, uint64_t offset, int64_t n, float* out, void* stream);
+ * element i = Box-Muller of Philox4x32-10(key = seed ^ stream_id, counter = offset + i/4)[i%4 pair].
+ * rng_state: NULL, or a device {seed, offset} pair overriding the by-value one (as in mmvae_forward);
+ * stream_id = 0 is the rsample stream, any other value an independent stream of the same generator
+ * (VAE.loss draws the MMD diagnostic's true_samples, model.py:395, from stream 1). */
+int mmvae_philox_normal(uint64_t seed, uint64_t offset, const uint64_t* rng_state, uint64_t stream_id,
+                        int64_t n, float* out, void* stream);
 
-/* Fused multi-tensor Adam over the flat arenas (optim.Adam defaults of main.py:468):
- * p -= lr * m_hat / (sqrt(v_hat) + eps), grads pre-scaled by grad_scale (1/world_size for DP). */
+/* The MMD diagnostic VAE.loss returns as its 4th value (model.py:367-383,394-396,406):
+ *   k(a,b) = exp(-mean_d((a_d-b_d)^2)/dim),  mmd = sum k(x,x) + sum k(y,y) - 2 sum k(x,y),  out[0] = mmd / N
+ * with x = true_samples [N,z] and y = encoding [N,z] (fp32, device).  One launch, fp64 combine in a fixed
+ * order.  scratch: >= mmvae_mmd_scratch_bytes(N) bytes, ZERO before its first use. */
+size_t mmvae_mmd_scratch_bytes(int32_t n);
+int mmvae_mmd(const float* true_samples, const float* encoding, int32_t n, int32_t z_dim, float* out,
+              void* scratch, void* stream);
+
+/* Fused multi-tensor Adam over the flat arenas (optim.Adam defaults of main.py:468, optimizer.step()
+ * main.py:399): p -= lr * m_hat / (sqrt(v_hat) + eps), grads pre-scaled by grad_scale
+ * (1/world_size when the gradients were summed, not averaged, over ranks).  `step` is the 1-based step
+ * count; step_dev: NULL, or a device int64 that overrides it (bias corrections computed on the device, so
+ * one captured CUDA graph serves every step -- the host increments *step_dev before each replay). */
 int mmvae_adam_step(int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
                     float lr, float beta1, float beta2, float eps, float weight_decay,
-                    int64_t step, float grad_scale, void* stream);
+                    int64_t step, const int64_t* step_dev, float grad_scale, void* stream);
 
 /* i-th Conv2d / ConvTranspose2d in execution order: name ("encoder.layer1.0.conv1") and
  * shape = {kind (0 conv, 1 transposed), k, stride, padding, Ci, Co, H_in, H_out}. */

@@ -17,7 +17,7 @@ BWD_DECODER, BWD_ENC_DEEP, BWD_ENC_SHALLOW, BWD_ALL = 1, 2, 4, 7
 FLAG_FORCE_SIMT = 1
 FLAG_DEFER_LOGITS = 2
 ARCH_RESNET, ARCH_NOTEBOOK = 0, 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 EXPORTS = [
     "mmvae_abi_version", "mmvae_last_error", "mmvae_layout", "mmvae_param_entry", "mmvae_bn_entry",
@@ -25,7 +25,7 @@ EXPORTS = [
     "mmvae_loss_forward", "mmvae_loss_backward", "mmvae_backward", "mmvae_backward_range",
     "mmvae_philox_normal", "mmvae_adam_step", "mmvae_prepare_input", "mmvae_launch_count",
     "mmvae_conv_entry", "mmvae_selftest_tc", "mmvae_bench_conv", "mmvae_debug_set_trace",
-    "mmvae_nb_loss_backward", "mmvae_nb_bench_tail",
+    "mmvae_nb_loss_backward", "mmvae_nb_bench_tail", "mmvae_mmd", "mmvae_mmd_scratch_bytes",
 ]
 
 
@@ -45,7 +45,7 @@ class LayoutInfo(Structure):
 class LossArgs(Structure):
     _fields_ = [("struct_size", c_int32), ("kind", c_int32), ("nll", c_float), ("kl", c_float),
                 ("sigma", c_float), ("batch", c_int32), ("channels", c_int32), ("height", c_int32),
-                ("width", c_int32), ("z_dim", c_int32)]
+                ("width", c_int32), ("z_dim", c_int32), ("reserved", c_int32), ("kl_dev", c_void_p)]
 
 
 class MMVAEError(RuntimeError):
@@ -75,16 +75,20 @@ def _load():
     lib.mmvae_nb_loss_backward.argtypes = [POINTER(Desc), P, P, P, P, c_size_t, c_float, P, P, P]
     lib.mmvae_nb_bench_tail.argtypes = [POINTER(Desc), c_int32, P, P, P, c_size_t, P, POINTER(c_int64), POINTER(c_int64), P]
     lib.mmvae_backward_range.argtypes = [POINTER(Desc), c_int32, POINTER(c_int64), POINTER(c_int64)]
-    lib.mmvae_philox_normal.argtypes = [c_uint64, c_uint64, c_int64, P, P]
+    lib.mmvae_philox_normal.argtypes = [c_uint64, c_uint64, P, c_uint64, c_int64, P, P]
     lib.mmvae_adam_step.argtypes = [c_int64, P, P, P, P, c_float, c_float, c_float, c_float, c_float, c_int64,
-                                    c_float, P]
+                                    P, c_float, P]
+    lib.mmvae_mmd_scratch_bytes.argtypes = [c_int32]
+    lib.mmvae_mmd_scratch_bytes.restype = c_size_t
+    lib.mmvae_mmd.argtypes = [P, P, c_int32, c_int32, P, P, P]
     lib.mmvae_prepare_input.argtypes = [P, c_int64, c_float, c_float, P, P, P]
     lib.mmvae_conv_entry.argtypes = [POINTER(Desc), c_int32, c_char_p, c_size_t, POINTER(c_int32 * 8)]
     lib.mmvae_selftest_tc.argtypes = [POINTER(Desc), P, P, c_size_t, P, P, P, c_int32, P]
     lib.mmvae_bench_conv.argtypes = [POINTER(Desc), c_int32, c_int32, P, P, c_size_t, P, POINTER(c_int64), POINTER(c_int64), P]
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name not in ("mmvae_last_error", "mmvae_loss_scratch_bytes", "mmvae_launch_count", "mmvae_debug_set_trace"):
+        if name not in ("mmvae_last_error", "mmvae_loss_scratch_bytes", "mmvae_launch_count", "mmvae_debug_set_trace",
+                        "mmvae_mmd_scratch_bytes"):
             fn.restype = c_int32
     lib.mmvae_launch_count.restype = c_int64
     lib.mmvae_debug_set_trace.argtypes = [P]

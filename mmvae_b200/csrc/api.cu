@@ -1010,7 +1010,7 @@ int mmvae_loss_forward(const mmvae_loss_args* a, const float* recon, const void*
   if (!out || !scratch) return fail(MMVAE_ERR_BAD_ARG, "out/scratch must be non-NULL");
   if ((recon == nullptr) != (target == nullptr)) return fail(MMVAE_ERR_BAD_ARG, "recon and target must both be given or both be NULL (KL only)");
   if (!aligned16(recon) || !aligned16(target)) return fail(MMVAE_ERR_BAD_ARG, "recon and target must be 16-byte aligned");
-  launch_loss_fwd(L, recon, target, ce_weight, mu, logvar, out, scratch, reinterpret_cast<cudaStream_t>(stream));
+  launch_loss_fwd(L, recon, target, ce_weight, mu, logvar, a->kl_dev, out, scratch, reinterpret_cast<cudaStream_t>(stream));
   return check_launches("mmvae_loss_forward");
 }
 
@@ -1024,7 +1024,7 @@ int mmvae_loss_backward(const mmvae_loss_args* a, const float* recon, const void
   if (d_recon && (!recon || !target)) return fail(MMVAE_ERR_BAD_ARG, "d_recon needs recon and target");
   if (!aligned16(recon) || !aligned16(target) || (d_recon && !aligned16(d_recon)))
     return fail(MMVAE_ERR_BAD_ARG, "recon, target and d_recon must be 16-byte aligned");
-  launch_loss_bwd(L, recon, target, ce_weight, mu, logvar, grad_out, d_recon, d_mu, d_logvar,
+  launch_loss_bwd(L, recon, target, ce_weight, mu, logvar, grad_out, a->kl_dev, d_recon, d_mu, d_logvar,
                   reinterpret_cast<cudaStream_t>(stream));
   return check_launches("mmvae_loss_backward");
 }
@@ -1036,24 +1036,38 @@ int mmvae_prepare_input(const uint8_t* labels, int64_t n, float data_mean, float
                         void* stream) {
   if (int rc = check_device()) return rc;
   if (!labels || !x || n < 0 || !(data_std > 0.f)) return fail(MMVAE_ERR_BAD_ARG, "bad arguments");
-  launch_prepare_input(labels, n, data_mean, 1.0f / data_std, x, (long long*)target, reinterpret_cast<cudaStream_t>(stream));
+  launch_prepare_input(labels, n, data_mean, data_std, x, (long long*)target, reinterpret_cast<cudaStream_t>(stream));
   return check_launches("mmvae_prepare_input");
 }
 
-int mmvae_philox_normal(uint64_t seed, uint64_t offset, int64_t n, float* out, void* stream) {
+int mmvae_philox_normal(uint64_t seed, uint64_t offset, const uint64_t* rng_state, uint64_t stream_id, int64_t n,
+                        float* out, void* stream) {
   if (int rc = check_device()) return rc;
   if (!out || n < 0) return fail(MMVAE_ERR_BAD_ARG, "bad arguments");
-  launch_philox_normal(seed, offset, n, out, reinterpret_cast<cudaStream_t>(stream));
+  launch_philox_normal(seed, offset, reinterpret_cast<const unsigned long long*>(rng_state), stream_id, n, out,
+                       reinterpret_cast<cudaStream_t>(stream));
   return check_launches("mmvae_philox_normal");
 }
 
-int mmvae_adam_step(int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float lr,
-                    float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
-                    void* stream) {
+size_t mmvae_mmd_scratch_bytes(int32_t n) { return mmd_scratch_bytes(n > 0 ? n : 1); }
+
+int mmvae_mmd(const float* true_samples, const float* encoding, int32_t n, int32_t z_dim, float* out, void* scratch,
+              void* stream) {
   if (int rc = check_device()) return rc;
-  if (!params || !grads || !exp_avg || !exp_avg_sq || n < 0 || step < 1) return fail(MMVAE_ERR_BAD_ARG, "bad arguments");
-  launch_adam(n, params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale,
-              reinterpret_cast<cudaStream_t>(stream));
+  if (!true_samples || !encoding || !out || !scratch || n < 1 || z_dim < 1 || z_dim > 8192)
+    return fail(MMVAE_ERR_BAD_ARG, "mmvae_mmd: bad arguments");
+  launch_mmd(true_samples, encoding, n, z_dim, out, scratch, reinterpret_cast<cudaStream_t>(stream));
+  return check_launches("mmvae_mmd");
+}
+
+int mmvae_adam_step(int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float lr,
+                    float beta1, float beta2, float eps, float weight_decay, int64_t step, const int64_t* step_dev,
+                    float grad_scale, void* stream) {
+  if (int rc = check_device()) return rc;
+  if (!params || !grads || !exp_avg || !exp_avg_sq || n < 0 || (!step_dev && step < 1))
+    return fail(MMVAE_ERR_BAD_ARG, "bad arguments");
+  launch_adam(n, params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step > 0 ? step : 1,
+              reinterpret_cast<const long long*>(step_dev), grad_scale, reinterpret_cast<cudaStream_t>(stream));
   return check_launches("mmvae_adam_step");
 }
 

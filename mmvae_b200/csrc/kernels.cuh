@@ -336,17 +336,22 @@ struct LossArgs {
   int kind; float nll, kl, sigma; int N, C, H, W, z;
 };
 size_t loss_scratch_bytes();
+// kl_dev: device scalar overriding a.kl (KL annealing inside a captured graph) or nullptr
 void launch_loss_fwd(const LossArgs& a, const float* recon, const void* target, const float* w,
-                     const float* mu, const float* lv, float* out, void* scratch, cudaStream_t st);
+                     const float* mu, const float* lv, const float* kl_dev, float* out, void* scratch, cudaStream_t st);
 void launch_loss_bwd(const LossArgs& a, const float* recon, const void* target, const float* w,
-                     const float* mu, const float* lv, const float* gout,
+                     const float* mu, const float* lv, const float* gout, const float* kl_dev,
                      float* d_recon, float* d_mu, float* d_lv, cudaStream_t st);
+// MMD diagnostic of model.py:367-383 (x = true_samples, y = encoding, both [N][z] fp32): out[0] = mmd / N
+size_t mmd_scratch_bytes(int N);
+void launch_mmd(const float* x, const float* y, int N, int z, float* out, void* scratch, cudaStream_t st);
 // k-means label map (uint8) -> normalised fp32 network input (+ int64 CE target)   main.py:381-388
-void launch_prepare_input(const unsigned char* labels, long long n, float mean, float inv_std, float* x,
+void launch_prepare_input(const unsigned char* labels, long long n, float mean, float std, float* x,
                           long long* target, cudaStream_t st);
-void launch_philox_normal(unsigned long long seed, unsigned long long offset, long long n, float* out, cudaStream_t st);
+void launch_philox_normal(unsigned long long seed, unsigned long long offset, const unsigned long long* rng_dev,
+                          unsigned long long stream_id, long long n, float* out, cudaStream_t st);
 void launch_adam(long long n, float* p, const float* g, float* m, float* v, float lr, float b1, float b2,
-                 float eps, float wd, long long step, float gscale, cudaStream_t st);
+                 float eps, float wd, long long step, const long long* step_dev, float gscale, cudaStream_t st);
 
 // ---- notebook-variant VAE: BatchNorm-free pointwise / loss kernels (nb.cu) ----
 // nearest-neighbour upsample by f: out[n, f*h+a, f*w+b, c] = in[n,h,w,c]            (vae-kl.ipynb:152-155)

@@ -668,6 +668,23 @@ void launch_heads_bwd(const HeadsBwdArgs& a, cudaStream_t st) {
   // the weight gradients of the two heads are a separate launch (launch_heads_wgrad): the caller decides the stream
 }
 
+// co-resident CTAs of bn_bwd_coop_kernel on the current device (cached per device)
+static int coop_max_ctas() {
+  static std::atomic<int> cached[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  int v = cached[dev].load();
+  if (v > 0) return v;
+  int per_sm = 0, sms = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_bwd_coop_kernel, 256, 0) != cudaSuccess ||
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+  v = std::min(per_sm, 2) * sms;
+  static const int cap = [] { const char* e = getenv("MMVAE_COOP_CTAS"); return e ? atoi(e) : 0; }();   // A/B runs
+  if (cap > 0) v = std::min(v, cap);
+  cached[dev].store(v);
+  return v;
+}
+
 template <typename T>
 void launch_bn_bwd(const BnBwdArgs& a, cudaStream_t st) {
   constexpr int V = vec_of<T>();
@@ -682,9 +699,10 @@ void launch_bn_bwd(const BnBwdArgs& a, cudaStream_t st) {
       // up to two CTAs per SM (__launch_bounds__(256, 2), 34 KB of shared memory each): tensors up to 4.8 MB.  Whatever
       // else occupies the SMs finishes without waiting for this stream, and a programmatic dependent of this launch is
       // not scheduled before every CTA here has started, so all CTAs reach the grid barrier.  MMVAE_COOP_CTAS: A/B.
-      static const int coop_ctas = [] { const char* e = getenv("MMVAE_COOP_CTAS"); return e ? atoi(e) : 296; }();
-      const int grid = (int)std::min<long long>(coop_ctas, row_groups);
-      const int E = (int)((row_groups + grid - 1) / grid);
+      // The grid never exceeds what the device can hold at once (occupancy x SM count, queried per device): on a part with
+      // fewer SMs, or where only one CTA fits, a larger grid would leave CTAs unscheduled and the resident ones spinning.
+      const int grid = (int)std::min<long long>(coop_max_ctas(), row_groups);
+      const int E = grid > 0 ? (int)((row_groups + grid - 1) / grid) : kCoopE + 1;
       if (E <= kCoopE) {
         count_launch();
         launch_pdl(bn_bwd_coop_kernel, grid, 256, 0, st, a, E);

@@ -40,8 +40,9 @@ def _ptr(t):
     return c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
 
 
-def _stream():
-    return c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(dev=None):
+    """The current stream of the device the tensors live on (not of whatever device happens to be current)."""
+    return c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
 class _VAEForwardFn(torch.autograd.Function):
@@ -57,8 +58,8 @@ class _VAEForwardFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_mu, d_logvar, d_enc, d_recon):
         (x,) = ctx.saved_tensors
-        if d_recon is None:                            # a loss without a reconstruction term
-            d_recon = torch.zeros_like(ctx.module._last_recon_like(x))
+        # d_recon None (a loss without a reconstruction term, e.g. kl_divergence(mu, logvar).backward()) goes through
+        # as NULL: the C ABI treats it as zero and skips the decoder sweep
         grads = ctx.module._run_backward(ctx.state, x, d_mu, d_logvar, d_enc, d_recon)
         return (None, None, None) + grads
 
@@ -66,9 +67,11 @@ class _VAEForwardFn(torch.autograd.Function):
 class _LossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, recon, target, mu, logvar, largs, ce_weight, scratch):
-        out = torch.empty(3, dtype=torch.float32, device=mu.device if recon is None else recon.device)
-        check(lib.mmvae_loss_forward(byref(largs), _ptr(recon), _ptr(target), _ptr(ce_weight), _ptr(mu),
-                                     _ptr(logvar), _ptr(out), _ptr(scratch), _stream()), "mmvae_loss_forward")
+        dev = mu.device if recon is None else recon.device
+        out = torch.empty(4, dtype=torch.float32, device=dev)          # loss, pxz/N, KL/N, MMD/N (filled by VAE.loss)
+        with torch.cuda.device(dev):
+            check(lib.mmvae_loss_forward(byref(largs), _ptr(recon), _ptr(target), _ptr(ce_weight), _ptr(mu),
+                                         _ptr(logvar), _ptr(out), _ptr(scratch), _stream(dev)), "mmvae_loss_forward")
         ctx.largs, ctx.ce_weight = largs, ce_weight
         ctx.save_for_backward(recon, target, mu, logvar)
         ctx.mark_non_differentiable(out)
@@ -85,9 +88,11 @@ class _LossFn(torch.autograd.Function):
         need_kl = mu is not None and logvar is not None and (ctx.needs_input_grad[2] or ctx.needs_input_grad[3])
         d_mu = torch.empty_like(mu) if need_kl else None
         d_lv = torch.empty_like(logvar) if need_kl else None
-        check(lib.mmvae_loss_backward(byref(ctx.largs), _ptr(recon), _ptr(target), _ptr(ctx.ce_weight), _ptr(mu),
-                                      _ptr(logvar), _ptr(g), _ptr(d_recon), _ptr(d_mu), _ptr(d_lv), _stream()),
-              "mmvae_loss_backward")
+        dev = g.device
+        with torch.cuda.device(dev):
+            check(lib.mmvae_loss_backward(byref(ctx.largs), _ptr(recon), _ptr(target), _ptr(ctx.ce_weight), _ptr(mu),
+                                          _ptr(logvar), _ptr(g), _ptr(d_recon), _ptr(d_mu), _ptr(d_lv), _stream(dev)),
+                  "mmvae_loss_backward")
         return d_recon, None, d_mu, d_lv, None, None, None
 
 
@@ -157,6 +162,12 @@ class VAE(nn.Module):
         self._rng_dev = None          # int64[2] device tensor {seed, offset} while a GraphedTrainStep owns the noise
         self.last_eps = None
         self._loss_scratch = None
+        self._mmd_scratch = None
+        self._side = None             # torch side stream of the MMD diagnostic
+        self._kl_dev = None           # device scalar holding the KL weight while a GraphedTrainStep owns it (annealing)
+        self.mmd_diagnostic = True    # compute the 4th return value of loss() like the reference (model.py:394-396)
+        self.last_true_samples = None
+        self._mmd_calls = 0
         self._grad_sync = None        # set by mmvae_b200.parallel.DataParallel
         self.defer_metrics = False    # True: loss() returns 0-d device tensors instead of 3 host floats
 
@@ -257,6 +268,8 @@ class VAE(nn.Module):
         self._arena, self._bn_arena, self._counters = arena, bn_arena, counters
         self._ws = {}
         self._loss_scratch = None
+        self._mmd_scratch = None
+        self._side = None
 
     def _check_arena(self):
         base = self._arena.data_ptr()
@@ -322,24 +335,28 @@ class VAE(nn.Module):
                 if eps.numel() != n * z:
                     raise ValueError("eps must have N*z elements")
         self._gen += 1
-        check(lib.mmvae_forward(byref(desc), _ptr(x), _ptr(self._arena), _ptr(self._bn_arena), _ptr(self._counters),
-                                _ptr(eps), seed, offset, _ptr(eps_out), _ptr(rng), _ptr(ws), ws.numel(), _ptr(mu),
-                                _ptr(logvar), _ptr(enc), _ptr(recon), _stream()), "mmvae_forward")
-        if rng is not None:
-            rng[1] += (n * z + 3) // 4
+        with torch.cuda.device(dev):
+            check(lib.mmvae_forward(byref(desc), _ptr(x), _ptr(self._arena), _ptr(self._bn_arena), _ptr(self._counters),
+                                    _ptr(eps), seed, offset, _ptr(eps_out), _ptr(rng), _ptr(ws), ws.numel(), _ptr(mu),
+                                    _ptr(logvar), _ptr(enc), _ptr(recon), _stream(dev)), "mmvae_forward")
+            if rng is not None:
+                rng[1] += (n * z + 3) // 4
         self.last_eps = eps_out if eps_out is not None else eps
-        return mu, logvar, enc, recon, (desc, ws, self._gen)
-
-    def _last_recon_like(self, x):
-        """Shape / dtype of the (uncropped) reconstruction the forward Function returned for input x."""
-        return torch.empty(x.shape[0], self.decoder_out_channels, self.input_image_size, self.input_image_size,
-                           dtype=torch.float32, device=x.device)
+        return mu, logvar, enc, recon, [desc, ws, self._gen, False]
 
     def _run_backward(self, state, x, d_mu, d_logvar, d_enc, d_recon):
-        desc, ws, gen = state
+        desc, ws, gen, consumed = state
         if gen != self._gen:
             raise RuntimeError("the activation workspace was overwritten by a later forward(); "
                                "call backward() before the next forward() of the same module")
+        if consumed:
+            # the BatchNorm-backward accumulators / CTA counters in the workspace are zeroed by the forward only: a second
+            # sweep would double-accumulate
+            raise RuntimeError("mmvae_b200.VAE: backward() through the same forward() twice (retain_graph) is not "
+                               "supported; run forward() again")
+        state[3] = True
+        if d_recon is not None and tuple(d_recon.shape[-2:]) != (self._decoder_size, self._decoder_size):
+            raise RuntimeError("d_recon must be the gradient of the uncropped reconstruction")
 
         def prep(t):
             return None if t is None else t.to(torch.float32).contiguous()
@@ -349,9 +366,10 @@ class VAE(nn.Module):
         sync = self._grad_sync
         phases = (_lib.BWD_ALL,) if sync is None else (_lib.BWD_DECODER, _lib.BWD_ENC_DEEP, _lib.BWD_ENC_SHALLOW)
         for ph in phases:
-            check(lib.mmvae_backward(byref(desc), _ptr(x), _ptr(self._arena), _ptr(ws), ws.numel(), _ptr(d_mu),
-                                     _ptr(d_logvar), _ptr(d_enc), _ptr(d_recon), _ptr(grads), ph, _stream()),
-                  "mmvae_backward")
+            with torch.cuda.device(x.device):
+                check(lib.mmvae_backward(byref(desc), _ptr(x), _ptr(self._arena), _ptr(ws), ws.numel(), _ptr(d_mu),
+                                         _ptr(d_logvar), _ptr(d_enc), _ptr(d_recon), _ptr(grads), ph, _stream(x.device)),
+                      "mmvae_backward")
             if sync is not None:
                 sync.phase_done(self, desc, grads, ph)
         if sync is not None:
@@ -387,8 +405,9 @@ class VAE(nn.Module):
         d = self._decoder_size
         recon = torch.empty(n, self.decoder_out_channels, d, d, dtype=torch.float32, device=e.device)
         self._gen += 1
-        check(lib.mmvae_decode(byref(desc), _ptr(e), _ptr(self._arena), _ptr(self._bn_arena), _ptr(self._counters),
-                               _ptr(ws), ws.numel(), _ptr(recon), _stream()), "mmvae_decode")
+        with torch.cuda.device(e.device):
+            check(lib.mmvae_decode(byref(desc), _ptr(e), _ptr(self._arena), _ptr(self._bn_arena), _ptr(self._counters),
+                                   _ptr(ws), ws.numel(), _ptr(recon), _stream(e.device)), "mmvae_decode")
         if self.adjust != 0:
             a = self.adjust
             recon = recon[:, :, a:-a, a:-a]
@@ -403,44 +422,105 @@ class VAE(nn.Module):
         return self._decode(encoding)
 
     # ------------------------------------------------------------------ loss
-    def _loss_args(self, n, c, h, w, nz, kl, nll):
+    def _loss_args(self, n, c, h, w, nz, kl, nll, kl_dev=None):
         a = _lib.LossArgs()
         a.struct_size = ctypes.sizeof(_lib.LossArgs)
         a.kind = _lib.LOSS_CATEGORICAL if self.decoder_out_channels > self.in_channels else _lib.LOSS_GAUSSIAN
         a.nll, a.kl, a.sigma = float(nll), float(kl), float(self.sigma_decoder)
         a.batch, a.channels, a.height, a.width, a.z_dim = n, c, h, w, nz
+        a.kl_dev = kl_dev.data_ptr() if kl_dev is not None else None
         return a
 
     def _scratch(self, dev):
         if self._loss_scratch is None or self._loss_scratch.device != dev:
-            self._loss_scratch = torch.empty(lib.mmvae_loss_scratch_bytes(), dtype=torch.uint8, device=dev)
+            # zero before its first use: it holds the CTA-done counter, which every call leaves at zero again
+            self._loss_scratch = torch.zeros(lib.mmvae_loss_scratch_bytes(), dtype=torch.uint8, device=dev)
         return self._loss_scratch
+
+    def compute_mmd(self, true_samples, encoding, out=None):
+        """model.py:367-383 divided by N as `loss` returns it (model.py:406): sum k(x,x) + sum k(y,y) - 2 sum k(x,y)
+        with k(a,b) = exp(-mean((a-b)^2)/dim), as a 0-d device tensor.  One kernel (mmvae_mmd)."""
+        self._require_cuda(encoding)
+        dev = encoding.device
+        y = encoding.detach().to(torch.float32).reshape(encoding.shape[0], -1).contiguous()
+        x = true_samples.to(device=dev, dtype=torch.float32).contiguous()
+        if x.shape != y.shape:
+            raise ValueError(f"true_samples {tuple(x.shape)} and encoding {tuple(y.shape)} differ in shape")
+        n, z = y.shape
+        need = lib.mmvae_mmd_scratch_bytes(n)
+        if self._mmd_scratch is None or self._mmd_scratch.device != dev or self._mmd_scratch.numel() < need:
+            self._mmd_scratch = torch.zeros(need, dtype=torch.uint8, device=dev)
+        if out is None:
+            out = torch.empty((), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.mmvae_mmd(_ptr(x), _ptr(y), n, z, _ptr(out), _ptr(self._mmd_scratch), _stream(dev)), "mmvae_mmd")
+        return out
+
+    def _mmd_side(self, encoding, true_samples, out):
+        """The MMD diagnostic on a side stream, beside the loss kernel (it has coefficient 0 in every supported model,
+        so nothing waits for it except the read of the value).  true_samples default to a Philox draw (stream 1 of the
+        module's generator; the reference draws torch.randn on the host, model.py:395) kept in `last_true_samples`."""
+        dev = encoding.device
+        n, z = encoding.shape[0], encoding.numel() // encoding.shape[0]
+        cur = torch.cuda.current_stream(dev)
+        if true_samples is None:
+            ts = torch.empty(n, z, dtype=torch.float32, device=dev)
+        else:
+            ts = true_samples.to(device=dev, dtype=torch.float32).contiguous()
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=dev)
+        side = self._side
+        side.wait_stream(cur)
+        with torch.cuda.stream(side), torch.cuda.device(dev):
+            if true_samples is None:
+                if self._philox_seed is None:
+                    self._philox_seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
+                # counter range disjoint from call to call; with a device-resident rng state (graph replays) the offset of
+                # the rsample stream, which advances every replay, is used instead
+                off = (1 << 62) + self._mmd_calls * ((n * z + 3) // 4)
+                self._mmd_calls += 1
+                check(lib.mmvae_philox_normal(self._philox_seed, off, _ptr(self._rng_dev), 1, n * z, _ptr(ts),
+                                              _stream(dev)), "mmvae_philox_normal")
+            self.compute_mmd(ts, encoding, out=out)
+        cur.wait_stream(side)
+        self.last_true_samples = ts
 
     def kl_divergence(self, encoding_mu, encoding_logvar):
         """model.py:364-365: -0.5 * sum(logvar - exp(logvar) - mu^2 + 1)."""
         self._require_cuda(encoding_mu)
         mu = encoding_mu.to(torch.float32).contiguous()
         lv = encoding_logvar.to(torch.float32).contiguous()
+        if lv.numel() != mu.numel():
+            raise ValueError("mu and logvar differ in size")
         a = self._loss_args(1, 1, 1, 1, mu.numel(), 1.0, 0.0)
         a.kind = _lib.LOSS_GAUSSIAN
         a.sigma = 1.0
         kl, _ = _LossFn.apply(None, None, mu, lv, a, None, self._scratch(mu.device))
         return kl            # (0 + 1*KL)/1, with a grad_fn
 
-    def loss(self, target, encoding_mu, encoding_logvar, encoding, reconstruction, device, args, kl_weight=None):
+    def loss(self, target, encoding_mu, encoding_logvar, encoding, reconstruction, device, args, kl_weight=None,
+             true_samples=None):
         """model.py:385-406.  `kl_weight` (optional) overrides the constructor's KL coefficient for this call
         (annealing).  Returns (loss, pxz/N, KL/N, MMD/N); the last three are host floats like the reference's
         `.item()` calls (one device sync), or 0-d device tensors when `self.defer_metrics`.
-        The MMD diagnostic (coefficient 0 in every supported model) is reported as 0."""
+        The MMD diagnostic (model.py:394-396; coefficient 0 in every supported model, so it is outside the loss and
+        its gradient) is computed from `true_samples` ([N, z]; default: a Philox draw kept in `last_true_samples`)
+        when `encoding` is not None and `self.mmd_diagnostic`; otherwise it is 0 as in the reference."""
         self._require_cuda(reconstruction)
         recon = reconstruction.to(torch.float32).contiguous()
         n, c, h, w = recon.shape
         categorical = self.decoder_out_channels > self.in_channels
+        if target.shape[0] != n:
+            raise ValueError(f"target has {target.shape[0]} frames, reconstruction {n}")
         if categorical:
             tgt = target.to(device=recon.device, dtype=torch.int64).contiguous()
+            if tgt.numel() != n * h * w:
+                raise ValueError(f"categorical target must have N*H*W = {n * h * w} class indices, got {tuple(target.shape)}")
             cew = getattr(args, "data_ratio_of_labels", None)
             if cew is not None:
                 cew = cew.to(device=recon.device, dtype=torch.float32).contiguous()
+                if cew.numel() != c:
+                    raise ValueError(f"data_ratio_of_labels must have {c} entries")
         else:
             tgt = target.to(device=recon.device, dtype=torch.float32).contiguous()
             if tgt.numel() != recon.numel():
@@ -452,12 +532,17 @@ class VAE(nn.Module):
             mu = encoding_mu.to(torch.float32).contiguous()
             lv = encoding_logvar.to(torch.float32).contiguous()
             nz = mu.numel() // n
-        a = self._loss_args(n, c, h, w, nz, self.kl if kl_weight is None else kl_weight, self.nll)
+        kl_dev = self._kl_dev if kl_weight is None else None
+        a = self._loss_args(n, c, h, w, nz, self.kl if kl_weight is None else kl_weight, self.nll, kl_dev)
         loss, out = _LossFn.apply(recon, tgt, mu, lv, a, cew, self._scratch(recon.device))
+        if encoding is not None and self.mmd_diagnostic:                   # model.py:394-396
+            self._mmd_side(encoding, true_samples, out[3])
+        else:
+            out[3] = 0.0
         if self.defer_metrics:
-            return loss, out[1], out[2], torch.zeros((), device=recon.device)
+            return loss, out[1], out[2], out[3]
         vals = out.tolist()
-        return loss, vals[1], vals[2], 0.0
+        return loss, vals[1], vals[2], vals[3]
 
     def __repr__(self):
         kind = "categorical" if self.decoder_out_channels > self.in_channels else f"normal(sigma={self.sigma_decoder})"

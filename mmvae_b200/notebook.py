@@ -136,6 +136,8 @@ class NotebookVAE(nn.Module):
     def flat_grads(self):
         return self._grads
 
+    last_flat_grad = flat_grads                          # the name mmvae_b200.FusedAdam looks for
+
     def load_pair(self, encoder_state, decoder_state):
         """load the notebook's two state dicts (``encoder.state_dict()``, ``decoder.state_dict()``)"""
         st = {"encoder." + k: v for k, v in encoder_state.items()}

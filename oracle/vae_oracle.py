@@ -197,6 +197,18 @@ class _RoundBF16(torch.autograd.Function):
         return g.to(torch.bfloat16).to(g.dtype)
 
 
+class _RoundGradBF16(torch.autograd.Function):
+    """Identity on the way forward, bf16 rounding of the gradient on the way back (gradient storage only)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(g.dtype)
+
+
 class _RoundBF16Operand(torch.autograd.Function):
     """A tensor-core operand that is kept in fp32 in HBM (a weight): bf16 on the way into the product,
     gradient left in fp32 (the CUDA path accumulates dW in fp32)."""
@@ -210,30 +222,57 @@ class _RoundBF16Operand(torch.autograd.Function):
         return g
 
 
+# the 1-channel ends of the network run as fp32 SIMT kernels on fp32 weights in the CUDA bf16 mode
+FP32_OPERANDS = ("encoder.conv1.weight", "decoder.conv2.weight")
+
+
 class _Ctx:
     """Carries the state dict, the training flag and the BN side effects."""
 
-    def __init__(self, st, training: bool, keep: bool, emulate_bf16: bool = False):
+    def __init__(self, st, training: bool, keep: bool, emulate_bf16: bool = False, relu_masks=None, forced_acts=None,
+                 emulate_bf16_grads: bool = False):
         self.st = st
         self.training = training
         self.keep = keep
         self.emulate_bf16 = emulate_bf16
+        self.relu_masks = relu_masks
+        self.forced_acts = forced_acts
+        self.emulate_bf16_grads = emulate_bf16_grads      # with forced_acts: round the gradient at every store point
         self.native_bn = False
         self.new_buffers: Dict[str, torch.Tensor] = {}
         self.acts: Dict[str, torch.Tensor] = {}
 
-    def store(self, t: torch.Tensor) -> torch.Tensor:
-        """A tensor the CUDA path materialises in HBM in its storage type."""
+    def store(self, t: torch.Tensor, name: Optional[str] = None) -> torch.Tensor:
+        """A tensor the CUDA path materialises in HBM in its storage type.
+        ``forced_acts`` (name -> tensor read back from ANOTHER evaluation's workspace) replaces the forward VALUE
+        by that evaluation's stored one while keeping this graph's derivative: the backward pass then runs, in
+        this evaluation's arithmetic, on exactly the forward the other evaluation saw -- a referee for a bf16
+        implementation's backward kernels that its forward rounding (ReLU gates, statistics) cannot blur."""
+        if self.forced_acts is not None and name is not None and name in self.forced_acts:
+            t = t + (self.forced_acts[name].to(t.dtype) - t).detach()
+            return _RoundGradBF16.apply(t) if self.emulate_bf16_grads else t
         return _RoundBF16.apply(t) if self.emulate_bf16 else t
 
     def w(self, name: str) -> torch.Tensor:
         """A conv / transposed-conv weight as the tensor cores see it (bf16 operand in the bf16 mode)."""
         t = self.st[name]
-        return _RoundBF16Operand.apply(t) if self.emulate_bf16 else t
+        if name in FP32_OPERANDS:
+            return t
+        return _RoundBF16Operand.apply(t) if (self.emulate_bf16 or self.forced_acts is not None) else t
 
     def save(self, name: str, t: torch.Tensor):
         if self.keep:
             self.acts[name] = t
+
+    def relu(self, name: str, t: torch.Tensor) -> torch.Tensor:
+        """ReLU (model.py:44,53,75,83,117,184).  With ``relu_masks`` (name -> bool tensor, the sign pattern of
+        ANOTHER evaluation's stored activation) the gate is frozen to that pattern: t * mask.  Used to referee
+        a bf16 implementation's backward pass at 1e-2: rounding activations to bf16 flips ~1 % of the gates,
+        and a flipped gate changes its gradient entry by O(1); with the gates pinned, what is left is the
+        arithmetic of the implementation itself."""
+        if self.relu_masks is not None and name in self.relu_masks:
+            return t * self.relu_masks[name].to(t.dtype)
+        return torch.relu(t)
 
 
 def _batchnorm(ctx: _Ctx, y: torch.Tensor, prefix: str) -> torch.Tensor:
@@ -264,14 +303,15 @@ def _batchnorm(ctx: _Ctx, y: torch.Tensor, prefix: str) -> torch.Tensor:
 def _basic_block(ctx: _Ctx, x: torch.Tensor, p: str) -> torch.Tensor:
     """model.py:39-55 with the 1x1 stride-2 shortcut of model.py:132-138."""
     st = ctx.st
-    y1 = ctx.store(F.conv2d(x, ctx.w(p + ".conv1.weight"), stride=2, padding=1))
+    y1 = ctx.store(F.conv2d(x, ctx.w(p + ".conv1.weight"), stride=2, padding=1), p + ".conv1")
     ctx.save(p + ".conv1", y1)
-    a1 = ctx.store(torch.relu(_batchnorm(ctx, y1, p + ".bn1")))
-    y2 = ctx.store(F.conv2d(a1, ctx.w(p + ".conv2.weight"), stride=1, padding=1))
+    a1 = ctx.store(ctx.relu(p + ".relu1", _batchnorm(ctx, y1, p + ".bn1")), p + ".relu1")
+    ctx.save(p + ".relu1", a1)
+    y2 = ctx.store(F.conv2d(a1, ctx.w(p + ".conv2.weight"), stride=1, padding=1), p + ".conv2")
     ctx.save(p + ".conv2", y2)
-    yd = ctx.store(F.conv2d(x, ctx.w(p + ".downsample.0.weight"), stride=2))
+    yd = ctx.store(F.conv2d(x, ctx.w(p + ".downsample.0.weight"), stride=2), p + ".downsample.0")
     ctx.save(p + ".downsample.0", yd)
-    out = ctx.store(torch.relu(_batchnorm(ctx, y2, p + ".bn2") + _batchnorm(ctx, yd, p + ".downsample.1")))
+    out = ctx.store(ctx.relu(p, _batchnorm(ctx, y2, p + ".bn2") + _batchnorm(ctx, yd, p + ".downsample.1")), p)
     ctx.save(p, out)
     return out
 
@@ -279,23 +319,25 @@ def _basic_block(ctx: _Ctx, x: torch.Tensor, p: str) -> torch.Tensor:
 def _deconv_block(ctx: _Ctx, x: torch.Tensor, p: str) -> torch.Tensor:
     """model.py:70-85 with the upsample branch of model.py:197-204."""
     st = ctx.st
-    y1 = ctx.store(F.conv2d(x, ctx.w(p + ".conv1.weight")))
+    y1 = ctx.store(F.conv2d(x, ctx.w(p + ".conv1.weight")), p + ".conv1")
     ctx.save(p + ".conv1", y1)
-    a1 = ctx.store(torch.relu(_batchnorm(ctx, y1, p + ".bn1")))
-    y2 = ctx.store(F.conv_transpose2d(a1, ctx.w(p + ".conv2.weight"), stride=2, padding=1))
+    a1 = ctx.store(ctx.relu(p + ".relu1", _batchnorm(ctx, y1, p + ".bn1")), p + ".relu1")
+    ctx.save(p + ".relu1", a1)
+    y2 = ctx.store(F.conv_transpose2d(a1, ctx.w(p + ".conv2.weight"), stride=2, padding=1), p + ".conv2")
     ctx.save(p + ".conv2", y2)
-    yu = ctx.store(F.conv_transpose2d(x, ctx.w(p + ".upsample.0.weight"), stride=2, padding=1))
+    yu = ctx.store(F.conv_transpose2d(x, ctx.w(p + ".upsample.0.weight"), stride=2, padding=1), p + ".upsample.0")
     ctx.save(p + ".upsample.0", yu)
-    out = ctx.store(torch.relu(_batchnorm(ctx, y2, p + ".bn2") + _batchnorm(ctx, yu, p + ".upsample.1")))
+    out = ctx.store(ctx.relu(p, _batchnorm(ctx, y2, p + ".bn2") + _batchnorm(ctx, yu, p + ".upsample.1")), p)
     ctx.save(p, out)
     return out
 
 
 def encode(ctx: _Ctx, cfg: VAEConfig, x: torch.Tensor):
     st = ctx.st
-    y = ctx.store(F.conv2d(x, ctx.w("encoder.conv1.weight"), stride=2, padding=2))    # model.py:115
+    y = ctx.store(F.conv2d(x, ctx.w("encoder.conv1.weight"), stride=2, padding=2), "encoder.conv1")    # model.py:115
     ctx.save("encoder.conv1", y)
-    a = ctx.store(torch.relu(_batchnorm(ctx, y, "encoder.bn1")))                   # model.py:116-117
+    a = ctx.store(ctx.relu("encoder.relu", _batchnorm(ctx, y, "encoder.bn1")), "encoder.relu")     # model.py:116-117
+    ctx.save("encoder.relu", a)
     for i in range(1, 5):                                                      # model.py:119-122
         a = _basic_block(ctx, a, f"encoder.layer{i}.0")
     pooled = a.mean(dim=(2, 3), keepdim=True)                                  # model.py:123
@@ -308,12 +350,15 @@ def encode(ctx: _Ctx, cfg: VAEConfig, x: torch.Tensor):
 
 def decode(ctx: _Ctx, cfg: VAEConfig, z: torch.Tensor) -> torch.Tensor:
     st = ctx.st
-    y = ctx.store(F.conv_transpose2d(ctx.store(z), ctx.w("decoder.conv1.weight")))    # model.py:182
+    zs = ctx.store(z, "decoder.input")
+    ctx.save("decoder.input", zs)
+    y = ctx.store(F.conv_transpose2d(zs, ctx.w("decoder.conv1.weight")), "decoder.conv1")    # model.py:182
     ctx.save("decoder.conv1", y)
-    a = ctx.store(torch.relu(_batchnorm(ctx, y, "decoder.bn1")))                   # model.py:183-184
+    a = ctx.store(ctx.relu("decoder.relu", _batchnorm(ctx, y, "decoder.bn1")), "decoder.relu")     # model.py:183-184
+    ctx.save("decoder.relu", a)
     for i in range(1, len(cfg.dec_planes) + 1):                                # model.py:186-192
         a = _deconv_block(ctx, a, f"decoder.uplayer{i}.0")
-    y = ctx.store(F.conv2d(a, ctx.w("decoder.conv2.weight"), st["decoder.conv2.bias"], padding=1))
+    y = ctx.store(F.conv2d(a, ctx.w("decoder.conv2.weight"), st["decoder.conv2.bias"], padding=1), "decoder.conv2")
     ctx.save("decoder.conv2", y)
     out = _batchnorm(ctx, y, "decoder.bn2")                                    # model.py:193
     adj = cfg.adjust
@@ -323,11 +368,12 @@ def decode(ctx: _Ctx, cfg: VAEConfig, z: torch.Tensor) -> torch.Tensor:
 
 
 def forward(st, cfg: VAEConfig, x: torch.Tensor, eps: Optional[torch.Tensor],
-            training: bool = True, keep_activations: bool = False, emulate_bf16: bool = False):
+            training: bool = True, keep_activations: bool = False, emulate_bf16: bool = False, relu_masks=None,
+            forced_acts=None, emulate_bf16_grads: bool = False):
     """VAE.forward (model.py:316-342) for the ``pixelcnn is None`` configuration.
     ``eps`` is the standard-normal draw of ``rsample`` (model.py:149-150),
     shape [N, z, 1, 1].  Returns (mu, logvar, encoding, reconstruction, ctx)."""
-    ctx = _Ctx(st, training, keep_activations, emulate_bf16)
+    ctx = _Ctx(st, training, keep_activations, emulate_bf16, relu_masks, forced_acts, emulate_bf16_grads)
     mu, logvar = encode(ctx, cfg, x)
     if cfg.require_rsample:
         encoding = mu + eps * torch.exp(0.5 * logvar)
@@ -358,6 +404,17 @@ def weighted_ce_sum(recon: torch.Tensor, target: torch.Tensor, weight: Optional[
     if weight is not None:
         picked = picked * weight[target]
     return -picked.sum()
+
+
+def compute_mmd(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """model.py:367-383: RBF-kernel MMD between ``x`` (true_samples [N, z]) and ``y`` (encoding [N, z]);
+    k(a, b) = exp(-mean_d((a_d - b_d)^2) / dim) over all N x N pairs.  VAE.loss returns this / N as its 4th value
+    (model.py:394-396,406); with mmd = 0 it is a diagnostic outside the loss."""
+    def kern(a, b):
+        dim = a.shape[1]
+        d2 = ((a[:, None, :] - b[None, :, :]) ** 2).mean(dim=2) / float(dim)
+        return torch.exp(-d2)
+    return kern(x, x).sum() + kern(y, y).sum() - 2 * kern(x, y).sum()
 
 
 def loss(cfg: VAEConfig, target, mu, logvar, recon, ce_weight=None, kl_weight: Optional[float] = None):
@@ -394,7 +451,8 @@ class StepResult:
 
 
 def train_step(st, cfg: VAEConfig, x, target, eps, ce_weight=None, kl_weight=None,
-               keep_activations: bool = False, dtype=None, emulate_bf16: bool = False) -> StepResult:
+               keep_activations: bool = False, dtype=None, emulate_bf16: bool = False, relu_masks=None,
+               forced_acts=None, emulate_bf16_grads: bool = False) -> StepResult:
     """forward -> loss -> backward on the CPU.  ``dtype=torch.float64`` gives a
     higher-precision referee for the 1e-5 fp32 comparison.  ``emulate_bf16`` rounds
     every tensor the CUDA bf16 mode keeps in HBM (conv outputs, activations and their
@@ -418,7 +476,8 @@ def train_step(st, cfg: VAEConfig, x, target, eps, ce_weight=None, kl_weight=Non
         if ce_weight is not None:
             ce_weight = ce_weight.to(dtype)
     mu, logvar, enc, recon, ctx = forward(work, cfg, x, eps, training=True, keep_activations=keep_activations,
-                                          emulate_bf16=emulate_bf16)
+                                          emulate_bf16=emulate_bf16, relu_masks=relu_masks, forced_acts=forced_acts,
+                                          emulate_bf16_grads=emulate_bf16_grads)
     total, pxz, kl = loss(cfg, target, mu, logvar, recon, ce_weight, kl_weight)
     grads = torch.autograd.grad(total, [work[n] for n in names], allow_unused=True)
     gd = {n: (g if g is not None else torch.zeros_like(work[n])) for n, g in zip(names, grads)}
@@ -510,3 +569,166 @@ def normalise(labels: torch.Tensor) -> torch.Tensor:
     """main.py:383-388: (x - data_mean) / data_std on the label map, as [N,1,H,W] fp32."""
     n, h, w = labels.shape
     return (labels.float().view(n, 1, h, w) - DATA_MEAN) / DATA_STD
+
+
+# ----------------------------------------------------------------------------
+# layer-local referee of a backward pass (bf16 mode)
+# ----------------------------------------------------------------------------
+
+def local_backward(st, cfg: VAEConfig, x, eps, fwd: Dict[str, torch.Tensor], grd: Dict[str, torch.Tensor],
+                   d_recon: torch.Tensor, d_mu: Optional[torch.Tensor], d_logvar: Optional[torch.Tensor],
+                   dtype=torch.float64):
+    """Every backward kernel of an implementation judged on ITS OWN inputs.
+
+    ``fwd[name]`` / ``grd[name]`` are the forward tensors and gradient tensors another evaluation stored (NCHW; names as
+    ``_Ctx.save``: raw conv outputs "<conv>", ReLU outputs "encoder.relu" / "<block>.relu1" / "<block>" /
+    "decoder.relu", the latent "decoder.input").  For each layer the adjoint of the reference's forward formula
+    (BatchNorm2d in training mode + ReLU gate, model.py:41-55,72-85; conv / transposed conv; pooling + heads + rsample,
+    model.py:123-128,148-150) is evaluated in ``dtype`` on the STORED inputs of that layer, so one layer's rounding never
+    reaches the next one's expectation.  Returns (param_grads, act_grads): expected parameter gradients by name, and
+    expected gradient tensors by activation name with the ReLU gate (or None) under which they are to be compared
+    (an implementation may store d(activation) before or after the gate of that activation)."""
+    P: Dict[str, torch.Tensor] = {}
+    A: Dict[str, Tuple[torch.Tensor, Optional[torch.Tensor]]] = {}
+    f = {k: v.to(dtype) for k, v in fwd.items()}
+    g = {k: v.to(dtype) for k, v in grd.items()}
+
+    def w_of(name):
+        t = st[name].to(dtype)
+        return t if name in FP32_OPERANDS else st[name].to(torch.bfloat16).to(dtype)
+
+    def bn_bwd(y_name, prefix, gate_name, dA, out_name=None):
+        """dA = gradient wrt the (pre-gate) BatchNorm output sum; returns nothing, fills P and A."""
+        y = f[y_name]
+        gamma = st[prefix + ".weight"].to(dtype)
+        m = y.shape[0] * y.shape[2] * y.shape[3]
+        mean = y.mean(dim=(0, 2, 3), keepdim=True)
+        var = ((y - mean) ** 2).mean(dim=(0, 2, 3), keepdim=True)
+        rstd = 1.0 / torch.sqrt(var + BN_EPS)
+        xhat = (y - mean) * rstd
+        gg = dA if gate_name is None else dA * (f[gate_name] > 0).to(dtype)
+        dbeta = gg.sum(dim=(0, 2, 3))
+        dgamma = (gg * xhat).sum(dim=(0, 2, 3))
+        P[prefix + ".bias"] = dbeta
+        P[prefix + ".weight"] = dgamma
+        dY = gamma[None, :, None, None] * rstd * (gg - dbeta[None, :, None, None] / m - xhat * dgamma[None, :, None, None] / m)
+        A[y_name] = (dY, None)
+
+    def conv_bwd(kind, wname, in_name, y_name, stride, padding, bias=None, x_in=None):
+        """weight gradient (+ data gradient) of one conv from the stored input and the stored dY."""
+        xin = (f[in_name] if x_in is None else x_in.to(dtype)).clone().requires_grad_(in_name is not None)
+        w = w_of(wname).clone().requires_grad_(True)
+        if kind == "conv":
+            y = F.conv2d(xin, w, stride=stride, padding=padding)
+        else:
+            y = F.conv_transpose2d(xin, w, stride=stride, padding=padding)
+        outs = [w] + ([xin] if in_name is not None else [])
+        res = torch.autograd.grad(y, outs, g[y_name])
+        P[wname] = res[0]
+        if bias is not None:
+            P[bias] = g[y_name].sum(dim=(0, 2, 3))
+        return res[1] if in_name is not None else None
+
+    # ---- decoder tail: d_recon -> BatchNorm (no gate) -> conv 3x3 + bias ----
+    ndec = len(cfg.dec_planes)
+    last = f"decoder.uplayer{ndec}.0"
+    dr = d_recon.to(dtype)
+    adj = cfg.adjust
+    if adj != 0:
+        dr = F.pad(dr, (adj, adj, adj, adj))
+    bn_bwd("decoder.conv2", "decoder.bn2", None, dr)
+    # decoder.conv2.bias feeds a BatchNorm: true gradient 0 (sum of dY over a normalised channel), SURVEY.md Appendix B.1
+    dX = conv_bwd("conv", "decoder.conv2.weight", last, "decoder.conv2", 1, 1)
+    A[last] = (dX, f[last] > 0)
+    # ---- up-blocks, last to first ----
+    for i in range(ndec, 0, -1):
+        p = f"decoder.uplayer{i}.0"
+        src = f"decoder.uplayer{i - 1}.0" if i > 1 else "decoder.relu"
+        dOut = g[p]
+        bn_bwd(p + ".conv2", p + ".bn2", p, dOut)
+        bn_bwd(p + ".upsample.0", p + ".upsample.1", p, dOut)
+        d_a1 = conv_bwd("convT", p + ".conv2.weight", p + ".relu1", p + ".conv2", 2, 1)
+        A[p + ".relu1"] = (d_a1, f[p + ".relu1"] > 0)
+        bn_bwd(p + ".conv1", p + ".bn1", p + ".relu1", g[p + ".relu1"])
+        d_in = conv_bwd("conv", p + ".conv1.weight", src, p + ".conv1", 1, 0)
+        d_in = d_in + conv_bwd("convT", p + ".upsample.0.weight", src, p + ".upsample.0", 2, 1)
+        A[src] = (d_in, f[src] > 0)
+    bn_bwd("decoder.conv1", "decoder.bn1", "decoder.relu", g["decoder.relu"])
+    dz = conv_bwd("convT", "decoder.conv1.weight", "decoder.input", "decoder.conv1", 1, 0)
+    A["decoder.input"] = (dz, None)
+    # ---- rsample + heads + pooling (model.py:123-128,148-150) ----
+    feat_name = "encoder.layer4.0"
+    feat = f[feat_name].clone().requires_grad_(True)
+    wmu = st["encoder.conv_mu.weight"].to(dtype).clone().requires_grad_(True)
+    pooled = feat.mean(dim=(2, 3), keepdim=True)
+    mu = F.conv2d(pooled, wmu)
+    outs, seeds = [], []
+    dzs = g["decoder.input"]
+    if cfg.require_rsample:
+        wlv = st["encoder.conv_logvar.weight"].to(dtype).clone().requires_grad_(True)
+        lv = F.conv2d(pooled, wlv)
+        z = mu + eps.to(dtype) * torch.exp(0.5 * lv)
+        total = (z * dzs).sum()
+        if d_mu is not None:
+            total = total + (mu * d_mu.to(dtype)).sum() + (lv * d_logvar.to(dtype)).sum()
+        r = torch.autograd.grad(total, [feat, wmu, wlv])
+        P["encoder.conv_logvar.weight"] = r[2]
+    else:
+        total = (mu * dzs).sum()
+        if d_mu is not None:
+            total = total + (mu * d_mu.to(dtype)).sum()
+        r = torch.autograd.grad(total, [feat, wmu])
+    P["encoder.conv_mu.weight"] = r[1]
+    A[feat_name] = (r[0], f[feat_name] > 0)
+    # ---- encoder blocks, last to first ----
+    for i in range(4, 0, -1):
+        p = f"encoder.layer{i}.0"
+        src = f"encoder.layer{i - 1}.0" if i > 1 else "encoder.relu"
+        dOut = g[p]
+        bn_bwd(p + ".conv2", p + ".bn2", p, dOut)
+        bn_bwd(p + ".downsample.0", p + ".downsample.1", p, dOut)
+        d_a1 = conv_bwd("conv", p + ".conv2.weight", p + ".relu1", p + ".conv2", 1, 1)
+        A[p + ".relu1"] = (d_a1, f[p + ".relu1"] > 0)
+        bn_bwd(p + ".conv1", p + ".bn1", p + ".relu1", g[p + ".relu1"])
+        d_in = conv_bwd("conv", p + ".conv1.weight", src, p + ".conv1", 2, 1)
+        d_in = d_in + conv_bwd("conv", p + ".downsample.0.weight", src, p + ".downsample.0", 2, 0)
+        A[src] = (d_in, f[src] > 0)
+    bn_bwd("encoder.conv1", "encoder.bn1", "encoder.relu", g["encoder.relu"])
+    conv_bwd("conv", "encoder.conv1.weight", None, "encoder.conv1", 2, 2, x_in=x)
+    return P, A
+
+
+# ----------------------------------------------------------------------------
+# the step after the hot path: optim.Adam (main.py:468, optimizer.step() main.py:399)
+# ----------------------------------------------------------------------------
+
+def adam_update(p, g, m, v, step: int, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0):
+    """torch.optim.Adam defaults restated (amsgrad=False, maximize=False): returns (p', m', v') for the 1-based
+    ``step``.  L2 weight decay is added to the gradient; eps sits outside the square root, after the bias correction."""
+    if weight_decay != 0.0:
+        g = g + weight_decay * p
+    m = beta1 * m + (1 - beta1) * g
+    v = beta2 * v + (1 - beta2) * g * g
+    bc1 = 1 - beta1 ** step
+    bc2 = 1 - beta2 ** step
+    denom = v.sqrt() / math.sqrt(bc2) + eps
+    return p - (lr / bc1) * (m / denom), m, v
+
+
+def train_loop(st, cfg: VAEConfig, x, target, eps_list, lr=1e-3, dtype=None):
+    """The loop body main.py:389-399 repeated over ``eps_list`` (one rsample draw per iteration) on a fixed batch:
+    forward, loss, backward, Adam.  Returns (losses, final_state) with BatchNorm buffers advanced as training does."""
+    cur = {k: (v.detach().clone().to(dtype) if (dtype is not None and v.is_floating_point()) else v.detach().clone())
+           for k, v in st.items()}
+    names = [n for n, _ in param_specs(cfg)]
+    mom = {n: torch.zeros_like(cur[n]) for n in names}
+    var = {n: torch.zeros_like(cur[n]) for n in names}
+    losses = []
+    for it, eps in enumerate(eps_list, start=1):
+        r = train_step(cur, cfg, x, target, eps, dtype=dtype)
+        losses.append(r.loss)
+        for n in names:
+            cur[n], mom[n], var[n] = adam_update(cur[n], r.grads[n].to(cur[n].dtype), mom[n], var[n], it, lr=lr)
+        for k, b in r.new_buffers.items():
+            cur[k] = b
+    return losses, cur

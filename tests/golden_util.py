@@ -11,7 +11,7 @@ from oracle import vae_oracle as O
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
-               if not os.path.basename(p).startswith(("init_", "nb")))
+               if not os.path.basename(p).startswith(("init_", "nb", "aux_")))
 
 
 def sample_idx(numel, n=257):

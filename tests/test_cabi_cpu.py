@@ -26,12 +26,12 @@ def test_exports_match_header(M):
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/mmvae.h but not exported"
     assert declared == set(M._lib.EXPORTS)
-    assert lib.mmvae_abi_version() == M._lib.ABI_VERSION == 3
+    assert lib.mmvae_abi_version() == M._lib.ABI_VERSION == 4
 
 
 def test_struct_sizes(M):
     assert ctypes.sizeof(M._lib.Desc) == 64
-    assert ctypes.sizeof(M._lib.LossArgs) == 40
+    assert ctypes.sizeof(M._lib.LossArgs) == 56
 
 
 @pytest.mark.parametrize("kw", [dict(), dict(input_image_size=32, z_dimension=32), dict(input_image_size=28, z_dimension=16),

@@ -201,3 +201,28 @@ def test_mid_kernels_with_several_bands_per_cta():
     for k, r in ref.grads.items():
         if k.startswith("decoder."):
             assert float((res[7][k].double() - r).norm() / r.norm()) <= 1e-2, k
+
+
+def test_fp32_mode_16_frames_128_vs_fp64_oracle():
+    """The notebook variant at the BENCH frame size (128 x 128) on 16 frames -- past the 2-frame fixture, enough for
+    several tiles / CTAs per kernel -- fp32 validation mode against the fp64 oracle: loss 1e-5, tensors and gradients 1e-4."""
+    cfg = NB.NbConfig(image_size=128)
+    st = NB.init_state(cfg, seed=7)
+    n = 16
+    x, y = NB.synthetic_batch(cfg, n, seed=99)
+    eps = torch.randn(n, cfg.z_dimensions, cfg.latent_hw, cfg.latent_hw, generator=torch.Generator().manual_seed(3))
+    ref = NB.train_step(st, cfg, x, y, eps, kl_weight=0.6, dtype=torch.float64, keep_logits=False)
+    m = build(cfg, st, "fp32")
+    loss, pxz, kl, mu, logvar, enc, recon, grads = run(m, x, y, eps, 0.6, materialize=False)
+    assert abs(loss - ref.loss) <= 1e-5 * abs(ref.loss)
+    assert float((mu.double() - ref.mu).norm() / ref.mu.norm()) <= 1e-4
+    bad = {k: float((grads[k].double() - r).norm() / r.norm()) for k, r in ref.grads.items()
+           if float((grads[k].double() - r).norm() / r.norm()) > 1e-4}
+    assert not bad, bad
+    # and the bf16 product path on the same 16 frames: loss and decoder gradients within the north_star 1e-2
+    mb = build(cfg, st, "bf16")
+    lb, _, _, _, _, _, _, gb = run(mb, x, y, eps, 0.6, materialize=False)
+    assert abs(lb - ref.loss) <= 1e-2 * abs(ref.loss)
+    badb = {k: float((gb[k].double() - r).norm() / r.norm()) for k, r in ref.grads.items()
+            if k.startswith("decoder.") and float((gb[k].double() - r).norm() / r.norm()) > 1e-2}
+    assert not badb, badb

@@ -185,8 +185,8 @@ def test_philox_eps_is_reproducible_and_normal():
     n = 1 << 16
     a = torch.empty(n, device="cuda"); b = torch.empty(n, device="cuda")
     s = c_void_p(torch.cuda.current_stream().cuda_stream)
-    M._lib.check(M._lib.lib.mmvae_philox_normal(1234, 0, n, c_void_p(a.data_ptr()), s))
-    M._lib.check(M._lib.lib.mmvae_philox_normal(1234, 0, n, c_void_p(b.data_ptr()), s))
+    M._lib.check(M._lib.lib.mmvae_philox_normal(1234, 0, None, 0, n, c_void_p(a.data_ptr()), s))
+    M._lib.check(M._lib.lib.mmvae_philox_normal(1234, 0, None, 0, n, c_void_p(b.data_ptr()), s))
     assert torch.equal(a, b)
     assert abs(a.mean().item()) < 0.02 and abs(a.std().item() - 1.0) < 0.02
     # the module's own draw is exposed so the same noise can be fed to the reference
@@ -210,3 +210,32 @@ def test_kl_weight_and_kl_divergence():
     kl.backward()
     assert rel_l2(mu.grad.cpu(), mu.detach().cpu()) < 1e-5                       # dKL/dmu = mu
     assert rel_l2(lv.grad.cpu(), 0.5 * (torch.exp(lv.detach().cpu()) - 1)) < 1e-5
+
+
+@pytest.mark.parametrize("kw,n", [(dict(input_image_size=64, z_dimension=64), 256),                 # BASELINE configs[1]
+                                  (dict(input_image_size=64, z_dimension=256, width=2), 128)])     # configs[3], per-GPU share
+def test_fp32_mode_at_bench_sizes_vs_fp64_oracle(kw, n):
+    """The BENCH batch sizes pinned to the oracle: fp32 validation mode of the library against an fp64 evaluation of
+    the reference's formulas on the same frames, weights and noise.  Same two-sided bar as the small fixtures: loss
+    1e-5; every gradient no worse than 3x torch-fp32's own distance from fp64 (floor 1e-5)."""
+    cfg = O.VAEConfig(**kw)
+    st = O.init_state(cfg, seed=3)
+    x = O.normalise(O.synthetic_labels(n, 64))
+    eps = torch.randn(n, cfg.z_dimension, 1, 1, generator=torch.Generator().manual_seed(11))
+    r64 = O.train_step(st, cfg, x, x, eps, dtype=torch.float64)
+    r32 = O.train_step(st, cfg, x, x, eps)
+    res = train_step(build_model(cfg, st, "fp32"), cfg, x, x, eps)
+    assert abs(res.loss - r64.loss) <= 1e-5 * abs(r64.loss)
+    assert rel_l2(res.recon, r64.recon) <= 1e-4 and rel_l2(res.mu, r64.mu) <= 1e-4
+    bad, worst, worst_ref = [], 0.0, 0.0
+    for k, _ in O.param_specs(cfg):
+        if k == "decoder.conv2.bias":
+            continue
+        e, e_ref = rel_l2(res.grads[k], r64.grads[k]), rel_l2(r32.grads[k], r64.grads[k])
+        worst, worst_ref = max(worst, e), max(worst_ref, e_ref)
+        if e > max(1e-5, 3 * e_ref):
+            bad.append((k, e, e_ref))
+    print(f"width {cfg.width} N={n}: worst grad rel-L2 vs fp64: ours {worst:.2e}, torch-fp32 {worst_ref:.2e}")
+    assert not bad, bad[:10]
+    for prefix, _ in O.bn_names(cfg):
+        assert rel_l2(res.new_buffers[prefix + ".running_var"], r64.new_buffers[prefix + ".running_var"]) <= 1e-4
