@@ -1054,8 +1054,9 @@ size_t mmvae_mmd_scratch_bytes(int32_t n) { return mmd_scratch_bytes(n > 0 ? n :
 int mmvae_mmd(const float* true_samples, const float* encoding, int32_t n, int32_t z_dim, float* out, void* scratch,
               void* stream) {
   if (int rc = check_device()) return rc;
-  if (!true_samples || !encoding || !out || !scratch || n < 1 || z_dim < 1 || z_dim > 8192)
-    return fail(MMVAE_ERR_BAD_ARG, "mmvae_mmd: bad arguments");
+  if (!true_samples || !encoding || !out || !scratch || n < 1 || z_dim < 1 || z_dim > 1024)
+    return fail(MMVAE_ERR_BAD_ARG, "mmvae_mmd: bad arguments (z_dim <= 1024)");
+  if (!aligned16(true_samples) || !aligned16(encoding)) return fail(MMVAE_ERR_BAD_ARG, "mmvae_mmd: inputs must be 16-byte aligned");
   launch_mmd(true_samples, encoding, n, z_dim, out, scratch, reinterpret_cast<cudaStream_t>(stream));
   return check_launches("mmvae_mmd");
 }

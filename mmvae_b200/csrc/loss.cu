@@ -246,32 +246,61 @@ __global__ void __launch_bounds__(256) loss_ce_bwd_kernel(LossArgs a, const floa
 
 // ---- MMD diagnostic (model.py:367-383): k(a, b) = exp(-mean_d((a_d - b_d)^2) / dim) = exp(-|a - b|^2 / dim^2),
 // mmd = sum k(x,x) + sum k(y,y) - 2 sum k(x,y) over all N x N pairs, x = true_samples, y = encoding.
-// grid (N, 3): CTA (i, which) holds row i of the left operand in shared memory and sums k over every row of the right
-// operand; the per-CTA sums are combined in fp64 in a fixed order by the CTA that finishes last.
+// grid (ceil(N / kMmdRows), 3): CTA (t, which) holds kMmdRows rows of the left operand in shared memory; thread j walks
+// the rows of the right operand (one row per thread and pass, 16-byte loads, each element reused for all kMmdRows left
+// rows) and sums k; the per-CTA sums are combined in fp64 in a fixed order by the CTA that finishes last.
+constexpr int kMmdRows = 8, kMmdThreads = 256;
 struct MmdScratch { unsigned int counter; unsigned int pad[3]; float part[1]; };
-__global__ void __launch_bounds__(128) mmd_kernel(const float* __restrict__ x, const float* __restrict__ y, int N, int z,
-                                                  MmdScratch* __restrict__ sc, float* __restrict__ out) {
-  extern __shared__ float row[];
-  __shared__ float sh[4];
-  __shared__ double shd[4];
+__global__ void __launch_bounds__(kMmdThreads) mmd_kernel(const float* __restrict__ x, const float* __restrict__ y, int N, int z,
+                                                          MmdScratch* __restrict__ sc, float* __restrict__ out) {
+  extern __shared__ float rows[];                      // [kMmdRows][z]
+  __shared__ float sh[kMmdThreads / 32];
+  __shared__ double shd[kMmdThreads / 32];
   __shared__ int is_last;
-  const int i = blockIdx.x, which = blockIdx.y;
+  const int which = blockIdx.y, i0 = blockIdx.x * kMmdRows;
   const float* A = which == 1 ? y : x;                 // 0: (x,x)  1: (y,y)  2: (x,y)
   const float* B = which == 0 ? x : y;
-  for (int d = threadIdx.x; d < z; d += 128) row[d] = A[(size_t)i * z + d];
+  const int nrows = min(kMmdRows, N - i0);
+  for (int e = threadIdx.x; e < kMmdRows * z; e += kMmdThreads) rows[e] = e < nrows * z ? A[(size_t)i0 * z + e] : 0.f;
   __syncthreads();
   const float inv = 1.0f / ((float)z * (float)z);
   float s = 0.f;
-  for (int j = threadIdx.x; j < N; j += 128) {
+  for (int j = threadIdx.x; j < N; j += kMmdThreads) {
     const float* b = B + (size_t)j * z;
-    float q = 0.f;
-    for (int d = 0; d < z; ++d) { const float t = row[d] - __ldg(b + d); q = fmaf(t, t, q); }
-    s += expf(-q * inv);
+    float q[kMmdRows];
+#pragma unroll
+    for (int r = 0; r < kMmdRows; ++r) q[r] = 0.f;
+    if ((z & 3) == 0) {
+#pragma unroll 4
+      for (int d = 0; d < z; d += 4) {
+        const float4 bv = __ldg(reinterpret_cast<const float4*>(b + d));
+#pragma unroll
+        for (int r = 0; r < kMmdRows; ++r) {
+          const float4 av = *reinterpret_cast<const float4*>(rows + r * z + d);
+          const float t0 = av.x - bv.x, t1 = av.y - bv.y, t2 = av.z - bv.z, t3 = av.w - bv.w;
+          q[r] = fmaf(t0, t0, fmaf(t1, t1, fmaf(t2, t2, fmaf(t3, t3, q[r]))));
+        }
+      }
+    } else {
+      for (int d = 0; d < z; ++d) {
+        const float bv = __ldg(b + d);
+#pragma unroll
+        for (int r = 0; r < kMmdRows; ++r) { const float t = rows[r * z + d] - bv; q[r] = fmaf(t, t, q[r]); }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < kMmdRows; ++r) if (r < nrows) s += expf(-q[r] * inv);
   }
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
   __syncthreads();
-  if (threadIdx.x == 0) sc->part[which * N + i] = (sh[0] + sh[1]) + (sh[2] + sh[3]);
+  const int nparts = gridDim.x;
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < kMmdThreads / 32; ++w) t += sh[w];
+    sc->part[which * nparts + blockIdx.x] = t;
+  }
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) is_last = (atomicAdd(&sc->counter, 1u) == gridDim.x * gridDim.y - 1u) ? 1 : 0;
@@ -279,12 +308,15 @@ __global__ void __launch_bounds__(128) mmd_kernel(const float* __restrict__ x, c
   if (!is_last) return;
   __threadfence();
   double t = 0.0;
-  for (int e = threadIdx.x; e < 3 * N; e += 128) t += (e >= 2 * N ? -2.0 : 1.0) * (double)__ldcg(sc->part + e);
+  for (int e = threadIdx.x; e < 3 * nparts; e += kMmdThreads) t += (e >= 2 * nparts ? -2.0 : 1.0) * (double)__ldcg(sc->part + e);
   t = warp_sum_d(t);
   if ((threadIdx.x & 31) == 0) shd[threadIdx.x >> 5] = t;
   __syncthreads();
   if (threadIdx.x == 0) {
-    out[0] = (float)(((shd[0] + shd[1]) + (shd[2] + shd[3])) / (double)N);     // MMD / N, the 4th return value (model.py:406)
+    double tot = 0.0;
+#pragma unroll
+    for (int w = 0; w < kMmdThreads / 32; ++w) tot += shd[w];
+    out[0] = (float)(tot / (double)N);                 // MMD / N, the 4th return value (model.py:406)
     sc->counter = 0u;
   }
 }
@@ -386,10 +418,11 @@ void launch_loss_bwd(const LossArgs& a, const float* recon, const void* target, 
                lv, gout, kl_dev, d_recon, d_mu, d_lv, rblocks);
 }
 
-size_t mmd_scratch_bytes(int N) { return sizeof(MmdScratch) + sizeof(float) * 3 * (size_t)N; }
+size_t mmd_scratch_bytes(int N) { return sizeof(MmdScratch) + sizeof(float) * 3 * (size_t)((N + kMmdRows - 1) / kMmdRows); }
 void launch_mmd(const float* x, const float* y, int N, int z, float* out, void* scratch, cudaStream_t st) {
   count_launch();
-  mmd_kernel<<<dim3(N, 3), 128, sizeof(float) * z, st>>>(x, y, N, z, reinterpret_cast<MmdScratch*>(scratch), out);
+  mmd_kernel<<<dim3((N + kMmdRows - 1) / kMmdRows, 3), kMmdThreads, sizeof(float) * kMmdRows * z, st>>>(
+      x, y, N, z, reinterpret_cast<MmdScratch*>(scratch), out);
 }
 
 void launch_prepare_input(const unsigned char* labels, long long n, float mean, float std, float* x,

@@ -65,7 +65,12 @@ class GraphedTrainStep:
         opt_snap = None
         if optimizer is not None:
             opt_snap = (optimizer.exp_avg.clone(), optimizer.exp_avg_sq.clone(), optimizer._step_dev.clone(), optimizer.step_count)
-        side = torch.cuda.Stream(device=dev)
+        # one warm-up / capture stream per module: the parameters' AccumulateGrad nodes live on the stream that was current
+        # when they were created (and a GraphedTrainStep keeps them alive through its outputs), so a second graph of the
+        # same module captured on another stream would make autograd insert a cross-stream hand-over per parameter
+        side = getattr(model, "_capture_stream", None)
+        if side is None or side.device != dev:
+            side = model._capture_stream = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(max(1, warmup)):

@@ -68,7 +68,7 @@ class _LossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, recon, target, mu, logvar, largs, ce_weight, scratch):
         dev = mu.device if recon is None else recon.device
-        out = torch.empty(4, dtype=torch.float32, device=dev)          # loss, pxz/N, KL/N, MMD/N (filled by VAE.loss)
+        out = torch.empty(3, dtype=torch.float32, device=dev)          # loss, pxz/N, KL/N
         with torch.cuda.device(dev):
             check(lib.mmvae_loss_forward(byref(largs), _ptr(recon), _ptr(target), _ptr(ce_weight), _ptr(mu),
                                          _ptr(logvar), _ptr(out), _ptr(scratch), _stream(dev)), "mmvae_loss_forward")
@@ -456,11 +456,13 @@ class VAE(nn.Module):
             check(lib.mmvae_mmd(_ptr(x), _ptr(y), n, z, _ptr(out), _ptr(self._mmd_scratch), _stream(dev)), "mmvae_mmd")
         return out
 
-    def _mmd_side(self, encoding, true_samples, out):
-        """The MMD diagnostic on a side stream, beside the loss kernel (it has coefficient 0 in every supported model,
-        so nothing waits for it except the read of the value).  true_samples default to a Philox draw (stream 1 of the
-        module's generator; the reference draws torch.randn on the host, model.py:395) kept in `last_true_samples`."""
+    def _mmd_fork(self, encoding, true_samples):
+        """Start the MMD diagnostic on a side stream, BESIDE the loss kernel that the caller launches next (it has
+        coefficient 0 in every supported model, so nothing but the read of its value depends on it); `_mmd_join` makes the
+        current stream wait for it.  true_samples default to a Philox draw (stream 1 of the module's generator; the
+        reference draws torch.randn on the host, model.py:395) kept in `last_true_samples`.  Returns the 0-d result."""
         dev = encoding.device
+        out = torch.empty((), dtype=torch.float32, device=dev)
         n, z = encoding.shape[0], encoding.numel() // encoding.shape[0]
         cur = torch.cuda.current_stream(dev)
         if true_samples is None:
@@ -482,8 +484,11 @@ class VAE(nn.Module):
                 check(lib.mmvae_philox_normal(self._philox_seed, off, _ptr(self._rng_dev), 1, n * z, _ptr(ts),
                                               _stream(dev)), "mmvae_philox_normal")
             self.compute_mmd(ts, encoding, out=out)
-        cur.wait_stream(side)
         self.last_true_samples = ts
+        return out
+
+    def _mmd_join(self):
+        torch.cuda.current_stream(self._side.device).wait_stream(self._side)
 
     def kl_divergence(self, encoding_mu, encoding_logvar):
         """model.py:364-365: -0.5 * sum(logvar - exp(logvar) - mu^2 + 1)."""
@@ -534,15 +539,16 @@ class VAE(nn.Module):
             nz = mu.numel() // n
         kl_dev = self._kl_dev if kl_weight is None else None
         a = self._loss_args(n, c, h, w, nz, self.kl if kl_weight is None else kl_weight, self.nll, kl_dev)
-        loss, out = _LossFn.apply(recon, tgt, mu, lv, a, cew, self._scratch(recon.device))
+        mmd = None
         if encoding is not None and self.mmd_diagnostic:                   # model.py:394-396
-            self._mmd_side(encoding, true_samples, out[3])
-        else:
-            out[3] = 0.0
+            mmd = self._mmd_fork(encoding, true_samples)
+        loss, out = _LossFn.apply(recon, tgt, mu, lv, a, cew, self._scratch(recon.device))
+        if mmd is not None:
+            self._mmd_join()
         if self.defer_metrics:
-            return loss, out[1], out[2], out[3]
+            return loss, out[1], out[2], (mmd if mmd is not None else torch.zeros((), device=recon.device))
         vals = out.tolist()
-        return loss, vals[1], vals[2], vals[3]
+        return loss, vals[1], vals[2], (float(mmd) if mmd is not None else 0.0)
 
     def __repr__(self):
         kind = "categorical" if self.decoder_out_channels > self.in_channels else f"normal(sigma={self.sigma_decoder})"

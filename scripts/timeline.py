@@ -16,6 +16,7 @@ torch.manual_seed(0)
 model = M.VAE(1, 32, decoder_out_channels=1, pixelcnn_out_channels=0, z_dimension=64 if width == 1 else 256, pixelcnn=False,
               only_pixelcnn=False, sigma_decoder=0.1, input_image_size=64, precision="bf16", width=width).cuda().train()
 model.defer_metrics = True
+model.mmd_diagnostic = os.environ.get("MMD", "1") == "1"     # A/B: the MMD diagnostic's side branch
 largs = types.SimpleNamespace(data_ratio_of_labels=None)
 g = M.GraphedTrainStep(model, n, args=largs, warmup=2)
 g.x.copy_(D.prepare_input(D.synthetic_labels(n, 64).cuda()))
