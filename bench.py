@@ -658,10 +658,11 @@ def run_resnet(args, ctx, width, zdim, n, full=True):
     #                    decoder.uplayer5.0.conv2 (16->16 transposed conv, 256x32x32 -> 256x64x64): forward, data
     #                    gradient, weight gradient -- HBM-bound
     roof, roof_others = None, []
+    if full:
+        step_resident(0)                       # every rank (the replay holds the exchange): leaves a step's tensors in the workspace
+        torch.cuda.synchronize()
     if full and rank == 0 and args.precision == "bf16" and width == 1:    # per-kernel rooflines: the headline configuration only
         import ctypes
-        step_resident(0)
-        torch.cuda.synchronize()
         desc, ws, _info = model._workspace(n, True)
         names = [c[0] for c in M._lib.conv_table(desc)]
         ab, af = ctypes.c_int64(), ctypes.c_int64()
@@ -785,6 +786,9 @@ def brief(line):
 
 def main():
     guard_stdout()
+    # a stalled collective must not hold the box until the caller's limit: dump every thread's stack and leave
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("MMVAE_BENCH_STALL_S", "900")), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)

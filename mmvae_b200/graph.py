@@ -106,6 +106,11 @@ class GraphedTrainStep:
         self._copy_stream = None                        # prefetch(): double-buffered H2D beside the running step
         self._staged = None
 
+    def close(self):
+        """Release the captured graph (and the NCCL work a data-parallel capture holds on the communicator: a process
+        group must not be destroyed while such a graph is alive)."""
+        self.graph = None
+
     def set_kl_weight(self, value):
         """KL annealing: the coefficient of the next replays (a device scalar the captured loss kernels read)."""
         self.kl_weight_dev.fill_(float(value))

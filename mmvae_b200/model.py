@@ -46,8 +46,18 @@ def _stream(dev=None):
 
 
 class _VAEForwardFn(torch.autograd.Function):
+    """forward -> (mu, logvar, encoding, reconstruction); backward fills every parameter's `.grad`.
+
+    The parameters are NOT autograd inputs of this node: its backward writes the flat gradient arena and binds (or
+    accumulates into) each `p.grad` itself, exactly what ~93 AccumulateGrad nodes would do, minus their per-parameter
+    host work and minus their stream bookkeeping (an AccumulateGrad node lives on the stream that was current when it was
+    created and outlives the step through any tensor of the old graph the caller still holds; replaying it under a CUDA
+    graph capture on another stream is an error).  `anchor` is a fresh 0-d leaf per call whose only job is to make the
+    outputs require grad.  Consequence: `loss.backward()` behaves as in the reference; `torch.autograd.grad(loss,
+    parameters)` and per-parameter hooks do not see these gradients."""
+
     @staticmethod
-    def forward(ctx, module, x, eps, *params):
+    def forward(ctx, module, x, eps, anchor):
         mu, logvar, enc, recon, state = module._run_forward(x, eps, training=True)
         ctx.set_materialize_grads(False)               # unused outputs (encoding) arrive as None, not as a zero-filled tensor
         ctx.module = module
@@ -61,7 +71,15 @@ class _VAEForwardFn(torch.autograd.Function):
         # d_recon None (a loss without a reconstruction term, e.g. kl_divergence(mu, logvar).backward()) goes through
         # as NULL: the C ABI treats it as zero and skips the decoder sweep
         grads = ctx.module._run_backward(ctx.state, x, d_mu, d_logvar, d_enc, d_recon)
-        return (None, None, None) + grads
+        with torch.no_grad():
+            for p, g in zip(ctx.module._plist, grads):
+                if not p.requires_grad:
+                    continue
+                if p.grad is None:
+                    p.grad = g
+                else:
+                    p.grad += g                        # accumulate like autograd (main.py zeroes before backward)
+        return None, None, None, None
 
 
 class _LossFn(torch.autograd.Function):
@@ -387,7 +405,8 @@ class VAE(nn.Module):
             raise ValueError(f"expected x of shape [N, {self.in_channels}, {self.input_image_size}, "
                              f"{self.input_image_size}], got {tuple(x.shape)}")
         if self.training and torch.is_grad_enabled():
-            mu, logvar, enc, recon = _VAEForwardFn.apply(self, x, eps, *self._plist)
+            anchor = torch.empty((), dtype=torch.float32, device=x.device, requires_grad=True)
+            mu, logvar, enc, recon = _VAEForwardFn.apply(self, x, eps, anchor)
         else:
             with torch.no_grad():
                 mu, logvar, enc, recon, _ = self._run_forward(x, eps, training=self.training)

@@ -19,6 +19,19 @@ def _free_port():
 
 
 def _worker(rank, world, port, out):
+    """A failed assertion on one rank must not leave the other waiting in a collective (nor this one in
+    destroy_process_group): report the traceback through `out` and leave the process at once."""
+    import faulthandler
+    import traceback
+    faulthandler.dump_traceback_later(150, exit=True)
+    try:
+        _worker_body(rank, world, port, out)
+    except BaseException:
+        out[rank] = traceback.format_exc()
+        os._exit(1)
+
+
+def _worker_body(rank, world, port, out):
     import types
 
     import torch.distributed as dist
@@ -26,7 +39,7 @@ def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
-    try:
+    if True:
         import sys
         sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
         import mmvae_b200 as M
@@ -95,9 +108,14 @@ def _worker(rank, world, port, out):
             dist.all_gather(w, m2.flat_parameters)
             assert torch.equal(w[0], w[1]), f"{prec}: replicas drifted after three captured Adam steps"
             assert torch.isfinite(m2.flat_parameters).all()
+            step.close()                 # a live graph holds NCCL work: destroy_process_group() would wait for it forever
+            del step
         out[rank] = True
-    finally:
-        dist.destroy_process_group()
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
+    dist.barrier()
+    dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
@@ -106,5 +124,8 @@ def test_data_parallel_nccl_world2():
     world = 2
     with mp.Manager() as mgr:
         out = mgr.dict()
-        mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
-        assert all(out.get(r) for r in range(world))
+        try:
+            mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+        except Exception as e:                       # a worker left through os._exit(1): show what it reported
+            raise AssertionError("\n".join(f"rank {r}: {out.get(r)}" for r in range(world)) + f"\n{e}")
+        assert all(out.get(r) is True for r in range(world)), dict(out)
