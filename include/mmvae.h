@@ -139,14 +139,15 @@ int mmvae_workspace_tensor(const mmvae_desc* d, const char* name, int64_t* byte_
  *            device with Philox4x32-10 keyed by (seed, offset) and written to eps_out
  *   eps_out  [N, z] fp32 or NULL
  *   rng_state  NULL, or a device pointer to {seed, offset} (uint64 x 2) that overrides the by-value pair:
- *            lets a captured CUDA graph draw fresh noise on every replay (the host advances the offset
- *            with a device-side add between replays)
+ *            lets a captured CUDA graph draw fresh noise on every replay.  The call itself advances
+ *            rng_state[1] by ceil(N*z/4) after the draw (model.py VAE; the notebook variant leaves it to
+ *            the host)
  *   mu, logvar, encoding   [N, z] fp32 outputs (logvar may be NULL iff !require_rsample)
  *   recon    [N, out_channels, D, D] fp32 NCHW, D = decoder_size (crop is a host-side view)
  * The workspace keeps what mmvae_backward needs. */
 int mmvae_forward(const mmvae_desc* d, const float* x, const float* params, float* bn_buffers,
                   int64_t* bn_counters, const float* eps, uint64_t seed, uint64_t offset, float* eps_out,
-                  const uint64_t* rng_state, void* workspace, size_t workspace_bytes,
+                  uint64_t* rng_state, void* workspace, size_t workspace_bytes,
                   float* mu, float* logvar, float* encoding, float* recon, void* stream);
 
 /* MMVAE_ARCH_NOTEBOOK: mmvae_forward takes the same arguments (bn_buffers / bn_counters unused, may be NULL); `recon`

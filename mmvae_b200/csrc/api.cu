@@ -117,7 +117,8 @@ static void geom_dgrad(const ConvT_& c, int N, GConvParams& g) { geom_build(c, D
 // a parallel branch of the CUDA graph.  The pair (stream, events) is the only state the library keeps.
 // ------------------------------------------------------------------------------------------------
 struct AuxPool {
-  cudaStream_t s = nullptr;
+  cudaStream_t s = nullptr;      // weight gradients, shortcut convs, weight packing
+  cudaStream_t s2 = nullptr;     // the shortcut branch's data gradient of a block (backward), beside the main branch's chain
   cudaEvent_t ev[32];
   int next = 0;
   bool ok = false;
@@ -135,6 +136,7 @@ static AuxPool* aux_pool() {
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     static const bool flat = getenv("MMVAE_AUX_FLAT_PRIORITY") != nullptr;       // A/B: default priority (measured +0.4 % step time)
     if (cudaStreamCreateWithPriority(&p.s, cudaStreamNonBlocking, flat ? 0 : prio_lo) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (cudaStreamCreateWithFlags(&p.s2, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     for (auto& e : p.ev)
       if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     p.ok = true;
@@ -184,6 +186,26 @@ struct Exec {
     forked = false;
   }
   bool forked = false;
+  // the same pair for the second auxiliary stream
+  template <typename F> void side2(F f) {
+    if (!aux) { f(); return; }
+    cudaEvent_t e = next_event();
+    cudaEventRecord(e, st);
+    cudaStreamWaitEvent(aux->s2, e, 0);
+    cudaStream_t keep = st;
+    st = aux->s2;
+    f();
+    st = keep;
+    forked2 = true;
+  }
+  void join2() {
+    if (!aux || !forked2) return;
+    cudaEvent_t e = next_event();
+    cudaEventRecord(e, aux->s2);
+    cudaStreamWaitEvent(st, e, 0);
+    forked2 = false;
+  }
+  bool forked2 = false;
 
   // dedicated kernels of the 1-channel stem / tail convolutions (bf16 mode)
   bool special_ok() const { return std::is_same<T, __nv_bfloat16>::value && !(P.d.flags & MMVAE_FLAG_FORCE_SIMT); }
@@ -299,6 +321,15 @@ struct Exec {
     h.feat = at<T>(f.off);
     h.w_mu = params + P.w_mu; h.w_lv = P.w_lv >= 0 ? params + P.w_lv : nullptr;
     h.eps = eps; h.seed = seed; h.offset = offset; h.rng_dev = reinterpret_cast<const unsigned long long*>(rng_state);
+    h.rng_adv = nullptr; h.rng_ticket = nullptr; h.rng_inc = 0;
+    if (rng_state && !eps && P.d.require_rsample) {
+      // device-resident generator state: the kernel advances the offset itself (its last CTA, through a ticket that the
+      // bf16 path zeroes with its per-forward memset, clear_bn_acc)
+      h.rng_adv = const_cast<unsigned long long*>(h.rng_dev);
+      h.rng_ticket = at<unsigned int>(P.ticket_off);
+      h.rng_inc = (unsigned long long)(((long long)P.d.batch * P.d.z_dim + 3) / 4);
+      if (!std::is_same<T, __nv_bfloat16>::value) cudaMemsetAsync(h.rng_ticket, 0, sizeof(unsigned int), st);
+    }
     h.pooled = at<float>(P.pooled_off); h.heads = at<float>(P.heads_off);
     h.mu_out = mu; h.lv_out = logvar; h.enc_out = enc; h.eps_out = eps_out;
     h.z_act = at<T>(act(P.a_z).off);
@@ -422,10 +453,20 @@ struct Exec {
     f.inv_rows = 1.0 / ((double)P.d.batch * bc->Ho * bc->Wo);
   }
 
-  void dgrad(const ConvT_& c, int accumulate) {
+  // Block inputs whose gradient is kept in two parts (Plan: goff2): the shortcut branch's data gradient goes to the
+  // second buffer on the second auxiliary stream, beside the main branch's bn_bwd -> dgrad -> bn_bwd -> dgrad chain, and the
+  // BatchNorm backward that consumes the gradient adds the parts (BnBwdArgs::dA2): one launch less on the critical path
+  // of every block.
+  bool split_grad(int a) const {
+    static const bool off = getenv("MMVAE_NO_SPLIT_GRAD") != nullptr;
+    return !off && aux && a >= 0 && act(a).goff2 != 0 && !fused_reduce(a);
+  }
+
+  void dgrad(const ConvT_& c, int accumulate, bool to_alt = false) {
     GConvParams g;
     fill_dgrad(c, g);
     g.accumulate = accumulate;
+    if (to_alt) g.out = at<T>(act(c.in).goff2);
     if (c.in >= 0 && fused_reduce(c.in)) {
       const int last = last_dgrad_conv(c.in);
       GConvParams gl;
@@ -465,18 +506,31 @@ struct Exec {
     }
     a.rows = (long long)P.d.batch * c.Ho * c.Wo; a.C = c.Co;
     if (mask_act >= 0 && fused_reduce(mask_act)) { a.reduced = 1; a.a = nullptr; }   // dA arrives masked and reduced
+    if (mask_act >= 0 && !dA_f32 && dA == (const void*)at<T>(act(mask_act).goff) && split_grad(mask_act))
+      a.dA2 = at<T>(act(mask_act).goff2);
     launch_bn_bwd<T>(a, st);
   }
 
   void block_bwd(const BlockT& b) {
     const ConvT_& c1 = P.convs[b.c1]; const ConvT_& c2 = P.convs[b.c2]; const ConvT_& cs = P.convs[b.cs];
     bn_bwd(at<T>(act(b.out).goff), 0, b.out, c2, &cs);
+    const bool split = split_grad(b.in);
+    if (split) {
+      side2([&] {                                     // shortcut branch -> second part of d in, off the critical path
+        GConvParams g;
+        fill_dgrad(cs, g);
+        if (!dgrad_covers_all(g))                     // a strided 1x1 shortcut only reaches the even pixels
+          cudaMemsetAsync(at<T>(act(b.in).goff2), 0, sizeof(T) * size_t(P.d.batch) * act(b.in).H * act(b.in).W * act(b.in).C, st);
+        dgrad(cs, 0, true);
+      });
+    }
     side([&] { wgrad(c2); wgrad(cs); });              // weight gradients are off the critical path
     dgrad(c2, 0);                                     // -> d a1
     bn_bwd(at<T>(act(b.a1).goff), 0, b.a1, c1, nullptr);
     side([&] { wgrad(c1); });
     dgrad(c1, 0);                                     // -> d in
-    dgrad(cs, 1);                                     // += shortcut
+    if (split) join2();
+    else dgrad(cs, 1);                                // += shortcut
   }
 
   // ---------------- notebook variant (MMVAE_ARCH_NOTEBOOK; vae-kl.ipynb:119-166, loop body :210-233) ----------------
@@ -809,11 +863,13 @@ int mmvae_workspace_tensor(const mmvae_desc* d, const char* name, int64_t* byte_
   if (!P.build(d)) return fail(MMVAE_ERR_BAD_DESC, "%s", P.err.c_str());
   if (!name) return fail(MMVAE_ERR_BAD_ARG, "name is NULL");
   std::string nm(name);
-  bool grad = false;
-  if (nm.size() > 5 && nm.compare(nm.size() - 5, 5, ".grad") == 0) { grad = true; nm.resize(nm.size() - 5); }
+  bool grad = false, grad2 = false;
+  if (nm.size() > 6 && nm.compare(nm.size() - 6, 6, ".grad2") == 0) { grad2 = true; nm.resize(nm.size() - 6); }
+  else if (nm.size() > 5 && nm.compare(nm.size() - 5, 5, ".grad") == 0) { grad = true; nm.resize(nm.size() - 5); }
   const ActT* a = P.find_act(nm.c_str());
   if (!a) return fail(MMVAE_ERR_BAD_ARG, "no workspace tensor named '%s'", name);
-  if (byte_offset) *byte_offset = (int64_t)(grad ? a->goff : a->off);
+  if (grad2 && a->goff2 == 0) return fail(MMVAE_ERR_BAD_ARG, "'%s' has no second gradient buffer", nm.c_str());
+  if (byte_offset) *byte_offset = (int64_t)(grad2 ? a->goff2 : (grad ? a->goff : a->off));
   if (dims) { dims[0] = P.d.batch; dims[1] = a->H; dims[2] = a->W; dims[3] = a->C; }
   return 0;
 }
@@ -828,7 +884,7 @@ int mmvae_workspace_tensor(const mmvae_desc* d, const char* name, int64_t* byte_
 
 int mmvae_forward(const mmvae_desc* d, const float* x, const float* params, float* bn_buffers,
                   int64_t* bn_counters, const float* eps, uint64_t seed, uint64_t offset, float* eps_out,
-                  const uint64_t* rng_state, void* workspace, size_t workspace_bytes, float* mu, float* logvar,
+                  uint64_t* rng_state, void* workspace, size_t workspace_bytes, float* mu, float* logvar,
                   float* encoding, float* recon, void* stream) {
   MMVAE_COMMON_CHECKS();
   if (P.d.arch == MMVAE_ARCH_NOTEBOOK) {

@@ -285,6 +285,9 @@ struct HeadsArgs {
   const float* eps;        // [N][z] or nullptr -> Philox
   unsigned long long seed, offset;
   const unsigned long long* rng_dev;   // device {seed, offset} overriding the pair above, or nullptr
+  unsigned long long* rng_adv;         // == rng_dev when the kernel is to advance the device offset itself (the CTA that
+  unsigned int* rng_ticket;            // finishes last adds rng_inc; ticket: zeroed counter), else nullptr
+  unsigned long long rng_inc;
   float* pooled;           // [N][C]
   float* heads;            // [4][N][z]: mu, logvar, eps, std
   float* mu_out; float* lv_out; float* enc_out; float* eps_out;   // user-visible fp32 outputs
@@ -312,6 +315,7 @@ template <typename T> void launch_heads_bwd(const HeadsBwdArgs& a, cudaStream_t 
 //   S0 = sum g, S1 = sum g*xhat(y), S2 = sum g*xhat(y2)
 struct BnBwdArgs {
   const void* dA;          // incoming gradient NHWC storage type (or fp32 when dA_f32)
+  const void* dA2;         // second part of the incoming gradient (storage type; dA + dA2 is the gradient) or nullptr
   const void* a;           // activation output for the ReLU mask, or nullptr (no ReLU)
   const void* y;  const float* stat;  const float* gamma;           // main branch
   const void* y2; const float* stat2; const float* gamma2;          // second branch or nullptr

@@ -29,6 +29,8 @@ struct ActT {              // NHWC tensor in the workspace (storage type of the 
   std::string name;
   size_t off = 0;          // bytes: the tensor itself
   size_t goff = 0;         // bytes: its gradient (same shape / type)
+  size_t goff2 = 0;        // bytes: second gradient buffer of a block input (the shortcut branch's data gradient lands
+                           // here, beside the main branch's in goff; their sum is the gradient), or 0
   int H = 0, W = 0, C = 0;
 };
 
@@ -110,6 +112,7 @@ struct Plan {
   size_t dpool_off = 0;              // fp32 [N][feat_c]
   size_t drecon_off = 0;             // fp32 NHWC copy of d_recon when out_channels > 1
   size_t bnacc_off = 0, bnacc_bytes = 0;   // all BatchNorm accumulators + counters: one memset per forward
+  size_t ticket_off = 0;                   // uint32 inside that region: CTA ticket of the heads kernel (rng advance)
   size_t ws_bytes = 0;
   int64_t train_flops = 0;
   NbT nb;
@@ -331,11 +334,22 @@ struct Plan {
       size_t total = 0;
       for (auto& b : bns) { b.acc_off = total; total += sizeof(double) * 8 * 5 * b.C; }
       for (auto& b : bns) { b.cnt_off = total; total += 16; }
+      ticket_off = total; total += 16;
       bnacc_bytes = total;
       bnacc_off = bump(total);
       for (auto& b : bns) { b.acc_off += bnacc_off; b.cnt_off += bnacc_off; }
+      ticket_off += bnacc_off;
     }
 
+    // split gradients of the block inputs (api.cu block_bwd): bf16 product path, tensors wider than the 16 channels whose
+    // BatchNorm-backward reduction is fused into the data-gradient epilogue instead
+    if (d.precision == MMVAE_PREC_BF16 && !(d.flags & MMVAE_FLAG_FORCE_SIMT) && d.training) {
+      for (const std::vector<BlockT>* bl : {&enc, &dec})
+        for (const BlockT& b : *bl) {
+          ActT& a = acts[b.in];
+          if (a.C > 16) a.goff2 = bump(size_t(d.batch) * a.H * a.W * a.C * esz);
+        }
+    }
     plan_packing();
     return true;
   }

@@ -235,6 +235,15 @@ __global__ void __launch_bounds__(128) heads_fwd_kernel(const HeadsArgs a) {
     if (a.eps_out) a.eps_out[idx] = eps;
     reinterpret_cast<T*>(a.z_act)[idx] = from_f<T>(enc);
   }
+  if (a.rng_adv) {
+    // device-resident generator state (a captured graph draws fresh noise per replay): every CTA has read the offset
+    // above; the one that finishes last advances it for the next forward
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      if (atomicAdd(a.rng_ticket, 1u) == gridDim.x * gridDim.y - 1u) { a.rng_adv[1] += a.rng_inc; *a.rng_ticket = 0u; }
+    }
+  }
 }
 
 template <typename T>
@@ -304,6 +313,12 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
       size_t off = size_t(r) * a.C + c0;
       float g[VEC], yv[VEC];
       load_grad<T, VEC>(a.dA, a.dA_f32, off, g);
+      if (a.dA2) {                                   // the gradient arrives in two parts (main branch, shortcut branch)
+        float g2[VEC];
+        load_vec<T, VEC>(reinterpret_cast<const T*>(a.dA2) + off, g2);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) g[k] = to_f(from_f<T>(g[k] + g2[k]));
+      }
       if (a.a) {
         float av[VEC];
         load_vec<T, VEC>(reinterpret_cast<const T*>(a.a) + off, av);
@@ -411,6 +426,12 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a) {
     const size_t off = size_t(i) * VEC;
     float g[VEC], yv[VEC], o[VEC];
     load_grad<T, VEC>(a.dA, a.dA_f32, off, g);
+    if (a.dA2) {
+      float g2[VEC];
+      load_vec<T, VEC>(reinterpret_cast<const T*>(a.dA2) + off, g2);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) g[k] = to_f(from_f<T>(g[k] + g2[k]));
+    }
     if (a.a) {
       float av[VEC];
       load_vec<T, VEC>(reinterpret_cast<const T*>(a.a) + off, av);
@@ -491,6 +512,13 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_coop_kernel(const BnBwdArgs a, 
       rg[e] = load_raw<T, VEC>(dA + off);
       ry[e] = load_raw<T, VEC>(y1 + off);
       if (y2) rz[e] = load_raw<T, VEC>(y2 + off);
+      if (a.dA2) {                                   // the gradient arrives in two parts (main branch, shortcut branch)
+        const RawVec<T, VEC> r2 = load_raw<T, VEC>(reinterpret_cast<const T*>(a.dA2) + off);
+        const T* g2 = reinterpret_cast<const T*>(&r2.r);
+        T* ge = reinterpret_cast<T*>(&rg[e].r);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) ge[k] = from_f<T>(to_f(ge[k]) + to_f(g2[k]));
+      }
       if (am) {
         const RawVec<T, VEC> ra = load_raw<T, VEC>(am + off);
         const T* ae = reinterpret_cast<const T*>(&ra.r);
@@ -601,6 +629,219 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_coop_kernel(const BnBwdArgs a, 
   }
 }
 
+// BatchNorm backward in ONE launch with a SMALL footprint (bf16 storage): a persistent grid of at most two CTAs per SM
+// walks its rows twice -- pass 1 reduces the three per-channel sums (S1 is accumulated as sum g*y and centred at the end:
+// S1 = rstd * (sum g*y - mean * S0)) into the fp64 accumulators, a grid-wide barrier follows, pass 2 re-reads the same
+// rows (they are L2-resident: the whole working set of a layer is a few MB of the 126 MB L2; the big decoder tensors
+// re-stream, as the two-kernel path did) and writes dY (dY2).  Unlike bn_bwd_coop_kernel nothing is carried in registers
+// across the barrier: ~48 registers and 7 KB of shared memory per CTA, so the grid is co-resident BESIDE the weight-gradient
+// kernels of the auxiliary stream and the tail of the previous kernel (the register-resident version needs a whole SM's
+// register file per CTA pair and, measured, waited 8-15 us for the SMs to drain: profiles/r02_bn_bwd.md).
+__global__ void __launch_bounds__(256, 4) bn_bwd_sweep_kernel(const BnBwdArgs a) {
+  pdl_wait();
+  pdl_trigger();
+  typedef __nv_bfloat16 T;
+  constexpr int VEC = 8;
+  __shared__ float red[3][256];                        // [sum][channel], C <= 256 (the warps add up with shared atomics)
+  __shared__ float coef[2][3][256];                    // per branch: scale, c1 (mean of g), c2 (mean of g * xhat)
+  __shared__ float mr[2][2][256];                      // per branch: mean, rstd
+  const int CV = a.C / VEC, RPI = 256 / CV;
+  const int tid = threadIdx.x;
+  const int cv = tid % CV, rsub = tid / CV, c0 = cv * VEC;
+  const T* dA = reinterpret_cast<const T*>(a.dA);
+  const T* dA2 = reinterpret_cast<const T*>(a.dA2);
+  const T* am = reinterpret_cast<const T*>(a.a);
+  const T* y1 = reinterpret_cast<const T*>(a.y);
+  const T* y2 = reinterpret_cast<const T*>(a.y2);
+  for (int c = tid; c < a.C; c += 256) {
+    mr[0][0][c] = a.stat[c]; mr[0][1][c] = a.stat[a.C + c];
+    if (y2) { mr[1][0][c] = a.stat2[c]; mr[1][1][c] = a.stat2[a.C + c]; }
+    red[0][c] = 0.f; red[1][c] = 0.f; red[2][c] = 0.f;
+  }
+  __syncthreads();
+  const long long rstride = (long long)gridDim.x * RPI;
+  const long long r0 = (long long)blockIdx.x * RPI + rsub;
+  // g = (dA [+ dA2]) * [a > 0], rounded to the storage type once (what the accumulate-in-place path stored)
+  auto load_g = [&](size_t off, float (&g)[VEC]) {
+    load_vec<T, VEC>(dA + off, g);
+    if (dA2) {
+      float g2[VEC];
+      load_vec<T, VEC>(dA2 + off, g2);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) g[k] = to_f(from_f<T>(g[k] + g2[k]));
+    }
+    if (am) {
+      float av[VEC];
+      load_vec<T, VEC>(am + off, av);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) g[k] = av[k] > 0.f ? g[k] : 0.f;
+    }
+  };
+  // ---- pass 1 ----
+  float s0[VEC], s1[VEC], s2[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) { s0[k] = s1[k] = s2[k] = 0.f; }
+#pragma unroll 1
+  for (long long r = r0; r < a.rows; r += rstride) {
+    const size_t off = size_t(r) * a.C + c0;
+    float g[VEC], yv[VEC];
+    load_g(off, g);
+    load_vec<T, VEC>(y1 + off, yv);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) { s0[k] += g[k]; s1[k] = fmaf(g[k], yv[k], s1[k]); }
+    if (y2) {
+      load_vec<T, VEC>(y2 + off, yv);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) s2[k] = fmaf(g[k], yv[k], s2[k]);
+    }
+  }
+  for (int d = CV; d < 32; d <<= 1) {
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      s0[k] += __shfl_xor_sync(0xffffffffu, s0[k], d);
+      s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], d);
+      s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], d);
+    }
+  }
+  if ((tid & 31) < CV) {                               // lanes < CV of every warp hold the warp's sums of their channel vector
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      atomicAdd(&red[0][c0 + k], s0[k]); atomicAdd(&red[1][c0 + k], s1[k]);
+      if (y2) atomicAdd(&red[2][c0 + k], s2[k]);
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < 3 * a.C; e += 256) {
+    const int which = e / a.C, c = e - which * a.C;
+    float sum = red[which][c];
+    // centre the raw moments: sum g * xhat = rstd * (sum g*y - mean * sum g), per CTA in fp32 (|mean * S0| ~ |sum g*y|
+    // only when the channel mean dominates its spread; the fp64 accumulation across CTAs keeps the rest exact)
+    if (which == 1 || (which == 2 && y2)) sum = mr[which - 1][1][c] * (sum - mr[which - 1][0][c] * red[0][c]);
+    if (which < 2 || y2) atomicAdd(a.acc + (size_t)(blockIdx.x % kBnAccCopies) * 3 * a.C + which * a.C + c, (double)sum);
+  }
+  // ---- grid-wide barrier (the grid is co-resident: at most coop_max_ctas() CTAs) ----
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    atomicAdd(a.counter, 1u);
+    while (ld_acquire_u32(a.counter) < gridDim.x) { __nanosleep(20); }
+  }
+  __syncthreads();
+  // ---- coefficients ----
+  const double im = 1.0 / (double)a.rows;
+  for (int c = tid; c < a.C; c += 256) {
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < kBnAccCopies; ++k) {
+      const double* ak = a.acc + (size_t)k * 3 * a.C;
+      t0 += ld_cg_f64(ak + c); t1 += ld_cg_f64(ak + a.C + c);
+      if (y2) t2 += ld_cg_f64(ak + 2 * a.C + c);
+    }
+    coef[0][0][c] = a.gamma[c] * mr[0][1][c]; coef[0][1][c] = (float)(t0 * im); coef[0][2][c] = (float)(t1 * im);
+    if (y2) { coef[1][0][c] = a.gamma2[c] * mr[1][1][c]; coef[1][1][c] = (float)(t0 * im); coef[1][2][c] = (float)(t2 * im); }
+    if (blockIdx.x == 0) {
+      a.g_beta[c] = (float)t0; a.g_gamma[c] = (float)t1;
+      if (y2) { a.g_beta2[c] = (float)t0; a.g_gamma2[c] = (float)t2; }
+    }
+  }
+  __syncthreads();
+  // ---- pass 2 ----
+#pragma unroll 1
+  for (long long r = r0; r < a.rows; r += rstride) {
+    const size_t off = size_t(r) * a.C + c0;
+    float g[VEC], yv[VEC], o[VEC];
+    load_g(off, g);
+    load_vec<T, VEC>(y1 + off, yv);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      const int c = c0 + k;
+      const float xh = (yv[k] - mr[0][0][c]) * mr[0][1][c];
+      o[k] = coef[0][0][c] * (g[k] - coef[0][1][c] - xh * coef[0][2][c]);
+    }
+    store_vec<T, VEC>(reinterpret_cast<T*>(a.dY) + off, o);
+    if (y2) {
+      load_vec<T, VEC>(y2 + off, yv);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        const int c = c0 + k;
+        const float xh = (yv[k] - mr[1][0][c]) * mr[1][1][c];
+        o[k] = coef[1][0][c] * (g[k] - coef[1][1][c] - xh * coef[1][2][c]);
+      }
+      store_vec<T, VEC>(reinterpret_cast<T*>(a.dY2) + off, o);
+    }
+  }
+}
+
+// BatchNorm backward of a ONE-channel tensor (the decoder's output BatchNorm, model.py:173,193) whose incoming gradient is
+// fp32 (d recon from the loss): same scheme as bn_bwd_coop_kernel -- every thread keeps its (at most kCoopE) groups of 4
+// gradients and pre-activations in registers across the grid barrier -- for rows up to grid * 256 * 4 * kCoopE.
+__global__ void __launch_bounds__(256, 2) bn_bwd_c1_coop_kernel(const BnBwdArgs a, int E) {
+  pdl_wait();
+  pdl_trigger();
+  typedef __nv_bfloat16 T;
+  __shared__ float red[2][8];
+  __shared__ float coef[3];
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+  const float4* dA = reinterpret_cast<const float4*>(a.dA);
+  const uint2* y = reinterpret_cast<const uint2*>(a.y);
+  const long long nq = a.rows >> 2;                   // groups of 4 (rows % 4 == 0 guaranteed by the launcher)
+  const float mean = a.stat[0], rstd = a.stat[1];
+  float4 g[kCoopE];
+  float xh[kCoopE][4];
+  float s0 = 0.f, s1 = 0.f;
+  const long long q00 = (long long)blockIdx.x * 256 + tid, qstride = (long long)gridDim.x * 256;
+#pragma unroll
+  for (int e = 0; e < kCoopE; ++e) {
+    const long long q = q00 + e * qstride;
+    if (e < E && q < nq) {
+      g[e] = __ldg(dA + q);
+      const uint2 yr = __ldg(y + q);
+      xh[e][0] = (__uint_as_float(yr.x << 16) - mean) * rstd; xh[e][1] = (__uint_as_float(yr.x & 0xffff0000u) - mean) * rstd;
+      xh[e][2] = (__uint_as_float(yr.y << 16) - mean) * rstd; xh[e][3] = (__uint_as_float(yr.y & 0xffff0000u) - mean) * rstd;
+      s0 += (g[e].x + g[e].y) + (g[e].z + g[e].w);
+      s1 = fmaf(g[e].x, xh[e][0], fmaf(g[e].y, xh[e][1], fmaf(g[e].z, xh[e][2], fmaf(g[e].w, xh[e][3], s1))));
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, d); s1 += __shfl_xor_sync(0xffffffffu, s1, d); }
+  if (lane == 0) { red[0][wrp] = s0; red[1][wrp] = s1; }
+  __syncthreads();
+  if (tid < 2) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[tid][w];
+    atomicAdd(a.acc + (size_t)(blockIdx.x % kBnAccCopies) * 3 + tid, (double)t);
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    atomicAdd(a.counter, 1u);
+    while (ld_acquire_u32(a.counter) < gridDim.x) { __nanosleep(32); }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < kBnAccCopies; ++k) { t0 += ld_cg_f64(a.acc + (size_t)k * 3); t1 += ld_cg_f64(a.acc + (size_t)k * 3 + 1); }
+    const double im = 1.0 / (double)a.rows;
+    coef[0] = a.gamma[0] * rstd; coef[1] = (float)(t0 * im); coef[2] = (float)(t1 * im);
+    if (blockIdx.x == 0) { a.g_beta[0] = (float)t0; a.g_gamma[0] = (float)t1; }
+  }
+  __syncthreads();
+  const float sc = coef[0], c1 = coef[1], c2 = coef[2];
+  uint2* dY = reinterpret_cast<uint2*>(a.dY);
+#pragma unroll
+  for (int e = 0; e < kCoopE; ++e) {
+    const long long q = q00 + e * qstride;
+    if (e < E && q < nq) {
+      const float o0 = sc * (g[e].x - c1 - xh[e][0] * c2), o1 = sc * (g[e].y - c1 - xh[e][1] * c2);
+      const float o2 = sc * (g[e].z - c1 - xh[e][2] * c2), o3 = sc * (g[e].w - c1 - xh[e][3] * c2);
+      __nv_bfloat162 lo = __floats2bfloat162_rn(o0, o1), hi = __floats2bfloat162_rn(o2, o3);
+      dY[q] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                            long long total, int C, int HW) {
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
@@ -668,19 +909,37 @@ void launch_heads_bwd(const HeadsBwdArgs& a, cudaStream_t st) {
   // the weight gradients of the two heads are a separate launch (launch_heads_wgrad): the caller decides the stream
 }
 
-// co-resident CTAs of bn_bwd_coop_kernel on the current device (cached per device)
+// co-resident CTAs of the grid-barrier BatchNorm-backward kernels on the current device (cached per device; the smaller of
+// the two kernels' occupancies)
 static int coop_max_ctas() {
   static std::atomic<int> cached[64];
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
   int v = cached[dev].load();
   if (v > 0) return v;
-  int per_sm = 0, sms = 0;
+  int per_sm = 0, per_sm1 = 0, sms = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm1, bn_bwd_c1_coop_kernel, 256, 0) != cudaSuccess) { cudaGetLastError(); return 0; }
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_bwd_coop_kernel, 256, 0) != cudaSuccess ||
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) { cudaGetLastError(); return 0; }
-  v = std::min(per_sm, 2) * sms;
+  v = std::min(std::min(per_sm, per_sm1), 2) * sms;
   static const int cap = [] { const char* e = getenv("MMVAE_COOP_CTAS"); return e ? atoi(e) : 0; }();   // A/B runs
   if (cap > 0) v = std::min(v, cap);
+  cached[dev].store(v);
+  return v;
+}
+
+// co-resident CTAs of bn_bwd_sweep_kernel (two per SM at most; cached per device)
+static int sweep_max_ctas() {
+  static std::atomic<int> cached[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  int v = cached[dev].load();
+  if (v > 0) return v;
+  int per_sm = 0, sms = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_bwd_sweep_kernel, 256, 0) != cudaSuccess ||
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+  static const int per = [] { const char* e = getenv("MMVAE_BN_SWEEP_PER_SM"); return e ? atoi(e) : 2; }();
+  v = std::min(per_sm, per) * sms;
   cached[dev].store(v);
   return v;
 }
@@ -692,7 +951,20 @@ void launch_bn_bwd(const BnBwdArgs& a, cudaStream_t st) {
     // one cooperative launch when every thread's share fits its registers: half a register file per SM for two CTAs,
     // so it stays co-resident with the weight-gradient kernels of the auxiliary stream
     static const bool coop_off = getenv("MMVAE_NO_COOP_BN") != nullptr;
+    static const bool sweep_off = getenv("MMVAE_NO_BN_SWEEP") != nullptr;       // A/B: the register-resident kernel below
+    static const long long sweep_max = [] { const char* e = getenv("MMVAE_BN_SWEEP_MAX_MB"); return (long long)(e ? atoi(e) : 1 << 20) << 20; }();
     const int CV = a.C / 8;
+    if (!coop_off && !sweep_off && a.acc && !a.reduced && !a.dA_f32 && a.C % 8 == 0 && CV >= 1 && CV <= 32 && 256 % CV == 0 &&
+        a.rows * a.C * 2 <= sweep_max) {
+      const int RPI = 256 / CV;
+      const long long row_groups = (a.rows + RPI - 1) / RPI;
+      const int grid = (int)std::min<long long>(sweep_max_ctas(), row_groups);
+      if (grid > 0) {
+        count_launch();
+        launch_pdl(bn_bwd_sweep_kernel, grid, 256, 0, st, a);
+        return;
+      }
+    }
     if (!coop_off && a.acc && !a.reduced && !a.dA_f32 && a.C % 8 == 0 && CV >= 1 && CV <= 32 && 256 % CV == 0) {
       const int RPI = 256 / CV;
       const long long row_groups = (a.rows + RPI - 1) / RPI;
@@ -706,6 +978,20 @@ void launch_bn_bwd(const BnBwdArgs& a, cudaStream_t st) {
       if (E <= kCoopE) {
         count_launch();
         launch_pdl(bn_bwd_coop_kernel, grid, 256, 0, st, a, E);
+        return;
+      }
+    }
+  }
+  if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+    // the one-channel output BatchNorm with an fp32 incoming gradient: its own grid-barrier kernel
+    static const bool coop_off = getenv("MMVAE_NO_COOP_BN") != nullptr;
+    if (!coop_off && a.acc && !a.reduced && a.dA_f32 && a.C == 1 && !a.a && !a.y2 && (a.rows & 3) == 0) {
+      const long long groups = ((a.rows >> 2) + 255) / 256;
+      const int grid = (int)std::min<long long>(coop_max_ctas(), groups);
+      const int E = grid > 0 ? (int)((groups + grid - 1) / grid) : kCoopE + 1;
+      if (E <= kCoopE) {
+        count_launch();
+        launch_pdl(bn_bwd_c1_coop_kernel, grid, 256, 0, st, a, E);
         return;
       }
     }

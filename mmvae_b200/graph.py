@@ -42,6 +42,7 @@ class GraphedTrainStep:
         self.x = torch.zeros(batch_size, model.in_channels, s, s, dtype=torch.float32, device=dev)
         self.target = (torch.zeros(batch_size, s, s, dtype=torch.int64, device=dev) if categorical else self.x)
         self.args = args if args is not None else types.SimpleNamespace(data_ratio_of_labels=None)
+        self._one = torch.ones((), dtype=torch.float32, device=dev)      # d loss / d loss: no fill kernel inside the graph
         self.kl_weight_dev = torch.tensor(float(model.kl if kl_weight is None else kl_weight), dtype=torch.float32, device=dev)
         self.optimizer = optimizer
         self._own_target = categorical
@@ -126,7 +127,7 @@ class GraphedTrainStep:
                           out=self.x, out_target=self.target if self._own_target else None)
         mu, logvar, enc, recon = m(self.x)
         loss, pxz, kl, mmd = m.loss(self.target, mu, logvar, enc, recon, self.x.device, self.args)
-        loss.backward()
+        loss.backward(self._one)
         if self.optimizer is not None:
             self.optimizer.step(m.last_flat_grad)       # optimizer.step(), main.py:399
         self.mu, self.logvar, self.encoding, self.reconstruction = mu, logvar, enc, recon

@@ -357,8 +357,7 @@ class VAE(nn.Module):
             check(lib.mmvae_forward(byref(desc), _ptr(x), _ptr(self._arena), _ptr(self._bn_arena), _ptr(self._counters),
                                     _ptr(eps), seed, offset, _ptr(eps_out), _ptr(rng), _ptr(ws), ws.numel(), _ptr(mu),
                                     _ptr(logvar), _ptr(enc), _ptr(recon), _stream(dev)), "mmvae_forward")
-            if rng is not None:
-                rng[1] += (n * z + 3) // 4
+            # with a device-resident generator state the call advanced rng[1] itself (its heads kernel)
         self.last_eps = eps_out if eps_out is not None else eps
         return mu, logvar, enc, recon, [desc, ws, self._gen, False]
 
