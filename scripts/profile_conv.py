@@ -15,6 +15,7 @@ n = int(os.environ.get("N", "256"))
 model = M.VAE(1, 32, decoder_out_channels=1, pixelcnn_out_channels=0, z_dimension=64, pixelcnn=False, only_pixelcnn=False,
               sigma_decoder=0.1, input_image_size=64, precision="bf16").cuda().train()
 model.defer_metrics = True
+model.mmd_diagnostic = False
 x = D.prepare_input(D.synthetic_labels(n, 64).cuda())
 largs = types.SimpleNamespace(data_ratio_of_labels=None)
 for _ in range(2):

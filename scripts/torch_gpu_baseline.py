@@ -83,7 +83,7 @@ class NotebookVAE(nn.Module):                    # vae-kl.ipynb:122-166
         return pxz + kl
 
 
-def time_model(model, x, y, steps, autocast):
+def time_model(model, x, y, steps, autocast, graph=False):
     params = list(model.parameters())
 
     def one():
@@ -93,6 +93,21 @@ def time_model(model, x, y, steps, autocast):
             loss = model.step(x, y)
         loss.backward()
 
+    if graph:
+        # the same step captured once and replayed (no host launch overhead): the fair comparison with our graph replay
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                one()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        for p in params:
+            p.grad = None
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            one()
+        one = g.replay                                 # noqa: F811
     for _ in range(3):
         one()
     torch.cuda.synchronize()
@@ -120,7 +135,9 @@ def main():
                               ("vae-kl.ipynb VAE, 512 x 128x128", lambda: NotebookVAE(), 512, 128)):
         x = torch.randn(n, 1, size, size, device=dev, generator=g)
         y = torch.randint(0, 256, (n, size, size), device=dev, generator=g)
-        for mode, autocast, cl in (("bf16 autocast, channels_last", True, True), ("fp32 (TF32 allowed)", False, False)):
+        for mode, autocast, cl, graph in (("bf16 autocast, channels_last", True, True, False),
+                                          ("bf16 autocast, channels_last, CUDA-graph replay", True, True, True),
+                                          ("fp32 (TF32 allowed)", False, False, False)):
             torch.manual_seed(0)
             m = mk().to(dev).train()
             xx = x
@@ -128,7 +145,7 @@ def main():
                 m = m.to(memory_format=torch.channels_last)
                 xx = x.contiguous(memory_format=torch.channels_last)
             try:
-                ms = time_model(m, xx, y, args.steps, autocast)
+                ms = time_model(m, xx, y, args.steps, autocast, graph)
                 out[f"{name}; {mode}"] = {"ms_per_step": ms, "frames_per_s": n / ms * 1e3}
             except RuntimeError as e:                    # e.g. out of memory for the fp32 logits
                 out[f"{name}; {mode}"] = {"error": str(e).split("\n")[0][:160]}
