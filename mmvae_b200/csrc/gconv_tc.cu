@@ -102,6 +102,13 @@ __global__ void __launch_bounds__(kTcThreads, kBwd ? 2 : 3) gconv_tc_kernel(cons
   // csz > 1: the CTAs of a cluster share one pixel tile (one channel tile each) and multicast their slice of every A box
   // to all of them, so a ring slot is free only when the MMA threads of ALL csz CTAs have released it
   const int csz = p.tc_csz > 1 ? p.tc_csz : 1;
+  // Split-K over a thread-block cluster (deep-K layers on few pixel tiles: launch_gconv_tc): the ksplit CTAs of a cluster
+  // own ONE tile and a contiguous range of its k-chunks each; the non-leaders hand their fp32 partial accumulators to the
+  // leader's shared memory (DSMEM stores), one cluster barrier, and the leader's epilogue adds them to its own.
+  const int ksplit = p.tc_ksplit > 1 ? p.tc_ksplit : 1;
+  const uint32_t krank = ksplit > 1 ? cluster_ctarank() : 0u;
+  const int t_begin = ksplit > 1 ? (int)(blockIdx.x / (unsigned)ksplit) : (int)blockIdx.x;
+  const int t_step = ksplit > 1 ? p.total_tiles : (int)gridDim.x;          // one tile per cluster
   if (tid == 0) {
     if (p.use_tma) prefetch_tensormap(&p.tmap_a);
     for (int s = 0; s < S; ++s) {
@@ -145,24 +152,26 @@ __global__ void __launch_bounds__(kTcThreads, kBwd ? 2 : 3) gconv_tc_kernel(cons
         const int mc_n = (int)crank * p.tc_mc_imgs;
         int stage = 0;
         uint32_t ephase = 1;                    // the first lap over the ring passes immediately
-        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        for (int t = t_begin; t < p.total_tiles; t += t_step) {
           int mt, vi, nt;
           decode_tile(p, t, mt, vi, nt);
           const GVar& var = p.var[vi];
           const int K = var.ntaps * p.Ci;
           const int nchunks = (K + 63) >> 6;
+          const int kc0 = ksplit > 1 ? ((int)krank * nchunks) / ksplit : 0;
+          const int kc1 = ksplit > 1 ? (((int)krank + 1) * nchunks) / ksplit : nchunks;
           // origin of the tile's pixel box in the gather grid: m0 -> (n0, i0, 0)
           int n0, i0, j0, rem;
           p.fd_hw.divmod(mt * 128, n0, rem);
           p.fd_wg.divmod(rem, i0, j0);
+          const size_t wstep = (size_t)p.co_pad * 128;
           const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(p.wpack) + (size_t)vi * p.wpack_var_stride +
-                                      (size_t)((nt * BN) >> 3) * 1024;
+                                      (size_t)((nt * BN) >> 3) * 1024 + (size_t)kc0 * wstep;
           if (pw == 0 && lane == 0 && t == (int)blockIdx.x) MMVAE_TRACE(p, 16);
           const int xb = j0 * p.is, yb = i0 * p.is;
           const uint32_t* tab = tma_tab + ((vi * p.tc_maxchunks) << sub_shift);
-          const size_t wstep = (size_t)p.co_pad * 128;
           const int nsub_full = 1 << sub_shift, nsub_last = (K - (nchunks - 1) * 64 + kb - 1) >> kb_log2;
-          for (int kc = 0; kc < nchunks; ++kc, wsrc += wstep) {
+          for (int kc = kc0; kc < kc1; ++kc, wsrc += wstep) {
             if ((stage & pmask) == pw) {
               mbar_wait(smem_u32(&empty[stage]), ephase);
               const uint32_t bar = smem_u32(&full[stage]);
@@ -290,28 +299,30 @@ __global__ void __launch_bounds__(kTcThreads, kBwd ? 2 : 3) gconv_tc_kernel(cons
       int stage = 0;
       uint32_t fphase = 0;
       int i = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
+      for (int t = t_begin; t < p.total_tiles; t += t_step, ++i) {
         int mt, vi, nt;
         decode_tile(p, t, mt, vi, nt);
         const int K = p.var[vi].ntaps * p.Ci;
         const int nchunks = (K + 63) >> 6;
+        const int kc0 = ksplit > 1 ? ((int)krank * nchunks) / ksplit : 0;
+        const int kc1 = ksplit > 1 ? (((int)krank + 1) * nchunks) / ksplit : nchunks;
         const int nk_last = (K - (nchunks - 1) * 64 + 15) >> 4;           // MMAs of the last k-chunk (1..4)
         const int buf = i & 1;
         mbar_wait(smem_u32(&tempty[buf]), (uint32_t)(((i >> 1) & 1) ^ 1));   // epilogue drained this buffer
         tc_fence_after();
         const uint32_t dtm = tmem + (uint32_t)(buf * BN);
-        for (int kc = 0; kc < nchunks; ++kc) {
+        for (int kc = kc0; kc < kc1; ++kc) {
           mbar_wait(fbar, fphase);
           tc_fence_after();
           if (elect_one()) {
             if (kc + 1 < nchunks) {
 #pragma unroll
               for (int q = 0; q < 4; ++q)
-                mma_bf16(dtm, da + aoff[q], db + (uint64_t)(q * 2), idesc, (kc | q) != 0);
+                mma_bf16(dtm, da + aoff[q], db + (uint64_t)(q * 2), idesc, ((kc - kc0) | q) != 0);
             } else {
 #pragma unroll
               for (int q = 0; q < 4; ++q)
-                if (q < nk_last) mma_bf16(dtm, da + aoff[q], db + (uint64_t)(q * 2), idesc, (kc | q) != 0);
+                if (q < nk_last) mma_bf16(dtm, da + aoff[q], db + (uint64_t)(q * 2), idesc, ((kc - kc0) | q) != 0);
             }
             if (csz > 1) mma_commit_mc(ebar, cmask);
             else mma_commit(ebar);
@@ -334,8 +345,10 @@ __global__ void __launch_bounds__(kTcThreads, kBwd ? 2 : 3) gconv_tc_kernel(cons
     const int q = warp & 3;                              // TMEM lane quarter this warp may read
     const int r = q * 32 + lane;                         // tile row == TMEM lane
     __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
-    const bool stats = p.bn.acc != nullptr;
+    const bool stats = p.bn.acc != nullptr && krank == 0;  // split-K: the leader's epilogue sees the complete sums
     const bool merge = p.tc_merge != 0;                  // one channel tile: sums can live in registers over all tiles
+    // split-K partials in the LEADER's shared memory, behind the operand ring: [peer - 1][column][row] fp32
+    const uint32_t part_base = ring + (uint32_t)S * (uint32_t)(kStageA + stageB);
     const int lane_col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
     float run_s[NR], run_q[NR];
 #pragma unroll
@@ -345,13 +358,31 @@ __global__ void __launch_bounds__(kTcThreads, kBwd ? 2 : 3) gconv_tc_kernel(cons
     for (int e = 0; e < (kBwd ? 3 * NG : 1); ++e) run_b[e] = 0.f;
     const bool bwd2 = kBwd && p.bb.y2 != nullptr;
     int i = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
+    for (int t = t_begin; t < p.total_tiles; t += t_step, ++i) {
       int mt, vi, nt;
       decode_tile(p, t, mt, vi, nt);
       const GVar& var = p.var[vi];
       const int m0 = mt * 128, n0 = nt * BN;
       const int buf = i & 1;
       const int m = m0 + r;
+      if (ksplit > 1 && krank != 0) {
+        // non-leader: this CTA's partial accumulator -> the leader's shared memory, then the cluster barrier
+        mbar_wait(smem_u32(&tfull[buf]), (uint32_t)((i >> 1) & 1));
+        tc_fence_after();
+        const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
+        const uint32_t dst0 = dsmem_addr(part_base + (((krank - 1u) * (uint32_t)BN) * 128u + (uint32_t)r) * 4u, 0u);
+#pragma unroll
+        for (int gq = 0; gq < NG; ++gq) {
+          uint32_t rv[16];
+          tmem_ld16_issue(tl + (uint32_t)(gq * 16), rv);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 16; ++e) st_dsmem_u32(dst0 + (uint32_t)((gq * 16 + e) * 128 * 4), rv[e]);
+        }
+        tc_fence_before();
+        cluster_sync_all();
+        break;
+      }
       bool valid = m < p.M;
       size_t obase = 0;
       if (valid) {
@@ -365,6 +396,7 @@ __global__ void __launch_bounds__(kTcThreads, kBwd ? 2 : 3) gconv_tc_kernel(cons
       const bool fuse_v = kBwd && ((p.bb.var_mask >> vi) & 1);       // this tile's pixels are final here: mask + reduce
       mbar_wait(smem_u32(&tfull[buf]), (uint32_t)((i >> 1) & 1));
       tc_fence_after();
+      if (ksplit > 1) cluster_sync_all();                // the peers' partials have landed in this CTA's shared memory
       if (i == 0 && tid == 160) MMVAE_TRACE(p, 8);
       const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
       uint32_t rnext[16];                                // the next 16-column group is in flight while this one is worked on
@@ -377,6 +409,13 @@ __global__ void __launch_bounds__(kTcThreads, kBwd ? 2 : 3) gconv_tc_kernel(cons
 #pragma unroll
         for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(rnext[e]);
         if (gq + 1 < NG) tmem_ld16_issue(tlane + (uint32_t)(c0 + 16), rnext);
+        if (ksplit > 1) {
+          for (int pe = 0; pe < ksplit - 1; ++pe) {
+            const uint32_t src = part_base + (uint32_t)(((pe * BN + c0) * 128 + r) * 4);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] += ld_smem_f32(src + (uint32_t)(e * 128 * 4));
+          }
+        }
         const int co0 = n0 + c0;
         if (p.bias) {
 #pragma unroll
@@ -530,6 +569,7 @@ __global__ void __launch_bounds__(kTcThreads, kBwd ? 2 : 3) gconv_tc_kernel(cons
     }
   }
   if (tid == 160) MMVAE_TRACE(p, 11);
+  if (ksplit > 1 && warp <= 4) cluster_sync_all();       // producers / MMA warp: their share of the split-K cluster barrier
   tc_fence_before();
   __syncthreads();
   if (warp == 4) {
@@ -956,8 +996,31 @@ StatLayout launch_gconv_tc(const GConvParams& p0, cudaStream_t st) {
       make_tmap(p.tmap_a, p.in, p.N, p.Hi, p.Wi, p.Ci, p.tc_kb, bw, bh, bnb, p.is);
     }
   }
-  const size_t smem = (size_t)stages * stage_bytes + 1024;
   const bool bwd = p.bb.acc != nullptr;
+  // Split-K over a cluster: layers whose tiles do not fill the machine and whose K is deep (layer3/4, uplayer1/2 and their
+  // data gradients).  The k-chunks of a tile are dealt to 2 / 4 / 8 CTAs of a cluster; every variant keeps >= 4 chunks per CTA.
+  p.tc_ksplit = 1;
+  {
+    // OFF by default (MMVAE_KSPLIT_MAX=4 turns it on; profiles/r02_split_k.md): the k-loop of encoder.layer4.0.conv2
+    // shrinks from 7.4 to 3 us, but the DSMEM hand-over + cluster barrier cost 2.5 us and the fixed parts of the launch
+    // (prologue, epilogue, statistics) do not shrink: 10.3 vs 11.3 us on that layer, 0.6-1.6 us SLOWER on the 18-chunk layers.
+    static const int ks_max = [] { const char* e = getenv("MMVAE_KSPLIT_MAX"); return e ? atoi(e) : 1; }();
+    int minchunks = 1 << 30;
+    for (int v = 0; v < p.nvar; ++v) minchunks = min(minchunks, (p.var[v].ntaps * p.Ci + 63) / 64);
+    if (p.use_tma && p.tc_csz == 1 && !bwd && !(p.act || p.dact) && p.total_tiles <= 148) {
+      int ks = 1;
+      while (ks * 2 <= ks_max && p.total_tiles * ks * 2 <= 2 * 148 && minchunks / (ks * 2) >= 4) ks *= 2;
+      if (ks > 1) {
+        // ring + partials of one CTA must leave room for a second CTA on the SM when the grid exceeds one per SM
+        const int per_sm_k = p.total_tiles * ks > 148 ? 2 : 1;
+        const int budget = (per_sm_k == 2 ? 110 : 198) * 1024 - (ks - 1) * bn * 128 * 4;
+        const int chunks_per_cta = (maxchunks + ks - 1) / ks;
+        const int st2 = min(min(kMaxStages, chunks_per_cta), budget / stage_bytes);
+        if (st2 >= 2) { p.tc_ksplit = ks; stages = st2; p.tc_stages = stages; }
+      }
+    }
+  }
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + (size_t)(p.tc_ksplit - 1) * bn * 128 * 4;
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(gconv_tc_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -977,11 +1040,13 @@ StatLayout launch_gconv_tc(const GConvParams& p0, cudaStream_t st) {
   const int per_sm = min(gconv_per_sm(), bwd ? 2 : (smem <= 72 * 1024 ? 3 : 2));
   int grid = min(p.total_tiles, per_sm * 148);
   if (p.tc_csz > 1) grid -= grid % p.tc_csz;     // whole clusters; total_tiles is a multiple of n_tiles == csz
+  if (p.tc_ksplit > 1) grid = p.total_tiles * p.tc_ksplit;      // one tile per cluster
   p.trace = debug_trace_buffer();
   { static int fl = [] { const char* e = getenv("MMVAE_TC_FLAGS"); return e ? atoi(e) : 0; }(); p.tc_flags = fl; }
   count_launch();
 #define LAUNCH_GCONV(...) \
-  (p.tc_csz > 1 ? launch_pdl_cluster(__VA_ARGS__, grid, kTcThreads, smem, st, p.tc_csz, p) : launch_pdl(__VA_ARGS__, grid, kTcThreads, smem, st, p))
+  (p.tc_ksplit > 1 ? launch_pdl_cluster(__VA_ARGS__, grid, kTcThreads, smem, st, p.tc_ksplit, p) : \
+   p.tc_csz > 1 ? launch_pdl_cluster(__VA_ARGS__, grid, kTcThreads, smem, st, p.tc_csz, p) : launch_pdl(__VA_ARGS__, grid, kTcThreads, smem, st, p))
   if (p.act || p.dact) {
     switch (bn) {
       case 16: LAUNCH_GCONV(gconv_tc_kernel<16, false, true>); break;

@@ -165,6 +165,7 @@ struct GConvParams {
   // TMA multicast over a thread-block cluster: the tc_csz CTAs of a cluster hold the tc_csz channel tiles of ONE pixel
   // tile; each fetches 1/tc_csz of the A box (tc_mc_imgs images = tc_mc_bytes bytes of every sub-tile) for all of them
   int tc_csz, tc_mc_imgs, tc_mc_bytes;
+  int tc_ksplit;               // split-K: CTAs of a cluster sharing one tile (1 = off)
   unsigned long long* trace;   // debugging: [CTA][16] globaltimer stamps (mmvae_debug_set_trace), nullptr = off
   int tiles_m, n_tiles, total_tiles;
   FastDiv fd_wg, fd_hg, fd_ci, fd_hw, fd_ntiles, fd_nvar;
