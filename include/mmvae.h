@@ -195,11 +195,20 @@ int mmvae_loss_backward(const mmvae_loss_args* a, const float* recon, const void
 enum { MMVAE_BWD_DECODER = 1,      /* tail conv .. decoder stem: every decoder.* gradient          */
        MMVAE_BWD_ENC_DEEP = 2,     /* heads, encoder.layer4, encoder.layer3                        */
        MMVAE_BWD_ENC_SHALLOW = 4,  /* encoder.layer2, layer1, stem                                 */
-       MMVAE_BWD_ALL = 7 };
+       MMVAE_BWD_ALL = 7,
+       /* OR-ed into a single DECODER / ENC_DEEP phase: its weight gradients (enqueued on the library's auxiliary stream)
+        * are NOT joined into `stream` when the call returns, so the rest of the sweep does not wait for them; whoever
+        * consumes that phase's gradients first makes ITS stream wait with mmvae_aux_fence().  The ENC_SHALLOW phase
+        * always joins (everything the sweep forked is back on `stream` when it returns). */
+       MMVAE_BWD_DEFER_JOIN = 8 };
 int mmvae_backward(const mmvae_desc* d, const float* x, const float* params,
                    void* workspace, size_t workspace_bytes,
                    const float* d_mu, const float* d_logvar, const float* d_encoding, const float* d_recon,
                    float* grads, int32_t phases, void* stream);
+/* Make `stream` wait for everything this library has enqueued so far on its auxiliary streams of the current device
+ * (an event hand-over; nothing blocks on the host).  With MMVAE_BWD_DEFER_JOIN this is how a communication stream gets a
+ * phase's weight gradients without stalling the compute stream. */
+int mmvae_aux_fence(void* stream);
 /* [begin, end) float offsets of the gradient-arena range written by one phase. */
 int mmvae_backward_range(const mmvae_desc* d, int32_t phase, int64_t* begin, int64_t* end);
 

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(HERE, "libmmvae_b200.so")
 PREC_FP32, PREC_BF16 = 0, 1
 LOSS_GAUSSIAN, LOSS_CATEGORICAL = 0, 1
 BWD_DECODER, BWD_ENC_DEEP, BWD_ENC_SHALLOW, BWD_ALL = 1, 2, 4, 7
+BWD_DEFER_JOIN = 8
 FLAG_FORCE_SIMT = 1
 FLAG_DEFER_LOGITS = 2
 ARCH_RESNET, ARCH_NOTEBOOK = 0, 1
@@ -26,6 +27,7 @@ EXPORTS = [
     "mmvae_philox_normal", "mmvae_adam_step", "mmvae_prepare_input", "mmvae_launch_count",
     "mmvae_conv_entry", "mmvae_selftest_tc", "mmvae_bench_conv", "mmvae_debug_set_trace",
     "mmvae_nb_loss_backward", "mmvae_nb_bench_tail", "mmvae_mmd", "mmvae_mmd_scratch_bytes",
+    "mmvae_aux_fence",
 ]
 
 
@@ -81,6 +83,7 @@ def _load():
     lib.mmvae_mmd_scratch_bytes.argtypes = [c_int32]
     lib.mmvae_mmd_scratch_bytes.restype = c_size_t
     lib.mmvae_mmd.argtypes = [P, P, c_int32, c_int32, P, P, P]
+    lib.mmvae_aux_fence.argtypes = [P]
     lib.mmvae_prepare_input.argtypes = [P, c_int64, c_float, c_float, P, P, P]
     lib.mmvae_conv_entry.argtypes = [POINTER(Desc), c_int32, c_char_p, c_size_t, POINTER(c_int32 * 8)]
     lib.mmvae_selftest_tc.argtypes = [POINTER(Desc), P, P, c_size_t, P, P, P, c_int32, P]

@@ -720,7 +720,9 @@ struct Exec {
     cudaMemsetAsync(grads + b, 0, sizeof(float) * size_t(e - b), st);
   }
 
-  void backward(const float* d_mu, const float* d_lv, const float* d_enc, const float* d_recon, int phases) {
+  void backward(const float* d_mu, const float* d_lv, const float* d_enc, const float* d_recon, int phases_in) {
+    const bool defer_join = (phases_in & MMVAE_BWD_DEFER_JOIN) != 0;
+    const int phases = phases_in & MMVAE_BWD_ALL;
     if (phases & MMVAE_BWD_DECODER) {
       clear(MMVAE_BWD_DECODER);
       if (d_recon) {
@@ -749,7 +751,8 @@ struct Exec {
         side([&] { wgrad(s); });
         dgrad(s, 0);
       }
-      if (phases != MMVAE_BWD_ALL) join();     // a phase on its own hands complete gradients to the caller (all-reduce); the
+      if (phases != MMVAE_BWD_ALL && !defer_join) join();   // a phase on its own hands complete gradients to the caller (all-reduce)
+                                               // unless the caller fences its consumer itself (MMVAE_BWD_DEFER_JOIN); the
                                                // whole sweep in one call joins the auxiliary stream once, at the end
     }
     if (phases & MMVAE_BWD_ENC_DEEP) {
@@ -768,7 +771,7 @@ struct Exec {
       side([&] { launch_heads_wgrad(h.dheads, h.pooled, h.g_wmu, h.w_lv ? h.g_wlv : nullptr, h.N, h.z, h.C, st); });
       block_bwd(P.enc[3]);
       block_bwd(P.enc[2]);
-      if (phases != MMVAE_BWD_ALL) join();
+      if (phases != MMVAE_BWD_ALL && !defer_join) join();
     }
     if (phases & MMVAE_BWD_ENC_SHALLOW) {
       clear(MMVAE_BWD_ENC_SHALLOW);
@@ -777,6 +780,7 @@ struct Exec {
       const ConvT_& s = P.convs[P.stem];
       bn_bwd(at<T>(act(P.a_stem).goff), 0, P.a_stem, s, nullptr);
       wgrad(s);
+      forked = forked || (aux != nullptr);     // earlier phases may have left un-joined work on the auxiliary stream
       join();
     }
   }
@@ -971,7 +975,10 @@ int mmvae_backward(const mmvae_desc* d, const float* x, const float* params, voi
   MMVAE_COMMON_CHECKS();
   if (P.d.arch != MMVAE_ARCH_RESNET) return fail(MMVAE_ERR_BAD_DESC, "mmvae_backward: use mmvae_nb_loss_backward for the notebook variant");
   if (!x || !params || !grads) return fail(MMVAE_ERR_BAD_ARG, "x/params/grads must be non-NULL");
-  if (phases <= 0 || phases > MMVAE_BWD_ALL) return fail(MMVAE_ERR_BAD_ARG, "phases must be a non-empty MMVAE_BWD_* mask");
+  if ((phases & MMVAE_BWD_ALL) == 0 || phases > (MMVAE_BWD_ALL | MMVAE_BWD_DEFER_JOIN))
+    return fail(MMVAE_ERR_BAD_ARG, "phases must be a non-empty MMVAE_BWD_* mask");
+  if ((phases & MMVAE_BWD_DEFER_JOIN) && (phases & MMVAE_BWD_ALL) != MMVAE_BWD_DECODER && (phases & MMVAE_BWD_ALL) != MMVAE_BWD_ENC_DEEP)
+    return fail(MMVAE_ERR_BAD_ARG, "MMVAE_BWD_DEFER_JOIN goes with a single DECODER or ENC_DEEP phase");
   if (!d->training) return fail(MMVAE_ERR_BAD_DESC, "mmvae_backward needs a training-mode forward (batch statistics)");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (P.d.precision == MMVAE_PREC_FP32) {
@@ -1031,6 +1038,19 @@ int mmvae_nb_bench_tail(const mmvae_desc* d, int32_t which, const float* params,
   }
   if (!ok) return fail(MMVAE_ERR_CUDA, "TMA descriptor could not be encoded");
   return check_launches("mmvae_nb_bench_tail");
+}
+
+int mmvae_aux_fence(void* stream) {
+  if (int rc = check_device()) return rc;
+  AuxPool* p = aux_pool();
+  if (!p) return fail(MMVAE_ERR_CUDA, "auxiliary streams unavailable");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  for (cudaStream_t a : {p->s, p->s2}) {
+    cudaEvent_t e = p->ev[p->next]; p->next = (p->next + 1) & 31;
+    cudaEventRecord(e, a);
+    cudaStreamWaitEvent(st, e, 0);
+  }
+  return check_launches("mmvae_aux_fence");
 }
 
 int mmvae_backward_range(const mmvae_desc* d, int32_t phase, int64_t* begin, int64_t* end) {

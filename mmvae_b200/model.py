@@ -382,12 +382,18 @@ class VAE(nn.Module):
         grads = torch.empty(self._n_params, dtype=torch.float32, device=x.device)
         sync = self._grad_sync
         phases = (_lib.BWD_ALL,) if sync is None else (_lib.BWD_DECODER, _lib.BWD_ENC_DEEP, _lib.BWD_ENC_SHALLOW)
+        # a gradient exchange that fences its own stream on the auxiliary streams (GradSync on CUDA) lets the sweep go on
+        # without waiting for a phase's weight gradients
+        uses_aux = self._prec == _lib.PREC_BF16 and not (self.kernel_flags & _lib.FLAG_FORCE_SIMT)   # who forks auxiliary streams
+        defer = _lib.BWD_DEFER_JOIN if (uses_aux and getattr(sync, "fences_aux", False)) else 0
         for ph in phases:
             with torch.cuda.device(x.device):
+                flag = defer if ph in (_lib.BWD_DECODER, _lib.BWD_ENC_DEEP) else 0
                 check(lib.mmvae_backward(byref(desc), _ptr(x), _ptr(self._arena), _ptr(ws), ws.numel(), _ptr(d_mu),
-                                         _ptr(d_logvar), _ptr(d_enc), _ptr(d_recon), _ptr(grads), ph, _stream(x.device)),
-                      "mmvae_backward")
+                                         _ptr(d_logvar), _ptr(d_enc), _ptr(d_recon), _ptr(grads), ph | flag,
+                                         _stream(x.device)), "mmvae_backward")
             if sync is not None:
+                sync.fence_now = bool(defer) and ph in (_lib.BWD_DECODER, _lib.BWD_ENC_DEEP)
                 sync.phase_done(self, desc, grads, ph)
         if sync is not None:
             sync.finish()

@@ -29,6 +29,9 @@ class GradSync:
         self.comm_stream = None
         self._ranges = {}
         self.bytes_reduced = 0
+        # phase_done() makes the communication stream wait for the library's auxiliary streams itself (mmvae_aux_fence),
+        # so mmvae_backward need not join a phase's weight gradients into the compute stream (MMVAE_BWD_DEFER_JOIN)
+        self.fences_aux = torch.cuda.is_available()
 
     def ranges(self, desc):
         key = (desc.batch, desc.width, desc.z_dim, desc.image_size, desc.out_channels, desc.in_channels)
@@ -60,6 +63,9 @@ class GradSync:
         ev.record()                             # the phase's last kernel, on the compute stream
         with torch.cuda.stream(self.comm_stream):
             self.comm_stream.wait_event(ev)
+            if self.fences_aux and getattr(self, "fence_now", False):
+                import ctypes
+                _lib.check(_lib.lib.mmvae_aux_fence(ctypes.c_void_p(self.comm_stream.cuda_stream)), "mmvae_aux_fence")
             self.reduce_range(grads, begin, end)
         if not torch.cuda.is_current_stream_capturing():
             grads.record_stream(self.comm_stream)
