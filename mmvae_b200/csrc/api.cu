@@ -22,6 +22,11 @@
 namespace mmvae {
 
 thread_local char g_err[512] = "";
+// experiment switch, read once per process: no auxiliary streams (everything on the caller's stream)
+static bool aux_disabled() {
+  static const bool off = getenv("MMVAE_NO_AUX") != nullptr;
+  return off;
+}
 bool pdl_enabled() {
   static bool on = [] { const char* e = getenv("MMVAE_NO_PDL"); return !(e && e[0] == '1'); }();
   return on;
@@ -163,7 +168,7 @@ struct Exec {
   template <typename U> U* at(size_t off) const { return reinterpret_cast<U*>(ws + off); }
   const ActT& act(int i) const { return P.acts[i]; }
 
-  void use_aux() { if (special_ok() && !getenv("MMVAE_NO_AUX")) aux = aux_pool(); }
+  void use_aux() { if (special_ok() && !aux_disabled()) aux = aux_pool(); }
   cudaEvent_t next_event() { cudaEvent_t e = aux->ev[aux->next]; aux->next = (aux->next + 1) & 31; return e; }
   // run f() on the auxiliary stream, ordered after everything enqueued on the main stream so far
   template <typename F> void side(F f) {
@@ -514,7 +519,11 @@ struct Exec {
   void block_bwd(const BlockT& b) {
     const ConvT_& c1 = P.convs[b.c1]; const ConvT_& c2 = P.convs[b.c2]; const ConvT_& cs = P.convs[b.cs];
     bn_bwd(at<T>(act(b.out).goff), 0, b.out, c2, &cs);
-    const bool split = split_grad(b.in);
+    bool split = split_grad(b.in);
+    { static const int dbg = [] { const char* e = getenv("MMVAE_SPLIT_DBG"); return e ? atoi(e) : 0; }();   // 1: decoder blocks only, 2: encoder only
+      GConvParams gq; fill_dgrad(cs, gq);
+      if (dbg == 1 && !dgrad_covers_all(gq)) split = false;
+      if (dbg == 2 && dgrad_covers_all(gq)) split = false; }
     if (split) {
       side2([&] {                                     // shortcut branch -> second part of d in, off the critical path
         GConvParams g;
@@ -1003,7 +1012,7 @@ int mmvae_nb_loss_backward(const mmvae_desc* d, const float* x, const int64_t* t
     E.nb_loss_backward(reinterpret_cast<const long long*>(target), kl_weight, out);
   } else {
     Exec<__nv_bfloat16> E{P, (char*)workspace, params, grads, nullptr, nullptr, st, x};
-    if (!(P.d.flags & MMVAE_FLAG_FORCE_SIMT) && !getenv("MMVAE_NO_AUX")) E.aux = aux_pool();
+    if (!(P.d.flags & MMVAE_FLAG_FORCE_SIMT) && !aux_disabled()) E.aux = aux_pool();
     E.nb_loss_backward(reinterpret_cast<const long long*>(target), kl_weight, out);
   }
   return check_launches("mmvae_nb_loss_backward");

@@ -642,7 +642,9 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_sweep_kernel(const BnBwdArgs a)
   pdl_trigger();
   typedef __nv_bfloat16 T;
   constexpr int VEC = 8;
-  __shared__ float red[3][256];                        // [sum][channel], C <= 256 (the warps add up with shared atomics)
+  extern __shared__ float red[];                       // [3 sums][8 warps][C]: combined in a FIXED order (run-to-run
+                                                       // reproducible: a 1e-7 wobble here is amplified to 1e-2 at the stem by
+                                                       // the bf16 rounding of the ~25 gradient tensors downstream)
   __shared__ float coef[2][3][256];                    // per branch: scale, c1 (mean of g), c2 (mean of g * xhat)
   __shared__ float mr[2][2][256];                      // per branch: mean, rstd
   const int CV = a.C / VEC, RPI = 256 / CV;
@@ -656,9 +658,7 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_sweep_kernel(const BnBwdArgs a)
   for (int c = tid; c < a.C; c += 256) {
     mr[0][0][c] = a.stat[c]; mr[0][1][c] = a.stat[a.C + c];
     if (y2) { mr[1][0][c] = a.stat2[c]; mr[1][1][c] = a.stat2[a.C + c]; }
-    red[0][c] = 0.f; red[1][c] = 0.f; red[2][c] = 0.f;
   }
-  __syncthreads();
   const long long rstride = (long long)gridDim.x * RPI;
   const long long r0 = (long long)blockIdx.x * RPI + rsub;
   // g = (dA [+ dA2]) * [a > 0], rounded to the storage type once (what the accumulate-in-place path stored)
@@ -703,20 +703,23 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_sweep_kernel(const BnBwdArgs a)
       s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], d);
     }
   }
+  const int wrp = tid >> 5;
   if ((tid & 31) < CV) {                               // lanes < CV of every warp hold the warp's sums of their channel vector
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
-      atomicAdd(&red[0][c0 + k], s0[k]); atomicAdd(&red[1][c0 + k], s1[k]);
-      if (y2) atomicAdd(&red[2][c0 + k], s2[k]);
+      red[(0 * 8 + wrp) * a.C + c0 + k] = s0[k]; red[(1 * 8 + wrp) * a.C + c0 + k] = s1[k];
+      red[(2 * 8 + wrp) * a.C + c0 + k] = s2[k];
     }
   }
   __syncthreads();
   for (int e = tid; e < 3 * a.C; e += 256) {
     const int which = e / a.C, c = e - which * a.C;
-    float sum = red[which][c];
+    float sum = 0.f, t0 = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { sum += red[(which * 8 + q) * a.C + c]; t0 += red[q * a.C + c]; }
     // centre the raw moments: sum g * xhat = rstd * (sum g*y - mean * sum g), per CTA in fp32 (|mean * S0| ~ |sum g*y|
     // only when the channel mean dominates its spread; the fp64 accumulation across CTAs keeps the rest exact)
-    if (which == 1 || (which == 2 && y2)) sum = mr[which - 1][1][c] * (sum - mr[which - 1][0][c] * red[0][c]);
+    if (which == 1 || (which == 2 && y2)) sum = mr[which - 1][1][c] * (sum - mr[which - 1][0][c] * t0);
     if (which < 2 || y2) atomicAdd(a.acc + (size_t)(blockIdx.x % kBnAccCopies) * 3 * a.C + which * a.C + c, (double)sum);
   }
   // ---- grid-wide barrier (the grid is co-resident: at most coop_max_ctas() CTAs) ----
@@ -936,7 +939,7 @@ static int sweep_max_ctas() {
   int v = cached[dev].load();
   if (v > 0) return v;
   int per_sm = 0, sms = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_bwd_sweep_kernel, 256, 0) != cudaSuccess ||
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_bwd_sweep_kernel, 256, sizeof(float) * 3 * 8 * 256) != cudaSuccess ||
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) { cudaGetLastError(); return 0; }
   static const int per = [] { const char* e = getenv("MMVAE_BN_SWEEP_PER_SM"); return e ? atoi(e) : 2; }();
   v = std::min(per_sm, per) * sms;
@@ -961,7 +964,7 @@ void launch_bn_bwd(const BnBwdArgs& a, cudaStream_t st) {
       const int grid = (int)std::min<long long>(sweep_max_ctas(), row_groups);
       if (grid > 0) {
         count_launch();
-        launch_pdl(bn_bwd_sweep_kernel, grid, 256, 0, st, a);
+        launch_pdl(bn_bwd_sweep_kernel, grid, 256, sizeof(float) * 3 * 8 * a.C, st, a);
         return;
       }
     }

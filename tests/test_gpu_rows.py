@@ -312,3 +312,24 @@ def test_graphed_step_kl_annealing():
         vals[w] = (float(loss), float(pxz), float(kl))
         assert abs(float(loss) - (float(pxz) + w * float(kl))) <= 1e-5 * abs(float(loss)), (w, vals[w])
     assert vals[0.0][2] > 0
+
+
+def test_backward_chain_is_reproducible():
+    """Two bf16 steps on identical inputs: every stored gradient tensor of the backward chain is BIT-identical (fixed
+    reduction orders; fp64 accumulation across CTAs), so the run-to-run difference of the parameter gradients is the fp32
+    atomics of the weight-gradient reductions alone.  A 1e-7 wobble in one BatchNorm-backward sum would be amplified to
+    ~1e-2 at the stem by the bf16 rounding of the ~25 gradient tensors downstream (it was, with shared-memory float atomics)."""
+    from ours_util import workspace_tensor
+    g = Golden("base64_n32")
+    runs = []
+    for _ in range(2):
+        m = build_model(g.cfg, g.state(), "bf16")
+        res = train_step(m, g.cfg, g.x, g.x, g.eps)
+        chain = {k: workspace_tensor(m, g.x.shape[0], k + ".grad") for k in
+                 ("decoder.uplayer3.0.conv2", "decoder.input", "encoder.layer4.0", "encoder.layer2.0.conv1", "encoder.relu", "encoder.conv1")}
+        runs.append((res, chain))
+    for k in runs[0][1]:
+        assert torch.equal(runs[0][1][k], runs[1][1][k]), f"{k}.grad differs between two identical steps"
+    for k, ga in runs[0][0].grads.items():
+        if k != "decoder.conv2.bias":
+            assert rel_l2(runs[1][0].grads[k], ga) <= 1e-5, k
