@@ -11,8 +11,13 @@ for r in csv.DictReader(io.StringIO("".join(lines))):
     rows.setdefault(k, {"name": name})[r["Metric Name"]] = v * scale
 seq = list(rows.values())
 starts = [i for i, r in enumerate(seq) if "pack_weights_kernel" in r["name"]]
-b, e = starts[-3], starts[-2]
-step = seq[b:e]
+step = None
+for k in range(len(starts) - 1, 0, -1):              # the last complete step without the optimizer (bench.py's resident / e2e graphs)
+    cand = seq[starts[k - 1]:starts[k]]
+    if not any("adam_kernel" in r["name"] or "prepare_input" in r["name"] for r in cand):
+        step = cand
+        break
+assert step is not None
 rd = sum(r.get("dram__bytes_read.sum", 0) for r in step); wr = sum(r.get("dram__bytes_write.sum", 0) for r in step)
 print(f"one step: {len(step)} launches, dram read {rd / 1e6:.1f} MB + write {wr / 1e6:.1f} MB = {(rd + wr) / 1e6:.1f} MB "
       f"(algorithmic 2.79 MB/frame x 256 = 714 MB: x{(rd + wr) / 714.2e6:.2f})")
