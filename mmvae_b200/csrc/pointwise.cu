@@ -167,6 +167,22 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ y, 
   }
 }
 
+// one output channel (NHWC == NCHW): 8 values per thread, 16-byte load, two 16-byte stores
+__global__ void __launch_bounds__(256) bn_apply_out_c1_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ coef,
+                                                              float* __restrict__ out, long long nvec) {
+  pdl_wait();
+  pdl_trigger();
+  const float sc = __ldg(coef), sh = __ldg(coef + 1);
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < nvec; i += gridDim.x * 256LL) {
+    float v[8];
+    load_vec<__nv_bfloat16, 8>(y + i * 8, v);
+    float4 a = make_float4(fmaf(v[0], sc, sh), fmaf(v[1], sc, sh), fmaf(v[2], sc, sh), fmaf(v[3], sc, sh));
+    float4 b = make_float4(fmaf(v[4], sc, sh), fmaf(v[5], sc, sh), fmaf(v[6], sc, sh), fmaf(v[7], sc, sh));
+    reinterpret_cast<float4*>(out)[2 * i] = a;
+    reinterpret_cast<float4*>(out)[2 * i + 1] = b;
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) bn_apply_out_kernel(const T* __restrict__ y, const float* __restrict__ coef,
                                                            float* __restrict__ out, long long total, int HW, int C) {
@@ -181,7 +197,7 @@ __global__ void __launch_bounds__(256) bn_apply_out_kernel(const T* __restrict__
 
 // ---------------- encoder heads: avg-pool + two 1x1 convs + rsample (model.py:123-128,148-150) ----------
 // grid (N, kHeadsSplit): CTA (n, q) pools frame n and produces latent channels [q * zq, (q+1) * zq) of mu and logvar
-constexpr int kHeadsSplit = 4;
+constexpr int kHeadsSplit = 8;
 template <typename T>
 __global__ void __launch_bounds__(128) heads_fwd_kernel(const HeadsArgs a) {
   pdl_wait();                                       // PDL: may start while the previous kernel drains
@@ -269,12 +285,12 @@ __global__ void __launch_bounds__(128) heads_bwd_kernel(const HeadsBwdArgs a) {
     float gl = a.d_lv ? a.d_lv[idx] : 0.f;
     if (a.w_lv) gl += dz * 0.5f * a.heads[2 * NZ + idx] * a.heads[3 * NZ + idx];   // dz * 0.5 * eps * std
     dmu[zc] = gm; dlv[zc] = gl;
-    a.dheads[idx] = gm; a.dheads[NZ + idx] = gl;
+    if (blockIdx.y == 0) { a.dheads[idx] = gm; a.dheads[NZ + idx] = gl; }
   }
   __syncthreads();
   T* dfeat = reinterpret_cast<T*>(a.dfeat) + size_t(n) * a.hw * a.C;
   const float inv = 1.0f / (float)a.hw;
-  for (int c = tid; c < a.C; c += 128) {
+  for (int c = blockIdx.y * 128 + tid; c < a.C; c += 128 * gridDim.y) {      // grid.y CTAs share a frame's channels
     float s = 0.f;
     for (int zc = 0; zc < a.z; ++zc) {
       s = fmaf(dmu[zc], __ldg(a.w_mu + size_t(zc) * a.C + c), s);
@@ -888,6 +904,12 @@ template <typename T>
 void launch_bn_apply_out(const T* y, const float* coef, float* out_nchw, int N, int HW, int C, cudaStream_t st) {
   long long total = (long long)N * HW * C;
   count_launch();
+  if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+    if (C == 1 && (total & 7) == 0 && (reinterpret_cast<uintptr_t>(out_nchw) & 15) == 0) {
+      launch_pdl(bn_apply_out_c1_kernel, grid_for(total / 8), 256, 0, st, y, coef, out_nchw, total / 8);
+      return;
+    }
+  }
   launch_pdl(bn_apply_out_kernel<T>, grid_for(total), 256, 0, st, y, coef, out_nchw, total, HW, C);
 }
 
@@ -908,7 +930,7 @@ template <typename T>
 void launch_heads_bwd(const HeadsBwdArgs& a, cudaStream_t st) {
   size_t smem = sizeof(float) * 2 * size_t(a.z);
   count_launch();
-  launch_pdl(heads_bwd_kernel<T>, a.N, 128, smem, st, a);
+  launch_pdl(heads_bwd_kernel<T>, dim3(a.N, std::max(1, std::min(4, a.C / 128))), 128, smem, st, a);
   // the weight gradients of the two heads are a separate launch (launch_heads_wgrad): the caller decides the stream
 }
 
