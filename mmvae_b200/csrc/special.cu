@@ -45,12 +45,14 @@ __device__ __forceinline__ void cp_async8(uint32_t dst_smem, const void* src, ui
 // ------------------------------------------------------------------------------------------------
 constexpr int kStemXs = 1408;          // floats: (2R+3) rows x pitch of the x halo tile (19 x 68 or 35 x 36)
 
+__device__ __forceinline__ void stem_x_prefetch(const StemArgs& a, int tile, float* xs, int nthreads);
+
 template <int CO>
 __global__ void __launch_bounds__(256, 3) stem_fwd_kernel(const StemArgs a) {
   pdl_wait();                                       // PDL: may start while the previous kernel drains
   pdl_trigger();
   constexpr int CG = CO / 8;                         // channel groups of 8
-  __shared__ __align__(16) float xs[kStemXs];
+  __shared__ __align__(16) float xs2[2][kStemXs];      // double-buffered x halo tile (cp.async; the next tile loads under this one)
   __shared__ __align__(16) float ws[25 * CO];
   __shared__ float wred[8][2][CO];
   const int tid = threadIdx.x, lane = tid & 31;
@@ -61,19 +63,21 @@ __global__ void __launch_bounds__(256, 3) stem_fwd_kernel(const StemArgs a) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) { run_s[j] = 0.f; run_q[j] = 0.f; }
   for (int e = tid; e < 25 * CO; e += 256) { int co = e / 25, t = e - co * 25; ws[t * CO + co] = __ldg(a.w + e); }
-  const int rows = 2 * a.R + 3, pitch = a.pitch;
-  for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+  for (int e = tid; e < 2 * kStemXs; e += 256) (&xs2[0][0])[e] = 0.f;            // halo columns stay zero
+  __syncthreads();
+  const int pitch = a.pitch;
+  int buf = 0;
+  if ((int)blockIdx.x < a.ntiles) stem_x_prefetch(a, blockIdx.x, xs2[0], 256);
+  cp_async_commit();
+  for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, buf ^= 1) {
     const int n = tile / a.tiles_per_frame, oy0 = (tile - n * a.tiles_per_frame) * a.R;
-    __syncthreads();                                 // previous tile's readers are done with xs
-    {
-      const float* xn = a.x + (size_t)n * a.S * a.S;
-      for (int e = tid; e < rows * pitch; e += 256) {
-        const int rr = e / pitch, cc = e - rr * pitch;
-        const int iy = 2 * oy0 - 2 + rr, ix = cc - 2;
-        xs[e] = ((unsigned)iy < (unsigned)a.S && (unsigned)ix < (unsigned)a.S) ? __ldg(xn + (size_t)iy * a.S + ix) : 0.f;
-      }
-    }
+    const int next = tile + gridDim.x;
+    __syncthreads();                                 // the previous tile's readers are done with the buffer refilled now
+    if (next < a.ntiles) stem_x_prefetch(a, next, xs2[buf ^ 1], 256);
+    cp_async_commit();
+    cp_async_wait<1>();
     __syncthreads();
+    const float* xs = xs2[buf];
     if (!active) continue;
     float acc[4][8];
 #pragma unroll
@@ -122,6 +126,7 @@ __global__ void __launch_bounds__(256, 3) stem_fwd_kernel(const StemArgs a) {
       }
     }
   }
+  cp_async_wait<0>();
   if (a.bn.acc) {
     // per-channel sums over this CTA's pixels: lanes with equal (lane % CG) hold the same channel group
 #pragma unroll
@@ -149,17 +154,35 @@ __global__ void __launch_bounds__(256, 3) stem_fwd_kernel(const StemArgs a) {
 constexpr int kStemWgThreads = 640;
 constexpr int kStemDyBytes = 256 * 64;               // 256 pixels x 32 channels x 2 bytes
 
-__device__ __forceinline__ void stem_wgrad_prefetch(const StemArgs& a, int tile, int co_base, int CO, float* xs, unsigned char* dys) {
+// x tile of a stem tile: (2R+3) input rows as 8-byte pairs, cp.async; rows outside the image are zero-filled, the halo
+// columns (-2, -1, S, S+1, ..) of the tile are zeroed once by the kernel and never written here.
+__device__ __forceinline__ void stem_x_prefetch(const StemArgs& a, int tile, float* xs, int nthreads) {
   const int n = tile / a.tiles_per_frame, oy0 = (tile - n * a.tiles_per_frame) * a.R;
   const int rows = 2 * a.R + 3, pitch = a.pitch, tid = threadIdx.x;
   const float* xn = a.x + (size_t)n * a.S * a.S;
   const int halfp = a.S >> 1;                        // 8-byte pairs per input row
-  for (int e = tid; e < rows * halfp; e += kStemWgThreads) {
+  if ((halfp & (halfp - 1)) == 0) {                  // power of two (S = 32, 64): shifts only
+    const int j = tid & (halfp - 1), r0 = tid / halfp, rstep = nthreads / halfp;
+    const uint32_t d0 = smem_u32(xs + 2 + 2 * j);
+    for (int rr = r0; rr < rows; rr += rstep) {
+      const int iy = 2 * oy0 - 2 + rr;
+      const bool ok = (unsigned)iy < (unsigned)a.S;
+      cp_async8(d0 + (uint32_t)(rr * pitch) * 4u, ok ? (const void*)(xn + (size_t)iy * a.S + 2 * j) : (const void*)xn, ok ? 8u : 0u);
+    }
+    return;
+  }
+  for (int e = tid; e < rows * halfp; e += nthreads) {
     const int rr = e / halfp, j = e - rr * halfp;
     const int iy = 2 * oy0 - 2 + rr;
     const bool ok = (unsigned)iy < (unsigned)a.S;
     cp_async8(smem_u32(xs + rr * pitch + 2 + 2 * j), ok ? (const void*)(xn + (size_t)iy * a.S + 2 * j) : (const void*)xn, ok ? 8u : 0u);
   }
+}
+
+__device__ __forceinline__ void stem_wgrad_prefetch(const StemArgs& a, int tile, int co_base, int CO, float* xs, unsigned char* dys) {
+  const int n = tile / a.tiles_per_frame, oy0 = (tile - n * a.tiles_per_frame) * a.R;
+  const int tid = threadIdx.x;
+  stem_x_prefetch(a, tile, xs, kStemWgThreads);
   const int rv = min(a.R, a.Ho - oy0);               // valid output rows of this tile
   const int npx = rv * a.Wo;
   const unsigned char* src = reinterpret_cast<const unsigned char*>(a.dy + (((size_t)n * a.Ho + oy0) * a.Wo) * CO + co_base);
@@ -198,19 +221,38 @@ __global__ void __launch_bounds__(kStemWgThreads, 1) stem_wgrad_kernel(const Ste
     const int npx = min(a.R, a.Ho - oy0) * a.Wo;
     const float* xb = xs[buf];
     const unsigned char* db = dys[buf];
+    if (a.Wo == 32) {
+      // one output row per pass of the warp: pixel p = 32 * i + lane, so the row index is i, the column is the lane and the
+      // swizzle term of the dY chunk is a per-lane constant -- the loop is two pointer increments, 4 loads, 40 FMAs
+      const unsigned char* dp = db + lane * 64 + ((cg ^ ((lane >> 1) & 3)) << 4);
+      const float* xr = xb + kh * pitch + 2 * lane;
+      const int nrow = npx >> 5;
 #pragma unroll 4
-    for (int p = lane; p < npx; p += 32) {
-      int oy_l, ox;
-      a.fd_wo.divmod(p, oy_l, ox);
-      float g[8];
-      unpack8(*reinterpret_cast<const uint4*>(db + p * 64 + ((cg ^ ((p >> 1) & 3)) << 4)), g);
-      const float* xr = xb + (2 * oy_l + kh) * pitch + 2 * ox;
-      const float2 x01 = *reinterpret_cast<const float2*>(xr), x23 = *reinterpret_cast<const float2*>(xr + 2);
-      const float xv[5] = {x01.x, x01.y, x23.x, x23.y, xr[4]};
+      for (int i = 0; i < nrow; ++i, dp += 2048, xr += 2 * pitch) {
+        float g[8];
+        unpack8(*reinterpret_cast<const uint4*>(dp), g);
+        const float2 x01 = *reinterpret_cast<const float2*>(xr), x23 = *reinterpret_cast<const float2*>(xr + 2);
+        const float xv[5] = {x01.x, x01.y, x23.x, x23.y, xr[4]};
 #pragma unroll
-      for (int kw = 0; kw < 5; ++kw)
+        for (int kw = 0; kw < 5; ++kw)
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc[kw][c] = fmaf(xv[kw], g[c], acc[kw][c]);
+          for (int c = 0; c < 8; ++c) acc[kw][c] = fmaf(xv[kw], g[c], acc[kw][c]);
+      }
+    } else {
+#pragma unroll 4
+      for (int p = lane; p < npx; p += 32) {
+        int oy_l, ox;
+        a.fd_wo.divmod(p, oy_l, ox);
+        float g[8];
+        unpack8(*reinterpret_cast<const uint4*>(db + p * 64 + ((cg ^ ((p >> 1) & 3)) << 4)), g);
+        const float* xr = xb + (2 * oy_l + kh) * pitch + 2 * ox;
+        const float2 x01 = *reinterpret_cast<const float2*>(xr), x23 = *reinterpret_cast<const float2*>(xr + 2);
+        const float xv[5] = {x01.x, x01.y, x23.x, x23.y, xr[4]};
+#pragma unroll
+        for (int kw = 0; kw < 5; ++kw)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[kw][c] = fmaf(xv[kw], g[c], acc[kw][c]);
+      }
     }
     __syncthreads();                                 // everyone is done with this buffer before it is refilled
   }
@@ -232,19 +274,24 @@ __global__ void __launch_bounds__(kStemWgThreads, 1) stem_wgrad_kernel(const Ste
 // Forward.  Thread = (image column x, group g of 8 input channels) of one band of 8 output rows; the G = CI/8 lanes of
 // a pixel are adjacent, so a quarter warp reads 128 contiguous bytes of the tile.  The thread walks the band's 10 input
 // rows once (3 x 16-byte loads per row, converted once) and keeps its 9 x 8 weights in registers.
+// Tile loader: the (R+2) x W interior pixels of a tile as 16-byte chunks, cp.async.  A row holds W*G chunks (a power of two
+// dividing 256, tail_supported): thread -> (row of this pass, chunk of the row) by shifts only; rows outside the image are
+// zero-filled; the two halo COLUMNS of the tile are zeroed once by the kernel and never written here.  (The first version
+// derived (row, column, group) of every chunk from a flat index with two runtime divisions: 66 % of the kernel's
+// instructions were not FMAs, profiles/r02_pointwise_loss_hbm.md.)
 template <int CI>
 __device__ __forceinline__ void tail_prefetch(const TailArgs& a, int tile, unsigned char* dst, int nthreads) {
   constexpr int G = CI / 8;
   const int n = tile / a.tiles_per_frame, oy0 = (tile - n * a.tiles_per_frame) * a.R;
   const int W2 = a.W + 2;
-  const uint4* in = reinterpret_cast<const uint4*>(a.in);
-  for (int e = threadIdx.x; e < (a.R + 2) * W2 * G; e += nthreads) {
-    const int pix = e / G, c = e - pix * G;
-    const int rr = pix / W2, cc = pix - rr * W2;
-    const int iy = oy0 - 1 + rr, ix = cc - 1;
-    const bool ok = (unsigned)iy < (unsigned)a.H && (unsigned)ix < (unsigned)a.W;
-    cp_async16(smem_u32(dst + (size_t)e * 16), ok ? (const void*)(in + (((size_t)n * a.H + iy) * a.W + ix) * G + c) : (const void*)in,
-               ok ? 16u : 0u);
+  const int cpr = a.W * G;                           // chunks per row
+  const int idx = threadIdx.x & (cpr - 1), rsub = threadIdx.x / cpr, rstep = nthreads / cpr;
+  const uint4* in = reinterpret_cast<const uint4*>(a.in) + (size_t)n * a.H * cpr + idx;
+  const uint32_t d0 = smem_u32(dst) + (uint32_t)(G + idx) * 16u;          // column 1 of a tile row
+  for (int rr = rsub; rr < a.R + 2; rr += rstep) {
+    const int iy = oy0 - 1 + rr;
+    const bool ok = (unsigned)iy < (unsigned)a.H;
+    cp_async16(d0 + (uint32_t)(rr * W2 * G) * 16u, ok ? (const void*)(in + (size_t)iy * cpr) : (const void*)a.in, ok ? 16u : 0u);
   }
 }
 
@@ -267,6 +314,13 @@ __global__ void __launch_bounds__(256, 2) tail_fwd_kernel(const TailArgs a) {
   const float bias = a.bias ? __ldg(a.bias) : 0.f;
   float run_s = 0.f, run_q = 0.f;
   int buf = 0;
+  // zero halo columns of both buffers (the loader only writes the interior)
+  for (int e = tid; e < 2 * (a.R + 2) * 2 * G; e += 256) {
+    const int b = e / ((a.R + 2) * 2 * G), r2 = e - b * ((a.R + 2) * 2 * G);
+    const int rr = r2 / (2 * G), side = (r2 / G) & 1, c = r2 % G;
+    reinterpret_cast<uint4*>(tail_smem + b * tile_bytes)[((size_t)rr * W2 + (side ? W2 - 1 : 0)) * G + c] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  __syncthreads();
   if ((int)blockIdx.x < a.ntiles) tail_prefetch<CI>(a, blockIdx.x, tail_smem, 256);
   cp_async_commit();
   for (int t_i = blockIdx.x; t_i < a.ntiles; t_i += gridDim.x, buf ^= 1) {
