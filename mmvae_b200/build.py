@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmmvae_b200.so")
-SOURCES = ["api.cu", "gconv_simt.cu", "gconv_tc.cu", "slab_tc.cu", "special.cu", "pointwise.cu", "loss.cu", "nb.cu", "nb_tail.cu"]
+SOURCES = ["api.cu", "gconv_simt.cu", "gconv_tc.cu", "slab_tc.cu", "special.cu", "stem_tc.cu", "tail_tc.cu", "pointwise.cu", "loss.cu", "nb.cu", "nb_tail.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-cudart", "shared"]
 

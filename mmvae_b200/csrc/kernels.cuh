@@ -255,7 +255,17 @@ struct TailArgs {
 bool stem_supported(int Cin, int Co, int S, int k, int s, int p);
 bool tail_supported(int Ci, int Co, int H, int k, int s, int p);
 StatLayout launch_stem_fwd(StemArgs a, int Co, cudaStream_t st);
+// the same convolution on the tensor cores (stem_tc.cu): im2col built in shared memory, bf16 head + tail split of both operands
+bool stem_tc_supported(int Co, int S);
+void launch_stem_fwd_tc(StemArgs a, int Co, cudaStream_t st);
+bool stem_wgrad_tc_supported(int Co, int S);
+void launch_stem_wgrad_tc(StemArgs a, cudaStream_t st);
 void launch_stem_wgrad(StemArgs a, int Co, cudaStream_t st);
+// the tail convolution's backward pass on the tensor cores (tail_tc.cu)
+bool tail_bwd_tc_supported(int Ci, int H, int W);
+void launch_tail_bwd_tc(TailArgs a, int Ci, cudaStream_t st);
+bool tail_fwd_tc_supported(int Ci, int H, int W);
+void launch_tail_fwd_tc(TailArgs a, int Ci, cudaStream_t st);
 StatLayout launch_tail_fwd(TailArgs a, int Ci, cudaStream_t st);
 void launch_tail_bwd(TailArgs a, int Ci, cudaStream_t st);
 void launch_heads_wgrad(const float* dheads, const float* pooled, float* g_mu, float* g_lv, int N, int z, int C,

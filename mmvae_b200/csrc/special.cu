@@ -575,6 +575,10 @@ static void stem_fill(StemArgs& a, int quads_per_tile) {
 }
 
 StatLayout launch_stem_fwd(StemArgs a, int Co, cudaStream_t st) {
+  if (a.bn.acc && stem_tc_supported(Co, a.S)) {      // training-mode forward with fused statistics: the tensor-core kernel
+    launch_stem_fwd_tc(a, Co, st);
+    return StatLayout{0, 0, 0, 0};
+  }
   stem_fill(a, 256 / (Co / 8));
   const int grid = min(a.ntiles, 148 * 3);
   count_launch();
@@ -584,6 +588,7 @@ StatLayout launch_stem_fwd(StemArgs a, int Co, cudaStream_t st) {
 }
 
 void launch_stem_wgrad(StemArgs a, int Co, cudaStream_t st) {
+  if (stem_wgrad_tc_supported(Co, a.S)) { launch_stem_wgrad_tc(a, st); return; }
   stem_fill(a, 64);
   const int ny = Co / 32;
   dim3 grid(min(a.ntiles, 148 / ny), ny);
@@ -608,6 +613,7 @@ static void tail_fill(TailArgs& a, int threads_per_pixel) {
 }
 
 StatLayout launch_tail_fwd(TailArgs a, int Ci, cudaStream_t st) {
+  if (a.bn.acc && tail_fwd_tc_supported(Ci, a.H, a.W)) { launch_tail_fwd_tc(a, Ci, st); return StatLayout{0, 0, 0, 0}; }
   tail_fill(a, Ci / 8);
   const int grid = min(a.ntiles, 148 * 2);
   const size_t smem = 2 * (size_t)(a.R + 2) * (a.W + 2) * Ci * 2;
@@ -624,6 +630,7 @@ StatLayout launch_tail_fwd(TailArgs a, int Ci, cudaStream_t st) {
 }
 
 void launch_tail_bwd(TailArgs a, int Ci, cudaStream_t st) {
+  if (tail_bwd_tc_supported(Ci, a.H, a.W)) { launch_tail_bwd_tc(a, Ci, st); return; }
   tail_fill(a, Ci / 4);
   const int grid = min(a.ntiles, 148 * 2);
   const size_t smem = sizeof(float) * ((size_t)(a.R + 2) * (a.W + 2) + (size_t)8 * (Ci / 4) * 48);
