@@ -8,8 +8,8 @@
 // Backward, per tile of 128 consecutive pixels (R = 128 / W image rows), thread = pixel:
 //   A  = im2col of the ONE-channel dY: A[q][t] = dY[q + (1-kh, 1-kw)], 9 taps padded to 16, built by the thread from a
 //        cp.async-staged halo tile and written as plane[t / 8][pixel][8 taps] (bf16 is exact: dY is bf16)
-//   dX[q][ci]  = A[q][:] . w[ci][:]            MMA 1: M = 128 pixels, N = 2 CI, K = 16; B = [w_hi | w_lo] K-major (the fp32
-//                                              weights as a bf16 head and tail in separate COLUMNS: one MMA, the epilogue adds)
+//   dX[q][ci]  = A[q][:] . w[ci][:]            MMA 1: M = 128 pixels, N = CI, K = 16, twice: B = the bf16 head, then the bf16
+//                                              tail of the fp32 weights, accumulated
 //   dW[ci][t] += sum_q A[q][t] * a[q][ci]      MMA 2: the pixel axis is K (8 k-steps), both operands MN-major views: A is the
 //                                              same shared-memory image, B = the activation tile plane[ci / 8][pixel][8 ch];
 //                                              M = 128 with taps in rows 0..8 (planes 2..15 of the A descriptor run into the
@@ -35,7 +35,6 @@ __device__ __forceinline__ void split_bf16(float v, float& hi, float& lo) {
   hi = __bfloat162float(__float2bfloat16_rn(v));
   lo = v - hi;
 }
-__device__ __forceinline__ float bf16_round_f(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 __device__ __forceinline__ void unpack8(const uint4& u, float* v) {
   v[0] = __uint_as_float(u.x << 16); v[1] = __uint_as_float(u.x & 0xffff0000u);
   v[2] = __uint_as_float(u.y << 16); v[3] = __uint_as_float(u.y & 0xffff0000u);
@@ -50,7 +49,7 @@ __global__ void __launch_bounds__(128, CI == 16 ? 4 : 2) tail_bwd_tc_kernel(cons
   constexpr int kSlot = 3 * kTens + kHaloBytes;      // a | y | y2 | dY halo
   constexpr int kABuf = 2 * kPlane;                  // im2col operand: 2 planes (taps 0..7, 8..15)
   constexpr int kWPlane = 2 * CI * 16;               // weight plane: 2 CI rows (hi | lo) x 8 taps
-  constexpr int kTmemCols = 5 * CI <= 128 ? 128 : 256;   // D1 double-buffered (2 x 2 CI) + D2 (CI)
+  constexpr int kTmemCols = 3 * CI <= 64 ? 64 : 128;     // D1 double-buffered (2 x CI) + D2 (CI)
   extern __shared__ __align__(128) unsigned char ttc_smem[];
   __shared__ __align__(8) unsigned long long mma_done[2];
   __shared__ uint32_t tmem_base_s;
@@ -102,9 +101,9 @@ __global__ void __launch_bounds__(128, CI == 16 ? 4 : 2) tail_bwd_tc_kernel(cons
   const int w_log2 = 31 - __clz(a.W);
   const int ry = tid >> w_log2, ox = tid & (a.W - 1);
   const int hp = a.W + 16;                           // halo row pitch in elements
-  const uint32_t idesc1 = make_idesc_bf16(128, 2 * CI, 0, 0);
+  const uint32_t idesc1 = make_idesc_bf16(128, CI, 0, 0);
   const uint32_t idesc2 = make_idesc_bf16(128, CI, 1, 1);
-  const uint32_t d2 = tmem + (uint32_t)(4 * CI);
+  const uint32_t d2 = tmem + (uint32_t)(2 * CI);
 
   // stage tile `tile` into ring slot `slot`
   auto prefetch = [&](int tile, int slot) {
@@ -141,17 +140,17 @@ __global__ void __launch_bounds__(128, CI == 16 ? 4 : 2) tail_bwd_tc_kernel(cons
   auto epilogue = [&](int tile, int b, int slot, uint32_t parity) {
     mbar_wait(smem_u32(&mma_done[b]), parity);
     tc_fence_after();
-    const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(b * 2 * CI);
+    const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(b * CI);
     const unsigned char* sp = s_ptr + slot * kSlot + tid * 16;
     __nv_bfloat16* out = a.dx + ((size_t)tile * 128 + tid) * CI;
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
-      float hi[16], lo[16], av[16], yv[16], zv[16];
-      tmem_ld16(tl + (uint32_t)(g * 16), hi);
-      tmem_ld16(tl + (uint32_t)(CI + g * 16), lo);
+      float d[16], yv[16], zv[16];
+      uint32_t au[8];
+      tmem_ld16(tl + (uint32_t)(g * 16), d);
       if (fuse) {
-        unpack8(*reinterpret_cast<const uint4*>(sp + (2 * g) * kPlane), av);
-        unpack8(*reinterpret_cast<const uint4*>(sp + (2 * g + 1) * kPlane), av + 8);
+        *reinterpret_cast<uint4*>(au) = *reinterpret_cast<const uint4*>(sp + (2 * g) * kPlane);
+        *reinterpret_cast<uint4*>(au + 4) = *reinterpret_cast<const uint4*>(sp + (2 * g + 1) * kPlane);
         unpack8(*reinterpret_cast<const uint4*>(sp + kTens + (2 * g) * kPlane), yv);
         unpack8(*reinterpret_cast<const uint4*>(sp + kTens + (2 * g + 1) * kPlane), yv + 8);
         if (two) {
@@ -159,17 +158,21 @@ __global__ void __launch_bounds__(128, CI == 16 ? 4 : 2) tail_bwd_tc_kernel(cons
           unpack8(*reinterpret_cast<const uint4*>(sp + 2 * kTens + (2 * g + 1) * kPlane), zv + 8);
         }
       }
+      // g = bf16(dX) * [a > 0] on the packed pairs: the ReLU gate is the sign / zero test of a's bf16 bit pattern, the
+      // values that enter the sums are the stored ones (a shift / a mask each)
+      uint32_t pk[8];
       float gm[16];
 #pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        const float d = hi[e] + lo[e];
-        gm[e] = fuse ? (av[e] > 0.f ? bf16_round_f(d) : 0.f) : d;
+      for (int e = 0; e < 8; ++e) {
+        pk[e] = pack_bf16x2(d[2 * e], d[2 * e + 1]);
+        if (fuse) {
+          const uint32_t keep = ((int)(au[e] << 16) > 0 ? 0x0000ffffu : 0u) | ((int)(au[e] & 0xffff0000u) > 0 ? 0xffff0000u : 0u);
+          pk[e] &= keep;
+        }
+        gm[2 * e] = __uint_as_float(pk[e] << 16); gm[2 * e + 1] = __uint_as_float(pk[e] & 0xffff0000u);
       }
-      uint4 p0, p1;
-      p0.x = pack_bf16x2(gm[0], gm[1]); p0.y = pack_bf16x2(gm[2], gm[3]); p0.z = pack_bf16x2(gm[4], gm[5]); p0.w = pack_bf16x2(gm[6], gm[7]);
-      p1.x = pack_bf16x2(gm[8], gm[9]); p1.y = pack_bf16x2(gm[10], gm[11]); p1.z = pack_bf16x2(gm[12], gm[13]); p1.w = pack_bf16x2(gm[14], gm[15]);
-      *reinterpret_cast<uint4*>(out + g * 16) = p0;
-      *reinterpret_cast<uint4*>(out + g * 16 + 8) = p1;
+      *reinterpret_cast<uint4*>(out + g * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      *reinterpret_cast<uint4*>(out + g * 16 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
       if (fuse) {
         if constexpr (kPerThread) {
 #pragma unroll
@@ -222,8 +225,9 @@ __global__ void __launch_bounds__(128, CI == 16 ? 4 : 2) tail_bwd_tc_kernel(cons
       tc_fence_after();
       if (elect_one()) {
         const uint32_t ab = a_base + (uint32_t)(buf * kABuf), sb = s_base + (uint32_t)(slot * kSlot);
-        mma_bf16(tmem + (uint32_t)(buf * 2 * CI), make_smem_desc(ab, kPlane, 128, SWZ_NONE),
-                 make_smem_desc(w_base, kWPlane, 128, SWZ_NONE), idesc1, 0);
+        const uint64_t d_a = make_smem_desc(ab, kPlane, 128, SWZ_NONE);
+        mma_bf16(tmem + (uint32_t)(buf * CI), d_a, make_smem_desc(w_base, kWPlane, 128, SWZ_NONE), idesc1, 0);
+        mma_bf16(tmem + (uint32_t)(buf * CI), d_a, make_smem_desc(w_base + CI * 16, kWPlane, 128, SWZ_NONE), idesc1, 1);
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks)               // 16 pixels per MMA: two core matrices of 8 pixels, 128 B apart
           mma_bf16(d2, make_smem_desc(ab + ks * 256, 128, kPlane, SWZ_NONE), make_smem_desc(sb + ks * 256, 128, kPlane, SWZ_NONE),
@@ -353,19 +357,34 @@ __global__ void __launch_bounds__(128, 4) tail_fwd_tc_kernel(const TailArgs a, c
   const bool stats = a.bn.acc != nullptr;
   float run_s = 0.f, run_q = 0.f;
 
-  // stage chunk `chunk`: padded positions [h0 - Wp - 1, h0 + kFwdTiles * 128 + Wp + 1) of its frame, h0 = Wp + k * 384
+  // stage chunk `chunk`: padded positions [hfirst, hfirst + count) of its frame, hfirst = k * kFwdTiles * 128 - 1 (one padded
+  // row + one position before the chunk's first output).  Walked by padded ROW: the interior of a row is W * G consecutive
+  // 16-byte chunks of the NHWC tensor (thread -> (column, plane) by shifts only; the first version derived (row, column) of
+  // every staged position with a multiply-high division and spent 5.4 M of its 7.3 M instructions there); rows 0 and H + 1
+  // are zero-filled, the two halo columns of every row are zeroed by plain stores.
   auto prefetch = [&](int chunk, int sidx) {
     const int n = chunk / g.chunks_per_frame, k = chunk - n * g.chunks_per_frame;
-    const int hfirst = k * (kFwdTiles * 128) - 1;                        // = h0 - Wp - 1
+    const int hfirst = k * (kFwdTiles * 128) - 1;
     const uint32_t sb = st_base + (uint32_t)sidx * stage_bytes;
     const unsigned char* frame = reinterpret_cast<const unsigned char*>(a.in + (size_t)n * a.H * a.W * CI);
-    for (int e = tid; e < g.count * G; e += 128) {
-      const int j = e / G, c = e % G;
-      const int h = hfirst + j;
-      const int r = (int)__umulhi((unsigned)max(h, 0), g.wp_mul), col = h - r * g.Wp;
-      const bool ok = h >= 0 && r >= 1 && r <= a.H && col >= 1 && col <= a.W;
-      const size_t off = ok ? ((size_t)((r - 1) * a.W + (col - 1)) * G + c) * 16 : 0;
-      cp_async16(sb + (uint32_t)(c * g.plane + j * 16), frame + off, ok ? 16u : 0u);
+    const int r0 = (int)__umulhi((unsigned)max(hfirst, 0), g.wp_mul);
+    const int r1 = min((int)__umulhi((unsigned)(hfirst + g.count - 1), g.wp_mul), a.H + 1);
+    const int row_chunks = a.W * G;
+    for (int r = r0; r <= r1; ++r) {
+      const int jrow = r * g.Wp - hfirst;                                // stage position of padded column 0 of this row
+      const bool ok_row = r >= 1 && r <= a.H;
+      const unsigned char* src = frame + (size_t)(ok_row ? r - 1 : 0) * row_chunks * 16;
+      for (int idx = tid; idx < row_chunks; idx += 128) {
+        const int x = idx / G, c = idx % G, j = jrow + 1 + x;
+        if (j >= 0 && j < g.count) cp_async16(sb + (uint32_t)(c * g.plane + j * 16), src + (size_t)idx * 16, ok_row ? 16u : 0u);
+      }
+    }
+    // halo columns 0 and Wp - 1 of the staged rows
+    const int nh = (r1 - r0 + 1) * 2 * G;
+    if (tid < nh) {
+      const int c = tid % G, side = (tid / G) & 1, r = r0 + tid / (2 * G);
+      const int j = r * g.Wp - hfirst + (side ? g.Wp - 1 : 0);
+      if (j >= 0 && j < g.count) *reinterpret_cast<uint4*>(ttc_smem + (sb - smem_u32(ttc_smem)) + c * g.plane + j * 16) = make_uint4(0u, 0u, 0u, 0u);
     }
   };
 
