@@ -791,6 +791,176 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_sweep_kernel(const BnBwdArgs a)
   }
 }
 
+// BatchNorm backward of a SMALL tensor (a few MB, C >= 32) without any grid-wide synchronisation: the reduction of
+// BatchNorm is per channel, so the work is partitioned BY CHANNEL over thread-block clusters -- cluster = one vector of 8
+// channels, its S CTAs (x 256 threads x E rows per thread) cover all rows of those channels.  The three sums never leave
+// the cluster: warp shuffles -> shared memory -> every CTA pushes its 24 partial sums into the slot [its rank] of every
+// peer through distributed shared memory -> ONE hardware cluster barrier -> every CTA adds the S slots in rank order
+// (fixed order: bit-reproducible).  The rows stay in registers across the barrier (the cluster's CTAs are co-scheduled by
+// the hardware: no residency assumption, no spinning), dY (dY2) is written from them: every byte is touched once.
+// Replaces, for these layers, bn_bwd_sweep_kernel's fp64 global atomics + __threadfence + atomic grid barrier + second pass
+// (12-15 us on the backward chain per BatchNorm layer, profiles/r02_bn_cluster.md).  A thread reads 16 B of a C * 2 B row:
+// half-used 32-byte sectors for the loads, but these tensors are bound by latency, not by L2 bandwidth.
+__device__ __forceinline__ uint32_t bnc_cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t bnc_cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void bnc_st_peer_f32(const float* local, uint32_t rank, float v) {
+  uint32_t la = (uint32_t)__cvta_generic_to_shared(local), ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
+}
+__device__ __forceinline__ void bnc_unpack8(const uint4& u, float (&v)[8]) {
+  v[0] = __uint_as_float(u.x << 16); v[1] = __uint_as_float(u.x & 0xffff0000u);
+  v[2] = __uint_as_float(u.y << 16); v[3] = __uint_as_float(u.y & 0xffff0000u);
+  v[4] = __uint_as_float(u.z << 16); v[5] = __uint_as_float(u.z & 0xffff0000u);
+  v[6] = __uint_as_float(u.w << 16); v[7] = __uint_as_float(u.w & 0xffff0000u);
+}
+__device__ __forceinline__ uint32_t bnc_pack2(float lo, float hi) {
+  const __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&t);
+}
+__device__ __forceinline__ uint4 bnc_pack8(const float (&v)[8]) {
+  return make_uint4(bnc_pack2(v[0], v[1]), bnc_pack2(v[2], v[3]), bnc_pack2(v[4], v[5]), bnc_pack2(v[6], v[7]));
+}
+
+constexpr int kBncMaxCluster = 16;
+
+template <int E>
+__global__ void __launch_bounds__(256, E <= 2 ? 3 : 2) bn_bwd_cluster_kernel(const BnBwdArgs a) {
+  __shared__ float wred[8][24];
+  __shared__ float slots[kBncMaxCluster][24];          // [peer rank][3 sums][8 channels]
+  __shared__ float tot[24];
+  __shared__ __align__(16) float cst[2][3][8];         // [branch][rstd | -mean * rstd | gamma * rstd][channel]
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+  const uint32_t S = bnc_cluster_nctarank(), rank = bnc_cluster_ctarank();
+  const int c0 = (int)(blockIdx.x / S) * 8;
+  const bool two = a.y2 != nullptr;
+  // xhat = y * rstd + nmr; statistics and affine weights were written long before the predecessor: no need to wait for it
+  if (tid < 16) {
+    const int br = tid >> 3, k = tid & 7;
+    if (br == 0 || two) {
+      const float* st = br ? a.stat2 : a.stat;
+      const float m = st[c0 + k], r = st[a.C + c0 + k];
+      cst[br][0][k] = r; cst[br][1][k] = -m * r; cst[br][2][k] = (br ? a.gamma2 : a.gamma)[c0 + k] * r;
+    } else {
+      cst[1][0][k] = 0.f; cst[1][1][k] = 0.f; cst[1][2][k] = 0.f;
+    }
+  }
+  __syncthreads();
+  pdl_wait();
+  pdl_trigger();
+  const uint4* dA = reinterpret_cast<const uint4*>(a.dA);
+  const uint4* dA2 = reinterpret_cast<const uint4*>(a.dA2);
+  const uint4* am = reinterpret_cast<const uint4*>(a.a);
+  const uint4* y1 = reinterpret_cast<const uint4*>(a.y);
+  const uint4* y2 = reinterpret_cast<const uint4*>(a.y2);
+  const int CV = a.C >> 3, cv = c0 >> 3;
+  // ---- every load of this thread in flight at once ----
+  uint4 rg[E], rg2[E], ra[E], ry[E], rz[E];
+  size_t off[E];
+  bool ok[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const long long r = ((long long)e * S + rank) * 256 + tid;
+    ok[e] = r < a.rows;
+    off[e] = (size_t)(ok[e] ? r : 0) * CV + cv;
+    const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+    rg[e] = ok[e] ? dA[off[e]] : z4;
+    rg2[e] = (dA2 && ok[e]) ? dA2[off[e]] : z4;
+    ra[e] = (am && ok[e]) ? am[off[e]] : z4;
+    ry[e] = ok[e] ? y1[off[e]] : z4;
+    rz[e] = (two && ok[e]) ? y2[off[e]] : z4;
+  }
+  // ---- g = (dA [+ dA2]) * [a > 0] rounded to bf16 once (what the accumulate-in-place path stored); the three sums ----
+  float s[24];
+#pragma unroll
+  for (int k = 0; k < 24; ++k) s[k] = 0.f;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    float g[8], v[8];
+    bnc_unpack8(rg[e], g);
+    if (dA2) {
+      bnc_unpack8(rg2[e], v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) g[k] = __bfloat162float(__float2bfloat16_rn(g[k] + v[k]));
+    }
+    if (am) {
+      bnc_unpack8(ra[e], v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) g[k] = v[k] > 0.f ? g[k] : 0.f;
+    }
+    rg[e] = bnc_pack8(g);                              // exact: g is a bf16 value
+    bnc_unpack8(ry[e], v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      s[k] += g[k];
+      s[8 + k] = fmaf(g[k], fmaf(v[k], cst[0][0][k], cst[0][1][k]), s[8 + k]);
+    }
+    if (two) {
+      bnc_unpack8(rz[e], v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s[16 + k] = fmaf(g[k], fmaf(v[k], cst[1][0][k], cst[1][1][k]), s[16 + k]);
+    }
+  }
+  const int nsum = two ? 24 : 16;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+#pragma unroll
+    for (int k = 0; k < 24; ++k)
+      if (k < nsum) s[k] += __shfl_xor_sync(0xffffffffu, s[k], d);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 24; ++k) wred[wrp][k] = s[k];
+  }
+  __syncthreads();
+  if (tid < 24) {
+    float p = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) p += wred[w][tid];
+    for (uint32_t r = 0; r < S; ++r) bnc_st_peer_f32(&slots[rank][tid], r, p);
+  }
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (tid < 24) {
+    float t = 0.f;
+    for (uint32_t r = 0; r < S; ++r) t += slots[r][tid];
+    tot[tid] = t;
+  }
+  __syncthreads();
+  // ---- dY = gamma * rstd * (g - mean(g) - xhat * mean(g * xhat)) from the registers ----
+  const float im = (float)(1.0 / (double)a.rows);
+  if (rank == 0 && tid < 8) {
+    a.g_beta[c0 + tid] = tot[tid]; a.g_gamma[c0 + tid] = tot[8 + tid];
+    if (two) { a.g_beta2[c0 + tid] = tot[tid]; a.g_gamma2[c0 + tid] = tot[16 + tid]; }
+  }
+  uint4* dY = reinterpret_cast<uint4*>(a.dY);
+  uint4* dY2 = reinterpret_cast<uint4*>(a.dY2);
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    if (!ok[e]) continue;
+    float g[8], v[8], o[8];
+    bnc_unpack8(rg[e], g);
+    bnc_unpack8(ry[e], v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = cst[0][2][k] * (g[k] - tot[k] * im - fmaf(v[k], cst[0][0][k], cst[0][1][k]) * (tot[8 + k] * im));
+    dY[off[e]] = bnc_pack8(o);
+    if (two) {
+      bnc_unpack8(rz[e], v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = cst[1][2][k] * (g[k] - tot[k] * im - fmaf(v[k], cst[1][0][k], cst[1][1][k]) * (tot[16 + k] * im));
+      dY2[off[e]] = bnc_pack8(o);
+    }
+  }
+}
+
 // BatchNorm backward of a ONE-channel tensor (the decoder's output BatchNorm, model.py:173,193) whose incoming gradient is
 // fp32 (d recon from the loss): same scheme as bn_bwd_coop_kernel -- every thread keeps its (at most kCoopE) groups of 4
 // gradients and pre-activations in registers across the grid barrier -- for rows up to grid * 256 * 4 * kCoopE.
@@ -969,10 +1139,72 @@ static int sweep_max_ctas() {
   return v;
 }
 
+// largest cluster bn_bwd_cluster_kernel may be launched with on this device: 16 (non-portable, opted in) when the device can
+// hold at least one such cluster, else 8 (portable); cached per device
+static int bnc_max_cluster() {
+  static std::atomic<int> cached[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  int v = cached[dev].load();
+  if (v > 0) return v;
+  static const int cap = [] { const char* e = getenv("MMVAE_BN_CLUSTER_MAX"); return e ? atoi(e) : 8; }();   // A/B runs
+  v = 8;
+  if (cap >= 16) {
+    bool ok16 = true;
+    auto opt_in = [&](auto kern) {
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); ok16 = false; return; }
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(16); cfg.blockDim = dim3(256);
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 16; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); ok16 = false; }
+    };
+    opt_in(bn_bwd_cluster_kernel<1>); opt_in(bn_bwd_cluster_kernel<2>); opt_in(bn_bwd_cluster_kernel<4>);
+    if (ok16) v = 16;
+  } else if (cap >= 1) {
+    v = std::min(cap, 8);
+  }
+  cached[dev].store(v);
+  return v;
+}
+
+// cluster shape of bn_bwd_cluster_kernel for `rows` rows: the fewest rows per thread (E in 1, 2, 4) whose cluster (a power of
+// two of CTAs x 256 threads x E rows) stays portable (<= 8 CTAs), else E = 4 with up to `smax` CTAs; false: too many rows
+static bool bnc_shape(long long rows, int smax, int& E, int& S) {
+  for (int pass = 0; pass < 2; ++pass) {
+    const int lim = pass == 0 ? std::min(smax, 8) : smax;
+    for (int e = 1; e <= 4; e <<= 1) {
+      const long long need = (rows + 256LL * e - 1) / (256LL * e);
+      int s = 1;
+      while (s < need) s <<= 1;
+      if (s <= lim) { E = e; S = s; return true; }
+    }
+  }
+  return false;
+}
+
 template <typename T>
 void launch_bn_bwd(const BnBwdArgs& a, cudaStream_t st) {
   constexpr int V = vec_of<T>();
   if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+    // channel-partitioned clusters (no grid-wide synchronisation) for the small many-channel tensors
+    static const bool cluster_off = getenv("MMVAE_NO_BN_CLUSTER") != nullptr;
+    if (!cluster_off && !a.reduced && !a.dA_f32 && a.C % 8 == 0 && a.C >= 32) {
+      int E = 0, S = 0;
+      const int smax = bnc_max_cluster();
+      if (smax > 0 && bnc_shape(a.rows, smax, E, S)) {
+        const int grid = (a.C / 8) * S;
+        cudaError_t err;
+        if (E == 1) err = launch_pdl_cluster(bn_bwd_cluster_kernel<1>, grid, 256, 0, st, S, a);
+        else if (E == 2) err = launch_pdl_cluster(bn_bwd_cluster_kernel<2>, grid, 256, 0, st, S, a);
+        else err = launch_pdl_cluster(bn_bwd_cluster_kernel<4>, grid, 256, 0, st, S, a);
+        if (err == cudaSuccess) { count_launch(); return; }
+        cudaGetLastError();                            // could not be launched in this shape: the grid-barrier kernel below
+      }
+    }
     // one cooperative launch when every thread's share fits its registers: half a register file per SM for two CTAs,
     // so it stays co-resident with the weight-gradient kernels of the auxiliary stream
     static const bool coop_off = getenv("MMVAE_NO_COOP_BN") != nullptr;
