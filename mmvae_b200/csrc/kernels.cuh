@@ -340,6 +340,7 @@ struct BnBwdArgs {
   void* dY; void* dY2;     // outputs, storage type
   long long rows; int C;
   int dA_f32;
+  int late_loads;          // A/B (MMVAE_BN_LATE_LOADS): fetch the forward-written operands only after the dependency wait
 };
 template <typename T> void launch_bn_bwd(const BnBwdArgs& a, cudaStream_t st);
 

@@ -654,8 +654,6 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_coop_kernel(const BnBwdArgs a, 
 // kernels of the auxiliary stream and the tail of the previous kernel (the register-resident version needs a whole SM's
 // register file per CTA pair and, measured, waited 8-15 us for the SMs to drain: profiles/r02_bn_bwd.md).
 __global__ void __launch_bounds__(256, 4) bn_bwd_sweep_kernel(const BnBwdArgs a) {
-  pdl_wait();
-  pdl_trigger();
   typedef __nv_bfloat16 T;
   constexpr int VEC = 8;
   extern __shared__ float red[];                       // [3 sums][8 warps][C]: combined in a FIXED order (run-to-run
@@ -677,6 +675,16 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_sweep_kernel(const BnBwdArgs a)
   }
   const long long rstride = (long long)gridDim.x * RPI;
   const long long r0 = (long long)blockIdx.x * RPI + rsub;
+  // The ReLU output and the raw conv outputs were written by the FORWARD and are cold by now: their rows are pulled into L2
+  // under the predecessor's tail, before the dependency wait; only the incoming gradient is the predecessor's.
+  for (long long r = r0; r < a.rows && !a.late_loads; r += rstride) {
+    const size_t off = size_t(r) * a.C + c0;
+    if (am) asm volatile("prefetch.global.L2 [%0];" ::"l"(am + off));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(y1 + off));
+    if (y2) asm volatile("prefetch.global.L2 [%0];" ::"l"(y2 + off));
+  }
+  pdl_wait();
+  pdl_trigger();
   // g = (dA [+ dA2]) * [a > 0], rounded to the storage type once (what the accumulate-in-place path stored)
   auto load_g = [&](size_t off, float (&g)[VEC]) {
     load_vec<T, VEC>(dA + off, g);
@@ -816,6 +824,11 @@ __device__ __forceinline__ void bnc_st_peer_f32(const float* local, uint32_t ran
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
 }
+__device__ __forceinline__ uint4 ld_cg_u4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void bnc_unpack8(const uint4& u, float (&v)[8]) {
   v[0] = __uint_as_float(u.x << 16); v[1] = __uint_as_float(u.x & 0xffff0000u);
   v[2] = __uint_as_float(u.y << 16); v[3] = __uint_as_float(u.y & 0xffff0000u);
@@ -854,29 +867,43 @@ __global__ void __launch_bounds__(256, E <= 2 ? 3 : 2) bn_bwd_cluster_kernel(con
     }
   }
   __syncthreads();
-  pdl_wait();
-  pdl_trigger();
   const uint4* dA = reinterpret_cast<const uint4*>(a.dA);
   const uint4* dA2 = reinterpret_cast<const uint4*>(a.dA2);
   const uint4* am = reinterpret_cast<const uint4*>(a.a);
   const uint4* y1 = reinterpret_cast<const uint4*>(a.y);
   const uint4* y2 = reinterpret_cast<const uint4*>(a.y2);
   const int CV = a.C >> 3, cv = c0 >> 3;
-  // ---- every load of this thread in flight at once ----
+  // ---- every load of this thread in flight at once.  The ReLU output and the raw conv outputs were written by the
+  // FORWARD (cold in L2 by now, ~1 us from HBM): they are fetched BEFORE the dependency wait, under the predecessor's tail;
+  // only the incoming gradient is the predecessor's ----
   uint4 rg[E], rg2[E], ra[E], ry[E], rz[E];
   size_t off[E];
   bool ok[E];
+  const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
   for (int e = 0; e < E; ++e) {
     const long long r = ((long long)e * S + rank) * 256 + tid;
     ok[e] = r < a.rows;
     off[e] = (size_t)(ok[e] ? r : 0) * CV + cv;
-    const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+    const bool early = ok[e] && !a.late_loads;
+    ra[e] = (am && early) ? am[off[e]] : z4;
+    ry[e] = early ? y1[off[e]] : z4;
+    rz[e] = (two && early) ? y2[off[e]] : z4;
+  }
+  pdl_wait();
+  pdl_trigger();
+  if (a.late_loads) {
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      ra[e] = (am && ok[e]) ? ld_cg_u4(am + off[e]) : z4;
+      ry[e] = ok[e] ? ld_cg_u4(y1 + off[e]) : z4;
+      rz[e] = (two && ok[e]) ? ld_cg_u4(y2 + off[e]) : z4;
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
     rg[e] = ok[e] ? dA[off[e]] : z4;
     rg2[e] = (dA2 && ok[e]) ? dA2[off[e]] : z4;
-    ra[e] = (am && ok[e]) ? am[off[e]] : z4;
-    ry[e] = ok[e] ? y1[off[e]] : z4;
-    rz[e] = (two && ok[e]) ? y2[off[e]] : z4;
   }
   // ---- g = (dA [+ dA2]) * [a > 0] rounded to bf16 once (what the accumulate-in-place path stored); the three sums ----
   float s[24];
@@ -1187,8 +1214,11 @@ static bool bnc_shape(long long rows, int smax, int& E, int& S) {
 }
 
 template <typename T>
-void launch_bn_bwd(const BnBwdArgs& a, cudaStream_t st) {
+void launch_bn_bwd(const BnBwdArgs& a_in, cudaStream_t st) {
   constexpr int V = vec_of<T>();
+  BnBwdArgs a = a_in;
+  static const bool late = getenv("MMVAE_BN_LATE_LOADS") != nullptr;
+  a.late_loads = late ? 1 : 0;
   if constexpr (std::is_same<T, __nv_bfloat16>::value) {
     // channel-partitioned clusters (no grid-wide synchronisation) for the small many-channel tensors
     static const bool cluster_off = getenv("MMVAE_NO_BN_CLUSTER") != nullptr;
