@@ -843,6 +843,106 @@ __device__ __forceinline__ uint4 bnc_pack8(const float (&v)[8]) {
   return make_uint4(bnc_pack2(v[0], v[1]), bnc_pack2(v[2], v[3]), bnc_pack2(v[4], v[5]), bnc_pack2(v[6], v[7]));
 }
 
+// bn_bwd_apply for bf16 storage with the per-channel algebra hoisted out of the streaming loop: the grid stride is a
+// multiple of C, so a thread sees ONE vector of 8 channels for its whole life and dY = A * g + B * y + D with three
+// coefficients per channel and branch kept in registers (the generic kernel re-loads ten coefficient vectors per
+// iteration: more LSU instructions than data loads).  Two vectors per trip, every load issued before the first use.
+// `reverse`: walk the tensor from its END: the producer of dA (and of the forward tensors it re-read) walked it from the
+// start, so the end is what is still in L2 (126 MB against 134-168 MB touched by the uplayer5 / tail kernels).
+__global__ void __launch_bounds__(256) bn_bwd_apply_bf16_kernel(const BnBwdArgs a, int reverse) {
+  const long long nvec = a.rows * a.C / 8;
+  const long long stride = (long long)gridDim.x * 256;
+  const long long i0 = blockIdx.x * 256LL + threadIdx.x;
+  const int c0 = (int)((i0 * 8) % a.C);
+  const bool two = a.y2 != nullptr;
+  float mean[8], rstd[8], mean2[8], rstd2[8];
+  load_coef<8>(a.stat + c0, mean); load_coef<8>(a.stat + a.C + c0, rstd);      // written by the forward
+  if (two) { load_coef<8>(a.stat2 + c0, mean2); load_coef<8>(a.stat2 + a.C + c0, rstd2); }
+  pdl_wait();
+  pdl_trigger();
+  if (a.reduced && blockIdx.x == 0) {
+    for (int c = threadIdx.x; c < a.C; c += 256) {
+      a.g_beta[c] = a.bcoef[3 * a.C + c]; a.g_gamma[c] = a.bcoef[4 * a.C + c];
+      if (two) { a.g_beta2[c] = a.bcoef2[3 * a.C + c]; a.g_gamma2[c] = a.bcoef2[4 * a.C + c]; }
+    }
+  }
+  float A[8], B[8], D[8], A2[8], B2[8], D2[8];
+  {
+    float b0[8], b1[8], b2[8];
+    load_coef<8>(a.bcoef + c0, b0); load_coef<8>(a.bcoef + a.C + c0, b1); load_coef<8>(a.bcoef + 2 * a.C + c0, b2);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float t = b0[k] * b2[k] * rstd[k];
+      A[k] = b0[k]; B[k] = -t; D[k] = fmaf(t, mean[k], -b0[k] * b1[k]);
+    }
+    if (two) {
+      load_coef<8>(a.bcoef2 + c0, b0); load_coef<8>(a.bcoef2 + a.C + c0, b1); load_coef<8>(a.bcoef2 + 2 * a.C + c0, b2);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float t = b0[k] * b2[k] * rstd2[k];
+        A2[k] = b0[k]; B2[k] = -t; D2[k] = fmaf(t, mean2[k], -b0[k] * b1[k]);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { A2[k] = 0.f; B2[k] = 0.f; D2[k] = 0.f; }
+    }
+  }
+  const uint4* dA = reinterpret_cast<const uint4*>(a.dA);
+  const uint4* dA2 = reinterpret_cast<const uint4*>(a.dA2);
+  const uint4* am = reinterpret_cast<const uint4*>(a.a);
+  const uint4* y1 = reinterpret_cast<const uint4*>(a.y);
+  const uint4* y2 = reinterpret_cast<const uint4*>(a.y2);
+  uint4* dY = reinterpret_cast<uint4*>(a.dY);
+  uint4* dY2 = reinterpret_cast<uint4*>(a.dY2);
+  const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+  const long long rbase = nvec - (a.C >> 3) + 2 * (c0 >> 3);     // mirrored row, same vector within the row
+#pragma unroll 1
+  for (long long i = i0; i < nvec; i += 2 * stride) {
+    uint4 qg[2], qg2[2], qa[2], qy[2], qz[2];
+    long long j[2];
+    bool ok[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long long iu = i + u * stride;
+      ok[u] = iu < nvec;
+      // reverse: the same thread <-> channel-vector assignment, rows from the end (nvec - 1 - i is congruent to a different
+      // channel vector, so the vector INDEX within the row is kept and only the row order is mirrored)
+      j[u] = ok[u] ? (reverse ? rbase - iu : iu) : 0;
+      qg[u] = ok[u] ? dA[j[u]] : z4;
+      qg2[u] = (dA2 && ok[u]) ? dA2[j[u]] : z4;
+      qa[u] = (am && ok[u]) ? am[j[u]] : z4;
+      qy[u] = ok[u] ? y1[j[u]] : z4;
+      qz[u] = (two && ok[u]) ? y2[j[u]] : z4;
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (!ok[u]) continue;
+      float g[8], v[8], o[8];
+      bnc_unpack8(qg[u], g);
+      if (dA2) {
+        bnc_unpack8(qg2[u], v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) g[k] = __bfloat162float(__float2bfloat16_rn(g[k] + v[k]));
+      }
+      if (am) {
+        bnc_unpack8(qa[u], v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) g[k] = v[k] > 0.f ? g[k] : 0.f;
+      }
+      bnc_unpack8(qy[u], v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = fmaf(A[k], g[k], fmaf(B[k], v[k], D[k]));
+      dY[j[u]] = bnc_pack8(o);
+      if (two) {
+        bnc_unpack8(qz[u], v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = fmaf(A2[k], g[k], fmaf(B2[k], v[k], D2[k]));
+        dY2[j[u]] = bnc_pack8(o);
+      }
+    }
+  }
+}
+
 constexpr int kBncMaxCluster = 16;
 
 template <int E>
@@ -1302,6 +1402,16 @@ void launch_bn_bwd(const BnBwdArgs& a_in, cudaStream_t st) {
     bn_bwd_finalize_kernel<<<a.C, 128, 0, st>>>(a, nblocks, a.rows);
   }
   long long total = a.rows * a.C;
+  if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+    // hoisted-coefficient kernel: needs a thread's channel vector to be loop-invariant (grid stride a multiple of C / 8)
+    static const int apply_mode = [] { const char* e = getenv("MMVAE_BN_APPLY"); return e ? atoi(e) : 3; }();   // A/B: bit 0 fast kernel, bit 1 reverse
+    const int grid = grid_for(total / V);
+    if ((apply_mode & 1) && !a.dA_f32 && a.C % 8 == 0 && ((long long)grid * 256) % (a.C / 8) == 0) {
+      count_launch();
+      launch_pdl(bn_bwd_apply_bf16_kernel, grid, 256, 0, st, a, (apply_mode >> 1) & 1);
+      return;
+    }
+  }
   if (a.C % V == 0) { count_launch(); launch_pdl(bn_bwd_apply_kernel<T, V>, grid_for(total / V), 256, 0, st, a); }
   else { count_launch(); launch_pdl(bn_bwd_apply_kernel<T, 1>, grid_for(total), 256, 0, st, a); }
 }
