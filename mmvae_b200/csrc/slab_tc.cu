@@ -213,9 +213,14 @@ __global__ void __launch_bounds__(kFwdThreads, 1) slab_fwd_kernel(const __grid_c
     // ---------------- epilogue: set `es` drains accumulator `es` (tiles es, es + kFwdSets, ...) ----------------
     const int ew = warp - 5, es = ew >> 2, q = warp & 3;
     const bool stats = p.bn.acc != nullptr;
-    float run_s[16], run_q[16];
+    // BatchNorm sums of this thread's rows, two channels per 64-bit register (FADD2 / FFMA2): the epilogue sets are bound
+    // by instruction issue (3 warps per scheduler: profiles/r02_slab_epilogue.md), so the statistics are taken from the
+    // fp32 accumulators as they come out of TMEM -- no unpacking of the rounded pairs, 4 packed instructions per 4 values
+    // instead of 12 scalar ones.  (The mean / variance of the unrounded values differ from those of the stored bf16 values
+    // by the mean of ~1e6 independent rounding errors per channel: ~1e-6 relative.)
+    unsigned long long rs2[8], rq2[8];
 #pragma unroll
-    for (int e = 0; e < 16; ++e) { run_s[e] = 0.f; run_q[e] = 0.f; }
+    for (int e = 0; e < 8; ++e) { rs2[e] = 0ull; rq2[e] = 0ull; }
     const int r = q * 32 + lane;
     for (int gt = es;; gt += kFwdSets) {
       const int it = gt / G.T, t = gt - it * G.T;
@@ -234,32 +239,29 @@ __global__ void __launch_bounds__(kFwdThreads, 1) slab_fwd_kernel(const __grid_c
       const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * 64);
 #pragma unroll
       for (int py = 0; py < 2; ++py) {
-        float v0[16], v1[16];
-        {                                            // both loads in flight, one wait
-          uint32_t r0[16], r1[16];
-          tmem_ld16_issue(tl + (uint32_t)(py * 32), r0);
-          tmem_ld16_issue(tl + (uint32_t)(py * 32 + 16), r1);
-          tmem_ld_wait();
-#pragma unroll
-          for (int e = 0; e < 16; ++e) { v0[e] = __uint_as_float(r0[e]); v1[e] = __uint_as_float(r1[e]); }
-        }
+        uint32_t r0[16], r1[16];                     // both loads in flight, one wait
+        tmem_ld16_issue(tl + (uint32_t)(py * 32), r0);
+        tmem_ld16_issue(tl + (uint32_t)(py * 32 + 16), r1);
+        tmem_ld_wait();
         if (valid) {
           uint4* dst = reinterpret_cast<uint4*>(p.y + (((size_t)n * 2 * G.H + 2 * i + py) * 2 * G.W + 2 * j) * 16);
           uint32_t pk[16];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) { pk[e] = pack_bf16x2(v0[2 * e], v0[2 * e + 1]); pk[8 + e] = pack_bf16x2(v1[2 * e], v1[2 * e + 1]); }
+          for (int e = 0; e < 8; ++e) {
+            pk[e] = pack_bf16x2(__uint_as_float(r0[2 * e]), __uint_as_float(r0[2 * e + 1]));
+            pk[8 + e] = pack_bf16x2(__uint_as_float(r1[2 * e]), __uint_as_float(r1[2 * e + 1]));
+          }
           dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           dst[2] = make_uint4(pk[8], pk[9], pk[10], pk[11]);
           dst[3] = make_uint4(pk[12], pk[13], pk[14], pk[15]);
           if (stats) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {            // statistics over the values as stored: unpack the rounded pairs
-              const float a0 = __uint_as_float(pk[e] << 16), a1 = __uint_as_float(pk[e] & 0xffff0000u);
-              const float b0 = __uint_as_float(pk[8 + e] << 16), b1 = __uint_as_float(pk[8 + e] & 0xffff0000u);
-              run_s[2 * e] += a0 + b0; run_s[2 * e + 1] += a1 + b1;
-              run_q[2 * e] = fmaf(a0, a0, fmaf(b0, b0, run_q[2 * e]));
-              run_q[2 * e + 1] = fmaf(a1, a1, fmaf(b1, b1, run_q[2 * e + 1]));
+            for (int e = 0; e < 8; ++e) {            // channels (2e, 2e + 1) of the two output columns px = 0, 1
+              const unsigned long long a2 = f2_pack(__uint_as_float(r0[2 * e]), __uint_as_float(r0[2 * e + 1]));
+              const unsigned long long b2 = f2_pack(__uint_as_float(r1[2 * e]), __uint_as_float(r1[2 * e + 1]));
+              rs2[e] = f2_add(rs2[e], f2_add(a2, b2));
+              rq2[e] = f2_fma(a2, a2, f2_fma(b2, b2, rq2[e]));
             }
           }
         }
@@ -268,6 +270,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) slab_fwd_kernel(const __grid_c
       mbar_arrive(smem_u32(&tempty[ab]));
       if (gt == 0 && ew == 0 && lane == 0) SLAB_TRACE(p, 11);
     }
+    float run_s[16], run_q[16];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { f2_unpack(rs2[e], run_s[2 * e], run_s[2 * e + 1]); f2_unpack(rq2[e], run_q[2 * e], run_q[2 * e + 1]); }
     if (ew == 0 && lane == 0) SLAB_TRACE(p, 12);
     if (stats) {
       const int lane_col = warp_colsum16(run_s, lane);

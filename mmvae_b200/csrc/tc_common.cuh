@@ -296,6 +296,27 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// Packed fp32 pairs (FADD2 / FFMA2 on sm_100: one issue slot for two lanes of epilogue arithmetic).  The operands are
+// 64-bit registers holding {x, y}; ptxas allocates the halves as an aligned pair, the moves in and out are free.
+__device__ __forceinline__ unsigned long long f2_pack(float x, float y) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(unsigned long long v, float& x, float& y) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
 // Sum over the 32 rows held by the lanes of a warp of 16 per-thread column values: a transposing
 // butterfly (16 shuffles).  Returns the column this lane ends up owning; its sum is in v[0]
 // (lanes 2c and 2c+1 hold the same column).
