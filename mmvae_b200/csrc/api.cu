@@ -152,6 +152,17 @@ static AuxPool* aux_pool() {
 // ------------------------------------------------------------------------------------------------
 // step executor
 // ------------------------------------------------------------------------------------------------
+// The stem BatchNorm's backward folded into the stem weight gradient's loader (stem_tc.cu, kFuse): bf16 tensor-core path
+// with the tcgen05 stem weight gradient available.  Then the gradient of the raw stem output is never materialised
+// (mmvae_workspace_tensor reports it as absent).  MMVAE_NO_STEM_BWD_FUSE: A/B and the stored-dY validation path.
+static bool stem_bwd_fused(const Plan& P) {
+  static const bool off = getenv("MMVAE_NO_STEM_BWD_FUSE") != nullptr;
+  if (off || P.d.arch != MMVAE_ARCH_RESNET || P.d.precision != MMVAE_PREC_BF16 || (P.d.flags & MMVAE_FLAG_FORCE_SIMT) || P.stem < 0)
+    return false;
+  const ConvT_& c = P.convs[P.stem];
+  return c.in < 0 && stem_supported(c.Ci, c.Co, c.Hi, c.k, c.s, c.p) && stem_wgrad_tc_supported(c.Co, c.Hi);
+}
+
 template <typename T>
 struct Exec {
   const Plan& P;
@@ -490,7 +501,7 @@ struct Exec {
   }
 
   // BatchNorm (+ReLU mask from `mask_act`) backward of conv c (and of the parallel branch c2)
-  void bn_bwd(const void* dA, int dA_f32, int mask_act, const ConvT_& c, const ConvT_* c2) {
+  void bn_bwd(const void* dA, int dA_f32, int mask_act, const ConvT_& c, const ConvT_* c2, bool no_apply = false) {
     const BnT& b = P.bns[c.bn];
     BnBwdArgs a;
     memset(&a, 0, sizeof(a));
@@ -513,6 +524,7 @@ struct Exec {
     if (mask_act >= 0 && fused_reduce(mask_act)) { a.reduced = 1; a.a = nullptr; }   // dA arrives masked and reduced
     if (mask_act >= 0 && !dA_f32 && dA == (const void*)at<T>(act(mask_act).goff) && split_grad(mask_act))
       a.dA2 = at<T>(act(mask_act).goff2);
+    a.no_apply = no_apply ? 1 : 0;
     launch_bn_bwd<T>(a, st);
   }
 
@@ -787,8 +799,23 @@ struct Exec {
       block_bwd(P.enc[1]);
       block_bwd(P.enc[0]);
       const ConvT_& s = P.convs[P.stem];
-      bn_bwd(at<T>(act(P.a_stem).goff), 0, P.a_stem, s, nullptr);
-      wgrad(s);
+      if (stem_bwd_fused(P) && use_stem(s) && !fused_reduce(P.a_stem)) {
+        // the stem BatchNorm's backward is one reduction pass; the weight-gradient kernel forms dY in its loader from
+        // (gradient parts, ReLU output, raw conv output) and the reduction's coefficients: dY is never stored
+        bn_bwd(at<T>(act(P.a_stem).goff), 0, P.a_stem, s, nullptr, true);
+        const BnT& b = P.bns[s.bn];
+        StemArgs a{};
+        a.x = x; a.dw = grads + s.w; a.N = P.d.batch; a.S = s.Hi;
+        a.g1 = at<__nv_bfloat16>(act(P.a_stem).goff);
+        a.g2 = split_grad(P.a_stem) ? at<__nv_bfloat16>(act(P.a_stem).goff2) : nullptr;
+        a.mask = at<__nv_bfloat16>(act(P.a_stem).off);
+        a.yraw = at<__nv_bfloat16>(act(s.out).off);
+        a.stat = at<float>(b.stat_off); a.bcoef = at<float>(b.bcoef_off);
+        launch_stem_wgrad(a, s.Co, st);
+      } else {
+        bn_bwd(at<T>(act(P.a_stem).goff), 0, P.a_stem, s, nullptr);
+        wgrad(s);
+      }
       forked = forked || (aux != nullptr);     // earlier phases may have left un-joined work on the auxiliary stream
       join();
     }
@@ -882,6 +909,8 @@ int mmvae_workspace_tensor(const mmvae_desc* d, const char* name, int64_t* byte_
   const ActT* a = P.find_act(nm.c_str());
   if (!a) return fail(MMVAE_ERR_BAD_ARG, "no workspace tensor named '%s'", name);
   if (grad2 && a->goff2 == 0) return fail(MMVAE_ERR_BAD_ARG, "'%s' has no second gradient buffer", nm.c_str());
+  if (grad && P.stem >= 0 && a == &P.acts[P.convs[P.stem].out] && stem_bwd_fused(P))
+    return fail(MMVAE_ERR_BAD_ARG, "'%s' is not materialised: the stem weight gradient forms it in its loader", name);
   if (byte_offset) *byte_offset = (int64_t)(grad2 ? a->goff2 : (grad ? a->goff : a->off));
   if (dims) { dims[0] = P.d.batch; dims[1] = a->H; dims[2] = a->W; dims[3] = a->C; }
   return 0;

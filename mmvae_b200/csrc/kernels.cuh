@@ -232,6 +232,14 @@ struct StemArgs {
   float* partials;             // forward: [tiles][Co][2] or nullptr
   BnFused bn;                  // forward: fused statistics when bn.acc != nullptr (then `partials` is unused)
   const __nv_bfloat16* dy;     // wgrad: dY [N,Ho,Wo,Co]
+  // wgrad with the stem BatchNorm's backward folded into its loader (yraw != nullptr; `dy` unused): dY is formed on the fly
+  // as scale * (g - c1 - xhat * c2), g = bf16(g1 [+ g2]) * [mask > 0], and never stored (launch_stem_wgrad_tc only)
+  const __nv_bfloat16* g1;     // gradient of the stem's ReLU output (main part)
+  const __nv_bfloat16* g2;     // its second part (shortcut branch) or nullptr
+  const __nv_bfloat16* mask;   // the ReLU output
+  const __nv_bfloat16* yraw;   // the raw conv output
+  const float* stat;           // [2][Co]: mean, rstd (forward)
+  const float* bcoef;          // [3][Co]: scale, c1, c2 (bn_bwd_reduce's finalize)
   float* dw;                   // wgrad: gradient arena slot (atomically accumulated; pre-zeroed)
   int N, S;
   int Ho, Wo, R, tiles_per_frame, ntiles;   // filled by the launcher
@@ -340,6 +348,7 @@ struct BnBwdArgs {
   void* dY; void* dY2;     // outputs, storage type
   long long rows; int C;
   int dA_f32;
+  int no_apply;            // reduce + finalize only (bcoef, d gamma, d beta): the consumer of dY forms it itself
   int late_loads;          // A/B (MMVAE_BN_LATE_LOADS): fetch the forward-written operands only after the dependency wait
 };
 template <typename T> void launch_bn_bwd(const BnBwdArgs& a, cudaStream_t st);

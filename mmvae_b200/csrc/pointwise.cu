@@ -843,6 +843,108 @@ __device__ __forceinline__ uint4 bnc_pack8(const float (&v)[8]) {
   return make_uint4(bnc_pack2(v[0], v[1]), bnc_pack2(v[2], v[3]), bnc_pack2(v[4], v[5]), bnc_pack2(v[6], v[7]));
 }
 
+// BatchNorm-backward REDUCTION alone for a large bf16 tensor whose dY is formed by its consumer (the fused stem backward:
+// BnBwdArgs::no_apply): raw moments sum g, sum g*y in fp32 per thread (centred per CTA: S1 = rstd * (sum g*y - mean * S0)),
+// two rows per trip with all eight loads issued first, the forward-written operands pulled into L2 before the dependency
+// wait, fixed-order shared-memory reduction, fp64 atomics across CTAs, and the CTA that finishes last writes the
+// coefficients (scale, c1, c2) and d gamma / d beta.  One branch only (no y2).
+__global__ void __launch_bounds__(256, 4) bn_bwd_reduce_bf16_kernel(const BnBwdArgs a) {
+  extern __shared__ float red[];                       // [2 sums][8 warps][C]
+  __shared__ int is_last;
+  const int CV = a.C / 8, RPI = 256 / CV;
+  const int tid = threadIdx.x;
+  const int cv = tid % CV, rsub = tid / CV;
+  const uint4* dA = reinterpret_cast<const uint4*>(a.dA);
+  const uint4* dA2 = reinterpret_cast<const uint4*>(a.dA2);
+  const uint4* am = reinterpret_cast<const uint4*>(a.a);
+  const uint4* y1 = reinterpret_cast<const uint4*>(a.y);
+  const long long rstride = (long long)gridDim.x * RPI;
+  const long long r0 = (long long)blockIdx.x * RPI + rsub;
+  for (long long r = r0; r < a.rows; r += rstride) {
+    const size_t off = size_t(r) * CV + cv;
+    if (am) asm volatile("prefetch.global.L2 [%0];" ::"l"(am + off));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(y1 + off));
+  }
+  pdl_wait();
+  pdl_trigger();
+  float s0[8], s1[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { s0[k] = 0.f; s1[k] = 0.f; }
+  const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll 1
+  for (long long r = r0; r < a.rows; r += 2 * rstride) {
+    uint4 qg[2], qg2[2], qa[2], qy[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long long ru = r + u * rstride;
+      const bool ok = ru < a.rows;
+      const size_t off = size_t(ok ? ru : 0) * CV + cv;
+      qg[u] = ok ? dA[off] : z4;
+      qg2[u] = (dA2 && ok) ? dA2[off] : z4;
+      qa[u] = (am && ok) ? am[off] : z4;
+      qy[u] = ok ? y1[off] : z4;
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      float g[8], v[8];
+      bnc_unpack8(qg[u], g);
+      if (dA2) {
+        bnc_unpack8(qg2[u], v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) g[k] = __bfloat162float(__float2bfloat16_rn(g[k] + v[k]));
+      }
+      if (am) {
+        bnc_unpack8(qa[u], v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) g[k] = v[k] > 0.f ? g[k] : 0.f;
+      }
+      bnc_unpack8(qy[u], v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { s0[k] += g[k]; s1[k] = fmaf(g[k], v[k], s1[k]); }
+    }
+  }
+  for (int d = CV; d < 32; d <<= 1) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      s0[k] += __shfl_xor_sync(0xffffffffu, s0[k], d);
+      s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], d);
+    }
+  }
+  const int wrp = tid >> 5, c0 = cv * 8;
+  if ((tid & 31) < CV) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { red[(0 * 8 + wrp) * a.C + c0 + k] = s0[k]; red[(1 * 8 + wrp) * a.C + c0 + k] = s1[k]; }
+  }
+  __syncthreads();
+  for (int e = tid; e < 2 * a.C; e += 256) {
+    const int which = e / a.C, c = e - which * a.C;
+    float sum = 0.f, t0 = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { sum += red[(which * 8 + q) * a.C + c]; t0 += red[q * a.C + c]; }
+    if (which == 1) sum = a.stat[a.C + c] * (sum - a.stat[c] * t0);
+    atomicAdd(a.acc + (size_t)(blockIdx.x % kBnAccCopies) * 3 * a.C + which * a.C + c, (double)sum);
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) is_last = (atomicAdd(a.counter, 1u) == gridDim.x - 1u) ? 1 : 0;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const double im = 1.0 / (double)a.rows;
+  for (int c = tid; c < a.C; c += 256) {
+    double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < kBnAccCopies; ++k) {
+      const double* ak = a.acc + (size_t)k * 3 * a.C;
+      t0 += ld_cg_f64(ak + c); t1 += ld_cg_f64(ak + a.C + c);
+    }
+    a.g_beta[c] = (float)t0; a.g_gamma[c] = (float)t1;
+    a.bcoef[c] = a.gamma[c] * a.stat[a.C + c];
+    a.bcoef[a.C + c] = (float)(t0 * im);
+    a.bcoef[2 * a.C + c] = (float)(t1 * im);
+  }
+}
+
 // bn_bwd_apply for bf16 storage with the per-channel algebra hoisted out of the streaming loop: the grid stride is a
 // multiple of C, so a thread sees ONE vector of 8 channels for its whole life and dY = A * g + B * y + D with three
 // coefficients per channel and branch kept in registers (the generic kernel re-loads ten coefficient vectors per
@@ -1322,7 +1424,7 @@ void launch_bn_bwd(const BnBwdArgs& a_in, cudaStream_t st) {
   if constexpr (std::is_same<T, __nv_bfloat16>::value) {
     // channel-partitioned clusters (no grid-wide synchronisation) for the small many-channel tensors
     static const bool cluster_off = getenv("MMVAE_NO_BN_CLUSTER") != nullptr;
-    if (!cluster_off && !a.reduced && !a.dA_f32 && a.C % 8 == 0 && a.C >= 32) {
+    if (!cluster_off && !a.no_apply && !a.reduced && !a.dA_f32 && a.C % 8 == 0 && a.C >= 32) {
       int E = 0, S = 0;
       const int smax = bnc_max_cluster();
       if (smax > 0 && bnc_shape(a.rows, smax, E, S)) {
@@ -1341,7 +1443,7 @@ void launch_bn_bwd(const BnBwdArgs& a_in, cudaStream_t st) {
     static const bool sweep_off = getenv("MMVAE_NO_BN_SWEEP") != nullptr;       // A/B: the register-resident kernel below
     static const long long sweep_max = [] { const char* e = getenv("MMVAE_BN_SWEEP_MAX_MB"); return (long long)(e ? atoi(e) : 1 << 20) << 20; }();
     const int CV = a.C / 8;
-    if (!coop_off && !sweep_off && a.acc && !a.reduced && !a.dA_f32 && a.C % 8 == 0 && CV >= 1 && CV <= 32 && 256 % CV == 0 &&
+    if (!coop_off && !sweep_off && !a.no_apply && a.acc && !a.reduced && !a.dA_f32 && a.C % 8 == 0 && CV >= 1 && CV <= 32 && 256 % CV == 0 &&
         a.rows * a.C * 2 <= sweep_max) {
       const int RPI = 256 / CV;
       const long long row_groups = (a.rows + RPI - 1) / RPI;
@@ -1352,7 +1454,7 @@ void launch_bn_bwd(const BnBwdArgs& a_in, cudaStream_t st) {
         return;
       }
     }
-    if (!coop_off && a.acc && !a.reduced && !a.dA_f32 && a.C % 8 == 0 && CV >= 1 && CV <= 32 && 256 % CV == 0) {
+    if (!coop_off && !a.no_apply && a.acc && !a.reduced && !a.dA_f32 && a.C % 8 == 0 && CV >= 1 && CV <= 32 && 256 % CV == 0) {
       const int RPI = 256 / CV;
       const long long row_groups = (a.rows + RPI - 1) / RPI;
       // up to two CTAs per SM (__launch_bounds__(256, 2), 34 KB of shared memory each): tensors up to 4.8 MB.  Whatever
@@ -1383,6 +1485,17 @@ void launch_bn_bwd(const BnBwdArgs& a_in, cudaStream_t st) {
       }
     }
   }
+  if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+    const int CV = a.C / 8;
+    if (a.no_apply && a.acc && !a.reduced && !a.dA_f32 && !a.y2 && a.C % 8 == 0 && CV >= 1 && CV <= 32 && 256 % CV == 0) {
+      const int RPI = 256 / CV;
+      const long long row_groups = (a.rows + RPI - 1) / RPI;
+      const int grid = (int)std::min<long long>(148 * 4, row_groups);
+      count_launch();
+      launch_pdl(bn_bwd_reduce_bf16_kernel, grid, 256, sizeof(float) * 2 * 8 * a.C, st, a);
+      return;
+    }
+  }
   const bool vec_ok = (a.C % V == 0) && (a.C / V <= 256);
   int nblocks;
   if (vec_ok) {
@@ -1401,6 +1514,7 @@ void launch_bn_bwd(const BnBwdArgs& a_in, cudaStream_t st) {
     count_launch();
     bn_bwd_finalize_kernel<<<a.C, 128, 0, st>>>(a, nblocks, a.rows);
   }
+  if (a.no_apply) return;                            // the consumer of dY forms it from bcoef itself (fused stem backward)
   long long total = a.rows * a.C;
   if constexpr (std::is_same<T, __nv_bfloat16>::value) {
     // hoisted-coefficient kernel: needs a thread's channel vector to be loop-invariant (grid stride a multiple of C / 8)

@@ -249,6 +249,12 @@ __global__ void __launch_bounds__(128, CO == 32 ? 4 : 3) stem_fwd_tc_kernel(cons
 // into whatever shared memory follows (inside the allocation; those accumulator rows are never read).  x is split into a
 // bf16 head and tail (two MMAs per 16 pixels), dY is bf16 already: the result matches the fp32 SIMT kernel to ~1e-6.
 // One TMEM accumulator lives for the CTA's whole life; 16 MMAs per 128-pixel tile; the epilogue is 25 x 32 atomics per CTA.
+// kFuse: the B operand is not a stored dY but the stem BatchNorm's backward evaluated in the loader: a thread owns one
+// 16-byte channel chunk (8 channels: tid & 3) of 4 pixels of the tile, keeps dY = A * g + B * y + D as three coefficients
+// per channel in registers, holds the NEXT tile's four raw vectors (g1, g2, mask, y) in registers while the current tile's
+// MMAs run, and writes the bf16 dY chunk straight into the operand plane (st.shared): dY never touches HBM, and the
+// BatchNorm backward of the 16.8 MB stem output is one reduction pass instead of reduce + grid barrier + apply.
+template <bool kFuse>
 __global__ void __launch_bounds__(128, 3) stem_wgrad_tc_kernel(const StemArgs a) {
   constexpr int CO = 32;
   extern __shared__ __align__(128) unsigned char stc_smem[];
@@ -276,8 +282,6 @@ __global__ void __launch_bounds__(128, 3) stem_wgrad_tc_kernel(const StemArgs a)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
-  pdl_wait();
-  pdl_trigger();
   const int wo_log2 = 31 - __clz(a.Wo);
   const int ry = tid >> wo_log2, ox = tid & (a.Wo - 1);
   const uint32_t idesc = make_idesc_bf16(128, CO, 1, 1);                        // both operands MN-major
@@ -285,18 +289,83 @@ __global__ void __launch_bounds__(128, 3) stem_wgrad_tc_kernel(const StemArgs a)
   // stage tile `tile` into slot `slot`: the x halo tile and the 128 x CO dY tile (chunk c of pixel p -> plane c, row p)
   auto prefetch = [&](int tile, int slot) {
     stem_tc_prefetch(a, tile, xs3[slot]);
-    const int n = tile / a.tiles_per_frame, oy0 = (tile - n * a.tiles_per_frame) * a.R;
-    const unsigned char* src = reinterpret_cast<const unsigned char*>(a.dy + (((size_t)n * a.Ho + oy0) * a.Wo) * CO);
-    const uint32_t dst = b_base + (uint32_t)(slot * kBBuf);
+    if constexpr (!kFuse) {
+      const int n = tile / a.tiles_per_frame, oy0 = (tile - n * a.tiles_per_frame) * a.R;
+      const unsigned char* src = reinterpret_cast<const unsigned char*>(a.dy + (((size_t)n * a.Ho + oy0) * a.Wo) * CO);
+      const uint32_t dst = b_base + (uint32_t)(slot * kBBuf);
 #pragma unroll
-    for (int i = 0; i < CO / 8; ++i) {
-      const int e = tid + i * 128, p = e >> 2, c = e & 3;                       // CO / 8 == 4 chunks per pixel
-      cp_async16(dst + (uint32_t)(c * kPlane + p * 16), src + (size_t)p * (CO * 2) + c * 16, 16u);
+      for (int i = 0; i < CO / 8; ++i) {
+        const int e = tid + i * 128, p = e >> 2, c = e & 3;                     // CO / 8 == 4 chunks per pixel
+        cp_async16(dst + (uint32_t)(c * kPlane + p * 16), src + (size_t)p * (CO * 2) + c * 16, 16u);
+      }
+    }
+  };
+  // fused BatchNorm backward: chunk e = tid + 128 i of the tile (pixel e >> 2, channel chunk e & 3 == tid & 3)
+  uint4 qg[4], qg2[4], qm[4], qy[4];
+  float cA[8], cB[8], cD[8];
+  const size_t tile_chunks = (size_t)128 * (CO / 8);
+  auto load_fwd = [&](int tile) {                    // what the forward wrote: may be fetched before the dependency wait
+    const uint4* pm = reinterpret_cast<const uint4*>(a.mask) + (size_t)tile * tile_chunks + tid;
+    const uint4* py = reinterpret_cast<const uint4*>(a.yraw) + (size_t)tile * tile_chunks + tid;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { qm[i] = pm[i * 128]; qy[i] = py[i * 128]; }
+  };
+  auto load_grad = [&](int tile) {
+    const uint4* p1 = reinterpret_cast<const uint4*>(a.g1) + (size_t)tile * tile_chunks + tid;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) qg[i] = p1[i * 128];
+    if (a.g2) {
+      const uint4* p2 = reinterpret_cast<const uint4*>(a.g2) + (size_t)tile * tile_chunks + tid;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) qg2[i] = p2[i * 128];
+    }
+  };
+  auto unpack8 = [](const uint4& u, float* v) {
+    v[0] = __uint_as_float(u.x << 16); v[1] = __uint_as_float(u.x & 0xffff0000u);
+    v[2] = __uint_as_float(u.y << 16); v[3] = __uint_as_float(u.y & 0xffff0000u);
+    v[4] = __uint_as_float(u.z << 16); v[5] = __uint_as_float(u.z & 0xffff0000u);
+    v[6] = __uint_as_float(u.w << 16); v[7] = __uint_as_float(u.w & 0xffff0000u);
+  };
+  auto transform = [&](int bslot) {                  // registers -> bf16 dY chunks in the B operand plane (tid & 3)
+    unsigned char* bp = stc_smem + (b_base - smem_u32(stc_smem)) + bslot * kBBuf + (tid & 3) * kPlane + (tid >> 2) * 16;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float g[8], v[8], o[8];
+      unpack8(qg[i], g);
+      if (a.g2) {
+        unpack8(qg2[i], v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) g[k] = __bfloat162float(__float2bfloat16_rn(g[k] + v[k]));
+      }
+      unpack8(qm[i], v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) g[k] = v[k] > 0.f ? g[k] : 0.f;
+      unpack8(qy[i], v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = fmaf(cA[k], g[k], fmaf(cB[k], v[k], cD[k]));
+      *reinterpret_cast<uint4*>(bp + i * 32 * 16) =
+          make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
     }
   };
 
   int it = 0;
   const int t0 = blockIdx.x, tstep = gridDim.x;
+  if constexpr (kFuse) {
+    if (t0 < a.ntiles) load_fwd(t0);                 // forward-written operands of the first tile: under the predecessor's tail
+  }
+  pdl_wait();
+  pdl_trigger();
+  if constexpr (kFuse) {
+    const int ch = (tid & 3) * 8;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float sc = a.bcoef[ch + k], c1 = a.bcoef[CO + ch + k], c2 = a.bcoef[2 * CO + ch + k];
+      const float mean = a.stat[ch + k], rstd = a.stat[CO + ch + k];
+      const float t = sc * c2 * rstd;
+      cA[k] = sc; cB[k] = -t; cD[k] = fmaf(t, mean, -sc * c1);
+    }
+    if (t0 < a.ntiles) load_grad(t0);
+  }
   if (t0 < a.ntiles) prefetch(t0, 0);
   cp_async_commit();
   if (t0 + tstep < a.ntiles) prefetch(t0 + tstep, 1);
@@ -333,9 +402,13 @@ __global__ void __launch_bounds__(128, 3) stem_wgrad_tc_kernel(const StemArgs a)
                        pack_bf16x2(lo[k8 * 8 + 4], lo[k8 * 8 + 5]), pack_bf16x2(lo[k8 * 8 + 6], lo[k8 * 8 + 7]));
       }
     }
+    if constexpr (kFuse) transform(slot);            // B[slot]: last read by the MMAs of tile it-3, complete (wait above)
     fence_proxy_async_smem();                        // operand writes (generic proxy, and cp.async) -> the tensor core
     tc_fence_before();
     __syncthreads();
+    if constexpr (kFuse) {                           // the next tile's raw vectors fly while this tile's MMAs run
+      if (tile + tstep < a.ntiles) { load_fwd(tile + tstep); load_grad(tile + tstep); }
+    }
     if (warp == 0) {
       tc_fence_after();
       if (elect_one()) {
@@ -403,13 +476,15 @@ void launch_stem_wgrad_tc(StemArgs a, cudaStream_t st) {
   const size_t smem = 2 * 16384 + 3 * 4 * 2048 + 128;        // two A buffers, three B slots
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(stem_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(stem_wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(stem_wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     attr_done = true;
   }
   static const int per_sm = getenv("MMVAE_STEM_WG_CTAS") ? atoi(getenv("MMVAE_STEM_WG_CTAS")) : 3;
   const int grid = a.ntiles < 148 * per_sm ? a.ntiles : 148 * per_sm;
   count_launch();
-  launch_pdl(stem_wgrad_tc_kernel, grid, 128, smem, st, a);
+  if (a.yraw) launch_pdl(stem_wgrad_tc_kernel<true>, grid, 128, smem, st, a);
+  else launch_pdl(stem_wgrad_tc_kernel<false>, grid, 128, smem, st, a);
 }
 
 void launch_stem_fwd_tc(StemArgs a, int Co, cudaStream_t st) {

@@ -62,7 +62,12 @@ def _cuda_step(n, seed=3):
     loss.backward()
     torch.cuda.synchronize()
     fwd = {k: workspace_tensor(m, n, k) for k in _act_names(cfg)}
-    grd = {k: workspace_tensor(m, n, k + ".grad") for k in _act_names(cfg)}
+    grd = {}
+    for k in _act_names(cfg):
+        try:
+            grd[k] = workspace_tensor(m, n, k + ".grad")
+        except M.MMVAEError:            # not materialised (the stem's dY lives only in the weight-gradient kernel's loader)
+            assert k == "encoder.conv1", k
     for k in grd:                       # a block input's gradient may be kept in two parts (main + shortcut branch)
         try:
             grd[k] = grd[k] + workspace_tensor(m, n, k + ".grad2")
@@ -87,6 +92,8 @@ def test_bf16_backward_layer_local(n):
         if not e <= 1e-2:
             bad.append(("param " + name, e))
     for name, (want, gate) in A.items():
+        if name not in grd:
+            continue
         got = grd[name].double()
         if gate is not None:                      # stored before or after the gate of that activation: compare gated
             got, want = got * gate, want * gate
