@@ -848,8 +848,9 @@ __device__ __forceinline__ uint4 bnc_pack8(const float (&v)[8]) {
 // two rows per trip with all eight loads issued first, the forward-written operands pulled into L2 before the dependency
 // wait, fixed-order shared-memory reduction, fp64 atomics across CTAs, and the CTA that finishes last writes the
 // coefficients (scale, c1, c2) and d gamma / d beta.  One branch only (no y2).
-__global__ void __launch_bounds__(256, 4) bn_bwd_reduce_bf16_kernel(const BnBwdArgs a) {
-  extern __shared__ float red[];                       // [2 sums][8 warps][C]
+template <bool kTwo>
+__global__ void __launch_bounds__(256, kTwo ? 3 : 4) bn_bwd_reduce_bf16_kernel(const BnBwdArgs a) {
+  extern __shared__ float red[];                       // [2 or 3 sums][8 warps][C]
   __shared__ int is_last;
   const int CV = a.C / 8, RPI = 256 / CV;
   const int tid = threadIdx.x;
@@ -858,22 +859,24 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_reduce_bf16_kernel(const BnBwdA
   const uint4* dA2 = reinterpret_cast<const uint4*>(a.dA2);
   const uint4* am = reinterpret_cast<const uint4*>(a.a);
   const uint4* y1 = reinterpret_cast<const uint4*>(a.y);
+  const uint4* y2 = reinterpret_cast<const uint4*>(a.y2);
   const long long rstride = (long long)gridDim.x * RPI;
   const long long r0 = (long long)blockIdx.x * RPI + rsub;
   for (long long r = r0; r < a.rows; r += rstride) {
     const size_t off = size_t(r) * CV + cv;
     if (am) asm volatile("prefetch.global.L2 [%0];" ::"l"(am + off));
     asm volatile("prefetch.global.L2 [%0];" ::"l"(y1 + off));
+    if (kTwo) asm volatile("prefetch.global.L2 [%0];" ::"l"(y2 + off));
   }
   pdl_wait();
   pdl_trigger();
-  float s0[8], s1[8];
+  float s0[8], s1[8], s2[kTwo ? 8 : 1];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) { s0[k] = 0.f; s1[k] = 0.f; }
+  for (int k = 0; k < 8; ++k) { s0[k] = 0.f; s1[k] = 0.f; if (kTwo) s2[k] = 0.f; }
   const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll 1
   for (long long r = r0; r < a.rows; r += 2 * rstride) {
-    uint4 qg[2], qg2[2], qa[2], qy[2];
+    uint4 qg[2], qg2[2], qa[2], qy[2], qz[kTwo ? 2 : 1];
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const long long ru = r + u * rstride;
@@ -883,6 +886,7 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_reduce_bf16_kernel(const BnBwdA
       qg2[u] = (dA2 && ok) ? dA2[off] : z4;
       qa[u] = (am && ok) ? am[off] : z4;
       qy[u] = ok ? y1[off] : z4;
+      if (kTwo) qz[u] = ok ? y2[off] : z4;
     }
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
@@ -901,6 +905,11 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_reduce_bf16_kernel(const BnBwdA
       bnc_unpack8(qy[u], v);
 #pragma unroll
       for (int k = 0; k < 8; ++k) { s0[k] += g[k]; s1[k] = fmaf(g[k], v[k], s1[k]); }
+      if (kTwo) {
+        bnc_unpack8(qz[u], v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s2[k] = fmaf(g[k], v[k], s2[k]);
+      }
     }
   }
   for (int d = CV; d < 32; d <<= 1) {
@@ -908,20 +917,25 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_reduce_bf16_kernel(const BnBwdA
     for (int k = 0; k < 8; ++k) {
       s0[k] += __shfl_xor_sync(0xffffffffu, s0[k], d);
       s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], d);
+      if (kTwo) s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], d);
     }
   }
   const int wrp = tid >> 5, c0 = cv * 8;
   if ((tid & 31) < CV) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { red[(0 * 8 + wrp) * a.C + c0 + k] = s0[k]; red[(1 * 8 + wrp) * a.C + c0 + k] = s1[k]; }
+    for (int k = 0; k < 8; ++k) {
+      red[(0 * 8 + wrp) * a.C + c0 + k] = s0[k]; red[(1 * 8 + wrp) * a.C + c0 + k] = s1[k];
+      if (kTwo) red[(2 * 8 + wrp) * a.C + c0 + k] = s2[k];
+    }
   }
   __syncthreads();
-  for (int e = tid; e < 2 * a.C; e += 256) {
+  for (int e = tid; e < (kTwo ? 3 : 2) * a.C; e += 256) {
     const int which = e / a.C, c = e - which * a.C;
     float sum = 0.f, t0 = 0.f;
 #pragma unroll
     for (int q = 0; q < 8; ++q) { sum += red[(which * 8 + q) * a.C + c]; t0 += red[q * a.C + c]; }
     if (which == 1) sum = a.stat[a.C + c] * (sum - a.stat[c] * t0);
+    if (which == 2) sum = a.stat2[a.C + c] * (sum - a.stat2[c] * t0);
     atomicAdd(a.acc + (size_t)(blockIdx.x % kBnAccCopies) * 3 * a.C + which * a.C + c, (double)sum);
   }
   __threadfence();
@@ -932,16 +946,23 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_reduce_bf16_kernel(const BnBwdA
   __threadfence();
   const double im = 1.0 / (double)a.rows;
   for (int c = tid; c < a.C; c += 256) {
-    double t0 = 0.0, t1 = 0.0;
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0;
 #pragma unroll
     for (int k = 0; k < kBnAccCopies; ++k) {
       const double* ak = a.acc + (size_t)k * 3 * a.C;
       t0 += ld_cg_f64(ak + c); t1 += ld_cg_f64(ak + a.C + c);
+      if (kTwo) t2 += ld_cg_f64(ak + 2 * a.C + c);
     }
     a.g_beta[c] = (float)t0; a.g_gamma[c] = (float)t1;
     a.bcoef[c] = a.gamma[c] * a.stat[a.C + c];
     a.bcoef[a.C + c] = (float)(t0 * im);
     a.bcoef[2 * a.C + c] = (float)(t1 * im);
+    if (kTwo) {
+      a.g_beta2[c] = (float)t0; a.g_gamma2[c] = (float)t2;
+      a.bcoef2[c] = a.gamma2[c] * a.stat2[a.C + c];
+      a.bcoef2[a.C + c] = (float)(t0 * im);
+      a.bcoef2[2 * a.C + c] = (float)(t2 * im);
+    }
   }
 }
 
@@ -1485,15 +1506,19 @@ void launch_bn_bwd(const BnBwdArgs& a_in, cudaStream_t st) {
       }
     }
   }
+  bool lean_done = false;
   if constexpr (std::is_same<T, __nv_bfloat16>::value) {
     const int CV = a.C / 8;
-    if (a.no_apply && a.acc && !a.reduced && !a.dA_f32 && !a.y2 && a.C % 8 == 0 && CV >= 1 && CV <= 32 && 256 % CV == 0) {
+    // lean reduction (+ the hoisted-coefficient apply below unless the consumer forms dY itself)
+    static const bool lean_off = getenv("MMVAE_NO_BN_LEAN_REDUCE") != nullptr;
+    if ((a.no_apply || !lean_off) && a.acc && !a.reduced && !a.dA_f32 && a.C % 8 == 0 && CV >= 1 && CV <= 32 && 256 % CV == 0) {
       const int RPI = 256 / CV;
       const long long row_groups = (a.rows + RPI - 1) / RPI;
-      const int grid = (int)std::min<long long>(148 * 4, row_groups);
       count_launch();
-      launch_pdl(bn_bwd_reduce_bf16_kernel, grid, 256, sizeof(float) * 2 * 8 * a.C, st, a);
-      return;
+      if (a.y2) launch_pdl(bn_bwd_reduce_bf16_kernel<true>, (int)std::min<long long>(148 * 3, row_groups), 256, sizeof(float) * 3 * 8 * a.C, st, a);
+      else launch_pdl(bn_bwd_reduce_bf16_kernel<false>, (int)std::min<long long>(148 * 4, row_groups), 256, sizeof(float) * 2 * 8 * a.C, st, a);
+      if (a.no_apply) return;
+      lean_done = true;
     }
   }
   const bool vec_ok = (a.C % V == 0) && (a.C / V <= 256);
@@ -1507,7 +1532,7 @@ void launch_bn_bwd(const BnBwdArgs& a_in, cudaStream_t st) {
   }
   if (nblocks > 592) nblocks = 592;
   if (nblocks < 1) nblocks = 1;
-  if (a.reduced) { /* masked and reduced by the producer of dA */ }
+  if (a.reduced || lean_done) { /* masked and reduced by the producer of dA / by the lean kernel above */ }
   else if (vec_ok) { count_launch(); launch_pdl(bn_bwd_reduce_kernel<T, V>, nblocks, 256, 0, st, a); }
   else { count_launch(); launch_pdl(bn_bwd_reduce_kernel<T, 1>, nblocks, 256, 0, st, a); }
   if (!a.acc && !a.reduced) {
