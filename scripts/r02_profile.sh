@@ -22,9 +22,9 @@ if [[ " $* " == *" full "* ]]; then
 W=0 S=1 timeout 200 python scripts/profile_step.py > $O/r02_plain_step.log 2>&1 || exit 1
 export W=0 S=1
 full ends 'tail_bwd|tail_fwd|stem_fwd|stem_wgrad|loss_gauss|bn_apply_out|mmd_kernel|bn_bwd_c1|philox|heads_' 0 16 python scripts/profile_step.py
-ncu -i /tmp/ends.ncu-rep --page source --csv -k regex:tail_bwd > $O/r02_src_tail_bwd.csv 2>/dev/null
+
 full bnapply 'bn_apply_kernel' 0 3 python scripts/profile_step.py
-full bnbwd 'bn_bwd_sweep|bn_bwd_apply' 0 7 python scripts/profile_step.py
+full bnbwd 'bn_bwd_sweep|bn_bwd_apply|bn_bwd_cluster|bn_bwd_reduce' 0 24 python scripts/profile_step.py
 timeout 200 python scripts/profile_conv.py > $O/r02_plain_conv.log 2>&1 && \
 full conv 'gconv_tc|slab_' 116 12 python scripts/profile_conv.py
 fi
