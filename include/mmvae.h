@@ -127,7 +127,9 @@ int mmvae_param_entry(const mmvae_desc* d, int32_t i, char* name, size_t name_ca
 int mmvae_bn_entry(const mmvae_desc* d, int32_t i, char* prefix, size_t prefix_cap,
                    int32_t* channels, int64_t* buffer_offset);
 /* Named tensor inside the workspace (debug / parity tests): "encoder.layer1.0.conv1" is the raw
- * conv output y (NHWC, storage type), "encoder.layer1.0" the block output.  dims = {N,H,W,C}. */
+ * conv output y (NHWC, storage type), "encoder.layer1.0" the block output; "<name>.grad" / "<name>.grad2" the gradient
+ * buffer(s) of that tensor after mmvae_backward.  dims = {N,H,W,C}.  MMVAE_ERR_BAD_ARG for a tensor the selected kernels
+ * never materialise (bf16 tensor-core path: "encoder.conv1.grad" -- the stem weight gradient forms that dY in its loader). */
 int mmvae_workspace_tensor(const mmvae_desc* d, const char* name, int64_t* byte_offset, int32_t dims[4]);
 
 /* ---- the hot path ---------------------------------------------------------------------------
