@@ -126,10 +126,17 @@ class GraphedTrainStep:
             prepare_input(self.labels, self.from_labels[0], self.from_labels[1], want_target=self._own_target,
                           out=self.x, out_target=self.target if self._own_target else None)
         mu, logvar, enc, recon = m(self.x)
-        loss, pxz, kl, mmd = m.loss(self.target, mu, logvar, enc, recon, self.x.device, self.args)
+        m._mmd_join_deferred = True                     # the MMD diagnostic's side branch joins at the end of the step
+        try:
+            loss, pxz, kl, mmd = m.loss(self.target, mu, logvar, enc, recon, self.x.device, self.args)
+        finally:
+            m._mmd_join_deferred = False
         loss.backward(self._one)
         if self.optimizer is not None:
             self.optimizer.step(m.last_flat_grad)       # optimizer.step(), main.py:399
+        if m._mmd_pending:
+            m._mmd_join()
+            m._mmd_pending = False
         self.mu, self.logvar, self.encoding, self.reconstruction = mu, logvar, enc, recon
         self.loss, self.pxz, self.kl, self.mmd = loss.detach(), pxz, kl, mmd
 

@@ -184,6 +184,8 @@ class VAE(nn.Module):
         self._side = None             # torch side stream of the MMD diagnostic
         self._kl_dev = None           # device scalar holding the KL weight while a GraphedTrainStep owns it (annealing)
         self.mmd_diagnostic = True    # compute the 4th return value of loss() like the reference (model.py:394-396)
+        self._mmd_join_deferred = False   # set by GraphedTrainStep around its step body
+        self._mmd_pending = False
         self.last_true_samples = None
         self._mmd_calls = 0
         self._grad_sync = None        # set by mmvae_b200.parallel.DataParallel
@@ -568,7 +570,10 @@ class VAE(nn.Module):
             mmd = self._mmd_fork(encoding, true_samples)
         loss, out = _LossFn.apply(recon, tgt, mu, lv, a, cew, self._scratch(recon.device))
         if mmd is not None:
-            self._mmd_join()
+            if self._mmd_join_deferred:             # GraphedTrainStep joins the side branch at the END of the step: the
+                self._mmd_pending = True            # diagnostic then runs beside the backward instead of in front of it
+            else:
+                self._mmd_join()
         if self.defer_metrics:
             return loss, out[1], out[2], (mmd if mmd is not None else torch.zeros((), device=recon.device))
         vals = out.tolist()
