@@ -6,7 +6,7 @@ are read once per process, so each setting runs in its own interpreter and the g
                                   apply kernel, the stem's dY stored and read back by the plain weight-gradient kernel
 
 Both sides store gradients in bf16 between layers, so they differ by independent roundings (a sum taken in another order moves
-a bf16 dY by one ulp here and there), not by more: the flat gradient within 5e-3 (measured 2.3e-3), every tensor within 3e-2 (measured 1.4e-2; (BatchNorm affine
+a bf16 dY by one ulp here and there), not by more: the flat gradient within 5e-3 (measured 2.3e-3), every tensor within 3e-2 (measured 1.4e-2:
 BatchNorm affine gradients are sums with heavy cancellation), the loss bit-identical (same forward)."""
 import os
 import subprocess
