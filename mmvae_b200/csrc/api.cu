@@ -377,6 +377,7 @@ struct Exec {
     if (P.d.arch == MMVAE_ARCH_NOTEBOOK) nb_pad_grid(c, g);
     WGradParams w;
     memset(&w, 0, sizeof(w));
+    if (P.d.arch == MMVAE_ARCH_NOTEBOOK) w.cta_budget = 120;      // no BatchNorm chain beside it to leave SMs for
     if (c.in < 0) { w.in = x; w.in_nchw_f32 = 1; }
     else w.in = at<T>(act(c.in).off);
     w.dout = at<T>(act(c.out).goff);

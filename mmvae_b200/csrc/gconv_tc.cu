@@ -913,10 +913,16 @@ bool pixel_box(int rows, int Hg, int Wg, int& bw, int& bh, int& bn) {
 
 // CTA budget of a weight-gradient launch (MMVAE_WGRAD_CTAS env, tuning).  Weight gradients run on the auxiliary stream
 // beside the critical path: leaving ~1/5 of the SMs free for the main stream's kernels beats one CTA per SM
-// (base step 1.2435 ms at 148, 1.232 +- 0.003 ms at 88 .. 132; the widened and notebook steps do not care).
+// (r01: base step 1.2435 ms at 148, 1.232 +- 0.003 ms at 88 .. 132; the widened and notebook steps do not care.  r02 final,
+// with the shorter BatchNorm-backward links: 1.1072 ms at 140, 1.0980 at 120, 1.0915-1.0922 at 64 / 80 / 100: 96).
 int wgrad_ctas() {
-  static int m = [] { const char* e = getenv("MMVAE_WGRAD_CTAS"); return e ? atoi(e) : 120; }();
+  static int m = [] { const char* e = getenv("MMVAE_WGRAD_CTAS"); return e ? atoi(e) : 96; }();
   return m;
+}
+// the notebook variant asks for 120 (WGradParams::cta_budget: 5.67 ms / step against 5.74 at 96) unless the switch is set
+bool wgrad_ctas_forced() {
+  static bool f = getenv("MMVAE_WGRAD_CTAS") != nullptr;
+  return f;
 }
 int gconv_per_sm() {
   static int m = [] { const char* e = getenv("MMVAE_GCONV_PER_SM"); return e ? atoi(e) : 3; }();
@@ -1083,7 +1089,7 @@ void launch_wgrad_tc(const WGradParams& p0, cudaStream_t st) {
   const int bn = co_pad >= 64 ? 64 : (co_pad >= 32 ? 32 : 16);
   const int gx = (maxK + 127) / 128, gy = (co_pad + bn - 1) / bn;
   const int base = gx * gy * p.nvar;
-  int nsplit = max(1, wgrad_ctas() / base);
+  int nsplit = max(1, (p.cta_budget > 0 && !wgrad_ctas_forced() ? p.cta_budget : wgrad_ctas()) / base);
   nsplit = min(nsplit, max(1, (p.M + 255) / 256));      // at least 256 pixels per split
   int rps = (p.M + nsplit - 1) / nsplit;
   rps = (rps + 63) / 64 * 64;

@@ -187,6 +187,7 @@ struct WGradParams {
   int conv_class;              // 1: ConvTranspose2d k4 s2 p1 (slab_tc.cu candidate), else 0
   int tc_bn, tc_stages;        // set by the launcher (tcgen05 path)
   int tc_kb, tma_a, tma_b;
+  int cta_budget;              // CTAs of this weight-gradient launch (0: the library default, wgrad_ctas())
   FastDiv fd_wg, fd_hg, fd_ci, fd_hw;
   GVar var[kMaxVar];
   TmaDesc tmap_a, tmap_b;      // layer input (box = tc_kb channels x 64 pixels) / dY (box = tc_bn channels x 64 pixels)
